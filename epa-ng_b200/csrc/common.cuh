@@ -1,0 +1,127 @@
+// common.cuh - shared device-side definitions of libepa_b200 (sm_100a only).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <math.h>
+
+namespace epa {
+
+constexpr int MAX_STATES = 20;
+constexpr int MAX_RATES = 8;
+constexpr int MAX_CODES = 32;                 // query character codes (DNA: 16 masks, AA: 25 codes)
+
+// 2^256 / 2^-256: libpll's scaling factor / threshold (libpll pll.h:96-97)
+#define EPA_SCALE_FACTOR 0x1p256
+#define EPA_SCALE_THRESHOLD 0x1p-256
+// log(2^-256)
+#define EPA_LOG_SCALE_THRESHOLD (-177.445678223345993274)
+
+// Model tables. One copy lives in global memory per context; kernels read the few entries they
+// need through the read-only path (uniform addresses broadcast) or stage them in shared memory.
+struct DevModel {
+  int S, R, n, K;                                 // states, rate cats, sites, lookup columns (internal)
+  int ncodes;                                     // number of query character codes
+  int per_rate, bugcompat;
+  int pad0;
+  double eigenvals[MAX_STATES];
+  double eigenvecs[MAX_STATES * MAX_STATES];      // V    [j*S+k]
+  double inv_eigenvecs[MAX_STATES * MAX_STATES];  // Vinv [k*S+j]
+  double pivinv[MAX_STATES * MAX_STATES];         // freqs[k] * Vinv[k*S+j]  (sumtable, left side)
+  double freqs[MAX_STATES];
+  double rates[MAX_RATES];
+  double weights[MAX_RATES];
+  uint32_t code2mask[MAX_CODES];                  // query code -> state mask (thorough path)
+  uint32_t colmask[MAX_CODES];                    // lookup column -> state mask (0 = zero column)
+  uint8_t code2col[MAX_CODES];                    // query code -> lookup column (preplacement)
+  uint8_t ascii2code[256];                        // 255 = invalid character
+};
+
+// Node id -> storage: ids 0..n_tips-1 are tips (their 0/1 CLVs are materialised once), ids
+// >= n_tips are the directional CLV slots of the inner nodes.
+struct DevTree {
+  double * clv;                                   // [n_nodes][n][R][S]
+  uint32_t * scaler;                              // [n_nodes][n]
+  size_t clv_stride;                              // n*R*S
+  uint32_t n_tips;
+  uint32_t n_nodes;
+};
+
+struct ClvOpDev {
+  uint32_t parent, left, right;
+  uint32_t tip_tip;                               // both children are tips: never rescale
+  uint32_t lmat, rmat;                            // indices into the pmatrix array of the launch
+};
+
+struct EdgeDev {
+  uint32_t distal, proximal;                      // node ids (a tip is always distal)
+  double length;
+};
+
+__device__ __forceinline__ double warp_sum(double v)
+{
+  // fixed-order butterfly: every lane ends with the same bits
+  #pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+__device__ __forceinline__ double warp_max(double v)
+{
+  #pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+template <int S>
+__device__ __forceinline__ void load_vec(const double * __restrict__ p, double (&v)[S])
+{
+  static_assert(S % 2 == 0, "even state count expected");
+  const double2 * p2 = reinterpret_cast<const double2 *>(p);
+  #pragma unroll
+  for (int i = 0; i < S / 2; ++i) { double2 t = __ldg(p2 + i); v[2 * i] = t.x; v[2 * i + 1] = t.y; }
+}
+
+template <int S>
+__device__ __forceinline__ void store_vec(double * __restrict__ p, const double (&v)[S])
+{
+  double2 * p2 = reinterpret_cast<double2 *>(p);
+  #pragma unroll
+  for (int i = 0; i < S / 2; ++i) p2[i] = make_double2(v[2 * i], v[2 * i + 1]);
+}
+
+// ---- mbarrier / bulk-copy (TMA 1D) helpers, sm_90+ PTX -------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void * p)
+{
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint64_t * bar, uint32_t count)
+{
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init()
+{
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t * bar, uint32_t bytes)
+{
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;"
+               :: "r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void * dst, const void * src, uint32_t bytes, uint64_t * bar)
+{
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               :: "r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t * bar, uint32_t parity)
+{
+  uint32_t done;
+  do {
+    asm volatile("{\n\t.reg .pred p;\n\t"
+                 "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+                 "selp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+  } while (!done);
+}
+
+}  // namespace epa

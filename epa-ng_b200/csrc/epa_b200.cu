@@ -1,0 +1,1004 @@
+// epa_b200.cu - context management and the C ABI of libepa_b200.so (see include/epa_b200.h).
+// Everything that computes runs in the hand-written sm_100a kernels of kernels_*.cuh; there is
+// no CPU fallback: without a CUDA device every entry point fails with EPA_ERR_CUDA.
+#include "../../include/epa_b200.h"
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+#include "kernels_clv.cuh"
+#include "kernels_preplace.cuh"
+#include "kernels_blo.cuh"
+#include "kernels_blo_generic.cuh"
+#include "kernels_collect.cuh"
+
+using namespace epa;
+
+static_assert(sizeof(epa_placement) == sizeof(PlacementRec), "record layout");
+static_assert(sizeof(epa_placement) == 40, "Placement is 40 bytes");
+
+namespace {
+
+thread_local std::string g_create_error;
+
+struct DevBuf {
+  void * p = nullptr;
+  size_t cap = 0;
+  cudaError_t ensure(size_t bytes)
+  {
+    if (bytes <= cap) return cudaSuccess;
+    if (p) { cudaFree(p); p = nullptr; cap = 0; }
+    // grow with some slack so that slightly larger chunks do not reallocate
+    const size_t want = bytes + bytes / 8 + 256;
+    cudaError_t e = cudaMalloc(&p, want);
+    if (e != cudaSuccess) { (void) cudaGetLastError(); e = cudaMalloc(&p, bytes); }
+    if (e == cudaSuccess) cap = (want > bytes && p) ? want : bytes;
+    return e;
+  }
+  void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+  template <typename T> T * as() const { return static_cast<T *>(p); }
+};
+
+enum Stage { ST_NONE = 0, ST_QUERIES = 1, ST_PREPLACED = 2, ST_SELECTED = 3, ST_PLACED = 4 };
+
+}  // namespace
+
+struct epa_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  int sm_count = 0;
+  size_t smem_optin = 0;
+
+  DevModel hm;
+  DevModel * d_model = nullptr;
+  int S = 0, R = 0, n = 0, n_pad = 0, K = 0;
+  uint32_t n_tips = 0, n_slots = 0, n_nodes = 0, n_edges = 0;
+  DevTree tree{};
+  std::vector<EdgeDev> h_edges;
+  EdgeDev * d_edges = nullptr;
+  double * d_lookup = nullptr;
+  bool clvs_ready = false, lookup_ready = false;
+  std::vector<uint8_t> slot_filled;
+
+  // chunk state
+  int stage = ST_NONE;
+  uint32_t nq = 0;
+  int max_span = 0;
+  bool implicit_pairs = false;
+  uint64_t n_pairs = 0;
+  size_t pre_stride = 0;
+  DevBuf raw, codes, begin, span, perm, hist, range, pre, cnt, cutv, cuti, off, pair_q, pair_e,
+         edge_hist, edge_off, work, res, out_rec, out_cnt, scratch, tmp;
+  int * d_flags = nullptr;              // [0..1] error, [2] max tile width, [3] max span
+  unsigned long long * d_counter = nullptr;
+  uint64_t * d_total = nullptr;
+
+  cudaEvent_t ev[6] = {};
+  float ms[5] = {0, 0, 0, 0, 0};
+  uint64_t launches = 0;
+  std::string err;
+};
+
+namespace {
+
+std::mutex g_const_mutex;
+epa_ctx * g_const_owner[64] = {};
+
+int fail(epa_ctx * ctx, int code, const char * fmt, ...)
+{
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  if (ctx) ctx->err = buf; else g_create_error = buf;
+  return code;
+}
+
+#define CU(call)                                                                                   \
+  do {                                                                                             \
+    cudaError_t e_ = (call);                                                                       \
+    if (e_ != cudaSuccess)                                                                         \
+    {                                                                                              \
+      (void) cudaGetLastError();                                                                   \
+      return fail(ctx, e_ == cudaErrorMemoryAllocation ? EPA_ERR_NOMEM : EPA_ERR_CUDA,             \
+                  "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__);     \
+    }                                                                                              \
+  } while (0)
+
+#define LAUNCHED(ctx) do { (ctx)->launches++; CU(cudaGetLastError()); } while (0)
+
+// dispatch over the compiled (states, rate categories) combinations
+#define EPA_DISPATCH_SR(ctx, BODY)                                                                 \
+  do {                                                                                             \
+    const int S__ = (ctx)->S, R__ = (ctx)->R;                                                      \
+    if (S__ == 4 && R__ == 1) { constexpr int S_ = 4, R_ = 1; BODY; }                              \
+    else if (S__ == 4 && R__ == 2) { constexpr int S_ = 4, R_ = 2; BODY; }                         \
+    else if (S__ == 4 && R__ == 4) { constexpr int S_ = 4, R_ = 4; BODY; }                         \
+    else if (S__ == 4 && R__ == 8) { constexpr int S_ = 4, R_ = 8; BODY; }                         \
+    else if (S__ == 20 && R__ == 1) { constexpr int S_ = 20, R_ = 1; BODY; }                       \
+    else if (S__ == 20 && R__ == 4) { constexpr int S_ = 20, R_ = 4; BODY; }                       \
+    else return fail(ctx, EPA_ERR_ARG, "unsupported states/rate_cats combination %d/%d", S__, R__);\
+  } while (0)
+
+bool supported_sr(int S, int R)
+{
+  return (S == 4 && (R == 1 || R == 2 || R == 4 || R == 8)) || (S == 20 && (R == 1 || R == 4));
+}
+
+int bind_constants(epa_ctx * ctx)
+{
+  std::lock_guard<std::mutex> lock(g_const_mutex);
+  if (g_const_owner[ctx->device] == ctx) return EPA_OK;
+  CU(cudaDeviceSynchronize());
+  CU(cudaMemcpyToSymbol(c_model, &ctx->hm, sizeof(DevModel)));
+  g_const_owner[ctx->device] = ctx;
+  return EPA_OK;
+}
+
+int set_device(epa_ctx * ctx)
+{
+  CU(cudaSetDevice(ctx->device));
+  return EPA_OK;
+}
+
+// ---- character tables ------------------------------------------------------------------------
+// DNA: code = libpll state mask (A=1,C=2,G=4,T=8; libpll maps.c:46-64), lookup column = mask,
+//      column 0 is the zero column.
+// AA:  codes 0..19 = ARNDCQEGHILKMFPSTWYV singles, 20 = B, 21 = Z, 22 = J, 23 = fully ambiguous
+//      ('-', '?', '*', '.'), 24 = X. Lookup columns 0..23 follow the codes, column 24 is the zero
+//      column; X scores on the column of N in preplacement (reference quirk,
+//      src/core/Lookup_Store.hpp:63-66) but is fully ambiguous in the thorough phase.
+void build_char_tables(DevModel & m)
+{
+  memset(m.ascii2code, 255, sizeof m.ascii2code);
+  memset(m.code2mask, 0, sizeof m.code2mask);
+  memset(m.colmask, 0, sizeof m.colmask);
+  memset(m.code2col, 0, sizeof m.code2col);
+  auto both = [&](char c, uint8_t code) {
+    m.ascii2code[(unsigned char) c] = code;
+    if (c >= 'A' && c <= 'Z') m.ascii2code[(unsigned char) (c - 'A' + 'a')] = code;
+  };
+  if (m.S == 4)
+  {
+    m.K = 16; m.ncodes = 16;
+    const char * chars = "ABCDGHKMNORSTUVWXY-.?";
+    const int masks[] = {1, 14, 2, 13, 4, 11, 12, 3, 15, 15, 5, 6, 8, 8, 7, 9, 15, 10, 15, 15, 15};
+    for (int i = 0; chars[i]; ++i) both(chars[i], (uint8_t) masks[i]);
+    for (int c = 0; c < 16; ++c) { m.code2mask[c] = c; m.code2col[c] = (uint8_t) c; m.colmask[c] = c; }
+  }
+  else
+  {
+    m.K = 26; m.ncodes = 25;
+    const char * order = "ARNDCQEGHILKMFPSTWYV";
+    for (int i = 0; i < 20; ++i) { both(order[i], (uint8_t) i); m.code2mask[i] = 1u << i; }
+    auto bit = [&](char c) { return 1u << (uint32_t) (strchr(order, c) - order); };
+    both('B', 20); m.code2mask[20] = bit('N') | bit('D');
+    both('Z', 21); m.code2mask[21] = bit('Q') | bit('E');
+    both('J', 22); m.code2mask[22] = bit('I') | bit('L');
+    for (const char * p = "-?*."; *p; ++p) both(*p, 23);
+    m.code2mask[23] = 0xfffffu;
+    both('X', 24); m.code2mask[24] = 0xfffffu;
+    for (int c = 0; c < 24; ++c) { m.code2col[c] = (uint8_t) c; m.colmask[c] = m.code2mask[c]; }
+    m.code2col[24] = (uint8_t) (strchr(order, 'N') - order);
+    m.colmask[24] = 0; m.colmask[25] = 0;       // zero column + padding
+  }
+}
+
+}  // namespace
+
+// ==============================================================================================
+//  context
+// ==============================================================================================
+extern "C" void epa_options_default(epa_options * o)
+{
+  if (!o) return;
+  o->prescoring = 1;
+  o->heuristic = 0;
+  o->prescoring_threshold = 0.99999;
+  o->premasking = 1;
+  o->sliding_blo = 1;
+  o->filter_acc_lwr = 0;
+  o->support_threshold = 0.01;
+  o->filter_min = 1;
+  o->filter_max = 7;
+}
+
+extern "C" const char * epa_last_error(const epa_ctx * ctx)
+{
+  return ctx ? ctx->err.c_str() : g_create_error.c_str();
+}
+
+extern "C" uint64_t epa_launch_count(const epa_ctx * ctx) { return ctx ? ctx->launches : 0; }
+
+extern "C" void epa_ctx_destroy(epa_ctx * ctx)
+{
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+  {
+    std::lock_guard<std::mutex> lock(g_const_mutex);
+    if (g_const_owner[ctx->device] == ctx) g_const_owner[ctx->device] = nullptr;
+  }
+  DevBuf * bufs[] = {&ctx->raw, &ctx->codes, &ctx->begin, &ctx->span, &ctx->perm, &ctx->hist, &ctx->range,
+                     &ctx->pre, &ctx->cnt, &ctx->cutv, &ctx->cuti, &ctx->off, &ctx->pair_q, &ctx->pair_e,
+                     &ctx->edge_hist, &ctx->edge_off, &ctx->work, &ctx->res, &ctx->out_rec, &ctx->out_cnt,
+                     &ctx->scratch, &ctx->tmp};
+  for (DevBuf * b : bufs) b->release();
+  cudaFree(ctx->d_model); cudaFree(ctx->tree.clv); cudaFree(ctx->tree.scaler); cudaFree(ctx->d_edges);
+  cudaFree(ctx->d_lookup); cudaFree(ctx->d_flags); cudaFree(ctx->d_counter); cudaFree(ctx->d_total);
+  for (auto & e : ctx->ev) if (e) cudaEventDestroy(e);
+  if (ctx->stream) cudaStreamDestroy(ctx->stream);
+  delete ctx;
+}
+
+extern "C" int epa_ctx_create(epa_ctx ** out, int device, const epa_model_desc * model,
+                              uint32_t n_tips, const uint32_t * tip_masks, uint32_t n_clv_slots,
+                              const epa_edge_desc * edges, uint32_t n_edges)
+{
+  epa_ctx * ctx = nullptr;      // errors before the context exists go to the thread-local message
+  if (!out || !model || !tip_masks || !edges) return fail(ctx, EPA_ERR_ARG, "null argument");
+  *out = nullptr;
+  if (!supported_sr((int) model->states, (int) model->rate_cats))
+    return fail(ctx, EPA_ERR_ARG, "unsupported states/rate_cats combination %u/%u", model->states, model->rate_cats);
+  if (model->flags & EPA_FLAG_RATE_SCALERS)
+    return fail(ctx, EPA_ERR_ARG, "per-rate scalers are not supported (use per-site scaling)");
+  if (model->pinv != 0.0) return fail(ctx, EPA_ERR_ARG, "+I models are not supported");
+  if (model->sites == 0 || n_tips < 3 || n_edges == 0) return fail(ctx, EPA_ERR_ARG, "empty tree or alignment");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+  {
+    (void) cudaGetLastError();
+    return fail(ctx, EPA_ERR_CUDA, "no CUDA device available: libepa_b200 has no CPU path");
+  }
+  if (device < 0 || device >= ndev || device >= 64) return fail(ctx, EPA_ERR_ARG, "invalid device %d", device);
+  for (uint32_t i = 0; i < n_edges; ++i)
+  {
+    const uint32_t lim = n_tips + n_clv_slots;
+    if (edges[i].distal >= lim || edges[i].proximal >= lim)
+      return fail(ctx, EPA_ERR_ARG, "edge %u references node out of range", i);
+    if (edges[i].proximal < n_tips && edges[i].distal >= n_tips)
+      return fail(ctx, EPA_ERR_ARG, "edge %u: a tip must be the distal side", i);
+  }
+
+  ctx = new epa_ctx();
+  ctx->device = device;
+  auto bail = [&](int code) { std::string msg = ctx->err; epa_ctx_destroy(ctx); g_create_error = msg; return code; };
+#define CUC(call)                                                                                  \
+  do {                                                                                             \
+    cudaError_t e_ = (call);                                                                       \
+    if (e_ != cudaSuccess)                                                                         \
+    {                                                                                              \
+      (void) cudaGetLastError();                                                                   \
+      fail(ctx, EPA_ERR_CUDA, "%s failed: %s", #call, cudaGetErrorString(e_));                     \
+      return bail(e_ == cudaErrorMemoryAllocation ? EPA_ERR_NOMEM : EPA_ERR_CUDA);                 \
+    }                                                                                              \
+  } while (0)
+
+  CUC(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CUC(cudaGetDeviceProperties(&prop, device));
+  if (prop.major < 10)
+  {
+    fail(ctx, EPA_ERR_CUDA, "device %d is sm_%d%d; libepa_b200 is built for sm_100a only", device, prop.major, prop.minor);
+    return bail(EPA_ERR_CUDA);
+  }
+  ctx->sm_count = prop.multiProcessorCount;
+  ctx->smem_optin = prop.sharedMemPerBlockOptin;
+  CUC(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+  for (auto & e : ctx->ev) CUC(cudaEventCreate(&e));
+
+  DevModel & m = ctx->hm;
+  memset(&m, 0, sizeof m);
+  const int S = (int) model->states, R = (int) model->rate_cats;
+  m.S = S; m.R = R; m.n = (int) model->sites;
+  m.per_rate = 0;
+  m.bugcompat = (model->flags & EPA_FLAG_BUGCOMPAT_FOCUS) ? 1 : 0;
+  for (int i = 0; i < S; ++i) { m.eigenvals[i] = model->eigenvals[i]; m.freqs[i] = model->freqs[i]; }
+  for (int i = 0; i < S * S; ++i)
+  {
+    m.eigenvecs[i] = model->eigenvecs[i];
+    m.inv_eigenvecs[i] = model->inv_eigenvecs[i];
+    m.pivinv[i] = model->freqs[i / S] * model->inv_eigenvecs[i];
+  }
+  for (int r = 0; r < R; ++r) { m.rates[r] = model->rates[r]; m.weights[r] = model->rate_weights[r]; }
+  build_char_tables(m);
+  ctx->S = S; ctx->R = R; ctx->n = m.n; ctx->n_pad = (m.n + 3) & ~3; ctx->K = m.K;
+  ctx->n_tips = n_tips; ctx->n_slots = n_clv_slots; ctx->n_nodes = n_tips + n_clv_slots; ctx->n_edges = n_edges;
+  ctx->slot_filled.assign(ctx->n_nodes, 0);
+  for (uint32_t i = 0; i < n_tips; ++i) ctx->slot_filled[i] = 1;
+
+  const uint32_t all = S == 4 ? 0xfu : 0xfffffu;
+  const size_t tip_sites = (size_t) n_tips * m.n;
+  for (size_t i = 0; i < tip_sites; ++i)
+    if (tip_masks[i] == 0 || (tip_masks[i] & ~all))
+    {
+      fail(ctx, EPA_ERR_ARG, "invalid tip state mask at tip %zu site %zu", i / m.n, i % m.n);
+      return bail(EPA_ERR_ARG);
+    }
+
+  CUC(cudaMalloc(&ctx->d_model, sizeof(DevModel)));
+  CUC(cudaMemcpy(ctx->d_model, &m, sizeof(DevModel), cudaMemcpyHostToDevice));
+  ctx->tree.clv_stride = (size_t) m.n * R * S;
+  ctx->tree.n_tips = n_tips; ctx->tree.n_nodes = ctx->n_nodes;
+  CUC(cudaMalloc(&ctx->tree.clv, ctx->tree.clv_stride * ctx->n_nodes * sizeof(double)));
+  CUC(cudaMalloc(&ctx->tree.scaler, (size_t) m.n * ctx->n_nodes * sizeof(uint32_t)));
+  CUC(cudaMemset(ctx->tree.scaler, 0, (size_t) m.n * ctx->n_nodes * sizeof(uint32_t)));
+  ctx->h_edges.resize(n_edges);
+  for (uint32_t i = 0; i < n_edges; ++i) ctx->h_edges[i] = EdgeDev{edges[i].distal, edges[i].proximal, edges[i].length};
+  CUC(cudaMalloc(&ctx->d_edges, n_edges * sizeof(EdgeDev)));
+  CUC(cudaMemcpy(ctx->d_edges, ctx->h_edges.data(), n_edges * sizeof(EdgeDev), cudaMemcpyHostToDevice));
+  CUC(cudaMalloc(&ctx->d_flags, 8 * sizeof(int)));
+  CUC(cudaMemset(ctx->d_flags, 0, 8 * sizeof(int)));
+  CUC(cudaMalloc(&ctx->d_counter, sizeof(unsigned long long)));
+  CUC(cudaMalloc(&ctx->d_total, 2 * sizeof(uint64_t)));
+
+  // tips -> 0/1 CLVs
+  {
+    uint32_t * d_masks = nullptr;
+    CUC(cudaMalloc(&d_masks, tip_sites * sizeof(uint32_t)));
+    CUC(cudaMemcpy(d_masks, tip_masks, tip_sites * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    const unsigned blocks = (unsigned) ((tip_sites + 255) / 256);
+    if (S == 4) tip_expand_kernel<4><<<blocks, 256, 0, ctx->stream>>>(ctx->d_model, ctx->tree, d_masks, tip_sites);
+    else tip_expand_kernel<20><<<blocks, 256, 0, ctx->stream>>>(ctx->d_model, ctx->tree, d_masks, tip_sites);
+    ctx->launches++;
+    CUC(cudaGetLastError());
+    CUC(cudaStreamSynchronize(ctx->stream));
+    cudaFree(d_masks);
+  }
+  {
+    std::lock_guard<std::mutex> lock(g_const_mutex);
+    cudaDeviceSynchronize();
+    CUC(cudaMemcpyToSymbol(c_model, &ctx->hm, sizeof(DevModel)));
+    g_const_owner[device] = ctx;
+  }
+#undef CUC
+  *out = ctx;
+  return EPA_OK;
+}
+
+// ==============================================================================================
+//  reference CLVs
+// ==============================================================================================
+static int launch_pmatrices(epa_ctx * ctx, const double * d_lengths, double * d_out, uint32_t count)
+{
+  if (ctx->S == 4) pmatrix_kernel<4><<<count, 128, 0, ctx->stream>>>(ctx->d_model, d_lengths, d_out);
+  else pmatrix_kernel<20><<<count, 128, 0, ctx->stream>>>(ctx->d_model, d_lengths, d_out);
+  LAUNCHED(ctx);
+  return EPA_OK;
+}
+
+extern "C" int epa_compute_clvs(epa_ctx * ctx, const epa_clv_op * ops, uint32_t n_ops)
+{
+  if (!ctx) return EPA_ERR_ARG;
+  if (!ops && n_ops) return fail(ctx, EPA_ERR_ARG, "null ops");
+  if (int rc = set_device(ctx)) return rc;
+  const uint32_t N = ctx->n_nodes, T = ctx->n_tips;
+  // dependency depth of every op
+  std::vector<int> producer(N, -1);
+  for (uint32_t i = 0; i < n_ops; ++i)
+  {
+    const epa_clv_op & o = ops[i];
+    if (o.parent < T || o.parent >= N || o.left >= N || o.right >= N)
+      return fail(ctx, EPA_ERR_ARG, "op %u references node out of range", i);
+    if (producer[o.parent] != -1) return fail(ctx, EPA_ERR_ARG, "CLV slot %u computed twice", o.parent - T);
+    producer[o.parent] = (int) i;
+  }
+  std::vector<int> level(N, -1);
+  for (uint32_t i = 0; i < N; ++i)
+    if (ctx->slot_filled[i] && producer[i] == -1) level[i] = 0;
+  // iterative DFS
+  std::vector<uint32_t> stack;
+  for (uint32_t i = 0; i < n_ops; ++i)
+  {
+    stack.push_back(ops[i].parent);
+    while (!stack.empty())
+    {
+      const uint32_t node = stack.back();
+      if (level[node] >= 0) { stack.pop_back(); continue; }
+      if (producer[node] < 0) return fail(ctx, EPA_ERR_STATE, "CLV slot %u is needed but never computed or uploaded", node - T);
+      const epa_clv_op & o = ops[producer[node]];
+      if (level[node] == -2 && (level[o.left] < 0 || level[o.right] < 0))
+        return fail(ctx, EPA_ERR_ARG, "cyclic CLV dependencies at slot %u", node - T);
+      if (level[o.left] >= 0 && level[o.right] >= 0)
+      {
+        level[node] = 1 + std::max(level[o.left], level[o.right]);
+        stack.pop_back();
+      }
+      else
+      {
+        level[node] = -2;      // visiting
+        if (level[o.left] == -2 || level[o.right] == -2)
+          return fail(ctx, EPA_ERR_ARG, "cyclic CLV dependencies at slot %u", node - T);
+        if (level[o.left] < 0) stack.push_back(o.left);
+        if (level[o.right] < 0) stack.push_back(o.right);
+      }
+    }
+  }
+  int max_level = 0;
+  for (uint32_t i = 0; i < n_ops; ++i) max_level = std::max(max_level, level[ops[i].parent]);
+  std::vector<std::vector<uint32_t>> by_level(max_level + 1);
+  for (uint32_t i = 0; i < n_ops; ++i) by_level[level[ops[i].parent]].push_back(i);
+
+  std::vector<ClvOpDev> hops;
+  std::vector<double> lengths;
+  hops.reserve(n_ops); lengths.reserve(2 * (size_t) n_ops);
+  std::vector<std::pair<uint32_t, uint32_t>> ranges;
+  for (int l = 1; l <= max_level; ++l)
+  {
+    const uint32_t start = (uint32_t) hops.size();
+    for (uint32_t i : by_level[l])
+    {
+      const epa_clv_op & o = ops[i];
+      ClvOpDev d;
+      d.parent = o.parent; d.left = o.left; d.right = o.right;
+      d.tip_tip = (o.left < T && o.right < T) ? 1u : 0u;
+      d.lmat = (uint32_t) lengths.size(); lengths.push_back(o.left_length);
+      d.rmat = (uint32_t) lengths.size(); lengths.push_back(o.right_length);
+      hops.push_back(d);
+    }
+    ranges.emplace_back(start, (uint32_t) hops.size() - start);
+  }
+  if (hops.empty()) { ctx->clvs_ready = true; return EPA_OK; }
+
+  const size_t pm = (size_t) ctx->R * ctx->S * ctx->S;
+  ClvOpDev * d_ops = nullptr; double * d_len = nullptr; double * d_pm = nullptr;
+  CU(cudaMalloc(&d_ops, hops.size() * sizeof(ClvOpDev)));
+  CU(cudaMalloc(&d_len, lengths.size() * sizeof(double)));
+  CU(cudaMalloc(&d_pm, lengths.size() * pm * sizeof(double)));
+  CU(cudaMemcpyAsync(d_ops, hops.data(), hops.size() * sizeof(ClvOpDev), cudaMemcpyHostToDevice, ctx->stream));
+  CU(cudaMemcpyAsync(d_len, lengths.data(), lengths.size() * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  if (int rc = launch_pmatrices(ctx, d_len, d_pm, (uint32_t) lengths.size())) return rc;
+  const size_t smem = 2 * pm * sizeof(double);
+  for (auto & rg : ranges)
+  {
+    if (!rg.second) continue;
+    dim3 grid(rg.second, (ctx->n + 127) / 128);
+    EPA_DISPATCH_SR(ctx, (clv_update_kernel<S_, R_><<<grid, 128, smem, ctx->stream>>>(ctx->tree, ctx->n, d_ops + rg.first, d_pm)));
+    LAUNCHED(ctx);
+  }
+  CU(cudaStreamSynchronize(ctx->stream));
+  cudaFree(d_ops); cudaFree(d_len); cudaFree(d_pm);
+  for (auto & o : hops) ctx->slot_filled[o.parent] = 1;
+  ctx->clvs_ready = true;
+  ctx->lookup_ready = false;
+  return EPA_OK;
+}
+
+extern "C" int epa_upload_clvs(epa_ctx * ctx, const epa_host_clv * clvs, uint32_t n_clvs)
+{
+  if (!ctx) return EPA_ERR_ARG;
+  if (!clvs && n_clvs) return fail(ctx, EPA_ERR_ARG, "null clvs");
+  if (int rc = set_device(ctx)) return rc;
+  for (uint32_t i = 0; i < n_clvs; ++i)
+  {
+    const epa_host_clv & c = clvs[i];
+    if (c.slot < ctx->n_tips || c.slot >= ctx->n_nodes || !c.clv)
+      return fail(ctx, EPA_ERR_ARG, "clv %u: invalid slot %u", i, c.slot);
+    CU(cudaMemcpyAsync(ctx->tree.clv + c.slot * ctx->tree.clv_stride, c.clv, ctx->tree.clv_stride * sizeof(double),
+                       cudaMemcpyHostToDevice, ctx->stream));
+    if (c.scaler)
+      CU(cudaMemcpyAsync(ctx->tree.scaler + (size_t) c.slot * ctx->n, c.scaler, ctx->n * sizeof(uint32_t),
+                         cudaMemcpyHostToDevice, ctx->stream));
+    else
+      CU(cudaMemsetAsync(ctx->tree.scaler + (size_t) c.slot * ctx->n, 0, ctx->n * sizeof(uint32_t), ctx->stream));
+    ctx->slot_filled[c.slot] = 1;
+  }
+  CU(cudaStreamSynchronize(ctx->stream));
+  ctx->clvs_ready = true;
+  ctx->lookup_ready = false;
+  return EPA_OK;
+}
+
+extern "C" int epa_get_clv(epa_ctx * ctx, uint32_t slot, double * clv, uint32_t * scaler)
+{
+  if (!ctx) return EPA_ERR_ARG;
+  if (slot >= ctx->n_nodes) return fail(ctx, EPA_ERR_ARG, "node %u out of range", slot);
+  if (int rc = set_device(ctx)) return rc;
+  CU(cudaStreamSynchronize(ctx->stream));
+  if (clv) CU(cudaMemcpy(clv, ctx->tree.clv + slot * ctx->tree.clv_stride, ctx->tree.clv_stride * sizeof(double), cudaMemcpyDeviceToHost));
+  if (scaler) CU(cudaMemcpy(scaler, ctx->tree.scaler + (size_t) slot * ctx->n, ctx->n * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+  return EPA_OK;
+}
+
+static int check_edges_ready(epa_ctx * ctx)
+{
+  for (const EdgeDev & e : ctx->h_edges)
+    if (!ctx->slot_filled[e.distal] || !ctx->slot_filled[e.proximal])
+      return fail(ctx, EPA_ERR_STATE, "edge CLVs have not been computed or uploaded");
+  return EPA_OK;
+}
+
+extern "C" int epa_edge_loglikelihood(epa_ctx * ctx, uint32_t edge, double * logl)
+{
+  if (!ctx || !logl) return EPA_ERR_ARG;
+  if (edge >= ctx->n_edges) return fail(ctx, EPA_ERR_ARG, "edge %u out of range", edge);
+  if (int rc = set_device(ctx)) return rc;
+  if (int rc = check_edges_ready(ctx)) return rc;
+  const size_t pm = (size_t) ctx->R * ctx->S * ctx->S;
+  const int blocks = (ctx->n + 127) / 128;
+  CU(ctx->tmp.ensure((pm + 1 + blocks) * sizeof(double)));
+  double * d_len = ctx->tmp.as<double>(), * d_pm = d_len + 1, * d_part = d_pm + pm;
+  const EdgeDev e = ctx->h_edges[edge];
+  CU(cudaMemcpyAsync(d_len, &e.length, sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  if (int rc = launch_pmatrices(ctx, d_len, d_pm, 1)) return rc;
+  EPA_DISPATCH_SR(ctx, (edge_logl_kernel<S_, R_><<<blocks, 128, pm * sizeof(double), ctx->stream>>>(ctx->d_model, ctx->tree, ctx->n, e, d_pm, d_part)));
+  LAUNCHED(ctx);
+  std::vector<double> part(blocks);
+  CU(cudaMemcpyAsync(part.data(), d_part, blocks * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  double s = 0;
+  for (double v : part) s += v;
+  *logl = s;
+  return EPA_OK;
+}
+
+// ==============================================================================================
+//  lookup tables
+// ==============================================================================================
+extern "C" int epa_build_lookup(epa_ctx * ctx)
+{
+  if (!ctx) return EPA_ERR_ARG;
+  if (int rc = set_device(ctx)) return rc;
+  if (int rc = check_edges_ready(ctx)) return rc;
+  const int S = ctx->S, R = ctx->R, K = ctx->K, n = ctx->n;
+  const size_t pm = (size_t) R * S * S;
+  const uint32_t B = ctx->n_edges;
+  const size_t lookup_doubles = (size_t) B * ctx->n_pad * K;
+  if (!ctx->d_lookup) CU(cudaMalloc(&ctx->d_lookup, lookup_doubles * sizeof(double)));
+  CU(cudaMemsetAsync(ctx->d_lookup, 0, lookup_doubles * sizeof(double), ctx->stream));
+
+  std::vector<double> lengths(B + 1);
+  for (uint32_t i = 0; i < B; ++i) lengths[i] = ctx->h_edges[i].length / 2.0;
+  lengths[B] = EPA_DEFAULT_PENDANT;
+  const size_t coltab = (size_t) R * K * S;
+  CU(ctx->tmp.ensure(((B + 1) * (pm + 1) + coltab) * sizeof(double)));
+  double * d_len = ctx->tmp.as<double>(), * d_pm = d_len + (B + 1), * d_col = d_pm + (B + 1) * pm;
+  CU(cudaMemcpyAsync(d_len, lengths.data(), (B + 1) * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  CU(cudaEventRecord(ctx->ev[0], ctx->stream));
+  if (int rc = launch_pmatrices(ctx, d_len, d_pm, B + 1)) return rc;
+  if (S == 4) lookup_coltable_kernel<4><<<1, 256, 0, ctx->stream>>>(ctx->d_model, d_pm + (size_t) B * pm, d_col);
+  else lookup_coltable_kernel<20><<<1, 256, 0, ctx->stream>>>(ctx->d_model, d_pm + (size_t) B * pm, d_col);
+  LAUNCHED(ctx);
+  if (S == 4 && R == 4)
+  {
+    dim3 grid(B, (n + 63) / 64);
+    lookup_build_dna_kernel<<<grid, 256, 0, ctx->stream>>>(ctx->d_model, ctx->tree, n, ctx->n_pad, ctx->d_edges, d_pm, d_col, ctx->d_lookup);
+    LAUNCHED(ctx);
+  }
+  else
+  {
+    const size_t smem = (pm + coltab) * sizeof(double);
+    dim3 grid(B, (n + 127) / 128);
+    EPA_DISPATCH_SR(ctx, (lookup_build_kernel<S_, R_><<<grid, 128, smem, ctx->stream>>>(ctx->d_model, ctx->tree, n, ctx->n_pad, K, ctx->d_edges, d_pm, d_col, ctx->d_lookup)));
+    LAUNCHED(ctx);
+  }
+  CU(cudaEventRecord(ctx->ev[1], ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  ctx->lookup_ready = true;
+  return EPA_OK;
+}
+
+extern "C" int epa_last_lookup_ms(epa_ctx * ctx, float * ms)
+{
+  if (!ctx || !ms) return EPA_ERR_ARG;
+  if (int rc = set_device(ctx)) return rc;
+  CU(cudaEventElapsedTime(ms, ctx->ev[0], ctx->ev[1]));
+  return EPA_OK;
+}
+
+extern "C" int epa_get_lookup(epa_ctx * ctx, uint32_t edge, double * out)
+{
+  if (!ctx || !out) return EPA_ERR_ARG;
+  if (!ctx->lookup_ready) return fail(ctx, EPA_ERR_STATE, "epa_build_lookup has not run");
+  if (edge >= ctx->n_edges) return fail(ctx, EPA_ERR_ARG, "edge %u out of range", edge);
+  if (int rc = set_device(ctx)) return rc;
+  const int K = ctx->K, n = ctx->n;
+  std::vector<double> raw((size_t) n * K);
+  CU(cudaMemcpy(raw.data(), ctx->d_lookup + (size_t) edge * ctx->n_pad * K, raw.size() * sizeof(double), cudaMemcpyDeviceToHost));
+  // reference column order: NT_MAP / AA_MAP (src/util/maps.hpp:9-28)
+  const char * map = ctx->S == 4 ? "-TGKCYSBAWRDMHVN" : "ACDEFGHIKLMNPQRSTVWY-XBZ";
+  const int KR = (int) strlen(map);
+  for (int c = 0; c < KR; ++c)
+  {
+    int code = ctx->hm.ascii2code[(unsigned char) map[c]];
+    // the reference's own X column is a genuine fully-ambiguous column (only the char->column
+    // map redirects X to N), so report the fully ambiguous column for it
+    if (ctx->S == 20 && map[c] == 'X') code = 23;
+    const int col = (ctx->S == 20 && map[c] == 'X') ? 23 : ctx->hm.code2col[code];
+    for (int s = 0; s < n; ++s) out[(size_t) s * KR + c] = raw[(size_t) s * K + col];
+  }
+  return EPA_OK;
+}
+
+// ==============================================================================================
+//  chunk pipeline
+// ==============================================================================================
+static int read_flags(epa_ctx * ctx, int flags[8])
+{
+  CU(cudaMemcpyAsync(flags, ctx->d_flags, 8 * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  return EPA_OK;
+}
+
+extern "C" int epa_upload_queries(epa_ctx * ctx, const char * seqs, uint32_t n_queries, int premasking)
+{
+  if (!ctx) return EPA_ERR_ARG;
+  if (!seqs && n_queries) return fail(ctx, EPA_ERR_ARG, "null seqs");
+  if (int rc = set_device(ctx)) return rc;
+  ctx->stage = ST_NONE;
+  ctx->nq = n_queries;
+  if (n_queries == 0) { ctx->stage = ST_QUERIES; ctx->max_span = 0; return EPA_OK; }
+  const size_t bytes = (size_t) n_queries * ctx->n;
+  CU(ctx->raw.ensure(bytes));
+  CU(ctx->codes.ensure(bytes));
+  CU(ctx->begin.ensure(n_queries * sizeof(int)));
+  CU(ctx->span.ensure(n_queries * sizeof(int)));
+  CU(cudaEventRecord(ctx->ev[0], ctx->stream));
+  CU(cudaMemcpyAsync(ctx->raw.p, seqs, bytes, cudaMemcpyHostToDevice, ctx->stream));
+  return epa_encode_queries_dev(ctx, nullptr, n_queries, premasking);
+}
+
+// Device-resident variant: `seqs_dev` already lives in HBM (NULL = the context's own staging
+// buffer filled by epa_upload_queries).
+extern "C" int epa_encode_queries_dev(epa_ctx * ctx, const char * seqs_dev, uint32_t n_queries, int premasking)
+{
+  if (!ctx) return EPA_ERR_ARG;
+  if (int rc = set_device(ctx)) return rc;
+  ctx->stage = ST_NONE;
+  ctx->nq = n_queries;
+  if (n_queries == 0) { ctx->stage = ST_QUERIES; ctx->max_span = 0; return EPA_OK; }
+  const size_t bytes = (size_t) n_queries * ctx->n;
+  if (seqs_dev)
+  {
+    CU(ctx->codes.ensure(bytes));
+    CU(ctx->begin.ensure(n_queries * sizeof(int)));
+    CU(ctx->span.ensure(n_queries * sizeof(int)));
+    CU(cudaEventRecord(ctx->ev[0], ctx->stream));
+  }
+  const uint8_t * src = seqs_dev ? reinterpret_cast<const uint8_t *>(seqs_dev) : ctx->raw.as<uint8_t>();
+  CU(cudaMemsetAsync(ctx->d_flags, 0, 8 * sizeof(int), ctx->stream));
+  const unsigned blocks = (n_queries + 7) / 8;
+  encode_queries_kernel<<<blocks, 256, 0, ctx->stream>>>(ctx->d_model, src, n_queries, ctx->n, premasking ? 1 : 0,
+                                                         ctx->codes.as<uint8_t>(), ctx->begin.as<int>(),
+                                                         ctx->span.as<int>(), ctx->d_flags);
+  LAUNCHED(ctx);
+  CU(cudaEventRecord(ctx->ev[1], ctx->stream));
+  int flags[8];
+  if (int rc = read_flags(ctx, flags)) return rc;
+  if (flags[0] == 1) return fail(ctx, EPA_ERR_QUERY, "query %d contains a character that is not valid for this data type", flags[1] - 1);
+  if (flags[0] == 2) return fail(ctx, EPA_ERR_QUERY, "query %d consists entirely of gaps", flags[1] - 1);
+  ctx->max_span = flags[3];
+  ctx->stage = ST_QUERIES;
+  return EPA_OK;
+}
+
+namespace {
+template <int K>
+int launch_preplace(epa_ctx * ctx, int maxw)
+{
+  constexpr int TQ = 256, NS = 2;
+  const uint32_t nq = ctx->nq;
+  const uint32_t n_tiles = (nq + TQ - 1) / TQ;
+  const size_t per_site = (size_t) NS * K * 8 + TQ;              // stage bytes + code bytes per site
+  const size_t budget = ctx->smem_optin - 4096;
+  int wc = maxw;
+  if ((size_t) wc * per_site > budget) wc = (int) (budget / per_site) & ~3;
+  const size_t smem = (size_t) wc * per_site + NS * 8;
+  CU(cudaFuncSetAttribute(preplace_kernel<K, TQ, NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+  preplace_kernel<K, TQ, NS><<<n_tiles, TQ, smem, ctx->stream>>>(
+      ctx->d_model, ctx->d_lookup, ctx->n, ctx->n_pad, ctx->n_edges, ctx->codes.as<uint8_t>(), ctx->begin.as<int>(),
+      ctx->span.as<int>(), ctx->perm.as<uint32_t>(), nq, ctx->range.as<int2>(), wc, ctx->pre.as<double>(), ctx->pre_stride);
+  LAUNCHED(ctx);
+  return EPA_OK;
+}
+}  // namespace
+
+extern "C" int epa_preplace(epa_ctx * ctx)
+{
+  if (!ctx) return EPA_ERR_ARG;
+  if (int rc = set_device(ctx)) return rc;
+  if (!ctx->lookup_ready) return fail(ctx, EPA_ERR_STATE, "epa_build_lookup has not run");
+  if (ctx->stage < ST_QUERIES) return fail(ctx, EPA_ERR_STATE, "no queries uploaded");
+  const uint32_t nq = ctx->nq;
+  ctx->pre_stride = (ctx->n_edges + 3u) & ~3u;
+  if (nq == 0) { ctx->stage = ST_PREPLACED; return EPA_OK; }
+  constexpr int TQ = 256;
+  const uint32_t n_tiles = (nq + TQ - 1) / TQ;
+  const int n = ctx->n;
+  CU(ctx->perm.ensure(nq * sizeof(uint32_t)));
+  CU(ctx->hist.ensure((size_t) (n + 2) * sizeof(uint32_t)));
+  CU(ctx->range.ensure(n_tiles * sizeof(int2)));
+  CU(ctx->pre.ensure((size_t) nq * ctx->pre_stride * sizeof(double)));
+  CU(cudaEventRecord(ctx->ev[1], ctx->stream));
+  // counting sort of the queries by window start
+  CU(cudaMemsetAsync(ctx->hist.p, 0, (size_t) (n + 2) * sizeof(uint32_t), ctx->stream));
+  histogram_kernel<<<(nq + 255) / 256, 256, 0, ctx->stream>>>(ctx->begin.as<int>(), nq, ctx->hist.as<uint32_t>());
+  LAUNCHED(ctx);
+  exclusive_scan_kernel<<<1, 1024, 0, ctx->stream>>>(ctx->hist.as<uint32_t>(), ctx->hist.as<uint32_t>(), (uint32_t) n + 1, nullptr);
+  LAUNCHED(ctx);
+  scatter_by_key_kernel<<<(nq + 255) / 256, 256, 0, ctx->stream>>>(ctx->begin.as<int>(), nq, ctx->hist.as<uint32_t>(), ctx->perm.as<uint32_t>());
+  LAUNCHED(ctx);
+  CU(cudaMemsetAsync(ctx->d_flags + 2, 0, sizeof(int), ctx->stream));
+  tile_range_kernel<<<(n_tiles + 7) / 8, 256, 0, ctx->stream>>>(ctx->perm.as<uint32_t>(), ctx->begin.as<int>(), ctx->span.as<int>(),
+                                                             nq, TQ, n_tiles, ctx->range.as<int2>(), ctx->d_flags + 2);
+  LAUNCHED(ctx);
+  int flags[8];
+  if (int rc = read_flags(ctx, flags)) return rc;
+  const int maxw = std::max(4, flags[2]);
+  int rc = (ctx->K == 16) ? launch_preplace<16>(ctx, maxw) : launch_preplace<26>(ctx, maxw);
+  if (rc) return rc;
+  CU(cudaEventRecord(ctx->ev[2], ctx->stream));
+  ctx->stage = ST_PREPLACED;
+  return EPA_OK;
+}
+
+extern "C" int epa_get_prescores(epa_ctx * ctx, double * out)
+{
+  if (!ctx || !out) return EPA_ERR_ARG;
+  if (ctx->stage < ST_PREPLACED) return fail(ctx, EPA_ERR_STATE, "epa_preplace has not run");
+  if (int rc = set_device(ctx)) return rc;
+  if (ctx->nq == 0) return EPA_OK;
+  CU(cudaStreamSynchronize(ctx->stream));
+  CU(cudaMemcpy2D(out, (size_t) ctx->n_edges * sizeof(double), ctx->pre.p, ctx->pre_stride * sizeof(double),
+                  (size_t) ctx->n_edges * sizeof(double), ctx->nq, cudaMemcpyDeviceToHost));
+  return EPA_OK;
+}
+
+extern "C" int epa_select(epa_ctx * ctx, const epa_options * opts, uint64_t * n_pairs)
+{
+  if (!ctx || !opts) return EPA_ERR_ARG;
+  if (int rc = set_device(ctx)) return rc;
+  const uint32_t nq = ctx->nq, B = ctx->n_edges;
+  CU(cudaEventRecord(ctx->ev[2], ctx->stream));
+  if (!opts->prescoring)
+  {
+    if (ctx->stage < ST_QUERIES) return fail(ctx, EPA_ERR_STATE, "no queries uploaded");
+    if ((uint64_t) nq * B > 0xffffffffull) return fail(ctx, EPA_ERR_ARG, "chunk too large: %u queries x %u edges exceeds 2^32 pairs", nq, B);
+    ctx->implicit_pairs = true;
+    ctx->n_pairs = (uint64_t) nq * B;
+  }
+  else
+  {
+    if (ctx->stage < ST_PREPLACED) return fail(ctx, EPA_ERR_STATE, "epa_preplace has not run");
+    if (opts->heuristic != 0) return fail(ctx, EPA_ERR_ARG, "only the dynamic (accumulated LWR) heuristic is supported");
+    if (!(opts->prescoring_threshold >= 0.0 && opts->prescoring_threshold <= 1.0))
+      return fail(ctx, EPA_ERR_ARG, "prescoring threshold outside [0,1]");
+    ctx->implicit_pairs = false;
+    ctx->n_pairs = 0;
+    if (nq)
+    {
+      CU(ctx->cnt.ensure(nq * sizeof(uint32_t)));
+      CU(ctx->off.ensure(nq * sizeof(uint32_t)));
+      CU(ctx->cutv.ensure(nq * sizeof(double)));
+      CU(ctx->cuti.ensure(nq * sizeof(int)));
+      CU(ctx->edge_hist.ensure((size_t) (B + 1) * sizeof(uint32_t)));
+      CU(ctx->edge_off.ensure((size_t) (B + 1) * sizeof(uint32_t)));
+      const unsigned blocks = (nq + 7) / 8;
+      select_count_kernel<<<blocks, 256, 0, ctx->stream>>>(ctx->pre.as<double>(), ctx->pre_stride, (int) B, nq,
+                                                           opts->prescoring_threshold, ctx->cnt.as<uint32_t>(),
+                                                           ctx->cutv.as<double>(), ctx->cuti.as<int>());
+      LAUNCHED(ctx);
+      exclusive_scan_kernel<<<1, 1024, 0, ctx->stream>>>(ctx->cnt.as<uint32_t>(), ctx->off.as<uint32_t>(), nq, ctx->d_total);
+      LAUNCHED(ctx);
+      uint64_t total = 0;
+      CU(cudaMemcpyAsync(&total, ctx->d_total, sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
+      CU(cudaStreamSynchronize(ctx->stream));
+      if (total > 0xffffffffull) return fail(ctx, EPA_ERR_ARG, "chunk too large: %llu candidate pairs", (unsigned long long) total);
+      ctx->n_pairs = total;
+      CU(ctx->pair_q.ensure(total * sizeof(uint32_t)));
+      CU(ctx->pair_e.ensure(total * sizeof(uint32_t)));
+      CU(ctx->work.ensure(total * sizeof(uint32_t)));
+      CU(cudaMemsetAsync(ctx->edge_hist.p, 0, (size_t) (B + 1) * sizeof(uint32_t), ctx->stream));
+      select_fill_kernel<<<blocks, 256, 0, ctx->stream>>>(ctx->pre.as<double>(), ctx->pre_stride, (int) B, nq,
+                                                          ctx->off.as<uint32_t>(), ctx->cutv.as<double>(), ctx->cuti.as<int>(),
+                                                          ctx->pair_q.as<uint32_t>(), ctx->pair_e.as<uint32_t>(),
+                                                          ctx->edge_hist.as<uint32_t>());
+      LAUNCHED(ctx);
+      exclusive_scan_kernel<<<1, 1024, 0, ctx->stream>>>(ctx->edge_hist.as<uint32_t>(), ctx->edge_off.as<uint32_t>(), B, nullptr);
+      LAUNCHED(ctx);
+      if (total)
+      {
+        work_scatter_kernel<<<(unsigned) ((total + 255) / 256), 256, 0, ctx->stream>>>(ctx->pair_e.as<uint32_t>(), (uint32_t) total,
+                                                                                    ctx->edge_off.as<uint32_t>(), ctx->work.as<uint32_t>());
+        LAUNCHED(ctx);
+      }
+    }
+  }
+  CU(cudaEventRecord(ctx->ev[3], ctx->stream));
+  if (n_pairs) *n_pairs = ctx->n_pairs;
+  ctx->stage = ST_SELECTED;
+  return EPA_OK;
+}
+
+namespace {
+template <int R>
+int launch_blo_dna(epa_ctx * ctx, BloArgs & a)
+{
+  const int wmax = std::max(1, ctx->max_span);
+  const size_t per_warp = BloWarpSmem<R>::doubles(wmax) * sizeof(double);
+  const size_t budget = ctx->smem_optin - 2048;
+  int warps = (int) std::min<size_t>(8, budget / per_warp);
+  if (warps >= 1)
+  {
+    a.wcap = wmax;
+    const size_t smem = per_warp * warps;
+    int ctas_per_sm = (int) std::max<size_t>(1, std::min<size_t>(4, (ctx->smem_optin + 1024) / (smem + 2048)));
+    // keep every SM busy but do not launch far more warps than there are pairs
+    uint64_t grid = (uint64_t) ctx->sm_count * ctas_per_sm;
+    grid = std::min<uint64_t>(grid, (a.n_pairs + warps - 1) / warps);
+    CU(cudaFuncSetAttribute(blo_dna_kernel<R, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+    blo_dna_kernel<R, false><<<(unsigned) grid, warps * 32, smem, ctx->stream>>>(a);
+  }
+  else
+  {
+    warps = 8;
+    const unsigned grid = (unsigned) std::min<uint64_t>((uint64_t) ctx->sm_count * 2, (a.n_pairs + warps - 1) / warps);
+    CU(ctx->scratch.ensure((size_t) grid * warps * ctx->n * R * 4 * sizeof(double)));
+    a.scratch = ctx->scratch.as<double>();
+    a.wcap = 0;
+    const size_t smem = BloWarpSmem<R>::doubles(0) * sizeof(double) * warps;
+    blo_dna_kernel<R, true><<<grid, warps * 32, smem, ctx->stream>>>(a);
+  }
+  LAUNCHED(ctx);
+  return EPA_OK;
+}
+}  // namespace
+
+extern "C" int epa_place_pairs(epa_ctx * ctx, const epa_options * opts)
+{
+  if (!ctx || !opts) return EPA_ERR_ARG;
+  if (int rc = set_device(ctx)) return rc;
+  if (ctx->stage < ST_SELECTED) return fail(ctx, EPA_ERR_STATE, "epa_select has not run");
+  if (!opts->sliding_blo) return fail(ctx, EPA_ERR_ARG, "--raxml-blo is not supported");
+  if (int rc = check_edges_ready(ctx)) return rc;
+  if (int rc = bind_constants(ctx)) return rc;
+  CU(cudaEventRecord(ctx->ev[3], ctx->stream));
+  if (ctx->n_pairs)
+  {
+    CU(ctx->res.ensure(ctx->n_pairs * sizeof(BloResult)));
+    CU(cudaMemsetAsync(ctx->d_counter, 0, sizeof(unsigned long long), ctx->stream));
+    BloArgs a{};
+    a.tree = ctx->tree; a.n = ctx->n; a.edges = ctx->d_edges; a.codes = ctx->codes.as<uint8_t>();
+    a.begin = ctx->begin.as<int>(); a.span = ctx->span.as<int>();
+    a.work = ctx->implicit_pairs ? nullptr : ctx->work.as<uint32_t>();
+    a.pair_q = ctx->implicit_pairs ? nullptr : ctx->pair_q.as<uint32_t>();
+    a.pair_e = ctx->implicit_pairs ? nullptr : ctx->pair_e.as<uint32_t>();
+    a.n_pairs = (uint32_t) ctx->n_pairs; a.nq = ctx->nq; a.n_edges = ctx->n_edges;
+    a.counter = ctx->d_counter; a.out = ctx->res.as<BloResult>(); a.scratch = nullptr; a.wcap = 0;
+    int rc;
+    if (ctx->S == 4)
+    {
+      switch (ctx->R)
+      {
+        case 1: rc = launch_blo_dna<1>(ctx, a); break;
+        case 2: rc = launch_blo_dna<2>(ctx, a); break;
+        case 4: rc = launch_blo_dna<4>(ctx, a); break;
+        case 8: rc = launch_blo_dna<8>(ctx, a); break;
+        default: return fail(ctx, EPA_ERR_ARG, "unsupported rate category count %d", ctx->R);
+      }
+    }
+    else
+      rc = launch_blo_generic(ctx->S, ctx->R, ctx->sm_count, ctx->smem_optin, ctx->max_span, ctx->d_model, a, &ctx->scratch.p,
+                              &ctx->scratch.cap, ctx->stream) == cudaSuccess ? EPA_OK
+           : fail(ctx, EPA_ERR_CUDA, "generic BLO launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+    if (rc) return rc;
+    if (ctx->S != 4) LAUNCHED(ctx);
+  }
+  CU(cudaEventRecord(ctx->ev[4], ctx->stream));
+  ctx->stage = ST_PLACED;
+  return EPA_OK;
+}
+
+extern "C" int epa_collect(epa_ctx * ctx, const epa_options * opts, epa_placement * out, uint32_t * out_counts)
+{
+  if (!ctx || !opts) return EPA_ERR_ARG;
+  if (int rc = set_device(ctx)) return rc;
+  if (ctx->stage < ST_PLACED) return fail(ctx, EPA_ERR_STATE, "epa_place_pairs has not run");
+  if (opts->filter_max == 0) return fail(ctx, EPA_ERR_ARG, "filter_max = 0 (unlimited) is not supported: it is the record stride");
+  if (opts->filter_min < 1) return fail(ctx, EPA_ERR_ARG, "Filter min cannot be smaller than 1!");
+  if (!(opts->support_threshold >= 0.0 && opts->support_threshold <= 1.0))
+    return fail(ctx, EPA_ERR_ARG, "thresh is not a valid likelihood weight ratio (outside of [0,1])");
+  if (opts->filter_acc_lwr && opts->filter_min > opts->filter_max) return fail(ctx, EPA_ERR_ARG, "Filter min cannot be smaller than max!");
+  const uint32_t nq = ctx->nq;
+  if (nq == 0) return EPA_OK;
+  CU(ctx->out_rec.ensure((size_t) nq * opts->filter_max * sizeof(PlacementRec)));
+  CU(ctx->out_cnt.ensure(nq * sizeof(uint32_t)));
+  CU(cudaMemsetAsync(ctx->d_flags, 0, 2 * sizeof(int), ctx->stream));
+  CollectArgs a{};
+  a.res = ctx->res.as<BloResult>();
+  a.pair_e = ctx->implicit_pairs ? nullptr : ctx->pair_e.as<uint32_t>();
+  a.off = ctx->off.as<uint32_t>(); a.cnt = ctx->cnt.as<uint32_t>();
+  a.nq = nq; a.n_edges = ctx->n_edges;
+  a.acc_mode = opts->filter_acc_lwr ? 1 : 0;
+  a.thresh = opts->support_threshold; a.fmin = opts->filter_min; a.fmax = opts->filter_max;
+  a.out = ctx->out_rec.as<PlacementRec>(); a.out_cnt = ctx->out_cnt.as<uint32_t>(); a.err = ctx->d_flags;
+  collect_kernel<<<(nq + 7) / 8, 256, 0, ctx->stream>>>(a);
+  LAUNCHED(ctx);
+  if (out) CU(cudaMemcpyAsync(out, ctx->out_rec.p, (size_t) nq * opts->filter_max * sizeof(PlacementRec), cudaMemcpyDeviceToHost, ctx->stream));
+  if (out_counts) CU(cudaMemcpyAsync(out_counts, ctx->out_cnt.p, nq * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaEventRecord(ctx->ev[5], ctx->stream));
+  int flags[8];
+  if (int rc = read_flags(ctx, flags)) return rc;
+  for (int i = 0; i < 5; ++i) (void) cudaEventElapsedTime(&ctx->ms[i], ctx->ev[i], ctx->ev[i + 1]);
+  (void) cudaGetLastError();
+  if (flags[0] == 3) return fail(ctx, EPA_ERR_QUERY, "query %d: likelihood is not finite", flags[1] - 1);
+  return EPA_OK;
+}
+
+extern "C" int epa_place_chunk(epa_ctx * ctx, const char * seqs, uint32_t n_queries, const epa_options * opts,
+                               epa_placement * out, uint32_t * out_counts)
+{
+  if (!ctx || !opts) return EPA_ERR_ARG;
+  if (!ctx->lookup_ready && opts->prescoring)
+    if (int rc = epa_build_lookup(ctx)) return rc;
+  if (int rc = epa_upload_queries(ctx, seqs, n_queries, opts->premasking)) return rc;
+  if (opts->prescoring)
+    if (int rc = epa_preplace(ctx)) return rc;
+  if (int rc = epa_select(ctx, opts, nullptr)) return rc;
+  if (int rc = epa_place_pairs(ctx, opts)) return rc;
+  return epa_collect(ctx, opts, out, out_counts);
+}
+
+extern "C" int epa_get_pairs(epa_ctx * ctx, uint32_t * query_ids, uint32_t * edge_ids, epa_placement * raw, uint64_t capacity)
+{
+  if (!ctx) return EPA_ERR_ARG;
+  if (ctx->stage < ST_SELECTED) return fail(ctx, EPA_ERR_STATE, "epa_select has not run");
+  if (capacity < ctx->n_pairs) return fail(ctx, EPA_ERR_ARG, "capacity %llu < %llu pairs", (unsigned long long) capacity, (unsigned long long) ctx->n_pairs);
+  if (int rc = set_device(ctx)) return rc;
+  CU(cudaStreamSynchronize(ctx->stream));
+  const uint64_t np = ctx->n_pairs;
+  std::vector<uint32_t> q(np), e(np);
+  if (ctx->implicit_pairs)
+    for (uint64_t p = 0; p < np; ++p) { q[p] = (uint32_t) (p / ctx->n_edges); e[p] = (uint32_t) (p % ctx->n_edges); }
+  else if (np)
+  {
+    CU(cudaMemcpy(q.data(), ctx->pair_q.p, np * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(e.data(), ctx->pair_e.p, np * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+  }
+  if (query_ids) memcpy(query_ids, q.data(), np * sizeof(uint32_t));
+  if (edge_ids) memcpy(edge_ids, e.data(), np * sizeof(uint32_t));
+  if (raw)
+  {
+    if (ctx->stage < ST_PLACED) return fail(ctx, EPA_ERR_STATE, "epa_place_pairs has not run");
+    std::vector<BloResult> r(np);
+    if (np) CU(cudaMemcpy(r.data(), ctx->res.p, np * sizeof(BloResult), cudaMemcpyDeviceToHost));
+    for (uint64_t p = 0; p < np; ++p)
+    {
+      raw[p].branch_id = e[p];
+      raw[p].likelihood = r[p].logl;
+      raw[p].lwr = 0.0;
+      raw[p].pendant_length = r[p].pendant;
+      raw[p].distal_length = r[p].distal;
+    }
+  }
+  return EPA_OK;
+}
+
+extern "C" int epa_last_timings(epa_ctx * ctx, float ms[5])
+{
+  if (!ctx || !ms) return EPA_ERR_ARG;
+  for (int i = 0; i < 5; ++i) ms[i] = ctx->ms[i];
+  return EPA_OK;
+}
+
+extern "C" int epa_num_pairs(epa_ctx * ctx, uint64_t * n_pairs)
+{
+  if (!ctx || !n_pairs) return EPA_ERR_ARG;
+  *n_pairs = ctx->n_pairs;
+  return EPA_OK;
+}
+
+extern "C" int epa_synchronize(epa_ctx * ctx)
+{
+  if (!ctx) return EPA_ERR_ARG;
+  if (int rc = set_device(ctx)) return rc;
+  CU(cudaStreamSynchronize(ctx->stream));
+  return EPA_OK;
+}

@@ -1,0 +1,466 @@
+// kernels_blo.cuh - HOT LOOP B: branch-length optimisation of one (query, edge) pair on the
+// three-taxon "tiny tree" (distal D, proximal X, new tip T).
+//
+// Reference behaviour restated (paths relative to /root/reference, LP = libs/pll-modules/libs/libpll/src,
+// PM = libs/pll-modules/src):
+//   Tiny_Tree::place (opt)          src/tree/Tiny_Tree.cpp:131-218
+//   optimize_branch_triplet         src/core/pll/optimize.cpp:253-286
+//   opt_branch_lengths_pplacer      src/core/pll/optimize.cpp:60-248
+//   pllmod_opt_minimize_newton      PM/optimize/opt_algorithms.c:86-262
+//   sumtable / derivatives          LP/core_derivatives.c:321-471,473-641,643-858
+//   CLV update / edge logl          LP/core_partials.c:202-352,612-766, LP/core_likelihood.c:351-578
+//   range focus                     src/core/pll/pll_util.cpp:388-418
+//
+// DNA kernel (S = 4): ONE WARP PER PAIR. R lanes share a site (lane % R = rate category), so a warp
+// sweeps 32/R sites per step and every lane reads exactly one 32-byte sector of each CLV: the
+// CLV windows stream fully coalesced from L2/HBM. The rate sum is log2(R) xor-shuffles, the site
+// sum a fixed-order butterfly. The sumtable (the only per-pair state that the Newton iterations
+// re-read) lives in the warp's shared-memory slice; transition matrices and the per-mask tip
+// vectors are rebuilt by the warp itself whenever a length changes. Nothing but 24 bytes per
+// pair leaves the SM.
+#pragma once
+#include "common.cuh"
+
+namespace epa {
+
+// model tables as constant-bank operands (static indices fold into the DFMA; one translation unit)
+__constant__ DevModel c_model;
+
+#define EPA_DEFAULT_PENDANT 0.10536051565782630123   /* -ln(0.9), src/util/constants.hpp:12 */
+#define EPA_MIN_BRLEN 1.0e-4                          /* PM/optimize/pll_optimize.h:57 */
+#define EPA_MAX_BRLEN 100.0                           /* :58 */
+#define EPA_DEFAULT_BRLEN 0.1                         /* :54 */
+#define EPA_BLO_EPSILON 1e-1                          /* src/core/pll/optimize.hpp:9 */
+#define EPA_NR_MAX_ITERS 30
+#define EPA_SMOOTHINGS 32
+
+struct BloResult { double logl, pendant, distal; };
+
+struct BloArgs {
+  DevTree tree;
+  int n;
+  const EdgeDev * edges;
+  const uint8_t * codes;          // [nq][n]
+  const int * begin;
+  const int * span;
+  const uint32_t * work;          // edge-major permutation of pair ids, or NULL (identity)
+  const uint32_t * pair_q;        // NULL = implicit all-pairs mode
+  const uint32_t * pair_e;
+  uint32_t n_pairs;
+  uint32_t nq, n_edges;           // implicit mode: item i -> edge i / nq, query i % nq, pair id q*n_edges+e
+  unsigned long long * counter;   // dynamic work counter (zeroed before launch)
+  BloResult * out;                // [pair id]
+  double * scratch;               // global sumtable scratch (GS variant): [total warps][n*R*4]
+  int wcap;                       // sites the shared-memory sumtable can hold
+};
+
+template <int R>
+struct BloWarpSmem {
+  // offsets in doubles inside one warp's slice
+  static constexpr int P_D = 0;
+  static constexpr int P_P = R * 16;
+  static constexpr int P_E = 2 * R * 16;
+  static constexpr int TV = 3 * R * 16;              // [R][16 masks][4]
+  static constexpr int EX = TV + R * 64;             // [R*4]
+  static constexpr int SUM = EX + R * 4;             // [wcap][R][4]
+  __host__ __device__ static constexpr size_t doubles(int wcap) { return (size_t) SUM + (size_t) wcap * R * 4; }
+};
+
+struct BloCtaSmem {
+  double V[16], Vinv[16];             // lane-divergent indexing in warp_pmatrix
+  __align__(16) double tipleft[64];   // [mask][j] = sum_{k in mask} pi_k Vinv[k][j]
+};
+
+// sumtable of one pair, split in two 16-byte planes so that a warp's accesses are conflict-free
+struct SumTab { double2 * lo; double2 * hi; };
+
+// P[r][i][j] = delta_ij + sum_k Vinv[i][k] expm1(lambda_k rate_r t) V[k][j]   (LP/core_pmatrix.c:185-249)
+template <int R>
+__device__ __forceinline__ void warp_pmatrix(const BloCtaSmem & cs, double t, double * P, double * ex, int lane)
+{
+  for (int idx = lane; idx < R * 4; idx += 32)
+    ex[idx] = expm1(c_model.eigenvals[idx & 3] * c_model.rates[idx >> 2] * t);
+  __syncwarp();
+  for (int idx = lane; idx < R * 16; idx += 32)
+  {
+    const int r = idx >> 4, i = (idx >> 2) & 3, j = idx & 3;
+    double acc = (i == j) ? 1.0 : 0.0;
+    #pragma unroll
+    for (int k = 0; k < 4; ++k) acc += (cs.Vinv[i * 4 + k] * ex[r * 4 + k]) * cs.V[k * 4 + j];
+    P[idx] = acc;
+  }
+  __syncwarp();
+}
+
+// tv[r][mask][i] = sum_{j in mask} P[r][i][j]  (the pendant matrix applied to a tip state set)
+template <int R>
+__device__ __forceinline__ void warp_tipvec(const double * P, double * tv, int lane)
+{
+  for (int idx = lane; idx < R * 64; idx += 32)
+  {
+    const int r = idx >> 6, mask = (idx >> 2) & 15, i = idx & 3;
+    double acc = 0.0;
+    #pragma unroll
+    for (int j = 0; j < 4; ++j)
+      if ((mask >> j) & 1) acc += P[r * 16 + i * 4 + j];
+    tv[idx] = acc;
+  }
+  __syncwarp();
+}
+
+template <int R>
+__device__ __forceinline__ double rate_sum(double v)
+{
+  #pragma unroll
+  for (int o = 1; o < R; o <<= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// true when all R lanes of the site group report `small`
+template <int R>
+__device__ __forceinline__ bool group_all(bool small, int lane)
+{
+  if (R == 1) return small;
+  const unsigned ballot = __ballot_sync(0xffffffffu, small);
+  const unsigned gm = (R == 32) ? 0xffffffffu : ((1u << R) - 1u);
+  return ((ballot >> (lane & ~(R - 1))) & gm) == gm;
+}
+
+// first and second derivative sums over the window (LP/core_derivatives.c:643-858)
+template <int R>
+__device__ __forceinline__ void warp_derivatives(const SumTab sum, int w, double t, int lane,
+                                                 double & f, double & df)
+{
+  constexpr int SPW = 32 / R;
+  const int r = lane % R, so = lane / R;
+  // diag table of this lane's rate: lanes 0..4R-1 compute one exponential each
+  double e = 0.0, lk = 0.0;
+  {
+    const int idx = lane % (R * 4);
+    lk = c_model.eigenvals[idx & 3] * c_model.rates[idx >> 2];
+    e = exp(lk * t);
+  }
+  double d0[4], d1[4], d2[4];
+  #pragma unroll
+  for (int j = 0; j < 4; ++j)
+  {
+    const double ej = __shfl_sync(0xffffffffu, e, r * 4 + j);
+    const double lj = __shfl_sync(0xffffffffu, lk, r * 4 + j);
+    d0[j] = ej; d1[j] = lj * ej; d2[j] = lj * lj * ej;
+  }
+  const double wr = c_model.weights[r];
+  double a1 = 0.0, a2 = 0.0;
+  for (int s0 = 0; s0 < w; s0 += SPW)
+  {
+    const int s = s0 + so;
+    const bool act = s < w;
+    const int sc = act ? s : w - 1;
+    const double2 x01 = sum.lo[sc * R + r], x23 = sum.hi[sc * R + r];
+    double c0 = x01.x * d0[0] + x01.y * d0[1] + x23.x * d0[2] + x23.y * d0[3];
+    double c1 = x01.x * d1[0] + x01.y * d1[1] + x23.x * d1[2] + x23.y * d1[3];
+    double c2 = x01.x * d2[0] + x01.y * d2[1] + x23.x * d2[2] + x23.y * d2[3];
+    c0 = rate_sum<R>(c0 * wr);
+    c1 = rate_sum<R>(c1 * wr);
+    c2 = rate_sum<R>(c2 * wr);
+    if (act && r == 0)
+    {
+      const double inv = 1.0 / c0;
+      const double g1 = -c1 * inv;
+      a1 += g1;
+      a2 += g1 * g1 - c2 * inv;
+    }
+  }
+  f = warp_sum(a1);
+  df = warp_sum(a2);
+}
+
+// bounded Newton-Raphson, PM/optimize/opt_algorithms.c:133-262; returns 0.0 on failure
+template <int R>
+__device__ __forceinline__ double warp_newton(const SumTab sum, int w, int lane, double xmin,
+                                              double xguess, double xmax, double tol)
+{
+  double x = fmax(fmin(xguess, xmax), xmin);
+  double xl = xmin, xh = xmax;
+  const double dxmax = xmax / EPA_NR_MAX_ITERS;
+  int iter = 0;
+  for (;;)
+  {
+    if (iter++ > EPA_NR_MAX_ITERS) return 0.0;
+    double f, df;
+    warp_derivatives<R>(sum, w, x, lane, f, df);
+    if (!isfinite(f) || !isfinite(df)) return 0.0;
+    double dx;
+    if (df > 0.0)
+    {
+      if (fabs(f) < tol) return x;
+      if (f < 0.0) xl = x; else xh = x;
+      dx = -1.0 * f / df;
+    }
+    else
+      dx = -1.0 * f / fabs(df);
+    dx = fmax(fmin(dx, dxmax), -dxmax);
+    if (x + dx < xl) dx = xl - x;
+    if (x + dx > xh) dx = xh - x;
+    if (fabs(dx) < tol) return x;
+    x += dx;
+    x = fmax(fmin(x, xmax), xmin);
+  }
+}
+
+// Pass A: inner CLV toward the new tip from (D, X); returns the edge log-likelihood
+// new_tip | inner over the window and leaves the pendant sumtable (inner vs tip) in `sum`.
+template <int R>
+__device__ __forceinline__ double warp_pass_tip(const BloCtaSmem & cs, const double * ws, const SumTab sum,
+                                                const double * __restrict__ D, const double * __restrict__ X,
+                                                const uint32_t * __restrict__ sD, const uint32_t * __restrict__ sX,
+                                                const uint8_t * __restrict__ qc, int w, int lane)
+{
+  constexpr int SPW = 32 / R;
+  const int r = lane % R, so = lane / R;
+  double pd[16], pp[16];
+  #pragma unroll
+  for (int k = 0; k < 16; ++k) { pd[k] = ws[BloWarpSmem<R>::P_D + r * 16 + k]; pp[k] = ws[BloWarpSmem<R>::P_P + r * 16 + k]; }
+  const double * tv = ws + BloWarpSmem<R>::TV + r * 64;
+  const double wr = c_model.weights[r];
+  double acc = 0.0;
+  #pragma unroll 2
+  for (int s0 = 0; s0 < w; s0 += SPW)
+  {
+    const int s = s0 + so;
+    const bool act = s < w;
+    const int sc = act ? s : w - 1;
+    double dv[4], xv[4], in[4];
+    load_vec<4>(D + ((size_t) sc * R + r) * 4, dv);
+    load_vec<4>(X + ((size_t) sc * R + r) * 4, xv);
+    const int mask = qc[sc] & 15;
+    uint32_t scal = 0;
+    if (r == 0) scal = sD[sc] + sX[sc];
+    bool small = true;
+    #pragma unroll
+    for (int i = 0; i < 4; ++i)
+    {
+      const double ta = pd[i * 4] * dv[0] + pd[i * 4 + 1] * dv[1] + pd[i * 4 + 2] * dv[2] + pd[i * 4 + 3] * dv[3];
+      const double tb = pp[i * 4] * xv[0] + pp[i * 4 + 1] * xv[1] + pp[i * 4 + 2] * xv[2] + pp[i * 4 + 3] * xv[3];
+      in[i] = ta * tb;
+      small = small && (in[i] < EPA_SCALE_THRESHOLD);
+    }
+    if (group_all<R>(small, lane))
+    {
+      #pragma unroll
+      for (int i = 0; i < 4; ++i) in[i] *= EPA_SCALE_FACTOR;
+      scal += 1;
+    }
+    // edge log-likelihood term of this rate
+    const double2 * tp = reinterpret_cast<const double2 *>(tv + mask * 4);
+    const double2 t01 = tp[0], t23 = tp[1];
+    double term = (in[0] * c_model.freqs[0]) * t01.x + (in[1] * c_model.freqs[1]) * t01.y
+                + (in[2] * c_model.freqs[2]) * t23.x + (in[3] * c_model.freqs[3]) * t23.y;
+    term = rate_sum<R>(term * wr);
+    if (act && r == 0)
+      acc += log(term) + (scal ? (double) scal * EPA_LOG_SCALE_THRESHOLD : 0.0);
+    // pendant sumtable: tip side takes pi*Vinv, inner side takes V
+    if (act)
+    {
+      double st[4];
+      #pragma unroll
+      for (int j = 0; j < 4; ++j)
+      {
+        const double right = c_model.eigenvecs[j * 4] * in[0] + c_model.eigenvecs[j * 4 + 1] * in[1]
+                           + c_model.eigenvecs[j * 4 + 2] * in[2] + c_model.eigenvecs[j * 4 + 3] * in[3];
+        st[j] = cs.tipleft[mask * 4 + j] * right;
+      }
+      sum.lo[s * R + r] = make_double2(st[0], st[1]);
+      sum.hi[s * R + r] = make_double2(st[2], st[3]);
+    }
+  }
+  __syncwarp();
+  return warp_sum(acc);
+}
+
+// Pass B: inner CLV toward the distal node from (T, X); leaves the distal sumtable (D vs inner)
+template <int R>
+__device__ __forceinline__ void warp_pass_distal(const BloCtaSmem & cs, const double * ws, const SumTab sum,
+                                                 const double * __restrict__ D, const double * __restrict__ X,
+                                                 const uint8_t * __restrict__ qc, int w, int lane)
+{
+  constexpr int SPW = 32 / R;
+  const int r = lane % R, so = lane / R;
+  double pp[16];
+  #pragma unroll
+  for (int k = 0; k < 16; ++k) pp[k] = ws[BloWarpSmem<R>::P_P + r * 16 + k];
+  const double * tv = ws + BloWarpSmem<R>::TV + r * 64;
+  #pragma unroll 2
+  for (int s0 = 0; s0 < w; s0 += SPW)
+  {
+    const int s = s0 + so;
+    const bool act = s < w;
+    const int sc = act ? s : w - 1;
+    double dv[4], xv[4], in[4];
+    load_vec<4>(D + ((size_t) sc * R + r) * 4, dv);
+    load_vec<4>(X + ((size_t) sc * R + r) * 4, xv);
+    const int mask = qc[sc] & 15;
+    bool small = true;
+    #pragma unroll
+    for (int i = 0; i < 4; ++i)
+    {
+      const double tb = pp[i * 4] * xv[0] + pp[i * 4 + 1] * xv[1] + pp[i * 4 + 2] * xv[2] + pp[i * 4 + 3] * xv[3];
+      in[i] = tv[mask * 4 + i] * tb;
+      small = small && (in[i] < EPA_SCALE_THRESHOLD);
+    }
+    if (group_all<R>(small, lane))
+    {
+      #pragma unroll
+      for (int i = 0; i < 4; ++i) in[i] *= EPA_SCALE_FACTOR;
+    }
+    if (act)
+    {
+      double st[4];
+      #pragma unroll
+      for (int j = 0; j < 4; ++j)
+      {
+        const double left = dv[0] * c_model.pivinv[j] + dv[1] * c_model.pivinv[4 + j]
+                          + dv[2] * c_model.pivinv[8 + j] + dv[3] * c_model.pivinv[12 + j];
+        const double right = c_model.eigenvecs[j * 4] * in[0] + c_model.eigenvecs[j * 4 + 1] * in[1]
+                           + c_model.eigenvecs[j * 4 + 2] * in[2] + c_model.eigenvecs[j * 4 + 3] * in[3];
+        st[j] = left * right;
+      }
+      sum.lo[s * R + r] = make_double2(st[0], st[1]);
+      sum.hi[s * R + r] = make_double2(st[2], st[3]);
+    }
+  }
+  __syncwarp();
+}
+
+// GS = sumtable in global scratch (windows that do not fit the shared-memory slice)
+template <int R, bool GS>
+__global__ void __launch_bounds__(256, 1)
+blo_dna_kernel(BloArgs a)
+{
+  extern __shared__ __align__(16) double smem_d[];
+  __shared__ BloCtaSmem cs;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int n_warps = blockDim.x >> 5;
+  for (int i = threadIdx.x; i < 16; i += blockDim.x)
+  {
+    cs.V[i] = c_model.eigenvecs[i];
+    cs.Vinv[i] = c_model.inv_eigenvecs[i];
+  }
+  for (int i = threadIdx.x; i < 64; i += blockDim.x)
+  {
+    // tipleft[mask][j] = sum_{k in mask} pi_k Vinv[k][j]
+    const int mask = i >> 2, j = i & 3;
+    double acc = 0.0;
+    for (int k = 0; k < 4; ++k)
+      if ((mask >> k) & 1) acc += c_model.pivinv[k * 4 + j];
+    cs.tipleft[i] = acc;
+  }
+  __syncthreads();
+
+  const size_t per_warp = BloWarpSmem<R>::doubles(GS ? 0 : a.wcap);
+  double * ws = smem_d + (size_t) warp * per_warp;
+  const int cap_units = (GS ? a.n : a.wcap) * R;
+  double * sum_base = GS ? a.scratch + ((size_t) blockIdx.x * n_warps + warp) * (size_t) a.n * R * 4
+                         : ws + BloWarpSmem<R>::SUM;
+  SumTab sum;
+  sum.lo = reinterpret_cast<double2 *>(sum_base);
+  sum.hi = sum.lo + cap_units;
+  double * ex = ws + BloWarpSmem<R>::EX;
+
+  for (;;)
+  {
+    unsigned long long item = 0;
+    if (lane == 0) item = atomicAdd(a.counter, 1ull);
+    item = __shfl_sync(0xffffffffu, item, 0);
+    if (item >= a.n_pairs) break;
+    uint32_t pid, q, e;
+    if (a.pair_q)
+    {
+      pid = a.work ? a.work[item] : (uint32_t) item;
+      q = a.pair_q[pid];
+      e = a.pair_e[pid];
+    }
+    else
+    {
+      e = (uint32_t) (item / a.nq);
+      q = (uint32_t) (item % a.nq);
+      pid = q * a.n_edges + e;
+    }
+    const EdgeDev ed = a.edges[e];
+    const int begin = a.begin[q], w = a.span[q];
+    if (w <= 0 || (!GS && w > a.wcap))
+    {
+      if (lane == 0) a.out[pid] = BloResult{NAN, NAN, NAN};
+      continue;
+    }
+    const int n = a.n;
+    const double * D = a.tree.clv + ed.distal * a.tree.clv_stride + (size_t) begin * R * 4;
+    const double * X = a.tree.clv + ed.proximal * a.tree.clv_stride + (size_t) begin * R * 4;
+    const uint32_t * sD = a.tree.scaler + (size_t) ed.distal * n + begin;
+    const uint32_t * sX = a.tree.scaler + (size_t) ed.proximal * n + begin;
+    const uint8_t * qc = a.codes + (size_t) q * n + begin;
+
+    // optimize_branch_triplet: lengths orig/2, orig/2, -ln 0.9
+    const double orig = ed.length;
+    double len_d = orig / 2.0, len_p = orig / 2.0, len_e = EPA_DEFAULT_PENDANT;
+    const double original_length = len_d * 2;
+    warp_pmatrix<R>(cs, len_d, ws + BloWarpSmem<R>::P_D, ex, lane);
+    for (int i = lane; i < R * 16; i += 32) ws[BloWarpSmem<R>::P_P + i] = ws[BloWarpSmem<R>::P_D + i];
+    warp_pmatrix<R>(cs, len_e, ws + BloWarpSmem<R>::P_E, ex, lane);
+    warp_tipvec<R>(ws + BloWarpSmem<R>::P_E, ws + BloWarpSmem<R>::TV, lane);
+
+    double loglikelihood = -warp_pass_tip<R>(cs, ws, sum, D, X, sD, sX, qc, w, lane);
+    int smoothings = EPA_SMOOTHINGS;
+    while (smoothings)
+    {
+      const double old_d = len_d, old_e = len_e;
+      // pendant
+      double xmin = EPA_MIN_BRLEN, xmax = EPA_MAX_BRLEN, xtol = xmin / 10.0, xguess = len_e;
+      if (xguess < xmin || xguess > xmax) xguess = EPA_DEFAULT_BRLEN;
+      double xres = warp_newton<R>(sum, w, lane, xmin, xguess, xmax, xtol);
+      if (xres > 0.0)
+      {
+        len_e = xres;
+        warp_pmatrix<R>(cs, len_e, ws + BloWarpSmem<R>::P_E, ex, lane);
+        warp_tipvec<R>(ws + BloWarpSmem<R>::P_E, ws + BloWarpSmem<R>::TV, lane);
+      }
+      // distal
+      warp_pass_distal<R>(cs, ws, sum, D, X, qc, w, lane);
+      xguess = len_d;
+      xmin = fmin(EPA_MIN_BRLEN / 2.0, original_length / 2.0);
+      xtol = xmin / 10.0;
+      xmax = original_length - xtol;
+      if (xguess < xmin || xguess > xmax) xguess = original_length / 2.0;
+      xres = warp_newton<R>(sum, w, lane, xmin, xguess, xmax, xtol);
+      if (xres > 0.0)
+      {
+        len_d = xres;
+        len_p = original_length - xres;
+        warp_pmatrix<R>(cs, len_d, ws + BloWarpSmem<R>::P_D, ex, lane);
+        warp_pmatrix<R>(cs, len_p, ws + BloWarpSmem<R>::P_P, ex, lane);
+      }
+      // score (also prepares the pendant sumtable of the next round)
+      const double new_logl = -warp_pass_tip<R>(cs, ws, sum, D, X, sD, sX, qc, w, lane);
+      if (new_logl - loglikelihood > new_logl * 1e-14)
+      {
+        len_e = old_e;
+        len_d = old_d;
+        len_p = original_length - old_d;
+        break;
+      }
+      --smoothings;
+      if (fabs(new_logl - loglikelihood) < EPA_BLO_EPSILON) smoothings = 0;
+      loglikelihood = new_logl;
+    }
+    if (lane == 0)
+    {
+      BloResult res;
+      res.logl = -loglikelihood;
+      res.distal = (orig / (len_d + len_p)) * len_d;      // Tiny_Tree.cpp:183-185
+      res.pendant = len_e;
+      a.out[pid] = res;
+    }
+    __syncwarp();
+  }
+}
+
+}  // namespace epa

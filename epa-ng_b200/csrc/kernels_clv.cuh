@@ -1,0 +1,357 @@
+// kernels_clv.cuh - reference-tree side of the hot path: transition matrices, directional CLVs,
+// per-edge lookup tables, edge log-likelihood.
+//
+// Reference behaviour restated (paths relative to /root/reference, LP = libs/pll-modules/libs/libpll/src):
+//   pmatrix            LP/core_pmatrix.c:185-249
+//   CLV update         LP/core_partials.c:202-352 (tip-inner), :612-766 (inner-inner), :24-46 (scalers)
+//   edge logl / lookup LP/core_likelihood.c:441-578, src/tree/Tiny_Tree.cpp:18-46,84-128,
+//                      src/core/Lookup_Store.hpp:73-81
+#pragma once
+#include "common.cuh"
+
+namespace epa {
+
+// ---------------------------------------------------------------------------------------------
+// P(t) = I + Vinv diag(expm1(lambda * rate * t)) V  for a list of branch lengths.
+// grid = n_mats, block = 128. out[m][r][i][j]
+// ---------------------------------------------------------------------------------------------
+template <int S>
+__global__ void pmatrix_kernel(const DevModel * __restrict__ m, const double * __restrict__ lengths,
+                               double * __restrict__ out)
+{
+  __shared__ double expd[MAX_RATES * S];
+  const int R = m->R;
+  const double t = lengths[blockIdx.x];
+  for (int idx = threadIdx.x; idx < R * S; idx += blockDim.x)
+    expd[idx] = expm1(m->eigenvals[idx % S] * m->rates[idx / S] * t);
+  __syncthreads();
+  double * P = out + (size_t) blockIdx.x * R * S * S;
+  for (int idx = threadIdx.x; idx < R * S * S; idx += blockDim.x)
+  {
+    const int r = idx / (S * S), i = (idx / S) % S, j = idx % S;
+    double acc = (i == j) ? 1.0 : 0.0;
+    #pragma unroll
+    for (int k = 0; k < S; ++k)
+      acc += (m->inv_eigenvecs[i * S + k] * expd[r * S + k]) * m->eigenvecs[k * S + j];
+    P[idx] = acc;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Tip state masks -> 0/1 CLVs (all rate blocks identical), scaler 0. One thread per (tip, site).
+// ---------------------------------------------------------------------------------------------
+template <int S>
+__global__ void tip_expand_kernel(const DevModel * __restrict__ m, DevTree tree,
+                                  const uint32_t * __restrict__ masks, size_t total)
+{
+  const size_t idx = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int R = m->R;
+  const uint32_t mask = masks[idx];
+  double * dst = tree.clv + idx * (size_t) (R * S);
+  double v[S];
+  #pragma unroll
+  for (int j = 0; j < S; ++j) v[j] = (mask >> j) & 1u ? 1.0 : 0.0;
+  for (int r = 0; r < R; ++r) store_vec<S>(dst + r * S, v);
+  tree.scaler[idx] = 0;
+}
+
+// stage `count` doubles from global into shared memory (whole block)
+__device__ __forceinline__ void stage_doubles(double * dst, const double * __restrict__ src, int count)
+{
+  for (int i = threadIdx.x; i < count; i += blockDim.x) dst[i] = __ldg(src + i);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Felsenstein pruning step, one thread per site, all ops of one dependency level in one launch.
+// grid = (n_ops, ceil(n / blockDim)), dynamic smem = 2*R*S*S doubles.
+// ---------------------------------------------------------------------------------------------
+template <int S, int R>
+__global__ void __launch_bounds__(128)
+clv_update_kernel(DevTree tree, int n, const ClvOpDev * __restrict__ ops, const double * __restrict__ pmats)
+{
+  extern __shared__ double smem[];
+  double * Pl = smem;
+  double * Pr = smem + R * S * S;
+  const ClvOpDev op = ops[blockIdx.x];
+  stage_doubles(Pl, pmats + (size_t) op.lmat * R * S * S, R * S * S);
+  stage_doubles(Pr, pmats + (size_t) op.rmat * R * S * S, R * S * S);
+  __syncthreads();
+  const int site = blockIdx.y * blockDim.x + threadIdx.x;
+  if (site >= n) return;
+
+  const double * L = tree.clv + op.left * tree.clv_stride + (size_t) site * (R * S);
+  const double * Rc = tree.clv + op.right * tree.clv_stride + (size_t) site * (R * S);
+  double * out = tree.clv + op.parent * tree.clv_stride + (size_t) site * (R * S);
+
+  double res[R][S];
+  bool all_small = true;
+  #pragma unroll
+  for (int r = 0; r < R; ++r)
+  {
+    double lv[S], rv[S];
+    load_vec<S>(L + r * S, lv);
+    load_vec<S>(Rc + r * S, rv);
+    #pragma unroll
+    for (int i = 0; i < S; ++i)
+    {
+      double ta = 0.0, tb = 0.0;
+      #pragma unroll
+      for (int j = 0; j < S; ++j)
+      {
+        ta += Pl[(r * S + i) * S + j] * lv[j];
+        tb += Pr[(r * S + i) * S + j] * rv[j];
+      }
+      res[r][i] = ta * tb;
+      all_small = all_small && (res[r][i] < EPA_SCALE_THRESHOLD);
+    }
+  }
+  uint32_t sc = tree.scaler[(size_t) op.left * n + site] + tree.scaler[(size_t) op.right * n + site];
+  const bool scale = all_small && !op.tip_tip;
+  if (scale) sc += 1;
+  #pragma unroll
+  for (int r = 0; r < R; ++r)
+  {
+    if (scale)
+    {
+      #pragma unroll
+      for (int i = 0; i < S; ++i) res[r][i] *= EPA_SCALE_FACTOR;
+    }
+    store_vec<S>(out + r * S, res[r]);
+  }
+  tree.scaler[(size_t) op.parent * n + site] = sc;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Column table of the lookup build: M[r][c][i] = pi_i * sum_{j in colmask[c]} Ppend[r][i][j].
+// One block; Ppend = P(-ln 0.9) is pmats[pend_index].
+// ---------------------------------------------------------------------------------------------
+template <int S>
+__global__ void lookup_coltable_kernel(const DevModel * __restrict__ m, const double * __restrict__ ppend,
+                                       double * __restrict__ M)
+{
+  const int R = m->R, K = m->K;
+  for (int idx = threadIdx.x; idx < R * K * S; idx += blockDim.x)
+  {
+    const int r = idx / (K * S), c = (idx / S) % K, i = idx % S;
+    const uint32_t mask = m->colmask[c];
+    double termb = 0.0;
+    #pragma unroll
+    for (int j = 0; j < S; ++j)
+      if ((mask >> j) & 1u) termb += ppend[(r * S + i) * S + j];
+    M[idx] = m->freqs[i] * termb;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Per-edge lookup table, one thread per site (generic path; any S, any compiled R).
+//   inner[r][i] = (P(len/2) D)[r][i] * (P(len/2) X)[r][i]          (+ per-site scaling)
+//   lookup[e][s][c] = log( sum_r w_r sum_i inner[r][i] M[r][c][i] ) + scaler * log(2^-256)
+// Column c with colmask 0 is the zero column (preplacement reads it for out-of-range sites).
+// grid = (n_edges, ceil(n/blockDim)); dynamic smem = (R*S*S + R*K*S) doubles.
+// ---------------------------------------------------------------------------------------------
+template <int S, int R>
+__global__ void __launch_bounds__(128)
+lookup_build_kernel(const DevModel * __restrict__ m, DevTree tree, int n, int n_pad, int K,
+                    const EdgeDev * __restrict__ edges, const double * __restrict__ pmats_half,
+                    const double * __restrict__ coltab, double * __restrict__ lookup)
+{
+  extern __shared__ double smem[];
+  double * P = smem;                    // [R][S][S]
+  double * M = smem + R * S * S;        // [R][K][S]
+  const EdgeDev e = edges[blockIdx.x];
+  stage_doubles(P, pmats_half + (size_t) blockIdx.x * R * S * S, R * S * S);
+  stage_doubles(M, coltab, R * K * S);
+  __syncthreads();
+  const int site = blockIdx.y * blockDim.x + threadIdx.x;
+  if (site >= n) return;
+
+  const double * D = tree.clv + e.distal * tree.clv_stride + (size_t) site * (R * S);
+  const double * X = tree.clv + e.proximal * tree.clv_stride + (size_t) site * (R * S);
+  double inner[R][S];
+  bool all_small = true;
+  #pragma unroll
+  for (int r = 0; r < R; ++r)
+  {
+    double dv[S], xv[S];
+    load_vec<S>(D + r * S, dv);
+    load_vec<S>(X + r * S, xv);
+    #pragma unroll
+    for (int i = 0; i < S; ++i)
+    {
+      double ta = 0.0, tb = 0.0;
+      #pragma unroll
+      for (int j = 0; j < S; ++j)
+      {
+        ta += P[(r * S + i) * S + j] * dv[j];
+        tb += P[(r * S + i) * S + j] * xv[j];
+      }
+      inner[r][i] = ta * tb;
+      all_small = all_small && (inner[r][i] < EPA_SCALE_THRESHOLD);
+    }
+  }
+  uint32_t sc = tree.scaler[(size_t) e.distal * n + site] + tree.scaler[(size_t) e.proximal * n + site];
+  if (all_small)
+  {
+    sc += 1;
+    #pragma unroll
+    for (int r = 0; r < R; ++r)
+      #pragma unroll
+      for (int i = 0; i < S; ++i) inner[r][i] *= EPA_SCALE_FACTOR;
+  }
+  const double scale_term = sc ? (double) sc * EPA_LOG_SCALE_THRESHOLD : 0.0;
+  double wr[R];
+  #pragma unroll
+  for (int r = 0; r < R; ++r) wr[r] = m->weights[r];
+
+  double * out = lookup + ((size_t) blockIdx.x * n_pad + site) * K;
+  for (int c = 0; c < K; ++c)
+  {
+    double v = 0.0;
+    if (m->colmask[c] != 0)
+    {
+      double terma = 0.0;
+      #pragma unroll
+      for (int r = 0; r < R; ++r)
+      {
+        double tr = 0.0;
+        #pragma unroll
+        for (int i = 0; i < S; ++i) tr += inner[r][i] * M[(r * K + c) * S + i];
+        terma += tr * wr[r];
+      }
+      v = log(terma) + scale_term;
+    }
+    out[c] = v;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// DNA fast path of the lookup build (S = 4, R = 4, K = 16): four lanes per site, lane = rate.
+// Every lane loads one 32-byte sector of each CLV (a warp covers 1 KB contiguous per CLV), the
+// rate sum and the scaling decision run over 2 xor-shuffles, and each lane finishes 4 of the 16
+// columns (log + 32-byte store; the four lanes of a site write one 128-byte line).
+// grid = (n_edges, ceil(n / 64)), block = 256 threads = 64 sites.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+lookup_build_dna_kernel(const DevModel * __restrict__ m, DevTree tree, int n, int n_pad,
+                        const EdgeDev * __restrict__ edges, const double * __restrict__ pmats_half,
+                        const double * __restrict__ coltab, double * __restrict__ lookup)
+{
+  constexpr int S = 4, R = 4, K = 16;
+  __shared__ double P[R * S * S];
+  __shared__ double M[R * K * S];
+  const EdgeDev e = edges[blockIdx.x];
+  stage_doubles(P, pmats_half + (size_t) blockIdx.x * R * S * S, R * S * S);
+  stage_doubles(M, coltab, R * K * S);
+  __syncthreads();
+  const int r = threadIdx.x & 3;
+  const int site = blockIdx.y * 64 + (threadIdx.x >> 2);
+  const bool active = site < n;
+  const int s = active ? site : n - 1;
+
+  double dv[S], xv[S], inner[S];
+  load_vec<S>(tree.clv + e.distal * tree.clv_stride + (size_t) s * (R * S) + r * S, dv);
+  load_vec<S>(tree.clv + e.proximal * tree.clv_stride + (size_t) s * (R * S) + r * S, xv);
+  bool small = true;
+  #pragma unroll
+  for (int i = 0; i < S; ++i)
+  {
+    double ta = 0.0, tb = 0.0;
+    #pragma unroll
+    for (int j = 0; j < S; ++j)
+    {
+      ta += P[(r * S + i) * S + j] * dv[j];
+      tb += P[(r * S + i) * S + j] * xv[j];
+    }
+    inner[i] = ta * tb;
+    small = small && (inner[i] < EPA_SCALE_THRESHOLD);
+  }
+  // all 16 entries of the site below the threshold? (lanes 4k..4k+3 hold one site)
+  const unsigned ballot = __ballot_sync(0xffffffffu, small);
+  const unsigned grp = (ballot >> ((threadIdx.x & 31) & ~3)) & 0xfu;
+  uint32_t sc = 0;
+  if (r == 0)
+    sc = tree.scaler[(size_t) e.distal * n + s] + tree.scaler[(size_t) e.proximal * n + s];
+  sc = __shfl_sync(0xffffffffu, sc, (threadIdx.x & 31) & ~3);
+  if (grp == 0xfu)
+  {
+    sc += 1;
+    #pragma unroll
+    for (int i = 0; i < S; ++i) inner[i] *= EPA_SCALE_FACTOR;
+  }
+  const double scale_term = sc ? (double) sc * EPA_LOG_SCALE_THRESHOLD : 0.0;
+  const double w = m->weights[r];
+
+  // per-rate contribution of every column, then sum over the four rate lanes (fixed order)
+  double mine[4];
+  #pragma unroll
+  for (int c = 0; c < K; ++c)
+  {
+    double tr = 0.0;
+    #pragma unroll
+    for (int i = 0; i < S; ++i) tr += inner[i] * M[(r * K + c) * S + i];
+    tr *= w;
+    tr += __shfl_xor_sync(0xffffffffu, tr, 1);
+    tr += __shfl_xor_sync(0xffffffffu, tr, 2);
+    if ((c >> 2) == r) mine[c & 3] = tr;      // lane r finishes columns 4r..4r+3
+  }
+  double res[4];
+  #pragma unroll
+  for (int k = 0; k < 4; ++k)
+    res[k] = (r == 0 && k == 0) ? 0.0 : log(mine[k]) + scale_term;   // column 0 = zero column
+  if (active)
+    store_vec<4>(lookup + ((size_t) blockIdx.x * n_pad + site) * K + r * 4, res);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Log-likelihood of the reference tree evaluated across one edge (inspection / tests):
+// per-block partial sums, summed on the host in block order.
+// ---------------------------------------------------------------------------------------------
+template <int S, int R>
+__global__ void __launch_bounds__(128)
+edge_logl_kernel(const DevModel * __restrict__ m, DevTree tree, int n, EdgeDev e,
+                 const double * __restrict__ pmat, double * __restrict__ partial)
+{
+  extern __shared__ double smem[];
+  double * P = smem;
+  __shared__ double red[128];
+  stage_doubles(P, pmat, R * S * S);
+  __syncthreads();
+  const int site = blockIdx.x * blockDim.x + threadIdx.x;
+  double lk = 0.0;
+  if (site < n)
+  {
+    const double * A = tree.clv + e.distal * tree.clv_stride + (size_t) site * (R * S);
+    const double * B = tree.clv + e.proximal * tree.clv_stride + (size_t) site * (R * S);
+    double terma = 0.0;
+    #pragma unroll
+    for (int r = 0; r < R; ++r)
+    {
+      double av[S], bv[S];
+      load_vec<S>(A + r * S, av);
+      load_vec<S>(B + r * S, bv);
+      double tr = 0.0;
+      #pragma unroll
+      for (int i = 0; i < S; ++i)
+      {
+        double tb = 0.0;
+        #pragma unroll
+        for (int j = 0; j < S; ++j) tb += P[(r * S + i) * S + j] * bv[j];
+        tr += av[i] * m->freqs[i] * tb;
+      }
+      terma += tr * m->weights[r];
+    }
+    const uint32_t sc = tree.scaler[(size_t) e.distal * n + site] + tree.scaler[(size_t) e.proximal * n + site];
+    lk = log(terma) + (sc ? (double) sc * EPA_LOG_SCALE_THRESHOLD : 0.0);
+  }
+  red[threadIdx.x] = lk;
+  __syncthreads();
+  for (int o = 64; o > 0; o >>= 1)
+  {
+    if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) partial[blockIdx.x] = red[0];
+}
+
+}  // namespace epa

@@ -1,0 +1,347 @@
+// kernels_preplace.cuh - query ingest, preplacement (HOT LOOP A) and candidate selection.
+//
+// Reference behaviour restated (paths relative to /root/reference):
+//   valid range            src/util/Range.hpp:34-49  (only '-' trims)
+//   preplacement score     src/core/Lookup_Store.hpp:110-141, src/core/place.cpp:41-95
+//   LWR + candidate choice src/set_manipulators.cpp:43-69,90-113, src/core/heuristics.hpp:40-64
+#pragma once
+#include "common.cuh"
+
+namespace epa {
+
+// ---------------------------------------------------------------------------------------------
+// small generic helpers
+// ---------------------------------------------------------------------------------------------
+__global__ void histogram_kernel(const int * __restrict__ keys, uint32_t count, uint32_t * __restrict__ hist)
+{
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < count) atomicAdd(&hist[keys[i]], 1u);
+}
+
+// exclusive scan of `count` uint32 by ONE block of 1024 threads; out may alias in; total optional
+__global__ void __launch_bounds__(1024)
+exclusive_scan_kernel(const uint32_t * in, uint32_t * out, uint32_t count, uint64_t * total)
+{
+  __shared__ uint64_t part[1024];
+  const uint32_t per = (count + 1023u) / 1024u;
+  const uint32_t lo = min(count, threadIdx.x * per), hi = min(count, lo + per);
+  uint64_t s = 0;
+  for (uint32_t i = lo; i < hi; ++i) s += in[i];
+  part[threadIdx.x] = s;
+  __syncthreads();
+  // Hillis-Steele over 1024 partials
+  for (int o = 1; o < 1024; o <<= 1)
+  {
+    uint64_t v = (threadIdx.x >= (unsigned) o) ? part[threadIdx.x - o] : 0;
+    __syncthreads();
+    part[threadIdx.x] += v;
+    __syncthreads();
+  }
+  uint64_t run = threadIdx.x ? part[threadIdx.x - 1] : 0;
+  for (uint32_t i = lo; i < hi; ++i) { const uint32_t v = in[i]; out[i] = (uint32_t) run; run += v; }
+  if (total && threadIdx.x == 1023) *total = part[1023];
+}
+
+// perm[offset[key] + k] = i  (order inside one key is arbitrary)
+__global__ void scatter_by_key_kernel(const int * __restrict__ keys, uint32_t count,
+                                      uint32_t * __restrict__ cursor, uint32_t * __restrict__ perm)
+{
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < count) perm[atomicAdd(&cursor[keys[i]], 1u)] = i;
+}
+
+// ---------------------------------------------------------------------------------------------
+// ASCII -> codes, valid range. One warp per query.
+// err[0] = status (0 ok, 1 invalid character, 2 all-gap query), err[1] = first offending query + 1,
+// err[3] = longest valid range of the chunk
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+encode_queries_kernel(const DevModel * __restrict__ m, const uint8_t * __restrict__ raw, uint32_t nq, int n,
+                      int premask, uint8_t * __restrict__ codes, int * __restrict__ begin,
+                      int * __restrict__ span, int * __restrict__ err)
+{
+  __shared__ uint8_t a2c[256];
+  a2c[threadIdx.x] = m->ascii2code[threadIdx.x];
+  __syncthreads();
+  const uint32_t q = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (q >= nq) return;
+  const uint8_t * row = raw + (size_t) q * n;
+  uint8_t * crow = codes + (size_t) q * n;
+  int lo = n, hi = -1;
+  bool bad = false;
+  for (int s = lane; s < n; s += 32)
+  {
+    const uint8_t ch = row[s];
+    const uint8_t c = a2c[ch];
+    bad = bad || (c == 255);
+    crow[s] = c;
+    if (ch != '-') { lo = min(lo, s); hi = max(hi, s); }
+  }
+  #pragma unroll
+  for (int o = 16; o > 0; o >>= 1)
+  {
+    lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+    hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+  }
+  bad = __any_sync(0xffffffffu, bad);
+  if (lane == 0)
+  {
+    int b = 0, w = n;
+    if (premask) { b = (hi < 0) ? 0 : lo; w = (hi < 0) ? 0 : hi - lo + 1; }
+    begin[q] = b;
+    span[q] = w;
+    atomicMax(&err[3], w);
+    if (bad) { if (atomicCAS(&err[0], 0, 1) == 0) err[1] = (int) q + 1; }
+    else if (hi < 0) { if (atomicCAS(&err[0], 0, 2) == 0) err[1] = (int) q + 1; }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Site range covered by each tile of TQ (begin-sorted) queries. One warp per tile.
+// range[t] = (lo rounded down to 4, hi); maxw = max over tiles of the 4-aligned width.
+// ---------------------------------------------------------------------------------------------
+__global__ void tile_range_kernel(const uint32_t * __restrict__ perm, const int * __restrict__ begin,
+                                  const int * __restrict__ span, uint32_t nq, int tq, uint32_t n_tiles,
+                                  int2 * __restrict__ range, int * __restrict__ maxw)
+{
+  const uint32_t t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (t >= n_tiles) return;
+  int lo = INT_MAX, hi = 0;
+  for (uint32_t k = lane; k < (uint32_t) tq; k += 32)
+  {
+    const uint32_t idx = t * tq + k;
+    if (idx < nq)
+    {
+      const uint32_t q = perm[idx];
+      const int b = begin[q], w = span[q];
+      if (w > 0) { lo = min(lo, b); hi = max(hi, b + w); }
+    }
+  }
+  #pragma unroll
+  for (int o = 16; o > 0; o >>= 1)
+  {
+    lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+    hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+  }
+  if (lane == 0)
+  {
+    if (hi == 0) lo = 0;
+    lo &= ~3;
+    range[t] = make_int2(lo, hi);
+    atomicMax(maxw, ((hi - lo) + 3) & ~3);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// HOT LOOP A. One CTA = one tile of TQ begin-sorted queries (thread = query) x ALL edges.
+//   pre[q][b] = sum_{s in [begin_q, begin_q+span_q)} lookup[b][s][col(q_s)]
+// The tile's column indices are staged once in shared memory (4 sites per 32-bit word, already
+// multiplied by 8; out-of-range sites point at the zero column), then the CTA streams the
+// [lo,hi) slice of every edge's table through an NS-deep TMA (cp.async.bulk) ring.
+// Four accumulators keyed by the ABSOLUTE site index mod 4 make the result independent of how
+// the tiles were cut. Tiles wider than `wc` sites run in several chunks (read-modify-write).
+// lookup layout: [edge][n_pad][K] doubles, n_pad = n rounded up to 4, pad rows zero.
+// dynamic smem: NS*wc*K*8 (stages, 128-byte aligned) + (wc/4)*TQ*4 (codes) + NS*8 (barriers)
+// ---------------------------------------------------------------------------------------------
+template <int K, int TQ, int NS>
+__global__ void __launch_bounds__(TQ)
+preplace_kernel(const DevModel * __restrict__ m, const double * __restrict__ lookup, int n, int n_pad,
+                uint32_t n_edges, const uint8_t * __restrict__ codes, const int * __restrict__ begin,
+                const int * __restrict__ span, const uint32_t * __restrict__ perm, uint32_t nq,
+                const int2 * __restrict__ range, int wc, double * __restrict__ pre, size_t pre_stride)
+{
+  extern __shared__ __align__(128) uint8_t smem_raw[];
+  double * stage = reinterpret_cast<double *>(smem_raw);                         // [NS][wc*K]
+  uint32_t * cw = reinterpret_cast<uint32_t *>(smem_raw + (size_t) NS * wc * K * 8);   // [wc/4][TQ]
+  uint64_t * bars = reinterpret_cast<uint64_t *>(cw + (size_t) (wc / 4) * TQ);
+  __shared__ uint8_t c2c[MAX_CODES];
+  __shared__ uint32_t tq_q[TQ];
+  __shared__ int tq_b[TQ], tq_e[TQ];
+
+  const int tid = threadIdx.x;
+  if (tid < MAX_CODES) c2c[tid] = m->code2col[tid];
+  const uint32_t slot = blockIdx.x * TQ + tid;
+  const bool valid = slot < nq;
+  const uint32_t q = valid ? perm[slot] : 0;
+  {
+    const int b = valid ? begin[q] : 0, w = valid ? span[q] : 0;
+    tq_q[tid] = q; tq_b[tid] = b; tq_e[tid] = b + w;
+  }
+  if (tid == 0)
+  {
+    for (int s = 0; s < NS; ++s) mbar_init(&bars[s], 1);
+    mbar_fence_init();
+  }
+  __syncthreads();
+
+  const int2 rg = range[blockIdx.x];
+  const int lo = rg.x, hi = rg.y;
+  uint32_t it = 0;                                  // running stage counter (ring position + parity)
+  double * out = pre + (size_t) q * pre_stride;
+
+  for (int c0 = lo; c0 < hi; c0 += wc)
+  {
+    const int w4 = (min(wc, hi - c0) + 3) >> 2;     // words (4 sites each) in this chunk
+    const uint32_t bytes = (uint32_t) w4 * 4u * K * 8u;
+    // ---- stage the tile's column indices: word (j, t) covers sites c0+4j .. c0+4j+3 of query t
+    for (int idx = tid; idx < w4 * TQ; idx += TQ)
+    {
+      const int t = idx / w4, j = idx - t * w4;
+      const int b = tq_b[t], e = tq_e[t];
+      const uint8_t * crow = codes + (size_t) tq_q[t] * n;
+      uint32_t word = 0;
+      #pragma unroll
+      for (int k = 0; k < 4; ++k)
+      {
+        const int s = c0 + 4 * j + k;
+        uint32_t col8 = 0;
+        if (s >= b && s < e) col8 = (uint32_t) c2c[crow[s] & (MAX_CODES - 1)] * 8u;
+        word |= col8 << (8 * k);
+      }
+      cw[(size_t) j * TQ + t] = word;
+    }
+    __syncthreads();
+    const bool first = (c0 == lo);
+    const double * src0 = lookup + (size_t) c0 * K;
+    const size_t edge_stride = (size_t) n_pad * K;
+    if (tid == 0)
+    {
+      for (uint32_t p = 0; p < (uint32_t) (NS - 1) && p < n_edges; ++p)
+      {
+        const uint32_t st = (it + p) % NS;
+        mbar_expect_tx(&bars[st], bytes);
+        bulk_g2s(stage + (size_t) st * wc * K, src0 + p * edge_stride, bytes, &bars[st]);
+      }
+    }
+    for (uint32_t b = 0; b < n_edges; ++b, ++it)
+    {
+      if (tid == 0 && b + NS - 1 < n_edges)
+      {
+        const uint32_t st = (it + NS - 1) % NS;
+        mbar_expect_tx(&bars[st], bytes);
+        bulk_g2s(stage + (size_t) st * wc * K, src0 + (size_t) (b + NS - 1) * edge_stride, bytes, &bars[st]);
+      }
+      const uint32_t st = it % NS;
+      mbar_wait(&bars[st], (it / NS) & 1u);
+      const uint8_t * T = reinterpret_cast<const uint8_t *>(stage + (size_t) st * wc * K);
+      double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+      #pragma unroll 2
+      for (int j = 0; j < w4; ++j)
+      {
+        const uint32_t word = cw[(size_t) j * TQ + tid];
+        const uint8_t * row = T + (size_t) j * (4 * K * 8);
+        a0 += *reinterpret_cast<const double *>(row + (word & 0xffu));
+        a1 += *reinterpret_cast<const double *>(row + K * 8 + ((word >> 8) & 0xffu));
+        a2 += *reinterpret_cast<const double *>(row + 2 * K * 8 + ((word >> 16) & 0xffu));
+        a3 += *reinterpret_cast<const double *>(row + 3 * K * 8 + (word >> 24));
+      }
+      const double sum = (a0 + a1) + (a2 + a3);
+      if (valid)
+      {
+        if (first) out[b] = sum;
+        else out[b] += sum;
+      }
+      __syncthreads();                              // stage st may be refilled from now on
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Candidate selection, dynamic heuristic (accumulated LWR threshold). One warp per query.
+// Order: LWR descending, ties by lower edge index. Elements are taken while the running LWR sum
+// is still below the threshold (the element that crosses it is included).
+// Pass 1 (count): cnt[q], cut_v[q], cut_i[q] = the last element taken.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ bool ranks_before(double v, int i, double pv, int pi)
+{
+  // (v,i) strictly before (pv,pi) in (value desc, index asc) order
+  return (v > pv) || (v == pv && i < pi);
+}
+
+__global__ void __launch_bounds__(256)
+select_count_kernel(const double * __restrict__ pre, size_t pre_stride, int n_edges, uint32_t nq,
+                    double thresh, uint32_t * __restrict__ cnt, double * __restrict__ cut_v,
+                    int * __restrict__ cut_i)
+{
+  const uint32_t q = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (q >= nq) return;
+  const double * row = pre + (size_t) q * pre_stride;
+  double mx = -INFINITY;
+  for (int b = lane; b < n_edges; b += 32) mx = fmax(mx, row[b]);
+  mx = warp_max(mx);
+  double tot = 0.0;
+  for (int b = lane; b < n_edges; b += 32) tot += exp(row[b] - mx);
+  tot = warp_sum(tot);
+
+  double pv = INFINITY; int pi = -1;
+  double acc = 0.0;
+  uint32_t c = 0;
+  while (acc < thresh && c < (uint32_t) n_edges)
+  {
+    double bv = -INFINITY; int bi = INT_MAX;
+    for (int b = lane; b < n_edges; b += 32)
+    {
+      const double v = row[b];
+      if (ranks_before(pv, pi, v, b) && ranks_before(v, b, bv, bi)) { bv = v; bi = b; }
+    }
+    #pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+    {
+      const double ov = __shfl_xor_sync(0xffffffffu, bv, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      if (ranks_before(ov, oi, bv, bi)) { bv = ov; bi = oi; }
+    }
+    if (bi == INT_MAX) break;                       // nothing left (NaNs)
+    acc += exp(bv - mx) / tot;
+    pv = bv; pi = bi;
+    ++c;
+  }
+  if (lane == 0) { cnt[q] = c; cut_v[q] = pv; cut_i[q] = pi; }
+}
+
+// Pass 2 (fill): pair list in query-major order, edges ascending inside a query.
+__global__ void __launch_bounds__(256)
+select_fill_kernel(const double * __restrict__ pre, size_t pre_stride, int n_edges, uint32_t nq,
+                   const uint32_t * __restrict__ off, const double * __restrict__ cut_v,
+                   const int * __restrict__ cut_i, uint32_t * __restrict__ pair_q,
+                   uint32_t * __restrict__ pair_e, uint32_t * __restrict__ edge_hist)
+{
+  const uint32_t q = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (q >= nq) return;
+  const double * row = pre + (size_t) q * pre_stride;
+  const double cv = cut_v[q]; const int ci = cut_i[q];
+  uint32_t o = off[q];
+  for (int base = 0; base < n_edges; base += 32)
+  {
+    const int b = base + lane;
+    bool sel = false;
+    if (b < n_edges)
+    {
+      const double v = row[b];
+      sel = (v > cv) || (v == cv && b <= ci);
+    }
+    const unsigned mask = __ballot_sync(0xffffffffu, sel);
+    if (sel)
+    {
+      const uint32_t p = o + __popc(mask & ((1u << lane) - 1u));
+      pair_q[p] = q;
+      pair_e[p] = (uint32_t) b;
+      atomicAdd(&edge_hist[b], 1u);
+    }
+    o += __popc(mask);
+  }
+}
+
+// work[edge_off[e] + k] = pair id (edge-major work list so that concurrent warps share CLVs)
+__global__ void work_scatter_kernel(const uint32_t * __restrict__ pair_e, uint32_t n_pairs,
+                                    uint32_t * __restrict__ cursor, uint32_t * __restrict__ work)
+{
+  const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p < n_pairs) work[atomicAdd(&cursor[pair_e[p]], 1u)] = p;
+}
+
+}  // namespace epa

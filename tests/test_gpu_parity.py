@@ -1,0 +1,228 @@
+"""GPU parity tests: every stage of the CUDA path, called through the C ABI (capi.py), against the
+CPU oracle on the same inputs, and the end result against the reference's recorded placements.
+
+Tolerances (floating point, north_star): log-likelihoods 1e-6 relative (we check much tighter
+where the arithmetic is a straight restatement), LWR 1e-6 absolute, branch lengths 1e-4 absolute,
+identical edge rankings.
+"""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import helpers
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def cfg1(built):
+    case = helpers.cfg1_case()
+    ctx = helpers.make_context(case)
+    ctx.build_lookup()
+    yield case, ctx
+    ctx.close()
+
+
+@pytest.fixture(scope="module")
+def synth64(built):
+    case = helpers.synth64_case()
+    ctx = helpers.make_context(case)
+    ctx.build_lookup()
+    case.placer.build_lookup()
+    yield case, ctx
+    ctx.close()
+
+
+def _check_clvs(case, ctx):
+    T = len(case.tree.tips)
+    for uid, side in case.ref.sides.items():
+        node = ctx.ids[uid]
+        clv, sc = ctx.get_clv(node)
+        if node < T:
+            S, R = case.model.states, case.model.rate_cats
+            want = ((side.tip[:, None] >> np.arange(S)[None, :]) & 1).astype(float)
+            assert np.array_equal(clv.reshape(case.n, R, S), np.repeat(want[:, None, :], R, axis=1))
+            assert not sc.any()
+        else:
+            assert np.allclose(clv, side.clv, rtol=1e-12, atol=0), f"clv of node {node}"
+            assert np.array_equal(sc, side.scaler)
+
+
+def test_clv_precompute_matches_oracle(cfg1):
+    _check_clvs(*cfg1)
+
+
+def test_clv_precompute_matches_oracle_synth(synth64):
+    _check_clvs(*synth64)
+
+
+def test_tree_logl_equal_on_every_edge(synth64):
+    case, ctx = synth64
+    want = case.ref.tree_logl(0)
+    vals = [ctx.edge_loglikelihood(e) for e in range(case.tree.num_branches)]
+    assert np.allclose(vals, want, rtol=1e-11, atol=0)
+
+
+def _check_lookup(case, ctx):
+    o = helpers.oracle()
+    lk = case.placer.lookup if case.placer.lookup is not None else case.placer.build_lookup()
+    for e in range(case.tree.num_branches):
+        got = ctx.get_lookup(e)
+        assert np.allclose(got, lk[e], rtol=1e-11, atol=1e-11), f"lookup of edge {e}"
+
+
+def test_lookup_matches_oracle(cfg1):
+    _check_lookup(*cfg1)
+
+
+def test_lookup_matches_oracle_synth(synth64):
+    _check_lookup(*synth64)
+
+
+def _check_preplace(case, ctx):
+    ctx.upload_queries(case.query_rows)
+    ctx.preplace()
+    got = ctx.get_prescores()
+    want = np.stack([case.placer.preplace(s) for s in case.qseqs])
+    assert np.allclose(got, want, rtol=1e-12, atol=0)
+    return got, want
+
+
+def test_preplace_matches_oracle(cfg1):
+    _check_preplace(*cfg1)
+
+
+def test_preplace_select_matches_oracle_synth(synth64, built):
+    case, ctx = synth64
+    got, want = _check_preplace(case, ctx)
+    opts = built.capi.default_options()
+    n_pairs = ctx.select(opts)
+    q, e, _ = ctx.get_pairs(raw=False)
+    assert len(q) == n_pairs
+    mine = {}
+    for qi, ei in zip(q, e):
+        mine.setdefault(int(qi), set()).add(int(ei))
+    for qi in range(len(case.qseqs)):
+        assert mine[qi] == set(case.placer.candidates(want[qi])), f"candidates of query {qi}"
+
+
+def test_thorough_all_pairs_matches_oracle(cfg1, built):
+    case, ctx = cfg1
+    opts = built.capi.default_options(prescoring=0)
+    ctx.upload_queries(case.query_rows)
+    n_pairs = ctx.select(opts)
+    assert n_pairs == len(case.qseqs) * case.tree.num_branches
+    ctx.place_pairs(opts)
+    q, e, raw = ctx.get_pairs()
+    for qi, ei, r in zip(q, e, raw):
+        p = case.placer.thorough(case.qseqs[qi], int(ei))
+        assert abs(r["likelihood"] - p.logl) <= 1e-9 * abs(p.logl), (qi, ei, r, p)
+        assert abs(r["pendant_length"] - p.pendant) <= 1e-6, (qi, ei, r, p)
+        assert abs(r["distal_length"] - p.distal) <= 1e-6, (qi, ei, r, p)
+
+
+def test_thorough_candidates_match_oracle_synth(synth64, built):
+    case, ctx = synth64
+    opts = built.capi.default_options()
+    ctx.upload_queries(case.query_rows)
+    ctx.preplace()
+    ctx.select(opts)
+    ctx.place_pairs(opts)
+    q, e, raw = ctx.get_pairs()
+    worst = 0.0
+    for qi, ei, r in zip(q, e, raw):
+        p = case.placer.thorough(case.qseqs[qi], int(ei))
+        assert abs(r["likelihood"] - p.logl) <= 1e-8 * abs(p.logl), (qi, ei, r, p)
+        assert abs(r["pendant_length"] - p.pendant) <= 1e-5, (qi, ei, r, p)
+        assert abs(r["distal_length"] - p.distal) <= 1e-5, (qi, ei, r, p)
+        worst = max(worst, abs(r["likelihood"] - p.logl) / abs(p.logl))
+    print("worst relative logl difference", worst)
+
+
+@pytest.mark.parametrize("mname,model", [("gtrg", helpers.GTRG), ("gtrb", helpers.GTR_B)])
+def test_cfg1_placements_match_reference(built, mname, model):
+    gold = helpers.golden("cfg1")
+    case = helpers.cfg1_case(model)
+    ctx = helpers.make_context(case)
+    runs = {
+        "default": dict(),
+        "noheur_all": dict(prescoring=0, support_threshold=0.0, filter_max=13),
+        "heur_all": dict(support_threshold=0.0, filter_max=13),
+        "acc": dict(filter_acc_lwr=1, support_threshold=0.999, filter_max=5),
+    }
+    for rname, kw in runs.items():
+        opts = built.capi.default_options(**kw)
+        out, counts = ctx.place_chunk(case.query_rows, opts)
+        got = dict(zip(case.qnames, helpers.records_to_lists(out, counts)))
+        want = gold[f"{mname}_{rname}"]["placements"]
+        for name in want:
+            helpers.assert_placements_close(got[name], want[name], f"{mname}/{rname}/{name}")
+    ctx.close()
+
+
+def test_synth64_placements_match_reference(synth64, built):
+    case, ctx = synth64
+    gold = helpers.golden("synth64")["default"]["placements"]
+    out, counts = ctx.place_chunk(case.query_rows, built.capi.default_options())
+    got = dict(zip(case.qnames, helpers.records_to_lists(out, counts)))
+    bad = []
+    for name in gold:
+        try:
+            helpers.assert_placements_close(got[name], gold[name], name)
+        except AssertionError as e:
+            bad.append(str(e))
+    assert not bad, f"{len(bad)} of {len(gold)} queries differ from the reference: {bad[:3]}"
+
+
+def test_uploaded_clvs_equal_computed(cfg1, built):
+    # drop-in for Tree::get_clv: host-owned CLVs (here the oracle's) handed over unchanged
+    case, ctx0 = cfg1
+    ctx = helpers.make_context(case, compute=False)
+    T = len(case.tree.tips)
+    ctx.upload_clvs([(ctx.ids[uid], s.clv, s.scaler) for uid, s in case.ref.sides.items() if ctx.ids[uid] >= T])
+    out, counts = ctx.place_chunk(case.query_rows, built.capi.default_options())
+    out0, counts0 = ctx0.place_chunk(case.query_rows, built.capi.default_options())
+    assert np.array_equal(counts, counts0)
+    a, b = helpers.records_to_lists(out, counts), helpers.records_to_lists(out0, counts0)
+    for x, y in zip(a, b):
+        helpers.assert_placements_close(x, y, "uploaded vs computed", logl_rel=1e-10, lwr_abs=1e-9, len_abs=1e-7)
+    ctx.close()
+
+
+def test_edge_cases(synth64, built):
+    case, ctx = synth64
+    capi = built.capi
+    opts = capi.default_options()
+    # empty chunk
+    out, counts = ctx.place_chunk(np.zeros((0, case.n), dtype=np.uint8), opts)
+    assert out.shape[0] == 0
+    # invalid character and all-gap query are errors (Tiny_Tree.cpp:145-156)
+    rows = case.query_rows[:3].copy()
+    rows[1, 10] = ord('!')
+    with pytest.raises(capi.EpaError) as ei:
+        ctx.place_chunk(rows, opts)
+    assert ei.value.code == capi.EPA_ERR_QUERY and "query 1" in str(ei.value)
+    rows = case.query_rows[:3].copy()
+    rows[2, :] = ord('-')
+    with pytest.raises(capi.EpaError) as ei:
+        ctx.place_chunk(rows, opts)
+    assert ei.value.code == capi.EPA_ERR_QUERY and "query 2" in str(ei.value)
+    # ragged windows: one site, full width, lower case, ambiguity codes
+    rows = np.full((4, case.n), ord('-'), dtype=np.uint8)
+    rows[0, 17] = ord('A')
+    rows[1, :] = np.frombuffer(case.qseqs[0].replace('-', 'N').lower().encode(), dtype=np.uint8)
+    rows[2, 5:60] = np.frombuffer(("ACGTRYKMSWBDHVN" * 4)[:55].encode(), dtype=np.uint8)
+    rows[3, case.n - 40:] = np.frombuffer(case.qseqs[1].replace('-', 'A')[:40].encode(), dtype=np.uint8)
+    out, counts = ctx.place_chunk(rows, opts)
+    got = helpers.records_to_lists(out, counts)
+    for qi in range(4):
+        want = case.placer.place(bytes(rows[qi]).decode().upper())
+        helpers.assert_placements_close(got[qi], [(p.edge, p.logl, p.lwr, p.distal, p.pendant) for p in want],
+                                        f"ragged query {qi}")
+    # state machine
+    ctx2 = helpers.make_context(case, compute=False)
+    with pytest.raises(capi.EpaError) as ei:
+        ctx2.build_lookup()
+    assert ei.value.code == capi.EPA_ERR_STATE
+    ctx2.close()
