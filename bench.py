@@ -1,0 +1,366 @@
+#!/usr/bin/env python
+"""bench.py - query-seqs/s placed on the BASELINE.json cfg2 workload (1k-taxon DNA tree, GTR+G4,
+1000-site MSA, 200-bp window queries, default heuristic), one process per GPU.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--queries Q] [--impl ours|reference]
+
+A step = one pass of the whole hot path (encode -> preplacement -> candidate selection ->
+branch-length optimisation -> LWR/filter) over this rank's Q queries.
+  value  device-resident: the query chunk already lives in HBM when the timed region starts
+  e2e    through the host-layer C ABI (epa_session_place) from PINNED HOST buffers, H2D of the
+         queries and D2H of the placement records inside the timed region
+Timing: CUDA events on the stream the library launches on (the context is switched to torch's
+current stream), barrier + synchronize on both sides, max over ranks. Inputs (1 GB of queries,
+256 MB of lookup tables, 0.5 GB of CLVs per step) are far larger than the 126 MB L2.
+`--impl reference` times the UNMODIFIED reference binary (oracle/_ref/epa-ng, all host threads) on
+a bounded sample of the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import shutil
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+import __graft_entry__ as ge  # noqa: E402
+
+T_TAXA, N_SITES, WINDOW = 1000, 1000, 200
+METRIC = "query-seqs/sec placed (1k-taxon tree)"
+HBM_FALLBACK_GBS = 6650.0
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return HBM_FALLBACK_GBS, "fallback (B200_PROFILING.md)"
+
+
+# ------------------------------------------------------------------------------------------------
+#  reference CPU arm (also the cpu_baseline of our arm)
+# ------------------------------------------------------------------------------------------------
+def ref_binary():
+    return os.path.join(ROOT, "oracle", "_ref", "epa-ng")
+
+
+def run_reference_sample(ds, n_sample, threads, keep_jplace=False):
+    """Times the unmodified reference on the first n_sample queries. The fixed start-up cost
+    (file parsing, reference CLV precompute) is removed by subtracting a 64-query run."""
+    synth = ge.load_package().synth
+    tmp = tempfile.mkdtemp(prefix="epa_ref_")
+    try:
+        tf, sf, _ = synth.write_dataset(dict(ds, queries=ds["queries"][:1], qnames=ds["qnames"][:1]), tmp)
+
+        def run(nq, sub):
+            qf = os.path.join(tmp, f"q_{sub}.fasta")
+            synth.write_fasta(qf, ds["qnames"][:nq], ds["queries"][:nq])
+            out = os.path.join(tmp, sub)
+            os.makedirs(out, exist_ok=True)
+            cmd = [ref_binary(), "-t", tf, "-s", sf, "-q", qf, "-m", ds["model"], "-w", out, "-T", str(threads), "--redo"]
+            t0 = time.perf_counter()
+            subprocess.run(cmd, check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+            return time.perf_counter() - t0, os.path.join(out, "epa_result.jplace")
+
+        run(min(64, n_sample), "small")                      # page the binary and the files in
+        t_small, _ = run(min(64, n_sample), "small")
+        t_full, jp = run(n_sample, "full")
+        if t_full <= t_small:
+            t_small = 0.0
+        placements = None
+        if keep_jplace:
+            doc = json.load(open(jp))
+            placements = {n: pq["p"] for pq in doc["placements"] for n in pq["n"]}
+        dt = max(t_full - t_small, 1e-6)
+        return (n_sample - min(64, n_sample)) / dt, t_full, t_small, placements
+    finally:
+        shutil.rmtree(tmp, ignore_errors=True)
+
+
+def reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    if not os.path.exists(ref_binary()):
+        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/epa-ng not built (oracle/Makefile.ref)"}))
+        return
+    synth = ge.load_package().synth
+    cores = os.cpu_count() or 1
+    n_sample = args.ref_queries or int(min(200000, max(4000, 1500 * cores)))
+    ds = synth.dataset(T=T_TAXA, n_sites=N_SITES, n_queries=n_sample, window=WINDOW)
+    vals, times = [], []
+    for it in range(args.warmup + args.steps):
+        qps, t_full, t_small, _ = run_reference_sample(ds, n_sample, cores)
+        if it >= args.warmup:
+            vals.append(qps)
+            times.append(t_full)
+    v = float(np.median(vals))
+    sample = (f"first {n_sample} of the cfg2 queries, oracle/_ref/epa-ng -T {cores}, wall clock of the whole run minus "
+              f"a 64-query run (start-up removed); median of {len(vals)} runs")
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": v, "unit": "query-seqs/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 * float(np.median(times)),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload_config(n_sample, args.gpus),
+        "cpu_baseline": {"value": v, "unit": "query-seqs/s", "cores": cores, "kind": "reference", "sample": sample},
+        "e2e": {"value": v, "unit": "query-seqs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def workload_config(q_per_gpu, gpus):
+    return {"workload": "cfg2: 1k-taxon DNA tree (GTR+G4, 1000-site MSA), synthetic 200bp window queries, "
+                        "preplacement heuristic -g 0.99999",
+            "taxa": T_TAXA, "edges": 2 * T_TAXA - 3, "sites": N_SITES, "window": WINDOW,
+            "queries_per_gpu": q_per_gpu, "queries_total": q_per_gpu * gpus,
+            "sharding": f"queries block-sharded over {gpus} GPU(s), reference state replicated",
+            "l2": "inputs larger than L2 (no flush needed)"}
+
+
+# ------------------------------------------------------------------------------------------------
+#  clocks
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except subprocess.TimeoutExpired:
+                self.proc.kill()
+        sm = [float(r[0]) for r in self.rows if len(r) >= 6 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 6 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for k, n in enumerate(names) if any(len(r) >= 6 and r[2 + k].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------
+#  our arm
+# ------------------------------------------------------------------------------------------------
+def ours(args):
+    import torch
+    import torch.distributed as dist
+
+    pkg = ge.load_package()
+    capi, synth, session = pkg.capi, pkg.synth, pkg.session
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py (impl ours) needs a CUDA device: the product has no CPU path")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    Q = args.queries
+    ds = synth.dataset(T=T_TAXA, n_sites=N_SITES, n_queries=Q, window=WINDOW, seed_q=2 + rank)
+    sess = session.Session(ds["newick"], ds["names"], ds["ref"], ds["model"], device=local)
+    ctx = sess.ctx
+    stream = torch.cuda.current_stream()
+    ctx.set_stream(stream.cuda_stream)
+    opts = capi.default_options()
+    fmax = opts.filter_max
+    chunk = args.chunk
+    B, n = sess.n_edges, sess.sites
+
+    host_q = torch.from_numpy(ds["queries"]).pin_memory()
+    dev_q = host_q.to(dev)
+    rec_dev = torch.zeros((Q, fmax * 5), dtype=torch.float64, device=dev)       # 40-byte records
+    cnt_dev = torch.zeros(Q, dtype=torch.int32, device=dev)
+    rec_host = torch.zeros((Q, fmax * 5), dtype=torch.float64).pin_memory()
+    cnt_host = torch.zeros(Q, dtype=torch.int32).pin_memory()
+    gather_list = None
+    if world > 1 and rank == 0:
+        gather_list = [torch.zeros_like(rec_dev) for _ in range(world)]
+
+    stage_ms = {"upload_encode": 0.0, "preplace": 0.0, "select": 0.0, "thorough": 0.0, "collect": 0.0}
+    pairs_total = [0]
+
+    def step_resident(record=False):
+        for lo in range(0, Q, chunk):
+            nq = min(chunk, Q - lo)
+            ctx.encode_queries_dev(dev_q.data_ptr() + lo * n, nq, True)
+            ctx.preplace()
+            npairs = ctx.select(opts)
+            ctx.place_pairs(opts)
+            ctx.collect_dev(opts, rec_dev.data_ptr() + lo * fmax * 40, cnt_dev.data_ptr() + lo * 4)
+            if record:
+                for k, v in ctx.timings().items():
+                    stage_ms[k] += v
+                pairs_total[0] += npairs
+        if world > 1:
+            dist.gather(rec_dev, gather_list, dst=0)     # the single NCCL gather of placement records
+
+    def step_e2e():
+        sess.place((host_q.data_ptr(), Q), opts, chunk, out=rec_host.data_ptr(), counts=cnt_host.data_ptr())
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, **kw):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(steps):
+            fn(**kw)
+        e1.record(stream)
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    for _ in range(args.warmup):
+        step_resident()
+    sampler = ClockSampler(local)
+    sampler.start()
+    l0 = ctx.launch_count()
+    ms_res = timed(step_resident, args.steps, record=True)
+    launches = ctx.launch_count() - l0
+    clocks = sampler.stop()
+    for _ in range(min(args.warmup, 1)):
+        step_e2e()
+    ms_e2e = timed(step_e2e, args.steps)
+
+    # device-resident and host paths must agree bit for bit
+    same = bool(np.array_equal(rec_host.numpy()[: min(Q, 4096)], rec_dev[: min(Q, 4096)].cpu().numpy()))
+
+    if rank == 0:
+        total_q = Q * world
+        value = total_q * args.steps / (ms_res / 1e3)
+        e2e = total_q * args.steps / (ms_e2e / 1e3)
+        peak, peak_src = peaks()
+        pairs = pairs_total[0] / args.steps           # candidate pairs per step (this rank)
+        w = WINDOW
+        per_unit = {
+            "preplace": 9.0 * w,                                   # w lookup doubles + w query bytes per (query, edge)
+            "thorough": 2.0 * w * 4 * 4 * 8 + 2.0 * w * 4 + w + 40,   # two CLV windows + scalers + query + record
+        }
+        units = {"preplace": float(Q) * B, "thorough": pairs}
+        kernels = {}
+        for k in ("preplace", "thorough"):
+            ms = stage_ms[k] / args.steps
+            ach = units[k] * per_unit[k] / (ms / 1e3) / 1e9 if ms > 0 else 0.0
+            kernels[k] = {"ms_per_step": ms, "units_per_step": units[k], "bytes_per_unit": per_unit[k],
+                          "achieved_gbs": ach, "frac": ach / peak}
+        lk_ms = ctx.lookup_ms()
+        kernels["lookup_build"] = {"ms": lk_ms, "units": B, "bytes_per_unit": 392000.0,
+                                   "achieved_gbs": B * 392000.0 / (lk_ms / 1e3) / 1e9 if lk_ms > 0 else 0.0}
+        kernels["lookup_build"]["frac"] = kernels["lookup_build"]["achieved_gbs"] / peak
+        for k in ("upload_encode", "select", "collect"):
+            kernels[k] = {"ms_per_step": stage_ms[k] / args.steps}
+        dom = max(("preplace", "thorough"), key=lambda k: kernels[k]["ms_per_step"])
+        kname = {"preplace": "preplace_kernel", "thorough": "blo_dna_kernel"}[dom]
+        n_launch = max(1, (Q + chunk - 1) // chunk)
+        roofline = {"kernel": kname, "bound": "hbm", "achieved": kernels[dom]["achieved_gbs"], "peak": peak,
+                    "unit": "GB/s", "frac": kernels[dom]["frac"], "traffic": None, "peak_source": peak_src,
+                    "launch_ms": kernels[dom]["ms_per_step"] / n_launch,
+                    "algorithmic_bytes_per_launch": units[dom] * per_unit[dom] / n_launch}
+
+        cpu = None
+        parity = None
+        if world == 1 and not args.no_cpu and os.path.exists(ref_binary()):
+            cores = os.cpu_count() or 1
+            n_sample = int(min(Q, args.ref_queries or min(100000, max(2000, 1000 * cores))))
+            qps, t_full, t_small, ref_pl = run_reference_sample(ds, n_sample, cores, keep_jplace=True)
+            cpu = {"value": qps, "unit": "query-seqs/s", "cores": cores, "kind": "reference",
+                   "sample": f"first {n_sample} of this run's queries, oracle/_ref/epa-ng -T {cores}: {t_full:.2f}s wall "
+                             f"minus {t_small:.2f}s for a 64-query run (start-up removed)"}
+            parity = compare_with_reference(rec_host.numpy(), cnt_host.numpy(), ds["qnames"], ref_pl, fmax)
+
+        out = {
+            "metric": METRIC, "value": value, "unit": "query-seqs/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_res / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload_config(Q, world),
+            "e2e": {"value": e2e, "unit": "query-seqs/s", "ms_per_step": ms_e2e / args.steps,
+                    "h2d_bytes_per_step": int(Q) * n, "d2h_bytes_per_step": int(Q) * (fmax * 40 + 4)},
+            "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "kernels": kernels,
+            "candidate_pairs_per_query": pairs / Q, "chunk": chunk, "resident_equals_e2e": same,
+        }
+        if cpu:
+            out["cpu_baseline"] = cpu
+        if parity:
+            out["parity_vs_reference"] = parity
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+    sess.close()
+
+
+def compare_with_reference(recs, counts, names, ref_pl, fmax):
+    """Name-keyed comparison with the reference's jplace: identical ordered edge lists, logl rel
+    1e-6, LWR abs 1e-6, lengths abs 1e-4 (the north_star tolerances)."""
+    recs = recs.reshape(len(counts), fmax, 5)
+    n_cmp = n_edges = n_bad = 0
+    worst = 0.0
+    for qi, name in enumerate(names):
+        if name not in ref_pl:
+            continue
+        want = ref_pl[name]
+        c = int(counts[qi])
+        got = recs[qi, :c]
+        n_cmp += 1
+        edges = [int(np.float64(x).view(np.uint64)) for x in got[:, 0]]
+        if edges != [int(p[0]) for p in want]:
+            n_edges += 1
+            continue
+        for g, p in zip(got, want):
+            rel = abs(g[1] - p[1]) / abs(p[1])
+            worst = max(worst, rel)
+            if rel > 1e-6 or abs(g[2] - p[2]) > 1e-6 or abs(g[4] - p[3]) > 1e-4 or abs(g[3] - p[4]) > 1e-4:
+                n_bad += 1
+                break
+    return {"queries_compared": n_cmp, "edge_list_mismatches": n_edges, "value_mismatches": n_bad,
+            "worst_logl_rel": worst}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--queries", type=int, default=1000000, help="queries per GPU per step")
+    ap.add_argument("--chunk", type=int, default=131072)
+    ap.add_argument("--ref-queries", type=int, default=0, help="size of the CPU reference sample")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        reference_arm(args)
+    else:
+        ours(args)
+
+
+if __name__ == "__main__":
+    main()

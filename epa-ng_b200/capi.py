@@ -72,6 +72,8 @@ SYMBOLS = [
     ("epa_select", C.c_int, [_vp, C.POINTER(Options), C.POINTER(C.c_uint64)]),
     ("epa_place_pairs", C.c_int, [_vp, C.POINTER(Options)]),
     ("epa_collect", C.c_int, [_vp, C.POINTER(Options), _vp, _u32p]),
+    ("epa_collect_dev", C.c_int, [_vp, C.POINTER(Options), _vp, _vp]),
+    ("epa_ctx_set_stream", C.c_int, [_vp, _vp]),
     ("epa_get_clv", C.c_int, [_vp, C.c_uint32, _dp, _u32p]),
     ("epa_get_lookup", C.c_int, [_vp, C.c_uint32, _dp]),
     ("epa_get_prescores", C.c_int, [_vp, _dp]),
@@ -251,6 +253,12 @@ class Context:
             counts = np.zeros(self.nq, dtype=np.uint32)
         self._check(self.lib.epa_collect(self.handle, C.byref(opts), out.ctypes.data, _ptr(counts, _u32p)))
         return out, counts
+
+    def collect_dev(self, opts, out_dev_ptr, counts_dev_ptr):
+        self._check(self.lib.epa_collect_dev(self.handle, C.byref(opts), out_dev_ptr, counts_dev_ptr))
+
+    def set_stream(self, cuda_stream):
+        self._check(self.lib.epa_ctx_set_stream(self.handle, cuda_stream))
 
     def place_chunk(self, seqs, opts, out=None, counts=None):
         a = self._rows(seqs, self.sites)

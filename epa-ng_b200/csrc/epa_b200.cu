@@ -52,6 +52,7 @@ enum Stage { ST_NONE = 0, ST_QUERIES = 1, ST_PREPLACED = 2, ST_SELECTED = 3, ST_
 struct epa_ctx {
   int device = 0;
   cudaStream_t stream = nullptr;
+  bool own_stream = true;
   int sm_count = 0;
   size_t smem_optin = 0;
 
@@ -234,7 +235,7 @@ extern "C" void epa_ctx_destroy(epa_ctx * ctx)
   cudaFree(ctx->d_model); cudaFree(ctx->tree.clv); cudaFree(ctx->tree.scaler); cudaFree(ctx->d_edges);
   cudaFree(ctx->d_lookup); cudaFree(ctx->d_flags); cudaFree(ctx->d_counter); cudaFree(ctx->d_total);
   for (auto & e : ctx->ev) if (e) cudaEventDestroy(e);
-  if (ctx->stream) cudaStreamDestroy(ctx->stream);
+  if (ctx->stream && ctx->own_stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
 }
 
@@ -896,7 +897,7 @@ extern "C" int epa_place_pairs(epa_ctx * ctx, const epa_options * opts)
   return EPA_OK;
 }
 
-extern "C" int epa_collect(epa_ctx * ctx, const epa_options * opts, epa_placement * out, uint32_t * out_counts)
+static int collect_impl(epa_ctx * ctx, const epa_options * opts, epa_placement * out, uint32_t * out_counts, bool to_device)
 {
   if (!ctx || !opts) return EPA_ERR_ARG;
   if (int rc = set_device(ctx)) return rc;
@@ -908,8 +909,12 @@ extern "C" int epa_collect(epa_ctx * ctx, const epa_options * opts, epa_placemen
   if (opts->filter_acc_lwr && opts->filter_min > opts->filter_max) return fail(ctx, EPA_ERR_ARG, "Filter min cannot be smaller than max!");
   const uint32_t nq = ctx->nq;
   if (nq == 0) return EPA_OK;
-  CU(ctx->out_rec.ensure((size_t) nq * opts->filter_max * sizeof(PlacementRec)));
-  CU(ctx->out_cnt.ensure(nq * sizeof(uint32_t)));
+  if (to_device && (!out || !out_counts)) return fail(ctx, EPA_ERR_ARG, "null device output");
+  if (!to_device)
+  {
+    CU(ctx->out_rec.ensure((size_t) nq * opts->filter_max * sizeof(PlacementRec)));
+    CU(ctx->out_cnt.ensure(nq * sizeof(uint32_t)));
+  }
   CU(cudaMemsetAsync(ctx->d_flags, 0, 2 * sizeof(int), ctx->stream));
   CollectArgs a{};
   a.res = ctx->res.as<BloResult>();
@@ -918,17 +923,39 @@ extern "C" int epa_collect(epa_ctx * ctx, const epa_options * opts, epa_placemen
   a.nq = nq; a.n_edges = ctx->n_edges;
   a.acc_mode = opts->filter_acc_lwr ? 1 : 0;
   a.thresh = opts->support_threshold; a.fmin = opts->filter_min; a.fmax = opts->filter_max;
-  a.out = ctx->out_rec.as<PlacementRec>(); a.out_cnt = ctx->out_cnt.as<uint32_t>(); a.err = ctx->d_flags;
+  a.out = to_device ? reinterpret_cast<PlacementRec *>(out) : ctx->out_rec.as<PlacementRec>();
+  a.out_cnt = to_device ? out_counts : ctx->out_cnt.as<uint32_t>();
+  a.err = ctx->d_flags;
   collect_kernel<<<(nq + 7) / 8, 256, 0, ctx->stream>>>(a);
   LAUNCHED(ctx);
-  if (out) CU(cudaMemcpyAsync(out, ctx->out_rec.p, (size_t) nq * opts->filter_max * sizeof(PlacementRec), cudaMemcpyDeviceToHost, ctx->stream));
-  if (out_counts) CU(cudaMemcpyAsync(out_counts, ctx->out_cnt.p, nq * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+  if (!to_device && out) CU(cudaMemcpyAsync(out, ctx->out_rec.p, (size_t) nq * opts->filter_max * sizeof(PlacementRec), cudaMemcpyDeviceToHost, ctx->stream));
+  if (!to_device && out_counts) CU(cudaMemcpyAsync(out_counts, ctx->out_cnt.p, nq * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
   CU(cudaEventRecord(ctx->ev[5], ctx->stream));
   int flags[8];
   if (int rc = read_flags(ctx, flags)) return rc;
   for (int i = 0; i < 5; ++i) (void) cudaEventElapsedTime(&ctx->ms[i], ctx->ev[i], ctx->ev[i + 1]);
   (void) cudaGetLastError();
   if (flags[0] == 3) return fail(ctx, EPA_ERR_QUERY, "query %d: likelihood is not finite", flags[1] - 1);
+  return EPA_OK;
+}
+
+extern "C" int epa_collect(epa_ctx * ctx, const epa_options * opts, epa_placement * out, uint32_t * out_counts)
+{
+  return collect_impl(ctx, opts, out, out_counts, false);
+}
+
+extern "C" int epa_collect_dev(epa_ctx * ctx, const epa_options * opts, epa_placement * out_dev, uint32_t * out_counts_dev)
+{
+  return collect_impl(ctx, opts, out_dev, out_counts_dev, true);
+}
+
+extern "C" int epa_ctx_set_stream(epa_ctx * ctx, void * cuda_stream)
+{
+  if (!ctx) return EPA_ERR_ARG;
+  if (int rc = set_device(ctx)) return rc;
+  CU(cudaStreamSynchronize(ctx->stream));
+  if (ctx->own_stream) { cudaStreamDestroy(ctx->stream); ctx->own_stream = false; }
+  ctx->stream = static_cast<cudaStream_t>(cuda_stream);
   return EPA_OK;
 }
 

@@ -1,0 +1,96 @@
+// main.cpp - command line of the B200 build. Accepts the reference's flag spellings
+// (/root/reference/src/main.cpp:96-261); flags that only make sense for the CPU program
+// (-T/--threads) are accepted and ignored, modes outside the hot path are rejected by name.
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "epa_b200_host.h"
+
+namespace {
+
+[[noreturn]] void die(const std::string & msg)
+{
+  std::fprintf(stderr, "ERROR %s\n", msg.c_str());
+  std::exit(1);
+}
+
+void usage()
+{
+  std::puts(
+      "epa-ng-b200 - massively parallel phylogenetic placement of genetic sequences (B200 build)\n"
+      "Usage: epa-ng-b200 -t TREE -s REF_MSA -q QUERY -m MODEL [-w OUTDIR] [options]\n"
+      "  -t,--tree FILE            reference tree (newick, unrooted binary)\n"
+      "  -s,--ref-msa,--msa FILE   reference alignment (fasta)\n"
+      "  -q,--query FILE           aligned query sequences (fasta)\n"
+      "  -m,--model STRING         e.g. GTR{0.7/1.8/1.2/0.6/3.0/1.0}+FU{0.25/0.23/0.30/0.22}+G4{0.47}\n"
+      "  -w,--outdir DIR           output directory [./]\n"
+      "  -g,--dyn-heur FLOAT       accumulated-LWR preplacement heuristic [0.99999]\n"
+      "  --no-heur                 evaluate every edge thoroughly\n"
+      "  --chunk-size INT          queries per device chunk [131072]\n"
+      "  --no-pre-mask             do not drop all-gap columns / trim query ranges\n"
+      "  --filter-acc-lwr FLOAT    accumulated-LWR output filter\n"
+      "  --filter-min-lwr FLOAT    minimum-LWR output filter [0.01]\n"
+      "  --filter-min INT [1]      --filter-max INT [7]      --precision INT [10]\n"
+      "  --device INT              CUDA device [0]\n"
+      "  --redo, -T/--threads N, --verbose  accepted for compatibility\n"
+      "  -v,--version\n");
+}
+
+}  // namespace
+
+int main(int argc, char ** argv)
+{
+  std::string tree, ref, query, model = "GTR+G", outdir = "./";
+  epa_options opts;
+  epa_options_default(&opts);
+  uint32_t chunk = 0;
+  int precision = 10, device = 0;
+  std::string invocation;
+  for (int i = 0; i < argc; ++i) { invocation += argv[i]; invocation += ' '; }
+
+  auto need = [&](int & i) -> const char * {
+    if (i + 1 >= argc) die(std::string("option ") + argv[i] + " needs a value");
+    return argv[++i];
+  };
+  for (int i = 1; i < argc; ++i)
+  {
+    const std::string a = argv[i];
+    if (a == "-h" || a == "--help") { usage(); return 0; }
+    else if (a == "-v" || a == "--version") { std::puts("EPA-ng-b200 v0.1 (placement hot path of EPA-ng v0.3.8 on sm_100a)"); return 0; }
+    else if (a == "-t" || a == "--tree") tree = need(i);
+    else if (a == "-s" || a == "--ref-msa" || a == "--msa") ref = need(i);
+    else if (a == "-q" || a == "--query") query = need(i);
+    else if (a == "-m" || a == "--model") model = need(i);
+    else if (a == "-w" || a == "--outdir") outdir = need(i);
+    else if (a == "-g" || a == "--dyn-heur") { opts.prescoring = 1; opts.heuristic = 0; opts.prescoring_threshold = std::atof(need(i)); }
+    else if (a == "--no-heur") opts.prescoring = 0;
+    else if (a == "--chunk-size") chunk = (uint32_t) std::atol(need(i));
+    else if (a == "--no-pre-mask") opts.premasking = 0;
+    else if (a == "--filter-acc-lwr") { opts.filter_acc_lwr = 1; opts.support_threshold = std::atof(need(i)); }
+    else if (a == "--filter-min-lwr") { opts.filter_acc_lwr = 0; opts.support_threshold = std::atof(need(i)); }
+    else if (a == "--filter-min") opts.filter_min = (uint32_t) std::atol(need(i));
+    else if (a == "--filter-max") opts.filter_max = (uint32_t) std::atol(need(i));
+    else if (a == "--precision") precision = std::atoi(need(i));
+    else if (a == "--device") device = std::atoi(need(i));
+    else if (a == "-T" || a == "--threads" || a == "--tmp") (void) need(i);
+    else if (a == "--redo" || a == "--verbose") {}
+    else if (a == "--rate-scalers")
+    {
+      const std::string v = need(i);
+      if (v == "on") die("--rate-scalers on: per-rate scalers are not supported by this build (per-site scaling is used)");
+    }
+    else if (a == "--preserve-rooting") (void) need(i);
+    else if (a == "-G" || a == "--fix-heur" || a == "--baseball-heur" || a == "--raxml-blo" || a == "-b" || a == "--binary" ||
+             a == "-B" || a == "--dump-binary" || a == "-c" || a == "--bfast" || a == "--split")
+      die("option " + a + " is outside the accelerated hot path and not supported by this build");
+    else die("unknown option " + a);
+  }
+  if (tree.empty() || ref.empty() || query.empty()) { usage(); die("-t, -s and -q are required"); }
+  const int rc = epa_run_files(tree.c_str(), ref.c_str(), query.c_str(), model.c_str(), outdir.c_str(), &opts, chunk, precision,
+                               device, invocation.c_str());
+  if (rc) die(epa_host_last_error());
+  return 0;
+}

@@ -1,0 +1,38 @@
+// model.hpp - substitution model of the host layer: the subset of the raxml-ng model grammar that
+// the reference accepts through -m (src/core/raxml/Model.cpp:123-560) and that the device path
+// supports: DNA JC/K80/F81/HKY/GTR and the protein matrices compiled into protein_models.cpp, with
+// user or equal frequencies (+FU{..}/+FE/+FO), and discrete GAMMA rate heterogeneity (+G[n][a|m]{alpha}).
+// +I, +R, ascertainment correction and per-rate scalers are rejected with a clear message.
+#pragma once
+#include <string>
+#include <vector>
+
+namespace epa_host {
+
+struct Model {
+  int states = 4;
+  std::string name;
+  std::vector<double> subst;        // upper triangle, S(S-1)/2, last entry = 1 after normalisation
+  std::vector<double> freqs;        // S
+  double alpha = 1.0;
+  int rate_cats = 1;
+  bool gamma_median = false;
+  std::vector<double> rates, weights;
+  std::vector<double> eigenvals, eigenvecs, inv_eigenvecs;   // libpll layout (models.c:394-404)
+
+  static Model parse(const std::string & desc);   // throws std::runtime_error
+  std::string describe() const;                   // log text in the spirit of the reference's model print-out
+};
+
+// Discrete GAMMA category rates, mean or median (Yang 1994; libpll gamma.c:220-292)
+std::vector<double> discrete_gamma_rates(double alpha, int ncat, bool median);
+
+// Eigen system of the symmetrised, mean-rate-normalised reversible rate matrix (libpll models.c:182-410)
+void eigen_decompose(int S, const std::vector<double> & subst, const std::vector<double> & freqs,
+                     std::vector<double> & eigenvals, std::vector<double> & eigenvecs,
+                     std::vector<double> & inv_eigenvecs);
+
+// Protein exchangeability tables (protein_models.cpp). Returns false when the name is unknown.
+bool protein_model(const std::string & upper_name, std::vector<double> & subst, std::vector<double> & freqs);
+
+}  // namespace epa_host

@@ -1,0 +1,387 @@
+// session.cpp - host layer: reference state construction, chunk loop, jplace, whole-run driver,
+// and the C ABI of include/epa_b200_host.h. All computation is delegated to the epa_* device API.
+#include "../../../include/epa_b200_host.h"
+
+#include <sys/stat.h>
+
+#include <algorithm>
+#include <chrono>
+#include <cstdio>
+#include <cstring>
+#include <fstream>
+#include <memory>
+#include <stdexcept>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "model.hpp"
+#include "seqio.hpp"
+#include "tree.hpp"
+
+using namespace epa_host;
+
+namespace {
+thread_local std::string g_host_error;
+
+int host_fail(int code, const std::string & msg)
+{
+  g_host_error = msg;
+  return code;
+}
+
+constexpr uint32_t kDefaultChunk = 131072;
+}  // namespace
+
+struct epa_session {
+  Tree tree;
+  Model model;
+  epa_ctx * ctx = nullptr;
+  uint32_t sites = 0;
+  std::string newick_cache;
+  int newick_precision = -1;
+  ~epa_session() { if (ctx) epa_ctx_destroy(ctx); }
+};
+
+extern "C" const char * epa_host_last_error(void) { return g_host_error.c_str(); }
+
+// DNA / protein state masks of the reference alignment (libpll maps.c:46-111)
+static uint32_t tip_mask(int states, uint8_t ch)
+{
+  const char c = (char) std::toupper(ch);
+  if (states == 4)
+  {
+    switch (c)
+    {
+      case 'A': return 1; case 'C': return 2; case 'G': return 4; case 'T': case 'U': return 8;
+      case 'M': return 3; case 'R': return 5; case 'W': return 9; case 'S': return 6; case 'Y': return 10;
+      case 'K': return 12; case 'V': return 7; case 'H': return 11; case 'D': return 13; case 'B': return 14;
+      case 'N': case 'O': case 'X': case '-': case '.': case '?': return 15;
+      default: return 0;
+    }
+  }
+  static const char * order = "ARNDCQEGHILKMFPSTWYV";
+  if (const char * p = c ? std::strchr(order, c) : nullptr) return 1u << (uint32_t) (p - order);
+  auto bit = [&](char x) { return 1u << (uint32_t) (std::strchr(order, x) - order); };
+  switch (c)
+  {
+    case 'B': return bit('N') | bit('D');
+    case 'Z': return bit('Q') | bit('E');
+    case 'J': return bit('I') | bit('L');
+    case 'X': case '*': case '-': case '.': case '?': return 0xfffffu;
+    default: return 0;
+  }
+}
+
+extern "C" int epa_session_open(epa_session ** out, const char * newick, uint32_t n_taxa, const char * const * names,
+                                const char * ref_rows, uint32_t sites, const char * model_desc, int device)
+{
+  if (!out || !newick || !names || !ref_rows || !model_desc) return host_fail(EPA_ERR_ARG, "null argument");
+  *out = nullptr;
+  try
+  {
+    std::unique_ptr<epa_session> s(new epa_session());
+    s->tree = Tree::parse(newick);
+    s->model = Model::parse(model_desc);
+    s->sites = sites;
+    const size_t T = s->tree.num_tips();
+    if (T != n_taxa)
+      return host_fail(EPA_ERR_ARG, "tree has " + std::to_string(T) + " tips but the reference MSA has " + std::to_string(n_taxa) + " sequences");
+    std::unordered_map<std::string, uint32_t> by_name;
+    for (uint32_t i = 0; i < n_taxa; ++i) by_name.emplace(names[i], i);
+    std::vector<uint32_t> masks(T * (size_t) sites);
+    for (size_t t = 0; t < T; ++t)
+    {
+      const std::string & label = s->tree.nodes[s->tree.tip_node[t]].label;
+      auto it = by_name.find(label);
+      if (it == by_name.end()) return host_fail(EPA_ERR_ARG, "Sequence with header '" + label + "' does not appear in the tree / MSA");
+      const uint8_t * row = reinterpret_cast<const uint8_t *>(ref_rows) + (size_t) it->second * sites;
+      for (uint32_t k = 0; k < sites; ++k)
+      {
+        const uint32_t m = tip_mask(s->model.states, row[k]);
+        if (!m) return host_fail(EPA_ERR_ARG, "invalid character '" + std::string(1, (char) row[k]) + "' in reference sequence " + label);
+        masks[t * sites + k] = m;
+      }
+    }
+    const Tree::Schedule sch = s->tree.schedule();
+    epa_model_desc md{};
+    md.states = (uint32_t) s->model.states;
+    md.rate_cats = (uint32_t) s->model.rate_cats;
+    md.sites = sites;
+    md.flags = 0;
+    md.eigenvals = s->model.eigenvals.data();
+    md.eigenvecs = s->model.eigenvecs.data();
+    md.inv_eigenvecs = s->model.inv_eigenvecs.data();
+    md.freqs = s->model.freqs.data();
+    md.rates = s->model.rates.data();
+    md.rate_weights = s->model.weights.data();
+    md.pinv = 0.0;
+    int rc = epa_ctx_create(&s->ctx, device, &md, (uint32_t) T, masks.data(), sch.n_slots, sch.edges.data(), (uint32_t) sch.edges.size());
+    if (rc) return host_fail(rc, epa_last_error(nullptr));
+    rc = epa_compute_clvs(s->ctx, sch.ops.data(), (uint32_t) sch.ops.size());
+    if (rc) return host_fail(rc, epa_last_error(s->ctx));
+    rc = epa_build_lookup(s->ctx);
+    if (rc) return host_fail(rc, epa_last_error(s->ctx));
+    *out = s.release();
+    return EPA_OK;
+  }
+  catch (const std::exception & e)
+  {
+    return host_fail(EPA_ERR_ARG, e.what());
+  }
+}
+
+extern "C" void epa_session_close(epa_session * s) { delete s; }
+extern "C" epa_ctx * epa_session_ctx(epa_session * s) { return s ? s->ctx : nullptr; }
+extern "C" uint32_t epa_session_num_edges(const epa_session * s) { return s ? (uint32_t) s->tree.num_edges() : 0; }
+extern "C" uint32_t epa_session_num_tips(const epa_session * s) { return s ? (uint32_t) s->tree.num_tips() : 0; }
+extern "C" uint32_t epa_session_sites(const epa_session * s) { return s ? s->sites : 0; }
+
+extern "C" const char * epa_session_numbered_newick(epa_session * s, int precision)
+{
+  if (!s) return "";
+  if (s->newick_precision != precision)
+  {
+    s->newick_cache = s->tree.numbered_newick(precision);
+    s->newick_precision = precision;
+  }
+  return s->newick_cache.c_str();
+}
+
+extern "C" int epa_session_tree_logl(epa_session * s, double * logl)
+{
+  if (!s || !logl) return host_fail(EPA_ERR_ARG, "null argument");
+  const int rc = epa_edge_loglikelihood(s->ctx, 0, logl);
+  return rc ? host_fail(rc, epa_last_error(s->ctx)) : EPA_OK;
+}
+
+extern "C" int epa_session_place(epa_session * s, const char * query_rows, uint64_t n_queries, const epa_options * opts,
+                                 uint32_t chunk_size, epa_placement * out, uint32_t * counts)
+{
+  if (!s || !opts || (!query_rows && n_queries)) return host_fail(EPA_ERR_ARG, "null argument");
+  if (chunk_size == 0) chunk_size = kDefaultChunk;
+  if (!opts->prescoring)
+  {
+    // all-pairs mode: keep a chunk below 2^32 pairs and a few GB of results
+    const uint64_t max_q = std::max<uint64_t>(1, (1ull << 28) / std::max<uint32_t>(1, epa_session_num_edges(s)));
+    chunk_size = (uint32_t) std::min<uint64_t>(chunk_size, max_q);
+  }
+  for (uint64_t done = 0; done < n_queries; done += chunk_size)
+  {
+    const uint32_t nq = (uint32_t) std::min<uint64_t>(chunk_size, n_queries - done);
+    const int rc = epa_place_chunk(s->ctx, query_rows + done * s->sites, nq, opts,
+                                   out ? out + done * opts->filter_max : nullptr, counts ? counts + done : nullptr);
+    if (rc)
+    {
+      std::string msg = epa_last_error(s->ctx);
+      if (rc == EPA_ERR_QUERY) msg += " (chunk starting at query " + std::to_string(done) + ")";
+      return host_fail(rc, msg);
+    }
+  }
+  return EPA_OK;
+}
+
+// ----------------------------------------------------------------------------------------------
+//  jplace
+// ----------------------------------------------------------------------------------------------
+static void write_pquery(FILE * fh, const char * name, const epa_placement * recs, uint32_t count, int precision, bool last)
+{
+  std::fputs("    {\"p\": [\n", fh);
+  for (uint32_t k = 0; k < count; ++k)
+  {
+    const epa_placement & p = recs[k];
+    std::fprintf(fh, "      [%llu, %.*f, %.*f, %.*f, %.*f]%s\n", (unsigned long long) p.branch_id, precision, p.likelihood,
+                 precision, p.lwr, precision, p.distal_length, precision, p.pendant_length, k + 1 < count ? "," : "");
+  }
+  std::fputs("      ],\n", fh);
+  std::fprintf(fh, "    \"n\": [\"%s\"]\n", name);
+  std::fprintf(fh, "    }%s\n", last ? "" : ",");
+}
+
+static void jplace_begin(FILE * fh, const char * newick)
+{
+  std::fprintf(fh, "{\n  \"tree\": \"%s\",\n  \"placements\": \n  [\n", newick);
+}
+
+static void jplace_end(FILE * fh, const char * invocation)
+{
+  std::fprintf(fh, "  ],\n  \"metadata\": {\"invocation\": \"%s\"},\n  \"version\": 3,\n", invocation ? invocation : "");
+  std::fputs("  \"fields\": [\"edge_num\", \"likelihood\", \"like_weight_ratio\", \"distal_length\", \"pendant_length\"]\n}\n", fh);
+}
+
+extern "C" int epa_write_jplace(const char * path, const char * numbered_newick, const char * invocation,
+                                const char * const * query_names, uint64_t n_queries, const epa_placement * recs,
+                                const uint32_t * counts, uint32_t stride, int precision)
+{
+  if (!path || !numbered_newick || !query_names || !recs || !counts) return host_fail(EPA_ERR_ARG, "null argument");
+  FILE * fh = std::fopen(path, "w");
+  if (!fh) return host_fail(EPA_ERR_ARG, std::string("cannot open ") + path);
+  jplace_begin(fh, numbered_newick);
+  for (uint64_t q = 0; q < n_queries; ++q)
+    write_pquery(fh, query_names[q], recs + q * stride, counts[q], precision, q + 1 == n_queries);
+  jplace_end(fh, invocation);
+  std::fclose(fh);
+  return EPA_OK;
+}
+
+// ----------------------------------------------------------------------------------------------
+//  whole run (src/main.cpp:470-552 + src/core/place.cpp:173-251)
+// ----------------------------------------------------------------------------------------------
+extern "C" int epa_run_files(const char * tree_file, const char * ref_msa_file, const char * query_file,
+                             const char * model, const char * outdir, const epa_options * opts, uint32_t chunk_size,
+                             int precision, int device, const char * invocation)
+{
+  if (!tree_file || !ref_msa_file || !query_file || !model || !outdir || !opts) return host_fail(EPA_ERR_ARG, "null argument");
+  try
+  {
+    const auto t0 = std::chrono::steady_clock::now();
+    std::string dir = outdir;
+    if (dir.empty()) dir = ".";
+    if (dir.back() != '/') dir += '/';
+    ::mkdir(dir.c_str(), 0755);
+    std::ofstream log(dir + "epa_info.log");
+    auto info = [&](const std::string & line) { log << "INFO " << line << "\n"; std::printf("INFO %s\n", line.c_str()); };
+    info("Selected: Output dir: " + dir);
+    info(std::string("Selected: Query file: ") + query_file);
+    info(std::string("Selected: Tree file: ") + tree_file);
+    info(std::string("Selected: Reference MSA: ") + ref_msa_file);
+    info(std::string("Selected: Specified model: ") + model);
+    info("Selected: device cuda:" + std::to_string(device) + " (libepa_b200, sm_100a)");
+
+    std::ifstream tf(tree_file);
+    if (!tf) return host_fail(EPA_ERR_ARG, std::string("Cannot open file: ") + tree_file);
+    std::string newick((std::istreambuf_iterator<char>(tf)), std::istreambuf_iterator<char>());
+    Alignment ref = read_fasta(ref_msa_file);
+    Alignment qry = read_fasta(query_file);
+    if (ref.sites != qry.sites)
+      return host_fail(EPA_ERR_ARG, "reference and query MSA have different widths (" + std::to_string(ref.sites) + " vs " + std::to_string(qry.sites) + ")");
+    if (opts->premasking)
+    {
+      std::vector<uint8_t> mask = gap_mask(ref);
+      const std::vector<uint8_t> qmask = gap_mask(qry);
+      for (size_t i = 0; i < mask.size(); ++i) mask[i] |= qmask[i];
+      ref = apply_mask(ref, mask);
+      qry = apply_mask(qry, mask);
+    }
+    const Model parsed = Model::parse(model);
+    info("Using model parameters:");
+    info(parsed.describe());
+
+    std::vector<const char *> names(ref.size());
+    for (size_t i = 0; i < ref.size(); ++i) names[i] = ref.names[i].c_str();
+    epa_session * s = nullptr;
+    int rc = epa_session_open(&s, newick.c_str(), (uint32_t) ref.size(), names.data(),
+                              reinterpret_cast<const char *>(ref.rows.data()), (uint32_t) ref.sites, model, device);
+    if (rc) return rc;
+    std::unique_ptr<epa_session> guard(s);
+    double tree_logl = 0.0;
+    if (epa_session_tree_logl(s, &tree_logl) == EPA_OK)
+    {
+      char buf[96];
+      std::snprintf(buf, sizeof buf, "Reference tree log-likelihood: %.6f", tree_logl);
+      info(buf);
+    }
+
+    const std::string jpath = dir + "epa_result.jplace";
+    FILE * fh = std::fopen(jpath.c_str(), "w");
+    if (!fh) return host_fail(EPA_ERR_ARG, "cannot open " + jpath);
+    info("Output file: " + jpath);
+    jplace_begin(fh, epa_session_numbered_newick(s, precision));
+    if (chunk_size == 0) chunk_size = kDefaultChunk;
+    const auto t1 = std::chrono::steady_clock::now();
+    const uint64_t Q = qry.size();
+    std::vector<epa_placement> recs((size_t) std::min<uint64_t>(Q, chunk_size) * opts->filter_max);
+    std::vector<uint32_t> counts((size_t) std::min<uint64_t>(Q, chunk_size));
+    for (uint64_t done = 0; done < Q; done += chunk_size)
+    {
+      const uint64_t nq = std::min<uint64_t>(chunk_size, Q - done);
+      rc = epa_session_place(s, reinterpret_cast<const char *>(qry.row(done)), nq, opts, chunk_size, recs.data(), counts.data());
+      if (rc) { std::fclose(fh); return rc; }
+      for (uint64_t q = 0; q < nq; ++q)
+        write_pquery(fh, qry.names[done + q].c_str(), recs.data() + q * opts->filter_max, counts[q], precision, done + q + 1 == Q);
+      info(std::to_string(done + nq) + " Sequences done!");
+    }
+    jplace_end(fh, invocation);
+    std::fclose(fh);
+    const auto t2 = std::chrono::steady_clock::now();
+    char buf[96];
+    std::snprintf(buf, sizeof buf, "Time spent placing: %.3fs", std::chrono::duration<double>(t2 - t1).count());
+    info(buf);
+    std::snprintf(buf, sizeof buf, "Elapsed Time: %.3fs", std::chrono::duration<double>(t2 - t0).count());
+    info(buf);
+    return EPA_OK;
+  }
+  catch (const std::exception & e)
+  {
+    return host_fail(EPA_ERR_ARG, e.what());
+  }
+}
+
+// ----------------------------------------------------------------------------------------------
+//  device-free inspection (CPU tests of the host logic)
+// ----------------------------------------------------------------------------------------------
+extern "C" int epa_host_parse_tree(const char * newick, int precision, char * out_newick, size_t cap, uint32_t * n_tips,
+                                   uint32_t * n_edges)
+{
+  if (!newick) return host_fail(EPA_ERR_ARG, "null argument");
+  try
+  {
+    const Tree t = Tree::parse(newick);
+    if (out_newick && cap)
+    {
+      const std::string s = t.numbered_newick(precision);
+      std::snprintf(out_newick, cap, "%s", s.c_str());
+    }
+    if (n_tips) *n_tips = (uint32_t) t.num_tips();
+    if (n_edges) *n_edges = (uint32_t) t.num_edges();
+    return EPA_OK;
+  }
+  catch (const std::exception & e) { return host_fail(EPA_ERR_ARG, e.what()); }
+}
+
+extern "C" int epa_host_tree_schedule(const char * newick, uint32_t * n_slots, epa_clv_op * ops, uint32_t ops_cap,
+                                      uint32_t * n_ops, epa_edge_desc * edges, uint32_t edges_cap, uint32_t * n_edges,
+                                      char * tip_labels, size_t labels_cap)
+{
+  if (!newick) return host_fail(EPA_ERR_ARG, "null argument");
+  try
+  {
+    const Tree t = Tree::parse(newick);
+    const Tree::Schedule s = t.schedule();
+    if (s.ops.size() > ops_cap || s.edges.size() > edges_cap) return host_fail(EPA_ERR_ARG, "capacity too small");
+    if (n_slots) *n_slots = s.n_slots;
+    if (n_ops) *n_ops = (uint32_t) s.ops.size();
+    if (n_edges) *n_edges = (uint32_t) s.edges.size();
+    if (ops) std::copy(s.ops.begin(), s.ops.end(), ops);
+    if (edges) std::copy(s.edges.begin(), s.edges.end(), edges);
+    if (tip_labels && labels_cap)
+    {
+      std::string all;
+      for (int v : t.tip_node) { all += t.nodes[v].label; all += '\n'; }
+      std::snprintf(tip_labels, labels_cap, "%s", all.c_str());
+    }
+    return EPA_OK;
+  }
+  catch (const std::exception & e) { return host_fail(EPA_ERR_ARG, e.what()); }
+}
+
+extern "C" int epa_host_parse_model(const char * model, uint32_t * states, uint32_t * rate_cats, double * rates,
+                                    double * weights, double * freqs, double * eigenvals, double * eigenvecs,
+                                    double * inv_eigenvecs)
+{
+  if (!model) return host_fail(EPA_ERR_ARG, "null argument");
+  try
+  {
+    const Model m = Model::parse(model);
+    if (states) *states = (uint32_t) m.states;
+    if (rate_cats) *rate_cats = (uint32_t) m.rate_cats;
+    if (rates) std::copy(m.rates.begin(), m.rates.end(), rates);
+    if (weights) std::copy(m.weights.begin(), m.weights.end(), weights);
+    if (freqs) std::copy(m.freqs.begin(), m.freqs.end(), freqs);
+    if (eigenvals) std::copy(m.eigenvals.begin(), m.eigenvals.end(), eigenvals);
+    if (eigenvecs) std::copy(m.eigenvecs.begin(), m.eigenvecs.end(), eigenvecs);
+    if (inv_eigenvecs) std::copy(m.inv_eigenvecs.begin(), m.inv_eigenvecs.end(), inv_eigenvecs);
+    return EPA_OK;
+  }
+  catch (const std::exception & e) { return host_fail(EPA_ERR_ARG, e.what()); }
+}

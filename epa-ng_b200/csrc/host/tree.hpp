@@ -1,0 +1,54 @@
+// tree.hpp - reference tree of the host layer.
+//
+// The reference keeps libpll's ring-of-unodes structure; here the tree is a plain array of nodes
+// hanging from the top-level trifurcation, because all the hot path needs from it are
+//   (1) the edge numbering = jplace edge_num: post-order over the newick as written, the edge
+//       above the i-th visited node is edge i (utree_query_branches, src/core/pll/pll_util.cpp:182-205,
+//       golden strings test/src/pll_util.cpp:134-186),
+//   (2) per edge the two directional CLVs looking away from it, i.e. the pruning schedule
+//       (precompute_clvs, src/core/pll/epa_pll_util.cpp:62-107), and
+//   (3) the numbered newick for the jplace header (src/core/pll/pll_util.cpp:207-352).
+#pragma once
+#include <cstdint>
+#include <string>
+#include <vector>
+
+#include "epa_b200.h"
+
+namespace epa_host {
+
+constexpr double kDefaultBranchLength = 0.10536051565782630123;   // -ln(0.9), src/util/constants.hpp:12
+
+struct TreeNode {
+  int parent = -1;
+  std::vector<int> children;      // file order
+  std::string label;
+  double length = 0.0;            // edge above the node
+  int edge = -1;                  // post-order index of the edge above the node (= jplace edge_num)
+  int tip = -1;                   // tip index (order of appearance in the post-order), -1 for inner nodes
+};
+
+struct Tree {
+  std::vector<TreeNode> nodes;
+  int root = -1;                  // top-level trifurcation
+  std::vector<int> edge_node;     // edge -> node below it
+  std::vector<int> tip_node;      // tip index -> node
+
+  size_t num_tips() const { return tip_node.size(); }
+  size_t num_edges() const { return edge_node.size(); }
+
+  // Parses an unrooted (top-level trifurcation), strictly binary newick tree. Throws std::runtime_error.
+  static Tree parse(const std::string & newick);
+  std::string numbered_newick(int precision = 10) const;
+
+  // Node ids handed to libepa_b200: tips 0..T-1; down-CLV of inner node v and up-CLV of node v get
+  // consecutive slots. ops/edges are ready for epa_compute_clvs / epa_ctx_create.
+  struct Schedule {
+    uint32_t n_slots = 0;
+    std::vector<epa_clv_op> ops;
+    std::vector<epa_edge_desc> edges;
+  };
+  Schedule schedule() const;
+};
+
+}  // namespace epa_host

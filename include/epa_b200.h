@@ -170,6 +170,15 @@ int epa_place_pairs(epa_ctx * ctx, const epa_options * opts);
 /* LWR over the evaluated candidates, filter, pack; D2H of the records. */
 int epa_collect(epa_ctx * ctx, const epa_options * opts, epa_placement * out, uint32_t * out_counts);
 
+/* Same, but the records stay in device memory: out_dev[n_queries][filter_max] and
+ * counts_dev[n_queries] are DEVICE pointers owned by the caller (e.g. the send buffer of the
+ * NCCL gather that collects the shards of a multi-GPU run). */
+int epa_collect_dev(epa_ctx * ctx, const epa_options * opts, epa_placement * out_dev, uint32_t * counts_dev);
+
+/* Makes the context issue all its work on the caller's CUDA stream (a cudaStream_t; NULL = the
+ * legacy default stream) so that the caller's events and collectives order against it. */
+int epa_ctx_set_stream(epa_ctx * ctx, void * cuda_stream);
+
 /* -------------------------------------------------------------------------------------------- */
 /* inspection (parity tests)                                                                    */
 /* -------------------------------------------------------------------------------------------- */

@@ -1,0 +1,83 @@
+/*
+ * epa_b200_host.h - C ABI of the C++ host layer in libepa_b200.so: everything the reference does
+ * around the hot path to get from files to a jplace, re-typed (not accelerated) so that the
+ * library is usable end to end:
+ *
+ *   tree parsing + edge numbering   /root/reference/src/io/file_io.cpp:120-192, src/core/pll/pll_util.cpp:182-352
+ *   model string                    src/core/raxml/Model.cpp:123-560 (subset, see csrc/host/model.hpp)
+ *   MSA reading + pre-masking       src/seq/MSA_Info.hpp:22-111, src/main.cpp:470-494
+ *   Tree(...) construction          src/tree/Tree.cpp:16-56 (CLVs are computed ON THE DEVICE)
+ *   chunk loop                      src/core/place.cpp:173-251 (simple_mpi)
+ *   jplace output                   src/io/jplace_util.cpp:20-86
+ *
+ * A session owns one epa_ctx (include/epa_b200.h); all compute goes through that C ABI.
+ * All functions return 0 or a negative epa_status; epa_host_last_error() gives the message of
+ * the last failure on the calling thread.
+ */
+#ifndef EPA_B200_HOST_H
+#define EPA_B200_HOST_H
+
+#include "epa_b200.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct epa_session epa_session;
+
+/* Builds the reference state on `device`: parses the newick text, matches the n_taxa rows of the
+ * reference alignment (ref_rows[n_taxa][sites], ASCII, already column-masked) to the tips by
+ * name, parses the model string, computes all directional CLVs and the lookup tables. */
+int epa_session_open(epa_session ** session, const char * newick, uint32_t n_taxa,
+                     const char * const * names, const char * ref_rows, uint32_t sites,
+                     const char * model, int device);
+
+/* Places n_queries rows (query_rows[n_queries][sites], ASCII, HOST memory; pinned memory gives
+ * full PCIe speed) in chunks of chunk_size queries (0 = default): the reference's chunk loop.
+ * out[n_queries][opts->filter_max], counts[n_queries] as in epa_place_chunk. */
+int epa_session_place(epa_session * session, const char * query_rows, uint64_t n_queries,
+                      const epa_options * opts, uint32_t chunk_size, epa_placement * out,
+                      uint32_t * counts);
+
+epa_ctx * epa_session_ctx(epa_session * session);
+uint32_t epa_session_num_edges(const epa_session * session);
+uint32_t epa_session_num_tips(const epa_session * session);
+uint32_t epa_session_sites(const epa_session * session);
+/* jplace "tree" string: newick with {edge_num} annotations. */
+const char * epa_session_numbered_newick(epa_session * session, int precision);
+/* Reference-tree log-likelihood evaluated across edge 0 (Tree::ref_tree_logl). */
+int epa_session_tree_logl(epa_session * session, double * logl);
+void epa_session_close(epa_session * session);
+
+/* Whole run, files to jplace: what the reference's main() does for
+ *   epa-ng -t tree -s ref_msa -q query -m model -w outdir [options]
+ * Writes <outdir>/epa_result.jplace and <outdir>/epa_info.log. */
+int epa_run_files(const char * tree_file, const char * ref_msa_file, const char * query_file,
+                  const char * model, const char * outdir, const epa_options * opts,
+                  uint32_t chunk_size, int precision, int device, const char * invocation);
+
+/* Formats placement records as a jplace document (src/io/jplace_util.cpp:20-86) into `path`. */
+int epa_write_jplace(const char * path, const char * numbered_newick, const char * invocation,
+                     const char * const * query_names, uint64_t n_queries, const epa_placement * recs,
+                     const uint32_t * counts, uint32_t stride, int precision);
+
+/* ---- device-free inspection of the host logic (CPU tests) ---------------------------------- */
+/* Parses the tree; writes the numbered newick (NUL-terminated, truncated to cap) and the counts. */
+int epa_host_parse_tree(const char * newick, int precision, char * out_newick, size_t cap,
+                        uint32_t * n_tips, uint32_t * n_edges);
+/* Pruning schedule and edge list that epa_session_open hands to the device API; tip_labels
+ * receives the tip names separated by '\n' in tip-id order. Capacities are in elements. */
+int epa_host_tree_schedule(const char * newick, uint32_t * n_slots, epa_clv_op * ops, uint32_t ops_cap,
+                           uint32_t * n_ops, epa_edge_desc * edges, uint32_t edges_cap, uint32_t * n_edges,
+                           char * tip_labels, size_t labels_cap);
+/* Parses the model string: arrays must hold 20 / 8 / 400 doubles. */
+int epa_host_parse_model(const char * model, uint32_t * states, uint32_t * rate_cats, double * rates,
+                         double * weights, double * freqs, double * eigenvals, double * eigenvecs,
+                         double * inv_eigenvecs);
+
+const char * epa_host_last_error(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* EPA_B200_HOST_H */

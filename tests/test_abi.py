@@ -29,9 +29,8 @@ def test_library_exports_every_declared_symbol(built):
     assert len(declared) >= 20
     missing = [n for n in sorted(declared) if not hasattr(lib, n)]
     assert not missing, f"declared in include/*.h but not exported: {missing}"
-    bound = {n for n, _, _ in built.capi.SYMBOLS}
-    assert declared - bound == set() or all(n.startswith("epa_host_") or n.startswith("epa_session_") or n.startswith("epa_run")
-                                            for n in declared - bound), declared - bound
+    bound = {n for n, _, _ in built.capi.SYMBOLS} | {n for n, _, _ in built.session.HOST_SYMBOLS}
+    assert declared == bound, f"ctypes bindings and headers disagree: {declared ^ bound}"
 
 
 def test_record_layout_matches_reference_placement(built):

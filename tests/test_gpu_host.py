@@ -1,0 +1,86 @@
+"""GPU: the C++ host layer end to end - files in, jplace out - against the reference's recorded
+placements, through both the library entry point and the command-line program."""
+import json
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import helpers
+
+pytestmark = pytest.mark.gpu
+
+
+def _read_jplace(path):
+    doc = json.load(open(path))
+    return {n: pq["p"] for pq in doc["placements"] for n in pq["n"]}, doc
+
+
+def _check(got, want, what):
+    assert set(got) == set(want)
+    bad = []
+    for name in want:
+        try:
+            helpers.assert_placements_close(got[name], want[name], f"{what}/{name}")
+        except AssertionError as e:
+            bad.append(str(e))
+    assert not bad, f"{len(bad)} of {len(want)} differ: {bad[:3]}"
+
+
+def test_run_files_cfg1_matches_reference(built, tmp_path):
+    d = os.path.join(helpers.GOLDEN, "cfg1")
+    gold = helpers.golden("cfg1")
+    for mname, model in (("gtrg", helpers.GTRG), ("gtrb", helpers.GTR_B)):
+        out = str(tmp_path / mname)
+        built.session.run_files(os.path.join(d, "ref.tre"), os.path.join(d, "aln.fasta"), os.path.join(d, "query.fasta"),
+                                model, out)
+        got, doc = _read_jplace(os.path.join(out, "epa_result.jplace"))
+        _check(got, gold[f"{mname}_default"]["placements"], mname)
+        assert doc["tree"] == gold[f"{mname}_default"]["tree"]
+        assert doc["version"] == 3
+        assert doc["fields"] == ["edge_num", "likelihood", "like_weight_ratio", "distal_length", "pendant_length"]
+        assert os.path.exists(os.path.join(out, "epa_info.log"))
+
+
+def test_cli_synth64_matches_reference(built, tmp_path):
+    d = os.path.join(helpers.GOLDEN, "synth64")
+    exe = os.path.join(helpers.ROOT, "epa-ng_b200", "epa-ng-b200")
+    assert os.path.exists(exe), "host program not built"
+    model = "GTR{1/1/1/1/1/1}+FU{0.25/0.25/0.25/0.25}+G4{0.5}"
+    out = str(tmp_path / "cli")
+    subprocess.run([exe, "-t", os.path.join(d, "tree.nwk"), "-s", os.path.join(d, "ref.fasta"), "-q",
+                    os.path.join(d, "query.fasta"), "-m", model, "-w", out, "-T", "4", "--redo", "--chunk-size", "64"],
+                   check=True, stdout=subprocess.DEVNULL)
+    got, doc = _read_jplace(os.path.join(out, "epa_result.jplace"))
+    gold = helpers.golden("synth64")["default"]
+    _check(got, gold["placements"], "cli")
+    assert doc["tree"] == gold["tree"]
+    # the query order of the file is kept
+    names = [pq["n"][0] for pq in doc["placements"]]
+    assert names == sorted(names)
+    # unsupported modes are refused by name, not silently ignored
+    r = subprocess.run([exe, "-t", "x", "-s", "x", "-q", "x", "--baseball-heur"], capture_output=True, text=True)
+    assert r.returncode != 0 and "not supported" in r.stderr
+
+
+def test_session_chunking_is_invisible(built):
+    case = helpers.synth64_case()
+    d = os.path.join(helpers.GOLDEN, "synth64")
+    o = helpers.oracle()
+    rn, rs = o.read_fasta(os.path.join(d, "ref.fasta"))
+    ref_rows = np.frombuffer("".join(rs).encode(), dtype=np.uint8).reshape(len(rs), -1)
+    sess = built.session.Session(open(os.path.join(d, "tree.nwk")).read(), rn, ref_rows,
+                                 "GTR{1/1/1/1/1/1}+FU{0.25/0.25/0.25/0.25}+G4{0.5}")
+    assert abs(sess.tree_logl() - case.ref.tree_logl(0)) <= 1e-10 * abs(case.ref.tree_logl(0))
+    a, ca = sess.place(case.query_rows, chunk_size=0)
+    b, cb = sess.place(case.query_rows, chunk_size=37)
+    assert np.array_equal(ca, cb) and np.array_equal(a, b)       # bit-identical whatever the chunking
+    opts = built.capi.default_options(prescoring=0, support_threshold=0.0, filter_max=5)
+    c, cc = sess.place(case.query_rows[:7], opts)
+    gold = helpers.golden("synth64")["default"]["placements"]
+    for qi in range(7):
+        best = helpers.records_to_lists(c, cc)[qi][0]
+        want = gold[case.qnames[qi]][0]
+        assert best[0] == want[0] and abs(best[1] - want[1]) <= 1e-6 * abs(want[1])
+    sess.close()

@@ -1,0 +1,106 @@
+"""CPU: the C++ host layer (tree numbering, pruning schedule, model parsing) against the oracle and
+the reference's recorded strings. No device is touched."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+import helpers
+
+
+@pytest.fixture(scope="module")
+def sess(built):
+    return built.session
+
+
+def _read(*p):
+    return open(os.path.join(helpers.GOLDEN, *p)).read()
+
+
+def test_numbered_newick_matches_reference(sess):
+    # golden strings come from the unmodified reference (jplace "tree" field)
+    nwk, nt, ne = sess.parse_tree(_read("cfg1", "ref.tre"))
+    assert (nt, ne) == (8, 13)
+    assert nwk == helpers.golden("cfg1")["gtrg_default"]["tree"]
+    nwk, nt, ne = sess.parse_tree(_read("synth64", "tree.nwk"))
+    assert (nt, ne) == (64, 125)
+    assert nwk == helpers.golden("synth64")["default"]["tree"]
+
+
+def test_tree_errors(sess, built):
+    for bad in ["(A:1,B:1);", "((A:1,B:1):1,(C:1,D:1):1);", "(A:1,B:1,(C:1,D:1,E:1):1);", "(A:1,B:1,C:1", "A;"]:
+        with pytest.raises(built.capi.EpaError):
+            sess.parse_tree(bad)
+    # missing / zero lengths fall back to -ln(0.9) (set_missing_branch_lengths)
+    nwk, _, _ = sess.parse_tree("(A,B:0,(C:0.5,D:0.25)x:0.125);", precision=4)
+    assert nwk == "(A:0.1054{0},B:0.1054{1},(C:0.5000{2},D:0.2500{3})x:0.1250{4});"
+
+
+@pytest.mark.parametrize("model", [helpers.GTRG, helpers.GTR_B, "GTR+G", "JC", "HKY{1.0/2.5}+FU{0.1/0.2/0.3/0.4}+G8{0.3}",
+                                   "GTR{1/2/3/4/5/6}+FE+G4a{2.0}", "K80{1.0/4.0}"])
+def test_model_matches_oracle(sess, model):
+    o = helpers.oracle()
+    want = o.parse_model(model)
+    got = sess.parse_model(model)
+    assert got["states"] == want.states and got["rate_cats"] == want.rate_cats
+    assert np.allclose(got["rates"], want.rates, rtol=1e-13, atol=0)
+    assert np.allclose(got["freqs"], want.freqs, rtol=1e-15, atol=0)
+    # eigen systems may differ by ordering/sign; P(t) must agree
+    S = 4
+    for t in (0.0, 1e-4, 0.05, 0.7, 25.0):
+        for r in got["rates"]:
+            V, Vi = got["eigenvecs"].reshape(S, S), got["inv_eigenvecs"].reshape(S, S)
+            P = np.eye(S) + (Vi * np.expm1(got["eigenvals"] * r * t)[None, :]) @ V
+            Vw, Viw = want.eigenvecs.reshape(S, S), want.inv_eigenvecs.reshape(S, S)
+            Pw = np.eye(S) + (Viw * np.expm1(want.eigenvals * r * t)[None, :]) @ Vw
+            assert np.allclose(P, Pw, rtol=0, atol=1e-14)
+            assert np.allclose(P.sum(axis=1), 1.0, atol=1e-13)
+
+
+def test_model_errors(sess, built):
+    for bad in ["GTR+I", "LG+G", "GTR{1/2/3}", "GTR+FU{0.5/0.5}", "GTR+R4", "FOO"]:
+        with pytest.raises(built.capi.EpaError):
+            sess.parse_model(bad)
+
+
+def test_schedule_reproduces_oracle_clvs(sess):
+    """Runs the host layer's pruning schedule with the ORACLE's CLV kernel on the CPU and checks the
+    reference's invariant (same tree log-likelihood across every edge, test/src/epa_pll_util.cpp:82-121)
+    plus equality with the oracle's own directional CLVs."""
+    o = helpers.oracle()
+    case = helpers.synth64_case()
+    n_slots, ops, edges, labels = sess.tree_schedule(_read("synth64", "tree.nwk"))
+    T = len(labels)
+    assert T == 64 and n_slots == 3 * (T - 2) and len(ops) == n_slots and len(edges) == 2 * T - 3
+    by_label = {t.label: case.ref.sides[t.uid] for t in case.tree.tips}
+    sides = {i: by_label[l] for i, l in enumerate(labels)}
+    pending = list(ops)
+    mc = case.model.c()
+    while pending:
+        rest = []
+        for (p, l, r, ll, rl) in pending:
+            if l in sides and r in sides:
+                clv = np.zeros(case.n * 16)
+                sc = np.zeros(case.n, dtype=np.uint32)
+                o.lib().orc_update_partial(C.byref(mc), case.n, clv.ctypes.data_as(C.POINTER(C.c_double)),
+                                           sc.ctypes.data_as(C.POINTER(C.c_uint32)), C.byref(sides[l].c),
+                                           case.ref.pmat(ll).ctypes.data_as(C.POINTER(C.c_double)), C.byref(sides[r].c),
+                                           case.ref.pmat(rl).ctypes.data_as(C.POINTER(C.c_double)))
+                sides[p] = o.SideData(clv=clv, scaler=sc)
+            else:
+                rest.append((p, l, r, ll, rl))
+        assert len(rest) < len(pending), "schedule has unsatisfiable dependencies"
+        pending = rest
+    want = case.ref.tree_logl(0)
+    for e, (d, p, length) in enumerate(edges):
+        assert d < T or p >= T
+        got = o.lib().orc_edge_logl(C.byref(mc), case.n, C.byref(sides[d].c), C.byref(sides[p].c),
+                                    case.ref.pmat(length).ctypes.data_as(C.POINTER(C.c_double)), None)
+        assert abs(got - want) <= 1e-10 * abs(want), f"edge {e}"
+        # same edge numbering and orientation as the oracle / reference
+        od, op_, ol = case.ref.edges[e]
+        assert ol == length
+        if od.clv is not None:
+            assert np.allclose(sides[d].clv, od.clv, rtol=1e-12, atol=0)
+        assert np.allclose(sides[p].clv, op_.clv, rtol=1e-12, atol=0)
