@@ -254,7 +254,8 @@ def ours(args):
     ms_e2e = timed(step_e2e, args.steps)
 
     # device-resident and host paths must agree bit for bit
-    same = bool(np.array_equal(rec_host.numpy()[: min(Q, 4096)], rec_dev[: min(Q, 4096)].cpu().numpy()))
+    same = bool(np.array_equal(rec_host.numpy(), rec_dev.cpu().numpy())
+                and np.array_equal(cnt_host.numpy(), cnt_dev.cpu().numpy()))
 
     if rank == 0:
         total_q = Q * world

@@ -46,6 +46,8 @@ struct DevBuf {
 };
 
 enum Stage { ST_NONE = 0, ST_QUERIES = 1, ST_PREPLACED = 2, ST_SELECTED = 3, ST_PLACED = 4 };
+constexpr int kPreplaceTQ = 256;        // queries per preplacement tile (= CTA size)
+constexpr int kWindowBin = 4;           // work list is sorted by (edge, window start / kWindowBin)
 
 }  // namespace
 
@@ -71,6 +73,7 @@ struct epa_ctx {
   int stage = ST_NONE;
   uint32_t nq = 0;
   int max_span = 0;
+  int max_tile_width = 4;
   bool implicit_pairs = false;
   uint64_t n_pairs = 0;
   size_t pre_stride = 0;
@@ -553,7 +556,8 @@ extern "C" int epa_build_lookup(epa_ctx * ctx)
   const uint32_t B = ctx->n_edges;
   const size_t lookup_doubles = (size_t) B * ctx->n_pad * K;
   if (!ctx->d_lookup) CU(cudaMalloc(&ctx->d_lookup, lookup_doubles * sizeof(double)));
-  CU(cudaMemsetAsync(ctx->d_lookup, 0, lookup_doubles * sizeof(double), ctx->stream));
+  if (ctx->n_pad != n)      // pad rows must read as zero; every real row is written by the kernel
+    CU(cudaMemsetAsync(ctx->d_lookup, 0, lookup_doubles * sizeof(double), ctx->stream));
 
   std::vector<double> lengths(B + 1);
   for (uint32_t i = 0; i < B; ++i) lengths[i] = ctx->h_edges[i].length / 2.0;
@@ -569,7 +573,7 @@ extern "C" int epa_build_lookup(epa_ctx * ctx)
   LAUNCHED(ctx);
   if (S == 4 && R == 4)
   {
-    dim3 grid(B, (n + 63) / 64);
+    dim3 grid(B, (n + LOOKUP_DNA_SITES_PER_BLOCK - 1) / LOOKUP_DNA_SITES_PER_BLOCK);
     lookup_build_dna_kernel<<<grid, 256, 0, ctx->stream>>>(ctx->d_model, ctx->tree, n, ctx->n_pad, ctx->d_edges, d_pm, d_col, ctx->d_lookup);
     LAUNCHED(ctx);
   }
@@ -670,11 +674,32 @@ extern "C" int epa_encode_queries_dev(epa_ctx * ctx, const char * seqs_dev, uint
                                                          ctx->codes.as<uint8_t>(), ctx->begin.as<int>(),
                                                          ctx->span.as<int>(), ctx->d_flags);
   LAUNCHED(ctx);
+  // counting sort of the queries by window start (tiles of the preplacement kernel and the
+  // all-pairs work order of the thorough kernel follow it) + site range of every tile
+  {
+    const uint32_t nq = n_queries;
+    const int n = ctx->n;
+    const uint32_t n_tiles = (nq + kPreplaceTQ - 1) / kPreplaceTQ;
+    CU(ctx->perm.ensure(nq * sizeof(uint32_t)));
+    CU(ctx->hist.ensure((size_t) (n + 2) * sizeof(uint32_t)));
+    CU(ctx->range.ensure(n_tiles * sizeof(int2)));
+    CU(cudaMemsetAsync(ctx->hist.p, 0, (size_t) (n + 2) * sizeof(uint32_t), ctx->stream));
+    histogram_kernel<<<(nq + 255) / 256, 256, 0, ctx->stream>>>(ctx->begin.as<int>(), nq, ctx->hist.as<uint32_t>());
+    LAUNCHED(ctx);
+    exclusive_scan_kernel<<<1, 1024, 0, ctx->stream>>>(ctx->hist.as<uint32_t>(), ctx->hist.as<uint32_t>(), (uint32_t) n + 1, nullptr);
+    LAUNCHED(ctx);
+    scatter_by_key_kernel<<<(nq + 255) / 256, 256, 0, ctx->stream>>>(ctx->begin.as<int>(), nq, ctx->hist.as<uint32_t>(), ctx->perm.as<uint32_t>());
+    LAUNCHED(ctx);
+    tile_range_kernel<<<(n_tiles + 7) / 8, 256, 0, ctx->stream>>>(ctx->perm.as<uint32_t>(), ctx->begin.as<int>(), ctx->span.as<int>(),
+                                                               nq, kPreplaceTQ, n_tiles, ctx->range.as<int2>(), ctx->d_flags + 2);
+    LAUNCHED(ctx);
+  }
   CU(cudaEventRecord(ctx->ev[1], ctx->stream));
   int flags[8];
   if (int rc = read_flags(ctx, flags)) return rc;
   if (flags[0] == 1) return fail(ctx, EPA_ERR_QUERY, "query %d contains a character that is not valid for this data type", flags[1] - 1);
   if (flags[0] == 2) return fail(ctx, EPA_ERR_QUERY, "query %d consists entirely of gaps", flags[1] - 1);
+  ctx->max_tile_width = std::max(4, flags[2]);
   ctx->max_span = flags[3];
   ctx->stage = ST_QUERIES;
   return EPA_OK;
@@ -684,7 +709,7 @@ namespace {
 template <int K>
 int launch_preplace(epa_ctx * ctx, int maxw)
 {
-  constexpr int TQ = 256, NS = 2;
+  constexpr int TQ = kPreplaceTQ, NS = 2;
   const uint32_t nq = ctx->nq;
   const uint32_t n_tiles = (nq + TQ - 1) / TQ;
   const size_t per_site = (size_t) NS * K * 8 + TQ;              // stage bytes + code bytes per site
@@ -710,29 +735,9 @@ extern "C" int epa_preplace(epa_ctx * ctx)
   const uint32_t nq = ctx->nq;
   ctx->pre_stride = (ctx->n_edges + 3u) & ~3u;
   if (nq == 0) { ctx->stage = ST_PREPLACED; return EPA_OK; }
-  constexpr int TQ = 256;
-  const uint32_t n_tiles = (nq + TQ - 1) / TQ;
-  const int n = ctx->n;
-  CU(ctx->perm.ensure(nq * sizeof(uint32_t)));
-  CU(ctx->hist.ensure((size_t) (n + 2) * sizeof(uint32_t)));
-  CU(ctx->range.ensure(n_tiles * sizeof(int2)));
   CU(ctx->pre.ensure((size_t) nq * ctx->pre_stride * sizeof(double)));
   CU(cudaEventRecord(ctx->ev[1], ctx->stream));
-  // counting sort of the queries by window start
-  CU(cudaMemsetAsync(ctx->hist.p, 0, (size_t) (n + 2) * sizeof(uint32_t), ctx->stream));
-  histogram_kernel<<<(nq + 255) / 256, 256, 0, ctx->stream>>>(ctx->begin.as<int>(), nq, ctx->hist.as<uint32_t>());
-  LAUNCHED(ctx);
-  exclusive_scan_kernel<<<1, 1024, 0, ctx->stream>>>(ctx->hist.as<uint32_t>(), ctx->hist.as<uint32_t>(), (uint32_t) n + 1, nullptr);
-  LAUNCHED(ctx);
-  scatter_by_key_kernel<<<(nq + 255) / 256, 256, 0, ctx->stream>>>(ctx->begin.as<int>(), nq, ctx->hist.as<uint32_t>(), ctx->perm.as<uint32_t>());
-  LAUNCHED(ctx);
-  CU(cudaMemsetAsync(ctx->d_flags + 2, 0, sizeof(int), ctx->stream));
-  tile_range_kernel<<<(n_tiles + 7) / 8, 256, 0, ctx->stream>>>(ctx->perm.as<uint32_t>(), ctx->begin.as<int>(), ctx->span.as<int>(),
-                                                             nq, TQ, n_tiles, ctx->range.as<int2>(), ctx->d_flags + 2);
-  LAUNCHED(ctx);
-  int flags[8];
-  if (int rc = read_flags(ctx, flags)) return rc;
-  const int maxw = std::max(4, flags[2]);
+  const int maxw = ctx->max_tile_width;
   int rc = (ctx->K == 16) ? launch_preplace<16>(ctx, maxw) : launch_preplace<26>(ctx, maxw);
   if (rc) return rc;
   CU(cudaEventRecord(ctx->ev[2], ctx->stream));
@@ -779,8 +784,11 @@ extern "C" int epa_select(epa_ctx * ctx, const epa_options * opts, uint64_t * n_
       CU(ctx->off.ensure(nq * sizeof(uint32_t)));
       CU(ctx->cutv.ensure(nq * sizeof(double)));
       CU(ctx->cuti.ensure(nq * sizeof(int)));
-      CU(ctx->edge_hist.ensure((size_t) (B + 1) * sizeof(uint32_t)));
-      CU(ctx->edge_off.ensure((size_t) (B + 1) * sizeof(uint32_t)));
+      // work list order: edge-major, then window start in bins of kWindowBin sites
+      const uint32_t nbins = (uint32_t) (ctx->n / kWindowBin) + 1;
+      const size_t nkeys = (size_t) B * nbins;
+      if (nkeys > 0x7fffffffull) return fail(ctx, EPA_ERR_ARG, "tree x alignment too large for the work-list sort");
+      CU(ctx->edge_hist.ensure((nkeys + 1) * sizeof(uint32_t)));
       const unsigned blocks = (nq + 7) / 8;
       select_count_kernel<<<blocks, 256, 0, ctx->stream>>>(ctx->pre.as<double>(), ctx->pre_stride, (int) B, nq,
                                                            opts->prescoring_threshold, ctx->cnt.as<uint32_t>(),
@@ -796,18 +804,20 @@ extern "C" int epa_select(epa_ctx * ctx, const epa_options * opts, uint64_t * n_
       CU(ctx->pair_q.ensure(total * sizeof(uint32_t)));
       CU(ctx->pair_e.ensure(total * sizeof(uint32_t)));
       CU(ctx->work.ensure(total * sizeof(uint32_t)));
-      CU(cudaMemsetAsync(ctx->edge_hist.p, 0, (size_t) (B + 1) * sizeof(uint32_t), ctx->stream));
+      CU(cudaMemsetAsync(ctx->edge_hist.p, 0, (nkeys + 1) * sizeof(uint32_t), ctx->stream));
       select_fill_kernel<<<blocks, 256, 0, ctx->stream>>>(ctx->pre.as<double>(), ctx->pre_stride, (int) B, nq,
                                                           ctx->off.as<uint32_t>(), ctx->cutv.as<double>(), ctx->cuti.as<int>(),
+                                                          ctx->begin.as<int>(), kWindowBin, nbins,
                                                           ctx->pair_q.as<uint32_t>(), ctx->pair_e.as<uint32_t>(),
                                                           ctx->edge_hist.as<uint32_t>());
       LAUNCHED(ctx);
-      exclusive_scan_kernel<<<1, 1024, 0, ctx->stream>>>(ctx->edge_hist.as<uint32_t>(), ctx->edge_off.as<uint32_t>(), B, nullptr);
+      exclusive_scan_kernel<<<1, 1024, 0, ctx->stream>>>(ctx->edge_hist.as<uint32_t>(), ctx->edge_hist.as<uint32_t>(), (uint32_t) nkeys, nullptr);
       LAUNCHED(ctx);
       if (total)
       {
-        work_scatter_kernel<<<(unsigned) ((total + 255) / 256), 256, 0, ctx->stream>>>(ctx->pair_e.as<uint32_t>(), (uint32_t) total,
-                                                                                    ctx->edge_off.as<uint32_t>(), ctx->work.as<uint32_t>());
+        work_scatter_kernel<<<(unsigned) ((total + 255) / 256), 256, 0, ctx->stream>>>(ctx->pair_q.as<uint32_t>(), ctx->pair_e.as<uint32_t>(),
+                                                                                    (uint32_t) total, ctx->begin.as<int>(), kWindowBin, nbins,
+                                                                                    ctx->edge_hist.as<uint32_t>(), ctx->work.as<uint32_t>());
         LAUNCHED(ctx);
       }
     }
@@ -841,7 +851,7 @@ int launch_blo_dna(epa_ctx * ctx, BloArgs & a)
   {
     warps = 8;
     const unsigned grid = (unsigned) std::min<uint64_t>((uint64_t) ctx->sm_count * 2, (a.n_pairs + warps - 1) / warps);
-    CU(ctx->scratch.ensure((size_t) grid * warps * ctx->n * R * 4 * sizeof(double)));
+    CU(ctx->scratch.ensure((size_t) grid * warps * (4 * R) * blo_plane_stride(ctx->n) * sizeof(double)));
     a.scratch = ctx->scratch.as<double>();
     a.wcap = 0;
     const size_t smem = BloWarpSmem<R>::doubles(0) * sizeof(double) * warps;
@@ -871,6 +881,7 @@ extern "C" int epa_place_pairs(epa_ctx * ctx, const epa_options * opts)
     a.work = ctx->implicit_pairs ? nullptr : ctx->work.as<uint32_t>();
     a.pair_q = ctx->implicit_pairs ? nullptr : ctx->pair_q.as<uint32_t>();
     a.pair_e = ctx->implicit_pairs ? nullptr : ctx->pair_e.as<uint32_t>();
+    a.perm = ctx->perm.as<uint32_t>();
     a.n_pairs = (uint32_t) ctx->n_pairs; a.nq = ctx->nq; a.n_edges = ctx->n_edges;
     a.counter = ctx->d_counter; a.out = ctx->res.as<BloResult>(); a.scratch = nullptr; a.wcap = 0;
     int rc;

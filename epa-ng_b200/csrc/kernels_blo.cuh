@@ -11,13 +11,18 @@
 //   CLV update / edge logl          LP/core_partials.c:202-352,612-766, LP/core_likelihood.c:351-578
 //   range focus                     src/core/pll/pll_util.cpp:388-418
 //
-// DNA kernel (S = 4): ONE WARP PER PAIR. R lanes share a site (lane % R = rate category), so a warp
-// sweeps 32/R sites per step and every lane reads exactly one 32-byte sector of each CLV: the
-// CLV windows stream fully coalesced from L2/HBM. The rate sum is log2(R) xor-shuffles, the site
-// sum a fixed-order butterfly. The sumtable (the only per-pair state that the Newton iterations
-// re-read) lives in the warp's shared-memory slice; transition matrices and the per-mask tip
-// vectors are rebuilt by the warp itself whenever a length changes. Nothing but 24 bytes per
-// pair leaves the SM.
+// DNA kernel (S = 4): ONE WARP PER PAIR, two lane mappings.
+//  * CLV passes (inner CLV, edge log-likelihood, sumtable build): R lanes share a site
+//    (lane % R = rate category), a warp sweeps 32/R sites per step and every lane reads exactly one
+//    32-byte sector of each CLV, so the CLV windows stream fully coalesced from L2/HBM. The rate sum
+//    is log2(R) xor-shuffles; the per-site log is rotated over the R lanes of a site (one log per
+//    lane per R sites instead of one per site).
+//  * Newton iterations: lane = site. The sumtable lives in the warp's shared-memory slice as 4R
+//    site-major planes, so the 4R loads of a site are conflict-free, the whole site evaluates in
+//    registers without any cross-lane traffic, and only the final (f, f') pair is butterfly-reduced.
+// Transition matrices and per-mask tip vectors are rebuilt by the warp whenever a length changes.
+// Work items come from an edge-major, window-sorted list in blocks of 32 per CTA, so the warps of a
+// CTA work on overlapping CLV windows (L1 reuse). Nothing but 24 bytes per pair leaves the SM.
 #pragma once
 #include "common.cuh"
 
@@ -33,6 +38,7 @@ __constant__ DevModel c_model;
 #define EPA_BLO_EPSILON 1e-1                          /* src/core/pll/optimize.hpp:9 */
 #define EPA_NR_MAX_ITERS 30
 #define EPA_SMOOTHINGS 32
+#define EPA_WORK_BLOCK 32u
 
 struct BloResult { double logl, pendant, distal; };
 
@@ -43,16 +49,19 @@ struct BloArgs {
   const uint8_t * codes;          // [nq][n]
   const int * begin;
   const int * span;
-  const uint32_t * work;          // edge-major permutation of pair ids, or NULL (identity)
+  const uint32_t * work;          // explicit mode: (edge, window)-sorted permutation of pair ids
   const uint32_t * pair_q;        // NULL = implicit all-pairs mode
   const uint32_t * pair_e;
+  const uint32_t * perm;          // implicit mode: queries sorted by window start
   uint32_t n_pairs;
-  uint32_t nq, n_edges;           // implicit mode: item i -> edge i / nq, query i % nq, pair id q*n_edges+e
+  uint32_t nq, n_edges;           // implicit mode: item i -> edge i / nq, query perm[i % nq], pair id q*n_edges+e
   unsigned long long * counter;   // dynamic work counter (zeroed before launch)
   BloResult * out;                // [pair id]
-  double * scratch;               // global sumtable scratch (GS variant): [total warps][n*R*4]
+  double * scratch;               // global sumtable scratch (GS variant): [total warps][4R planes]
   int wcap;                       // sites the shared-memory sumtable can hold
 };
+
+__host__ __device__ constexpr int blo_plane_stride(int wcap) { return ((wcap + 3) & ~3) + 1; }
 
 template <int R>
 struct BloWarpSmem {
@@ -61,18 +70,20 @@ struct BloWarpSmem {
   static constexpr int P_P = R * 16;
   static constexpr int P_E = 2 * R * 16;
   static constexpr int TV = 3 * R * 16;              // [R][16 masks][4]
-  static constexpr int EX = TV + R * 64;             // [R*4]
-  static constexpr int SUM = EX + R * 4;             // [wcap][R][4]
-  __host__ __device__ static constexpr size_t doubles(int wcap) { return (size_t) SUM + (size_t) wcap * R * 4; }
+  static constexpr int EX = TV + R * 64;             // [R*4] expm1 scratch; [3][4R] diag tables (R = 8)
+  static constexpr int SUM = EX + 3 * R * 4;         // [4R planes][plane stride]
+  __host__ __device__ static constexpr size_t doubles(int wcap)
+  {
+    return (size_t) SUM + (wcap > 0 ? (size_t) 4 * R * blo_plane_stride(wcap) : 0);
+  }
 };
 
 struct BloCtaSmem {
   double V[16], Vinv[16];             // lane-divergent indexing in warp_pmatrix
   __align__(16) double tipleft[64];   // [mask][j] = sum_{k in mask} pi_k Vinv[k][j]
+  unsigned long long q_next, q_end;   // current block of work items
+  int q_lock;
 };
-
-// sumtable of one pair, split in two 16-byte planes so that a warp's accesses are conflict-free
-struct SumTab { double2 * lo; double2 * hi; };
 
 // P[r][i][j] = delta_ij + sum_k Vinv[i][k] expm1(lambda_k rate_r t) V[k][j]   (LP/core_pmatrix.c:185-249)
 template <int R>
@@ -122,53 +133,71 @@ __device__ __forceinline__ bool group_all(bool small, int lane)
 {
   if (R == 1) return small;
   const unsigned ballot = __ballot_sync(0xffffffffu, small);
-  const unsigned gm = (R == 32) ? 0xffffffffu : ((1u << R) - 1u);
+  const unsigned gm = (1u << R) - 1u;
   return ((ballot >> (lane & ~(R - 1))) & gm) == gm;
 }
 
-// first and second derivative sums over the window (LP/core_derivatives.c:643-858)
+// first and second derivative sums over the window (LP/core_derivatives.c:643-858), lane = site
 template <int R>
-__device__ __forceinline__ void warp_derivatives(const SumTab sum, int w, double t, int lane,
-                                                 double & f, double & df)
+__device__ __forceinline__ void warp_derivatives(const double * sum, int pstride, double * ex, int w, double t,
+                                                 int lane, double & f, double & df)
 {
-  constexpr int SPW = 32 / R;
-  const int r = lane % R, so = lane / R;
-  // diag table of this lane's rate: lanes 0..4R-1 compute one exponential each
+  constexpr int NK = 4 * R;
+  // diag tables: lane k < 4R computes exp(lambda_j rate_r t), weights folded in
   double e = 0.0, lk = 0.0;
   {
-    const int idx = lane % (R * 4);
-    lk = c_model.eigenvals[idx & 3] * c_model.rates[idx >> 2];
-    e = exp(lk * t);
+    const int k = lane % NK;
+    lk = c_model.eigenvals[k & 3] * c_model.rates[k >> 2];
+    e = exp(lk * t) * c_model.weights[k >> 2];
   }
-  double d0[4], d1[4], d2[4];
-  #pragma unroll
-  for (int j = 0; j < 4; ++j)
-  {
-    const double ej = __shfl_sync(0xffffffffu, e, r * 4 + j);
-    const double lj = __shfl_sync(0xffffffffu, lk, r * 4 + j);
-    d0[j] = ej; d1[j] = lj * ej; d2[j] = lj * lj * ej;
-  }
-  const double wr = c_model.weights[r];
   double a1 = 0.0, a2 = 0.0;
-  for (int s0 = 0; s0 < w; s0 += SPW)
+  if constexpr (R <= 4)
   {
-    const int s = s0 + so;
-    const bool act = s < w;
-    const int sc = act ? s : w - 1;
-    const double2 x01 = sum.lo[sc * R + r], x23 = sum.hi[sc * R + r];
-    double c0 = x01.x * d0[0] + x01.y * d0[1] + x23.x * d0[2] + x23.y * d0[3];
-    double c1 = x01.x * d1[0] + x01.y * d1[1] + x23.x * d1[2] + x23.y * d1[3];
-    double c2 = x01.x * d2[0] + x01.y * d2[1] + x23.x * d2[2] + x23.y * d2[3];
-    c0 = rate_sum<R>(c0 * wr);
-    c1 = rate_sum<R>(c1 * wr);
-    c2 = rate_sum<R>(c2 * wr);
-    if (act && r == 0)
+    double d0[NK], d1[NK], d2[NK];
+    #pragma unroll
+    for (int k = 0; k < NK; ++k)
     {
+      const double ek = __shfl_sync(0xffffffffu, e, k);
+      const double lkk = __shfl_sync(0xffffffffu, lk, k);
+      d0[k] = ek; d1[k] = lkk * ek; d2[k] = lkk * d1[k];
+    }
+    #pragma unroll 2
+    for (int s = lane; s < w; s += 32)
+    {
+      double c0 = 0.0, c1 = 0.0, c2 = 0.0;
+      #pragma unroll
+      for (int k = 0; k < NK; ++k)
+      {
+        const double x = sum[k * pstride + s];
+        c0 += x * d0[k]; c1 += x * d1[k]; c2 += x * d2[k];
+      }
       const double inv = 1.0 / c0;
       const double g1 = -c1 * inv;
       a1 += g1;
       a2 += g1 * g1 - c2 * inv;
     }
+  }
+  else
+  {
+    // many rate categories: diag tables through shared memory (broadcast reads)
+    __syncwarp();
+    if (lane < NK) { ex[lane] = e; ex[NK + lane] = lk * e; ex[2 * NK + lane] = lk * lk * e; }
+    __syncwarp();
+    for (int s = lane; s < w; s += 32)
+    {
+      double c0 = 0.0, c1 = 0.0, c2 = 0.0;
+      #pragma unroll 8
+      for (int k = 0; k < NK; ++k)
+      {
+        const double x = sum[k * pstride + s];
+        c0 += x * ex[k]; c1 += x * ex[NK + k]; c2 += x * ex[2 * NK + k];
+      }
+      const double inv = 1.0 / c0;
+      const double g1 = -c1 * inv;
+      a1 += g1;
+      a2 += g1 * g1 - c2 * inv;
+    }
+    __syncwarp();
   }
   f = warp_sum(a1);
   df = warp_sum(a2);
@@ -176,8 +205,8 @@ __device__ __forceinline__ void warp_derivatives(const SumTab sum, int w, double
 
 // bounded Newton-Raphson, PM/optimize/opt_algorithms.c:133-262; returns 0.0 on failure
 template <int R>
-__device__ __forceinline__ double warp_newton(const SumTab sum, int w, int lane, double xmin,
-                                              double xguess, double xmax, double tol)
+__device__ __forceinline__ double warp_newton(const double * sum, int pstride, double * ex, int w, int lane,
+                                              double xmin, double xguess, double xmax, double tol)
 {
   double x = fmax(fmin(xguess, xmax), xmin);
   double xl = xmin, xh = xmax;
@@ -187,7 +216,7 @@ __device__ __forceinline__ double warp_newton(const SumTab sum, int w, int lane,
   {
     if (iter++ > EPA_NR_MAX_ITERS) return 0.0;
     double f, df;
-    warp_derivatives<R>(sum, w, x, lane, f, df);
+    warp_derivatives<R>(sum, pstride, ex, w, x, lane, f, df);
     if (!isfinite(f) || !isfinite(df)) return 0.0;
     double dx;
     if (df > 0.0)
@@ -207,10 +236,65 @@ __device__ __forceinline__ double warp_newton(const SumTab sum, int w, int lane,
   }
 }
 
+// One (site, rate) unit of pass A: inner CLV entries toward the new tip, the weighted likelihood
+// term of the site (summed over its R lanes) and the pendant sumtable row.
+struct TipUnit { double term; uint32_t scal; };
+
+template <int R>
+__device__ __forceinline__ TipUnit pass_tip_unit(const BloCtaSmem & cs, const double (&pd)[16], const double (&pp)[16],
+                                                 const double * tv, double wr, double * sum, int pstride,
+                                                 const double * __restrict__ D, const double * __restrict__ X,
+                                                 const uint32_t * __restrict__ sD, const uint32_t * __restrict__ sX,
+                                                 const uint8_t * __restrict__ qc, int s, int w, int r, int lane)
+{
+  const bool act = s < w;
+  const int sc = act ? s : w - 1;
+  double dv[4], xv[4], in[4];
+  load_vec<4>(D + ((size_t) sc * R + r) * 4, dv);
+  load_vec<4>(X + ((size_t) sc * R + r) * 4, xv);
+  const int mask = qc[sc] & 15;
+  uint32_t scal = __ldg(sD + sc) + __ldg(sX + sc);
+  bool small = true;
+  #pragma unroll
+  for (int i = 0; i < 4; ++i)
+  {
+    const double ta = pd[i * 4] * dv[0] + pd[i * 4 + 1] * dv[1] + pd[i * 4 + 2] * dv[2] + pd[i * 4 + 3] * dv[3];
+    const double tb = pp[i * 4] * xv[0] + pp[i * 4 + 1] * xv[1] + pp[i * 4 + 2] * xv[2] + pp[i * 4 + 3] * xv[3];
+    in[i] = ta * tb;
+    small = small && (in[i] < EPA_SCALE_THRESHOLD);
+  }
+  if (group_all<R>(small, lane))
+  {
+    #pragma unroll
+    for (int i = 0; i < 4; ++i) in[i] *= EPA_SCALE_FACTOR;
+    scal += 1;
+  }
+  const double2 * tp = reinterpret_cast<const double2 *>(tv + mask * 4);
+  const double2 t01 = tp[0], t23 = tp[1];
+  double term = (in[0] * c_model.freqs[0]) * t01.x + (in[1] * c_model.freqs[1]) * t01.y
+              + (in[2] * c_model.freqs[2]) * t23.x + (in[3] * c_model.freqs[3]) * t23.y;
+  term = rate_sum<R>(term * wr);
+  if (act)
+  {
+    // pendant sumtable: tip side takes pi*Vinv, inner side takes V
+    #pragma unroll
+    for (int j = 0; j < 4; ++j)
+    {
+      const double right = c_model.eigenvecs[j * 4] * in[0] + c_model.eigenvecs[j * 4 + 1] * in[1]
+                         + c_model.eigenvecs[j * 4 + 2] * in[2] + c_model.eigenvecs[j * 4 + 3] * in[3];
+      sum[(r * 4 + j) * pstride + s] = cs.tipleft[mask * 4 + j] * right;
+    }
+  }
+  TipUnit u;
+  u.term = act ? term : 1.0;
+  u.scal = act ? scal : 0u;
+  return u;
+}
+
 // Pass A: inner CLV toward the new tip from (D, X); returns the edge log-likelihood
 // new_tip | inner over the window and leaves the pendant sumtable (inner vs tip) in `sum`.
 template <int R>
-__device__ __forceinline__ double warp_pass_tip(const BloCtaSmem & cs, const double * ws, const SumTab sum,
+__device__ __forceinline__ double warp_pass_tip(const BloCtaSmem & cs, const double * ws, double * sum, int pstride,
                                                 const double * __restrict__ D, const double * __restrict__ X,
                                                 const uint32_t * __restrict__ sD, const uint32_t * __restrict__ sX,
                                                 const uint8_t * __restrict__ qc, int w, int lane)
@@ -223,55 +307,18 @@ __device__ __forceinline__ double warp_pass_tip(const BloCtaSmem & cs, const dou
   const double * tv = ws + BloWarpSmem<R>::TV + r * 64;
   const double wr = c_model.weights[r];
   double acc = 0.0;
-  #pragma unroll 2
-  for (int s0 = 0; s0 < w; s0 += SPW)
+  // R site groups per trip: the R lanes of a site take turns at the logarithm
+  for (int s0 = 0; s0 < w; s0 += SPW * R)
   {
-    const int s = s0 + so;
-    const bool act = s < w;
-    const int sc = act ? s : w - 1;
-    double dv[4], xv[4], in[4];
-    load_vec<4>(D + ((size_t) sc * R + r) * 4, dv);
-    load_vec<4>(X + ((size_t) sc * R + r) * 4, xv);
-    const int mask = qc[sc] & 15;
-    uint32_t scal = 0;
-    if (r == 0) scal = sD[sc] + sX[sc];
-    bool small = true;
+    double mine = 1.0;
+    uint32_t mscal = 0;
     #pragma unroll
-    for (int i = 0; i < 4; ++i)
+    for (int u = 0; u < R; ++u)
     {
-      const double ta = pd[i * 4] * dv[0] + pd[i * 4 + 1] * dv[1] + pd[i * 4 + 2] * dv[2] + pd[i * 4 + 3] * dv[3];
-      const double tb = pp[i * 4] * xv[0] + pp[i * 4 + 1] * xv[1] + pp[i * 4 + 2] * xv[2] + pp[i * 4 + 3] * xv[3];
-      in[i] = ta * tb;
-      small = small && (in[i] < EPA_SCALE_THRESHOLD);
+      const TipUnit t = pass_tip_unit<R>(cs, pd, pp, tv, wr, sum, pstride, D, X, sD, sX, qc, s0 + u * SPW + so, w, r, lane);
+      if (u == r) { mine = t.term; mscal = t.scal; }
     }
-    if (group_all<R>(small, lane))
-    {
-      #pragma unroll
-      for (int i = 0; i < 4; ++i) in[i] *= EPA_SCALE_FACTOR;
-      scal += 1;
-    }
-    // edge log-likelihood term of this rate
-    const double2 * tp = reinterpret_cast<const double2 *>(tv + mask * 4);
-    const double2 t01 = tp[0], t23 = tp[1];
-    double term = (in[0] * c_model.freqs[0]) * t01.x + (in[1] * c_model.freqs[1]) * t01.y
-                + (in[2] * c_model.freqs[2]) * t23.x + (in[3] * c_model.freqs[3]) * t23.y;
-    term = rate_sum<R>(term * wr);
-    if (act && r == 0)
-      acc += log(term) + (scal ? (double) scal * EPA_LOG_SCALE_THRESHOLD : 0.0);
-    // pendant sumtable: tip side takes pi*Vinv, inner side takes V
-    if (act)
-    {
-      double st[4];
-      #pragma unroll
-      for (int j = 0; j < 4; ++j)
-      {
-        const double right = c_model.eigenvecs[j * 4] * in[0] + c_model.eigenvecs[j * 4 + 1] * in[1]
-                           + c_model.eigenvecs[j * 4 + 2] * in[2] + c_model.eigenvecs[j * 4 + 3] * in[3];
-        st[j] = cs.tipleft[mask * 4 + j] * right;
-      }
-      sum.lo[s * R + r] = make_double2(st[0], st[1]);
-      sum.hi[s * R + r] = make_double2(st[2], st[3]);
-    }
+    acc += log(mine) + (mscal ? (double) mscal * EPA_LOG_SCALE_THRESHOLD : 0.0);
   }
   __syncwarp();
   return warp_sum(acc);
@@ -279,7 +326,7 @@ __device__ __forceinline__ double warp_pass_tip(const BloCtaSmem & cs, const dou
 
 // Pass B: inner CLV toward the distal node from (T, X); leaves the distal sumtable (D vs inner)
 template <int R>
-__device__ __forceinline__ void warp_pass_distal(const BloCtaSmem & cs, const double * ws, const SumTab sum,
+__device__ __forceinline__ void warp_pass_distal(const BloCtaSmem & cs, const double * ws, double * sum, int pstride,
                                                  const double * __restrict__ D, const double * __restrict__ X,
                                                  const uint8_t * __restrict__ qc, int w, int lane)
 {
@@ -314,7 +361,6 @@ __device__ __forceinline__ void warp_pass_distal(const BloCtaSmem & cs, const do
     }
     if (act)
     {
-      double st[4];
       #pragma unroll
       for (int j = 0; j < 4; ++j)
       {
@@ -322,13 +368,31 @@ __device__ __forceinline__ void warp_pass_distal(const BloCtaSmem & cs, const do
                           + dv[2] * c_model.pivinv[8 + j] + dv[3] * c_model.pivinv[12 + j];
         const double right = c_model.eigenvecs[j * 4] * in[0] + c_model.eigenvecs[j * 4 + 1] * in[1]
                            + c_model.eigenvecs[j * 4 + 2] * in[2] + c_model.eigenvecs[j * 4 + 3] * in[3];
-        st[j] = left * right;
+        sum[(r * 4 + j) * pstride + s] = left * right;
       }
-      sum.lo[s * R + r] = make_double2(st[0], st[1]);
-      sum.hi[s * R + r] = make_double2(st[2], st[3]);
     }
   }
   __syncwarp();
+}
+
+// next work item of the CTA's current block of EPA_WORK_BLOCK consecutive items (lane 0 only)
+__device__ __forceinline__ unsigned long long cta_next_item(BloCtaSmem & cs, unsigned long long * counter)
+{
+  while (atomicCAS(&cs.q_lock, 0, 1) != 0) { }
+  __threadfence_block();
+  volatile unsigned long long * qn = &cs.q_next;
+  volatile unsigned long long * qe = &cs.q_end;
+  if (*qn == *qe)
+  {
+    const unsigned long long base = atomicAdd(counter, (unsigned long long) EPA_WORK_BLOCK);
+    *qn = base;
+    *qe = base + EPA_WORK_BLOCK;
+  }
+  const unsigned long long item = *qn;
+  *qn = item + 1;
+  __threadfence_block();
+  atomicExch(&cs.q_lock, 0);
+  return item;
 }
 
 // GS = sumtable in global scratch (windows that do not fit the shared-memory slice)
@@ -347,29 +411,26 @@ blo_dna_kernel(BloArgs a)
   }
   for (int i = threadIdx.x; i < 64; i += blockDim.x)
   {
-    // tipleft[mask][j] = sum_{k in mask} pi_k Vinv[k][j]
     const int mask = i >> 2, j = i & 3;
     double acc = 0.0;
     for (int k = 0; k < 4; ++k)
       if ((mask >> k) & 1) acc += c_model.pivinv[k * 4 + j];
     cs.tipleft[i] = acc;
   }
+  if (threadIdx.x == 0) { cs.q_next = 0; cs.q_end = 0; cs.q_lock = 0; }
   __syncthreads();
 
+  const int pstride = blo_plane_stride(GS ? a.n : a.wcap);
   const size_t per_warp = BloWarpSmem<R>::doubles(GS ? 0 : a.wcap);
   double * ws = smem_d + (size_t) warp * per_warp;
-  const int cap_units = (GS ? a.n : a.wcap) * R;
-  double * sum_base = GS ? a.scratch + ((size_t) blockIdx.x * n_warps + warp) * (size_t) a.n * R * 4
-                         : ws + BloWarpSmem<R>::SUM;
-  SumTab sum;
-  sum.lo = reinterpret_cast<double2 *>(sum_base);
-  sum.hi = sum.lo + cap_units;
+  double * sum = GS ? a.scratch + ((size_t) blockIdx.x * n_warps + warp) * (size_t) (4 * R) * pstride
+                    : ws + BloWarpSmem<R>::SUM;
   double * ex = ws + BloWarpSmem<R>::EX;
 
   for (;;)
   {
     unsigned long long item = 0;
-    if (lane == 0) item = atomicAdd(a.counter, 1ull);
+    if (lane == 0) item = cta_next_item(cs, a.counter);
     item = __shfl_sync(0xffffffffu, item, 0);
     if (item >= a.n_pairs) break;
     uint32_t pid, q, e;
@@ -382,7 +443,7 @@ blo_dna_kernel(BloArgs a)
     else
     {
       e = (uint32_t) (item / a.nq);
-      q = (uint32_t) (item % a.nq);
+      q = a.perm ? a.perm[item % a.nq] : (uint32_t) (item % a.nq);
       pid = q * a.n_edges + e;
     }
     const EdgeDev ed = a.edges[e];
@@ -408,7 +469,7 @@ blo_dna_kernel(BloArgs a)
     warp_pmatrix<R>(cs, len_e, ws + BloWarpSmem<R>::P_E, ex, lane);
     warp_tipvec<R>(ws + BloWarpSmem<R>::P_E, ws + BloWarpSmem<R>::TV, lane);
 
-    double loglikelihood = -warp_pass_tip<R>(cs, ws, sum, D, X, sD, sX, qc, w, lane);
+    double loglikelihood = -warp_pass_tip<R>(cs, ws, sum, pstride, D, X, sD, sX, qc, w, lane);
     int smoothings = EPA_SMOOTHINGS;
     while (smoothings)
     {
@@ -416,7 +477,7 @@ blo_dna_kernel(BloArgs a)
       // pendant
       double xmin = EPA_MIN_BRLEN, xmax = EPA_MAX_BRLEN, xtol = xmin / 10.0, xguess = len_e;
       if (xguess < xmin || xguess > xmax) xguess = EPA_DEFAULT_BRLEN;
-      double xres = warp_newton<R>(sum, w, lane, xmin, xguess, xmax, xtol);
+      double xres = warp_newton<R>(sum, pstride, ex, w, lane, xmin, xguess, xmax, xtol);
       if (xres > 0.0)
       {
         len_e = xres;
@@ -424,13 +485,13 @@ blo_dna_kernel(BloArgs a)
         warp_tipvec<R>(ws + BloWarpSmem<R>::P_E, ws + BloWarpSmem<R>::TV, lane);
       }
       // distal
-      warp_pass_distal<R>(cs, ws, sum, D, X, qc, w, lane);
+      warp_pass_distal<R>(cs, ws, sum, pstride, D, X, qc, w, lane);
       xguess = len_d;
       xmin = fmin(EPA_MIN_BRLEN / 2.0, original_length / 2.0);
       xtol = xmin / 10.0;
       xmax = original_length - xtol;
       if (xguess < xmin || xguess > xmax) xguess = original_length / 2.0;
-      xres = warp_newton<R>(sum, w, lane, xmin, xguess, xmax, xtol);
+      xres = warp_newton<R>(sum, pstride, ex, w, lane, xmin, xguess, xmax, xtol);
       if (xres > 0.0)
       {
         len_d = xres;
@@ -439,7 +500,7 @@ blo_dna_kernel(BloArgs a)
         warp_pmatrix<R>(cs, len_p, ws + BloWarpSmem<R>::P_P, ex, lane);
       }
       // score (also prepares the pendant sumtable of the next round)
-      const double new_logl = -warp_pass_tip<R>(cs, ws, sum, D, X, sD, sX, qc, w, lane);
+      const double new_logl = -warp_pass_tip<R>(cs, ws, sum, pstride, D, X, sD, sX, qc, w, lane);
       if (new_logl - loglikelihood > new_logl * 1e-14)
       {
         len_e = old_e;

@@ -230,8 +230,10 @@ lookup_build_kernel(const DevModel * __restrict__ m, DevTree tree, int n, int n_
 // Every lane loads one 32-byte sector of each CLV (a warp covers 1 KB contiguous per CLV), the
 // rate sum and the scaling decision run over 2 xor-shuffles, and each lane finishes 4 of the 16
 // columns (log + 32-byte store; the four lanes of a site write one 128-byte line).
-// grid = (n_edges, ceil(n / 64)), block = 256 threads = 64 sites.
+// grid = (n_edges, ceil(n / LOOKUP_DNA_SITES_PER_BLOCK)), block = 256 threads = 64 sites per trip.
 // ---------------------------------------------------------------------------------------------
+constexpr int LOOKUP_DNA_SITES_PER_BLOCK = 256;
+
 __global__ void __launch_bounds__(256)
 lookup_build_dna_kernel(const DevModel * __restrict__ m, DevTree tree, int n, int n_pad,
                         const EdgeDev * __restrict__ edges, const double * __restrict__ pmats_half,
@@ -239,68 +241,80 @@ lookup_build_dna_kernel(const DevModel * __restrict__ m, DevTree tree, int n, in
 {
   constexpr int S = 4, R = 4, K = 16;
   __shared__ double P[R * S * S];
-  __shared__ double M[R * K * S];
+  // column table transposed to [c][i/2][r] pairs: the four rate lanes of a site read four
+  // consecutive 16-byte words (conflict-free), the eight site groups of a warp broadcast
+  __shared__ double2 M2[K * 2 * R];
   const EdgeDev e = edges[blockIdx.x];
   stage_doubles(P, pmats_half + (size_t) blockIdx.x * R * S * S, R * S * S);
-  stage_doubles(M, coltab, R * K * S);
+  for (int idx = threadIdx.x; idx < K * 2 * R; idx += blockDim.x)
+  {
+    const int c = idx / (2 * R), ih = (idx / R) & 1, rr = idx % R;
+    M2[idx] = make_double2(__ldg(coltab + (rr * K + c) * S + 2 * ih), __ldg(coltab + (rr * K + c) * S + 2 * ih + 1));
+  }
   __syncthreads();
   const int r = threadIdx.x & 3;
-  const int site = blockIdx.y * 64 + (threadIdx.x >> 2);
-  const bool active = site < n;
-  const int s = active ? site : n - 1;
-
-  double dv[S], xv[S], inner[S];
-  load_vec<S>(tree.clv + e.distal * tree.clv_stride + (size_t) s * (R * S) + r * S, dv);
-  load_vec<S>(tree.clv + e.proximal * tree.clv_stride + (size_t) s * (R * S) + r * S, xv);
-  bool small = true;
+  // this lane's rate block of P(len/2) stays in registers for all its sites
+  double p[S * S];
   #pragma unroll
-  for (int i = 0; i < S; ++i)
-  {
-    double ta = 0.0, tb = 0.0;
-    #pragma unroll
-    for (int j = 0; j < S; ++j)
-    {
-      ta += P[(r * S + i) * S + j] * dv[j];
-      tb += P[(r * S + i) * S + j] * xv[j];
-    }
-    inner[i] = ta * tb;
-    small = small && (inner[i] < EPA_SCALE_THRESHOLD);
-  }
-  // all 16 entries of the site below the threshold? (lanes 4k..4k+3 hold one site)
-  const unsigned ballot = __ballot_sync(0xffffffffu, small);
-  const unsigned grp = (ballot >> ((threadIdx.x & 31) & ~3)) & 0xfu;
-  uint32_t sc = 0;
-  if (r == 0)
-    sc = tree.scaler[(size_t) e.distal * n + s] + tree.scaler[(size_t) e.proximal * n + s];
-  sc = __shfl_sync(0xffffffffu, sc, (threadIdx.x & 31) & ~3);
-  if (grp == 0xfu)
-  {
-    sc += 1;
-    #pragma unroll
-    for (int i = 0; i < S; ++i) inner[i] *= EPA_SCALE_FACTOR;
-  }
-  const double scale_term = sc ? (double) sc * EPA_LOG_SCALE_THRESHOLD : 0.0;
+  for (int k = 0; k < S * S; ++k) p[k] = P[r * S * S + k];
   const double w = m->weights[r];
+  const double * Dn = tree.clv + e.distal * tree.clv_stride;
+  const double * Xn = tree.clv + e.proximal * tree.clv_stride;
+  const uint32_t * sDn = tree.scaler + (size_t) e.distal * n;
+  const uint32_t * sXn = tree.scaler + (size_t) e.proximal * n;
 
-  // per-rate contribution of every column, then sum over the four rate lanes (fixed order)
-  double mine[4];
-  #pragma unroll
-  for (int c = 0; c < K; ++c)
+  const int site0 = blockIdx.y * LOOKUP_DNA_SITES_PER_BLOCK;
+  #pragma unroll 2
+  for (int it = 0; it < LOOKUP_DNA_SITES_PER_BLOCK / 64; ++it)
   {
-    double tr = 0.0;
+    const int site = site0 + it * 64 + (threadIdx.x >> 2);
+    if (site0 + it * 64 >= n) break;                      // block-uniform
+    const bool active = site < n;
+    const int s = active ? site : n - 1;
+
+    double dv[S], xv[S], inner[S];
+    load_vec<S>(Dn + (size_t) s * (R * S) + r * S, dv);
+    load_vec<S>(Xn + (size_t) s * (R * S) + r * S, xv);
+    uint32_t sc = __ldg(sDn + s) + __ldg(sXn + s);
+    bool small = true;
     #pragma unroll
-    for (int i = 0; i < S; ++i) tr += inner[i] * M[(r * K + c) * S + i];
-    tr *= w;
-    tr += __shfl_xor_sync(0xffffffffu, tr, 1);
-    tr += __shfl_xor_sync(0xffffffffu, tr, 2);
-    if ((c >> 2) == r) mine[c & 3] = tr;      // lane r finishes columns 4r..4r+3
+    for (int i = 0; i < S; ++i)
+    {
+      const double ta = p[i * S] * dv[0] + p[i * S + 1] * dv[1] + p[i * S + 2] * dv[2] + p[i * S + 3] * dv[3];
+      const double tb = p[i * S] * xv[0] + p[i * S + 1] * xv[1] + p[i * S + 2] * xv[2] + p[i * S + 3] * xv[3];
+      inner[i] = ta * tb;
+      small = small && (inner[i] < EPA_SCALE_THRESHOLD);
+    }
+    // all 16 entries of the site below the threshold? (lanes 4k..4k+3 hold one site)
+    const unsigned ballot = __ballot_sync(0xffffffffu, small);
+    const unsigned grp = (ballot >> ((threadIdx.x & 31) & ~3)) & 0xfu;
+    if (grp == 0xfu)
+    {
+      sc += 1;
+      #pragma unroll
+      for (int i = 0; i < S; ++i) inner[i] *= EPA_SCALE_FACTOR;
+    }
+    const double scale_term = sc ? (double) sc * EPA_LOG_SCALE_THRESHOLD : 0.0;
+
+    // per-rate contribution of every column, then sum over the four rate lanes (fixed order)
+    double mine[4];
+    #pragma unroll
+    for (int c = 0; c < K; ++c)
+    {
+      const double2 m01 = M2[(c * 2) * R + r], m23 = M2[(c * 2 + 1) * R + r];
+      double tr = inner[0] * m01.x + inner[1] * m01.y + inner[2] * m23.x + inner[3] * m23.y;
+      tr *= w;
+      tr += __shfl_xor_sync(0xffffffffu, tr, 1);
+      tr += __shfl_xor_sync(0xffffffffu, tr, 2);
+      if ((c >> 2) == r) mine[c & 3] = tr;      // lane r finishes columns 4r..4r+3
+    }
+    double res[4];
+    #pragma unroll
+    for (int k = 0; k < 4; ++k)
+      res[k] = (r == 0 && k == 0) ? 0.0 : log(mine[k]) + scale_term;   // column 0 = zero column
+    if (active)
+      store_vec<4>(lookup + ((size_t) blockIdx.x * n_pad + site) * K + r * 4, res);
   }
-  double res[4];
-  #pragma unroll
-  for (int k = 0; k < 4; ++k)
-    res[k] = (r == 0 && k == 0) ? 0.0 : log(mine[k]) + scale_term;   // column 0 = zero column
-  if (active)
-    store_vec<4>(lookup + ((size_t) blockIdx.x * n_pad + site) * K + r * 4, res);
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -109,7 +109,12 @@ collect_kernel(CollectArgs a)
     ++kept;
     pv = bv; pi = bi;
   }
-  if (lane == 0) a.out_cnt[q] = (uint32_t) min(kept, (int) a.fmax);
+  if (lane == 0)
+  {
+    const uint32_t n_out = (uint32_t) min(kept, (int) a.fmax);
+    a.out_cnt[q] = n_out;
+    for (uint32_t k = n_out; k < a.fmax; ++k) out[k] = PlacementRec{0, 0.0, 0.0, 0.0, 0.0};   // unused slots
+  }
 }
 
 }  // namespace epa

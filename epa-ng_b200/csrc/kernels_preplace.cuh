@@ -22,24 +22,39 @@ __global__ void histogram_kernel(const int * __restrict__ keys, uint32_t count, 
 __global__ void __launch_bounds__(1024)
 exclusive_scan_kernel(const uint32_t * in, uint32_t * out, uint32_t count, uint64_t * total)
 {
-  __shared__ uint64_t part[1024];
-  const uint32_t per = (count + 1023u) / 1024u;
-  const uint32_t lo = min(count, threadIdx.x * per), hi = min(count, lo + per);
+  // every warp owns one contiguous segment and walks it 32 elements at a time (coalesced)
+  __shared__ uint64_t wsum[32];
+  const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t seg = (((count + 31u) / 32u) + 31u) & ~31u;
+  const uint32_t lo = min(count, warp * seg), hi = min(count, lo + seg);
   uint64_t s = 0;
-  for (uint32_t i = lo; i < hi; ++i) s += in[i];
-  part[threadIdx.x] = s;
+  for (uint32_t i = lo + lane; i < hi; i += 32) s += in[i];
+  #pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if (lane == 0) wsum[warp] = s;
   __syncthreads();
-  // Hillis-Steele over 1024 partials
-  for (int o = 1; o < 1024; o <<= 1)
+  if (threadIdx.x == 0)
   {
-    uint64_t v = (threadIdx.x >= (unsigned) o) ? part[threadIdx.x - o] : 0;
-    __syncthreads();
-    part[threadIdx.x] += v;
-    __syncthreads();
+    uint64_t run = 0;
+    for (int w = 0; w < 32; ++w) { const uint64_t v = wsum[w]; wsum[w] = run; run += v; }
+    if (total) *total = run;
   }
-  uint64_t run = threadIdx.x ? part[threadIdx.x - 1] : 0;
-  for (uint32_t i = lo; i < hi; ++i) { const uint32_t v = in[i]; out[i] = (uint32_t) run; run += v; }
-  if (total && threadIdx.x == 1023) *total = part[1023];
+  __syncthreads();
+  uint64_t run = wsum[warp];
+  for (uint32_t base = lo; base < hi; base += 32)
+  {
+    const uint32_t i = base + lane;
+    const uint32_t v = i < hi ? in[i] : 0u;
+    uint32_t x = v;
+    #pragma unroll
+    for (int o = 1; o < 32; o <<= 1)
+    {
+      const uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
+      if (lane >= (uint32_t) o) x += y;
+    }
+    if (i < hi) out[i] = (uint32_t) (run + x - v);
+    run += __shfl_sync(0xffffffffu, x, 31);
+  }
 }
 
 // perm[offset[key] + k] = i  (order inside one key is arbitrary)
@@ -306,14 +321,16 @@ select_count_kernel(const double * __restrict__ pre, size_t pre_stride, int n_ed
 __global__ void __launch_bounds__(256)
 select_fill_kernel(const double * __restrict__ pre, size_t pre_stride, int n_edges, uint32_t nq,
                    const uint32_t * __restrict__ off, const double * __restrict__ cut_v,
-                   const int * __restrict__ cut_i, uint32_t * __restrict__ pair_q,
-                   uint32_t * __restrict__ pair_e, uint32_t * __restrict__ edge_hist)
+                   const int * __restrict__ cut_i, const int * __restrict__ begin, int window_bin,
+                   uint32_t nbins, uint32_t * __restrict__ pair_q,
+                   uint32_t * __restrict__ pair_e, uint32_t * __restrict__ key_hist)
 {
   const uint32_t q = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (q >= nq) return;
   const double * row = pre + (size_t) q * pre_stride;
   const double cv = cut_v[q]; const int ci = cut_i[q];
+  const uint32_t wbin = (uint32_t) (begin[q] / window_bin);
   uint32_t o = off[q];
   for (int base = 0; base < n_edges; base += 32)
   {
@@ -330,18 +347,24 @@ select_fill_kernel(const double * __restrict__ pre, size_t pre_stride, int n_edg
       const uint32_t p = o + __popc(mask & ((1u << lane) - 1u));
       pair_q[p] = q;
       pair_e[p] = (uint32_t) b;
-      atomicAdd(&edge_hist[b], 1u);
+      atomicAdd(&key_hist[(size_t) b * nbins + wbin], 1u);
     }
     o += __popc(mask);
   }
 }
 
-// work[edge_off[e] + k] = pair id (edge-major work list so that concurrent warps share CLVs)
-__global__ void work_scatter_kernel(const uint32_t * __restrict__ pair_e, uint32_t n_pairs,
+// work[offset(edge, window bin) + k] = pair id: edge-major, window-sorted work list so that the
+// warps of a CTA (which take consecutive items) share CLV windows in L1/L2
+__global__ void work_scatter_kernel(const uint32_t * __restrict__ pair_q, const uint32_t * __restrict__ pair_e,
+                                    uint32_t n_pairs, const int * __restrict__ begin, int window_bin, uint32_t nbins,
                                     uint32_t * __restrict__ cursor, uint32_t * __restrict__ work)
 {
   const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
-  if (p < n_pairs) work[atomicAdd(&cursor[pair_e[p]], 1u)] = p;
+  if (p < n_pairs)
+  {
+    const size_t key = (size_t) pair_e[p] * nbins + (uint32_t) (begin[pair_q[p]] / window_bin);
+    work[atomicAdd(&cursor[key], 1u)] = p;
+  }
 }
 
 }  // namespace epa

@@ -69,6 +69,8 @@ def test_session_chunking_is_invisible(built):
     d = os.path.join(helpers.GOLDEN, "synth64")
     o = helpers.oracle()
     rn, rs = o.read_fasta(os.path.join(d, "ref.fasta"))
+    _, qs = o.read_fasta(os.path.join(d, "query.fasta"))
+    rs = o.apply_mask(rs, o.gap_mask(rs) | o.gap_mask(qs))        # the same pre-masking the case applied
     ref_rows = np.frombuffer("".join(rs).encode(), dtype=np.uint8).reshape(len(rs), -1)
     sess = built.session.Session(open(os.path.join(d, "tree.nwk")).read(), rn, ref_rows,
                                  "GTR{1/1/1/1/1/1}+FU{0.25/0.25/0.25/0.25}+G4{0.5}")
