@@ -4,6 +4,7 @@
 #include "../../include/epa_b200.h"
 
 #include <algorithm>
+#include <cmath>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
@@ -305,12 +306,29 @@ extern "C" int epa_ctx_create(epa_ctx ** out, int device, const epa_model_desc *
   m.per_rate = 0;
   m.bugcompat = (model->flags & EPA_FLAG_BUGCOMPAT_FOCUS) ? 1 : 0;
   for (int i = 0; i < S; ++i) { m.eigenvals[i] = model->eigenvals[i]; m.freqs[i] = model->freqs[i]; }
-  for (int i = 0; i < S * S; ++i)
+  for (int i = 0; i < S * S; ++i) { m.eigenvecs[i] = model->eigenvecs[i]; m.inv_eigenvecs[i] = model->inv_eigenvecs[i]; }
   {
-    m.eigenvecs[i] = model->eigenvecs[i];
-    m.inv_eigenvecs[i] = model->inv_eigenvecs[i];
-    m.pivinv[i] = model->freqs[i / S] * model->inv_eigenvecs[i];
+    // Put the stationary eigenpair (eigenvalue 0 of a reversible model) first: a permutation of the
+    // eigenpairs leaves P(t) unchanged, and the thorough kernel folds that component into one plane.
+    int z = 0;
+    double scale = 0.0;
+    for (int i = 0; i < S; ++i) { if (m.eigenvals[i] > m.eigenvals[z]) z = i; scale = std::max(scale, std::fabs(m.eigenvals[i])); }
+    if (std::fabs(m.eigenvals[z]) > 1e-9 * std::max(scale, 1e-300))
+    {
+      fail(ctx, EPA_ERR_ARG, "the rate matrix has no zero eigenvalue (largest is %g): not a reversible model", m.eigenvals[z]);
+      return bail(EPA_ERR_ARG);
+    }
+    if (z != 0)
+    {
+      std::swap(m.eigenvals[0], m.eigenvals[z]);
+      for (int k = 0; k < S; ++k)
+      {
+        std::swap(m.eigenvecs[0 * S + k], m.eigenvecs[z * S + k]);             // rows of V
+        std::swap(m.inv_eigenvecs[k * S + 0], m.inv_eigenvecs[k * S + z]);     // columns of Vinv
+      }
+    }
   }
+  for (int i = 0; i < S * S; ++i) m.pivinv[i] = m.freqs[i / S] * m.inv_eigenvecs[i];
   for (int r = 0; r < R; ++r) { m.rates[r] = model->rates[r]; m.weights[r] = model->rate_weights[r]; }
   build_char_tables(m);
   ctx->S = S; ctx->R = R; ctx->n = m.n; ctx->n_pad = (m.n + 3) & ~3; ctx->K = m.K;
@@ -851,7 +869,7 @@ int launch_blo_dna(epa_ctx * ctx, BloArgs & a)
   {
     warps = 8;
     const unsigned grid = (unsigned) std::min<uint64_t>((uint64_t) ctx->sm_count * 2, (a.n_pairs + warps - 1) / warps);
-    CU(ctx->scratch.ensure((size_t) grid * warps * (4 * R) * blo_plane_stride(ctx->n) * sizeof(double)));
+    CU(ctx->scratch.ensure((size_t) grid * warps * (1 + 3 * R) * blo_plane_stride(ctx->n) * sizeof(double)));
     a.scratch = ctx->scratch.as<double>();
     a.wcap = 0;
     const size_t smem = BloWarpSmem<R>::doubles(0) * sizeof(double) * warps;

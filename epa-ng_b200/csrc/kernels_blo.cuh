@@ -17,9 +17,10 @@
 //    32-byte sector of each CLV, so the CLV windows stream fully coalesced from L2/HBM. The rate sum
 //    is log2(R) xor-shuffles; the per-site log is rotated over the R lanes of a site (one log per
 //    lane per R sites instead of one per site).
-//  * Newton iterations: lane = site. The sumtable lives in the warp's shared-memory slice as 4R
-//    site-major planes, so the 4R loads of a site are conflict-free, the whole site evaluates in
-//    registers without any cross-lane traffic, and only the final (f, f') pair is butterfly-reduced.
+//  * Newton iterations: lane = site. The sumtable lives in the warp's shared-memory slice as 1 + 3R
+//    site-major planes (the eigenvalue-0 component of all rates is folded into one t-independent
+//    plane), so the loads of a site are conflict-free, the whole site evaluates in registers without
+//    any cross-lane traffic, and only the final (f, f') pair is butterfly-reduced.
 // Transition matrices and per-mask tip vectors are rebuilt by the warp whenever a length changes.
 // Work items come from an edge-major, window-sorted list in blocks of 32 per CTA, so the warps of a
 // CTA work on overlapping CLV windows (L1 reuse). Nothing but 24 bytes per pair leaves the SM.
@@ -57,11 +58,14 @@ struct BloArgs {
   uint32_t nq, n_edges;           // implicit mode: item i -> edge i / nq, query perm[i % nq], pair id q*n_edges+e
   unsigned long long * counter;   // dynamic work counter (zeroed before launch)
   BloResult * out;                // [pair id]
-  double * scratch;               // global sumtable scratch (GS variant): [total warps][4R planes]
+  double * scratch;               // global sumtable scratch (GS variant): [total warps][1 + 3R planes]
   int wcap;                       // sites the shared-memory sumtable can hold
 };
 
-__host__ __device__ constexpr int blo_plane_stride(int wcap) { return ((wcap + 3) & ~3) + 1; }
+// Plane stride (doubles) = 12 mod 16: the three decaying planes of consecutive rates then start
+// 32 bytes apart modulo the 128-byte bank window, so the 4 sites x 4 rates of a half-warp store
+// conflict-free; the site-major reads of the Newton loop are conflict-free for any stride.
+__host__ __device__ constexpr int blo_plane_stride(int wcap) { return ((wcap + 3) / 16) * 16 + 12; }
 
 template <int R>
 struct BloWarpSmem {
@@ -70,11 +74,11 @@ struct BloWarpSmem {
   static constexpr int P_P = R * 16;
   static constexpr int P_E = 2 * R * 16;
   static constexpr int TV = 3 * R * 16;              // [R][16 masks][4]
-  static constexpr int EX = TV + R * 64;             // [R*4] expm1 scratch; [3][4R] diag tables (R = 8)
-  static constexpr int SUM = EX + 3 * R * 4;         // [4R planes][plane stride]
+  static constexpr int EX = TV + R * 64;             // [R*4] expm1 scratch; [3][3R] diag tables (R = 8)
+  static constexpr int SUM = EX + 3 * R * 4;         // [1 + 3R planes][plane stride]
   __host__ __device__ static constexpr size_t doubles(int wcap)
   {
-    return (size_t) SUM + (wcap > 0 ? (size_t) 4 * R * blo_plane_stride(wcap) : 0);
+    return (size_t) SUM + (wcap > 0 ? (size_t) (1 + 3 * R) * blo_plane_stride(wcap) : 0);
   }
 };
 
@@ -87,7 +91,7 @@ struct BloCtaSmem {
 
 // P[r][i][j] = delta_ij + sum_k Vinv[i][k] expm1(lambda_k rate_r t) V[k][j]   (LP/core_pmatrix.c:185-249)
 template <int R>
-__device__ __forceinline__ void warp_pmatrix(const BloCtaSmem & cs, double t, double * P, double * ex, int lane)
+__device__ __noinline__ void warp_pmatrix(const BloCtaSmem & cs, double t, double * P, double * ex, int lane)
 {
   for (int idx = lane; idx < R * 4; idx += 32)
     ex[idx] = expm1(c_model.eigenvals[idx & 3] * c_model.rates[idx >> 2] * t);
@@ -105,7 +109,7 @@ __device__ __forceinline__ void warp_pmatrix(const BloCtaSmem & cs, double t, do
 
 // tv[r][mask][i] = sum_{j in mask} P[r][i][j]  (the pendant matrix applied to a tip state set)
 template <int R>
-__device__ __forceinline__ void warp_tipvec(const double * P, double * tv, int lane)
+__device__ __noinline__ void warp_tipvec(const double * P, double * tv, int lane)
 {
   for (int idx = lane; idx < R * 64; idx += 32)
   {
@@ -137,18 +141,20 @@ __device__ __forceinline__ bool group_all(bool small, int lane)
   return ((ballot >> (lane & ~(R - 1))) & gm) == gm;
 }
 
-// first and second derivative sums over the window (LP/core_derivatives.c:643-858), lane = site
+// first and second derivative sums over the window (LP/core_derivatives.c:643-858), lane = site.
+// Plane 0 holds the stationary (lambda = 0) part of every site, sum_r w_r x[r][0], which does not
+// depend on t; planes 1.. hold the 3R decaying components x[r][j], j = 1..3.
 template <int R>
-__device__ __forceinline__ void warp_derivatives(const double * sum, int pstride, double * ex, int w, double t,
-                                                 int lane, double & f, double & df)
+__device__ __noinline__ void warp_derivatives(const double * sum, int pstride, double * ex, int w, double t,
+                                              int lane, double & f, double & df)
 {
-  constexpr int NK = 4 * R;
-  // diag tables: lane k < 4R computes exp(lambda_j rate_r t), weights folded in
+  constexpr int NK = 3 * R;
+  // diag tables: lane k < 3R computes exp(lambda_j rate_r t), weights folded in
   double e = 0.0, lk = 0.0;
   {
     const int k = lane % NK;
-    lk = c_model.eigenvals[k & 3] * c_model.rates[k >> 2];
-    e = exp(lk * t) * c_model.weights[k >> 2];
+    lk = c_model.eigenvals[1 + k % 3] * c_model.rates[k / 3];
+    e = exp(lk * t) * c_model.weights[k / 3];
   }
   double a1 = 0.0, a2 = 0.0;
   if constexpr (R <= 4)
@@ -164,11 +170,11 @@ __device__ __forceinline__ void warp_derivatives(const double * sum, int pstride
     #pragma unroll 2
     for (int s = lane; s < w; s += 32)
     {
-      double c0 = 0.0, c1 = 0.0, c2 = 0.0;
+      double c0 = sum[s], c1 = 0.0, c2 = 0.0;
       #pragma unroll
       for (int k = 0; k < NK; ++k)
       {
-        const double x = sum[k * pstride + s];
+        const double x = sum[(k + 1) * pstride + s];
         c0 += x * d0[k]; c1 += x * d1[k]; c2 += x * d2[k];
       }
       const double inv = 1.0 / c0;
@@ -185,11 +191,11 @@ __device__ __forceinline__ void warp_derivatives(const double * sum, int pstride
     __syncwarp();
     for (int s = lane; s < w; s += 32)
     {
-      double c0 = 0.0, c1 = 0.0, c2 = 0.0;
+      double c0 = sum[s], c1 = 0.0, c2 = 0.0;
       #pragma unroll 8
       for (int k = 0; k < NK; ++k)
       {
-        const double x = sum[k * pstride + s];
+        const double x = sum[(k + 1) * pstride + s];
         c0 += x * ex[k]; c1 += x * ex[NK + k]; c2 += x * ex[2 * NK + k];
       }
       const double inv = 1.0 / c0;
@@ -203,9 +209,25 @@ __device__ __forceinline__ void warp_derivatives(const double * sum, int pstride
   df = warp_sum(a2);
 }
 
+// One sumtable row (site s, rate r) into the planes: the stationary component is weighted and summed
+// over the R lanes of the site, the decaying ones go to their own planes.
+template <int R>
+__device__ __forceinline__ void store_sum_row(double * sum, int pstride, int s, int r, bool act, double wr,
+                                              double st0, double st1, double st2, double st3)
+{
+  const double base = rate_sum<R>(st0 * wr);
+  if (act)
+  {
+    if (r == 0) sum[s] = base;
+    sum[(1 + r * 3) * pstride + s] = st1;
+    sum[(2 + r * 3) * pstride + s] = st2;
+    sum[(3 + r * 3) * pstride + s] = st3;
+  }
+}
+
 // bounded Newton-Raphson, PM/optimize/opt_algorithms.c:133-262; returns 0.0 on failure
 template <int R>
-__device__ __forceinline__ double warp_newton(const double * sum, int pstride, double * ex, int w, int lane,
+__device__ __noinline__ double warp_newton(const double * sum, int pstride, double * ex, int w, int lane,
                                               double xmin, double xguess, double xmax, double tol)
 {
   double x = fmax(fmin(xguess, xmax), xmin);
@@ -274,16 +296,17 @@ __device__ __forceinline__ TipUnit pass_tip_unit(const BloCtaSmem & cs, const do
   double term = (in[0] * c_model.freqs[0]) * t01.x + (in[1] * c_model.freqs[1]) * t01.y
               + (in[2] * c_model.freqs[2]) * t23.x + (in[3] * c_model.freqs[3]) * t23.y;
   term = rate_sum<R>(term * wr);
-  if (act)
   {
     // pendant sumtable: tip side takes pi*Vinv, inner side takes V
+    double st[4];
     #pragma unroll
     for (int j = 0; j < 4; ++j)
     {
       const double right = c_model.eigenvecs[j * 4] * in[0] + c_model.eigenvecs[j * 4 + 1] * in[1]
                          + c_model.eigenvecs[j * 4 + 2] * in[2] + c_model.eigenvecs[j * 4 + 3] * in[3];
-      sum[(r * 4 + j) * pstride + s] = cs.tipleft[mask * 4 + j] * right;
+      st[j] = cs.tipleft[mask * 4 + j] * right;
     }
+    store_sum_row<R>(sum, pstride, s, r, act, wr, st[0], st[1], st[2], st[3]);
   }
   TipUnit u;
   u.term = act ? term : 1.0;
@@ -294,7 +317,7 @@ __device__ __forceinline__ TipUnit pass_tip_unit(const BloCtaSmem & cs, const do
 // Pass A: inner CLV toward the new tip from (D, X); returns the edge log-likelihood
 // new_tip | inner over the window and leaves the pendant sumtable (inner vs tip) in `sum`.
 template <int R>
-__device__ __forceinline__ double warp_pass_tip(const BloCtaSmem & cs, const double * ws, double * sum, int pstride,
+__device__ __noinline__ double warp_pass_tip(const BloCtaSmem & cs, const double * ws, double * sum, int pstride,
                                                 const double * __restrict__ D, const double * __restrict__ X,
                                                 const uint32_t * __restrict__ sD, const uint32_t * __restrict__ sX,
                                                 const uint8_t * __restrict__ qc, int w, int lane)
@@ -308,11 +331,12 @@ __device__ __forceinline__ double warp_pass_tip(const BloCtaSmem & cs, const dou
   const double wr = c_model.weights[r];
   double acc = 0.0;
   // R site groups per trip: the R lanes of a site take turns at the logarithm
+  #pragma unroll 1
   for (int s0 = 0; s0 < w; s0 += SPW * R)
   {
     double mine = 1.0;
     uint32_t mscal = 0;
-    #pragma unroll
+    #pragma unroll 1
     for (int u = 0; u < R; ++u)
     {
       const TipUnit t = pass_tip_unit<R>(cs, pd, pp, tv, wr, sum, pstride, D, X, sD, sX, qc, s0 + u * SPW + so, w, r, lane);
@@ -326,7 +350,7 @@ __device__ __forceinline__ double warp_pass_tip(const BloCtaSmem & cs, const dou
 
 // Pass B: inner CLV toward the distal node from (T, X); leaves the distal sumtable (D vs inner)
 template <int R>
-__device__ __forceinline__ void warp_pass_distal(const BloCtaSmem & cs, const double * ws, double * sum, int pstride,
+__device__ __noinline__ void warp_pass_distal(const BloCtaSmem & cs, const double * ws, double * sum, int pstride,
                                                  const double * __restrict__ D, const double * __restrict__ X,
                                                  const uint8_t * __restrict__ qc, int w, int lane)
 {
@@ -336,6 +360,7 @@ __device__ __forceinline__ void warp_pass_distal(const BloCtaSmem & cs, const do
   #pragma unroll
   for (int k = 0; k < 16; ++k) pp[k] = ws[BloWarpSmem<R>::P_P + r * 16 + k];
   const double * tv = ws + BloWarpSmem<R>::TV + r * 64;
+  const double wr = c_model.weights[r];
   #pragma unroll 2
   for (int s0 = 0; s0 < w; s0 += SPW)
   {
@@ -359,8 +384,8 @@ __device__ __forceinline__ void warp_pass_distal(const BloCtaSmem & cs, const do
       #pragma unroll
       for (int i = 0; i < 4; ++i) in[i] *= EPA_SCALE_FACTOR;
     }
-    if (act)
     {
+      double st[4];
       #pragma unroll
       for (int j = 0; j < 4; ++j)
       {
@@ -368,8 +393,9 @@ __device__ __forceinline__ void warp_pass_distal(const BloCtaSmem & cs, const do
                           + dv[2] * c_model.pivinv[8 + j] + dv[3] * c_model.pivinv[12 + j];
         const double right = c_model.eigenvecs[j * 4] * in[0] + c_model.eigenvecs[j * 4 + 1] * in[1]
                            + c_model.eigenvecs[j * 4 + 2] * in[2] + c_model.eigenvecs[j * 4 + 3] * in[3];
-        sum[(r * 4 + j) * pstride + s] = left * right;
+        st[j] = left * right;
       }
+      store_sum_row<R>(sum, pstride, s, r, act, wr, st[0], st[1], st[2], st[3]);
     }
   }
   __syncwarp();
@@ -423,7 +449,7 @@ blo_dna_kernel(BloArgs a)
   const int pstride = blo_plane_stride(GS ? a.n : a.wcap);
   const size_t per_warp = BloWarpSmem<R>::doubles(GS ? 0 : a.wcap);
   double * ws = smem_d + (size_t) warp * per_warp;
-  double * sum = GS ? a.scratch + ((size_t) blockIdx.x * n_warps + warp) * (size_t) (4 * R) * pstride
+  double * sum = GS ? a.scratch + ((size_t) blockIdx.x * n_warps + warp) * (size_t) (1 + 3 * R) * pstride
                     : ws + BloWarpSmem<R>::SUM;
   double * ex = ws + BloWarpSmem<R>::EX;
 

@@ -234,7 +234,7 @@ lookup_build_kernel(const DevModel * __restrict__ m, DevTree tree, int n, int n_
 // ---------------------------------------------------------------------------------------------
 constexpr int LOOKUP_DNA_SITES_PER_BLOCK = 256;
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 3)
 lookup_build_dna_kernel(const DevModel * __restrict__ m, DevTree tree, int n, int n_pad,
                         const EdgeDev * __restrict__ edges, const double * __restrict__ pmats_half,
                         const double * __restrict__ coltab, double * __restrict__ lookup)
@@ -264,7 +264,7 @@ lookup_build_dna_kernel(const DevModel * __restrict__ m, DevTree tree, int n, in
   const uint32_t * sXn = tree.scaler + (size_t) e.proximal * n;
 
   const int site0 = blockIdx.y * LOOKUP_DNA_SITES_PER_BLOCK;
-  #pragma unroll 2
+  #pragma unroll 1
   for (int it = 0; it < LOOKUP_DNA_SITES_PER_BLOCK / 64; ++it)
   {
     const int site = site0 + it * 64 + (threadIdx.x >> 2);
