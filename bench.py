@@ -275,6 +275,7 @@ def ours(args):
             ach = units[k] * per_unit[k] / (ms / 1e3) / 1e9 if ms > 0 else 0.0
             kernels[k] = {"ms_per_step": ms, "units_per_step": units[k], "bytes_per_unit": per_unit[k],
                           "achieved_gbs": ach, "frac": ach / peak}
+        ctx.build_lookup()                 # re-run warm: the first build pays module loading
         lk_ms = ctx.lookup_ms()
         kernels["lookup_build"] = {"ms": lk_ms, "units": B, "bytes_per_unit": 392000.0,
                                    "achieved_gbs": B * 392000.0 / (lk_ms / 1e3) / 1e9 if lk_ms > 0 else 0.0}

@@ -853,7 +853,7 @@ int launch_blo_dna(epa_ctx * ctx, BloArgs & a)
   const int wmax = std::max(1, ctx->max_span);
   const size_t per_warp = BloWarpSmem<R>::doubles(wmax) * sizeof(double);
   const size_t budget = ctx->smem_optin - 2048;
-  int warps = (int) std::min<size_t>(8, budget / per_warp);
+  int warps = (int) std::min<size_t>(8, budget / per_warp);      // __launch_bounds__(256, 1)
   if (warps >= 1)
   {
     a.wcap = wmax;
@@ -869,7 +869,7 @@ int launch_blo_dna(epa_ctx * ctx, BloArgs & a)
   {
     warps = 8;
     const unsigned grid = (unsigned) std::min<uint64_t>((uint64_t) ctx->sm_count * 2, (a.n_pairs + warps - 1) / warps);
-    CU(ctx->scratch.ensure((size_t) grid * warps * (1 + 3 * R) * blo_plane_stride(ctx->n) * sizeof(double)));
+    CU(ctx->scratch.ensure((size_t) grid * warps * ctx->n * blo_row(R) * sizeof(double)));
     a.scratch = ctx->scratch.as<double>();
     a.wcap = 0;
     const size_t smem = BloWarpSmem<R>::doubles(0) * sizeof(double) * warps;

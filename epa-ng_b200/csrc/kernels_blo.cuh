@@ -17,10 +17,11 @@
 //    32-byte sector of each CLV, so the CLV windows stream fully coalesced from L2/HBM. The rate sum
 //    is log2(R) xor-shuffles; the per-site log is rotated over the R lanes of a site (one log per
 //    lane per R sites instead of one per site).
-//  * Newton iterations: lane = site. The sumtable lives in the warp's shared-memory slice as 1 + 3R
-//    site-major planes (the eigenvalue-0 component of all rates is folded into one t-independent
-//    plane), so the loads of a site are conflict-free, the whole site evaluates in registers without
-//    any cross-lane traffic, and only the final (f, f') pair is butterfly-reduced.
+//  * Newton iterations: lane = site. The sumtable lives in the warp's shared-memory slice as one
+//    row of 1 + 3R doubles per site (the eigenvalue-0 component of all rates is folded into one
+//    t-independent entry; odd row length = conflict-free lane-per-site reads at immediate offsets),
+//    the whole site evaluates in registers without any cross-lane traffic, and only the final
+//    (f, f') pair is butterfly-reduced.
 // Transition matrices and per-mask tip vectors are rebuilt by the warp whenever a length changes.
 // Work items come from an edge-major, window-sorted list in blocks of 32 per CTA, so the warps of a
 // CTA work on overlapping CLV windows (L1 reuse). Nothing but 24 bytes per pair leaves the SM.
@@ -62,10 +63,10 @@ struct BloArgs {
   int wcap;                       // sites the shared-memory sumtable can hold
 };
 
-// Plane stride (doubles) = 12 mod 16: the three decaying planes of consecutive rates then start
-// 32 bytes apart modulo the 128-byte bank window, so the 4 sites x 4 rates of a half-warp store
-// conflict-free; the site-major reads of the Newton loop are conflict-free for any stride.
-__host__ __device__ constexpr int blo_plane_stride(int wcap) { return ((wcap + 3) / 16) * 16 + 12; }
+// Sumtable row of one site: [stationary part, 3R decaying components], padded to an ODD number of
+// doubles so that the lane = site reads of the Newton loop (stride = one row) touch 16 distinct
+// bank pairs per half-warp, while every component sits at a compile-time offset inside the row.
+__host__ __device__ constexpr int blo_row(int R) { return (1 + 3 * R) | 1; }
 
 template <int R>
 struct BloWarpSmem {
@@ -75,10 +76,10 @@ struct BloWarpSmem {
   static constexpr int P_E = 2 * R * 16;
   static constexpr int TV = 3 * R * 16;              // [R][16 masks][4]
   static constexpr int EX = TV + R * 64;             // [R*4] expm1 scratch; [3][3R] diag tables (R = 8)
-  static constexpr int SUM = EX + 3 * R * 4;         // [1 + 3R planes][plane stride]
+  static constexpr int SUM = EX + 3 * R * 4;         // [wcap][blo_row(R)]
   __host__ __device__ static constexpr size_t doubles(int wcap)
   {
-    return (size_t) SUM + (wcap > 0 ? (size_t) (1 + 3 * R) * blo_plane_stride(wcap) : 0);
+    return (size_t) SUM + (size_t) wcap * blo_row(R);
   }
 };
 
@@ -91,7 +92,7 @@ struct BloCtaSmem {
 
 // P[r][i][j] = delta_ij + sum_k Vinv[i][k] expm1(lambda_k rate_r t) V[k][j]   (LP/core_pmatrix.c:185-249)
 template <int R>
-__device__ __noinline__ void warp_pmatrix(const BloCtaSmem & cs, double t, double * P, double * ex, int lane)
+__device__ __forceinline__ void warp_pmatrix(const BloCtaSmem & cs, double t, double * P, double * ex, int lane)
 {
   for (int idx = lane; idx < R * 4; idx += 32)
     ex[idx] = expm1(c_model.eigenvals[idx & 3] * c_model.rates[idx >> 2] * t);
@@ -109,7 +110,7 @@ __device__ __noinline__ void warp_pmatrix(const BloCtaSmem & cs, double t, doubl
 
 // tv[r][mask][i] = sum_{j in mask} P[r][i][j]  (the pendant matrix applied to a tip state set)
 template <int R>
-__device__ __noinline__ void warp_tipvec(const double * P, double * tv, int lane)
+__device__ __forceinline__ void warp_tipvec(const double * P, double * tv, int lane)
 {
   for (int idx = lane; idx < R * 64; idx += 32)
   {
@@ -145,10 +146,10 @@ __device__ __forceinline__ bool group_all(bool small, int lane)
 // Plane 0 holds the stationary (lambda = 0) part of every site, sum_r w_r x[r][0], which does not
 // depend on t; planes 1.. hold the 3R decaying components x[r][j], j = 1..3.
 template <int R>
-__device__ __noinline__ void warp_derivatives(const double * sum, int pstride, double * ex, int w, double t,
+__device__ __forceinline__ void warp_derivatives(const double * sum, double * ex, int w, double t,
                                               int lane, double & f, double & df)
 {
-  constexpr int NK = 3 * R;
+  constexpr int NK = 3 * R, ROW = blo_row(R);
   // diag tables: lane k < 3R computes exp(lambda_j rate_r t), weights folded in
   double e = 0.0, lk = 0.0;
   {
@@ -170,11 +171,12 @@ __device__ __noinline__ void warp_derivatives(const double * sum, int pstride, d
     #pragma unroll 2
     for (int s = lane; s < w; s += 32)
     {
-      double c0 = sum[s], c1 = 0.0, c2 = 0.0;
+      const double * row = sum + s * ROW;
+      double c0 = row[0], c1 = 0.0, c2 = 0.0;
       #pragma unroll
       for (int k = 0; k < NK; ++k)
       {
-        const double x = sum[(k + 1) * pstride + s];
+        const double x = row[k + 1];
         c0 += x * d0[k]; c1 += x * d1[k]; c2 += x * d2[k];
       }
       const double inv = 1.0 / c0;
@@ -191,11 +193,12 @@ __device__ __noinline__ void warp_derivatives(const double * sum, int pstride, d
     __syncwarp();
     for (int s = lane; s < w; s += 32)
     {
-      double c0 = sum[s], c1 = 0.0, c2 = 0.0;
+      const double * row = sum + s * ROW;
+      double c0 = row[0], c1 = 0.0, c2 = 0.0;
       #pragma unroll 8
       for (int k = 0; k < NK; ++k)
       {
-        const double x = sum[(k + 1) * pstride + s];
+        const double x = row[k + 1];
         c0 += x * ex[k]; c1 += x * ex[NK + k]; c2 += x * ex[2 * NK + k];
       }
       const double inv = 1.0 / c0;
@@ -209,25 +212,26 @@ __device__ __noinline__ void warp_derivatives(const double * sum, int pstride, d
   df = warp_sum(a2);
 }
 
-// One sumtable row (site s, rate r) into the planes: the stationary component is weighted and summed
-// over the R lanes of the site, the decaying ones go to their own planes.
+// One sumtable row (site s, rate r): the stationary component is weighted and summed over the R
+// lanes of the site, the decaying ones go to their slots of the site's row.
 template <int R>
-__device__ __forceinline__ void store_sum_row(double * sum, int pstride, int s, int r, bool act, double wr,
+__device__ __forceinline__ void store_sum_row(double * sum, int s, int r, bool act, double wr,
                                               double st0, double st1, double st2, double st3)
 {
   const double base = rate_sum<R>(st0 * wr);
   if (act)
   {
-    if (r == 0) sum[s] = base;
-    sum[(1 + r * 3) * pstride + s] = st1;
-    sum[(2 + r * 3) * pstride + s] = st2;
-    sum[(3 + r * 3) * pstride + s] = st3;
+    double * row = sum + s * blo_row(R);
+    if (r == 0) row[0] = base;
+    row[1 + r * 3] = st1;
+    row[2 + r * 3] = st2;
+    row[3 + r * 3] = st3;
   }
 }
 
 // bounded Newton-Raphson, PM/optimize/opt_algorithms.c:133-262; returns 0.0 on failure
 template <int R>
-__device__ __noinline__ double warp_newton(const double * sum, int pstride, double * ex, int w, int lane,
+__device__ __forceinline__ double warp_newton(const double * sum, double * ex, int w, int lane,
                                               double xmin, double xguess, double xmax, double tol)
 {
   double x = fmax(fmin(xguess, xmax), xmin);
@@ -238,7 +242,7 @@ __device__ __noinline__ double warp_newton(const double * sum, int pstride, doub
   {
     if (iter++ > EPA_NR_MAX_ITERS) return 0.0;
     double f, df;
-    warp_derivatives<R>(sum, pstride, ex, w, x, lane, f, df);
+    warp_derivatives<R>(sum, ex, w, x, lane, f, df);
     if (!isfinite(f) || !isfinite(df)) return 0.0;
     double dx;
     if (df > 0.0)
@@ -258,69 +262,31 @@ __device__ __noinline__ double warp_newton(const double * sum, int pstride, doub
   }
 }
 
-// One (site, rate) unit of pass A: inner CLV entries toward the new tip, the weighted likelihood
-// term of the site (summed over its R lanes) and the pendant sumtable row.
-struct TipUnit { double term; uint32_t scal; };
+// Inputs of one (site, rate) unit, loaded one unit ahead of their use (software prefetch: with
+// 8-9 resident warps per SM the L2 latency of the CLV stream is not hidden by other warps).
+struct UnitIn { double dv[4], xv[4]; int mask; uint32_t scal; };
 
-template <int R>
-__device__ __forceinline__ TipUnit pass_tip_unit(const BloCtaSmem & cs, const double (&pd)[16], const double (&pp)[16],
-                                                 const double * tv, double wr, double * sum, int pstride,
-                                                 const double * __restrict__ D, const double * __restrict__ X,
-                                                 const uint32_t * __restrict__ sD, const uint32_t * __restrict__ sX,
-                                                 const uint8_t * __restrict__ qc, int s, int w, int r, int lane)
+template <int R, bool SCALERS>
+__device__ __forceinline__ UnitIn load_unit(const double * __restrict__ D, const double * __restrict__ X,
+                                            const uint32_t * __restrict__ sD, const uint32_t * __restrict__ sX,
+                                            const uint8_t * __restrict__ qc, int s, int w, int r)
 {
-  const bool act = s < w;
-  const int sc = act ? s : w - 1;
-  double dv[4], xv[4], in[4];
-  load_vec<4>(D + ((size_t) sc * R + r) * 4, dv);
-  load_vec<4>(X + ((size_t) sc * R + r) * 4, xv);
-  const int mask = qc[sc] & 15;
-  uint32_t scal = __ldg(sD + sc) + __ldg(sX + sc);
-  bool small = true;
-  #pragma unroll
-  for (int i = 0; i < 4; ++i)
-  {
-    const double ta = pd[i * 4] * dv[0] + pd[i * 4 + 1] * dv[1] + pd[i * 4 + 2] * dv[2] + pd[i * 4 + 3] * dv[3];
-    const double tb = pp[i * 4] * xv[0] + pp[i * 4 + 1] * xv[1] + pp[i * 4 + 2] * xv[2] + pp[i * 4 + 3] * xv[3];
-    in[i] = ta * tb;
-    small = small && (in[i] < EPA_SCALE_THRESHOLD);
-  }
-  if (group_all<R>(small, lane))
-  {
-    #pragma unroll
-    for (int i = 0; i < 4; ++i) in[i] *= EPA_SCALE_FACTOR;
-    scal += 1;
-  }
-  const double2 * tp = reinterpret_cast<const double2 *>(tv + mask * 4);
-  const double2 t01 = tp[0], t23 = tp[1];
-  double term = (in[0] * c_model.freqs[0]) * t01.x + (in[1] * c_model.freqs[1]) * t01.y
-              + (in[2] * c_model.freqs[2]) * t23.x + (in[3] * c_model.freqs[3]) * t23.y;
-  term = rate_sum<R>(term * wr);
-  {
-    // pendant sumtable: tip side takes pi*Vinv, inner side takes V
-    double st[4];
-    #pragma unroll
-    for (int j = 0; j < 4; ++j)
-    {
-      const double right = c_model.eigenvecs[j * 4] * in[0] + c_model.eigenvecs[j * 4 + 1] * in[1]
-                         + c_model.eigenvecs[j * 4 + 2] * in[2] + c_model.eigenvecs[j * 4 + 3] * in[3];
-      st[j] = cs.tipleft[mask * 4 + j] * right;
-    }
-    store_sum_row<R>(sum, pstride, s, r, act, wr, st[0], st[1], st[2], st[3]);
-  }
-  TipUnit u;
-  u.term = act ? term : 1.0;
-  u.scal = act ? scal : 0u;
+  const int sc = s < w ? s : w - 1;            // tail lanes re-read the last site; results are discarded
+  UnitIn u;
+  load_vec<4>(D + ((size_t) sc * R + r) * 4, u.dv);
+  load_vec<4>(X + ((size_t) sc * R + r) * 4, u.xv);
+  u.mask = qc[sc] & 15;
+  u.scal = SCALERS ? __ldg(sD + sc) + __ldg(sX + sc) : 0u;
   return u;
 }
 
 // Pass A: inner CLV toward the new tip from (D, X); returns the edge log-likelihood
 // new_tip | inner over the window and leaves the pendant sumtable (inner vs tip) in `sum`.
 template <int R>
-__device__ __noinline__ double warp_pass_tip(const BloCtaSmem & cs, const double * ws, double * sum, int pstride,
-                                                const double * __restrict__ D, const double * __restrict__ X,
-                                                const uint32_t * __restrict__ sD, const uint32_t * __restrict__ sX,
-                                                const uint8_t * __restrict__ qc, int w, int lane)
+__device__ __forceinline__ double warp_pass_tip(const BloCtaSmem & cs, const double * ws, double * sum,
+                                             const double * __restrict__ D, const double * __restrict__ X,
+                                             const uint32_t * __restrict__ sD, const uint32_t * __restrict__ sX,
+                                             const uint8_t * __restrict__ qc, int w, int lane)
 {
   constexpr int SPW = 32 / R;
   const int r = lane % R, so = lane / R;
@@ -330,19 +296,55 @@ __device__ __noinline__ double warp_pass_tip(const BloCtaSmem & cs, const double
   const double * tv = ws + BloWarpSmem<R>::TV + r * 64;
   const double wr = c_model.weights[r];
   double acc = 0.0;
-  // R site groups per trip: the R lanes of a site take turns at the logarithm
+  double mine = 1.0;
+  uint32_t mscal = 0;
+  // whole trips of R unit steps: the R lanes of a site take turns at the logarithm
+  const int n_units = ((w + SPW * R - 1) / (SPW * R)) * R;
+  UnitIn nxt = load_unit<R, true>(D, X, sD, sX, qc, so, w, r);
   #pragma unroll 1
-  for (int s0 = 0; s0 < w; s0 += SPW * R)
+  for (int i = 0; i < n_units; ++i)
   {
-    double mine = 1.0;
-    uint32_t mscal = 0;
-    #pragma unroll 1
-    for (int u = 0; u < R; ++u)
+    const UnitIn cur = nxt;
+    const int s = i * SPW + so;
+    nxt = load_unit<R, true>(D, X, sD, sX, qc, s + SPW, w, r);
+    const bool act = s < w;
+    double in[4];
+    uint32_t scal = cur.scal;
+    bool small = true;
+    #pragma unroll
+    for (int k = 0; k < 4; ++k)
     {
-      const TipUnit t = pass_tip_unit<R>(cs, pd, pp, tv, wr, sum, pstride, D, X, sD, sX, qc, s0 + u * SPW + so, w, r, lane);
-      if (u == r) { mine = t.term; mscal = t.scal; }
+      const double ta = pd[k * 4] * cur.dv[0] + pd[k * 4 + 1] * cur.dv[1] + pd[k * 4 + 2] * cur.dv[2] + pd[k * 4 + 3] * cur.dv[3];
+      const double tb = pp[k * 4] * cur.xv[0] + pp[k * 4 + 1] * cur.xv[1] + pp[k * 4 + 2] * cur.xv[2] + pp[k * 4 + 3] * cur.xv[3];
+      in[k] = ta * tb;
+      small = small && (in[k] < EPA_SCALE_THRESHOLD);
     }
-    acc += log(mine) + (mscal ? (double) mscal * EPA_LOG_SCALE_THRESHOLD : 0.0);
+    if (group_all<R>(small, lane))
+    {
+      #pragma unroll
+      for (int k = 0; k < 4; ++k) in[k] *= EPA_SCALE_FACTOR;
+      scal += 1;
+    }
+    const double2 * tp = reinterpret_cast<const double2 *>(tv + cur.mask * 4);
+    const double2 t01 = tp[0], t23 = tp[1];
+    double term = (in[0] * c_model.freqs[0]) * t01.x + (in[1] * c_model.freqs[1]) * t01.y
+                + (in[2] * c_model.freqs[2]) * t23.x + (in[3] * c_model.freqs[3]) * t23.y;
+    term = rate_sum<R>(term * wr);
+    {
+      // pendant sumtable: tip side takes pi*Vinv, inner side takes V
+      double st[4];
+      #pragma unroll
+      for (int j = 0; j < 4; ++j)
+      {
+        const double right = c_model.eigenvecs[j * 4] * in[0] + c_model.eigenvecs[j * 4 + 1] * in[1]
+                           + c_model.eigenvecs[j * 4 + 2] * in[2] + c_model.eigenvecs[j * 4 + 3] * in[3];
+        st[j] = cs.tipleft[cur.mask * 4 + j] * right;
+      }
+      store_sum_row<R>(sum, s, r, act, wr, st[0], st[1], st[2], st[3]);
+    }
+    if ((i % R) == r) { mine = act ? term : 1.0; mscal = act ? scal : 0u; }
+    if ((i % R) == R - 1)
+      acc += log(mine) + (mscal ? (double) mscal * EPA_LOG_SCALE_THRESHOLD : 0.0);
   }
   __syncwarp();
   return warp_sum(acc);
@@ -350,9 +352,9 @@ __device__ __noinline__ double warp_pass_tip(const BloCtaSmem & cs, const double
 
 // Pass B: inner CLV toward the distal node from (T, X); leaves the distal sumtable (D vs inner)
 template <int R>
-__device__ __noinline__ void warp_pass_distal(const BloCtaSmem & cs, const double * ws, double * sum, int pstride,
-                                                 const double * __restrict__ D, const double * __restrict__ X,
-                                                 const uint8_t * __restrict__ qc, int w, int lane)
+__device__ __forceinline__ void warp_pass_distal(const BloCtaSmem & cs, const double * ws, double * sum,
+                                              const double * __restrict__ D, const double * __restrict__ X,
+                                              const uint8_t * __restrict__ qc, int w, int lane)
 {
   constexpr int SPW = 32 / R;
   const int r = lane % R, so = lane / R;
@@ -361,42 +363,40 @@ __device__ __noinline__ void warp_pass_distal(const BloCtaSmem & cs, const doubl
   for (int k = 0; k < 16; ++k) pp[k] = ws[BloWarpSmem<R>::P_P + r * 16 + k];
   const double * tv = ws + BloWarpSmem<R>::TV + r * 64;
   const double wr = c_model.weights[r];
-  #pragma unroll 2
-  for (int s0 = 0; s0 < w; s0 += SPW)
+  const int n_units = (w + SPW - 1) / SPW;
+  UnitIn nxt = load_unit<R, false>(D, X, nullptr, nullptr, qc, so, w, r);
+  #pragma unroll 1
+  for (int i = 0; i < n_units; ++i)
   {
-    const int s = s0 + so;
+    const UnitIn cur = nxt;
+    const int s = i * SPW + so;
+    nxt = load_unit<R, false>(D, X, nullptr, nullptr, qc, s + SPW, w, r);
     const bool act = s < w;
-    const int sc = act ? s : w - 1;
-    double dv[4], xv[4], in[4];
-    load_vec<4>(D + ((size_t) sc * R + r) * 4, dv);
-    load_vec<4>(X + ((size_t) sc * R + r) * 4, xv);
-    const int mask = qc[sc] & 15;
+    double in[4];
     bool small = true;
     #pragma unroll
-    for (int i = 0; i < 4; ++i)
+    for (int k = 0; k < 4; ++k)
     {
-      const double tb = pp[i * 4] * xv[0] + pp[i * 4 + 1] * xv[1] + pp[i * 4 + 2] * xv[2] + pp[i * 4 + 3] * xv[3];
-      in[i] = tv[mask * 4 + i] * tb;
-      small = small && (in[i] < EPA_SCALE_THRESHOLD);
+      const double tb = pp[k * 4] * cur.xv[0] + pp[k * 4 + 1] * cur.xv[1] + pp[k * 4 + 2] * cur.xv[2] + pp[k * 4 + 3] * cur.xv[3];
+      in[k] = tv[cur.mask * 4 + k] * tb;
+      small = small && (in[k] < EPA_SCALE_THRESHOLD);
     }
     if (group_all<R>(small, lane))
     {
       #pragma unroll
-      for (int i = 0; i < 4; ++i) in[i] *= EPA_SCALE_FACTOR;
+      for (int k = 0; k < 4; ++k) in[k] *= EPA_SCALE_FACTOR;
     }
+    double st[4];
+    #pragma unroll
+    for (int j = 0; j < 4; ++j)
     {
-      double st[4];
-      #pragma unroll
-      for (int j = 0; j < 4; ++j)
-      {
-        const double left = dv[0] * c_model.pivinv[j] + dv[1] * c_model.pivinv[4 + j]
-                          + dv[2] * c_model.pivinv[8 + j] + dv[3] * c_model.pivinv[12 + j];
-        const double right = c_model.eigenvecs[j * 4] * in[0] + c_model.eigenvecs[j * 4 + 1] * in[1]
-                           + c_model.eigenvecs[j * 4 + 2] * in[2] + c_model.eigenvecs[j * 4 + 3] * in[3];
-        st[j] = left * right;
-      }
-      store_sum_row<R>(sum, pstride, s, r, act, wr, st[0], st[1], st[2], st[3]);
+      const double left = cur.dv[0] * c_model.pivinv[j] + cur.dv[1] * c_model.pivinv[4 + j]
+                        + cur.dv[2] * c_model.pivinv[8 + j] + cur.dv[3] * c_model.pivinv[12 + j];
+      const double right = c_model.eigenvecs[j * 4] * in[0] + c_model.eigenvecs[j * 4 + 1] * in[1]
+                         + c_model.eigenvecs[j * 4 + 2] * in[2] + c_model.eigenvecs[j * 4 + 3] * in[3];
+      st[j] = left * right;
     }
+    store_sum_row<R>(sum, s, r, act, wr, st[0], st[1], st[2], st[3]);
   }
   __syncwarp();
 }
@@ -446,10 +446,9 @@ blo_dna_kernel(BloArgs a)
   if (threadIdx.x == 0) { cs.q_next = 0; cs.q_end = 0; cs.q_lock = 0; }
   __syncthreads();
 
-  const int pstride = blo_plane_stride(GS ? a.n : a.wcap);
   const size_t per_warp = BloWarpSmem<R>::doubles(GS ? 0 : a.wcap);
   double * ws = smem_d + (size_t) warp * per_warp;
-  double * sum = GS ? a.scratch + ((size_t) blockIdx.x * n_warps + warp) * (size_t) (1 + 3 * R) * pstride
+  double * sum = GS ? a.scratch + ((size_t) blockIdx.x * n_warps + warp) * (size_t) a.n * blo_row(R)
                     : ws + BloWarpSmem<R>::SUM;
   double * ex = ws + BloWarpSmem<R>::EX;
 
@@ -486,64 +485,72 @@ blo_dna_kernel(BloArgs a)
     const uint32_t * sX = a.tree.scaler + (size_t) ed.proximal * n + begin;
     const uint8_t * qc = a.codes + (size_t) q * n + begin;
 
-    // optimize_branch_triplet: lengths orig/2, orig/2, -ln 0.9
+    // optimize_branch_triplet: lengths orig/2, orig/2, -ln 0.9. The smoothing loop of
+    // opt_branch_lengths_pplacer is unrolled into half rounds (tip phase, distal phase) so that
+    // every device function has exactly one call site: the code stays small enough for the
+    // instruction cache without giving up inlining.
     const double orig = ed.length;
-    double len_d = orig / 2.0, len_p = orig / 2.0, len_e = EPA_DEFAULT_PENDANT;
-    const double original_length = len_d * 2;
-    warp_pmatrix<R>(cs, len_d, ws + BloWarpSmem<R>::P_D, ex, lane);
-    for (int i = lane; i < R * 16; i += 32) ws[BloWarpSmem<R>::P_P + i] = ws[BloWarpSmem<R>::P_D + i];
-    warp_pmatrix<R>(cs, len_e, ws + BloWarpSmem<R>::P_E, ex, lane);
-    warp_tipvec<R>(ws + BloWarpSmem<R>::P_E, ws + BloWarpSmem<R>::TV, lane);
-
-    double loglikelihood = -warp_pass_tip<R>(cs, ws, sum, pstride, D, X, sD, sX, qc, w, lane);
+    double len[3] = {orig / 2.0, orig / 2.0, EPA_DEFAULT_PENDANT};      // distal, proximal, pendant
+    const double original_length = len[0] * 2;
+    double old_d = len[0], old_e = len[2], loglikelihood = 0.0;
     int smoothings = EPA_SMOOTHINGS;
-    while (smoothings)
+    unsigned rebuild = 7u;                                               // matrices to recompute
+    bool first = true, distal_phase = false;
+    for (;;)
     {
-      const double old_d = len_d, old_e = len_e;
-      // pendant
-      double xmin = EPA_MIN_BRLEN, xmax = EPA_MAX_BRLEN, xtol = xmin / 10.0, xguess = len_e;
-      if (xguess < xmin || xguess > xmax) xguess = EPA_DEFAULT_BRLEN;
-      double xres = warp_newton<R>(sum, pstride, ex, w, lane, xmin, xguess, xmax, xtol);
+      #pragma unroll 1
+      for (int mi = 0; mi < 3; ++mi)
+        if (rebuild & (1u << mi))
+        {
+          const double t = mi == 0 ? len[0] : (mi == 1 ? len[1] : len[2]);
+          warp_pmatrix<R>(cs, t, ws + mi * (R * 16), ex, lane);
+          if (mi == 2) warp_tipvec<R>(ws + BloWarpSmem<R>::P_E, ws + BloWarpSmem<R>::TV, lane);
+        }
+      rebuild = 0u;
+      double xmin, xmax, xguess;
+      if (!distal_phase)
+      {
+        // score the current lengths (also builds the pendant sumtable of the coming round)
+        const double new_logl = -warp_pass_tip<R>(cs, ws, sum, D, X, sD, sX, qc, w, lane);
+        if (first) { loglikelihood = new_logl; first = false; }
+        else
+        {
+          if (new_logl - loglikelihood > new_logl * 1e-14)
+          {
+            len[2] = old_e; len[0] = old_d; len[1] = original_length - old_d;   // worse: restore and stop
+            break;
+          }
+          --smoothings;
+          if (fabs(new_logl - loglikelihood) < EPA_BLO_EPSILON) smoothings = 0;
+          loglikelihood = new_logl;
+        }
+        if (!smoothings) break;
+        old_d = len[0]; old_e = len[2];
+        xmin = EPA_MIN_BRLEN; xmax = EPA_MAX_BRLEN; xguess = len[2];
+        if (xguess < xmin || xguess > xmax) xguess = EPA_DEFAULT_BRLEN;
+      }
+      else
+      {
+        warp_pass_distal<R>(cs, ws, sum, D, X, qc, w, lane);
+        xmin = fmin(EPA_MIN_BRLEN / 2.0, original_length / 2.0);
+        xmax = original_length - xmin / 10.0;
+        xguess = len[0];
+        if (xguess < xmin || xguess > xmax) xguess = original_length / 2.0;
+      }
+      const double xres = warp_newton<R>(sum, ex, w, lane, xmin, xguess, xmax, xmin / 10.0);
       if (xres > 0.0)
       {
-        len_e = xres;
-        warp_pmatrix<R>(cs, len_e, ws + BloWarpSmem<R>::P_E, ex, lane);
-        warp_tipvec<R>(ws + BloWarpSmem<R>::P_E, ws + BloWarpSmem<R>::TV, lane);
+        if (!distal_phase) { len[2] = xres; rebuild = 4u; }
+        else { len[0] = xres; len[1] = original_length - xres; rebuild = 3u; }
       }
-      // distal
-      warp_pass_distal<R>(cs, ws, sum, pstride, D, X, qc, w, lane);
-      xguess = len_d;
-      xmin = fmin(EPA_MIN_BRLEN / 2.0, original_length / 2.0);
-      xtol = xmin / 10.0;
-      xmax = original_length - xtol;
-      if (xguess < xmin || xguess > xmax) xguess = original_length / 2.0;
-      xres = warp_newton<R>(sum, pstride, ex, w, lane, xmin, xguess, xmax, xtol);
-      if (xres > 0.0)
-      {
-        len_d = xres;
-        len_p = original_length - xres;
-        warp_pmatrix<R>(cs, len_d, ws + BloWarpSmem<R>::P_D, ex, lane);
-        warp_pmatrix<R>(cs, len_p, ws + BloWarpSmem<R>::P_P, ex, lane);
-      }
-      // score (also prepares the pendant sumtable of the next round)
-      const double new_logl = -warp_pass_tip<R>(cs, ws, sum, pstride, D, X, sD, sX, qc, w, lane);
-      if (new_logl - loglikelihood > new_logl * 1e-14)
-      {
-        len_e = old_e;
-        len_d = old_d;
-        len_p = original_length - old_d;
-        break;
-      }
-      --smoothings;
-      if (fabs(new_logl - loglikelihood) < EPA_BLO_EPSILON) smoothings = 0;
-      loglikelihood = new_logl;
+      distal_phase = !distal_phase;
     }
     if (lane == 0)
     {
       BloResult res;
       res.logl = -loglikelihood;
-      res.distal = (orig / (len_d + len_p)) * len_d;      // Tiny_Tree.cpp:183-185
-      res.pendant = len_e;
+      res.distal = (orig / (len[0] + len[1])) * len[0];      // Tiny_Tree.cpp:183-185
+      res.pendant = len[2];
       a.out[pid] = res;
     }
     __syncwarp();
