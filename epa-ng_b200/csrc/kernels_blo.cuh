@@ -74,7 +74,7 @@ struct BloWarpSmem {
   static constexpr int P_D = 0;
   static constexpr int P_P = R * 16;
   static constexpr int P_E = 2 * R * 16;
-  static constexpr int TV = 3 * R * 16;              // [R][16 masks][4]
+  static constexpr int TV = 3 * R * 16;              // [4][16 mask positions][R]
   static constexpr int EX = TV + R * 64;             // [R*4] expm1 scratch; [3][3R] diag tables (R = 8)
   static constexpr int SUM = EX + 3 * R * 4;         // [wcap][blo_row(R)]
   __host__ __device__ static constexpr size_t doubles(int wcap)
@@ -103,12 +103,22 @@ __device__ __forceinline__ void warp_pmatrix(const BloCtaSmem & cs, double t, do
     double acc = (i == j) ? 1.0 : 0.0;
     #pragma unroll
     for (int k = 0; k < 4; ++k) acc += (cs.Vinv[i * 4 + k] * ex[r * 4 + k]) * cs.V[k * 4 + j];
-    P[idx] = acc;
+    P[(i * 4 + j) * R + r] = acc;          // rate-minor: the R lanes of a site read consecutive words
   }
   __syncwarp();
 }
 
-// tv[r][mask][i] = sum_{j in mask} P[r][i][j]  (the pendant matrix applied to a tip state set)
+// Row position of a state mask inside the tip-vector table: A, C, G, T take positions 0..3 so that
+// (for R = 4) their 32-byte rate blocks fall into the four disjoint quarters of the 128-byte bank
+// window: a warp's lookups of unambiguous characters are conflict-free and broadcast.
+__device__ __forceinline__ int tv_pos(int mask)
+{
+  // mask:  0  1  2  3  4  5  6  7  8  9 10 11 12 13 14 15
+  // pos : 15  0  1  5  2  6  7  8  3  9 10 11 12 13 14  4
+  return (int) ((0x4EDCBA938762510Full >> (mask * 4)) & 15ull);
+}
+
+// tv[i][pos(mask)][r] = sum_{j in mask} P[r][i][j]  (the pendant matrix applied to a tip state set)
 template <int R>
 __device__ __forceinline__ void warp_tipvec(const double * P, double * tv, int lane)
 {
@@ -118,8 +128,8 @@ __device__ __forceinline__ void warp_tipvec(const double * P, double * tv, int l
     double acc = 0.0;
     #pragma unroll
     for (int j = 0; j < 4; ++j)
-      if ((mask >> j) & 1) acc += P[r * 16 + i * 4 + j];
-    tv[idx] = acc;
+      if ((mask >> j) & 1) acc += P[(i * 4 + j) * R + r];
+    tv[(i * 16 + tv_pos(mask)) * R + r] = acc;
   }
   __syncwarp();
 }
@@ -292,8 +302,8 @@ __device__ __forceinline__ double warp_pass_tip(const BloCtaSmem & cs, const dou
   const int r = lane % R, so = lane / R;
   double pd[16], pp[16];
   #pragma unroll
-  for (int k = 0; k < 16; ++k) { pd[k] = ws[BloWarpSmem<R>::P_D + r * 16 + k]; pp[k] = ws[BloWarpSmem<R>::P_P + r * 16 + k]; }
-  const double * tv = ws + BloWarpSmem<R>::TV + r * 64;
+  for (int k = 0; k < 16; ++k) { pd[k] = ws[BloWarpSmem<R>::P_D + k * R + r]; pp[k] = ws[BloWarpSmem<R>::P_P + k * R + r]; }
+  const double * tv = ws + BloWarpSmem<R>::TV + r;
   const double wr = c_model.weights[r];
   double acc = 0.0;
   double mine = 1.0;
@@ -325,10 +335,9 @@ __device__ __forceinline__ double warp_pass_tip(const BloCtaSmem & cs, const dou
       for (int k = 0; k < 4; ++k) in[k] *= EPA_SCALE_FACTOR;
       scal += 1;
     }
-    const double2 * tp = reinterpret_cast<const double2 *>(tv + cur.mask * 4);
-    const double2 t01 = tp[0], t23 = tp[1];
-    double term = (in[0] * c_model.freqs[0]) * t01.x + (in[1] * c_model.freqs[1]) * t01.y
-                + (in[2] * c_model.freqs[2]) * t23.x + (in[3] * c_model.freqs[3]) * t23.y;
+    const double * tp = tv + tv_pos(cur.mask) * R;
+    double term = (in[0] * c_model.freqs[0]) * tp[0] + (in[1] * c_model.freqs[1]) * tp[16 * R]
+                + (in[2] * c_model.freqs[2]) * tp[32 * R] + (in[3] * c_model.freqs[3]) * tp[48 * R];
     term = rate_sum<R>(term * wr);
     {
       // pendant sumtable: tip side takes pi*Vinv, inner side takes V
@@ -360,8 +369,8 @@ __device__ __forceinline__ void warp_pass_distal(const BloCtaSmem & cs, const do
   const int r = lane % R, so = lane / R;
   double pp[16];
   #pragma unroll
-  for (int k = 0; k < 16; ++k) pp[k] = ws[BloWarpSmem<R>::P_P + r * 16 + k];
-  const double * tv = ws + BloWarpSmem<R>::TV + r * 64;
+  for (int k = 0; k < 16; ++k) pp[k] = ws[BloWarpSmem<R>::P_P + k * R + r];
+  const double * tv = ws + BloWarpSmem<R>::TV + r;
   const double wr = c_model.weights[r];
   const int n_units = (w + SPW - 1) / SPW;
   UnitIn nxt = load_unit<R, false>(D, X, nullptr, nullptr, qc, so, w, r);
@@ -378,7 +387,7 @@ __device__ __forceinline__ void warp_pass_distal(const BloCtaSmem & cs, const do
     for (int k = 0; k < 4; ++k)
     {
       const double tb = pp[k * 4] * cur.xv[0] + pp[k * 4 + 1] * cur.xv[1] + pp[k * 4 + 2] * cur.xv[2] + pp[k * 4 + 3] * cur.xv[3];
-      in[k] = tv[cur.mask * 4 + k] * tb;
+      in[k] = tv[(k * 16 + tv_pos(cur.mask)) * R] * tb;
       small = small && (in[k] < EPA_SCALE_THRESHOLD);
     }
     if (group_all<R>(small, lane))
