@@ -198,9 +198,6 @@ def ours(args):
     cnt_dev = torch.zeros(Q, dtype=torch.int32, device=dev)
     rec_host = torch.zeros((Q, fmax * 5), dtype=torch.float64).pin_memory()
     cnt_host = torch.zeros(Q, dtype=torch.int32).pin_memory()
-    gather_list = None
-    if world > 1 and rank == 0:
-        gather_list = [torch.zeros_like(rec_dev) for _ in range(world)]
 
     stage_ms = {"upload_encode": 0.0, "preplace": 0.0, "select": 0.0, "thorough": 0.0, "collect": 0.0}
     pairs_total = [0]
@@ -218,7 +215,9 @@ def ours(args):
                     stage_ms[k] += v
                 pairs_total[0] += npairs
         if world > 1:
-            dist.gather(rec_dev, gather_list, dst=0)     # the single NCCL gather of placement records
+            # the single gather of placement records (NCCL over NVLink): rank 0 ends up with the
+            # records of all shards in global query order
+            pkg.shard.gather_records(rec_dev, cnt_dev, Q * world, dst=0)
 
     def step_e2e():
         sess.place((host_q.data_ptr(), Q), opts, chunk, out=rec_host.data_ptr(), counts=cnt_host.data_ptr())
