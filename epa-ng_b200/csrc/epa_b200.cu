@@ -47,7 +47,8 @@ struct DevBuf {
 };
 
 enum Stage { ST_NONE = 0, ST_QUERIES = 1, ST_PREPLACED = 2, ST_SELECTED = 3, ST_PLACED = 4 };
-constexpr int kPreplaceTQ = 256;        // queries per preplacement tile (= CTA size)
+constexpr int kPreplaceTQ = 256;        // queries per tile of the per-site preplacement kernel (= CTA size)
+constexpr int kPairTQ = 256;            // queries per tile of the DNA pair-table kernel
 constexpr int kWindowBin = 4;           // work list is sorted by (edge, window start / kWindowBin)
 
 }  // namespace
@@ -67,6 +68,7 @@ struct epa_ctx {
   std::vector<EdgeDev> h_edges;
   EdgeDev * d_edges = nullptr;
   double * d_lookup = nullptr;
+  double * d_pairtab = nullptr;    // DNA pair-sum tables [edge][n_pad/2][PAIR_ROW]
   bool clvs_ready = false, lookup_ready = false;
   std::vector<uint8_t> slot_filled;
 
@@ -74,11 +76,11 @@ struct epa_ctx {
   int stage = ST_NONE;
   uint32_t nq = 0;
   int max_span = 0;
-  int max_tile_width = 4;
+  uint32_t n_simple = 0;           // queries that take the pair-table preplacement kernel (sorted first)
   bool implicit_pairs = false;
   uint64_t n_pairs = 0;
   size_t pre_stride = 0;
-  DevBuf raw, codes, begin, span, perm, hist, range, pre, cnt, cutv, cuti, off, pair_q, pair_e,
+  DevBuf raw, codes, begin, span, sortkey, perm, hist, range, pre, cnt, cutv, cuti, off, pair_q, pair_e,
          edge_hist, edge_off, work, res, out_rec, out_cnt, scratch, tmp;
   int * d_flags = nullptr;              // [0..1] error, [2] max tile width, [3] max span
   unsigned long long * d_counter = nullptr;
@@ -231,13 +233,13 @@ extern "C" void epa_ctx_destroy(epa_ctx * ctx)
     std::lock_guard<std::mutex> lock(g_const_mutex);
     if (g_const_owner[ctx->device] == ctx) g_const_owner[ctx->device] = nullptr;
   }
-  DevBuf * bufs[] = {&ctx->raw, &ctx->codes, &ctx->begin, &ctx->span, &ctx->perm, &ctx->hist, &ctx->range,
+  DevBuf * bufs[] = {&ctx->raw, &ctx->codes, &ctx->begin, &ctx->span, &ctx->sortkey, &ctx->perm, &ctx->hist, &ctx->range,
                      &ctx->pre, &ctx->cnt, &ctx->cutv, &ctx->cuti, &ctx->off, &ctx->pair_q, &ctx->pair_e,
                      &ctx->edge_hist, &ctx->edge_off, &ctx->work, &ctx->res, &ctx->out_rec, &ctx->out_cnt,
                      &ctx->scratch, &ctx->tmp};
   for (DevBuf * b : bufs) b->release();
   cudaFree(ctx->d_model); cudaFree(ctx->tree.clv); cudaFree(ctx->tree.scaler); cudaFree(ctx->d_edges);
-  cudaFree(ctx->d_lookup); cudaFree(ctx->d_flags); cudaFree(ctx->d_counter); cudaFree(ctx->d_total);
+  cudaFree(ctx->d_lookup); cudaFree(ctx->d_pairtab); cudaFree(ctx->d_flags); cudaFree(ctx->d_counter); cudaFree(ctx->d_total);
   for (auto & e : ctx->ev) if (e) cudaEventDestroy(e);
   if (ctx->stream && ctx->own_stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
@@ -603,6 +605,14 @@ extern "C" int epa_build_lookup(epa_ctx * ctx)
     LAUNCHED(ctx);
   }
   CU(cudaEventRecord(ctx->ev[1], ctx->stream));
+  if (S == 4)
+  {
+    // pair-sum tables of the DNA preplacement fast path (derived data, built once)
+    const size_t pair_doubles = (size_t) B * (ctx->n_pad / 2) * PAIR_ROW;
+    if (!ctx->d_pairtab) CU(cudaMalloc(&ctx->d_pairtab, pair_doubles * sizeof(double)));
+    pairtab_build_kernel<<<(unsigned) ((pair_doubles + 255) / 256), 256, 0, ctx->stream>>>(ctx->d_lookup, ctx->n_pad, B, ctx->d_pairtab);
+    LAUNCHED(ctx);
+  }
   CU(cudaStreamSynchronize(ctx->stream));
   ctx->lookup_ready = true;
   return EPA_OK;
@@ -688,28 +698,24 @@ extern "C" int epa_encode_queries_dev(epa_ctx * ctx, const char * seqs_dev, uint
   const uint8_t * src = seqs_dev ? reinterpret_cast<const uint8_t *>(seqs_dev) : ctx->raw.as<uint8_t>();
   CU(cudaMemsetAsync(ctx->d_flags, 0, 8 * sizeof(int), ctx->stream));
   const unsigned blocks = (n_queries + 7) / 8;
+  CU(ctx->sortkey.ensure(n_queries * sizeof(int)));
   encode_queries_kernel<<<blocks, 256, 0, ctx->stream>>>(ctx->d_model, src, n_queries, ctx->n, premasking ? 1 : 0,
                                                          ctx->codes.as<uint8_t>(), ctx->begin.as<int>(),
-                                                         ctx->span.as<int>(), ctx->d_flags);
+                                                         ctx->span.as<int>(), ctx->sortkey.as<int>(), ctx->d_flags);
   LAUNCHED(ctx);
-  // counting sort of the queries by window start (tiles of the preplacement kernel and the
-  // all-pairs work order of the thorough kernel follow it) + site range of every tile
+  // counting sort of the queries by (class, window start): simple queries first. The tiles of the
+  // preplacement kernels and the all-pairs work order of the thorough kernel follow this order.
   {
     const uint32_t nq = n_queries;
-    const int n = ctx->n;
-    const uint32_t n_tiles = (nq + kPreplaceTQ - 1) / kPreplaceTQ;
+    const uint32_t nkeys = 2u * (uint32_t) (ctx->n + 1);
     CU(ctx->perm.ensure(nq * sizeof(uint32_t)));
-    CU(ctx->hist.ensure((size_t) (n + 2) * sizeof(uint32_t)));
-    CU(ctx->range.ensure(n_tiles * sizeof(int2)));
-    CU(cudaMemsetAsync(ctx->hist.p, 0, (size_t) (n + 2) * sizeof(uint32_t), ctx->stream));
-    histogram_kernel<<<(nq + 255) / 256, 256, 0, ctx->stream>>>(ctx->begin.as<int>(), nq, ctx->hist.as<uint32_t>());
+    CU(ctx->hist.ensure((size_t) (nkeys + 1) * sizeof(uint32_t)));
+    CU(cudaMemsetAsync(ctx->hist.p, 0, (size_t) (nkeys + 1) * sizeof(uint32_t), ctx->stream));
+    histogram_kernel<<<(nq + 255) / 256, 256, 0, ctx->stream>>>(ctx->sortkey.as<int>(), nq, ctx->hist.as<uint32_t>());
     LAUNCHED(ctx);
-    exclusive_scan_kernel<<<1, 1024, 0, ctx->stream>>>(ctx->hist.as<uint32_t>(), ctx->hist.as<uint32_t>(), (uint32_t) n + 1, nullptr);
+    exclusive_scan_kernel<<<1, 1024, 0, ctx->stream>>>(ctx->hist.as<uint32_t>(), ctx->hist.as<uint32_t>(), nkeys, nullptr);
     LAUNCHED(ctx);
-    scatter_by_key_kernel<<<(nq + 255) / 256, 256, 0, ctx->stream>>>(ctx->begin.as<int>(), nq, ctx->hist.as<uint32_t>(), ctx->perm.as<uint32_t>());
-    LAUNCHED(ctx);
-    tile_range_kernel<<<(n_tiles + 7) / 8, 256, 0, ctx->stream>>>(ctx->perm.as<uint32_t>(), ctx->begin.as<int>(), ctx->span.as<int>(),
-                                                               nq, kPreplaceTQ, n_tiles, ctx->range.as<int2>(), ctx->d_flags + 2);
+    scatter_by_key_kernel<<<(nq + 255) / 256, 256, 0, ctx->stream>>>(ctx->sortkey.as<int>(), nq, ctx->hist.as<uint32_t>(), ctx->perm.as<uint32_t>());
     LAUNCHED(ctx);
   }
   CU(cudaEventRecord(ctx->ev[1], ctx->stream));
@@ -717,19 +723,19 @@ extern "C" int epa_encode_queries_dev(epa_ctx * ctx, const char * seqs_dev, uint
   if (int rc = read_flags(ctx, flags)) return rc;
   if (flags[0] == 1) return fail(ctx, EPA_ERR_QUERY, "query %d contains a character that is not valid for this data type", flags[1] - 1);
   if (flags[0] == 2) return fail(ctx, EPA_ERR_QUERY, "query %d consists entirely of gaps", flags[1] - 1);
-  ctx->max_tile_width = std::max(4, flags[2]);
   ctx->max_span = flags[3];
+  ctx->n_simple = (uint32_t) flags[4];
   ctx->stage = ST_QUERIES;
   return EPA_OK;
 }
 
 namespace {
+// generic kernel over perm[first, first + count)
 template <int K>
-int launch_preplace(epa_ctx * ctx, int maxw)
+int launch_preplace(epa_ctx * ctx, uint32_t first, uint32_t count, const int2 * range, int maxw)
 {
   constexpr int TQ = kPreplaceTQ, NS = 2;
-  const uint32_t nq = ctx->nq;
-  const uint32_t n_tiles = (nq + TQ - 1) / TQ;
+  const uint32_t n_tiles = (count + TQ - 1) / TQ;
   const size_t per_site = (size_t) NS * K * 8 + TQ;              // stage bytes + code bytes per site
   const size_t budget = ctx->smem_optin - 4096;
   int wc = maxw;
@@ -738,7 +744,26 @@ int launch_preplace(epa_ctx * ctx, int maxw)
   CU(cudaFuncSetAttribute(preplace_kernel<K, TQ, NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
   preplace_kernel<K, TQ, NS><<<n_tiles, TQ, smem, ctx->stream>>>(
       ctx->d_model, ctx->d_lookup, ctx->n, ctx->n_pad, ctx->n_edges, ctx->codes.as<uint8_t>(), ctx->begin.as<int>(),
-      ctx->span.as<int>(), ctx->perm.as<uint32_t>(), nq, ctx->range.as<int2>(), wc, ctx->pre.as<double>(), ctx->pre_stride);
+      ctx->span.as<int>(), ctx->perm.as<uint32_t>() + first, count, range, wc, ctx->pre.as<double>(), ctx->pre_stride);
+  LAUNCHED(ctx);
+  return EPA_OK;
+}
+
+// DNA pair-table kernel over perm[0, count)
+int launch_preplace_pair(epa_ctx * ctx, uint32_t count, const int2 * range, int maxw)
+{
+  constexpr int TQ = kPairTQ, NS = 2;
+  const uint32_t n_tiles = (count + TQ - 1) / TQ;
+  // per 8 sites: 4 pair rows per stage + one index word per query
+  const size_t per_word = (size_t) NS * 4 * PAIR_ROW * 8 + (size_t) TQ * 4;
+  const size_t budget = ctx->smem_optin - 8192;
+  int wc = maxw;                                                  // multiple of 8
+  if ((size_t) (wc / 8) * per_word > budget) wc = (int) (budget / per_word) * 8;
+  const size_t smem = (size_t) (wc / 8) * per_word + NS * 8;
+  CU(cudaFuncSetAttribute(preplace_pair_kernel<TQ, NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+  preplace_pair_kernel<TQ, NS><<<n_tiles, TQ, smem, ctx->stream>>>(
+      ctx->d_pairtab, ctx->n, ctx->n_pad, ctx->n_edges, ctx->codes.as<uint8_t>(), ctx->begin.as<int>(),
+      ctx->span.as<int>(), ctx->perm.as<uint32_t>(), count, range, wc, ctx->pre.as<double>(), ctx->pre_stride);
   LAUNCHED(ctx);
   return EPA_OK;
 }
@@ -755,9 +780,35 @@ extern "C" int epa_preplace(epa_ctx * ctx)
   if (nq == 0) { ctx->stage = ST_PREPLACED; return EPA_OK; }
   CU(ctx->pre.ensure((size_t) nq * ctx->pre_stride * sizeof(double)));
   CU(cudaEventRecord(ctx->ev[1], ctx->stream));
-  const int maxw = ctx->max_tile_width;
-  int rc = (ctx->K == 16) ? launch_preplace<16>(ctx, maxw) : launch_preplace<26>(ctx, maxw);
-  if (rc) return rc;
+  // simple DNA queries (sorted first) take the pair-table kernel, the rest the per-site kernel
+  const uint32_t nA = ctx->d_pairtab ? ctx->n_simple : 0u, nB = nq - nA;
+  const uint32_t tilesA = (nA + kPairTQ - 1) / kPairTQ, tilesB = (nB + kPreplaceTQ - 1) / kPreplaceTQ;
+  CU(ctx->range.ensure((size_t) (tilesA + tilesB) * sizeof(int2)));
+  CU(cudaMemsetAsync(ctx->d_flags + 2, 0, sizeof(int), ctx->stream));
+  CU(cudaMemsetAsync(ctx->d_flags + 5, 0, sizeof(int), ctx->stream));
+  if (nA)
+  {
+    tile_range_kernel<<<(tilesA + 7) / 8, 256, 0, ctx->stream>>>(ctx->perm.as<uint32_t>(), ctx->begin.as<int>(), ctx->span.as<int>(),
+                                                              nA, kPairTQ, tilesA, 8, ctx->range.as<int2>(), ctx->d_flags + 2);
+    LAUNCHED(ctx);
+  }
+  if (nB)
+  {
+    tile_range_kernel<<<(tilesB + 7) / 8, 256, 0, ctx->stream>>>(ctx->perm.as<uint32_t>() + nA, ctx->begin.as<int>(), ctx->span.as<int>(),
+                                                              nB, kPreplaceTQ, tilesB, 4, ctx->range.as<int2>() + tilesA, ctx->d_flags + 5);
+    LAUNCHED(ctx);
+  }
+  int flags[8];
+  if (int rc = read_flags(ctx, flags)) return rc;
+  if (nA)
+    if (int rc = launch_preplace_pair(ctx, nA, ctx->range.as<int2>(), std::max(8, flags[2]))) return rc;
+  if (nB)
+  {
+    const int maxw = std::max(4, flags[5]);
+    const int rc = (ctx->K == 16) ? launch_preplace<16>(ctx, nA, nB, ctx->range.as<int2>() + tilesA, maxw)
+                                  : launch_preplace<26>(ctx, nA, nB, ctx->range.as<int2>() + tilesA, maxw);
+    if (rc) return rc;
+  }
   CU(cudaEventRecord(ctx->ev[2], ctx->stream));
   ctx->stage = ST_PREPLACED;
   return EPA_OK;

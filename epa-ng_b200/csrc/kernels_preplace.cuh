@@ -68,12 +68,14 @@ __global__ void scatter_by_key_kernel(const int * __restrict__ keys, uint32_t co
 // ---------------------------------------------------------------------------------------------
 // ASCII -> codes, valid range. One warp per query.
 // err[0] = status (0 ok, 1 invalid character, 2 all-gap query), err[1] = first offending query + 1,
-// err[3] = longest valid range of the chunk
+// err[3] = longest valid range of the chunk, err[4] = number of "simple" queries.
+// A DNA query is simple when it only holds A, C, G, T and fully ambiguous characters: those take
+// the pair-table preplacement kernel. sortkey = begin for simple queries, n + 1 + begin otherwise.
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 encode_queries_kernel(const DevModel * __restrict__ m, const uint8_t * __restrict__ raw, uint32_t nq, int n,
                       int premask, uint8_t * __restrict__ codes, int * __restrict__ begin,
-                      int * __restrict__ span, int * __restrict__ err)
+                      int * __restrict__ span, int * __restrict__ sortkey, int * __restrict__ err)
 {
   __shared__ uint8_t a2c[256];
   a2c[threadIdx.x] = m->ascii2code[threadIdx.x];
@@ -85,11 +87,13 @@ encode_queries_kernel(const DevModel * __restrict__ m, const uint8_t * __restric
   uint8_t * crow = codes + (size_t) q * n;
   int lo = n, hi = -1;
   bool bad = false;
+  bool simple = (m->S == 4);
   for (int s = lane; s < n; s += 32)
   {
     const uint8_t ch = row[s];
     const uint8_t c = a2c[ch];
     bad = bad || (c == 255);
+    simple = simple && ((0x8116u >> (c & 15)) & 1u);       // masks 1, 2, 4, 8, 15
     crow[s] = c;
     if (ch != '-') { lo = min(lo, s); hi = max(hi, s); }
   }
@@ -100,12 +104,15 @@ encode_queries_kernel(const DevModel * __restrict__ m, const uint8_t * __restric
     hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, o));
   }
   bad = __any_sync(0xffffffffu, bad);
+  simple = __all_sync(0xffffffffu, simple);
   if (lane == 0)
   {
     int b = 0, w = n;
     if (premask) { b = (hi < 0) ? 0 : lo; w = (hi < 0) ? 0 : hi - lo + 1; }
     begin[q] = b;
     span[q] = w;
+    sortkey[q] = simple ? b : n + 1 + b;
+    if (simple) atomicAdd(&err[4], 1);
     atomicMax(&err[3], w);
     if (bad) { if (atomicCAS(&err[0], 0, 1) == 0) err[1] = (int) q + 1; }
     else if (hi < 0) { if (atomicCAS(&err[0], 0, 2) == 0) err[1] = (int) q + 1; }
@@ -114,10 +121,10 @@ encode_queries_kernel(const DevModel * __restrict__ m, const uint8_t * __restric
 
 // ---------------------------------------------------------------------------------------------
 // Site range covered by each tile of TQ (begin-sorted) queries. One warp per tile.
-// range[t] = (lo rounded down to 4, hi); maxw = max over tiles of the 4-aligned width.
+// range[t] = (lo rounded down to `align`, hi); maxw = max over tiles of the aligned width.
 // ---------------------------------------------------------------------------------------------
 __global__ void tile_range_kernel(const uint32_t * __restrict__ perm, const int * __restrict__ begin,
-                                  const int * __restrict__ span, uint32_t nq, int tq, uint32_t n_tiles,
+                                  const int * __restrict__ span, uint32_t nq, int tq, uint32_t n_tiles, int align,
                                   int2 * __restrict__ range, int * __restrict__ maxw)
 {
   const uint32_t t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -143,9 +150,9 @@ __global__ void tile_range_kernel(const uint32_t * __restrict__ perm, const int 
   if (lane == 0)
   {
     if (hi == 0) lo = 0;
-    lo &= ~3;
+    lo &= ~(align - 1);
     range[t] = make_int2(lo, hi);
-    atomicMax(maxw, ((hi - lo) + 3) & ~3);
+    atomicMax(maxw, ((hi - lo) + align - 1) & ~(align - 1));
   }
 }
 
@@ -259,6 +266,168 @@ preplace_kernel(const DevModel * __restrict__ m, const double * __restrict__ loo
         else out[b] += sum;
       }
       __syncthreads();                              // stage st may be refilled from now on
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// DNA pair tables. A warp-wide 64-bit shared-memory load costs two wavefronts however many lanes
+// share an address, so HOT LOOP A is bound by the NUMBER of lookups. For queries made of A, C, G, T
+// and fully ambiguous characters only (practically all reads) two adjacent sites are scored with
+// ONE lookup into a table of pair sums:
+//   T2[edge][p][idx(c1, c2)] = lookup[edge][2p][col(c1)] + lookup[edge][2p+1][col(c2)]
+// with character classes 0 = outside the query's range (zero column), 1..4 = A, C, G, T, 5 = fully
+// ambiguous. The 16 unambiguous combinations take idx 0..15 (one 128-byte bank window: conflict
+// free), the 20 combinations with a range end or a gap follow; a row is padded to 40 doubles.
+// ---------------------------------------------------------------------------------------------
+constexpr int PAIR_ROW = 40;
+
+__host__ __device__ __forceinline__ int pair_index(int c1, int c2)
+{
+  if (c1 >= 1 && c1 <= 4 && c2 >= 1 && c2 <= 4) return (c1 - 1) * 4 + (c2 - 1);
+  // remaining 20 combinations: enumerate (c1, c2) with c1 or c2 in {0, 5}
+  const int e1 = (c1 == 0) ? 0 : (c1 == 5 ? 1 : -1);
+  const int e2 = (c2 == 0) ? 0 : (c2 == 5 ? 1 : -1);
+  if (e1 >= 0) return 16 + e1 * 6 + c2;           // 16..27: c1 in {0,5}, c2 in 0..5
+  return 28 + e2 * 4 + (c1 - 1);                  // 28..35: c1 in 1..4, c2 in {0,5}
+}
+
+// one thread per (edge, pair, idx)
+__global__ void pairtab_build_kernel(const double * __restrict__ lookup, int n_pad, uint32_t n_edges,
+                                     double * __restrict__ pairtab)
+{
+  const size_t total = (size_t) n_edges * (n_pad / 2) * PAIR_ROW;
+  const size_t t = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= total) return;
+  const int idx = (int) (t % PAIR_ROW);
+  const size_t ep = t / PAIR_ROW;                  // edge * (n_pad/2) + pair
+  int c1 = -1, c2 = -1;
+  for (int a = 0; a < 6 && c1 < 0; ++a)
+    for (int b = 0; b < 6; ++b)
+      if (pair_index(a, b) == idx) { c1 = a; c2 = b; break; }
+  double v = 0.0;
+  if (c1 >= 0)
+  {
+    const int col[6] = {0, 1, 2, 4, 8, 15};
+    const double * r0 = lookup + (ep * 2) * 16;
+    v = r0[col[c1]] + r0[16 + col[c2]];
+  }
+  pairtab[t] = v;
+}
+
+// Same structure as preplace_kernel; one shared-memory lookup per two sites.
+// dynamic smem: NS * (wc/2) * PAIR_ROW * 8 (stages) + (wc/8) * TQ * 4 (pair indices, 4 per word) + NS * 8
+template <int TQ, int NS>
+__global__ void __launch_bounds__(TQ)
+preplace_pair_kernel(const double * __restrict__ pairtab, int n, int n_pad, uint32_t n_edges,
+                     const uint8_t * __restrict__ codes, const int * __restrict__ begin,
+                     const int * __restrict__ span, const uint32_t * __restrict__ perm, uint32_t nq,
+                     const int2 * __restrict__ range, int wc, double * __restrict__ pre, size_t pre_stride)
+{
+  extern __shared__ __align__(128) uint8_t smem_raw[];
+  const size_t stage_doubles = (size_t) (wc / 2) * PAIR_ROW;
+  double * stage = reinterpret_cast<double *>(smem_raw);                              // [NS][wc/2][PAIR_ROW]
+  uint32_t * cw = reinterpret_cast<uint32_t *>(smem_raw + NS * stage_doubles * 8);    // [wc/8][TQ]
+  uint64_t * bars = reinterpret_cast<uint64_t *>(cw + (size_t) (wc / 8) * TQ);
+  __shared__ uint32_t tq_q[TQ];
+  __shared__ int tq_b[TQ], tq_e[TQ];
+
+  const int tid = threadIdx.x;
+  const uint32_t slot = blockIdx.x * TQ + tid;
+  const bool valid = slot < nq;
+  const uint32_t q = valid ? perm[slot] : 0;
+  {
+    const int b = valid ? begin[q] : 0, w = valid ? span[q] : 0;
+    tq_q[tid] = q; tq_b[tid] = b; tq_e[tid] = b + w;
+  }
+  if (tid == 0)
+  {
+    for (int s = 0; s < NS; ++s) mbar_init(&bars[s], 1);
+    mbar_fence_init();
+  }
+  __syncthreads();
+
+  const int2 rg = range[blockIdx.x];
+  const int lo = rg.x, hi = rg.y;                  // lo is a multiple of 8
+  uint32_t it = 0;
+  double * out = pre + (size_t) q * pre_stride;
+  const size_t edge_stride = (size_t) (n_pad / 2) * PAIR_ROW;
+
+  for (int c0 = lo; c0 < hi; c0 += wc)
+  {
+    const int w8 = (min(wc, hi - c0) + 7) >> 3;    // words (4 pairs = 8 sites each) in this chunk
+    // rows past the padded alignment end do not exist: clamp the copy, the indices there are 0 -> idx(0,0)
+    const int pairs_avail = n_pad / 2 - c0 / 2;
+    const int pairs = min(w8 * 4, pairs_avail);
+    const uint32_t bytes = (uint32_t) pairs * PAIR_ROW * 8u;
+    for (int idx = tid; idx < w8 * TQ; idx += TQ)
+    {
+      const int t = idx / w8, j = idx - t * w8;
+      const int b = tq_b[t], e = tq_e[t];
+      const uint8_t * crow = codes + (size_t) tq_q[t] * n;
+      uint32_t word = 0;
+      #pragma unroll
+      for (int k = 0; k < 4; ++k)
+      {
+        const int s = c0 + 8 * j + 2 * k;
+        int c1 = 0, c2 = 0;
+        if (s >= b && s < e) { const int m = crow[s] & 15; c1 = m == 15 ? 5 : (m == 8 ? 4 : (m == 4 ? 3 : m)); }
+        if (s + 1 >= b && s + 1 < e) { const int m = crow[s + 1] & 15; c2 = m == 15 ? 5 : (m == 8 ? 4 : (m == 4 ? 3 : m)); }
+        // a pair beyond the copied rows must not be read: both classes are 0 there by construction
+        word |= (uint32_t) pair_index(c1, c2) << (8 * k);
+      }
+      cw[(size_t) j * TQ + t] = word;
+    }
+    __syncthreads();
+    const bool first = (c0 == lo);
+    const double * src0 = pairtab + (size_t) (c0 / 2) * PAIR_ROW;
+    if (tid == 0)
+    {
+      for (uint32_t p = 0; p < (uint32_t) (NS - 1) && p < n_edges; ++p)
+      {
+        const uint32_t st = (it + p) % NS;
+        mbar_expect_tx(&bars[st], bytes);
+        bulk_g2s(stage + st * stage_doubles, src0 + p * edge_stride, bytes, &bars[st]);
+      }
+    }
+    for (uint32_t b = 0; b < n_edges; ++b, ++it)
+    {
+      if (tid == 0 && b + NS - 1 < n_edges)
+      {
+        const uint32_t st = (it + NS - 1) % NS;
+        mbar_expect_tx(&bars[st], bytes);
+        bulk_g2s(stage + st * stage_doubles, src0 + (size_t) (b + NS - 1) * edge_stride, bytes, &bars[st]);
+      }
+      const uint32_t st = it % NS;
+      mbar_wait(&bars[st], (it / NS) & 1u);
+      const double * T = stage + st * stage_doubles;
+      double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+      // words past the copied rows hold idx(0,0) and read row 0 of the stage instead (value 0.0)
+      const int w8_safe = pairs / 4;
+      #pragma unroll 2
+      for (int j = 0; j < w8_safe; ++j)
+      {
+        const uint32_t word = cw[(size_t) j * TQ + tid];
+        const double * row = T + (size_t) j * (4 * PAIR_ROW);
+        a0 += row[word & 0xffu];
+        a1 += row[PAIR_ROW + ((word >> 8) & 0xffu)];
+        a2 += row[2 * PAIR_ROW + ((word >> 16) & 0xffu)];
+        a3 += row[3 * PAIR_ROW + (word >> 24)];
+      }
+      for (int pp = w8_safe * 4; pp < pairs; ++pp)       // tail pairs of a clamped copy
+      {
+        const uint32_t word = cw[(size_t) (pp >> 2) * TQ + tid];
+        const double v = T[(size_t) pp * PAIR_ROW + ((word >> (8 * (pp & 3))) & 0xffu)];
+        // same accumulator as in the unrolled loop (keyed by the absolute pair index mod 4)
+        if ((pp & 3) == 0) a0 += v; else if ((pp & 3) == 1) a1 += v; else if ((pp & 3) == 2) a2 += v; else a3 += v;
+      }
+      const double sum = (a0 + a1) + (a2 + a3);
+      if (valid)
+      {
+        if (first) out[b] = sum;
+        else out[b] += sum;
+      }
+      __syncthreads();
     }
   }
 }
