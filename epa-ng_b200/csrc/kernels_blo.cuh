@@ -178,7 +178,7 @@ __device__ __forceinline__ void warp_derivatives(const double * sum, double * ex
       const double lkk = __shfl_sync(0xffffffffu, lk, k);
       d0[k] = ek; d1[k] = lkk * ek; d2[k] = lkk * d1[k];
     }
-    #pragma unroll 2
+    #pragma unroll 4
     for (int s = lane; s < w; s += 32)
     {
       const double * row = sum + s * ROW;

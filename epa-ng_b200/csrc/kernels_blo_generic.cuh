@@ -1,11 +1,438 @@
-// kernels_blo_generic.cuh - HOT LOOP B for any state count (amino acids): placeholder until the
-// CTA-per-pair kernel lands; the DNA kernel lives in kernels_blo.cuh.
+// kernels_blo_generic.cuh - HOT LOOP B for any state count (amino acids: S = 20).
+//
+// Same algorithm and reference citations as kernels_blo.cuh (Tiny_Tree::place with branch-length
+// optimisation, src/tree/Tiny_Tree.cpp:131-218, src/core/pll/optimize.cpp:60-286, libpll sumtable /
+// derivatives / partials / likelihood kernels, PM/optimize/opt_algorithms.c:86-262); different
+// shape: with 20 states one (site, rate) unit is 1200 FMAs and the sumtable of a 300-site window
+// is 185 KB, so ONE CTA OF 256 THREADS WORKS ON ONE PAIR:
+//  * CLV passes: thread = (site, rate) unit, the R threads of a site are adjacent lanes (rate sum and
+//    scaling vote by shuffles / ballot); the three transition matrices, the per-character tip vectors,
+//    V, V^-1 and pi V^-1 live in shared memory (rate blocks padded against bank conflicts);
+//  * Newton iterations: thread = site over 1 + R(S-1) site-major planes of the sumtable (coalesced;
+//    the planes live in an L2-resident per-CTA scratch), diag tables in shared memory, block reduction
+//    in a fixed order.
 #pragma once
 #include "kernels_blo.cuh"
 
 namespace epa {
-inline cudaError_t launch_blo_generic(int, int, int, size_t, int, const DevModel *, BloArgs &, void **, size_t *, cudaStream_t)
+
+constexpr int GEN_THREADS = 256;
+
+template <int S, int R>
+struct GenSmem {
+  static constexpr int PS = S * S + 4;                 // padded rate block of a P-matrix
+  static constexpr int TVS = MAX_CODES * S + 4;        // padded rate block of the tip-vector table
+  static constexpr int NK = R * (S - 1);               // decaying components of a site
+  static constexpr int V = 0;
+  static constexpr int VINV = V + S * S;
+  static constexpr int PIVINV = VINV + S * S;
+  static constexpr int TIPLEFT = PIVINV + S * S;       // [code][S]
+  static constexpr int P = TIPLEFT + MAX_CODES * S;    // [3][R][PS]: distal, proximal, pendant
+  static constexpr int TV = P + 3 * R * PS;            // [R][TVS]
+  static constexpr int EX = TV + R * TVS;              // [R*S]
+  static constexpr int DIAG = EX + R * S;              // [3][NK]
+  static constexpr int RED = DIAG + 3 * NK;            // [2][8] block-reduction scratch
+  static constexpr int TOTAL = RED + 16;
+};
+
+// deterministic block-wide sum of two values (fixed order over the 8 warps)
+__device__ __forceinline__ void block_sum2(double & a, double & b, double * red)
 {
+  a = warp_sum(a);
+  b = warp_sum(b);
+  const int warp = threadIdx.x >> 5;
+  __syncthreads();                                     // previous readers of `red` are done
+  if ((threadIdx.x & 31) == 0) { red[warp] = a; red[8 + warp] = b; }
+  __syncthreads();
+  double sa = 0.0, sb = 0.0;
+  #pragma unroll
+  for (int w = 0; w < GEN_THREADS / 32; ++w) { sa += red[w]; sb += red[8 + w]; }
+  a = sa; b = sb;
+}
+
+template <int S, int R>
+__device__ __forceinline__ void gen_pmatrix(double * sm, double t, int which)
+{
+  using L = GenSmem<S, R>;
+  for (int idx = threadIdx.x; idx < R * S; idx += GEN_THREADS)
+    sm[L::EX + idx] = expm1(c_model.eigenvals[idx % S] * c_model.rates[idx / S] * t);
+  __syncthreads();
+  double * P = sm + L::P + which * R * L::PS;
+  for (int idx = threadIdx.x; idx < R * S * S; idx += GEN_THREADS)
+  {
+    const int r = idx / (S * S), i = (idx / S) % S, j = idx % S;
+    double acc = (i == j) ? 1.0 : 0.0;
+    for (int k = 0; k < S; ++k) acc += (sm[L::VINV + i * S + k] * sm[L::EX + r * S + k]) * sm[L::V + k * S + j];
+    P[r * L::PS + i * S + j] = acc;
+  }
+  __syncthreads();
+}
+
+template <int S, int R>
+__device__ __forceinline__ void gen_tipvec(double * sm)
+{
+  using L = GenSmem<S, R>;
+  const double * P = sm + L::P + 2 * R * L::PS;
+  const int ncodes = c_model.ncodes;
+  for (int idx = threadIdx.x; idx < R * ncodes * S; idx += GEN_THREADS)
+  {
+    const int r = idx / (ncodes * S), c = (idx / S) % ncodes, i = idx % S;
+    const uint32_t mask = c_model.code2mask[c];
+    double acc = 0.0;
+    for (int j = 0; j < S; ++j)
+      if ((mask >> j) & 1u) acc += P[r * L::PS + i * S + j];
+    sm[L::TV + r * L::TVS + c * S + i] = acc;
+  }
+  __syncthreads();
+}
+
+// sumtable row of unit (site s, rate r): stationary component summed over the rates into plane 0,
+// decaying components into planes 1 + r(S-1) + (j-1)
+template <int S, int R>
+__device__ __forceinline__ void gen_store_row(double * sum, int wpad, int s, int r, bool act, double wr, const double (&st)[S])
+{
+  const double base = rate_sum<R>(st[0] * wr);
+  if (act)
+  {
+    if (r == 0) sum[s] = base;
+    #pragma unroll
+    for (int j = 1; j < S; ++j) sum[(size_t) (r * (S - 1) + j) * wpad + s] = st[j];
+  }
+}
+
+template <int S, int R>
+__device__ __forceinline__ double gen_pass_tip(double * sm, double * sum, int wpad, const double * __restrict__ D,
+                                               const double * __restrict__ X, const uint32_t * __restrict__ sD,
+                                               const uint32_t * __restrict__ sX, const uint8_t * __restrict__ qc, int w)
+{
+  using L = GenSmem<S, R>;
+  const int lane = threadIdx.x & 31;
+  const int r = threadIdx.x % R;
+  const double * Pd = sm + L::P + r * L::PS;
+  const double * Pp = sm + L::P + (R + r) * L::PS;
+  const double * tvr = sm + L::TV + r * L::TVS;
+  const double wr = c_model.weights[r];
+  double acc = 0.0, unused = 0.0;
+  const int n_units = ((w * R + GEN_THREADS - 1) / GEN_THREADS) * GEN_THREADS;
+  for (int u = threadIdx.x; u < n_units; u += GEN_THREADS)
+  {
+    const int s = u / R;
+    const bool act = s < w;
+    const int sc = act ? s : w - 1;
+    double dv[S], xv[S], in[S];
+    load_vec<S>(D + ((size_t) sc * R + r) * S, dv);
+    load_vec<S>(X + ((size_t) sc * R + r) * S, xv);
+    const int code = qc[sc] & (MAX_CODES - 1);
+    uint32_t scal = __ldg(sD + sc) + __ldg(sX + sc);
+    bool small = true;
+    #pragma unroll 4
+    for (int i = 0; i < S; ++i)
+    {
+      double ta = 0.0, tb = 0.0;
+      #pragma unroll
+      for (int j = 0; j < S; ++j) { ta += Pd[i * S + j] * dv[j]; tb += Pp[i * S + j] * xv[j]; }
+      in[i] = ta * tb;
+      small = small && (in[i] < EPA_SCALE_THRESHOLD);
+    }
+    if (group_all<R>(small, lane))
+    {
+      #pragma unroll
+      for (int i = 0; i < S; ++i) in[i] *= EPA_SCALE_FACTOR;
+      scal += 1;
+    }
+    double term = 0.0;
+    #pragma unroll
+    for (int i = 0; i < S; ++i) term += (in[i] * c_model.freqs[i]) * tvr[code * S + i];
+    term = rate_sum<R>(term * wr);
+    if (act && r == 0) acc += log(term) + (scal ? (double) scal * EPA_LOG_SCALE_THRESHOLD : 0.0);
+    double st[S];
+    #pragma unroll 4
+    for (int j = 0; j < S; ++j)
+    {
+      double right = 0.0;
+      #pragma unroll
+      for (int k = 0; k < S; ++k) right += sm[L::V + j * S + k] * in[k];
+      st[j] = sm[L::TIPLEFT + code * S + j] * right;
+    }
+    gen_store_row<S, R>(sum, wpad, s, r, act, wr, st);
+  }
+  block_sum2(acc, unused, sm + L::RED);
+  return acc;
+}
+
+template <int S, int R>
+__device__ __forceinline__ void gen_pass_distal(double * sm, double * sum, int wpad, const double * __restrict__ D,
+                                                const double * __restrict__ X, const uint8_t * __restrict__ qc, int w)
+{
+  using L = GenSmem<S, R>;
+  const int lane = threadIdx.x & 31;
+  const int r = threadIdx.x % R;
+  const double * Pp = sm + L::P + (R + r) * L::PS;
+  const double * tvr = sm + L::TV + r * L::TVS;
+  const double wr = c_model.weights[r];
+  const int n_units = ((w * R + GEN_THREADS - 1) / GEN_THREADS) * GEN_THREADS;
+  for (int u = threadIdx.x; u < n_units; u += GEN_THREADS)
+  {
+    const int s = u / R;
+    const bool act = s < w;
+    const int sc = act ? s : w - 1;
+    double dv[S], xv[S], in[S];
+    load_vec<S>(D + ((size_t) sc * R + r) * S, dv);
+    load_vec<S>(X + ((size_t) sc * R + r) * S, xv);
+    const int code = qc[sc] & (MAX_CODES - 1);
+    bool small = true;
+    #pragma unroll 4
+    for (int i = 0; i < S; ++i)
+    {
+      double tb = 0.0;
+      #pragma unroll
+      for (int j = 0; j < S; ++j) tb += Pp[i * S + j] * xv[j];
+      in[i] = tvr[code * S + i] * tb;
+      small = small && (in[i] < EPA_SCALE_THRESHOLD);
+    }
+    if (group_all<R>(small, lane))
+    {
+      #pragma unroll
+      for (int i = 0; i < S; ++i) in[i] *= EPA_SCALE_FACTOR;
+    }
+    double st[S];
+    #pragma unroll 4
+    for (int j = 0; j < S; ++j)
+    {
+      double left = 0.0, right = 0.0;
+      #pragma unroll
+      for (int k = 0; k < S; ++k) { left += dv[k] * sm[L::PIVINV + k * S + j]; right += sm[L::V + j * S + k] * in[k]; }
+      st[j] = left * right;
+    }
+    gen_store_row<S, R>(sum, wpad, s, r, act, wr, st);
+  }
+  __syncthreads();
+}
+
+template <int S, int R>
+__device__ __forceinline__ void gen_derivatives(double * sm, const double * sum, int wpad, int w, double t, double & f, double & df)
+{
+  using L = GenSmem<S, R>;
+  constexpr int NK = L::NK;
+  __syncthreads();
+  for (int k = threadIdx.x; k < NK; k += GEN_THREADS)
+  {
+    const double lk = c_model.eigenvals[1 + k % (S - 1)] * c_model.rates[k / (S - 1)];
+    const double e = exp(lk * t) * c_model.weights[k / (S - 1)];
+    sm[L::DIAG + k] = e; sm[L::DIAG + NK + k] = lk * e; sm[L::DIAG + 2 * NK + k] = lk * lk * e;
+  }
+  __syncthreads();
+  double a1 = 0.0, a2 = 0.0;
+  for (int s = threadIdx.x; s < w; s += GEN_THREADS)
+  {
+    double c0 = sum[s], c1 = 0.0, c2 = 0.0;
+    #pragma unroll 4
+    for (int k = 0; k < NK; ++k)
+    {
+      const double x = sum[(size_t) (k + 1) * wpad + s];
+      c0 += x * sm[L::DIAG + k]; c1 += x * sm[L::DIAG + NK + k]; c2 += x * sm[L::DIAG + 2 * NK + k];
+    }
+    const double inv = 1.0 / c0;
+    const double g1 = -c1 * inv;
+    a1 += g1;
+    a2 += g1 * g1 - c2 * inv;
+  }
+  block_sum2(a1, a2, sm + L::RED);
+  f = a1; df = a2;
+}
+
+template <int S, int R>
+__device__ __forceinline__ double gen_newton(double * sm, const double * sum, int wpad, int w, double xmin, double xguess,
+                                             double xmax, double tol)
+{
+  double x = fmax(fmin(xguess, xmax), xmin);
+  double xl = xmin, xh = xmax;
+  const double dxmax = xmax / EPA_NR_MAX_ITERS;
+  int iter = 0;
+  for (;;)
+  {
+    if (iter++ > EPA_NR_MAX_ITERS) return 0.0;
+    double f, df;
+    gen_derivatives<S, R>(sm, sum, wpad, w, x, f, df);
+    if (!isfinite(f) || !isfinite(df)) return 0.0;
+    double dx;
+    if (df > 0.0)
+    {
+      if (fabs(f) < tol) return x;
+      if (f < 0.0) xl = x; else xh = x;
+      dx = -1.0 * f / df;
+    }
+    else
+      dx = -1.0 * f / fabs(df);
+    dx = fmax(fmin(dx, dxmax), -dxmax);
+    if (x + dx < xl) dx = xl - x;
+    if (x + dx > xh) dx = xh - x;
+    if (fabs(dx) < tol) return x;
+    x += dx;
+    x = fmax(fmin(x, xmax), xmin);
+  }
+}
+
+template <int S, int R>
+__global__ void __launch_bounds__(GEN_THREADS, 1)
+blo_generic_kernel(BloArgs a, int wpad)
+{
+  using L = GenSmem<S, R>;
+  extern __shared__ __align__(16) double sm[];
+  __shared__ unsigned long long s_item;
+  for (int i = threadIdx.x; i < S * S; i += GEN_THREADS)
+  {
+    sm[L::V + i] = c_model.eigenvecs[i];
+    sm[L::VINV + i] = c_model.inv_eigenvecs[i];
+    sm[L::PIVINV + i] = c_model.pivinv[i];
+  }
+  const int ncodes = c_model.ncodes;
+  __syncthreads();
+  for (int i = threadIdx.x; i < ncodes * S; i += GEN_THREADS)
+  {
+    const int c = i / S, j = i % S;
+    const uint32_t mask = c_model.code2mask[c];
+    double acc = 0.0;
+    for (int k = 0; k < S; ++k)
+      if ((mask >> k) & 1u) acc += sm[L::PIVINV + k * S + j];
+    sm[L::TIPLEFT + i] = acc;
+  }
+  __syncthreads();
+  double * sum = a.scratch + (size_t) blockIdx.x * (size_t) (1 + L::NK) * wpad;
+
+  for (;;)
+  {
+    __syncthreads();
+    if (threadIdx.x == 0) s_item = atomicAdd(a.counter, 1ull);
+    __syncthreads();
+    const unsigned long long item = s_item;
+    if (item >= a.n_pairs) break;
+    uint32_t pid, q, e;
+    if (a.pair_q)
+    {
+      pid = a.work ? a.work[item] : (uint32_t) item;
+      q = a.pair_q[pid];
+      e = a.pair_e[pid];
+    }
+    else
+    {
+      e = (uint32_t) (item / a.nq);
+      q = a.perm ? a.perm[item % a.nq] : (uint32_t) (item % a.nq);
+      pid = q * a.n_edges + e;
+    }
+    const EdgeDev ed = a.edges[e];
+    const int begin = a.begin[q], w = a.span[q];
+    if (w <= 0 || w > wpad)
+    {
+      if (threadIdx.x == 0) a.out[pid] = BloResult{NAN, NAN, NAN};
+      continue;
+    }
+    const int n = a.n;
+    const double * D = a.tree.clv + ed.distal * a.tree.clv_stride + (size_t) begin * R * S;
+    const double * X = a.tree.clv + ed.proximal * a.tree.clv_stride + (size_t) begin * R * S;
+    const uint32_t * sD = a.tree.scaler + (size_t) ed.distal * n + begin;
+    const uint32_t * sX = a.tree.scaler + (size_t) ed.proximal * n + begin;
+    const uint8_t * qc = a.codes + (size_t) q * n + begin;
+
+    const double orig = ed.length;
+    double len[3] = {orig / 2.0, orig / 2.0, EPA_DEFAULT_PENDANT};
+    const double original_length = len[0] * 2;
+    double old_d = len[0], old_e = len[2], loglikelihood = 0.0;
+    int smoothings = EPA_SMOOTHINGS;
+    unsigned rebuild = 7u;
+    bool first = true, distal_phase = false;
+    for (;;)
+    {
+      #pragma unroll 1
+      for (int mi = 0; mi < 3; ++mi)
+        if (rebuild & (1u << mi))
+        {
+          const double t = mi == 0 ? len[0] : (mi == 1 ? len[1] : len[2]);
+          gen_pmatrix<S, R>(sm, t, mi);
+          if (mi == 2) gen_tipvec<S, R>(sm);
+        }
+      rebuild = 0u;
+      double xmin, xmax, xguess;
+      if (!distal_phase)
+      {
+        const double new_logl = -gen_pass_tip<S, R>(sm, sum, wpad, D, X, sD, sX, qc, w);
+        if (first) { loglikelihood = new_logl; first = false; }
+        else
+        {
+          if (new_logl - loglikelihood > new_logl * 1e-14)
+          {
+            len[2] = old_e; len[0] = old_d; len[1] = original_length - old_d;
+            break;
+          }
+          --smoothings;
+          if (fabs(new_logl - loglikelihood) < EPA_BLO_EPSILON) smoothings = 0;
+          loglikelihood = new_logl;
+        }
+        if (!smoothings) break;
+        old_d = len[0]; old_e = len[2];
+        xmin = EPA_MIN_BRLEN; xmax = EPA_MAX_BRLEN; xguess = len[2];
+        if (xguess < xmin || xguess > xmax) xguess = EPA_DEFAULT_BRLEN;
+      }
+      else
+      {
+        gen_pass_distal<S, R>(sm, sum, wpad, D, X, qc, w);
+        xmin = fmin(EPA_MIN_BRLEN / 2.0, original_length / 2.0);
+        xmax = original_length - xmin / 10.0;
+        xguess = len[0];
+        if (xguess < xmin || xguess > xmax) xguess = original_length / 2.0;
+      }
+      const double xres = gen_newton<S, R>(sm, sum, wpad, w, xmin, xguess, xmax, xmin / 10.0);
+      if (xres > 0.0)
+      {
+        if (!distal_phase) { len[2] = xres; rebuild = 4u; }
+        else { len[0] = xres; len[1] = original_length - xres; rebuild = 3u; }
+      }
+      distal_phase = !distal_phase;
+    }
+    if (threadIdx.x == 0)
+    {
+      BloResult res;
+      res.logl = -loglikelihood;
+      res.distal = (orig / (len[0] + len[1])) * len[0];
+      res.pendant = len[2];
+      a.out[pid] = res;
+    }
+  }
+}
+
+// host-side launcher; scratch is (re)allocated by the caller-owned buffer
+template <int S, int R>
+inline cudaError_t launch_blo_generic_sr(int sm_count, size_t smem_optin, int max_span, BloArgs & a, void ** scratch,
+                                         size_t * scratch_cap, cudaStream_t stream)
+{
+  using L = GenSmem<S, R>;
+  const size_t smem = (size_t) L::TOTAL * sizeof(double);
+  if (smem > smem_optin) return cudaErrorInvalidConfiguration;
+  const int wpad = (std::max(1, max_span) + 31) & ~31;
+  const int ctas_per_sm = (int) std::max<size_t>(1, std::min<size_t>(3, smem_optin / (smem + 1024)));
+  const unsigned grid = (unsigned) std::min<uint64_t>((uint64_t) sm_count * ctas_per_sm, a.n_pairs);
+  const size_t need = (size_t) grid * (1 + L::NK) * wpad * sizeof(double);
+  if (need > *scratch_cap)
+  {
+    if (*scratch) cudaFree(*scratch);
+    *scratch = nullptr; *scratch_cap = 0;
+    cudaError_t e = cudaMalloc(scratch, need);
+    if (e != cudaSuccess) return e;
+    *scratch_cap = need;
+  }
+  a.scratch = static_cast<double *>(*scratch);
+  cudaError_t e = cudaFuncSetAttribute(blo_generic_kernel<S, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+  if (e != cudaSuccess) return e;
+  blo_generic_kernel<S, R><<<grid, GEN_THREADS, smem, stream>>>(a, wpad);
+  return cudaGetLastError();
+}
+
+inline cudaError_t launch_blo_generic(int S, int R, int sm_count, size_t smem_optin, int max_span, const DevModel *,
+                                      BloArgs & a, void ** scratch, size_t * scratch_cap, cudaStream_t stream)
+{
+  if (S == 20 && R == 4) return launch_blo_generic_sr<20, 4>(sm_count, smem_optin, max_span, a, scratch, scratch_cap, stream);
+  if (S == 20 && R == 1) return launch_blo_generic_sr<20, 1>(sm_count, smem_optin, max_span, a, scratch, scratch_cap, stream);
   return cudaErrorNotSupported;
 }
+
 }  // namespace epa

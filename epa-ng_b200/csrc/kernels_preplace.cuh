@@ -218,7 +218,7 @@ preplace_kernel(const DevModel * __restrict__ m, const double * __restrict__ loo
       for (int k = 0; k < 4; ++k)
       {
         const int s = c0 + 4 * j + k;
-        uint32_t col8 = 0;
+        uint32_t col8 = (K == 16 ? 0u : 24u) * 8u;      // zero column: 0 for DNA, 24 for amino acids
         if (s >= b && s < e) col8 = (uint32_t) c2c[crow[s] & (MAX_CODES - 1)] * 8u;
         word |= col8 << (8 * k);
       }

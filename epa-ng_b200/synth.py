@@ -85,12 +85,21 @@ def pmatrix(lam, U, sq, t):
     return P / P.sum(axis=1, keepdims=True)
 
 
-def evolve_msa(structure, n_sites, subst, freqs, cat_rates, seed=1):
-    """uint8[T][n_sites] state indices evolved from a uniform root sequence."""
+def evolve_msa(structure, n_sites, subst, freqs, cat_rates, seed=1, eig=None):
+    """uint8[T][n_sites] state indices evolved from a uniform root sequence. eig = (eigenvals, V, Vinv)
+    in libpll layout replaces the numpy eigen-decomposition (protein models)."""
     children, length, roots, T = structure
     S = len(freqs)
     rng = np.random.default_rng(seed + 1000)
-    lam, U, sq = gtr_model_matrices(np.asarray(subst, float), np.asarray(freqs, float), cat_rates, S)
+    if eig is None:
+        lam, U, sq = gtr_model_matrices(np.asarray(subst, float), np.asarray(freqs, float), cat_rates, S)
+        pm = lambda t: pmatrix(lam, U, sq, t)
+    else:
+        ev, V, Vi = eig
+
+        def pm(t):
+            P = np.clip(np.eye(S) + (Vi * np.expm1(ev * t)[None, :]) @ V, 0, None)
+            return P / P.sum(axis=1, keepdims=True)
     site_cat = rng.integers(0, len(cat_rates), size=n_sites)
     root_seq = rng.integers(0, S, size=n_sites).astype(np.uint8)
     out = np.zeros((T, n_sites), dtype=np.uint8)
@@ -105,7 +114,7 @@ def evolve_msa(structure, n_sites, subst, freqs, cat_rates, seed=1):
                 sel = site_cat == c
                 if not sel.any():
                     continue
-                cum = np.cumsum(pmatrix(lam, U, sq, length[x] * r), axis=1)
+                cum = np.cumsum(pm(length[x] * r), axis=1)
                 rows = cum[pseq[sel]]
                 seq[sel] = (u[sel][:, None] > rows).sum(axis=1).clip(0, S - 1)
             if x < T:
@@ -154,10 +163,18 @@ def dataset(T=1000, n_sites=1000, n_queries=1000, window=200, kind="dna", seed_t
         subst, freqs = np.ones(6), np.full(4, 0.25)
         alpha = 0.5 if alpha is None else alpha
         model = "GTR{1/1/1/1/1/1}+FU{0.25/0.25/0.25/0.25}+G4{%g}" % alpha
+        eig = None
     else:
-        raise NotImplementedError("AA synthetic data needs the LG table from the host library")
+        # amino acids: LG, eigen system from the host library's model parser (no device needed)
+        from . import session
+        alphabet, S = AA, 20
+        alpha = 0.8 if alpha is None else alpha
+        model = "LG+G4{%g}" % alpha
+        pm = session.parse_model(model)
+        subst, freqs = None, pm["freqs"]
+        eig = (pm["eigenvals"], pm["eigenvecs"].reshape(S, S), pm["inv_eigenvecs"].reshape(S, S))
     cat_rates = discrete_gamma_mean(alpha, 4)
-    states = evolve_msa(st, n_sites, subst, freqs, cat_rates, seed_tree)
+    states = evolve_msa(st, n_sites, subst, freqs, cat_rates, seed_tree, eig=eig)
     letters = np.frombuffer(alphabet.encode(), dtype=np.uint8)
     ref = letters[states]
     names = [("t%04d" % t if T <= 10000 else "t%06d" % t) for t in range(T)]

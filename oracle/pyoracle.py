@@ -198,6 +198,16 @@ class Model:
         return out
 
 
+_PROT = None
+
+
+def protein_tables():
+    global _PROT
+    if _PROT is None:
+        _PROT = json.load(open(os.path.join(HERE, "protein_models.json")))
+    return _PROT
+
+
 def _read_braces(s: str, pos: int):
     """Parses an optional {a/b/c} at s[pos:]; returns (values|None, new_pos)."""
     if pos < len(s) and s[pos] == '{':
@@ -222,27 +232,38 @@ def parse_model(desc: str) -> Model:
         if p != -1:
             pos = min(pos, p)
     name, opts = desc[:pos].upper(), desc[pos:]
-    if name not in ("GTR", "JC", "K80", "F81", "HKY", "DNA"):
+    prot = protein_tables()
+    if name not in ("GTR", "JC", "K80", "F81", "HKY", "DNA") and name not in prot:
         raise ValueError(f"oracle: unsupported model name {name}")
     if name == "DNA":
         name, opts = "GTR", "+G+F"
-    S = 4
-    sym = {"JC": [0] * 6, "F81": [0] * 6, "K80": [0, 1, 0, 0, 1, 0], "HKY": [0, 1, 0, 0, 1, 0],
-           "GTR": list(range(6))}[name]
-    nuniq = max(sym) + 1
-    # defaults for ML-mode parameters: 0.5 .. 0.5 1.0 (Model.cpp:484-490); JC/F81 all-equal
-    if name in ("JC", "F81"):
-        subst = np.ones(6)
-    elif name in ("K80", "HKY"):
-        # unique rates default 0.5,... ,1.0 over the symmetry classes; last class is the normaliser
-        uniq = [1.0, 1.0]
-        subst = np.array([uniq[c] for c in sym], dtype=float)
+    if name in prot:
+        # empirical protein matrix: exchangeabilities and frequencies of the model
+        # (libs/pll-modules/libs/libpll/src/maps.c:288-, :1472-; data in oracle/protein_models.json)
+        S = 20
+        sym, nuniq = None, 0
+        subst = np.array(prot[name]["rates"], dtype=float)
+        freqs = np.array(prot[name]["freqs"], dtype=float)
     else:
-        subst = np.array([0.5] * 5 + [1.0])
-    freqs = np.full(S, 1.0 / S)
+        S = 4
+        sym = {"JC": [0] * 6, "F81": [0] * 6, "K80": [0, 1, 0, 0, 1, 0], "HKY": [0, 1, 0, 0, 1, 0],
+               "GTR": list(range(6))}[name]
+        nuniq = max(sym) + 1
+        # defaults for ML-mode parameters: 0.5 .. 0.5 1.0 (Model.cpp:484-490); JC/F81 all-equal
+        if name in ("JC", "F81"):
+            subst = np.ones(6)
+        elif name in ("K80", "HKY"):
+            # unique rates default 0.5,... ,1.0 over the symmetry classes; last class is the normaliser
+            uniq = [1.0, 1.0]
+            subst = np.array([uniq[c] for c in sym], dtype=float)
+        else:
+            subst = np.array([0.5] * 5 + [1.0])
+        freqs = np.full(S, 1.0 / S)
     alpha, ncat, median, gamma = 1.0, 1, False, False
     vals, i = _read_braces(opts, 0)
     if vals is not None:
+        if sym is None:
+            raise ValueError("oracle: user-defined protein rates are not supported")
         if len(vals) != nuniq:
             raise ValueError("wrong number of substitution rates")
         last = vals[sym[-1]]

@@ -6,6 +6,7 @@
 cfg1/      the reference's own test data (test/data/{ref.tre,aln.fasta,query.fasta}; data files,
            not sources) and the reference's placements on them for two model strings and three
            option sets (default heuristic, --no-heur unfiltered, heuristic unfiltered).
+synthaa/   a 32-taxon synthetic amino-acid data set (LG+G4) with 60 queries, a few ambiguity codes.
 synth64/   a 64-taxon synthetic DNA data set (epa-ng_b200/synth.py, seeds fixed) with the
            reference's placements of 200 window queries, default options and --no-heur for
            the first 5 queries.
@@ -62,6 +63,24 @@ def main():
     synth.write_fasta(q5, ds["qnames"][:5], ds["queries"][:5])
     runs["noheur_all_first5"] = run(tf, sf, q5, ds["model"], ("--no-heur", "--filter-min-lwr", "0", "--filter-max", "125"))
     os.remove(q5)
+    json.dump(runs, open(os.path.join(d, "reference_placements.json"), "w"), indent=1)
+
+    # amino acids (LG+G4): 32 taxa, 120 sites, 60 queries of 80 residues; a few ambiguity codes
+    # (X is scored on the column of N in the reference's preplacement)
+    d = os.path.join(HERE, "synthaa")
+    ds = synth.dataset(T=32, n_sites=120, n_queries=60, window=80, kind="aa")
+    q = ds["queries"]
+    for i, ch in enumerate("XBZ-X"):
+        row = q[i]
+        inside = [k for k in range(len(row)) if row[k] != ord('-')]
+        row[inside[7 + i]] = ord(ch)
+        row[inside[31 + 2 * i]] = ord(ch)
+    tf, sf, qf = synth.write_dataset(ds, d)
+    runs = {"default": run(tf, sf, qf, ds["model"], ())}
+    q3 = os.path.join(d, "query3.fasta")
+    synth.write_fasta(q3, ds["qnames"][:3], ds["queries"][:3])
+    runs["noheur_all_first3"] = run(tf, sf, q3, ds["model"], ("--no-heur", "--filter-min-lwr", "0", "--filter-max", "61"))
+    os.remove(q3)
     json.dump(runs, open(os.path.join(d, "reference_placements.json"), "w"), indent=1)
     print("golden fixtures written")
 

@@ -136,6 +136,12 @@ def synth64_case(query_file="query.fasta", **kw) -> Case:
     return load_case(os.path.join(d, "tree.nwk"), os.path.join(d, "ref.fasta"), os.path.join(d, query_file), model, **kw)
 
 
+def synthaa_case(query_file="query.fasta", **kw) -> Case:
+    d = os.path.join(GOLDEN, "synthaa")
+    return load_case(os.path.join(d, "tree.nwk"), os.path.join(d, "ref.fasta"), os.path.join(d, query_file),
+                     "LG+G4{0.8}", **kw)
+
+
 def assert_placements_close(got, want, what="", logl_rel=1e-6, lwr_abs=1e-6, len_abs=1e-4):
     """got/want: lists of (edge, logl, lwr, distal, pendant) sorted by LWR descending."""
     assert [int(g[0]) for g in got] == [int(w[0]) for w in want], f"{what}: edge lists differ {got} vs {want}"

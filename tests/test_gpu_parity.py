@@ -226,3 +226,65 @@ def test_edge_cases(synth64, built):
         ctx2.build_lookup()
     assert ei.value.code == capi.EPA_ERR_STATE
     ctx2.close()
+
+
+# ---------------------------------------------------------------------------------------------
+#  amino acids (20-state path, LG+G4)
+# ---------------------------------------------------------------------------------------------
+@pytest.fixture(scope="module")
+def synthaa(built):
+    case = helpers.synthaa_case()
+    ctx = helpers.make_context(case)
+    ctx.build_lookup()
+    case.placer.build_lookup()
+    yield case, ctx
+    ctx.close()
+
+
+def test_aa_clvs_and_tree_logl(synthaa):
+    case, ctx = synthaa
+    _check_clvs(case, ctx)
+    want = case.ref.tree_logl(0)
+    vals = [ctx.edge_loglikelihood(e) for e in range(case.tree.num_branches)]
+    assert np.allclose(vals, want, rtol=1e-11, atol=0)
+
+
+def test_aa_lookup_and_preplace(synthaa, built):
+    case, ctx = synthaa
+    _check_lookup(case, ctx)
+    got, want = _check_preplace(case, ctx)
+    n_pairs = ctx.select(built.capi.default_options())
+    q, e, _ = ctx.get_pairs(raw=False)
+    mine = {}
+    for qi, ei in zip(q, e):
+        mine.setdefault(int(qi), set()).add(int(ei))
+    for qi in range(len(case.qseqs)):
+        assert mine[qi] == set(case.placer.candidates(want[qi])), f"candidates of query {qi}"
+
+
+def test_aa_thorough_matches_oracle(synthaa, built):
+    case, ctx = synthaa
+    opts = built.capi.default_options(prescoring=0)
+    ctx.upload_queries(case.query_rows[:4])
+    ctx.select(opts)
+    ctx.place_pairs(opts)
+    q, e, raw = ctx.get_pairs()
+    for qi, ei, r in zip(q, e, raw):
+        p = case.placer.thorough(case.qseqs[qi], int(ei))
+        assert abs(r["likelihood"] - p.logl) <= 1e-9 * abs(p.logl), (qi, ei, r, p)
+        assert abs(r["pendant_length"] - p.pendant) <= 1e-6, (qi, ei, r, p)
+        assert abs(r["distal_length"] - p.distal) <= 1e-6, (qi, ei, r, p)
+
+
+def test_aa_placements_match_reference(synthaa, built):
+    case, ctx = synthaa
+    gold = helpers.golden("synthaa")
+    out, counts = ctx.place_chunk(case.query_rows, built.capi.default_options())
+    got = dict(zip(case.qnames, helpers.records_to_lists(out, counts)))
+    bad = []
+    for name, want in gold["default"]["placements"].items():
+        try:
+            helpers.assert_placements_close(got[name], want, name)
+        except AssertionError as e:
+            bad.append(str(e))
+    assert not bad, f"{len(bad)} of {len(gold['default']['placements'])} AA queries differ from the reference: {bad[:3]}"

@@ -58,8 +58,25 @@ def test_model_matches_oracle(sess, model):
             assert np.allclose(P.sum(axis=1), 1.0, atol=1e-13)
 
 
+@pytest.mark.parametrize("model", ["LG+G4{0.8}", "WAG", "JTT+G4{1.3}", "DAYHOFF+FE+G2{0.5}"])
+def test_protein_model_matches_oracle(sess, model):
+    o = helpers.oracle()
+    want = o.parse_model(model)
+    got = sess.parse_model(model)
+    S = 20
+    assert got["states"] == S and got["rate_cats"] == want.rate_cats
+    assert np.allclose(got["rates"], want.rates, rtol=1e-13, atol=0)
+    assert np.allclose(got["freqs"], want.freqs, rtol=1e-15, atol=0)
+    V, Vi = got["eigenvecs"].reshape(S, S), got["inv_eigenvecs"].reshape(S, S)
+    Vw, Viw = want.eigenvecs.reshape(S, S), want.inv_eigenvecs.reshape(S, S)
+    for t in (1e-3, 0.1, 2.0):
+        P = np.eye(S) + (Vi * np.expm1(got["eigenvals"] * t)[None, :]) @ V
+        Pw = np.eye(S) + (Viw * np.expm1(want.eigenvals * t)[None, :]) @ Vw
+        assert np.allclose(P, Pw, rtol=0, atol=1e-13)
+
+
 def test_model_errors(sess, built):
-    for bad in ["GTR+I", "LG+G", "GTR{1/2/3}", "GTR+FU{0.5/0.5}", "GTR+R4", "FOO"]:
+    for bad in ["GTR+I", "LG{1/2}+G", "GTR{1/2/3}", "GTR+FU{0.5/0.5}", "GTR+R4", "FOO"]:
         with pytest.raises(built.capi.EpaError):
             sess.parse_model(bad)
 

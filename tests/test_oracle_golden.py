@@ -81,3 +81,19 @@ def test_range_restriction_invariance():
     o.lib().orc_place_thorough(C.byref(case.model.c()), case.n, C.byref(d.c), C.byref(p.c), length,
                                m.ctypes.data_as(C.POINTER(C.c_uint32)), b, w, C.byref(res))
     assert res.logl == pl.logl and res.pendant == pl.pendant
+
+
+def test_synthaa_matches_reference():
+    """Amino acids (LG+G4, 20-state path) incl. the X -> N preplacement quirk of the reference."""
+    gold = helpers.golden("synthaa")
+    case = helpers.synthaa_case()
+    got = _oracle_run(case)
+    want = gold["default"]["placements"]
+    assert set(got) == set(want)
+    bad = []
+    for name in want:
+        try:
+            helpers.assert_placements_close(got[name], want[name], name)
+        except AssertionError as e:
+            bad.append(str(e))
+    assert not bad, f"{len(bad)} of {len(want)} queries differ: {bad[:3]}"
