@@ -842,8 +842,8 @@ extern "C" int epa_select(epa_ctx * ctx, const epa_options * opts, uint64_t * n_
   else
   {
     if (ctx->stage < ST_PREPLACED) return fail(ctx, EPA_ERR_STATE, "epa_preplace has not run");
-    if (opts->heuristic != 0) return fail(ctx, EPA_ERR_ARG, "only the dynamic (accumulated LWR) heuristic is supported");
-    if (!(opts->prescoring_threshold >= 0.0 && opts->prescoring_threshold <= 1.0))
+    if (opts->heuristic < 0 || opts->heuristic > 2) return fail(ctx, EPA_ERR_ARG, "unknown heuristic %d", opts->heuristic);
+    if (opts->heuristic != 2 && !(opts->prescoring_threshold >= 0.0 && opts->prescoring_threshold <= 1.0))
       return fail(ctx, EPA_ERR_ARG, "prescoring threshold outside [0,1]");
     ctx->implicit_pairs = false;
     ctx->n_pairs = 0;
@@ -860,7 +860,7 @@ extern "C" int epa_select(epa_ctx * ctx, const epa_options * opts, uint64_t * n_
       CU(ctx->edge_hist.ensure((nkeys + 1) * sizeof(uint32_t)));
       const unsigned blocks = (nq + 7) / 8;
       select_count_kernel<<<blocks, 256, 0, ctx->stream>>>(ctx->pre.as<double>(), ctx->pre_stride, (int) B, nq,
-                                                           opts->prescoring_threshold, ctx->cnt.as<uint32_t>(),
+                                                           opts->heuristic, opts->prescoring_threshold, ctx->cnt.as<uint32_t>(),
                                                            ctx->cutv.as<double>(), ctx->cuti.as<int>());
       LAUNCHED(ctx);
       exclusive_scan_kernel<<<1, 1024, 0, ctx->stream>>>(ctx->cnt.as<uint32_t>(), ctx->off.as<uint32_t>(), nq, ctx->d_total);

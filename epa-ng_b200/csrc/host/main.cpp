@@ -28,6 +28,8 @@ void usage()
       "  -m,--model STRING         e.g. GTR{0.7/1.8/1.2/0.6/3.0/1.0}+FU{0.25/0.23/0.30/0.22}+G4{0.47}\n"
       "  -w,--outdir DIR           output directory [./]\n"
       "  -g,--dyn-heur FLOAT       accumulated-LWR preplacement heuristic [0.99999]\n"
+      "  -G,--fix-heur FLOAT       fixed-fraction preplacement heuristic\n"
+      "  --baseball-heur           baseball heuristic (strike box 3, 6 strikes, 40 pitches)\n"
       "  --no-heur                 evaluate every edge thoroughly\n"
       "  --chunk-size INT          queries per device chunk [131072]\n"
       "  --no-pre-mask             do not drop all-gap columns / trim query ranges\n"
@@ -66,6 +68,8 @@ int main(int argc, char ** argv)
     else if (a == "-m" || a == "--model") model = need(i);
     else if (a == "-w" || a == "--outdir") outdir = need(i);
     else if (a == "-g" || a == "--dyn-heur") { opts.prescoring = 1; opts.heuristic = 0; opts.prescoring_threshold = std::atof(need(i)); }
+    else if (a == "-G" || a == "--fix-heur") { opts.prescoring = 1; opts.heuristic = 1; opts.prescoring_threshold = std::atof(need(i)); }
+    else if (a == "--baseball-heur") { opts.prescoring = 1; opts.heuristic = 2; }
     else if (a == "--no-heur") opts.prescoring = 0;
     else if (a == "--chunk-size") chunk = (uint32_t) std::atol(need(i));
     else if (a == "--no-pre-mask") opts.premasking = 0;
@@ -83,7 +87,7 @@ int main(int argc, char ** argv)
       if (v == "on") die("--rate-scalers on: per-rate scalers are not supported by this build (per-site scaling is used)");
     }
     else if (a == "--preserve-rooting") (void) need(i);
-    else if (a == "-G" || a == "--fix-heur" || a == "--baseball-heur" || a == "--raxml-blo" || a == "-b" || a == "--binary" ||
+    else if (a == "--raxml-blo" || a == "-b" || a == "--binary" ||
              a == "-B" || a == "--dump-binary" || a == "-c" || a == "--bfast" || a == "--split")
       die("option " + a + " is outside the accelerated hot path and not supported by this build");
     else die("unknown option " + a);

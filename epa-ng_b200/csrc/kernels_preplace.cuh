@@ -445,10 +445,14 @@ __device__ __forceinline__ bool ranks_before(double v, int i, double pv, int pi)
 }
 
 __global__ void __launch_bounds__(256)
-select_count_kernel(const double * __restrict__ pre, size_t pre_stride, int n_edges, uint32_t nq,
+select_count_kernel(const double * __restrict__ pre, size_t pre_stride, int n_edges, uint32_t nq, int mode,
                     double thresh, uint32_t * __restrict__ cnt, double * __restrict__ cut_v,
                     int * __restrict__ cut_i)
 {
+  // mode 0: dynamic  - accumulated LWR threshold (until_accumulated_reached, set_manipulators.cpp:90-113)
+  // mode 1: fixed    - the best ceil(thresh * edges) (until_top_percent, set_manipulators.cpp:82-88)
+  // mode 2: baseball - everything within 3 log-likelihood units of the best, plus min(40 - hits, 6)
+  //                    more (baseball_heuristic, src/core/heuristics.hpp:74-117)
   const uint32_t q = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (q >= nq) return;
@@ -463,7 +467,10 @@ select_count_kernel(const double * __restrict__ pre, size_t pre_stride, int n_ed
   double pv = INFINITY; int pi = -1;
   double acc = 0.0;
   uint32_t c = 0;
-  while (acc < thresh && c < (uint32_t) n_edges)
+  uint32_t target = (uint32_t) n_edges;            // modes 1, 2: number of candidates to take
+  if (mode == 1) target = min((uint32_t) n_edges, (uint32_t) ceil(thresh * (double) n_edges));
+  bool counting_hits = (mode == 2);
+  while (c < (uint32_t) n_edges && (mode == 0 ? acc < thresh : c < target))
   {
     double bv = -INFINITY; int bi = INT_MAX;
     for (int b = lane; b < n_edges; b += 32)
@@ -479,6 +486,15 @@ select_count_kernel(const double * __restrict__ pre, size_t pre_stride, int n_ed
       if (ranks_before(ov, oi, bv, bi)) { bv = ov; bi = oi; }
     }
     if (bi == INT_MAX) break;                       // nothing left (NaNs)
+    if (counting_hits && bv < mx - 3.0)
+    {
+      // first element outside the strike box: c hits so far, add up to 6 more (at most 40 in all)
+      const uint32_t hits = c;
+      const uint32_t extra = min((uint32_t) 40u - hits, 6u);      // size_t arithmetic of the reference (wraps)
+      target = min((uint32_t) n_edges, hits + extra);
+      counting_hits = false;
+      if (c >= target) break;
+    }
     acc += exp(bv - mx) / tot;
     pv = bv; pi = bi;
     ++c;

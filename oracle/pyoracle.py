@@ -635,6 +635,7 @@ class Options:
     filter_min: int = 1
     filter_max: int = 7
     premasking: bool = True
+    heuristic: int = 0          # 0 dynamic (-g), 1 fixed fraction (-G), 2 baseball
 
 
 @dataclass
@@ -696,6 +697,17 @@ class Placer:
         return pl
 
     def candidates(self, pre: np.ndarray):
+        if self.opts.heuristic == 1:
+            # until_top_percent (set_manipulators.cpp:82-88)
+            keep = int(math.ceil(self.opts.prescoring_threshold * len(pre)))
+            order = sorted(range(len(pre)), key=lambda i: (-pre[i], i))
+            return order[:keep]
+        if self.opts.heuristic == 2:
+            # baseball_heuristic (src/core/heuristics.hpp:74-117)
+            order = sorted(range(len(pre)), key=lambda i: (-pre[i], i))
+            thresh = pre[order[0]] - 3.0
+            hits = next((k for k, i in enumerate(order) if pre[i] < thresh), len(order))
+            return order[:min(len(order), hits + min(40 - hits, 6))]
         lwr = np.zeros_like(pre)
         lib().orc_lwr(_dp(pre), len(pre), _dp(lwr))
         idx = np.zeros(len(pre), dtype=np.int32)

@@ -58,7 +58,9 @@ def main():
     d = os.path.join(HERE, "synth64")
     ds = synth.dataset(T=64, n_sites=300, n_queries=200, window=100)
     tf, sf, qf = synth.write_dataset(ds, d)
-    runs = {"default": run(tf, sf, qf, ds["model"], ())}
+    runs = {"default": run(tf, sf, qf, ds["model"], ()),
+            "fix_heur": run(tf, sf, qf, ds["model"], ("-G", "0.05")),
+            "baseball": run(tf, sf, qf, ds["model"], ("--baseball-heur",))}
     q5 = os.path.join(d, "query5.fasta")
     synth.write_fasta(q5, ds["qnames"][:5], ds["queries"][:5])
     runs["noheur_all_first5"] = run(tf, sf, q5, ds["model"], ("--no-heur", "--filter-min-lwr", "0", "--filter-max", "125"))

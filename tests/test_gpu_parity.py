@@ -175,6 +175,36 @@ def test_synth64_placements_match_reference(synth64, built):
     assert not bad, f"{len(bad)} of {len(gold)} queries differ from the reference: {bad[:3]}"
 
 
+@pytest.mark.parametrize("rname,kw", [("fix_heur", dict(heuristic=1, prescoring_threshold=0.05)),
+                                      ("baseball", dict(heuristic=2))])
+def test_other_heuristics_match_reference(synth64, built, rname, kw):
+    # -G / --baseball-heur: candidate sets against the oracle, placements against the reference
+    case, ctx = synth64
+    o = helpers.oracle()
+    opts = built.capi.default_options(**kw)
+    ctx.upload_queries(case.query_rows)
+    ctx.preplace()
+    ctx.select(opts)
+    q, e, _ = ctx.get_pairs(raw=False)
+    mine = {}
+    for qi, ei in zip(q, e):
+        mine.setdefault(int(qi), set()).add(int(ei))
+    placer = o.Placer(case.ref, o.Options(**{k: v for k, v in kw.items()}))
+    placer.lookup = case.placer.lookup
+    for qi, seq in enumerate(case.qseqs):
+        assert mine[qi] == set(placer.candidates(placer.preplace(seq))), f"{rname}: candidates of query {qi}"
+    gold = helpers.golden("synth64")[rname]["placements"]
+    out, counts = ctx.place_chunk(case.query_rows, opts)
+    got = dict(zip(case.qnames, helpers.records_to_lists(out, counts)))
+    bad = []
+    for name in gold:
+        try:
+            helpers.assert_placements_close(got[name], gold[name], name)
+        except AssertionError as err:
+            bad.append(str(err))
+    assert not bad, f"{rname}: {len(bad)} of {len(gold)} queries differ from the reference: {bad[:3]}"
+
+
 def test_uploaded_clvs_equal_computed(cfg1, built):
     # drop-in for Tree::get_clv: host-owned CLVs (here the oracle's) handed over unchanged
     case, ctx0 = cfg1

@@ -97,3 +97,19 @@ def test_synthaa_matches_reference():
         except AssertionError as e:
             bad.append(str(e))
     assert not bad, f"{len(bad)} of {len(want)} queries differ: {bad[:3]}"
+
+
+@pytest.mark.parametrize("rname,kw", [("fix_heur", dict(heuristic=1, prescoring_threshold=0.05)),
+                                      ("baseball", dict(heuristic=2))])
+def test_synth64_other_heuristics_match_reference(rname, kw):
+    # -G / --baseball-heur (src/core/heuristics.hpp:66-117)
+    gold = helpers.golden("synth64")[rname]["placements"]
+    case = helpers.synth64_case()
+    got = _oracle_run(case, **kw)
+    bad = []
+    for name in gold:
+        try:
+            helpers.assert_placements_close(got[name], gold[name], name)
+        except AssertionError as e:
+            bad.append(str(e))
+    assert not bad, f"{rname}: {len(bad)} of {len(gold)} queries differ: {bad[:3]}"
