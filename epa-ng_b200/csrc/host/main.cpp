@@ -49,7 +49,7 @@ int main(int argc, char ** argv)
   epa_options opts;
   epa_options_default(&opts);
   uint32_t chunk = 0;
-  int precision = 10, device = 0;
+  int precision = 10, device = 0, preserve_rooting = 1;
   std::string invocation;
   for (int i = 0; i < argc; ++i) { invocation += argv[i]; invocation += ' '; }
 
@@ -86,15 +86,15 @@ int main(int argc, char ** argv)
       const std::string v = need(i);
       if (v == "on") die("--rate-scalers on: per-rate scalers are not supported by this build (per-site scaling is used)");
     }
-    else if (a == "--preserve-rooting") (void) need(i);
+    else if (a == "--preserve-rooting") { const std::string v = need(i); preserve_rooting = (v != "off"); }
     else if (a == "--raxml-blo" || a == "-b" || a == "--binary" ||
              a == "-B" || a == "--dump-binary" || a == "-c" || a == "--bfast" || a == "--split")
       die("option " + a + " is outside the accelerated hot path and not supported by this build");
     else die("unknown option " + a);
   }
   if (tree.empty() || ref.empty() || query.empty()) { usage(); die("-t, -s and -q are required"); }
-  const int rc = epa_run_files(tree.c_str(), ref.c_str(), query.c_str(), model.c_str(), outdir.c_str(), &opts, chunk, precision,
-                               device, invocation.c_str());
+  const int rc = epa_run_files_ex(tree.c_str(), ref.c_str(), query.c_str(), model.c_str(), outdir.c_str(), &opts, chunk,
+                                  precision, device, invocation.c_str(), preserve_rooting);
   if (rc) die(epa_host_last_error());
   return 0;
 }

@@ -40,6 +40,7 @@ struct epa_session {
   uint32_t sites = 0;
   std::string newick_cache;
   int newick_precision = -1;
+  bool preserve_rooting = true;    // rooted input: report placements on the rooted tree
   ~epa_session() { if (ctx) epa_ctx_destroy(ctx); }
 };
 
@@ -85,8 +86,8 @@ extern "C" int epa_session_open(epa_session ** out, const char * newick, uint32_
     s->model = Model::parse(model_desc);
     s->sites = sites;
     const size_t T = s->tree.num_tips();
-    if (T != n_taxa)
-      return host_fail(EPA_ERR_ARG, "tree has " + std::to_string(T) + " tips but the reference MSA has " + std::to_string(n_taxa) + " sequences");
+    if (T > n_taxa)
+      return host_fail(EPA_ERR_ARG, "tree has " + std::to_string(T) + " tips but the reference MSA has only " + std::to_string(n_taxa) + " sequences");
     std::unordered_map<std::string, uint32_t> by_name;
     for (uint32_t i = 0; i < n_taxa; ++i) by_name.emplace(names[i], i);
     std::vector<uint32_t> masks(T * (size_t) sites);
@@ -142,7 +143,7 @@ extern "C" const char * epa_session_numbered_newick(epa_session * s, int precisi
   if (!s) return "";
   if (s->newick_precision != precision)
   {
-    s->newick_cache = s->tree.numbered_newick(precision);
+    s->newick_cache = s->tree.numbered_newick(precision, s->preserve_rooting);
     s->newick_precision = precision;
   }
   return s->newick_cache.c_str();
@@ -177,9 +178,32 @@ extern "C" int epa_session_place(epa_session * s, const char * query_rows, uint6
       if (rc == EPA_ERR_QUERY) msg += " (chunk starting at query " + std::to_string(done) + ")";
       return host_fail(rc, msg);
     }
+    if (s->tree.mapper.active && s->preserve_rooting && out && counts)
+    {
+      // rooted input: edge numbers and distal lengths of the rooted tree (rtree_mapper::in_rtree,
+      // applied by the reference when it prints a placement, src/io/jplace_util.cpp:20-32)
+      for (uint32_t q = 0; q < nq; ++q)
+        for (uint32_t k = 0; k < counts[done + q]; ++k)
+        {
+          epa_placement & p = out[(done + q) * opts->filter_max + k];
+          const auto tr = s->tree.mapper.in_rtree((uint32_t) p.branch_id, p.distal_length);
+          p.branch_id = tr.first;
+          p.distal_length = tr.second;
+        }
+    }
   }
   return EPA_OK;
 }
+
+extern "C" int epa_session_set_preserve_rooting(epa_session * s, int on)
+{
+  if (!s) return host_fail(EPA_ERR_ARG, "null argument");
+  s->preserve_rooting = on != 0;
+  s->newick_precision = -1;
+  return EPA_OK;
+}
+
+extern "C" int epa_session_is_rooted(const epa_session * s) { return s && s->tree.mapper.active ? 1 : 0; }
 
 // ----------------------------------------------------------------------------------------------
 //  jplace
@@ -231,6 +255,14 @@ extern "C" int epa_run_files(const char * tree_file, const char * ref_msa_file, 
                              const char * model, const char * outdir, const epa_options * opts, uint32_t chunk_size,
                              int precision, int device, const char * invocation)
 {
+  return epa_run_files_ex(tree_file, ref_msa_file, query_file, model, outdir, opts, chunk_size, precision, device,
+                          invocation, 1);
+}
+
+extern "C" int epa_run_files_ex(const char * tree_file, const char * ref_msa_file, const char * query_file,
+                                const char * model, const char * outdir, const epa_options * opts, uint32_t chunk_size,
+                                int precision, int device, const char * invocation, int preserve_rooting)
+{
   if (!tree_file || !ref_msa_file || !query_file || !model || !outdir || !opts) return host_fail(EPA_ERR_ARG, "null argument");
   try
   {
@@ -274,6 +306,9 @@ extern "C" int epa_run_files(const char * tree_file, const char * ref_msa_file, 
                               reinterpret_cast<const char *>(ref.rows.data()), (uint32_t) ref.sites, model, device);
     if (rc) return rc;
     std::unique_ptr<epa_session> guard(s);
+    epa_session_set_preserve_rooting(s, preserve_rooting);
+    if (epa_session_is_rooted(s))
+      info(preserve_rooting ? "Selected: Preserving the root of the input tree" : "Selected: Unrooting the input tree");
     double tree_logl = 0.0;
     if (epa_session_tree_logl(s, &tree_logl) == EPA_OK)
     {
@@ -334,6 +369,27 @@ extern "C" int epa_host_parse_tree(const char * newick, int precision, char * ou
     }
     if (n_tips) *n_tips = (uint32_t) t.num_tips();
     if (n_edges) *n_edges = (uint32_t) t.num_edges();
+    return EPA_OK;
+  }
+  catch (const std::exception & e) { return host_fail(EPA_ERR_ARG, e.what()); }
+}
+
+extern "C" int epa_host_map_rooted(const char * newick, uint32_t * edges, double * distal, uint32_t count,
+                                   char * out_unrooted_newick, size_t cap)
+{
+  if (!newick) return host_fail(EPA_ERR_ARG, "null argument");
+  try
+  {
+    const Tree t = Tree::parse(newick);
+    if (!t.mapper.active) return host_fail(EPA_ERR_ARG, "the tree is not rooted");
+    for (uint32_t i = 0; i < count; ++i)
+    {
+      if (edges[i] >= t.num_edges()) return host_fail(EPA_ERR_ARG, "edge out of range");
+      const auto tr = t.mapper.in_rtree(edges[i], distal[i]);
+      edges[i] = tr.first;
+      distal[i] = tr.second;
+    }
+    if (out_unrooted_newick && cap) std::snprintf(out_unrooted_newick, cap, "%s", t.numbered_newick(10, false).c_str());
     return EPA_OK;
   }
   catch (const std::exception & e) { return host_fail(EPA_ERR_ARG, e.what()); }

@@ -121,6 +121,39 @@ struct Parser {
 
 }  // namespace
 
+namespace {
+
+// post-order over the file order: numbers the edge above every non-root node, collects the tips
+void number_edges(std::vector<TreeNode> & nodes, int root, std::vector<int> * edge_node, std::vector<int> * tip_node)
+{
+  int next_edge = 0, next_tip = 0;
+  std::vector<std::pair<int, size_t>> stack;
+  stack.emplace_back(root, 0);
+  while (!stack.empty())
+  {
+    auto & [v, k] = stack.back();
+    TreeNode & node = nodes[v];
+    if (k < node.children.size())
+    {
+      const int c = node.children[k++];
+      stack.emplace_back(c, 0);
+      continue;
+    }
+    if (v != root)
+    {
+      if (!node.children.empty() && node.children.size() != 2)
+        throw std::invalid_argument("Input Tree contains multifurcations (polytomies)!");
+      if (node.children.empty()) { node.tip = next_tip++; if (tip_node) tip_node->push_back(v); }
+      node.edge = next_edge++;
+      if (edge_node) edge_node->push_back(v);
+      if (!node.length) node.length = kDefaultBranchLength;     // set_missing_branch_lengths
+    }
+    stack.pop_back();
+  }
+}
+
+}  // namespace
+
 Tree Tree::parse(const std::string & newick)
 {
   Tree t;
@@ -128,38 +161,57 @@ Tree Tree::parse(const std::string & newick)
   t.root = p.parse_tree();
   const size_t top = t.nodes[t.root].children.size();
   if (top == 2)
-    throw std::runtime_error("Treeparsing failed! rooted reference trees (top-level bifurcation) are not supported yet");
-  if (top != 3) throw std::invalid_argument("Input Tree contains multifurcations (polytomies)!");
-  // post-order over the file order, iteratively: (node, next child index)
-  std::vector<std::pair<int, size_t>> stack;
-  stack.emplace_back(t.root, 0);
-  while (!stack.empty())
   {
-    auto & [v, k] = stack.back();
-    TreeNode & node = t.nodes[v];
-    if (k < node.children.size())
-    {
-      const int c = node.children[k++];
-      stack.emplace_back(c, 0);
-      continue;
-    }
-    if (v != t.root)
-    {
-      if (!node.children.empty() && node.children.size() != 2)
-        throw std::invalid_argument("Input Tree contains multifurcations (polytomies)!");
-      if (node.children.empty()) { node.tip = (int) t.tip_node.size(); t.tip_node.push_back(v); }
-      node.edge = (int) t.edge_node.size();
-      t.edge_node.push_back(v);
-      if (!node.length) node.length = kDefaultBranchLength;     // set_missing_branch_lengths
-    }
-    stack.pop_back();
+    // Rooted input. Keep the tree as written (rooted edge numbers for the jplace), then merge the
+    // two root edges: the working tree hangs from the left child of the root if that is an inner
+    // node (children: its two children, then the right subtree across the merged edge), otherwise
+    // from the right child (children: the left tip across the merged edge, then its two children).
+    t.rooted_nodes = t.nodes;
+    t.rooted_root = t.root;
+    number_edges(t.rooted_nodes, t.rooted_root, nullptr, nullptr);
+    const int L = t.nodes[t.root].children[0], R = t.nodes[t.root].children[1];
+    const bool left = !t.nodes[L].children.empty();
+    if (!left && t.nodes[R].children.empty()) throw std::runtime_error("Number of tip nodes too small");
+    const double lenL = t.nodes[L].length, lenR = t.nodes[R].length;
+    const int hub = left ? L : R, far = left ? R : L;
+    TreeNode & h = t.nodes[hub];
+    if (left) h.children.push_back(far);
+    else h.children.insert(h.children.begin(), far);
+    t.nodes[far].parent = hub;
+    t.nodes[far].length = lenL + lenR;
+    h.parent = -1;
+    h.length = 0.0;
+    t.nodes[t.root].children.clear();          // the old root node stays unused
+    t.root = hub;
+    t.mapper.active = true;
+    // the lengths the reference hands to the mapper are the ones in the file (no default applied)
+    t.mapper.distal_length = left ? lenR : lenL;
+    t.mapper.proximal_length = left ? lenL : lenR;
   }
+  else if (top != 3) throw std::invalid_argument("Input Tree contains multifurcations (polytomies)!");
+  number_edges(t.nodes, t.root, &t.edge_node, &t.tip_node);
   if (t.tip_node.size() < 3) throw std::runtime_error("Number of tip nodes too small");
+  if (t.mapper.active)
+  {
+    // working-tree edge -> rooted edge number: both numberings are post-orders of the same
+    // subtrees, the rooted one has one extra edge (the second root edge)
+    const int L = t.rooted_nodes[t.rooted_root].children[0], R = t.rooted_nodes[t.rooted_root].children[1];
+    t.mapper.map.resize(t.edge_node.size());
+    for (size_t e = 0; e < t.edge_node.size(); ++e) t.mapper.map[e] = (uint32_t) t.rooted_nodes[t.edge_node[e]].edge;
+    const bool left = (t.root == L);
+    const int far = left ? R : L;
+    t.mapper.utree_root_edge = (uint32_t) t.nodes[far].edge;
+    t.mapper.distal_edge = (uint32_t) t.rooted_nodes[far].edge;
+    t.mapper.proximal_edge = (uint32_t) t.rooted_nodes[left ? L : R].edge;
+  }
   return t;
 }
 
-std::string Tree::numbered_newick(int precision) const
+std::string Tree::numbered_newick(int precision, bool preserve_rooting) const
 {
+  const bool as_rooted = mapper.active && preserve_rooting;
+  const std::vector<TreeNode> & nodes = as_rooted ? this->rooted_nodes : this->nodes;
+  const int root = as_rooted ? this->rooted_root : this->root;
   std::string out;
   char buf[64];
   // iterative: (node, state) with state = index of the next child to print
@@ -198,14 +250,14 @@ Tree::Schedule Tree::schedule() const
   uint32_t next = T;
   for (size_t v = 0; v < nodes.size(); ++v)
   {
-    if ((int) v == root) continue;
+    if ((int) v == root || nodes[v].edge < 0) continue;       // edge < 0: the detached root of a rooted input
     down[v] = nodes[v].tip >= 0 ? (uint32_t) nodes[v].tip : next++;
     up[v] = next++;
   }
   s.n_slots = next - T;
   for (size_t v = 0; v < nodes.size(); ++v)
   {
-    if ((int) v == root) continue;
+    if ((int) v == root || nodes[v].edge < 0) continue;
     const TreeNode & node = nodes[v];
     if (node.tip < 0)
     {

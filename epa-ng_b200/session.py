@@ -18,9 +18,14 @@ HOST_SYMBOLS = [
     ("epa_session_sites", C.c_uint32, [_vp]),
     ("epa_session_numbered_newick", C.c_char_p, [_vp, C.c_int]),
     ("epa_session_tree_logl", C.c_int, [_vp, C.POINTER(C.c_double)]),
+    ("epa_session_set_preserve_rooting", C.c_int, [_vp, C.c_int]),
+    ("epa_session_is_rooted", C.c_int, [_vp]),
     ("epa_session_close", None, [_vp]),
     ("epa_run_files", C.c_int, [C.c_char_p, C.c_char_p, C.c_char_p, C.c_char_p, C.c_char_p, C.POINTER(capi.Options),
                                 C.c_uint32, C.c_int, C.c_int, C.c_char_p]),
+    ("epa_run_files_ex", C.c_int, [C.c_char_p, C.c_char_p, C.c_char_p, C.c_char_p, C.c_char_p, C.POINTER(capi.Options),
+                                   C.c_uint32, C.c_int, C.c_int, C.c_char_p, C.c_int]),
+    ("epa_host_map_rooted", C.c_int, [C.c_char_p, _u32p, C.POINTER(C.c_double), C.c_uint32, C.c_char_p, C.c_size_t]),
     ("epa_write_jplace", C.c_int, [C.c_char_p, C.c_char_p, C.c_char_p, C.POINTER(C.c_char_p), C.c_uint64, _vp, _u32p,
                                    C.c_uint32, C.c_int]),
     ("epa_host_parse_tree", C.c_int, [C.c_char_p, C.c_int, C.c_char_p, C.c_size_t, _u32p, _u32p]),
@@ -117,10 +122,22 @@ class Session:
 
 
 def run_files(tree_file, ref_msa, query_file, model, outdir, opts=None, chunk_size=0, precision=10, device=0,
-              invocation="epa_run_files"):
+              invocation="epa_run_files", preserve_rooting=True):
     opts = opts or capi.default_options()
-    _check(lib().epa_run_files(tree_file.encode(), ref_msa.encode(), query_file.encode(), model.encode(),
-                               outdir.encode(), C.byref(opts), chunk_size, precision, device, invocation.encode()))
+    _check(lib().epa_run_files_ex(tree_file.encode(), ref_msa.encode(), query_file.encode(), model.encode(),
+                                  outdir.encode(), C.byref(opts), chunk_size, precision, device, invocation.encode(),
+                                  int(preserve_rooting)))
+
+
+def map_rooted(newick: str, edges, distal):
+    """Rooted input: (edge, distal) on the unrooted working tree -> rooted tree; also returns the
+    numbered newick of the working tree."""
+    e = np.ascontiguousarray(edges, dtype=np.uint32).copy()
+    d = np.ascontiguousarray(distal, dtype=np.float64).copy()
+    buf = C.create_string_buffer(8 * len(newick) + 4096)
+    _check(lib().epa_host_map_rooted(newick.encode(), e.ctypes.data_as(_u32p), d.ctypes.data_as(C.POINTER(C.c_double)),
+                                     len(e), buf, len(buf)))
+    return e, d, buf.value.decode()
 
 
 def write_jplace(path, numbered_newick, invocation, names, recs, counts, precision=10):

@@ -43,6 +43,11 @@ epa_ctx * epa_session_ctx(epa_session * session);
 uint32_t epa_session_num_edges(const epa_session * session);
 uint32_t epa_session_num_tips(const epa_session * session);
 uint32_t epa_session_sites(const epa_session * session);
+/* Rooted reference trees are unrooted for the computation (build_tree_from_file,
+ * src/io/file_io.cpp:129-173); by default placements and the jplace tree are reported on the ROOTED
+ * tree (--preserve-rooting on; rtree_mapper, src/core/pll/rtree_mapper.hpp:38-61). */
+int epa_session_set_preserve_rooting(epa_session * session, int on);
+int epa_session_is_rooted(const epa_session * session);
 /* jplace "tree" string: newick with {edge_num} annotations. */
 const char * epa_session_numbered_newick(epa_session * session, int precision);
 /* Reference-tree log-likelihood evaluated across edge 0 (Tree::ref_tree_logl). */
@@ -56,6 +61,11 @@ int epa_run_files(const char * tree_file, const char * ref_msa_file, const char 
                   const char * model, const char * outdir, const epa_options * opts,
                   uint32_t chunk_size, int precision, int device, const char * invocation);
 
+int epa_run_files_ex(const char * tree_file, const char * ref_msa_file, const char * query_file,
+                     const char * model, const char * outdir, const epa_options * opts,
+                     uint32_t chunk_size, int precision, int device, const char * invocation,
+                     int preserve_rooting);
+
 /* Formats placement records as a jplace document (src/io/jplace_util.cpp:20-86) into `path`. */
 int epa_write_jplace(const char * path, const char * numbered_newick, const char * invocation,
                      const char * const * query_names, uint64_t n_queries, const epa_placement * recs,
@@ -65,6 +75,10 @@ int epa_write_jplace(const char * path, const char * numbered_newick, const char
 /* Parses the tree; writes the numbered newick (NUL-terminated, truncated to cap) and the counts. */
 int epa_host_parse_tree(const char * newick, int precision, char * out_newick, size_t cap,
                         uint32_t * n_tips, uint32_t * n_edges);
+/* Rooted input only: translates (edge, distal length) pairs of the unrooted working tree to the
+ * rooted tree, in place; writes the numbered newick of the working tree when out_newick != NULL. */
+int epa_host_map_rooted(const char * newick, uint32_t * edges, double * distal, uint32_t count,
+                        char * out_unrooted_newick, size_t cap);
 /* Pruning schedule and edge list that epa_session_open hands to the device API; tip_labels
  * receives the tip names separated by '\n' in tip-id order. Capacities are in elements. */
 int epa_host_tree_schedule(const char * newick, uint32_t * n_slots, epa_clv_op * ops, uint32_t ops_cap,

@@ -54,6 +54,18 @@ def main():
         runs[mname + "_acc"] = run(t, s, q, model, ("--filter-acc-lwr", "0.999", "--filter-max", "5"))
     json.dump(runs, open(os.path.join(cfg1, "reference_placements.json"), "w"), indent=1)
 
+    # rooted input trees of the reference's test data (6 of the 8 taxa): placements and tree string
+    # on the ROOTED tree (default --preserve-rooting on) and on the unrooted one (off)
+    rooted = {}
+    for f in ("ref_rooted.tre", "ref_rooted_2.tre", "ref_rooted_3.tre", "ref_rooted_innerlabels.tre"):
+        shutil.copy(os.path.join(REF_DATA, f), os.path.join(cfg1, f))
+        tr = os.path.join(cfg1, f)
+        model = "GTR{0.5/0.5/0.5/0.5/0.5/1.0}+FU{0.25/0.25/0.25/0.25}+G4{1.0}"
+        rooted[f] = {"default": run(tr, s, q, model, ()),
+                     "noheur_all": run(tr, s, q, model, ("--no-heur", "--filter-min-lwr", "0", "--filter-max", "10")),
+                     "unrooted": run(tr, s, q, model, ("--preserve-rooting", "off"))}
+    json.dump(rooted, open(os.path.join(cfg1, "reference_rooted.json"), "w"), indent=1)
+
     synth = ge.load_package().synth
     d = os.path.join(HERE, "synth64")
     ds = synth.dataset(T=64, n_sites=300, n_queries=200, window=100)

@@ -86,3 +86,22 @@ def test_session_chunking_is_invisible(built):
         want = gold[case.qnames[qi]][0]
         assert best[0] == want[0] and abs(best[1] - want[1]) <= 1e-6 * abs(want[1])
     sess.close()
+
+
+@pytest.mark.parametrize("fname", ["ref_rooted.tre", "ref_rooted_2.tre", "ref_rooted_3.tre", "ref_rooted_innerlabels.tre"])
+def test_rooted_trees_match_reference(built, tmp_path, fname):
+    """Rooted reference trees: unrooted for the computation, reported on the rooted tree
+    (file_io.cpp:129-173, rtree_mapper.hpp:38-61); the MSA holds two taxa the tree does not."""
+    d = os.path.join(helpers.GOLDEN, "cfg1")
+    gold = json.load(open(os.path.join(d, "reference_rooted.json")))[fname]
+    capi = built.capi
+    runs = {"default": (capi.default_options(), True),
+            "noheur_all": (capi.default_options(prescoring=0, support_threshold=0.0, filter_max=10), True),
+            "unrooted": (capi.default_options(), False)}
+    for rname, (opts, preserve) in runs.items():
+        out = str(tmp_path / rname)
+        built.session.run_files(os.path.join(d, fname), os.path.join(d, "aln.fasta"), os.path.join(d, "query.fasta"),
+                                helpers.GTRG, out, opts=opts, preserve_rooting=preserve)
+        got, doc = _read_jplace(os.path.join(out, "epa_result.jplace"))
+        assert doc["tree"] == gold[rname]["tree"], rname
+        _check(got, gold[rname]["placements"], f"{fname}/{rname}")

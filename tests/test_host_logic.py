@@ -29,7 +29,7 @@ def test_numbered_newick_matches_reference(sess):
 
 
 def test_tree_errors(sess, built):
-    for bad in ["(A:1,B:1);", "((A:1,B:1):1,(C:1,D:1):1);", "(A:1,B:1,(C:1,D:1,E:1):1);", "(A:1,B:1,C:1", "A;"]:
+    for bad in ["(A:1,B:1);", "(A:1,B:1,(C:1,D:1,E:1):1);", "(A:1,B:1,C:1", "A;", "((A:1,B:1,C:1):1,D:1);"]:
         with pytest.raises(built.capi.EpaError):
             sess.parse_tree(bad)
     # missing / zero lengths fall back to -ln(0.9) (set_missing_branch_lengths)
@@ -121,3 +121,30 @@ def test_schedule_reproduces_oracle_clvs(sess):
         if od.clv is not None:
             assert np.allclose(sides[d].clv, od.clv, rtol=1e-12, atol=0)
         assert np.allclose(sides[p].clv, op_.clv, rtol=1e-12, atol=0)
+
+
+ROOTED = ["ref_rooted.tre", "ref_rooted_2.tre", "ref_rooted_3.tre", "ref_rooted_innerlabels.tre"]
+
+
+@pytest.mark.parametrize("fname", ROOTED)
+def test_rooted_numbered_newick_matches_reference(sess, fname):
+    gold = __import__("json").load(open(os.path.join(helpers.GOLDEN, "cfg1", "reference_rooted.json")))[fname]
+    text = _read("cfg1", fname)
+    nwk, nt, ne = sess.parse_tree(text)
+    assert (nt, ne) == (6, 9)                      # the working tree is unrooted: 2T - 3 edges
+    assert nwk == gold["default"]["tree"]           # rooted tree, rooted edge numbers (10 of them)
+    _, _, unrooted = sess.map_rooted(text, [0], [0.0])
+    assert unrooted == gold["unrooted"]["tree"]     # --preserve-rooting off
+
+
+def test_rtree_mapper_goldens(sess):
+    """The reference's own known-answer vectors, test/src/rtree_mapper.cpp:58-102."""
+    cases = {
+        "ref_rooted.tre": ([(8, 1.0), (8, 1.5), (6, 0.5), (7, 0.001)], [(9, 1.0), (6, 0.63), (7, 0.5), (8, 0.001)]),
+        "ref_rooted_2.tre": ([(0, 1.34), (0, 1.345), (8, 0.5), (2, 0.001)], [(0, 1.34), (9, 0.005), (8, 0.5), (2, 0.001)]),
+        "ref_rooted_3.tre": ([(8, 0.5), (8, 0.005), (0, 0.5), (2, 0.001)], [(8, 1.41), (9, 0.005), (0, 0.5), (2, 0.001)]),
+    }
+    for fname, (u, r) in cases.items():
+        e, d, _ = sess.map_rooted(_read("cfg1", fname), [x[0] for x in u], [x[1] for x in u])
+        assert [int(x) for x in e] == [x[0] for x in r], fname
+        assert np.allclose(d, [x[1] for x in r], atol=1e-10), fname
