@@ -16,6 +16,7 @@
 #include "kernels_clv.cuh"
 #include "kernels_preplace.cuh"
 #include "kernels_blo.cuh"
+#include "kernels_blo_site.cuh"
 #include "kernels_blo_generic.cuh"
 #include "kernels_collect.cuh"
 
@@ -69,6 +70,8 @@ struct epa_ctx {
   EdgeDev * d_edges = nullptr;
   double * d_lookup = nullptr;
   double * d_pairtab = nullptr;    // DNA pair-sum tables [edge][n_pad/2][PAIR_ROW]
+  double * d_clvT = nullptr;       // DNA: site-blocked CLV copy read by the lane = site BLO kernel
+  bool clvT_ready = false;
   bool clvs_ready = false, lookup_ready = false;
   std::vector<uint8_t> slot_filled;
 
@@ -239,7 +242,7 @@ extern "C" void epa_ctx_destroy(epa_ctx * ctx)
                      &ctx->scratch, &ctx->tmp};
   for (DevBuf * b : bufs) b->release();
   cudaFree(ctx->d_model); cudaFree(ctx->tree.clv); cudaFree(ctx->tree.scaler); cudaFree(ctx->d_edges);
-  cudaFree(ctx->d_lookup); cudaFree(ctx->d_pairtab); cudaFree(ctx->d_flags); cudaFree(ctx->d_counter); cudaFree(ctx->d_total);
+  cudaFree(ctx->d_lookup); cudaFree(ctx->d_pairtab); cudaFree(ctx->d_clvT); cudaFree(ctx->d_flags); cudaFree(ctx->d_counter); cudaFree(ctx->d_total);
   for (auto & e : ctx->ev) if (e) cudaEventDestroy(e);
   if (ctx->stream && ctx->own_stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
@@ -469,6 +472,7 @@ extern "C" int epa_compute_clvs(epa_ctx * ctx, const epa_clv_op * ops, uint32_t 
     }
     ranges.emplace_back(start, (uint32_t) hops.size() - start);
   }
+  ctx->clvT_ready = false;
   if (hops.empty()) { ctx->clvs_ready = true; return EPA_OK; }
 
   const size_t pm = (size_t) ctx->R * ctx->S * ctx->S;
@@ -517,6 +521,7 @@ extern "C" int epa_upload_clvs(epa_ctx * ctx, const epa_host_clv * clvs, uint32_
   CU(cudaStreamSynchronize(ctx->stream));
   ctx->clvs_ready = true;
   ctx->lookup_ready = false;
+  ctx->clvT_ready = false;
   return EPA_OK;
 }
 
@@ -898,6 +903,59 @@ extern "C" int epa_select(epa_ctx * ctx, const epa_options * opts, uint64_t * n_
 }
 
 namespace {
+// site-blocked CLV copy for the lane = site kernel (derived data, rebuilt when the CLVs change)
+int ensure_clvT(epa_ctx * ctx)
+{
+  if (ctx->clvT_ready) return EPA_OK;
+  const int C = ctx->R * 4;
+  const size_t t_stride = clvt_node_stride(ctx->n, ctx->R);
+  if (!ctx->d_clvT) CU(cudaMalloc(&ctx->d_clvT, (size_t) ctx->n_nodes * t_stride * sizeof(double)));
+  dim3 grid((ctx->n + CLVT_BLOCK - 1) / CLVT_BLOCK, ctx->n_nodes);
+  clv_site_block_kernel<<<grid, 256, (size_t) CLVT_BLOCK * (C + 1) * sizeof(double), ctx->stream>>>(
+      ctx->tree.clv, ctx->tree.clv_stride, ctx->n, C, ctx->d_clvT, t_stride);
+  LAUNCHED(ctx);
+  ctx->clvT_ready = true;
+  return EPA_OK;
+}
+
+// R = 1, 2, 4: lane = site kernel (kernels_blo_site.cuh)
+template <int R>
+int launch_blo_site(epa_ctx * ctx, BloArgs & a)
+{
+  if (int rc = ensure_clvT(ctx)) return rc;
+  BloSiteArgs sa{};
+  sa.clvT = ctx->d_clvT; sa.t_stride = clvt_node_stride(ctx->n, ctx->R);
+  const int wmax = std::max(1, ctx->max_span);
+  const size_t per_warp = SiteWarpSmem<R>::doubles(wmax) * sizeof(double);
+  const size_t budget = ctx->smem_optin - 2048;
+  int warps = (int) std::min<size_t>(9, budget / per_warp);      // __launch_bounds__(288, 1)
+  if (warps >= 2)
+  {
+    a.wcap = wmax;
+    sa.b = a;
+    const size_t smem = per_warp * warps;
+    uint64_t grid = (uint64_t) ctx->sm_count;
+    grid = std::min<uint64_t>(grid, (a.n_pairs + warps - 1) / warps);
+    CU(cudaFuncSetAttribute(blo_site_kernel<R, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+    blo_site_kernel<R, false><<<(unsigned) grid, warps * 32, smem, ctx->stream>>>(sa);
+  }
+  else
+  {
+    warps = 8;
+    const unsigned grid = (unsigned) std::min<uint64_t>((uint64_t) ctx->sm_count, (a.n_pairs + warps - 1) / warps);
+    sa.wpad = (wmax + 31) & ~31;
+    CU(ctx->scratch.ensure((size_t) grid * warps * sa.wpad * blo_row(R) * sizeof(double)));
+    sa.gscratch = ctx->scratch.as<double>();
+    a.wcap = 0;
+    sa.b = a;
+    const size_t smem = SiteWarpSmem<R>::doubles(0) * sizeof(double) * warps;
+    CU(cudaFuncSetAttribute(blo_site_kernel<R, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+    blo_site_kernel<R, true><<<grid, warps * 32, smem, ctx->stream>>>(sa);
+  }
+  LAUNCHED(ctx);
+  return EPA_OK;
+}
+
 template <int R>
 int launch_blo_dna(epa_ctx * ctx, BloArgs & a)
 {
@@ -958,9 +1016,9 @@ extern "C" int epa_place_pairs(epa_ctx * ctx, const epa_options * opts)
     {
       switch (ctx->R)
       {
-        case 1: rc = launch_blo_dna<1>(ctx, a); break;
-        case 2: rc = launch_blo_dna<2>(ctx, a); break;
-        case 4: rc = launch_blo_dna<4>(ctx, a); break;
+        case 1: rc = launch_blo_site<1>(ctx, a); break;
+        case 2: rc = launch_blo_site<2>(ctx, a); break;
+        case 4: rc = launch_blo_site<4>(ctx, a); break;
         case 8: rc = launch_blo_dna<8>(ctx, a); break;
         default: return fail(ctx, EPA_ERR_ARG, "unsupported rate category count %d", ctx->R);
       }

@@ -1,0 +1,532 @@
+// kernels_blo_site.cuh - HOT LOOP B, lane = site formulation of the DNA branch-length optimisation.
+//
+// Same reference behaviour as kernels_blo.cuh (Tiny_Tree::place src/tree/Tiny_Tree.cpp:131-218,
+// opt_branch_lengths_pplacer src/core/pll/optimize.cpp:60-248, Newton-Raphson
+// PM/optimize/opt_algorithms.c:86-262, sumtable/derivatives LP/core_derivatives.c:321-858, CLV update
+// LP/core_partials.c:202-352,612-766, edge log-likelihood LP/core_likelihood.c:351-578), one warp per
+// (query, edge) pair, but EVERY phase maps one lane to one site:
+//   * the CLV passes read a site-blocked copy of the reference CLVs, clvT[node][site/32][r*4+k][32],
+//     so that the 32 lanes of a warp (32 consecutive sites, any alignment) read 256 contiguous bytes
+//     per component: coalesced, no lane owns less than a whole site, hence no cross-lane rate sums,
+//     no ballots for the scaling test, one logarithm per site;
+//   * the sumtable row of a site is written and read by the same lane (shared memory, odd row
+//     length = conflict-free), so passes and Newton iterations need no warp synchronisation;
+//   * transition matrices are read as warp-uniform 128-bit shared-memory broadcasts; the per-mask
+//     tip vectors use a skewed row (4R + 2 doubles) that keeps the A/C/G/T/N rows in disjoint banks;
+//   * the 3R decay factors of a Newton evaluation are computed by 3R lanes and broadcast through
+//     shared memory (no shuffles).
+#pragma once
+#include "kernels_blo.cuh"
+
+namespace epa {
+
+constexpr int CLVT_BLOCK = 32;      // sites per block of the site-blocked CLV copy
+
+__host__ __device__ inline size_t clvt_node_stride(int n, int R)
+{
+  return (size_t) ((n + CLVT_BLOCK - 1) / CLVT_BLOCK) * (size_t) (R * 4) * CLVT_BLOCK;
+}
+
+// clv[node][site][c] -> clvT[node][site/32][c][site%32]; pad sites read as zero. C = R * 4.
+// grid = (site blocks, nodes), block = 256 threads, dynamic smem = 32 * (C + 1) doubles.
+__global__ void __launch_bounds__(256)
+clv_site_block_kernel(const double * __restrict__ clv, size_t clv_stride, int n, int C,
+                      double * __restrict__ clvT, size_t t_stride)
+{
+  extern __shared__ double tile[];                 // [32][C + 1]
+  const int blk = blockIdx.x;
+  const size_t node = blockIdx.y;
+  const double * src = clv + node * clv_stride + (size_t) blk * CLVT_BLOCK * C;
+  double * dst = clvT + node * t_stride + (size_t) blk * CLVT_BLOCK * C;
+  const int total = CLVT_BLOCK * C;
+  const int valid = min(CLVT_BLOCK, n - blk * CLVT_BLOCK) * C;
+  for (int i = threadIdx.x; i < total; i += blockDim.x)
+    tile[(i / C) * (C + 1) + (i % C)] = i < valid ? src[i] : 0.0;
+  __syncthreads();
+  for (int i = threadIdx.x; i < total; i += blockDim.x)
+    dst[i] = tile[(i % CLVT_BLOCK) * (C + 1) + (i / CLVT_BLOCK)];
+}
+
+template <int R>
+struct SiteWarpSmem {
+  static constexpr int C = 4 * R;
+  static constexpr int P_D = 0;                     // [r][i][j]
+  static constexpr int P_P = 16 * R;
+  static constexpr int P_E = 32 * R;
+  static constexpr int TVS = C + 2;                 // tip-vector row: [r][i] + 2 doubles of skew
+  static constexpr int TV = 48 * R;                 // [16 mask positions][TVS]
+  static constexpr int EX = TV + 16 * TVS;          // [3][3R] decay tables / [4R] expm1 scratch
+  static constexpr int EXN = (9 * R > 4 * R ? 9 * R : 4 * R);
+  static constexpr int SUM = (EX + EXN + 1) & ~1;   // [w][blo_row(R)]
+  __host__ __device__ static constexpr size_t doubles(int wcap)
+  {
+    return (((size_t) SUM + (size_t) wcap * blo_row(R)) + 1) & ~(size_t) 1;
+  }
+};
+
+struct SiteCtaSmem {
+  double V[16], Vinv[16];
+  __align__(16) double tipleft[64];     // [tv_pos(mask)][j] = sum_{k in mask} pi_k Vinv[k][j]
+  unsigned long long q_next, q_end;
+  int q_lock;
+};
+
+struct BloSiteArgs {
+  BloArgs b;
+  const double * clvT;                  // site-blocked CLV copy
+  size_t t_stride;                      // doubles per node in clvT
+  double * gscratch;                    // global sumtable scratch [warp][blo_row][wpad] (GS variant)
+  int wpad;                             // padded window capacity of the global scratch
+};
+
+// P[r][i][j] = delta_ij + sum_k Vinv[i][k] expm1(lambda_k rate_r t) V[k][j]   (LP/core_pmatrix.c:185-249)
+template <int R>
+__device__ __forceinline__ void site_pmatrix(const SiteCtaSmem & cs, double t, double * P, double * ex, int lane)
+{
+  for (int idx = lane; idx < R * 4; idx += 32)
+    ex[idx] = expm1(c_model.eigenvals[idx & 3] * c_model.rates[idx >> 2] * t);
+  __syncwarp();
+  for (int idx = lane; idx < R * 16; idx += 32)
+  {
+    const int r = idx >> 4, i = (idx >> 2) & 3, j = idx & 3;
+    double acc = (i == j) ? 1.0 : 0.0;
+    #pragma unroll
+    for (int k = 0; k < 4; ++k) acc += (cs.Vinv[i * 4 + k] * ex[r * 4 + k]) * cs.V[k * 4 + j];
+    P[idx] = acc;
+  }
+  __syncwarp();
+}
+
+// tv[pos(mask)][r*4+i] = sum_{j in mask} P[r][i][j]
+template <int R>
+__device__ __forceinline__ void site_tipvec(const double * P, double * tv, int lane)
+{
+  for (int idx = lane; idx < R * 64; idx += 32)
+  {
+    const int mask = idx / (4 * R), ri = idx % (4 * R);
+    double acc = 0.0;
+    #pragma unroll
+    for (int j = 0; j < 4; ++j)
+      if ((mask >> j) & 1) acc += P[ri * 4 + j];
+    tv[tv_pos(mask) * SiteWarpSmem<R>::TVS + ri] = acc;
+  }
+  __syncwarp();
+}
+
+template <int N>
+__device__ __forceinline__ void lds_vec(const double * p, double (&v)[N])
+{
+  const double2 * p2 = reinterpret_cast<const double2 *>(p);
+  #pragma unroll
+  for (int i = 0; i < N / 2; ++i) { const double2 t = p2[i]; v[2 * i] = t.x; v[2 * i + 1] = t.y; }
+}
+
+// element offset of (window-relative site s, component 0) inside a node of the site-blocked copy
+template <int R>
+__device__ __forceinline__ size_t clvt_offset(int abs_site)
+{
+  return (size_t) (abs_site >> 5) * (size_t) (R * 4 * CLVT_BLOCK) + (size_t) (abs_site & 31);
+}
+
+// derivative sums over the window, lane = site (LP/core_derivatives.c:643-858)
+template <int R, bool GS>
+__device__ __forceinline__ void site_derivatives(const double * sum, int gstride, double * ex, int w, double t,
+                                                 int lane, double & f, double & df)
+{
+  constexpr int NK = 3 * R, ROW = blo_row(R);
+  if (lane < NK)
+  {
+    const double lk = c_model.eigenvals[1 + lane % 3] * c_model.rates[lane / 3];
+    const double e = exp(lk * t) * c_model.weights[lane / 3];
+    const double e1 = lk * e;
+    ex[lane] = e; ex[NK + lane] = e1; ex[2 * NK + lane] = lk * e1;
+  }
+  __syncwarp();
+  double d0[NK], d1[NK], d2[NK];
+  if constexpr ((NK % 2) == 0)
+  {
+    lds_vec<NK>(ex, d0); lds_vec<NK>(ex + NK, d1); lds_vec<NK>(ex + 2 * NK, d2);
+  }
+  else
+  {
+    #pragma unroll
+    for (int k = 0; k < NK; ++k) { d0[k] = ex[k]; d1[k] = ex[NK + k]; d2[k] = ex[2 * NK + k]; }
+  }
+  double a1 = 0.0, a2 = 0.0;
+  #pragma unroll 4
+  for (int s = lane; s < w; s += 32)
+  {
+    double c0, c1 = 0.0, c2 = 0.0;
+    if constexpr (GS)
+    {
+      c0 = sum[s];
+      #pragma unroll
+      for (int k = 0; k < NK; ++k)
+      {
+        const double x = sum[(size_t) (k + 1) * gstride + s];
+        c0 += x * d0[k]; c1 += x * d1[k]; c2 += x * d2[k];
+      }
+    }
+    else
+    {
+      const double * row = sum + s * ROW;
+      c0 = row[0];
+      #pragma unroll
+      for (int k = 0; k < NK; ++k)
+      {
+        const double x = row[k + 1];
+        c0 += x * d0[k]; c1 += x * d1[k]; c2 += x * d2[k];
+      }
+    }
+    const double inv = 1.0 / c0;
+    const double g1 = -c1 * inv;
+    a1 += g1;
+    a2 += g1 * g1 - c2 * inv;
+  }
+  f = warp_sum(a1);
+  df = warp_sum(a2);
+}
+
+// bounded Newton-Raphson, PM/optimize/opt_algorithms.c:133-262; returns 0.0 on failure
+template <int R, bool GS>
+__device__ __forceinline__ double site_newton(const double * sum, int gstride, double * ex, int w, int lane,
+                                              double xmin, double xguess, double xmax, double tol)
+{
+  double x = fmax(fmin(xguess, xmax), xmin);
+  double xl = xmin, xh = xmax;
+  const double dxmax = xmax / EPA_NR_MAX_ITERS;
+  int iter = 0;
+  for (;;)
+  {
+    if (iter++ > EPA_NR_MAX_ITERS) return 0.0;
+    double f, df;
+    site_derivatives<R, GS>(sum, gstride, ex, w, x, lane, f, df);
+    if (!isfinite(f) || !isfinite(df)) return 0.0;
+    double dx;
+    if (df > 0.0)
+    {
+      if (fabs(f) < tol) return x;
+      if (f < 0.0) xl = x; else xh = x;
+      dx = -1.0 * f / df;
+    }
+    else
+      dx = -1.0 * f / fabs(df);
+    dx = fmax(fmin(dx, dxmax), -dxmax);
+    if (x + dx < xl) dx = xl - x;
+    if (x + dx > xh) dx = xh - x;
+    if (fabs(dx) < tol) return x;
+    x += dx;
+    x = fmax(fmin(x, xmax), xmin);
+  }
+}
+
+// stores one finished sumtable row: st[r][j], j = 0 is the stationary component
+template <int R, bool GS>
+__device__ __forceinline__ void site_store_row(double * sum, int gstride, int s, double base, const double (&st)[3 * R])
+{
+  if constexpr (GS)
+  {
+    sum[s] = base;
+    #pragma unroll
+    for (int k = 0; k < 3 * R; ++k) sum[(size_t) (k + 1) * gstride + s] = st[k];
+  }
+  else
+  {
+    double * row = sum + s * blo_row(R);
+    row[0] = base;
+    #pragma unroll
+    for (int k = 0; k < 3 * R; ++k) row[k + 1] = st[k];
+  }
+}
+
+// Pass A: inner CLV toward the new tip from (D, X); returns the edge log-likelihood new_tip | inner
+// over the window and leaves the pendant sumtable (inner vs tip) in `sum`.
+template <int R, bool GS>
+__device__ __forceinline__ double site_pass_tip(const SiteCtaSmem & cs, const double * ws, double * sum, int gstride,
+                                             const double * __restrict__ DT, const double * __restrict__ XT,
+                                             const uint32_t * __restrict__ sD, const uint32_t * __restrict__ sX,
+                                             const uint8_t * __restrict__ qc, int begin, int w, int lane)
+{
+  using L = SiteWarpSmem<R>;
+  double acc = 0.0;
+  #pragma unroll 1
+  for (int s = lane; s < w; s += 32)
+  {
+    const size_t off = clvt_offset<R>(begin + s);
+    const double * dp = DT + off;
+    const double * xp = XT + off;
+    double dv[4 * R], xv[4 * R];
+    #pragma unroll
+    for (int c = 0; c < 4 * R; ++c) { dv[c] = __ldg(dp + (size_t) c * CLVT_BLOCK); xv[c] = __ldg(xp + (size_t) c * CLVT_BLOCK); }
+    const int mask = qc[s] & 15;
+    const int pos = tv_pos(mask);
+    uint32_t scal = __ldg(sD + s) + __ldg(sX + s);
+    double in[4 * R];
+    bool small = true;
+    #pragma unroll
+    for (int r = 0; r < R; ++r)
+    {
+      #pragma unroll
+      for (int i = 0; i < 4; ++i)
+      {
+        double pd[4], pp[4];
+        lds_vec<4>(ws + L::P_D + r * 16 + i * 4, pd);
+        lds_vec<4>(ws + L::P_P + r * 16 + i * 4, pp);
+        const double ta = pd[0] * dv[r * 4] + pd[1] * dv[r * 4 + 1] + pd[2] * dv[r * 4 + 2] + pd[3] * dv[r * 4 + 3];
+        const double tb = pp[0] * xv[r * 4] + pp[1] * xv[r * 4 + 1] + pp[2] * xv[r * 4 + 2] + pp[3] * xv[r * 4 + 3];
+        in[r * 4 + i] = ta * tb;
+        small = small && (in[r * 4 + i] < EPA_SCALE_THRESHOLD);
+      }
+    }
+    if (small)
+    {
+      #pragma unroll
+      for (int c = 0; c < 4 * R; ++c) in[c] *= EPA_SCALE_FACTOR;
+      scal += 1;
+    }
+    double tl[4];
+    lds_vec<4>(cs.tipleft + pos * 4, tl);
+    const double * tvp = ws + L::TV + pos * L::TVS;
+    double term = 0.0, base = 0.0;
+    double st[3 * R];
+    #pragma unroll
+    for (int r = 0; r < R; ++r)
+    {
+      double tp[4];
+      lds_vec<4>(tvp + r * 4, tp);
+      const double tr = (in[r * 4] * c_model.freqs[0]) * tp[0] + (in[r * 4 + 1] * c_model.freqs[1]) * tp[1]
+                      + (in[r * 4 + 2] * c_model.freqs[2]) * tp[2] + (in[r * 4 + 3] * c_model.freqs[3]) * tp[3];
+      term += tr * c_model.weights[r];
+      // pendant sumtable: tip side takes pi*Vinv (tipleft), inner side takes V
+      #pragma unroll
+      for (int j = 0; j < 4; ++j)
+      {
+        const double right = c_model.eigenvecs[j * 4] * in[r * 4] + c_model.eigenvecs[j * 4 + 1] * in[r * 4 + 1]
+                           + c_model.eigenvecs[j * 4 + 2] * in[r * 4 + 2] + c_model.eigenvecs[j * 4 + 3] * in[r * 4 + 3];
+        const double v = tl[j] * right;
+        if (j == 0) base += v * c_model.weights[r];
+        else st[r * 3 + j - 1] = v;
+      }
+    }
+    site_store_row<R, GS>(sum, gstride, s, base, st);
+    acc += log(term) + (scal ? (double) scal * EPA_LOG_SCALE_THRESHOLD : 0.0);
+  }
+  return warp_sum(acc);
+}
+
+// Pass B: inner CLV toward the distal node from (T, X); leaves the distal sumtable (D vs inner)
+template <int R, bool GS>
+__device__ __forceinline__ void site_pass_distal(const double * ws, double * sum, int gstride,
+                                              const double * __restrict__ DT, const double * __restrict__ XT,
+                                              const uint8_t * __restrict__ qc, int begin, int w, int lane)
+{
+  using L = SiteWarpSmem<R>;
+  #pragma unroll 1
+  for (int s = lane; s < w; s += 32)
+  {
+    const size_t off = clvt_offset<R>(begin + s);
+    const double * dp = DT + off;
+    const double * xp = XT + off;
+    double dv[4 * R], xv[4 * R];
+    #pragma unroll
+    for (int c = 0; c < 4 * R; ++c) { dv[c] = __ldg(dp + (size_t) c * CLVT_BLOCK); xv[c] = __ldg(xp + (size_t) c * CLVT_BLOCK); }
+    const int pos = tv_pos(qc[s] & 15);
+    const double * tvp = ws + L::TV + pos * L::TVS;
+    double in[4 * R];
+    bool small = true;
+    #pragma unroll
+    for (int r = 0; r < R; ++r)
+    {
+      double tp[4];
+      lds_vec<4>(tvp + r * 4, tp);
+      #pragma unroll
+      for (int i = 0; i < 4; ++i)
+      {
+        double pp[4];
+        lds_vec<4>(ws + L::P_P + r * 16 + i * 4, pp);
+        const double tb = pp[0] * xv[r * 4] + pp[1] * xv[r * 4 + 1] + pp[2] * xv[r * 4 + 2] + pp[3] * xv[r * 4 + 3];
+        in[r * 4 + i] = tp[i] * tb;
+        small = small && (in[r * 4 + i] < EPA_SCALE_THRESHOLD);
+      }
+    }
+    if (small)
+    {
+      #pragma unroll
+      for (int c = 0; c < 4 * R; ++c) in[c] *= EPA_SCALE_FACTOR;
+    }
+    double base = 0.0;
+    double st[3 * R];
+    #pragma unroll
+    for (int r = 0; r < R; ++r)
+    {
+      #pragma unroll
+      for (int j = 0; j < 4; ++j)
+      {
+        const double left = dv[r * 4] * c_model.pivinv[j] + dv[r * 4 + 1] * c_model.pivinv[4 + j]
+                          + dv[r * 4 + 2] * c_model.pivinv[8 + j] + dv[r * 4 + 3] * c_model.pivinv[12 + j];
+        const double right = c_model.eigenvecs[j * 4] * in[r * 4] + c_model.eigenvecs[j * 4 + 1] * in[r * 4 + 1]
+                           + c_model.eigenvecs[j * 4 + 2] * in[r * 4 + 2] + c_model.eigenvecs[j * 4 + 3] * in[r * 4 + 3];
+        const double v = left * right;
+        if (j == 0) base += v * c_model.weights[r];
+        else st[r * 3 + j - 1] = v;
+      }
+    }
+    site_store_row<R, GS>(sum, gstride, s, base, st);
+  }
+}
+
+__device__ __forceinline__ unsigned long long site_next_item(SiteCtaSmem & cs, unsigned long long * counter)
+{
+  while (atomicCAS(&cs.q_lock, 0, 1) != 0) { }
+  __threadfence_block();
+  volatile unsigned long long * qn = &cs.q_next;
+  volatile unsigned long long * qe = &cs.q_end;
+  if (*qn == *qe)
+  {
+    const unsigned long long base = atomicAdd(counter, (unsigned long long) EPA_WORK_BLOCK);
+    *qn = base;
+    *qe = base + EPA_WORK_BLOCK;
+  }
+  const unsigned long long item = *qn;
+  *qn = item + 1;
+  __threadfence_block();
+  atomicExch(&cs.q_lock, 0);
+  return item;
+}
+
+// GS = sumtable in global scratch (windows that do not fit the shared-memory slice)
+template <int R, bool GS>
+__global__ void __launch_bounds__(288, 1)
+blo_site_kernel(BloSiteArgs sa)
+{
+  using L = SiteWarpSmem<R>;
+  const BloArgs & a = sa.b;
+  extern __shared__ __align__(16) double smem_d[];
+  __shared__ SiteCtaSmem cs;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int n_warps = blockDim.x >> 5;
+  for (int i = threadIdx.x; i < 16; i += blockDim.x)
+  {
+    cs.V[i] = c_model.eigenvecs[i];
+    cs.Vinv[i] = c_model.inv_eigenvecs[i];
+  }
+  for (int i = threadIdx.x; i < 64; i += blockDim.x)
+  {
+    const int mask = i >> 2, j = i & 3;
+    double acc = 0.0;
+    for (int k = 0; k < 4; ++k)
+      if ((mask >> k) & 1) acc += c_model.pivinv[k * 4 + j];
+    cs.tipleft[tv_pos(mask) * 4 + j] = acc;
+  }
+  if (threadIdx.x == 0) { cs.q_next = 0; cs.q_end = 0; cs.q_lock = 0; }
+  __syncthreads();
+
+  const size_t per_warp = L::doubles(GS ? 0 : a.wcap);
+  double * ws = smem_d + (size_t) warp * per_warp;
+  const int gstride = GS ? sa.wpad : 0;
+  double * sum = GS ? sa.gscratch + ((size_t) blockIdx.x * n_warps + warp) * (size_t) sa.wpad * blo_row(R)
+                    : ws + L::SUM;
+  double * ex = ws + L::EX;
+
+  for (;;)
+  {
+    unsigned long long item = 0;
+    if (lane == 0) item = site_next_item(cs, a.counter);
+    item = __shfl_sync(0xffffffffu, item, 0);
+    if (item >= a.n_pairs) break;
+    uint32_t pid, q, e;
+    if (a.pair_q)
+    {
+      pid = a.work ? a.work[item] : (uint32_t) item;
+      q = a.pair_q[pid];
+      e = a.pair_e[pid];
+    }
+    else
+    {
+      e = (uint32_t) (item / a.nq);
+      q = a.perm ? a.perm[item % a.nq] : (uint32_t) (item % a.nq);
+      pid = q * a.n_edges + e;
+    }
+    const EdgeDev ed = a.edges[e];
+    const int begin = a.begin[q], w = a.span[q];
+    if (w <= 0 || (!GS && w > a.wcap) || (GS && w > sa.wpad))
+    {
+      if (lane == 0) a.out[pid] = BloResult{NAN, NAN, NAN};
+      continue;
+    }
+    const int n = a.n;
+    const double * DT = sa.clvT + (size_t) ed.distal * sa.t_stride;
+    const double * XT = sa.clvT + (size_t) ed.proximal * sa.t_stride;
+    const uint32_t * sD = a.tree.scaler + (size_t) ed.distal * n + begin;
+    const uint32_t * sX = a.tree.scaler + (size_t) ed.proximal * n + begin;
+    const uint8_t * qc = a.codes + (size_t) q * n + begin;
+
+    // optimize_branch_triplet / opt_branch_lengths_pplacer as half rounds (see kernels_blo.cuh)
+    const double orig = ed.length;
+    double len[3] = {orig / 2.0, orig / 2.0, EPA_DEFAULT_PENDANT};      // distal, proximal, pendant
+    const double original_length = len[0] * 2;
+    double old_d = len[0], old_e = len[2], loglikelihood = 0.0;
+    int smoothings = EPA_SMOOTHINGS;
+    unsigned rebuild = 7u;
+    bool first = true, distal_phase = false;
+    for (;;)
+    {
+      #pragma unroll 1
+      for (int mi = 0; mi < 3; ++mi)
+        if (rebuild & (1u << mi))
+        {
+          const double t = mi == 0 ? len[0] : (mi == 1 ? len[1] : len[2]);
+          site_pmatrix<R>(cs, t, ws + mi * (R * 16), ex, lane);
+          if (mi == 2) site_tipvec<R>(ws + L::P_E, ws + L::TV, lane);
+        }
+      rebuild = 0u;
+      double xmin, xmax, xguess;
+      if (!distal_phase)
+      {
+        const double new_logl = -site_pass_tip<R, GS>(cs, ws, sum, gstride, DT, XT, sD, sX, qc, begin, w, lane);
+        if (first) { loglikelihood = new_logl; first = false; }
+        else
+        {
+          if (new_logl - loglikelihood > new_logl * 1e-14)
+          {
+            len[2] = old_e; len[0] = old_d; len[1] = original_length - old_d;   // worse: restore and stop
+            break;
+          }
+          --smoothings;
+          if (fabs(new_logl - loglikelihood) < EPA_BLO_EPSILON) smoothings = 0;
+          loglikelihood = new_logl;
+        }
+        if (!smoothings) break;
+        old_d = len[0]; old_e = len[2];
+        xmin = EPA_MIN_BRLEN; xmax = EPA_MAX_BRLEN; xguess = len[2];
+        if (xguess < xmin || xguess > xmax) xguess = EPA_DEFAULT_BRLEN;
+      }
+      else
+      {
+        site_pass_distal<R, GS>(ws, sum, gstride, DT, XT, qc, begin, w, lane);
+        xmin = fmin(EPA_MIN_BRLEN / 2.0, original_length / 2.0);
+        xmax = original_length - xmin / 10.0;
+        xguess = len[0];
+        if (xguess < xmin || xguess > xmax) xguess = original_length / 2.0;
+      }
+      const double xres = site_newton<R, GS>(sum, gstride, ex, w, lane, xmin, xguess, xmax, xmin / 10.0);
+      if (xres > 0.0)
+      {
+        if (!distal_phase) { len[2] = xres; rebuild = 4u; }
+        else { len[0] = xres; len[1] = original_length - xres; rebuild = 3u; }
+      }
+      distal_phase = !distal_phase;
+    }
+    if (lane == 0)
+    {
+      BloResult res;
+      res.logl = -loglikelihood;
+      res.distal = (orig / (len[0] + len[1])) * len[0];      // Tiny_Tree.cpp:183-185
+      res.pendant = len[2];
+      a.out[pid] = res;
+    }
+    __syncwarp();
+  }
+}
+
+}  // namespace epa

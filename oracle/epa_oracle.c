@@ -462,9 +462,13 @@ void orc_sumtable(const orc_model_t * m, int n, const orc_side_t * parent,
   }
 }
 
+/* diagnostic counter (tools/blo_stats.py): derivative evaluations since the last reset */
+unsigned long long orc_stat_deriv_calls = 0;
+
 void orc_derivatives(const orc_model_t * m, int n, const double * sumtable, double t,
                      double * df, double * ddf)
 {
+  ++orc_stat_deriv_calls;
   /* core_derivatives.c:643-694 (site kernel), :757-772 (diagptable), :844-847 (accumulate) */
   const int S = m->states, R = m->rate_cats, span = S * R;
   double diag[ORC_MAX_RATES * ORC_MAX_STATES][3];
