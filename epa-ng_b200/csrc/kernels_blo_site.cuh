@@ -128,6 +128,19 @@ __device__ __forceinline__ size_t clvt_offset(int abs_site)
   return (size_t) (abs_site >> 5) * (size_t) (R * 4 * CLVT_BLOCK) + (size_t) (abs_site & 31);
 }
 
+// 1/x for positive normal x (a site likelihood): hardware seed + two Newton steps, no slow-path
+// branch, so that the compiler can interleave the reciprocals of several sites. Within 1 ulp.
+__device__ __forceinline__ double fast_rcp(double x)
+{
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+  double e = fma(-x, r, 1.0);
+  e = fma(e, e, e);
+  r = fma(r, e, r);
+  e = fma(-x, r, 1.0);
+  return fma(r, e, r);
+}
+
 // derivative sums over the window, lane = site (LP/core_derivatives.c:643-858)
 template <int R, bool GS>
 __device__ __forceinline__ void site_derivatives(const double * sum, int gstride, double * ex, int w, double t,
@@ -152,36 +165,60 @@ __device__ __forceinline__ void site_derivatives(const double * sum, int gstride
     #pragma unroll
     for (int k = 0; k < NK; ++k) { d0[k] = ex[k]; d1[k] = ex[NK + k]; d2[k] = ex[2 * NK + k]; }
   }
+  // Trips of 32 sites are taken two at a time (sites s and s + 32 of a lane): six independent FMA
+  // chains and two branch-free reciprocals in flight; an odd last trip runs alone. A lane whose
+  // site lies beyond the window re-reads its first row and discards the result.
   double a1 = 0.0, a2 = 0.0;
-  #pragma unroll 4
-  for (int s = lane; s < w; s += 32)
+  const int trips = (w + 31) >> 5;
+  const int s0 = lane < w ? lane : 0;
+  auto load_row = [&](int s, double (&x)[NK + 1])
   {
-    double c0, c1 = 0.0, c2 = 0.0;
     if constexpr (GS)
     {
-      c0 = sum[s];
       #pragma unroll
-      for (int k = 0; k < NK; ++k)
-      {
-        const double x = sum[(size_t) (k + 1) * gstride + s];
-        c0 += x * d0[k]; c1 += x * d1[k]; c2 += x * d2[k];
-      }
+      for (int k = 0; k <= NK; ++k) x[k] = sum[(size_t) k * gstride + s];
     }
     else
     {
       const double * row = sum + s * ROW;
-      c0 = row[0];
       #pragma unroll
-      for (int k = 0; k < NK; ++k)
-      {
-        const double x = row[k + 1];
-        c0 += x * d0[k]; c1 += x * d1[k]; c2 += x * d2[k];
-      }
+      for (int k = 0; k <= NK; ++k) x[k] = row[k];
     }
-    const double inv = 1.0 / c0;
-    const double g1 = -c1 * inv;
-    a1 += g1;
-    a2 += g1 * g1 - c2 * inv;
+  };
+  int tr = 0;
+  #pragma unroll 1
+  for (; tr + 2 <= trips; tr += 2)
+  {
+    const int sa = lane + 32 * tr, sb = sa + 32;
+    const bool va = sa < w, vb = sb < w;
+    double xa[NK + 1], xb[NK + 1];
+    load_row(va ? sa : s0, xa);
+    load_row(vb ? sb : s0, xb);
+    double c0a = xa[0], c1a = 0.0, c2a = 0.0, c0b = xb[0], c1b = 0.0, c2b = 0.0;
+    #pragma unroll
+    for (int k = 0; k < NK; ++k)
+    {
+      c0a += xa[k + 1] * d0[k]; c1a += xa[k + 1] * d1[k]; c2a += xa[k + 1] * d2[k];
+      c0b += xb[k + 1] * d0[k]; c1b += xb[k + 1] * d1[k]; c2b += xb[k + 1] * d2[k];
+    }
+    const double ia = fast_rcp(c0a), ib = fast_rcp(c0b);
+    const double g1a = -c1a * ia, g1b = -c1b * ib;
+    const double ha = g1a * g1a - c2a * ia, hb = g1b * g1b - c2b * ib;
+    if (va) { a1 += g1a; a2 += ha; }
+    if (vb) { a1 += g1b; a2 += hb; }
+  }
+  if (tr < trips)
+  {
+    const int sa = lane + 32 * tr;
+    const bool va = sa < w;
+    double xa[NK + 1];
+    load_row(va ? sa : s0, xa);
+    double c0a = xa[0], c1a = 0.0, c2a = 0.0;
+    #pragma unroll
+    for (int k = 0; k < NK; ++k) { c0a += xa[k + 1] * d0[k]; c1a += xa[k + 1] * d1[k]; c2a += xa[k + 1] * d2[k]; }
+    const double ia = fast_rcp(c0a);
+    const double g1a = -c1a * ia;
+    if (va) { a1 += g1a; a2 += g1a * g1a - c2a * ia; }
   }
   f = warp_sum(a1);
   df = warp_sum(a2);
@@ -248,7 +285,11 @@ __device__ __forceinline__ double site_pass_tip(const SiteCtaSmem & cs, const do
                                              const uint8_t * __restrict__ qc, int begin, int w, int lane)
 {
   using L = SiteWarpSmem<R>;
-  double acc = 0.0;
+  // The window log-likelihood is a sum of per-site logarithms. A lane multiplies the mantissas of
+  // its sites' likelihoods (each in [0.5, 1)) and adds their exponents as integers, so that one
+  // logarithm per 16 sites of a lane replaces one per site.
+  double acc = 0.0, prod = 1.0;
+  int esum = 0, ssum = 0, since = 0;
   #pragma unroll 1
   for (int s = lane; s < w; s += 32)
   {
@@ -309,8 +350,22 @@ __device__ __forceinline__ double site_pass_tip(const SiteCtaSmem & cs, const do
       }
     }
     site_store_row<R, GS>(sum, gstride, s, base, st);
-    acc += log(term) + (scal ? (double) scal * EPA_LOG_SCALE_THRESHOLD : 0.0);
+    ssum += (int) scal;
+    const int hi = __double2hiint(term);
+    const int ef = (hi >> 20) & 0x7ff;
+    if (hi > 0 && ef != 0 && ef != 0x7ff)
+    {
+      prod *= __hiloint2double((hi & 0x800fffff) | 0x3fe00000, __double2loint(term));
+      esum += ef - 1022;
+    }
+    else
+      acc += log(term);                     // zero, denormal, negative or non-finite: plain path
+    if (++since == 16)
+    {
+      acc += log(prod); prod = 1.0; since = 0;
+    }
   }
+  acc += log(prod) + (double) esum * 0.693147180559945309417 + (double) ssum * EPA_LOG_SCALE_THRESHOLD;
   return warp_sum(acc);
 }
 

@@ -34,11 +34,11 @@ for (f, l), v in sorted(per_line.items(), key=lambda kv: -kv[1])[:70]:
 if len(sys.argv) > 2:
     regs = [tuple(map(int, a.split("-"))) for a in sys.argv[2:]]
     for lo, hi in regs:
-        v = sum(x for (f, l), x in per_line.items() if f == "kernels_blo.cuh" and lo <= l <= hi)
+        v = sum(x for (f, l), x in per_line.items() if f == "kernels_blo_site.cuh" and lo <= l <= hi)
         print("lines %d-%d: %.2f%%" % (lo, hi, v / tot * 100))
-    v = sum(x for (f, l), x in per_line.items() if f != "kernels_blo.cuh")
+    v = sum(x for (f, l), x in per_line.items() if f != "kernels_blo_site.cuh")
     print("other files: %.2f%%" % (v / tot * 100))
     by = collections.Counter()
     for (f, l), x in per_line.items():
-        if f != "kernels_blo.cuh": by[f] += x
+        if f != "kernels_blo_site.cuh": by[f] += x
     print({k: "%.2f%%" % (v / tot * 100) for k, v in by.items()})
