@@ -15,6 +15,7 @@
 #include "common.cuh"
 #include "kernels_clv.cuh"
 #include "kernels_preplace.cuh"
+#include "kernels_preplace_mma.cuh"
 #include "kernels_blo.cuh"
 #include "kernels_blo_site.cuh"
 #include "kernels_blo_generic.cuh"
@@ -70,6 +71,9 @@ struct epa_ctx {
   EdgeDev * d_edges = nullptr;
   double * d_lookup = nullptr;
   double * d_pairtab = nullptr;    // DNA pair-sum tables [edge][n_pad/2][PAIR_ROW]
+  uint8_t * d_btab = nullptr;      // DNA: fixed-point digit table of the tensor-core preplacement
+  double * d_pn = nullptr;         // DNA: prefix sums of the fully-ambiguous lookup column [edge][n + 1]
+  bool mma_ok = false;             // every table entry fits the fixed-point format
   double * d_clvT = nullptr;       // DNA: site-blocked CLV copy read by the lane = site BLO kernel
   bool clvT_ready = false;
   bool clvs_ready = false, lookup_ready = false;
@@ -242,7 +246,7 @@ extern "C" void epa_ctx_destroy(epa_ctx * ctx)
                      &ctx->scratch, &ctx->tmp};
   for (DevBuf * b : bufs) b->release();
   cudaFree(ctx->d_model); cudaFree(ctx->tree.clv); cudaFree(ctx->tree.scaler); cudaFree(ctx->d_edges);
-  cudaFree(ctx->d_lookup); cudaFree(ctx->d_pairtab); cudaFree(ctx->d_clvT); cudaFree(ctx->d_flags); cudaFree(ctx->d_counter); cudaFree(ctx->d_total);
+  cudaFree(ctx->d_lookup); cudaFree(ctx->d_pairtab); cudaFree(ctx->d_clvT); cudaFree(ctx->d_btab); cudaFree(ctx->d_pn); cudaFree(ctx->d_flags); cudaFree(ctx->d_counter); cudaFree(ctx->d_total);
   for (auto & e : ctx->ev) if (e) cudaEventDestroy(e);
   if (ctx->stream && ctx->own_stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
@@ -617,6 +621,23 @@ extern "C" int epa_build_lookup(epa_ctx * ctx)
     if (!ctx->d_pairtab) CU(cudaMalloc(&ctx->d_pairtab, pair_doubles * sizeof(double)));
     pairtab_build_kernel<<<(unsigned) ((pair_doubles + 255) / 256), 256, 0, ctx->stream>>>(ctx->d_lookup, ctx->n_pad, B, ctx->d_pairtab);
     LAUNCHED(ctx);
+    // fixed-point digit table + prefix sums of the tensor-core preplacement (kernels_preplace_mma.cuh)
+    const int kc_total = mma_kc_total(n);
+    const uint32_t n_eb = (B + MMA_EB - 1) / MMA_EB;
+    const size_t btab_bytes = (size_t) n_eb * kc_total * MMA_B_CHUNK_BYTES;
+    if (!ctx->d_btab) CU(cudaMalloc(&ctx->d_btab, btab_bytes));
+    if (!ctx->d_pn) CU(cudaMalloc(&ctx->d_pn, (size_t) B * (n + 1) * sizeof(double)));
+    CU(cudaMemsetAsync(ctx->d_btab, 0, btab_bytes, ctx->stream));
+    CU(cudaMemsetAsync(ctx->d_flags + 6, 0, sizeof(int), ctx->stream));
+    const size_t tthreads = (size_t) B * ((n + 3) / 4);
+    mma_table_kernel<<<(unsigned) ((tthreads + 255) / 256), 256, 0, ctx->stream>>>(ctx->d_lookup, n, ctx->n_pad, B, kc_total, ctx->d_btab, ctx->d_flags + 6);
+    LAUNCHED(ctx);
+    mma_prefix_kernel<<<(B + 7) / 8, 256, 0, ctx->stream>>>(ctx->d_lookup, n, ctx->n_pad, B, ctx->d_pn);
+    LAUNCHED(ctx);
+    int bad = 1;
+    CU(cudaMemcpyAsync(&bad, ctx->d_flags + 6, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    ctx->mma_ok = (bad == 0) && !getenv("EPA_B200_NO_MMA");
   }
   CU(cudaStreamSynchronize(ctx->stream));
   ctx->lookup_ready = true;
@@ -772,6 +793,23 @@ int launch_preplace_pair(epa_ctx * ctx, uint32_t count, const int2 * range, int 
   LAUNCHED(ctx);
   return EPA_OK;
 }
+
+// DNA tensor-core kernel over perm[0, count): tiles of MMA_TQ queries, persistent CTAs
+int launch_preplace_mma(epa_ctx * ctx, uint32_t count, const int2 * range)
+{
+  PreMmaArgs a{};
+  a.btab = ctx->d_btab; a.pn = ctx->d_pn; a.kc_total = mma_kc_total(ctx->n); a.n = ctx->n;
+  a.n_edges = ctx->n_edges; a.n_eb = (ctx->n_edges + MMA_EB - 1) / MMA_EB;
+  a.codes = ctx->codes.as<uint8_t>(); a.begin = ctx->begin.as<int>(); a.span = ctx->span.as<int>();
+  a.perm = ctx->perm.as<uint32_t>(); a.nq = count; a.range = range;
+  a.n_tiles = (count + MMA_TQ - 1) / MMA_TQ;
+  a.pre = ctx->pre.as<double>(); a.pre_stride = ctx->pre_stride;
+  CU(cudaFuncSetAttribute(preplace_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) MMA_SMEM_BYTES));
+  const unsigned grid = (unsigned) std::min<uint32_t>((uint32_t) ctx->sm_count, a.n_tiles);
+  preplace_mma_kernel<<<grid, MMA_THREADS, MMA_SMEM_BYTES, ctx->stream>>>(a);
+  LAUNCHED(ctx);
+  return EPA_OK;
+}
 }  // namespace
 
 extern "C" int epa_preplace(epa_ctx * ctx)
@@ -785,14 +823,28 @@ extern "C" int epa_preplace(epa_ctx * ctx)
   if (nq == 0) { ctx->stage = ST_PREPLACED; return EPA_OK; }
   CU(ctx->pre.ensure((size_t) nq * ctx->pre_stride * sizeof(double)));
   CU(cudaEventRecord(ctx->ev[1], ctx->stream));
-  // simple DNA queries (sorted first) take the pair-table kernel, the rest the per-site kernel
+  // simple DNA queries (sorted first) take the tensor-core kernel (tile windows of at most
+  // MMA_KC_MAX * 4 sites) or else the pair-table kernel; the rest take the per-site kernel
   const uint32_t nA = ctx->d_pairtab ? ctx->n_simple : 0u, nB = nq - nA;
+  const uint32_t tilesM = (nA + MMA_TQ - 1) / MMA_TQ;
   const uint32_t tilesA = (nA + kPairTQ - 1) / kPairTQ, tilesB = (nB + kPreplaceTQ - 1) / kPreplaceTQ;
-  CU(ctx->range.ensure((size_t) (tilesA + tilesB) * sizeof(int2)));
-  CU(cudaMemsetAsync(ctx->d_flags + 2, 0, sizeof(int), ctx->stream));
-  CU(cudaMemsetAsync(ctx->d_flags + 5, 0, sizeof(int), ctx->stream));
-  if (nA)
+  CU(ctx->range.ensure((size_t) (std::max(tilesA, tilesM) + tilesB) * sizeof(int2)));
+  int2 * rangeB = ctx->range.as<int2>() + std::max(tilesA, tilesM);
+  bool use_mma = ctx->mma_ok && nA > 0 && ctx->max_span <= MMA_KC_MAX * 4;
+  int flags[8];
+  if (use_mma)
   {
+    CU(cudaMemsetAsync(ctx->d_flags + 2, 0, sizeof(int), ctx->stream));
+    tile_range_kernel<<<(tilesM + 7) / 8, 256, 0, ctx->stream>>>(ctx->perm.as<uint32_t>(), ctx->begin.as<int>(), ctx->span.as<int>(),
+                                                              nA, MMA_TQ, tilesM, 4, ctx->range.as<int2>(), ctx->d_flags + 2);
+    LAUNCHED(ctx);
+    if (int rc = read_flags(ctx, flags)) return rc;
+    use_mma = flags[2] <= MMA_KC_MAX * 4;
+  }
+  CU(cudaMemsetAsync(ctx->d_flags + 5, 0, sizeof(int), ctx->stream));
+  if (nA && !use_mma)
+  {
+    CU(cudaMemsetAsync(ctx->d_flags + 2, 0, sizeof(int), ctx->stream));
     tile_range_kernel<<<(tilesA + 7) / 8, 256, 0, ctx->stream>>>(ctx->perm.as<uint32_t>(), ctx->begin.as<int>(), ctx->span.as<int>(),
                                                               nA, kPairTQ, tilesA, 8, ctx->range.as<int2>(), ctx->d_flags + 2);
     LAUNCHED(ctx);
@@ -800,18 +852,22 @@ extern "C" int epa_preplace(epa_ctx * ctx)
   if (nB)
   {
     tile_range_kernel<<<(tilesB + 7) / 8, 256, 0, ctx->stream>>>(ctx->perm.as<uint32_t>() + nA, ctx->begin.as<int>(), ctx->span.as<int>(),
-                                                              nB, kPreplaceTQ, tilesB, 4, ctx->range.as<int2>() + tilesA, ctx->d_flags + 5);
+                                                              nB, kPreplaceTQ, tilesB, 4, rangeB, ctx->d_flags + 5);
     LAUNCHED(ctx);
   }
-  int flags[8];
-  if (int rc = read_flags(ctx, flags)) return rc;
-  if (nA)
+  if ((nA && !use_mma) || nB)
+    if (int rc = read_flags(ctx, flags)) return rc;
+  if (nA && use_mma)
+  {
+    if (int rc = launch_preplace_mma(ctx, nA, ctx->range.as<int2>())) return rc;
+  }
+  else if (nA)
     if (int rc = launch_preplace_pair(ctx, nA, ctx->range.as<int2>(), std::max(8, flags[2]))) return rc;
   if (nB)
   {
     const int maxw = std::max(4, flags[5]);
-    const int rc = (ctx->K == 16) ? launch_preplace<16>(ctx, nA, nB, ctx->range.as<int2>() + tilesA, maxw)
-                                  : launch_preplace<26>(ctx, nA, nB, ctx->range.as<int2>() + tilesA, maxw);
+    const int rc = (ctx->K == 16) ? launch_preplace<16>(ctx, nA, nB, rangeB, maxw)
+                                  : launch_preplace<26>(ctx, nA, nB, rangeB, maxw);
     if (rc) return rc;
   }
   CU(cudaEventRecord(ctx->ev[2], ctx->stream));

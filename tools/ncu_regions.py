@@ -35,7 +35,8 @@ if len(sys.argv) > 2:
     regs = [tuple(map(int, a.split("-"))) for a in sys.argv[2:]]
     for lo, hi in regs:
         v = sum(x for (f, l), x in per_line.items() if f == "kernels_blo_site.cuh" and lo <= l <= hi)
-        print("lines %d-%d: %.2f%%" % (lo, hi, v / tot * 100))
+        vs = sum(x for (f, l), x in per_line_s.items() if f == "kernels_blo_site.cuh" and lo <= l <= hi)
+        print("lines %d-%d: inst %.2f%% samples %.2f%%" % (lo, hi, v / tot * 100, vs / ts * 100))
     v = sum(x for (f, l), x in per_line.items() if f != "kernels_blo_site.cuh")
     print("other files: %.2f%%" % (v / tot * 100))
     by = collections.Counter()
