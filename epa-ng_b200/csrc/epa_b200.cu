@@ -626,13 +626,15 @@ extern "C" int epa_build_lookup(epa_ctx * ctx)
     const uint32_t n_eb = (B + MMA_EB - 1) / MMA_EB;
     const size_t btab_bytes = (size_t) n_eb * kc_total * MMA_B_CHUNK_BYTES;
     if (!ctx->d_btab) CU(cudaMalloc(&ctx->d_btab, btab_bytes));
-    if (!ctx->d_pn) CU(cudaMalloc(&ctx->d_pn, (size_t) B * (n + 1) * sizeof(double)));
+    const uint32_t e_pad = n_eb * MMA_EB;
+    if (!ctx->d_pn) CU(cudaMalloc(&ctx->d_pn, (size_t) e_pad * (n + 1) * sizeof(double)));
+    CU(cudaMemsetAsync(ctx->d_pn, 0, (size_t) e_pad * (n + 1) * sizeof(double), ctx->stream));
     CU(cudaMemsetAsync(ctx->d_btab, 0, btab_bytes, ctx->stream));
     CU(cudaMemsetAsync(ctx->d_flags + 6, 0, sizeof(int), ctx->stream));
     const size_t tthreads = (size_t) B * ((n + 3) / 4);
     mma_table_kernel<<<(unsigned) ((tthreads + 255) / 256), 256, 0, ctx->stream>>>(ctx->d_lookup, n, ctx->n_pad, B, kc_total, ctx->d_btab, ctx->d_flags + 6);
     LAUNCHED(ctx);
-    mma_prefix_kernel<<<(B + 7) / 8, 256, 0, ctx->stream>>>(ctx->d_lookup, n, ctx->n_pad, B, ctx->d_pn);
+    mma_prefix_kernel<<<(B + 7) / 8, 256, 0, ctx->stream>>>(ctx->d_lookup, n, ctx->n_pad, B, e_pad, ctx->d_pn);
     LAUNCHED(ctx);
     int bad = 1;
     CU(cudaMemcpyAsync(&bad, ctx->d_flags + 6, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));

@@ -40,7 +40,7 @@ constexpr int MMA_KC_STAGE = 8;                   // 16-byte K chunks (4 sites e
 constexpr int MMA_STAGES = 4;
 constexpr int MMA_KC_MAX = 56;                    // A tile: at most 224 sites
 constexpr int MMA_FRAC = 38;                      // fraction bits of the fixed-point delta
-constexpr int MMA_THREADS = 192;
+constexpr int MMA_THREADS = 320;                  // producer warp, MMA warp, 2 x 4 epilogue warps
 constexpr uint32_t MMA_A_CHUNK_BYTES = MMA_TQ * 16;                       // 2048
 constexpr uint32_t MMA_B_CHUNK_BYTES = MMA_N * 16;                        // 3072
 constexpr uint32_t MMA_B_STAGE_BYTES = MMA_KC_STAGE * MMA_B_CHUNK_BYTES;  // 24576
@@ -87,15 +87,17 @@ mma_table_kernel(const double * __restrict__ lookup, int n, int n_pad, uint32_t 
   for (int p = 0; p < MMA_P; ++p) dst[p] = make_uint4(w[p][0], w[p][1], w[p][2], w[p][3]);
 }
 
-// pn[e][s] = sum_{s' < s} lookup[e][s'][N], s = 0..n. One warp per edge (sequential over 32-site
-// groups, fixed order).
+// pn[s][e] = sum_{s' < s} lookup[e][s'][N], s = 0..n, rows of e_pad doubles (site-major: the 16
+// branches an epilogue thread needs for one site are 128 contiguous bytes). One warp per edge
+// (sequential over 32-site groups, fixed order).
 __global__ void __launch_bounds__(256)
-mma_prefix_kernel(const double * __restrict__ lookup, int n, int n_pad, uint32_t n_edges, double * __restrict__ pn)
+mma_prefix_kernel(const double * __restrict__ lookup, int n, int n_pad, uint32_t n_edges, uint32_t e_pad,
+                  double * __restrict__ pn)
 {
   const uint32_t e = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (e >= n_edges) return;
-  double * out = pn + (size_t) e * (n + 1);
+  double * out = pn + e;
   double run = 0.0;
   if (lane == 0) out[0] = 0.0;
   for (int base = 0; base < n; base += 32)
@@ -108,7 +110,7 @@ mma_prefix_kernel(const double * __restrict__ lookup, int n, int n_pad, uint32_t
       const double y = __shfl_up_sync(0xffffffffu, x, o);
       if (lane >= o) x += y;
     }
-    if (s < n) out[s + 1] = run + x;
+    if (s < n) out[(size_t) (s + 1) * e_pad] = run + x;
     run += __shfl_sync(0xffffffffu, x, 31);
   }
 }
@@ -160,7 +162,7 @@ __device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sy
 
 struct PreMmaArgs {
   const uint8_t * btab;        // [n_eb][kc_total][192][16]
-  const double * pn;           // [n_edges][n + 1]
+  const double * pn;           // [n + 1][n_eb * 32] prefix sums of the N column, site-major
   int kc_total, n;
   uint32_t n_edges, n_eb;
   const uint8_t * codes;       // [nq][n] state masks
@@ -196,7 +198,7 @@ preplace_mma_kernel(PreMmaArgs a)
   if (tid == 0)
   {
     for (int s = 0; s < MMA_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(&tfull[s], 1); mbar_init(&tempty[s], 4); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&tfull[s], 1); mbar_init(&tempty[s], 8); }
     mbar_fence_init();
   }
   if (warp == 1)
@@ -306,53 +308,74 @@ preplace_mma_kernel(PreMmaArgs a)
     }
     else
     {
-      // ===== epilogue: thread = query row =====
+      // ===== epilogue: thread = query row; warps 2-5 take branches 0-15 of a block, warps 6-9
+      // branches 16-31 =====
       const int quarter = warp & 3;                       // TMEM lanes this warp may read
+      const int half = (warp - 2) >> 2;
       const int r = quarter * 32 + lane;
       const uint32_t q = row_q[r];
-      const int pb = row_b[r], pe = row_e[r];
-      double * out = a.pre + (size_t) (q == 0xffffffffu ? 0u : q) * a.pre_stride;
+      const size_t e_pad = (size_t) a.n_eb * MMA_EB;
+      const double2 * __restrict__ pnb = reinterpret_cast<const double2 *>(a.pn + (size_t) row_b[r] * e_pad + half * 16);
+      const double2 * __restrict__ pne = reinterpret_cast<const double2 *>(a.pn + (size_t) row_e[r] * e_pad + half * 16);
+      double * out = a.pre + (size_t) (q == 0xffffffffu ? 0u : q) * a.pre_stride + half * 16;
       uint32_t bi = blk_it;
+      // prefix-sum term of the block's 16 branches, loaded one block ahead
+      double base[16];
+      #pragma unroll
+      for (int j = 0; j < 8; ++j)
+      {
+        const double2 hi = __ldg(pne + j), lo2 = __ldg(pnb + j);
+        base[2 * j] = hi.x - lo2.x; base[2 * j + 1] = hi.y - lo2.y;
+      }
       for (uint32_t eb = 0; eb < a.n_eb; ++eb, ++bi)
       {
         const uint32_t acc = bi & 1u, use_acc = bi >> 1;
+        const uint32_t taddr = tmem_base + ((uint32_t) (quarter * 32) << 16) + acc * 256u + half * 96;
+        double cur[16];
+        #pragma unroll
+        for (int j = 0; j < 16; ++j) cur[j] = base[j];
+        if (eb + 1 < a.n_eb)
+        {
+          #pragma unroll
+          for (int j = 0; j < 8; ++j)
+          {
+            const double2 hi = __ldg(pne + (size_t) (eb + 1) * 16 + j), lo2 = __ldg(pnb + (size_t) (eb + 1) * 16 + j);
+            base[2 * j] = hi.x - lo2.x; base[2 * j + 1] = hi.y - lo2.y;
+          }
+        }
         mbar_wait(&tfull[acc], use_acc & 1u);
         tc_fence_after();
-        const uint32_t taddr = tmem_base + ((uint32_t) (quarter * 32) << 16) + acc * 256u;
-        #pragma unroll 1
-        for (int half = 0; half < 2; ++half)
+        uint32_t v0[32], v1[32], v2[32];
+        tc_ld32(taddr, v0);
+        tc_ld32(taddr + 32, v1);
+        tc_ld32(taddr + 64, v2);
+        tc_wait_ld();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tempty[acc]);          // accumulator values are in registers
+        const uint32_t e0 = eb * MMA_EB + half * 16;
+        #pragma unroll
+        for (int j = 0; j < 16; j += 2)
         {
-          uint32_t v0[32], v1[32], v2[32];
-          tc_ld32(taddr + half * 96, v0);
-          tc_ld32(taddr + half * 96 + 32, v1);
-          tc_ld32(taddr + half * 96 + 64, v2);
-          tc_wait_ld();
-          if (half == 1)
-          {
-            // both halves are in registers or consumed: hand the accumulator back
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&tempty[acc]);
-          }
-          const uint32_t e0 = eb * MMA_EB + half * 16;
+          double res[2];
           #pragma unroll
-          for (int j = 0; j < 16; ++j)
+          for (int jj = 0; jj < 2; ++jj)
           {
             unsigned long long sum = 0;
             #pragma unroll
             for (int p = 0; p < MMA_P; ++p)
             {
-              const int c = j * MMA_P + p;
+              const int c = (j + jj) * MMA_P + p;
               const uint32_t d = c < 32 ? v0[c] : (c < 64 ? v1[c - 32] : v2[c - 64]);
               sum += (unsigned long long) d << (8 * p);
             }
-            const uint32_t e = e0 + j;
-            if (q != 0xffffffffu && e < a.n_edges)
-            {
-              const double * pn = a.pn + (size_t) e * (a.n + 1);
-              const double base = __ldg(pn + pe) - __ldg(pn + pb);
-              out[e] = base - (double) sum * (1.0 / (double) (1ull << MMA_FRAC));
-            }
+            res[jj] = cur[j + jj] - (double) sum * (1.0 / (double) (1ull << MMA_FRAC));
+          }
+          if (q != 0xffffffffu)
+          {
+            double * dst = out + (size_t) eb * MMA_EB + j;
+            if (e0 + j + 1 < a.n_edges) *reinterpret_cast<double2 *>(dst) = make_double2(res[0], res[1]);
+            else if (e0 + j < a.n_edges) dst[0] = res[0];
           }
         }
       }
