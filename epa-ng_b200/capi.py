@@ -67,6 +67,7 @@ SYMBOLS = [
     ("epa_build_lookup", C.c_int, [_vp]),
     ("epa_place_chunk", C.c_int, [_vp, _vp, C.c_uint32, C.POINTER(Options), _vp, _u32p]),
     ("epa_upload_queries", C.c_int, [_vp, _vp, C.c_uint32, C.c_int]),
+    ("epa_hint_next_chunk", C.c_int, [_vp, _vp, C.c_uint32]),
     ("epa_encode_queries_dev", C.c_int, [_vp, _vp, C.c_uint32, C.c_int]),
     ("epa_preplace", C.c_int, [_vp]),
     ("epa_select", C.c_int, [_vp, C.POINTER(Options), C.POINTER(C.c_uint64)]),
@@ -211,6 +212,10 @@ class Context:
         a = self._rows(seqs, self.sites)
         self.nq = a.shape[0]
         self._check(self.lib.epa_upload_queries(self.handle, a.ctypes.data, a.shape[0], int(premasking)))
+
+    def hint_next_chunk(self, host_ptr, nq):
+        """Announces the chunk after the next upload: its H2D copy overlaps the placement."""
+        self._check(self.lib.epa_hint_next_chunk(self.handle, host_ptr, nq))
 
     def upload_queries_ptr(self, host_ptr, nq, premasking=True):
         self.nq = nq

@@ -88,7 +88,13 @@ struct epa_ctx {
   uint64_t n_pairs = 0;
   size_t pre_stride = 0;
   DevBuf raw, codes, begin, span, sortkey, perm, hist, range, pre, cnt, cutv, cuti, off, pair_q, pair_e,
-         edge_hist, edge_off, work, res, out_rec, out_cnt, scratch, tmp;
+         edge_hist, edge_off, work, res, out_rec, out_cnt, scratch, tmp, qmax, cand;
+  // host -> device prefetch of the NEXT chunk on a second stream (epa_hint_next_chunk)
+  cudaStream_t copy_stream = nullptr;
+  cudaEvent_t ev_copy = nullptr;
+  DevBuf raw_next;
+  const char * hint_ptr = nullptr; uint32_t hint_n = 0;         // announced next chunk
+  const char * staged_ptr = nullptr; uint32_t staged_n = 0;     // chunk whose copy into raw_next is in flight
   int * d_flags = nullptr;              // [0..1] error, [2] max tile width, [3] max span
   unsigned long long * d_counter = nullptr;
   uint64_t * d_total = nullptr;
@@ -243,8 +249,11 @@ extern "C" void epa_ctx_destroy(epa_ctx * ctx)
   DevBuf * bufs[] = {&ctx->raw, &ctx->codes, &ctx->begin, &ctx->span, &ctx->sortkey, &ctx->perm, &ctx->hist, &ctx->range,
                      &ctx->pre, &ctx->cnt, &ctx->cutv, &ctx->cuti, &ctx->off, &ctx->pair_q, &ctx->pair_e,
                      &ctx->edge_hist, &ctx->edge_off, &ctx->work, &ctx->res, &ctx->out_rec, &ctx->out_cnt,
-                     &ctx->scratch, &ctx->tmp};
+                     &ctx->scratch, &ctx->tmp, &ctx->qmax, &ctx->cand};
   for (DevBuf * b : bufs) b->release();
+  ctx->raw_next.release();
+  if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+  if (ctx->ev_copy) cudaEventDestroy(ctx->ev_copy);
   cudaFree(ctx->d_model); cudaFree(ctx->tree.clv); cudaFree(ctx->tree.scaler); cudaFree(ctx->d_edges);
   cudaFree(ctx->d_lookup); cudaFree(ctx->d_pairtab); cudaFree(ctx->d_clvT); cudaFree(ctx->d_btab); cudaFree(ctx->d_pn); cudaFree(ctx->d_flags); cudaFree(ctx->d_counter); cudaFree(ctx->d_total);
   for (auto & e : ctx->ev) if (e) cudaEventDestroy(e);
@@ -697,13 +706,47 @@ extern "C" int epa_upload_queries(epa_ctx * ctx, const char * seqs, uint32_t n_q
   ctx->nq = n_queries;
   if (n_queries == 0) { ctx->stage = ST_QUERIES; ctx->max_span = 0; return EPA_OK; }
   const size_t bytes = (size_t) n_queries * ctx->n;
-  CU(ctx->raw.ensure(bytes));
   CU(ctx->codes.ensure(bytes));
   CU(ctx->begin.ensure(n_queries * sizeof(int)));
   CU(ctx->span.ensure(n_queries * sizeof(int)));
   CU(cudaEventRecord(ctx->ev[0], ctx->stream));
-  CU(cudaMemcpyAsync(ctx->raw.p, seqs, bytes, cudaMemcpyHostToDevice, ctx->stream));
-  return epa_encode_queries_dev(ctx, nullptr, n_queries, premasking);
+  if (ctx->staged_ptr == seqs && ctx->staged_n == n_queries)
+  {
+    // this chunk was prefetched while the previous one was being placed
+    std::swap(ctx->raw, ctx->raw_next);
+    CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_copy, 0));
+  }
+  else
+  {
+    if (ctx->staged_ptr) CU(cudaStreamSynchronize(ctx->copy_stream));     // stale prefetch: let it land first
+    CU(ctx->raw.ensure(bytes));
+    CU(cudaMemcpyAsync(ctx->raw.p, seqs, bytes, cudaMemcpyHostToDevice, ctx->stream));
+  }
+  ctx->staged_ptr = nullptr; ctx->staged_n = 0;
+  const int rc = epa_encode_queries_dev(ctx, nullptr, n_queries, premasking);
+  if (rc == EPA_OK && ctx->hint_ptr && ctx->hint_n)
+  {
+    // start the copy of the announced next chunk; it overlaps the placement of this one
+    if (!ctx->copy_stream)
+    {
+      CU(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+      CU(cudaEventCreateWithFlags(&ctx->ev_copy, cudaEventDisableTiming));
+    }
+    const size_t nbytes = (size_t) ctx->hint_n * ctx->n;
+    CU(ctx->raw_next.ensure(nbytes));
+    CU(cudaMemcpyAsync(ctx->raw_next.p, ctx->hint_ptr, nbytes, cudaMemcpyHostToDevice, ctx->copy_stream));
+    CU(cudaEventRecord(ctx->ev_copy, ctx->copy_stream));
+    ctx->staged_ptr = ctx->hint_ptr; ctx->staged_n = ctx->hint_n;
+  }
+  ctx->hint_ptr = nullptr; ctx->hint_n = 0;
+  return rc;
+}
+
+extern "C" int epa_hint_next_chunk(epa_ctx * ctx, const char * next_seqs, uint32_t next_n_queries)
+{
+  if (!ctx) return EPA_ERR_ARG;
+  ctx->hint_ptr = next_seqs; ctx->hint_n = next_seqs ? next_n_queries : 0;
+  return EPA_OK;
 }
 
 // Device-resident variant: `seqs_dev` already lives in HBM (NULL = the context's own staging
@@ -805,7 +848,7 @@ int launch_preplace_mma(epa_ctx * ctx, uint32_t count, const int2 * range)
   a.codes = ctx->codes.as<uint8_t>(); a.begin = ctx->begin.as<int>(); a.span = ctx->span.as<int>();
   a.perm = ctx->perm.as<uint32_t>(); a.nq = count; a.range = range;
   a.n_tiles = (count + MMA_TQ - 1) / MMA_TQ;
-  a.pre = ctx->pre.as<double>(); a.pre_stride = ctx->pre_stride;
+  a.pre = ctx->pre.as<double>(); a.pre_stride = ctx->pre_stride; a.qmax = ctx->qmax.as<double>();
   CU(cudaFuncSetAttribute(preplace_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) MMA_SMEM_BYTES));
   const unsigned grid = (unsigned) std::min<uint32_t>((uint32_t) ctx->sm_count, a.n_tiles);
   preplace_mma_kernel<<<grid, MMA_THREADS, MMA_SMEM_BYTES, ctx->stream>>>(a);
@@ -824,7 +867,9 @@ extern "C" int epa_preplace(epa_ctx * ctx)
   ctx->pre_stride = (ctx->n_edges + 3u) & ~3u;
   if (nq == 0) { ctx->stage = ST_PREPLACED; return EPA_OK; }
   CU(ctx->pre.ensure((size_t) nq * ctx->pre_stride * sizeof(double)));
+  CU(ctx->qmax.ensure(nq * sizeof(double)));
   CU(cudaEventRecord(ctx->ev[1], ctx->stream));
+  CU(cudaMemsetAsync(ctx->qmax.p, 0xff, nq * sizeof(double), ctx->stream));      // NaN = no row maximum recorded
   // simple DNA queries (sorted first) take the tensor-core kernel (tile windows of at most
   // MMA_KC_MAX * 4 sites) or else the pair-table kernel; the rest take the per-site kernel
   const uint32_t nA = ctx->d_pairtab ? ctx->n_simple : 0u, nB = nq - nA;
@@ -916,6 +961,9 @@ extern "C" int epa_select(epa_ctx * ctx, const epa_options * opts, uint64_t * n_
       CU(ctx->off.ensure(nq * sizeof(uint32_t)));
       CU(ctx->cutv.ensure(nq * sizeof(double)));
       CU(ctx->cuti.ensure(nq * sizeof(int)));
+      CU(ctx->cand.ensure((size_t) nq * SEL_CAP * sizeof(uint32_t)));
+      // single-scan selection is exact while the weight hidden below the cut cannot reach 1 - threshold
+      const int fast_ok = (1.0 - opts->prescoring_threshold) > 4.0 * (double) B * std::exp(-SEL_CUT) ? 1 : 0;
       // work list order: edge-major, then window start in bins of kWindowBin sites
       const uint32_t nbins = (uint32_t) (ctx->n / kWindowBin) + 1;
       const size_t nkeys = (size_t) B * nbins;
@@ -923,8 +971,9 @@ extern "C" int epa_select(epa_ctx * ctx, const epa_options * opts, uint64_t * n_
       CU(ctx->edge_hist.ensure((nkeys + 1) * sizeof(uint32_t)));
       const unsigned blocks = (nq + 7) / 8;
       select_count_kernel<<<blocks, 256, 0, ctx->stream>>>(ctx->pre.as<double>(), ctx->pre_stride, (int) B, nq,
-                                                           opts->heuristic, opts->prescoring_threshold, ctx->cnt.as<uint32_t>(),
-                                                           ctx->cutv.as<double>(), ctx->cuti.as<int>());
+                                                           opts->heuristic, opts->prescoring_threshold, fast_ok,
+                                                           ctx->qmax.as<double>(), ctx->cnt.as<uint32_t>(),
+                                                           ctx->cutv.as<double>(), ctx->cuti.as<int>(), ctx->cand.as<uint32_t>());
       LAUNCHED(ctx);
       exclusive_scan_kernel<<<1, 1024, 0, ctx->stream>>>(ctx->cnt.as<uint32_t>(), ctx->off.as<uint32_t>(), nq, ctx->d_total);
       LAUNCHED(ctx);
@@ -938,7 +987,8 @@ extern "C" int epa_select(epa_ctx * ctx, const epa_options * opts, uint64_t * n_
       CU(ctx->work.ensure(total * sizeof(uint32_t)));
       CU(cudaMemsetAsync(ctx->edge_hist.p, 0, (nkeys + 1) * sizeof(uint32_t), ctx->stream));
       select_fill_kernel<<<blocks, 256, 0, ctx->stream>>>(ctx->pre.as<double>(), ctx->pre_stride, (int) B, nq,
-                                                          ctx->off.as<uint32_t>(), ctx->cutv.as<double>(), ctx->cuti.as<int>(),
+                                                          ctx->off.as<uint32_t>(), ctx->cnt.as<uint32_t>(), ctx->cand.as<uint32_t>(),
+                                                          ctx->cutv.as<double>(), ctx->cuti.as<int>(),
                                                           ctx->begin.as<int>(), kWindowBin, nbins,
                                                           ctx->pair_q.as<uint32_t>(), ctx->pair_e.as<uint32_t>(),
                                                           ctx->edge_hist.as<uint32_t>());

@@ -170,6 +170,9 @@ extern "C" int epa_session_place(epa_session * s, const char * query_rows, uint6
   for (uint64_t done = 0; done < n_queries; done += chunk_size)
   {
     const uint32_t nq = (uint32_t) std::min<uint64_t>(chunk_size, n_queries - done);
+    if (done + nq < n_queries)
+      epa_hint_next_chunk(s->ctx, query_rows + (done + nq) * s->sites,
+                          (uint32_t) std::min<uint64_t>(chunk_size, n_queries - done - nq));
     const int rc = epa_place_chunk(s->ctx, query_rows + done * s->sites, nq, opts,
                                    out ? out + done * opts->filter_max : nullptr, counts ? counts + done : nullptr);
     if (rc)

@@ -444,25 +444,102 @@ __device__ __forceinline__ bool ranks_before(double v, int i, double pv, int pi)
   return (v > pv) || (v == pv && i < pi);
 }
 
+constexpr int SEL_CAP = 16;          // candidates staged per query by the count pass
+constexpr int SEL_LIST = 64;         // near-best entries a warp keeps while it scans a row
+#define SEL_CUT 40.0                 /* entries below max - 40 carry less than 4.3e-18 of the weight */
+
+// Fast path of the dynamic heuristic: ONE scan of the row computes the LWR normaliser and keeps the
+// entries within SEL_CUT of the best in shared memory (in ascending edge order); the best-first
+// accumulation then runs on that short list. It is exact as long as the threshold is crossed inside
+// the list, which the caller guarantees by only enabling it when 1 - thresh exceeds the weight
+// that can hide below the cut; otherwise, and for the other heuristics, every extraction scans the
+// row again (slow path). qmax (optional, NaN = absent) is the row maximum from the preplacement kernel.
 __global__ void __launch_bounds__(256)
 select_count_kernel(const double * __restrict__ pre, size_t pre_stride, int n_edges, uint32_t nq, int mode,
-                    double thresh, uint32_t * __restrict__ cnt, double * __restrict__ cut_v,
-                    int * __restrict__ cut_i)
+                    double thresh, int fast_ok, const double * __restrict__ qmax, uint32_t * __restrict__ cnt,
+                    double * __restrict__ cut_v, int * __restrict__ cut_i, uint32_t * __restrict__ cand)
 {
   // mode 0: dynamic  - accumulated LWR threshold (until_accumulated_reached, set_manipulators.cpp:90-113)
   // mode 1: fixed    - the best ceil(thresh * edges) (until_top_percent, set_manipulators.cpp:82-88)
   // mode 2: baseball - everything within 3 log-likelihood units of the best, plus min(40 - hits, 6)
   //                    more (baseball_heuristic, src/core/heuristics.hpp:74-117)
+  __shared__ double lv[8][SEL_LIST];
+  __shared__ int li[8][SEL_LIST];
   const uint32_t q = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int lane = threadIdx.x & 31;
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   if (q >= nq) return;
   const double * row = pre + (size_t) q * pre_stride;
-  double mx = -INFINITY;
-  for (int b = lane; b < n_edges; b += 32) mx = fmax(mx, row[b]);
-  mx = warp_max(mx);
+  double mx = qmax ? qmax[q] : NAN;
+  if (mx != mx)
+  {
+    mx = -INFINITY;
+    for (int b = lane; b < n_edges; b += 32) mx = fmax(mx, row[b]);
+    mx = warp_max(mx);
+  }
+  const bool fast = fast_ok && mode == 0;
   double tot = 0.0;
-  for (int b = lane; b < n_edges; b += 32) tot += exp(row[b] - mx);
+  int nl = 0;
+  for (int base = 0; base < n_edges; base += 32)
+  {
+    const int b = base + lane;
+    double v = -INFINITY;
+    if (b < n_edges) { v = row[b]; tot += exp(v - mx); }
+    if (fast)
+    {
+      const bool near = v > mx - SEL_CUT;
+      const unsigned m = __ballot_sync(0xffffffffu, near);
+      if (near)
+      {
+        const int pos = nl + __popc(m & ((1u << lane) - 1u));
+        if (pos < SEL_LIST) { lv[wib][pos] = v; li[wib][pos] = b; }
+      }
+      nl += __popc(m);
+    }
+  }
   tot = warp_sum(tot);
+  __syncwarp();
+
+  if (fast && nl <= SEL_LIST)
+  {
+    double v0 = lane < nl ? lv[wib][lane] : -INFINITY, v1 = lane + 32 < nl ? lv[wib][lane + 32] : -INFINITY;
+    const int i0 = lane < nl ? li[wib][lane] : INT_MAX, i1 = lane + 32 < nl ? li[wib][lane + 32] : INT_MAX;
+    bool t0 = false, t1 = false;
+    double acc = 0.0, pv = INFINITY; int pi = -1;
+    uint32_t c = 0;
+    bool exhausted = false;
+    while (acc < thresh)
+    {
+      double bv = v0; int bi = i0;
+      if (t0 || bi == INT_MAX) { bv = -INFINITY; bi = INT_MAX; }
+      if (!t1 && i1 != INT_MAX && ranks_before(v1, i1, bv, bi)) { bv = v1; bi = i1; }
+      #pragma unroll
+      for (int o = 16; o > 0; o >>= 1)
+      {
+        const double ov = __shfl_xor_sync(0xffffffffu, bv, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (ranks_before(ov, oi, bv, bi)) { bv = ov; bi = oi; }
+      }
+      if (bi == INT_MAX) { exhausted = true; break; }
+      if (bi == i0) t0 = true;
+      if (bi == i1) t1 = true;
+      acc += exp(bv - mx) / tot;
+      pv = bv; pi = bi;
+      ++c;
+    }
+    if (!exhausted || nl >= n_edges)
+    {
+      const unsigned m0 = __ballot_sync(0xffffffffu, t0), m1 = __ballot_sync(0xffffffffu, t1);
+      uint32_t * cq = cand + (size_t) q * SEL_CAP;
+      if (c <= SEL_CAP)
+      {
+        if (t0) cq[__popc(m0 & ((1u << lane) - 1u))] = (uint32_t) i0;
+        if (t1) cq[__popc(m0) + __popc(m1 & ((1u << lane) - 1u))] = (uint32_t) i1;
+      }
+      else if (lane == 0) cq[0] = 0xffffffffu;
+      if (lane == 0) { cnt[q] = c; cut_v[q] = pv; cut_i[q] = pi; }
+      return;
+    }
+  }
 
   double pv = INFINITY; int pi = -1;
   double acc = 0.0;
@@ -499,13 +576,15 @@ select_count_kernel(const double * __restrict__ pre, size_t pre_stride, int n_ed
     pv = bv; pi = bi;
     ++c;
   }
-  if (lane == 0) { cnt[q] = c; cut_v[q] = pv; cut_i[q] = pi; }
+  if (lane == 0) { cnt[q] = c; cut_v[q] = pv; cut_i[q] = pi; cand[(size_t) q * SEL_CAP] = 0xffffffffu; }
 }
 
-// Pass 2 (fill): pair list in query-major order, edges ascending inside a query.
+// Pass 2 (fill): pair list in query-major order, edges ascending inside a query. Queries whose
+// candidates were staged by the count pass are copied, the others scan their row again.
 __global__ void __launch_bounds__(256)
 select_fill_kernel(const double * __restrict__ pre, size_t pre_stride, int n_edges, uint32_t nq,
-                   const uint32_t * __restrict__ off, const double * __restrict__ cut_v,
+                   const uint32_t * __restrict__ off, const uint32_t * __restrict__ cnt,
+                   const uint32_t * __restrict__ cand, const double * __restrict__ cut_v,
                    const int * __restrict__ cut_i, const int * __restrict__ begin, int window_bin,
                    uint32_t nbins, uint32_t * __restrict__ pair_q,
                    uint32_t * __restrict__ pair_e, uint32_t * __restrict__ key_hist)
@@ -513,10 +592,22 @@ select_fill_kernel(const double * __restrict__ pre, size_t pre_stride, int n_edg
   const uint32_t q = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (q >= nq) return;
-  const double * row = pre + (size_t) q * pre_stride;
-  const double cv = cut_v[q]; const int ci = cut_i[q];
   const uint32_t wbin = (uint32_t) (begin[q] / window_bin);
   uint32_t o = off[q];
+  const uint32_t c = cnt[q];
+  if (c <= SEL_CAP && cand[(size_t) q * SEL_CAP] != 0xffffffffu)
+  {
+    if ((uint32_t) lane < c)
+    {
+      const uint32_t b = cand[(size_t) q * SEL_CAP + lane];
+      pair_q[o + lane] = q;
+      pair_e[o + lane] = b;
+      atomicAdd(&key_hist[(size_t) b * nbins + wbin], 1u);
+    }
+    return;
+  }
+  const double * row = pre + (size_t) q * pre_stride;
+  const double cv = cut_v[q]; const int ci = cut_i[q];
   for (int base = 0; base < n_edges; base += 32)
   {
     const int b = base + lane;

@@ -174,6 +174,7 @@ struct PreMmaArgs {
   uint32_t n_tiles;
   double * pre;
   size_t pre_stride;
+  double * qmax;               // [query] row maximum (read by the candidate selection)
 };
 
 // instruction descriptor (UMMA::InstrDescriptor): D = s32, A = B = unsigned 8 bit, both K-major
@@ -193,6 +194,7 @@ preplace_mma_kernel(PreMmaArgs a)
   uint32_t * tmem_slot = reinterpret_cast<uint32_t *>(tempty + 2);
   __shared__ uint32_t row_q[MMA_TQ];
   __shared__ int row_b[MMA_TQ], row_e[MMA_TQ];
+  __shared__ double row_max[2][MMA_TQ];
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if (tid == 0)
@@ -319,6 +321,7 @@ preplace_mma_kernel(PreMmaArgs a)
       const double2 * __restrict__ pne = reinterpret_cast<const double2 *>(a.pn + (size_t) row_e[r] * e_pad + half * 16);
       double * out = a.pre + (size_t) (q == 0xffffffffu ? 0u : q) * a.pre_stride + half * 16;
       uint32_t bi = blk_it;
+      double rmax = -INFINITY;
       // prefix-sum term of the block's 16 branches, loaded one block ahead
       double base[16];
       #pragma unroll
@@ -374,15 +377,17 @@ preplace_mma_kernel(PreMmaArgs a)
           if (q != 0xffffffffu)
           {
             double * dst = out + (size_t) eb * MMA_EB + j;
-            if (e0 + j + 1 < a.n_edges) *reinterpret_cast<double2 *>(dst) = make_double2(res[0], res[1]);
-            else if (e0 + j < a.n_edges) dst[0] = res[0];
+            if (e0 + j + 1 < a.n_edges) { *reinterpret_cast<double2 *>(dst) = make_double2(res[0], res[1]); rmax = fmax(rmax, fmax(res[0], res[1])); }
+            else if (e0 + j < a.n_edges) { dst[0] = res[0]; rmax = fmax(rmax, res[0]); }
           }
         }
       }
+      row_max[half][r] = rmax;
     }
     stage_it += a.n_eb * (uint32_t) n_ks;
     blk_it += a.n_eb;
     __syncthreads();           // the epilogue of the last block implies every MMA of the tile is done
+    if (tid < MMA_TQ && row_q[tid] != 0xffffffffu) a.qmax[row_q[tid]] = fmax(row_max[0][tid], row_max[1][tid]);
   }
 
   tc_fence_before();

@@ -156,6 +156,11 @@ int epa_place_chunk(epa_ctx * ctx, const char * seqs, uint32_t n_queries,
 
 /* H2D copy of the chunk + encoding + valid-range detection (src/util/Range.hpp:34-49). */
 int epa_upload_queries(epa_ctx * ctx, const char * seqs, uint32_t n_queries, int premasking);
+/* Announces the chunk that will follow the next epa_upload_queries / epa_place_chunk call: its
+ * host-to-device copy then runs on a second stream while that chunk is being placed (the
+ * reference prefetches the next chunk with std::async, src/seq/MSA_Stream.cpp:79-85). The host
+ * buffer must stay valid and unchanged until it has been uploaded. NULL cancels the hint. */
+int epa_hint_next_chunk(epa_ctx * ctx, const char * next_seqs, uint32_t next_n_queries);
 /* Same for a chunk that already lives in device memory (seqs_dev = DEVICE pointer to
  * n_queries * sites ASCII bytes): used for device-resident timing and by callers that stage
  * the query file in HBM themselves. */
