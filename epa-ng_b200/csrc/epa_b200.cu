@@ -75,7 +75,8 @@ struct epa_ctx {
   double * d_pn = nullptr;         // DNA: prefix sums of the fully-ambiguous lookup column [edge][n + 1]
   bool mma_ok = false;             // every table entry fits the fixed-point format
   double * d_clvT = nullptr;       // DNA: site-blocked CLV copy read by the lane = site BLO kernel
-  bool clvT_ready = false;
+  double * d_gT = nullptr;         // DNA: per-edge first-round tables of the BLO kernel (site-blocked)
+  bool clvT_ready = false;         // covers d_clvT and d_gT
   bool clvs_ready = false, lookup_ready = false;
   std::vector<uint8_t> slot_filled;
 
@@ -255,7 +256,7 @@ extern "C" void epa_ctx_destroy(epa_ctx * ctx)
   if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
   if (ctx->ev_copy) cudaEventDestroy(ctx->ev_copy);
   cudaFree(ctx->d_model); cudaFree(ctx->tree.clv); cudaFree(ctx->tree.scaler); cudaFree(ctx->d_edges);
-  cudaFree(ctx->d_lookup); cudaFree(ctx->d_pairtab); cudaFree(ctx->d_clvT); cudaFree(ctx->d_btab); cudaFree(ctx->d_pn); cudaFree(ctx->d_flags); cudaFree(ctx->d_counter); cudaFree(ctx->d_total);
+  cudaFree(ctx->d_lookup); cudaFree(ctx->d_pairtab); cudaFree(ctx->d_clvT); cudaFree(ctx->d_gT); cudaFree(ctx->d_btab); cudaFree(ctx->d_pn); cudaFree(ctx->d_flags); cudaFree(ctx->d_counter); cudaFree(ctx->d_total);
   for (auto & e : ctx->ev) if (e) cudaEventDestroy(e);
   if (ctx->stream && ctx->own_stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
@@ -1022,6 +1023,32 @@ int ensure_clvT(epa_ctx * ctx)
   clv_site_block_kernel<<<grid, 256, (size_t) CLVT_BLOCK * (C + 1) * sizeof(double), ctx->stream>>>(
       ctx->tree.clv, ctx->tree.clv_stride, ctx->n, C, ctx->d_clvT, t_stride);
   LAUNCHED(ctx);
+  // first-round tables: transition matrices of orig/2 per edge, then V * inner per (edge, site)
+  const uint32_t B = ctx->n_edges;
+  const size_t pm = (size_t) ctx->R * 16;
+  std::vector<double> lengths(B);
+  for (uint32_t i = 0; i < B; ++i) lengths[i] = ctx->h_edges[i].length / 2.0;
+  CU(ctx->tmp.ensure((size_t) B * (pm + 1) * sizeof(double)));
+  double * d_len = ctx->tmp.as<double>(), * d_pm = d_len + B;
+  CU(cudaMemcpyAsync(d_len, lengths.data(), B * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  if (int rc = launch_pmatrices(ctx, d_len, d_pm, B)) return rc;
+  if (!ctx->d_gT && cudaMalloc(&ctx->d_gT, (size_t) B * t_stride * sizeof(double)) != cudaSuccess)
+  {
+    (void) cudaGetLastError();
+    ctx->d_gT = nullptr;                         // optional table: the kernel then runs the full first pass
+  }
+  if (ctx->d_gT)
+  {
+    dim3 g2(B, (ctx->n + 127) / 128);
+    switch (ctx->R)
+    {
+      case 1: blo_first_table_kernel<1><<<g2, 128, 0, ctx->stream>>>(ctx->tree, ctx->n, ctx->d_edges, d_pm, ctx->d_gT, t_stride); break;
+      case 2: blo_first_table_kernel<2><<<g2, 128, 0, ctx->stream>>>(ctx->tree, ctx->n, ctx->d_edges, d_pm, ctx->d_gT, t_stride); break;
+      default: blo_first_table_kernel<4><<<g2, 128, 0, ctx->stream>>>(ctx->tree, ctx->n, ctx->d_edges, d_pm, ctx->d_gT, t_stride); break;
+    }
+    LAUNCHED(ctx);
+  }
+  CU(cudaStreamSynchronize(ctx->stream));        // lengths[] is host memory
   ctx->clvT_ready = true;
   return EPA_OK;
 }
@@ -1033,6 +1060,10 @@ int launch_blo_site(epa_ctx * ctx, BloArgs & a)
   if (int rc = ensure_clvT(ctx)) return rc;
   BloSiteArgs sa{};
   sa.clvT = ctx->d_clvT; sa.t_stride = clvt_node_stride(ctx->n, ctx->R);
+  if (ctx->d_gT && ctx->lookup_ready && !getenv("EPA_B200_NO_FIRST"))
+  {
+    sa.gT = ctx->d_gT; sa.g_stride = sa.t_stride; sa.lookup = ctx->d_lookup; sa.n_pad = ctx->n_pad;
+  }
   const int wmax = std::max(1, ctx->max_span);
   const size_t per_warp = SiteWarpSmem<R>::doubles(wmax) * sizeof(double);
   const size_t budget = ctx->smem_optin - 2048;

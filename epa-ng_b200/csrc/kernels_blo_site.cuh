@@ -77,7 +77,61 @@ struct BloSiteArgs {
   size_t t_stride;                      // doubles per node in clvT
   double * gscratch;                    // global sumtable scratch [warp][blo_row][wpad] (GS variant)
   int wpad;                             // padded window capacity of the global scratch
+  // first-round tables (NULL = not available): every pair of an edge starts from the same three
+  // lengths, so the inner CLV of the first pass, rotated into the eigenbasis, is per-edge data
+  const double * gT;                    // [edge] site-blocked V * inner(orig/2, orig/2), scaled like the CLV update
+  size_t g_stride;                      // doubles per edge in gT
+  const double * lookup;                // preplacement tables [edge][n_pad][16]: the first-pass site log-likelihoods
+  int n_pad;
 };
+
+// gT[e][s/32][r*4+j][s%32] = sum_k V[j][k] * inner[s][r][k], inner = (P(orig/2) D) * (P(orig/2) X), multiplied by
+// 2^256 where the CLV update would rescale (LP/core_partials.c:690-766). grid = (edges, ceil(n / 128)).
+template <int R>
+__global__ void __launch_bounds__(128)
+blo_first_table_kernel(DevTree tree, int n, const EdgeDev * __restrict__ edges, const double * __restrict__ pm,
+                       double * __restrict__ gT, size_t g_stride)
+{
+  __shared__ double P[R * 16];
+  const uint32_t e = blockIdx.x;
+  for (int i = threadIdx.x; i < R * 16; i += blockDim.x) P[i] = pm[(size_t) e * R * 16 + i];
+  __syncthreads();
+  const int s = blockIdx.y * 128 + threadIdx.x;
+  if (s >= n) return;
+  const EdgeDev ed = edges[e];
+  const double * D = tree.clv + ed.distal * tree.clv_stride + (size_t) s * R * 4;
+  const double * X = tree.clv + ed.proximal * tree.clv_stride + (size_t) s * R * 4;
+  double in[4 * R];
+  bool small = true;
+  #pragma unroll
+  for (int r = 0; r < R; ++r)
+  {
+    double dv[4], xv[4];
+    load_vec<4>(D + r * 4, dv);
+    load_vec<4>(X + r * 4, xv);
+    #pragma unroll
+    for (int i = 0; i < 4; ++i)
+    {
+      const double * p = P + r * 16 + i * 4;
+      const double ta = p[0] * dv[0] + p[1] * dv[1] + p[2] * dv[2] + p[3] * dv[3];
+      const double tb = p[0] * xv[0] + p[1] * xv[1] + p[2] * xv[2] + p[3] * xv[3];
+      in[r * 4 + i] = ta * tb;
+      small = small && (in[r * 4 + i] < EPA_SCALE_THRESHOLD);
+    }
+  }
+  if (small)
+  {
+    #pragma unroll
+    for (int c = 0; c < 4 * R; ++c) in[c] *= EPA_SCALE_FACTOR;
+  }
+  double * out = gT + (size_t) e * g_stride + (size_t) (s >> 5) * (R * 4 * CLVT_BLOCK) + (s & 31);
+  #pragma unroll
+  for (int r = 0; r < R; ++r)
+    #pragma unroll
+    for (int j = 0; j < 4; ++j)
+      out[(size_t) (r * 4 + j) * CLVT_BLOCK] = c_model.eigenvecs[j * 4] * in[r * 4] + c_model.eigenvecs[j * 4 + 1] * in[r * 4 + 1]
+                                             + c_model.eigenvecs[j * 4 + 2] * in[r * 4 + 2] + c_model.eigenvecs[j * 4 + 3] * in[r * 4 + 3];
+}
 
 // P[r][i][j] = delta_ij + sum_k Vinv[i][k] expm1(lambda_k rate_r t) V[k][j]   (LP/core_pmatrix.c:185-249)
 template <int R>
@@ -369,6 +423,40 @@ __device__ __forceinline__ double site_pass_tip(const SiteCtaSmem & cs, const do
   return warp_sum(acc);
 }
 
+// Pass A of the FIRST half round, from the per-edge tables: the pendant sumtable is the tip factor
+// times the stored eigen-rotated inner CLV, the window log-likelihood is the sum of the
+// preplacement table entries (the same three lengths, the same tiny tree).
+template <int R, bool GS>
+__device__ __forceinline__ double site_pass_first(const SiteCtaSmem & cs, double * sum, int gstride,
+                                                  const double * __restrict__ GT, const double * __restrict__ lk,
+                                                  const uint8_t * __restrict__ qc, int begin, int w, int lane)
+{
+  double acc = 0.0;
+  #pragma unroll 1
+  for (int s = lane; s < w; s += 32)
+  {
+    const double * gp = GT + clvt_offset<R>(begin + s);
+    double gv[4 * R];
+    #pragma unroll
+    for (int c = 0; c < 4 * R; ++c) gv[c] = __ldg(gp + (size_t) c * CLVT_BLOCK);
+    const int mask = qc[s] & 15;
+    acc += __ldg(lk + (size_t) (begin + s) * 16 + mask);
+    double tl[4];
+    lds_vec<4>(cs.tipleft + tv_pos(mask) * 4, tl);
+    double base = 0.0;
+    double st[3 * R];
+    #pragma unroll
+    for (int r = 0; r < R; ++r)
+    {
+      base += (tl[0] * gv[r * 4]) * c_model.weights[r];
+      #pragma unroll
+      for (int j = 1; j < 4; ++j) st[r * 3 + j - 1] = tl[j] * gv[r * 4 + j];
+    }
+    site_store_row<R, GS>(sum, gstride, s, base, st);
+  }
+  return warp_sum(acc);
+}
+
 // Pass B: inner CLV toward the distal node from (T, X); leaves the distal sumtable (D vs inner)
 template <int R, bool GS>
 __device__ __forceinline__ void site_pass_distal(const double * ws, double * sum, int gstride,
@@ -538,7 +626,12 @@ blo_site_kernel(BloSiteArgs sa)
       double xmin, xmax, xguess;
       if (!distal_phase)
       {
-        const double new_logl = -site_pass_tip<R, GS>(cs, ws, sum, gstride, DT, XT, sD, sX, qc, begin, w, lane);
+        double new_logl;
+        if (first && sa.gT)
+          new_logl = -site_pass_first<R, GS>(cs, sum, gstride, sa.gT + (size_t) e * sa.g_stride,
+                                             sa.lookup + (size_t) e * sa.n_pad * 16, qc, begin, w, lane);
+        else
+          new_logl = -site_pass_tip<R, GS>(cs, ws, sum, gstride, DT, XT, sD, sX, qc, begin, w, lane);
         if (first) { loglikelihood = new_logl; first = false; }
         else
         {
