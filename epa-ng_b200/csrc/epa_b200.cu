@@ -1065,14 +1065,22 @@ int launch_blo_site(epa_ctx * ctx, BloArgs & a)
     sa.gT = ctx->d_gT; sa.g_stride = sa.t_stride; sa.lookup = ctx->d_lookup; sa.n_pad = ctx->n_pad;
   }
   const int wmax = std::max(1, ctx->max_span);
-  const size_t per_warp = SiteWarpSmem<R>::doubles(wmax) * sizeof(double);
+  // up to 12 warps per CTA (register file): the first 8 keep their sumtable in tensor memory when
+  // the windows fit 8 rows of 32 sites, the others in shared memory
+  const size_t fix = (size_t) SiteWarpSmem<R>::SUM * sizeof(double);
+  const size_t rows = (size_t) wmax * blo_row(R) * sizeof(double);
   const size_t budget = ctx->smem_optin - 2048;
-  int warps = (int) std::min<size_t>(9, budget / per_warp);      // __launch_bounds__(288, 1)
+  const int max_warps = 12;
+  const int n_tm = (wmax <= SITE_TMEM_ROWS * 32 && !getenv("EPA_B200_NO_TMEM")) ? SITE_TMEM_WARPS : 0;
+  int n_sm = 0;
+  while (n_sm < (n_tm ? max_warps - n_tm : 9) && (size_t) (n_tm + n_sm + 1) * fix + (size_t) (n_sm + 1) * rows <= budget) ++n_sm;
+  int warps = n_tm + n_sm;
   if (warps >= 2)
   {
     a.wcap = wmax;
     sa.b = a;
-    const size_t smem = per_warp * warps;
+    sa.n_tmem_warps = n_tm;
+    const size_t smem = (size_t) warps * fix + (size_t) n_sm * rows;
     uint64_t grid = (uint64_t) ctx->sm_count;
     grid = std::min<uint64_t>(grid, (a.n_pairs + warps - 1) / warps);
     CU(cudaFuncSetAttribute(blo_site_kernel<R, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));

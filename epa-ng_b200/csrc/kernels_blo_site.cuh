@@ -17,6 +17,7 @@
 //     shared memory (no shuffles).
 #pragma once
 #include "kernels_blo.cuh"
+#include "kernels_preplace_mma.cuh"     // tcgen05.ld helpers
 
 namespace epa {
 
@@ -71,12 +72,41 @@ struct SiteCtaSmem {
   int q_lock;
 };
 
+// Where a warp keeps its sumtable: shared-memory rows, global planes (GS kernels), or - for the
+// first SITE_TMEM_WARPS warps of a CTA - tensor memory. TMEM is idle in this kernel, every thread
+// of a warp can reach its own TMEM lane with tcgen05.ld/st (32x32b shape), and a sumtable row is
+// only ever touched by the lane that owns the site: 32 columns (128 bytes) per row and lane,
+// 8 rows per warp, two warps per 32-lane quarter. This lifts the shared-memory limit on the
+// number of pairs in flight per SM.
+constexpr int SITE_TMEM_WARPS = 8;
+constexpr int SITE_TMEM_ROWS = 8;        // rows (trips of 32 sites) a TMEM-backed warp can hold: windows <= 256
+struct SumRef {
+  double * base;
+  int gstride;
+  uint32_t taddr;
+  int tm;
+};
+
+__device__ __forceinline__ void tc_st32(uint32_t taddr, const uint32_t (&v)[32])
+{
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+               "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+               "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+               :: "r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]),
+                  "r"(v[8]), "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]),
+                  "r"(v[16]), "r"(v[17]), "r"(v[18]), "r"(v[19]), "r"(v[20]), "r"(v[21]), "r"(v[22]), "r"(v[23]),
+                  "r"(v[24]), "r"(v[25]), "r"(v[26]), "r"(v[27]), "r"(v[28]), "r"(v[29]), "r"(v[30]), "r"(v[31])
+               : "memory");
+}
+__device__ __forceinline__ void tc_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
 struct BloSiteArgs {
   BloArgs b;
   const double * clvT;                  // site-blocked CLV copy
   size_t t_stride;                      // doubles per node in clvT
   double * gscratch;                    // global sumtable scratch [warp][blo_row][wpad] (GS variant)
   int wpad;                             // padded window capacity of the global scratch
+  int n_tmem_warps;                     // leading warps of a CTA that keep their sumtable in tensor memory
   // first-round tables (NULL = not available): every pair of an edge starts from the same three
   // lengths, so the inner CLV of the first pass, rotated into the eigenbasis, is per-edge data
   const double * gT;                    // [edge] site-blocked V * inner(orig/2, orig/2), scaled like the CLV update
@@ -197,7 +227,7 @@ __device__ __forceinline__ double fast_rcp(double x)
 
 // derivative sums over the window, lane = site (LP/core_derivatives.c:643-858)
 template <int R, bool GS>
-__device__ __forceinline__ void site_derivatives(const double * sum, int gstride, double * ex, int w, double t,
+__device__ __forceinline__ void site_derivatives(const SumRef & sr, double * ex, int w, double t,
                                                  int lane, double & f, double & df)
 {
   constexpr int NK = 3 * R, ROW = blo_row(R);
@@ -225,6 +255,8 @@ __device__ __forceinline__ void site_derivatives(const double * sum, int gstride
   double a1 = 0.0, a2 = 0.0;
   const int trips = (w + 31) >> 5;
   const int s0 = lane < w ? lane : 0;
+  const double * sum = sr.base;
+  const int gstride = sr.gstride;
   auto load_row = [&](int s, double (&x)[NK + 1])
   {
     if constexpr (GS)
@@ -239,6 +271,11 @@ __device__ __forceinline__ void site_derivatives(const double * sum, int gstride
       for (int k = 0; k <= NK; ++k) x[k] = row[k];
     }
   };
+  auto unpack = [](const uint32_t (&v)[32], double (&x)[NK + 1])
+  {
+    #pragma unroll
+    for (int k = 0; k <= NK; ++k) x[k] = __hiloint2double((int) v[2 * k + 1], (int) v[2 * k]);
+  };
   int tr = 0;
   #pragma unroll 1
   for (; tr + 2 <= trips; tr += 2)
@@ -246,8 +283,21 @@ __device__ __forceinline__ void site_derivatives(const double * sum, int gstride
     const int sa = lane + 32 * tr, sb = sa + 32;
     const bool va = sa < w, vb = sb < w;
     double xa[NK + 1], xb[NK + 1];
-    load_row(va ? sa : s0, xa);
-    load_row(vb ? sb : s0, xb);
+    if (!GS && sr.tm)
+    {
+      // every lane reads its own rows tr and tr + 1 (rows of sites beyond the window hold the
+      // harmless values their lane stored there)
+      uint32_t ra[32], rb[32];
+      tc_ld32(sr.taddr + tr * 32, ra);
+      tc_ld32(sr.taddr + tr * 32 + 32, rb);
+      tc_wait_ld();
+      unpack(ra, xa); unpack(rb, xb);
+    }
+    else
+    {
+      load_row(va ? sa : s0, xa);
+      load_row(vb ? sb : s0, xb);
+    }
     double c0a = xa[0], c1a = 0.0, c2a = 0.0, c0b = xb[0], c1b = 0.0, c2b = 0.0;
     #pragma unroll
     for (int k = 0; k < NK; ++k)
@@ -266,7 +316,15 @@ __device__ __forceinline__ void site_derivatives(const double * sum, int gstride
     const int sa = lane + 32 * tr;
     const bool va = sa < w;
     double xa[NK + 1];
-    load_row(va ? sa : s0, xa);
+    if (!GS && sr.tm)
+    {
+      uint32_t ra[32];
+      tc_ld32(sr.taddr + tr * 32, ra);
+      tc_wait_ld();
+      unpack(ra, xa);
+    }
+    else
+      load_row(va ? sa : s0, xa);
     double c0a = xa[0], c1a = 0.0, c2a = 0.0;
     #pragma unroll
     for (int k = 0; k < NK; ++k) { c0a += xa[k + 1] * d0[k]; c1a += xa[k + 1] * d1[k]; c2a += xa[k + 1] * d2[k]; }
@@ -280,7 +338,7 @@ __device__ __forceinline__ void site_derivatives(const double * sum, int gstride
 
 // bounded Newton-Raphson, PM/optimize/opt_algorithms.c:133-262; returns 0.0 on failure
 template <int R, bool GS>
-__device__ __forceinline__ double site_newton(const double * sum, int gstride, double * ex, int w, int lane,
+__device__ __forceinline__ double site_newton(const SumRef & sr, double * ex, int w, int lane,
                                               double xmin, double xguess, double xmax, double tol)
 {
   double x = fmax(fmin(xguess, xmax), xmin);
@@ -291,7 +349,7 @@ __device__ __forceinline__ double site_newton(const double * sum, int gstride, d
   {
     if (iter++ > EPA_NR_MAX_ITERS) return 0.0;
     double f, df;
-    site_derivatives<R, GS>(sum, gstride, ex, w, x, lane, f, df);
+    site_derivatives<R, GS>(sr, ex, w, x, lane, f, df);
     if (!isfinite(f) || !isfinite(df)) return 0.0;
     double dx;
     if (df > 0.0)
@@ -311,29 +369,52 @@ __device__ __forceinline__ double site_newton(const double * sum, int gstride, d
   }
 }
 
-// stores one finished sumtable row: st[r][j], j = 0 is the stationary component
+// stores one finished sumtable row: st[r][j], j = 0 is the stationary component. `trip` is the row
+// slot of a TMEM-backed warp (all 32 lanes store, a lane beyond the window keeps a harmless row in
+// its own slot); shared/global rows are only written for sites inside the window.
 template <int R, bool GS>
-__device__ __forceinline__ void site_store_row(double * sum, int gstride, int s, double base, const double (&st)[3 * R])
+__device__ __forceinline__ void site_store_row(const SumRef & sr, int trip, int s, bool act, double base,
+                                               const double (&st)[3 * R])
 {
   if constexpr (GS)
   {
-    sum[s] = base;
-    #pragma unroll
-    for (int k = 0; k < 3 * R; ++k) sum[(size_t) (k + 1) * gstride + s] = st[k];
+    if (act)
+    {
+      sr.base[s] = base;
+      #pragma unroll
+      for (int k = 0; k < 3 * R; ++k) sr.base[(size_t) (k + 1) * sr.gstride + s] = st[k];
+    }
   }
   else
   {
-    double * row = sum + s * blo_row(R);
-    row[0] = base;
-    #pragma unroll
-    for (int k = 0; k < 3 * R; ++k) row[k + 1] = st[k];
+    if (sr.tm)
+    {
+      uint32_t v[32];
+      v[0] = (uint32_t) __double2loint(act ? base : 1.0); v[1] = (uint32_t) __double2hiint(act ? base : 1.0);
+      #pragma unroll
+      for (int k = 0; k < 3 * R; ++k)
+      {
+        v[2 * k + 2] = (uint32_t) __double2loint(act ? st[k] : 0.0);
+        v[2 * k + 3] = (uint32_t) __double2hiint(act ? st[k] : 0.0);
+      }
+      #pragma unroll
+      for (int k = 6 * R + 2; k < 32; ++k) v[k] = 0u;
+      tc_st32(sr.taddr + trip * 32, v);
+    }
+    else if (act)
+    {
+      double * row = sr.base + s * blo_row(R);
+      row[0] = base;
+      #pragma unroll
+      for (int k = 0; k < 3 * R; ++k) row[k + 1] = st[k];
+    }
   }
 }
 
 // Pass A: inner CLV toward the new tip from (D, X); returns the edge log-likelihood new_tip | inner
 // over the window and leaves the pendant sumtable (inner vs tip) in `sum`.
 template <int R, bool GS>
-__device__ __forceinline__ double site_pass_tip(const SiteCtaSmem & cs, const double * ws, double * sum, int gstride,
+__device__ __forceinline__ double site_pass_tip(const SiteCtaSmem & cs, const double * ws, const SumRef & sr,
                                              const double * __restrict__ DT, const double * __restrict__ XT,
                                              const uint32_t * __restrict__ sD, const uint32_t * __restrict__ sX,
                                              const uint8_t * __restrict__ qc, int begin, int w, int lane)
@@ -344,9 +425,12 @@ __device__ __forceinline__ double site_pass_tip(const SiteCtaSmem & cs, const do
   // logarithm per 16 sites of a lane replaces one per site.
   double acc = 0.0, prod = 1.0;
   int esum = 0, ssum = 0, since = 0;
+  const int trips = (w + 31) >> 5;
   #pragma unroll 1
-  for (int s = lane; s < w; s += 32)
+  for (int tr = 0; tr < trips; ++tr)
   {
+    const bool act = lane + 32 * tr < w;
+    const int s = act ? lane + 32 * tr : w - 1;     // lanes beyond the window recompute the last site
     const size_t off = clvt_offset<R>(begin + s);
     const double * dp = DT + off;
     const double * xp = XT + off;
@@ -403,22 +487,26 @@ __device__ __forceinline__ double site_pass_tip(const SiteCtaSmem & cs, const do
         else st[r * 3 + j - 1] = v;
       }
     }
-    site_store_row<R, GS>(sum, gstride, s, base, st);
-    ssum += (int) scal;
-    const int hi = __double2hiint(term);
-    const int ef = (hi >> 20) & 0x7ff;
-    if (hi > 0 && ef != 0 && ef != 0x7ff)
+    site_store_row<R, GS>(sr, tr, s, act, base, st);
+    if (act)
     {
-      prod *= __hiloint2double((hi & 0x800fffff) | 0x3fe00000, __double2loint(term));
-      esum += ef - 1022;
-    }
-    else
-      acc += log(term);                     // zero, denormal, negative or non-finite: plain path
-    if (++since == 16)
-    {
-      acc += log(prod); prod = 1.0; since = 0;
+      ssum += (int) scal;
+      const int hi = __double2hiint(term);
+      const int ef = (hi >> 20) & 0x7ff;
+      if (hi > 0 && ef != 0 && ef != 0x7ff)
+      {
+        prod *= __hiloint2double((hi & 0x800fffff) | 0x3fe00000, __double2loint(term));
+        esum += ef - 1022;
+      }
+      else
+        acc += log(term);                     // zero, denormal, negative or non-finite: plain path
+      if (++since == 16)
+      {
+        acc += log(prod); prod = 1.0; since = 0;
+      }
     }
   }
+  if (!GS && sr.tm) tc_wait_st();
   acc += log(prod) + (double) esum * 0.693147180559945309417 + (double) ssum * EPA_LOG_SCALE_THRESHOLD;
   return warp_sum(acc);
 }
@@ -427,20 +515,23 @@ __device__ __forceinline__ double site_pass_tip(const SiteCtaSmem & cs, const do
 // times the stored eigen-rotated inner CLV, the window log-likelihood is the sum of the
 // preplacement table entries (the same three lengths, the same tiny tree).
 template <int R, bool GS>
-__device__ __forceinline__ double site_pass_first(const SiteCtaSmem & cs, double * sum, int gstride,
+__device__ __forceinline__ double site_pass_first(const SiteCtaSmem & cs, const SumRef & sr,
                                                   const double * __restrict__ GT, const double * __restrict__ lk,
                                                   const uint8_t * __restrict__ qc, int begin, int w, int lane)
 {
   double acc = 0.0;
+  const int trips = (w + 31) >> 5;
   #pragma unroll 1
-  for (int s = lane; s < w; s += 32)
+  for (int tr = 0; tr < trips; ++tr)
   {
+    const bool act = lane + 32 * tr < w;
+    const int s = act ? lane + 32 * tr : w - 1;
     const double * gp = GT + clvt_offset<R>(begin + s);
     double gv[4 * R];
     #pragma unroll
     for (int c = 0; c < 4 * R; ++c) gv[c] = __ldg(gp + (size_t) c * CLVT_BLOCK);
     const int mask = qc[s] & 15;
-    acc += __ldg(lk + (size_t) (begin + s) * 16 + mask);
+    if (act) acc += __ldg(lk + (size_t) (begin + s) * 16 + mask);
     double tl[4];
     lds_vec<4>(cs.tipleft + tv_pos(mask) * 4, tl);
     double base = 0.0;
@@ -452,21 +543,25 @@ __device__ __forceinline__ double site_pass_first(const SiteCtaSmem & cs, double
       #pragma unroll
       for (int j = 1; j < 4; ++j) st[r * 3 + j - 1] = tl[j] * gv[r * 4 + j];
     }
-    site_store_row<R, GS>(sum, gstride, s, base, st);
+    site_store_row<R, GS>(sr, tr, s, act, base, st);
   }
+  if (!GS && sr.tm) tc_wait_st();
   return warp_sum(acc);
 }
 
 // Pass B: inner CLV toward the distal node from (T, X); leaves the distal sumtable (D vs inner)
 template <int R, bool GS>
-__device__ __forceinline__ void site_pass_distal(const double * ws, double * sum, int gstride,
+__device__ __forceinline__ void site_pass_distal(const double * ws, const SumRef & sr,
                                               const double * __restrict__ DT, const double * __restrict__ XT,
                                               const uint8_t * __restrict__ qc, int begin, int w, int lane)
 {
   using L = SiteWarpSmem<R>;
+  const int trips = (w + 31) >> 5;
   #pragma unroll 1
-  for (int s = lane; s < w; s += 32)
+  for (int tr = 0; tr < trips; ++tr)
   {
+    const bool act = lane + 32 * tr < w;
+    const int s = act ? lane + 32 * tr : w - 1;
     const size_t off = clvt_offset<R>(begin + s);
     const double * dp = DT + off;
     const double * xp = XT + off;
@@ -514,8 +609,9 @@ __device__ __forceinline__ void site_pass_distal(const double * ws, double * sum
         else st[r * 3 + j - 1] = v;
       }
     }
-    site_store_row<R, GS>(sum, gstride, s, base, st);
+    site_store_row<R, GS>(sr, tr, s, act, base, st);
   }
+  if (!GS && sr.tm) tc_wait_st();
 }
 
 __device__ __forceinline__ unsigned long long site_next_item(SiteCtaSmem & cs, unsigned long long * counter)
@@ -539,7 +635,7 @@ __device__ __forceinline__ unsigned long long site_next_item(SiteCtaSmem & cs, u
 
 // GS = sumtable in global scratch (windows that do not fit the shared-memory slice)
 template <int R, bool GS>
-__global__ void __launch_bounds__(288, 1)
+__global__ void __launch_bounds__(384, 1)
 blo_site_kernel(BloSiteArgs sa)
 {
   using L = SiteWarpSmem<R>;
@@ -564,11 +660,29 @@ blo_site_kernel(BloSiteArgs sa)
   if (threadIdx.x == 0) { cs.q_next = 0; cs.q_end = 0; cs.q_lock = 0; }
   __syncthreads();
 
-  const size_t per_warp = L::doubles(GS ? 0 : a.wcap);
-  double * ws = smem_d + (size_t) warp * per_warp;
-  const int gstride = GS ? sa.wpad : 0;
-  double * sum = GS ? sa.gscratch + ((size_t) blockIdx.x * n_warps + warp) * (size_t) sa.wpad * blo_row(R)
-                    : ws + L::SUM;
+  // shared memory: the fixed part (matrices, tip vectors, decay tables) of every warp, then the
+  // sumtable rows of the warps that are not TMEM-backed
+  __shared__ uint32_t tmem_slot;
+  const int n_tm = GS ? 0 : sa.n_tmem_warps;
+  if (n_tm > 0 && warp == 0)
+  {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" :: "r"(smem_u32(&tmem_slot)) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  if (n_tm > 0)
+  {
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+  }
+  constexpr size_t FIX = (size_t) L::SUM;
+  double * ws = smem_d + (size_t) warp * FIX;
+  SumRef sr;
+  sr.tm = warp < n_tm ? 1 : 0;
+  sr.taddr = n_tm > 0 ? tmem_slot + ((uint32_t) ((warp & 3) * 32) << 16) + (uint32_t) (warp >> 2) * 256u : 0u;
+  sr.gstride = GS ? sa.wpad : 0;
+  sr.base = GS ? sa.gscratch + ((size_t) blockIdx.x * n_warps + warp) * (size_t) sa.wpad * blo_row(R)
+               : smem_d + (size_t) n_warps * FIX + (size_t) (warp - n_tm) * (size_t) a.wcap * blo_row(R);
   double * ex = ws + L::EX;
 
   for (;;)
@@ -628,10 +742,10 @@ blo_site_kernel(BloSiteArgs sa)
       {
         double new_logl;
         if (first && sa.gT)
-          new_logl = -site_pass_first<R, GS>(cs, sum, gstride, sa.gT + (size_t) e * sa.g_stride,
+          new_logl = -site_pass_first<R, GS>(cs, sr, sa.gT + (size_t) e * sa.g_stride,
                                              sa.lookup + (size_t) e * sa.n_pad * 16, qc, begin, w, lane);
         else
-          new_logl = -site_pass_tip<R, GS>(cs, ws, sum, gstride, DT, XT, sD, sX, qc, begin, w, lane);
+          new_logl = -site_pass_tip<R, GS>(cs, ws, sr, DT, XT, sD, sX, qc, begin, w, lane);
         if (first) { loglikelihood = new_logl; first = false; }
         else
         {
@@ -651,13 +765,13 @@ blo_site_kernel(BloSiteArgs sa)
       }
       else
       {
-        site_pass_distal<R, GS>(ws, sum, gstride, DT, XT, qc, begin, w, lane);
+        site_pass_distal<R, GS>(ws, sr, DT, XT, qc, begin, w, lane);
         xmin = fmin(EPA_MIN_BRLEN / 2.0, original_length / 2.0);
         xmax = original_length - xmin / 10.0;
         xguess = len[0];
         if (xguess < xmin || xguess > xmax) xguess = original_length / 2.0;
       }
-      const double xres = site_newton<R, GS>(sum, gstride, ex, w, lane, xmin, xguess, xmax, xmin / 10.0);
+      const double xres = site_newton<R, GS>(sr, ex, w, lane, xmin, xguess, xmax, xmin / 10.0);
       if (xres > 0.0)
       {
         if (!distal_phase) { len[2] = xres; rebuild = 4u; }
@@ -674,6 +788,13 @@ blo_site_kernel(BloSiteArgs sa)
       a.out[pid] = res;
     }
     __syncwarp();
+  }
+  if (n_tm > 0)
+  {
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0)
+      asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" :: "r"(tmem_slot) : "memory");
   }
 }
 
