@@ -318,3 +318,80 @@ def test_aa_placements_match_reference(synthaa, built):
         except AssertionError as e:
             bad.append(str(e))
     assert not bad, f"{len(bad)} of {len(gold['default']['placements'])} AA queries differ from the reference: {bad[:3]}"
+
+
+# ---------------------------------------------------------------------------------------------
+# Dense chunk: enough begin-sorted queries per tile for the tensor-core preplacement (tcgen05
+# digit GEMM), the single-scan selection with staged candidates, the first-round BLO tables and
+# the TMEM-backed sumtables to be the paths that run. Seeded synthetic data, oracle as the checker.
+# ---------------------------------------------------------------------------------------------
+@pytest.fixture(scope="module")
+def dense(built):
+    ds = built.synth.dataset(T=24, n_sites=400, n_queries=6000, window=120, seed_tree=3, seed_q=4)
+    q = ds["queries"].copy()
+    rng = np.random.default_rng(11)
+    for i in range(0, len(q), 5):                      # interior gaps and N: the fully ambiguous column
+        cols = np.flatnonzero(q[i] != ord("-"))
+        pick = rng.choice(cols[1:-1], size=4, replace=False)
+        q[i, pick[:2]] = ord("-")
+        q[i, pick[2:]] = ord("N")
+    case = helpers.case_from_arrays(ds["newick"], ds["names"], ds["ref"], ds["qnames"], q, ds["model"])
+    ctx = helpers.make_context(case)
+    ctx.build_lookup()
+    case.placer.build_lookup()
+    yield case, ctx
+    ctx.close()
+
+
+def test_dense_chunk_tensor_core_preplace_matches_oracle(dense, built):
+    case, ctx = dense
+    ctx.upload_queries(case.query_rows)
+    l0 = ctx.launch_count()
+    ctx.preplace()
+    got = ctx.get_prescores()
+    sample = list(range(0, len(case.qseqs), 97)) + [1, 5, len(case.qseqs) - 1]
+    want = {qi: case.placer.preplace(case.qseqs[qi]) for qi in sample}
+    for qi in sample:
+        # fixed-point table: 2^-38 per site, see kernels_preplace_mma.cuh (tolerance 1e-11 relative)
+        assert np.allclose(got[qi], want[qi], rtol=1e-11, atol=0), f"prescores of query {qi}"
+    # the same chunk through the shared-memory kernels (tensor-core path switched off per context)
+    import os
+    os.environ["EPA_B200_NO_MMA"] = "1"
+    try:
+        ctx2 = helpers.make_context(case)
+        ctx2.build_lookup()
+    finally:
+        del os.environ["EPA_B200_NO_MMA"]
+    ctx2.upload_queries(case.query_rows)
+    ctx2.preplace()
+    ref = ctx2.get_prescores()
+    assert not np.array_equal(got, ref), "both contexts took the same kernel: the tensor-core path did not run"
+    assert np.allclose(got, ref, rtol=1e-11, atol=0)
+    # candidate sets: staged single-scan selection vs the oracle on its own prescores
+    opts = built.capi.default_options()
+    n_pairs = ctx.select(opts)
+    q, e, _ = ctx.get_pairs(raw=False)
+    assert len(q) == n_pairs
+    mine = {}
+    for qi, ei in zip(q, e):
+        mine.setdefault(int(qi), set()).add(int(ei))
+    for qi in sample:
+        assert mine[qi] == set(case.placer.candidates(want[qi])), f"candidates of query {qi}"
+    ctx2.select(opts)
+    q2, e2, _ = ctx2.get_pairs(raw=False)
+    assert np.array_equal(q, q2) and np.array_equal(e, e2), "candidate lists differ between the two preplacement paths"
+    ctx2.close()
+
+
+def test_dense_chunk_placements_match_oracle(dense, built):
+    case, ctx = dense
+    opts = built.capi.default_options()
+    out, counts = ctx.place_chunk(case.query_rows, opts)
+    for qi in list(range(0, len(case.qseqs), 211)) + [5, 10]:
+        want = case.placer.place(case.qseqs[qi])
+        got = out[qi][:counts[qi]]
+        assert [int(g["branch_id"]) for g in got] == [p.edge for p in want], (qi, got, want)
+        for g, p in zip(got, want):
+            assert abs(g["likelihood"] - p.logl) <= 1e-8 * abs(p.logl), (qi, g, p)
+            assert abs(g["lwr"] - p.lwr) <= 1e-6
+            assert abs(g["pendant_length"] - p.pendant) <= 1e-5 and abs(g["distal_length"] - p.distal) <= 1e-5
