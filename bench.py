@@ -282,7 +282,15 @@ def ours(args):
         for k in ("upload_encode", "select", "collect"):
             kernels[k] = {"ms_per_step": stage_ms[k] / args.steps}
         dom = max(("preplace", "thorough"), key=lambda k: kernels[k]["ms_per_step"])
-        kname = {"preplace": "preplace_kernel", "thorough": "blo_dna_kernel"}[dom]
+        kname = {"preplace": "preplace_mma_kernel", "thorough": "blo_site_kernel"}[dom]
+        # the preplacement kernel is an exact u8 x u8 -> s32 digit GEMM on the tensor cores: useful integer
+        # operations = 2 * queries * (edges * 6 digits) * (window * 4 one-hot columns)
+        pre_ms = kernels["preplace"]["ms_per_step"]
+        if pre_ms > 0:
+            kernels["preplace"]["tensor"] = {
+                "kind": "tcgen05.mma kind::i8 (u8 x u8 -> s32), 128 x 192 x 32",
+                "useful_tops": 2.0 * Q * B * 6 * (4 * w) / (pre_ms / 1e3) / 1e12,
+                "note": "bf16 dense peak in MEASURED_PEAKS.json; the 8-bit integer rate is nominally twice that"}
         n_launch = max(1, (Q + chunk - 1) // chunk)
         roofline = {"kernel": kname, "bound": "hbm", "achieved": kernels[dom]["achieved_gbs"], "peak": peak,
                     "unit": "GB/s", "frac": kernels[dom]["frac"], "traffic": None, "peak_source": peak_src,

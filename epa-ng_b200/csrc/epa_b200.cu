@@ -585,12 +585,20 @@ extern "C" int epa_edge_loglikelihood(epa_ctx * ctx, uint32_t edge, double * log
 // ==============================================================================================
 //  lookup tables
 // ==============================================================================================
+namespace { int ensure_clvT(epa_ctx * ctx); }
+
 extern "C" int epa_build_lookup(epa_ctx * ctx)
 {
   if (!ctx) return EPA_ERR_ARG;
   if (int rc = set_device(ctx)) return rc;
   if (int rc = check_edges_ready(ctx)) return rc;
   const int S = ctx->S, R = ctx->R, K = ctx->K, n = ctx->n;
+  if (S == 4 && (R == 1 || R == 2 || R == 4))
+  {
+    // the DNA lookup kernel reads the site-blocked CLV copy (uses ctx->tmp: must come first)
+    if (int rc = bind_constants(ctx)) return rc;
+    if (int rc = ensure_clvT(ctx)) return rc;
+  }
   const size_t pm = (size_t) R * S * S;
   const uint32_t B = ctx->n_edges;
   const size_t lookup_doubles = (size_t) B * ctx->n_pad * K;
@@ -610,7 +618,20 @@ extern "C" int epa_build_lookup(epa_ctx * ctx)
   if (S == 4) lookup_coltable_kernel<4><<<1, 256, 0, ctx->stream>>>(ctx->d_model, d_pm + (size_t) B * pm, d_col);
   else lookup_coltable_kernel<20><<<1, 256, 0, ctx->stream>>>(ctx->d_model, d_pm + (size_t) B * pm, d_col);
   LAUNCHED(ctx);
-  if (S == 4 && R == 4)
+  if (S == 4 && (R == 1 || R == 2 || R == 4) && !getenv("EPA_B200_OLD_LOOKUP"))
+  {
+    // lane = site kernel over the site-blocked CLV copy
+    const size_t t_stride = clvt_node_stride(n, R);
+    dim3 grid(B, (n + 127) / 128);
+    switch (R)
+    {
+      case 1: lookup_build_site_kernel<1><<<grid, 128, 0, ctx->stream>>>(ctx->d_model, ctx->d_clvT, t_stride, ctx->tree.scaler, n, ctx->n_pad, ctx->d_edges, d_pm, d_col, ctx->d_lookup); break;
+      case 2: lookup_build_site_kernel<2><<<grid, 128, 0, ctx->stream>>>(ctx->d_model, ctx->d_clvT, t_stride, ctx->tree.scaler, n, ctx->n_pad, ctx->d_edges, d_pm, d_col, ctx->d_lookup); break;
+      default: lookup_build_site_kernel<4><<<grid, 128, 0, ctx->stream>>>(ctx->d_model, ctx->d_clvT, t_stride, ctx->tree.scaler, n, ctx->n_pad, ctx->d_edges, d_pm, d_col, ctx->d_lookup); break;
+    }
+    LAUNCHED(ctx);
+  }
+  else if (S == 4 && R == 4)
   {
     dim3 grid(B, (n + LOOKUP_DNA_SITES_PER_BLOCK - 1) / LOOKUP_DNA_SITES_PER_BLOCK);
     lookup_build_dna_kernel<<<grid, 256, 0, ctx->stream>>>(ctx->d_model, ctx->tree, n, ctx->n_pad, ctx->d_edges, d_pm, d_col, ctx->d_lookup);

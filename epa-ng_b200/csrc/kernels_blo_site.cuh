@@ -212,6 +212,93 @@ __device__ __forceinline__ size_t clvt_offset(int abs_site)
   return (size_t) (abs_site >> 5) * (size_t) (R * 4 * CLVT_BLOCK) + (size_t) (abs_site & 31);
 }
 
+// ---------------------------------------------------------------------------------------------
+// DNA lookup build, lane = site over the site-blocked CLV copy (rows 2-3 of the scope table:
+// Tiny_Tree ctor src/tree/Tiny_Tree.cpp:84-128 + precompute_sites_static :18-46):
+//   inner[r][i] = (P(len/2) D)[r][i] * (P(len/2) X)[r][i]          (+ per-site scaling)
+//   lookup[e][s][c] = log( sum_r w_r sum_i inner[r][i] M[r][c][i] ) + scaler * log(2^-256), column 0 = zero
+// A warp reads 256 contiguous bytes per CLV component, keeps the whole site in registers (no
+// shuffles), reads the transition matrix and the column table as warp-uniform 128-bit
+// shared-memory broadcasts, and every lane writes its site's 128-byte table row.
+// grid = (n_edges, ceil(n / 128)), block = 128.
+// ---------------------------------------------------------------------------------------------
+template <int R>
+__global__ void __launch_bounds__(128)
+lookup_build_site_kernel(const DevModel * __restrict__ m, const double * __restrict__ clvT, size_t t_stride,
+                         const uint32_t * __restrict__ scaler, int n, int n_pad,
+                         const EdgeDev * __restrict__ edges, const double * __restrict__ pmats_half,
+                         const double * __restrict__ coltab, double * __restrict__ lookup)
+{
+  constexpr int K = 16, C = 4 * R;
+  __shared__ __align__(16) double P[R * 16];
+  __shared__ __align__(16) double M[K * C];          // [c][r][i]
+  __shared__ double wts[R];
+  const EdgeDev e = edges[blockIdx.x];
+  for (int i = threadIdx.x; i < R * 16; i += blockDim.x) P[i] = __ldg(pmats_half + (size_t) blockIdx.x * R * 16 + i);
+  for (int idx = threadIdx.x; idx < K * C; idx += blockDim.x)
+  {
+    const int c = idx / C, r = (idx / 4) % R, i = idx & 3;
+    M[idx] = __ldg(coltab + (r * K + c) * 4 + i);
+  }
+  if (threadIdx.x < R) wts[threadIdx.x] = m->weights[threadIdx.x];
+  __syncthreads();
+  const int site = blockIdx.y * 128 + threadIdx.x;
+  const bool active = site < n;
+  const int s = active ? site : n - 1;
+  const size_t off = clvt_offset<R>(s);
+  const double * dp = clvT + (size_t) e.distal * t_stride + off;
+  const double * xp = clvT + (size_t) e.proximal * t_stride + off;
+  uint32_t sc = __ldg(scaler + (size_t) e.distal * n + s) + __ldg(scaler + (size_t) e.proximal * n + s);
+  double in[C];
+  bool small = true;
+  #pragma unroll
+  for (int r = 0; r < R; ++r)
+  {
+    double dv[4], xv[4];
+    #pragma unroll
+    for (int k = 0; k < 4; ++k) { dv[k] = __ldg(dp + (size_t) (r * 4 + k) * CLVT_BLOCK); xv[k] = __ldg(xp + (size_t) (r * 4 + k) * CLVT_BLOCK); }
+    #pragma unroll
+    for (int i = 0; i < 4; ++i)
+    {
+      double p[4];
+      lds_vec<4>(P + r * 16 + i * 4, p);
+      const double ta = p[0] * dv[0] + p[1] * dv[1] + p[2] * dv[2] + p[3] * dv[3];
+      const double tb = p[0] * xv[0] + p[1] * xv[1] + p[2] * xv[2] + p[3] * xv[3];
+      in[r * 4 + i] = ta * tb;
+      small = small && (in[r * 4 + i] < EPA_SCALE_THRESHOLD);
+    }
+  }
+  if (small)
+  {
+    sc += 1;
+    #pragma unroll
+    for (int c = 0; c < C; ++c) in[c] *= EPA_SCALE_FACTOR;
+  }
+  const double scale_term = sc ? (double) sc * EPA_LOG_SCALE_THRESHOLD : 0.0;
+  double * out = lookup + ((size_t) blockIdx.x * n_pad + s) * K;
+  #pragma unroll
+  for (int c2 = 0; c2 < K; c2 += 2)
+  {
+    double res[2];
+    #pragma unroll
+    for (int cc = 0; cc < 2; ++cc)
+    {
+      const int c = c2 + cc;
+      double term = 0.0;
+      #pragma unroll
+      for (int r = 0; r < R; ++r)
+      {
+        double mv[4];
+        lds_vec<4>(M + c * C + r * 4, mv);
+        const double tr = in[r * 4] * mv[0] + in[r * 4 + 1] * mv[1] + in[r * 4 + 2] * mv[2] + in[r * 4 + 3] * mv[3];
+        term += tr * wts[r];
+      }
+      res[cc] = c == 0 ? 0.0 : log(term) + scale_term;          // column 0 = zero column
+    }
+    if (active) *reinterpret_cast<double2 *>(out + c2) = make_double2(res[0], res[1]);
+  }
+}
+
 // 1/x for positive normal x (a site likelihood): hardware seed + two Newton steps, no slow-path
 // branch, so that the compiler can interleave the reciprocals of several sites. Within 1 ulp.
 __device__ __forceinline__ double fast_rcp(double x)
