@@ -498,6 +498,13 @@ __device__ __forceinline__ void site_store_row(const SumRef & sr, int trip, int 
   }
 }
 
+// The CLV updates of the reference rescale a site by 2^256 when all of its entries drop below
+// 2^-256 (LP/core_partials.c:690-766). Inside the tiny tree that only protects later products from
+// underflow: the derivative sums are ratios of per-site sums (scale free) and the site
+// log-likelihood adds back exactly what the scaling took out. The entries here are products of
+// two scaled CLV values and transition probabilities, far above the double range's lower end, so
+// the passes below skip the rescaling; results agree with the rescaled arithmetic to rounding.
+
 // Pass A: inner CLV toward the new tip from (D, X); returns the edge log-likelihood new_tip | inner
 // over the window and leaves the pendant sumtable (inner vs tip) in `sum`.
 template <int R, bool GS>
@@ -526,9 +533,8 @@ __device__ __forceinline__ double site_pass_tip(const SiteCtaSmem & cs, const do
     for (int c = 0; c < 4 * R; ++c) { dv[c] = __ldg(dp + (size_t) c * CLVT_BLOCK); xv[c] = __ldg(xp + (size_t) c * CLVT_BLOCK); }
     const int mask = qc[s] & 15;
     const int pos = tv_pos(mask);
-    uint32_t scal = __ldg(sD + s) + __ldg(sX + s);
+    const uint32_t scal = __ldg(sD + s) + __ldg(sX + s);
     double in[4 * R];
-    bool small = true;
     #pragma unroll
     for (int r = 0; r < R; ++r)
     {
@@ -541,14 +547,7 @@ __device__ __forceinline__ double site_pass_tip(const SiteCtaSmem & cs, const do
         const double ta = pd[0] * dv[r * 4] + pd[1] * dv[r * 4 + 1] + pd[2] * dv[r * 4 + 2] + pd[3] * dv[r * 4 + 3];
         const double tb = pp[0] * xv[r * 4] + pp[1] * xv[r * 4 + 1] + pp[2] * xv[r * 4 + 2] + pp[3] * xv[r * 4 + 3];
         in[r * 4 + i] = ta * tb;
-        small = small && (in[r * 4 + i] < EPA_SCALE_THRESHOLD);
       }
-    }
-    if (small)
-    {
-      #pragma unroll
-      for (int c = 0; c < 4 * R; ++c) in[c] *= EPA_SCALE_FACTOR;
-      scal += 1;
     }
     double tl[4];
     lds_vec<4>(cs.tipleft + pos * 4, tl);
@@ -658,7 +657,6 @@ __device__ __forceinline__ void site_pass_distal(const double * ws, const SumRef
     const int pos = tv_pos(qc[s] & 15);
     const double * tvp = ws + L::TV + pos * L::TVS;
     double in[4 * R];
-    bool small = true;
     #pragma unroll
     for (int r = 0; r < R; ++r)
     {
@@ -671,13 +669,7 @@ __device__ __forceinline__ void site_pass_distal(const double * ws, const SumRef
         lds_vec<4>(ws + L::P_P + r * 16 + i * 4, pp);
         const double tb = pp[0] * xv[r * 4] + pp[1] * xv[r * 4 + 1] + pp[2] * xv[r * 4 + 2] + pp[3] * xv[r * 4 + 3];
         in[r * 4 + i] = tp[i] * tb;
-        small = small && (in[r * 4 + i] < EPA_SCALE_THRESHOLD);
       }
-    }
-    if (small)
-    {
-      #pragma unroll
-      for (int c = 0; c < 4 * R; ++c) in[c] *= EPA_SCALE_FACTOR;
     }
     double base = 0.0;
     double st[3 * R];
