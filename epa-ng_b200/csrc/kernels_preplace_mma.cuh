@@ -158,7 +158,21 @@ __device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&v)[32])
                  "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
                : "r"(taddr) : "memory");
 }
+__device__ __forceinline__ void tc_ld16(uint32_t taddr, uint32_t (&v)[16])
+{
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+               "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                 "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+               : "r"(taddr) : "memory");
+}
 __device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// 256-bit store: one full 32-byte sector per lane
+__device__ __forceinline__ void st_global_v4(double * p, double a, double b, double c, double d)
+{
+  asm volatile("st.global.v4.f64 [%0], {%1, %2, %3, %4};" :: "l"(p), "d"(a), "d"(b), "d"(c), "d"(d) : "memory");
+}
 
 struct PreMmaArgs {
   const uint8_t * btab;        // [n_eb][kc_total][192][16]
@@ -322,64 +336,85 @@ preplace_mma_kernel(PreMmaArgs a)
       double * out = a.pre + (size_t) (q == 0xffffffffu ? 0u : q) * a.pre_stride + half * 16;
       uint32_t bi = blk_it;
       double rmax = -INFINITY;
-      // prefix-sum term of the block's 16 branches, loaded one block ahead
-      double base[16];
-      #pragma unroll
-      for (int j = 0; j < 8; ++j)
+      // A block is drained in two steps of 8 branches (48 accumulator columns). The prefix-sum rows
+      // of a step are requested one step ahead into one of two register buffers (raw values: the
+      // subtraction waits until they are used, so the loads stay in flight behind the tensor work).
+      struct PnBuf { double2 hi[4], lo[4]; };
+      auto load_pn = [&](PnBuf & b, uint32_t eb, int sub)
       {
-        const double2 hi = __ldg(pne + j), lo2 = __ldg(pnb + j);
-        base[2 * j] = hi.x - lo2.x; base[2 * j + 1] = hi.y - lo2.y;
-      }
+        #pragma unroll
+        for (int j = 0; j < 4; ++j)
+        {
+          b.hi[j] = __ldg(pne + (size_t) eb * 16 + sub * 4 + j);
+          b.lo[j] = __ldg(pnb + (size_t) eb * 16 + sub * 4 + j);
+        }
+      };
+      auto finish = [&](const PnBuf & b, const uint32_t (&v0)[32], const uint32_t (&v1)[16], uint32_t e0, double * dst)
+      {
+        double res[8];
+        #pragma unroll
+        for (int j = 0; j < 8; ++j)
+        {
+          unsigned long long sum = 0;
+          #pragma unroll
+          for (int p = 0; p < MMA_P; ++p)
+          {
+            const int c = j * MMA_P + p;
+            const uint32_t d = c < 32 ? v0[c] : v1[c - 32];
+            sum += (unsigned long long) d << (8 * p);
+          }
+          const double base = (j & 1) == 0 ? b.hi[j / 2].x - b.lo[j / 2].x : b.hi[j / 2].y - b.lo[j / 2].y;
+          res[j] = base - (double) sum * (1.0 / (double) (1ull << MMA_FRAC));
+        }
+        if (q != 0xffffffffu)
+        {
+          #pragma unroll
+          for (int j = 0; j < 8; j += 4)
+          {
+            if (e0 + j + 3 < a.n_edges)
+            {
+              st_global_v4(dst + j, res[j], res[j + 1], res[j + 2], res[j + 3]);
+              rmax = fmax(fmax(rmax, fmax(res[j], res[j + 1])), fmax(res[j + 2], res[j + 3]));
+            }
+            else
+            {
+              #pragma unroll
+              for (int k = 0; k < 4; ++k)
+                if (e0 + j + k < a.n_edges) { dst[j + k] = res[j + k]; rmax = fmax(rmax, res[j + k]); }
+            }
+          }
+        }
+      };
+      auto drain = [&](const PnBuf & b, uint32_t taddr, uint32_t e0, double * dst)
+      {
+        uint32_t v0[32], v1[16];
+        tc_ld32(taddr, v0);
+        tc_ld16(taddr + 32, v1);
+        tc_wait_ld();
+        finish(b, v0, v1, e0, dst);
+      };
+      PnBuf bufA, bufB;
+      load_pn(bufA, 0, 0);
       for (uint32_t eb = 0; eb < a.n_eb; ++eb, ++bi)
       {
         const uint32_t acc = bi & 1u, use_acc = bi >> 1;
         const uint32_t taddr = tmem_base + ((uint32_t) (quarter * 32) << 16) + acc * 256u + half * 96;
-        double cur[16];
-        #pragma unroll
-        for (int j = 0; j < 16; ++j) cur[j] = base[j];
-        if (eb + 1 < a.n_eb)
-        {
-          #pragma unroll
-          for (int j = 0; j < 8; ++j)
-          {
-            const double2 hi = __ldg(pne + (size_t) (eb + 1) * 16 + j), lo2 = __ldg(pnb + (size_t) (eb + 1) * 16 + j);
-            base[2 * j] = hi.x - lo2.x; base[2 * j + 1] = hi.y - lo2.y;
-          }
-        }
+        const uint32_t e0 = eb * MMA_EB + half * 16;
+        load_pn(bufB, eb, 1);
         mbar_wait(&tfull[acc], use_acc & 1u);
         tc_fence_after();
-        uint32_t v0[32], v1[32], v2[32];
-        tc_ld32(taddr, v0);
-        tc_ld32(taddr + 32, v1);
-        tc_ld32(taddr + 64, v2);
-        tc_wait_ld();
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&tempty[acc]);          // accumulator values are in registers
-        const uint32_t e0 = eb * MMA_EB + half * 16;
-        #pragma unroll
-        for (int j = 0; j < 16; j += 2)
+        drain(bufA, taddr, e0, out + (size_t) eb * MMA_EB);
+        if (eb + 1 < a.n_eb) load_pn(bufA, eb + 1, 0);
         {
-          double res[2];
-          #pragma unroll
-          for (int jj = 0; jj < 2; ++jj)
-          {
-            unsigned long long sum = 0;
-            #pragma unroll
-            for (int p = 0; p < MMA_P; ++p)
-            {
-              const int c = (j + jj) * MMA_P + p;
-              const uint32_t d = c < 32 ? v0[c] : (c < 64 ? v1[c - 32] : v2[c - 64]);
-              sum += (unsigned long long) d << (8 * p);
-            }
-            res[jj] = cur[j + jj] - (double) sum * (1.0 / (double) (1ull << MMA_FRAC));
-          }
-          if (q != 0xffffffffu)
-          {
-            double * dst = out + (size_t) eb * MMA_EB + j;
-            if (e0 + j + 1 < a.n_edges) { *reinterpret_cast<double2 *>(dst) = make_double2(res[0], res[1]); rmax = fmax(rmax, fmax(res[0], res[1])); }
-            else if (e0 + j < a.n_edges) { dst[0] = res[0]; rmax = fmax(rmax, res[0]); }
-          }
+          // second step: after its accumulator columns are in registers the block is handed back
+          uint32_t v0[32], v1[16];
+          tc_ld32(taddr + 48, v0);
+          tc_ld16(taddr + 80, v1);
+          tc_wait_ld();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tempty[acc]);
+          finish(bufB, v0, v1, e0 + 8, out + (size_t) eb * MMA_EB + 8);
         }
       }
       row_max[half][r] = rmax;

@@ -464,6 +464,7 @@ void orc_sumtable(const orc_model_t * m, int n, const orc_side_t * parent,
 
 /* diagnostic counter (tools/blo_stats.py): derivative evaluations since the last reset */
 unsigned long long orc_stat_deriv_calls = 0;
+unsigned long long orc_stat_clamped = 0, orc_stat_nr_calls = 0, orc_stat_nr_hist[40] = {0};
 
 void orc_derivatives(const orc_model_t * m, int n, const double * sumtable, double t,
                      double * df, double * ddf)
@@ -522,8 +523,10 @@ static double orc_newton(double xmin, double xguess, double xmax, double tol, in
   double xl = xmin, xh = xmax;
   const double dxmax = xmax / max_iters;
   int iter = 0;
+  ++orc_stat_nr_calls;
   for (;;)
   {
+    if (iter < 40) orc_stat_nr_hist[iter]++;
     if (iter++ > max_iters) return 0.0;
     double f, df;
     orc_derivatives(ctx->m, ctx->n, ctx->sumtable, x, &f, &df);
@@ -537,6 +540,7 @@ static double orc_newton(double xmin, double xguess, double xmax, double tol, in
     }
     else
       dx = -1 * f / fabs(df);
+    if (fabs(dx) > dxmax) ++orc_stat_clamped;
     dx = fmax(fmin(dx, dxmax), -dxmax);
     if (x + dx < xl) dx = xl - x;
     if (x + dx > xh) dx = xh - x;

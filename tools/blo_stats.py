@@ -30,3 +30,6 @@ print("pairs", len(rounds), "cand/query", np.mean(ncand))
 print("rounds mean %.2f hist %s" % (rounds.mean(), np.bincount(rounds)))
 print("deriv evals/pair mean %.1f median %.0f p90 %.0f max %d; per round %.1f" % (evals.mean(), np.median(evals), np.percentile(evals, 90), evals.max(), evals.sum() / rounds.sum()))
 print("restored", restored)
+H = (C.c_ulonglong * 40).in_dll(orc.lib(), "orc_stat_nr_hist")
+print("nr calls", C.c_ulonglong.in_dll(orc.lib(), "orc_stat_nr_calls").value, "clamped steps", C.c_ulonglong.in_dll(orc.lib(), "orc_stat_clamped").value)
+print("evals reaching iteration k:", list(H)[:34])
