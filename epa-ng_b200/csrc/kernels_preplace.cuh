@@ -479,11 +479,17 @@ select_count_kernel(const double * __restrict__ pre, size_t pre_stride, int n_ed
   const bool fast = fast_ok && mode == 0;
   double tot = 0.0;
   int nl = 0;
+  #pragma unroll 4
   for (int base = 0; base < n_edges; base += 32)
   {
     const int b = base + lane;
     double v = -INFINITY;
-    if (b < n_edges) { v = row[b]; tot += exp(v - mx); }
+    if (b < n_edges)
+    {
+      v = row[b];
+      // exp(-60) = 8.8e-27: thousands of such terms cannot reach half an ulp of a sum that holds exp(0)
+      if (v - mx > -60.0) tot += exp(v - mx);
+    }
     if (fast)
     {
       const bool near = v > mx - SEL_CUT;
