@@ -892,23 +892,20 @@ extern "C" int epa_preplace(epa_ctx * ctx)
   CU(ctx->qmax.ensure(nq * sizeof(double)));
   CU(cudaEventRecord(ctx->ev[1], ctx->stream));
   CU(cudaMemsetAsync(ctx->qmax.p, 0xff, nq * sizeof(double), ctx->stream));      // NaN = no row maximum recorded
-  // simple DNA queries (sorted first) take the tensor-core kernel (tile windows of at most
-  // MMA_KC_MAX * 4 sites) or else the pair-table kernel; the rest take the per-site kernel
+  // simple DNA queries (sorted first) take the tensor-core kernel (the pair-table kernel when the
+  // digit table could not be built); the rest take the per-site kernel
   const uint32_t nA = ctx->d_pairtab ? ctx->n_simple : 0u, nB = nq - nA;
   const uint32_t tilesM = (nA + MMA_TQ - 1) / MMA_TQ;
   const uint32_t tilesA = (nA + kPairTQ - 1) / kPairTQ, tilesB = (nB + kPreplaceTQ - 1) / kPreplaceTQ;
   CU(ctx->range.ensure((size_t) (std::max(tilesA, tilesM) + tilesB) * sizeof(int2)));
   int2 * rangeB = ctx->range.as<int2>() + std::max(tilesA, tilesM);
-  bool use_mma = ctx->mma_ok && nA > 0 && ctx->max_span <= MMA_KC_MAX * 4;
+  const bool use_mma = ctx->mma_ok && nA > 0;
   int flags[8];
   if (use_mma)
   {
-    CU(cudaMemsetAsync(ctx->d_flags + 2, 0, sizeof(int), ctx->stream));
     tile_range_kernel<<<(tilesM + 7) / 8, 256, 0, ctx->stream>>>(ctx->perm.as<uint32_t>(), ctx->begin.as<int>(), ctx->span.as<int>(),
                                                               nA, MMA_TQ, tilesM, 4, ctx->range.as<int2>(), ctx->d_flags + 2);
     LAUNCHED(ctx);
-    if (int rc = read_flags(ctx, flags)) return rc;
-    use_mma = flags[2] <= MMA_KC_MAX * 4;
   }
   CU(cudaMemsetAsync(ctx->d_flags + 5, 0, sizeof(int), ctx->stream));
   if (nA && !use_mma)

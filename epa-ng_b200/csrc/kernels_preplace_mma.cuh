@@ -233,10 +233,8 @@ preplace_mma_kernel(PreMmaArgs a)
   for (uint32_t tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x)
   {
     const int2 rg = a.range[tile];
-    const int lo = rg.x, hi = rg.y;
-    const int nkc = (hi - lo + 3) >> 2;                                  // K chunks that hold real sites
-    const int n_ks = (nkc + MMA_KC_STAGE - 1) / MMA_KC_STAGE;            // table stages per block
-    const int kc0 = lo >> 2;
+    const int nkc_all = (rg.y - rg.x + 3) >> 2;                          // K chunks that hold real sites
+    const int n_pass = max(1, (nkc_all + MMA_KC_MAX - 1) / MMA_KC_MAX);  // windows wider than the A tile: K is split
     if (tid < MMA_TQ)
     {
       const uint32_t slot = tile * MMA_TQ + tid;
@@ -246,6 +244,14 @@ preplace_mma_kernel(PreMmaArgs a)
       row_q[tid] = valid ? q : 0xffffffffu; row_b[tid] = b; row_e[tid] = b + w;
     }
     __syncthreads();
+   for (int pass = 0; pass < n_pass; ++pass)
+   {
+    // pass p covers sites [lo, lo + 4 nkc): later passes add to the scores the earlier ones wrote
+    const int lo = rg.x + pass * MMA_KC_MAX * 4;
+    const int nkc = min(MMA_KC_MAX, nkc_all - pass * MMA_KC_MAX);
+    const int n_ks = (nkc + MMA_KC_STAGE - 1) / MMA_KC_STAGE;            // table stages per block
+    const int kc0 = lo >> 2;
+    const bool first_pass = pass == 0, last_pass = pass == n_pass - 1;
     // ---- one-hot operand: chunk kc of row r = 4 sites x 4 state bytes
     for (int idx = tid; idx < n_ks * MMA_KC_STAGE * MMA_TQ; idx += MMA_THREADS)
     {
@@ -335,18 +341,32 @@ preplace_mma_kernel(PreMmaArgs a)
       const double2 * __restrict__ pne = reinterpret_cast<const double2 *>(a.pn + (size_t) row_e[r] * e_pad + half * 16);
       double * out = a.pre + (size_t) (q == 0xffffffffu ? 0u : q) * a.pre_stride + half * 16;
       uint32_t bi = blk_it;
-      double rmax = -INFINITY;
+      double rmax = -INFINITY;     // only the last pass sees final scores
       // A block is drained in two steps of 8 branches (48 accumulator columns). The prefix-sum rows
       // of a step are requested one step ahead into one of two register buffers (raw values: the
       // subtraction waits until they are used, so the loads stay in flight behind the tensor work).
       struct PnBuf { double2 hi[4], lo[4]; };
       auto load_pn = [&](PnBuf & b, uint32_t eb, int sub)
       {
-        #pragma unroll
-        for (int j = 0; j < 4; ++j)
+        if (first_pass)
         {
-          b.hi[j] = __ldg(pne + (size_t) eb * 16 + sub * 4 + j);
-          b.lo[j] = __ldg(pnb + (size_t) eb * 16 + sub * 4 + j);
+          #pragma unroll
+          for (int j = 0; j < 4; ++j)
+          {
+            b.hi[j] = __ldg(pne + (size_t) eb * 16 + sub * 4 + j);
+            b.lo[j] = __ldg(pnb + (size_t) eb * 16 + sub * 4 + j);
+          }
+        }
+        else
+        {
+          // read-modify-write of this thread's own scores of the previous pass
+          const double2 * prev = reinterpret_cast<const double2 *>(out + (size_t) eb * MMA_EB + sub * 8);
+          #pragma unroll
+          for (int j = 0; j < 4; ++j)
+          {
+            b.hi[j] = q != 0xffffffffu ? prev[j] : make_double2(0.0, 0.0);
+            b.lo[j] = make_double2(0.0, 0.0);
+          }
         }
       };
       auto finish = [&](const PnBuf & b, const uint32_t (&v0)[32], const uint32_t (&v1)[16], uint32_t e0, double * dst)
@@ -421,8 +441,9 @@ preplace_mma_kernel(PreMmaArgs a)
     }
     stage_it += a.n_eb * (uint32_t) n_ks;
     blk_it += a.n_eb;
-    __syncthreads();           // the epilogue of the last block implies every MMA of the tile is done
-    if (tid < MMA_TQ && row_q[tid] != 0xffffffffu) a.qmax[row_q[tid]] = fmax(row_max[0][tid], row_max[1][tid]);
+    __syncthreads();           // the epilogue of the last block implies every MMA of the pass is done
+    if (last_pass && tid < MMA_TQ && row_q[tid] != 0xffffffffu) a.qmax[row_q[tid]] = fmax(row_max[0][tid], row_max[1][tid]);
+   }
   }
 
   tc_fence_before();
