@@ -12,7 +12,7 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libepa_b200.so")
+LIB_PATH = os.environ.get("EPA_B200_LIB") or os.path.join(HERE, "libepa_b200.so")   # override: developer A/B builds
 
 EPA_OK, EPA_ERR_ARG, EPA_ERR_CUDA, EPA_ERR_NOMEM, EPA_ERR_STATE, EPA_ERR_QUERY = 0, -1, -2, -3, -4, -5
 EPA_FLAG_RATE_SCALERS = 1

@@ -312,6 +312,19 @@ __device__ __forceinline__ double fast_rcp(double x)
   return fma(r, e, r);
 }
 
+// sums two values over the warp with one butterfly: after the first exchange the low half-warp
+// carries the first value, the high half-warp the second (fixed order: every lane gets the same bits)
+__device__ __forceinline__ void warp_sum2(double & a, double & b, int lane)
+{
+  const bool hi = lane >= 16;
+  const double send = hi ? a : b, keep = hi ? b : a;
+  double v = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+  #pragma unroll
+  for (int o = 8; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  a = __shfl_sync(0xffffffffu, v, 0);
+  b = __shfl_sync(0xffffffffu, v, 16);
+}
+
 // derivative sums over the window, lane = site (LP/core_derivatives.c:643-858)
 template <int R, bool GS>
 __device__ __forceinline__ void site_derivatives(const SumRef & sr, double * ex, int w, double t,
@@ -419,8 +432,9 @@ __device__ __forceinline__ void site_derivatives(const SumRef & sr, double * ex,
     const double g1a = -c1a * ia;
     if (va) { a1 += g1a; a2 += g1a * g1a - c2a * ia; }
   }
-  f = warp_sum(a1);
-  df = warp_sum(a2);
+  warp_sum2(a1, a2, lane);
+  f = a1;
+  df = a2;
 }
 
 // bounded Newton-Raphson, PM/optimize/opt_algorithms.c:133-262; returns 0.0 on failure
