@@ -68,6 +68,8 @@ SYMBOLS = [
     ("epa_place_chunk", C.c_int, [_vp, _vp, C.c_uint32, C.POINTER(Options), _vp, _u32p]),
     ("epa_upload_queries", C.c_int, [_vp, _vp, C.c_uint32, C.c_int]),
     ("epa_hint_next_chunk", C.c_int, [_vp, _vp, C.c_uint32]),
+    ("epa_set_deferred_results", C.c_int, [_vp, C.c_int]),
+    ("epa_wait_results", C.c_int, [_vp]),
     ("epa_encode_queries_dev", C.c_int, [_vp, _vp, C.c_uint32, C.c_int]),
     ("epa_preplace", C.c_int, [_vp]),
     ("epa_select", C.c_int, [_vp, C.POINTER(Options), C.POINTER(C.c_uint64)]),

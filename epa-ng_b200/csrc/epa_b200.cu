@@ -94,6 +94,12 @@ struct epa_ctx {
   cudaStream_t copy_stream = nullptr;
   cudaEvent_t ev_copy = nullptr;
   DevBuf raw_next;
+  // device -> host copies of the placement records also run on the copy stream, from two
+  // alternating device buffers, so that they can overlap the next chunk (epa_set_deferred_results)
+  DevBuf out_rec2, out_cnt2;
+  cudaEvent_t ev_collect = nullptr, ev_d2h[2] = {nullptr, nullptr};
+  int out_flip = 0;
+  bool defer_results = false;
   const char * hint_ptr = nullptr; uint32_t hint_n = 0;         // announced next chunk
   const char * staged_ptr = nullptr; uint32_t staged_n = 0;     // chunk whose copy into raw_next is in flight
   int * d_flags = nullptr;              // [0..1] error, [2] max tile width, [3] max span
@@ -252,9 +258,11 @@ extern "C" void epa_ctx_destroy(epa_ctx * ctx)
                      &ctx->edge_hist, &ctx->edge_off, &ctx->work, &ctx->res, &ctx->out_rec, &ctx->out_cnt,
                      &ctx->scratch, &ctx->tmp, &ctx->qmax, &ctx->cand};
   for (DevBuf * b : bufs) b->release();
-  ctx->raw_next.release();
+  ctx->raw_next.release(); ctx->out_rec2.release(); ctx->out_cnt2.release();
   if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
   if (ctx->ev_copy) cudaEventDestroy(ctx->ev_copy);
+  if (ctx->ev_collect) cudaEventDestroy(ctx->ev_collect);
+  for (auto & e : ctx->ev_d2h) if (e) cudaEventDestroy(e);
   cudaFree(ctx->d_model); cudaFree(ctx->tree.clv); cudaFree(ctx->tree.scaler); cudaFree(ctx->d_edges);
   cudaFree(ctx->d_lookup); cudaFree(ctx->d_pairtab); cudaFree(ctx->d_clvT); cudaFree(ctx->d_gT); cudaFree(ctx->d_btab); cudaFree(ctx->d_pn); cudaFree(ctx->d_flags); cudaFree(ctx->d_counter); cudaFree(ctx->d_total);
   for (auto & e : ctx->ev) if (e) cudaEventDestroy(e);
@@ -719,6 +727,16 @@ static int read_flags(epa_ctx * ctx, int flags[8])
   return EPA_OK;
 }
 
+static int ensure_copy_stream(epa_ctx * ctx)
+{
+  if (ctx->copy_stream) return EPA_OK;
+  CU(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+  CU(cudaEventCreateWithFlags(&ctx->ev_copy, cudaEventDisableTiming));
+  CU(cudaEventCreateWithFlags(&ctx->ev_collect, cudaEventDisableTiming));
+  for (auto & e : ctx->ev_d2h) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  return EPA_OK;
+}
+
 extern "C" int epa_upload_queries(epa_ctx * ctx, const char * seqs, uint32_t n_queries, int premasking)
 {
   if (!ctx) return EPA_ERR_ARG;
@@ -749,11 +767,7 @@ extern "C" int epa_upload_queries(epa_ctx * ctx, const char * seqs, uint32_t n_q
   if (rc == EPA_OK && ctx->hint_ptr && ctx->hint_n)
   {
     // start the copy of the announced next chunk; it overlaps the placement of this one
-    if (!ctx->copy_stream)
-    {
-      CU(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
-      CU(cudaEventCreateWithFlags(&ctx->ev_copy, cudaEventDisableTiming));
-    }
+    if (int rc2 = ensure_copy_stream(ctx)) return rc2;
     const size_t nbytes = (size_t) ctx->hint_n * ctx->n;
     CU(ctx->raw_next.ensure(nbytes));
     CU(cudaMemcpyAsync(ctx->raw_next.p, ctx->hint_ptr, nbytes, cudaMemcpyHostToDevice, ctx->copy_stream));
@@ -762,6 +776,21 @@ extern "C" int epa_upload_queries(epa_ctx * ctx, const char * seqs, uint32_t n_q
   }
   ctx->hint_ptr = nullptr; ctx->hint_n = 0;
   return rc;
+}
+
+extern "C" int epa_set_deferred_results(epa_ctx * ctx, int on)
+{
+  if (!ctx) return EPA_ERR_ARG;
+  ctx->defer_results = on != 0;
+  return EPA_OK;
+}
+
+extern "C" int epa_wait_results(epa_ctx * ctx)
+{
+  if (!ctx) return EPA_ERR_ARG;
+  if (int rc = set_device(ctx)) return rc;
+  if (ctx->copy_stream) CU(cudaStreamSynchronize(ctx->copy_stream));
+  return EPA_OK;
 }
 
 extern "C" int epa_hint_next_chunk(epa_ctx * ctx, const char * next_seqs, uint32_t next_n_queries)
@@ -1213,10 +1242,17 @@ static int collect_impl(epa_ctx * ctx, const epa_options * opts, epa_placement *
   const uint32_t nq = ctx->nq;
   if (nq == 0) return EPA_OK;
   if (to_device && (!out || !out_counts)) return fail(ctx, EPA_ERR_ARG, "null device output");
+  DevBuf & rec_buf = ctx->out_flip ? ctx->out_rec2 : ctx->out_rec;
+  DevBuf & cnt_buf = ctx->out_flip ? ctx->out_cnt2 : ctx->out_cnt;
   if (!to_device)
   {
-    CU(ctx->out_rec.ensure((size_t) nq * opts->filter_max * sizeof(PlacementRec)));
-    CU(ctx->out_cnt.ensure(nq * sizeof(uint32_t)));
+    if (int rc = ensure_copy_stream(ctx)) return rc;
+    // the copy that last read this buffer pair (two chunks ago) must have finished
+    CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_d2h[ctx->out_flip], 0));
+    if ((size_t) nq * opts->filter_max * sizeof(PlacementRec) > rec_buf.cap || nq * sizeof(uint32_t) > cnt_buf.cap)
+      CU(cudaStreamSynchronize(ctx->copy_stream));          // growing frees the old buffer
+    CU(rec_buf.ensure((size_t) nq * opts->filter_max * sizeof(PlacementRec)));
+    CU(cnt_buf.ensure(nq * sizeof(uint32_t)));
   }
   CU(cudaMemsetAsync(ctx->d_flags, 0, 2 * sizeof(int), ctx->stream));
   CollectArgs a{};
@@ -1226,14 +1262,22 @@ static int collect_impl(epa_ctx * ctx, const epa_options * opts, epa_placement *
   a.nq = nq; a.n_edges = ctx->n_edges;
   a.acc_mode = opts->filter_acc_lwr ? 1 : 0;
   a.thresh = opts->support_threshold; a.fmin = opts->filter_min; a.fmax = opts->filter_max;
-  a.out = to_device ? reinterpret_cast<PlacementRec *>(out) : ctx->out_rec.as<PlacementRec>();
-  a.out_cnt = to_device ? out_counts : ctx->out_cnt.as<uint32_t>();
+  a.out = to_device ? reinterpret_cast<PlacementRec *>(out) : rec_buf.as<PlacementRec>();
+  a.out_cnt = to_device ? out_counts : cnt_buf.as<uint32_t>();
   a.err = ctx->d_flags;
   collect_kernel<<<(nq + 7) / 8, 256, 0, ctx->stream>>>(a);
   LAUNCHED(ctx);
-  if (!to_device && out) CU(cudaMemcpyAsync(out, ctx->out_rec.p, (size_t) nq * opts->filter_max * sizeof(PlacementRec), cudaMemcpyDeviceToHost, ctx->stream));
-  if (!to_device && out_counts) CU(cudaMemcpyAsync(out_counts, ctx->out_cnt.p, nq * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
   CU(cudaEventRecord(ctx->ev[5], ctx->stream));
+  if (!to_device && (out || out_counts))
+  {
+    CU(cudaEventRecord(ctx->ev_collect, ctx->stream));
+    CU(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_collect, 0));
+    if (out) CU(cudaMemcpyAsync(out, rec_buf.p, (size_t) nq * opts->filter_max * sizeof(PlacementRec), cudaMemcpyDeviceToHost, ctx->copy_stream));
+    if (out_counts) CU(cudaMemcpyAsync(out_counts, cnt_buf.p, nq * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->copy_stream));
+    CU(cudaEventRecord(ctx->ev_d2h[ctx->out_flip], ctx->copy_stream));
+    ctx->out_flip ^= 1;
+    if (!ctx->defer_results) CU(cudaStreamSynchronize(ctx->copy_stream));
+  }
   int flags[8];
   if (int rc = read_flags(ctx, flags)) return rc;
   for (int i = 0; i < 5; ++i) (void) cudaEventElapsedTime(&ctx->ms[i], ctx->ev[i], ctx->ev[i + 1]);

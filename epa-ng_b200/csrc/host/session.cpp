@@ -167,6 +167,14 @@ extern "C" int epa_session_place(epa_session * s, const char * query_rows, uint6
     const uint64_t max_q = std::max<uint64_t>(1, (1ull << 28) / std::max<uint32_t>(1, epa_session_num_edges(s)));
     chunk_size = (uint32_t) std::min<uint64_t>(chunk_size, max_q);
   }
+  // the record copies of a chunk overlap the next chunk unless the rooted-tree mapping must touch
+  // them right away
+  const bool defer = !(s->tree.mapper.active && s->preserve_rooting);
+  struct DeferGuard {
+    epa_ctx * c; bool on;
+    DeferGuard(epa_ctx * c_, bool on_) : c(c_), on(on_) { if (on) epa_set_deferred_results(c, 1); }
+    ~DeferGuard() { if (on) { epa_wait_results(c); epa_set_deferred_results(c, 0); } }
+  } guard(s->ctx, defer);
   for (uint64_t done = 0; done < n_queries; done += chunk_size)
   {
     const uint32_t nq = (uint32_t) std::min<uint64_t>(chunk_size, n_queries - done);

@@ -161,6 +161,12 @@ int epa_upload_queries(epa_ctx * ctx, const char * seqs, uint32_t n_queries, int
  * reference prefetches the next chunk with std::async, src/seq/MSA_Stream.cpp:79-85). The host
  * buffer must stay valid and unchanged until it has been uploaded. NULL cancels the hint. */
 int epa_hint_next_chunk(epa_ctx * ctx, const char * next_seqs, uint32_t next_n_queries);
+/* Deferred results: with on != 0, epa_place_chunk / epa_collect return once the records are
+ * computed and their device-to-host copy has been QUEUED on the copy stream; the host buffers may
+ * only be read after epa_wait_results (the reference writes its jplace chunks asynchronously too,
+ * src/io/jplace_writer.hpp:59-65). Default: off (results are in the host buffers on return). */
+int epa_set_deferred_results(epa_ctx * ctx, int on);
+int epa_wait_results(epa_ctx * ctx);
 /* Same for a chunk that already lives in device memory (seqs_dev = DEVICE pointer to
  * n_queries * sites ASCII bytes): used for device-resident timing and by callers that stage
  * the query file in HBM themselves. */
