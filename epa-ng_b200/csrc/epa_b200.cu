@@ -628,16 +628,29 @@ extern "C" int epa_build_lookup(epa_ctx * ctx)
   LAUNCHED(ctx);
   if (S == 4 && (R == 1 || R == 2 || R == 4) && !getenv("EPA_B200_OLD_LOOKUP"))
   {
-    // lane = site kernel over the site-blocked CLV copy
+    // lane = site kernel over the site-blocked CLV copy; its column table goes to constant memory
+    // as [c][r][i] (the mutex covers copy + launch: the symbol is shared by the contexts of a process)
     const size_t t_stride = clvt_node_stride(n, R);
     dim3 grid(B, (n + 127) / 128);
-    switch (R)
+    std::vector<double> hcol((size_t) R * K * 4), hperm((size_t) K * R * 4);
+    CU(cudaMemcpyAsync(hcol.data(), d_col, hcol.size() * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    for (int r = 0; r < R; ++r)
+      for (int c = 0; c < K; ++c)
+        for (int i = 0; i < 4; ++i) hperm[((size_t) c * R + r) * 4 + i] = hcol[((size_t) r * K + c) * 4 + i];
     {
-      case 1: lookup_build_site_kernel<1><<<grid, 128, 0, ctx->stream>>>(ctx->d_model, ctx->d_clvT, t_stride, ctx->tree.scaler, n, ctx->n_pad, ctx->d_edges, d_pm, d_col, ctx->d_lookup); break;
-      case 2: lookup_build_site_kernel<2><<<grid, 128, 0, ctx->stream>>>(ctx->d_model, ctx->d_clvT, t_stride, ctx->tree.scaler, n, ctx->n_pad, ctx->d_edges, d_pm, d_col, ctx->d_lookup); break;
-      default: lookup_build_site_kernel<4><<<grid, 128, 0, ctx->stream>>>(ctx->d_model, ctx->d_clvT, t_stride, ctx->tree.scaler, n, ctx->n_pad, ctx->d_edges, d_pm, d_col, ctx->d_lookup); break;
+      std::lock_guard<std::mutex> lock(g_const_mutex);
+      CU(cudaMemcpyToSymbol(c_coltab, hperm.data(), hperm.size() * sizeof(double)));
+      CU(cudaEventRecord(ctx->ev[0], ctx->stream));
+      switch (R)
+      {
+        case 1: lookup_build_site_kernel<1><<<grid, 128, 0, ctx->stream>>>(ctx->d_model, ctx->d_clvT, t_stride, ctx->tree.scaler, n, ctx->n_pad, ctx->d_edges, d_pm, ctx->d_lookup); break;
+        case 2: lookup_build_site_kernel<2><<<grid, 128, 0, ctx->stream>>>(ctx->d_model, ctx->d_clvT, t_stride, ctx->tree.scaler, n, ctx->n_pad, ctx->d_edges, d_pm, ctx->d_lookup); break;
+        default: lookup_build_site_kernel<4><<<grid, 128, 0, ctx->stream>>>(ctx->d_model, ctx->d_clvT, t_stride, ctx->tree.scaler, n, ctx->n_pad, ctx->d_edges, d_pm, ctx->d_lookup); break;
+      }
+      LAUNCHED(ctx);
+      CU(cudaStreamSynchronize(ctx->stream));
     }
-    LAUNCHED(ctx);
   }
   else if (S == 4 && R == 4)
   {

@@ -222,29 +222,26 @@ __device__ __forceinline__ size_t clvt_offset(int abs_site)
 // shared-memory broadcasts, and every lane writes its site's 128-byte table row.
 // grid = (n_edges, ceil(n / 128)), block = 128.
 // ---------------------------------------------------------------------------------------------
+// column table of the lookup build in constant memory, [c][r][i] (copied device-to-device before the
+// launch): the 240 table reads of a site become constant-bank operands of the FMAs
+__constant__ double c_coltab[16 * 4 * MAX_RATES / 2];      // R <= 4
+
 template <int R>
 __global__ void __launch_bounds__(128)
 lookup_build_site_kernel(const DevModel * __restrict__ m, const double * __restrict__ clvT, size_t t_stride,
                          const uint32_t * __restrict__ scaler, int n, int n_pad,
                          const EdgeDev * __restrict__ edges, const double * __restrict__ pmats_half,
-                         const double * __restrict__ coltab, double * __restrict__ lookup)
+                         double * __restrict__ lookup)
 {
   constexpr int K = 16, C = 4 * R;
   __shared__ __align__(16) double P[R * 16];
-  __shared__ __align__(16) double M[K * C];          // [c][r][i]
-  __shared__ double wts[R];
+  __shared__ double tile[4][32 * 17];                // per warp: 32 sites x 16 columns, row stride 17
   const EdgeDev e = edges[blockIdx.x];
   for (int i = threadIdx.x; i < R * 16; i += blockDim.x) P[i] = __ldg(pmats_half + (size_t) blockIdx.x * R * 16 + i);
-  for (int idx = threadIdx.x; idx < K * C; idx += blockDim.x)
-  {
-    const int c = idx / C, r = (idx / 4) % R, i = idx & 3;
-    M[idx] = __ldg(coltab + (r * K + c) * 4 + i);
-  }
-  if (threadIdx.x < R) wts[threadIdx.x] = m->weights[threadIdx.x];
   __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int site = blockIdx.y * 128 + threadIdx.x;
-  const bool active = site < n;
-  const int s = active ? site : n - 1;
+  const int s = site < n ? site : n - 1;
   const size_t off = clvt_offset<R>(s);
   const double * dp = clvT + (size_t) e.distal * t_stride + off;
   const double * xp = clvT + (size_t) e.proximal * t_stride + off;
@@ -275,27 +272,31 @@ lookup_build_site_kernel(const DevModel * __restrict__ m, const double * __restr
     for (int c = 0; c < C; ++c) in[c] *= EPA_SCALE_FACTOR;
   }
   const double scale_term = sc ? (double) sc * EPA_LOG_SCALE_THRESHOLD : 0.0;
-  double * out = lookup + ((size_t) blockIdx.x * n_pad + s) * K;
+  double * trow = tile[warp] + lane * 17;
+  trow[0] = 0.0;                                       // column 0 = zero column
   #pragma unroll
-  for (int c2 = 0; c2 < K; c2 += 2)
+  for (int c = 1; c < K; ++c)
   {
-    double res[2];
+    double term = 0.0;
     #pragma unroll
-    for (int cc = 0; cc < 2; ++cc)
+    for (int r = 0; r < R; ++r)
     {
-      const int c = c2 + cc;
-      double term = 0.0;
-      #pragma unroll
-      for (int r = 0; r < R; ++r)
-      {
-        double mv[4];
-        lds_vec<4>(M + c * C + r * 4, mv);
-        const double tr = in[r * 4] * mv[0] + in[r * 4 + 1] * mv[1] + in[r * 4 + 2] * mv[2] + in[r * 4 + 3] * mv[3];
-        term += tr * wts[r];
-      }
-      res[cc] = c == 0 ? 0.0 : log(term) + scale_term;          // column 0 = zero column
+      const double tr = in[r * 4] * c_coltab[c * C + r * 4] + in[r * 4 + 1] * c_coltab[c * C + r * 4 + 1]
+                      + in[r * 4 + 2] * c_coltab[c * C + r * 4 + 2] + in[r * 4 + 3] * c_coltab[c * C + r * 4 + 3];
+      term += tr * c_model.weights[r];
     }
-    if (active) *reinterpret_cast<double2 *>(out + c2) = make_double2(res[0], res[1]);
+    trow[c] = log(term) + scale_term;
+  }
+  __syncwarp();
+  // the warp's 32 table rows are 4 KB contiguous in global memory: coalesced 256-byte stores
+  const int site0 = blockIdx.y * 128 + warp * 32;
+  const int n_valid = min(32, n - site0) * K;
+  double * out = lookup + ((size_t) blockIdx.x * n_pad + site0) * K;
+  #pragma unroll
+  for (int k = 0; k < K; ++k)
+  {
+    const int idx = k * 32 + lane;
+    if (idx < n_valid) out[idx] = tile[warp][(idx >> 4) * 17 + (idx & 15)];
   }
 }
 
