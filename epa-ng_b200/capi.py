@@ -135,6 +135,7 @@ class Context:
         assert tip_masks.ndim == 2 and tip_masks.shape[1] == sites
         earr = (EdgeDesc * len(edges))(*[EdgeDesc(int(d), int(p), float(l)) for d, p, l in edges])
         self.states, self.rate_cats, self.sites = states, rate_cats, sites
+        self.scalers_per_site = rate_cats if (flags & EPA_FLAG_RATE_SCALERS) else 1
         self.n_tips, self.n_edges = tip_masks.shape[0], len(edges)
         self.handle = _vp()
         rc = self.lib.epa_ctx_create(C.byref(self.handle), device, C.byref(md), tip_masks.shape[0],
@@ -174,7 +175,7 @@ class Context:
 
     def get_clv(self, node):
         clv = np.zeros(self.sites * self.rate_cats * self.states)
-        sc = np.zeros(self.sites, dtype=np.uint32)
+        sc = np.zeros(self.sites * getattr(self, "scalers_per_site", 1), dtype=np.uint32)
         self._check(self.lib.epa_get_clv(self.handle, node, _ptr(clv, _dp), _ptr(sc, _u32p)))
         return clv, sc
 

@@ -41,11 +41,22 @@ struct DevModel {
 // >= n_tips are the directional CLV slots of the inner nodes.
 struct DevTree {
   double * clv;                                   // [n_nodes][n][R][S]
-  uint32_t * scaler;                              // [n_nodes][n]
+  uint32_t * scaler;                              // [n_nodes][n][sr]: sr = 1 (per-site scaling) or R (per-rate scalers)
   size_t clv_stride;                              // n*R*S
   uint32_t n_tips;
   uint32_t n_nodes;
+  uint32_t sr;                                    // scaler entries per site
 };
+
+// libpll caps the per-rate scaler difference of a site (PLL_SCALE_RATE_MAXDIFF, LP/pll.h:104)
+constexpr uint32_t EPA_RATE_MAXDIFF = 4;
+// 2^(-256 d), d = 0..4 (2^-1024 is subnormal): the weight of a rate whose scaler count is d above
+// the site's minimum (LP/core_likelihood.c:474-491,518-521)
+__device__ __forceinline__ double rate_scale_factor(uint32_t d)
+{
+  const int hi = d == 0 ? 0x3ff00000 : (d == 1 ? 0x2ff00000 : (d == 2 ? 0x1ff00000 : (d == 3 ? 0x0ff00000 : 0x00040000)));
+  return __hiloint2double(hi, 0);
+}
 
 struct ClvOpDev {
   uint32_t parent, left, right;

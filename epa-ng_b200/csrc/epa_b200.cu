@@ -279,8 +279,8 @@ extern "C" int epa_ctx_create(epa_ctx ** out, int device, const epa_model_desc *
   *out = nullptr;
   if (!supported_sr((int) model->states, (int) model->rate_cats))
     return fail(ctx, EPA_ERR_ARG, "unsupported states/rate_cats combination %u/%u", model->states, model->rate_cats);
-  if (model->flags & EPA_FLAG_RATE_SCALERS)
-    return fail(ctx, EPA_ERR_ARG, "per-rate scalers are not supported (use per-site scaling)");
+  if ((model->flags & EPA_FLAG_RATE_SCALERS) && !(model->states == 4 && model->rate_cats <= 4))
+    return fail(ctx, EPA_ERR_ARG, "per-rate scalers are only supported for DNA with at most 4 rate categories");
   if (model->pinv != 0.0) return fail(ctx, EPA_ERR_ARG, "+I models are not supported");
   if (model->sites == 0 || n_tips < 3 || n_edges == 0) return fail(ctx, EPA_ERR_ARG, "empty tree or alignment");
   int ndev = 0;
@@ -330,7 +330,7 @@ extern "C" int epa_ctx_create(epa_ctx ** out, int device, const epa_model_desc *
   memset(&m, 0, sizeof m);
   const int S = (int) model->states, R = (int) model->rate_cats;
   m.S = S; m.R = R; m.n = (int) model->sites;
-  m.per_rate = 0;
+  m.per_rate = (model->flags & EPA_FLAG_RATE_SCALERS) ? 1 : 0;
   m.bugcompat = (model->flags & EPA_FLAG_BUGCOMPAT_FOCUS) ? 1 : 0;
   for (int i = 0; i < S; ++i) { m.eigenvals[i] = model->eigenvals[i]; m.freqs[i] = model->freqs[i]; }
   for (int i = 0; i < S * S; ++i) { m.eigenvecs[i] = model->eigenvecs[i]; m.inv_eigenvecs[i] = model->inv_eigenvecs[i]; }
@@ -377,8 +377,9 @@ extern "C" int epa_ctx_create(epa_ctx ** out, int device, const epa_model_desc *
   ctx->tree.clv_stride = (size_t) m.n * R * S;
   ctx->tree.n_tips = n_tips; ctx->tree.n_nodes = ctx->n_nodes;
   CUC(cudaMalloc(&ctx->tree.clv, ctx->tree.clv_stride * ctx->n_nodes * sizeof(double)));
-  CUC(cudaMalloc(&ctx->tree.scaler, (size_t) m.n * ctx->n_nodes * sizeof(uint32_t)));
-  CUC(cudaMemset(ctx->tree.scaler, 0, (size_t) m.n * ctx->n_nodes * sizeof(uint32_t)));
+  ctx->tree.sr = m.per_rate ? (uint32_t) R : 1u;
+  CUC(cudaMalloc(&ctx->tree.scaler, (size_t) m.n * ctx->tree.sr * ctx->n_nodes * sizeof(uint32_t)));
+  CUC(cudaMemset(ctx->tree.scaler, 0, (size_t) m.n * ctx->tree.sr * ctx->n_nodes * sizeof(uint32_t)));
   ctx->h_edges.resize(n_edges);
   for (uint32_t i = 0; i < n_edges; ++i) ctx->h_edges[i] = EdgeDev{edges[i].distal, edges[i].proximal, edges[i].length};
   CUC(cudaMalloc(&ctx->d_edges, n_edges * sizeof(EdgeDev)));
@@ -533,11 +534,12 @@ extern "C" int epa_upload_clvs(epa_ctx * ctx, const epa_host_clv * clvs, uint32_
       return fail(ctx, EPA_ERR_ARG, "clv %u: invalid slot %u", i, c.slot);
     CU(cudaMemcpyAsync(ctx->tree.clv + c.slot * ctx->tree.clv_stride, c.clv, ctx->tree.clv_stride * sizeof(double),
                        cudaMemcpyHostToDevice, ctx->stream));
+    const size_t sn = (size_t) ctx->n * ctx->tree.sr;      // scaler entries per node
     if (c.scaler)
-      CU(cudaMemcpyAsync(ctx->tree.scaler + (size_t) c.slot * ctx->n, c.scaler, ctx->n * sizeof(uint32_t),
+      CU(cudaMemcpyAsync(ctx->tree.scaler + (size_t) c.slot * sn, c.scaler, sn * sizeof(uint32_t),
                          cudaMemcpyHostToDevice, ctx->stream));
     else
-      CU(cudaMemsetAsync(ctx->tree.scaler + (size_t) c.slot * ctx->n, 0, ctx->n * sizeof(uint32_t), ctx->stream));
+      CU(cudaMemsetAsync(ctx->tree.scaler + (size_t) c.slot * sn, 0, sn * sizeof(uint32_t), ctx->stream));
     ctx->slot_filled[c.slot] = 1;
   }
   CU(cudaStreamSynchronize(ctx->stream));
@@ -554,7 +556,8 @@ extern "C" int epa_get_clv(epa_ctx * ctx, uint32_t slot, double * clv, uint32_t 
   if (int rc = set_device(ctx)) return rc;
   CU(cudaStreamSynchronize(ctx->stream));
   if (clv) CU(cudaMemcpy(clv, ctx->tree.clv + slot * ctx->tree.clv_stride, ctx->tree.clv_stride * sizeof(double), cudaMemcpyDeviceToHost));
-  if (scaler) CU(cudaMemcpy(scaler, ctx->tree.scaler + (size_t) slot * ctx->n, ctx->n * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+  const size_t sn = (size_t) ctx->n * ctx->tree.sr;
+  if (scaler) CU(cudaMemcpy(scaler, ctx->tree.scaler + (size_t) slot * sn, sn * sizeof(uint32_t), cudaMemcpyDeviceToHost));
   return EPA_OK;
 }
 
@@ -626,7 +629,7 @@ extern "C" int epa_build_lookup(epa_ctx * ctx)
   if (S == 4) lookup_coltable_kernel<4><<<1, 256, 0, ctx->stream>>>(ctx->d_model, d_pm + (size_t) B * pm, d_col);
   else lookup_coltable_kernel<20><<<1, 256, 0, ctx->stream>>>(ctx->d_model, d_pm + (size_t) B * pm, d_col);
   LAUNCHED(ctx);
-  if (S == 4 && (R == 1 || R == 2 || R == 4) && !getenv("EPA_B200_OLD_LOOKUP"))
+  if (S == 4 && (R == 1 || R == 2 || R == 4) && (ctx->tree.sr > 1 || !getenv("EPA_B200_OLD_LOOKUP")))
   {
     // lane = site kernel over the site-blocked CLV copy; its column table goes to constant memory
     // as [c][r][i] (the mutex covers copy + launch: the symbol is shared by the contexts of a process)
@@ -644,9 +647,9 @@ extern "C" int epa_build_lookup(epa_ctx * ctx)
       CU(cudaEventRecord(ctx->ev[0], ctx->stream));
       switch (R)
       {
-        case 1: lookup_build_site_kernel<1><<<grid, 128, 0, ctx->stream>>>(ctx->d_model, ctx->d_clvT, t_stride, ctx->tree.scaler, n, ctx->n_pad, ctx->d_edges, d_pm, ctx->d_lookup); break;
-        case 2: lookup_build_site_kernel<2><<<grid, 128, 0, ctx->stream>>>(ctx->d_model, ctx->d_clvT, t_stride, ctx->tree.scaler, n, ctx->n_pad, ctx->d_edges, d_pm, ctx->d_lookup); break;
-        default: lookup_build_site_kernel<4><<<grid, 128, 0, ctx->stream>>>(ctx->d_model, ctx->d_clvT, t_stride, ctx->tree.scaler, n, ctx->n_pad, ctx->d_edges, d_pm, ctx->d_lookup); break;
+        case 1: lookup_build_site_kernel<1><<<grid, 128, 0, ctx->stream>>>(ctx->d_model, ctx->d_clvT, t_stride, ctx->tree.scaler, (int) ctx->tree.sr, n, ctx->n_pad, ctx->d_edges, d_pm, ctx->d_lookup); break;
+        case 2: lookup_build_site_kernel<2><<<grid, 128, 0, ctx->stream>>>(ctx->d_model, ctx->d_clvT, t_stride, ctx->tree.scaler, (int) ctx->tree.sr, n, ctx->n_pad, ctx->d_edges, d_pm, ctx->d_lookup); break;
+        default: lookup_build_site_kernel<4><<<grid, 128, 0, ctx->stream>>>(ctx->d_model, ctx->d_clvT, t_stride, ctx->tree.scaler, (int) ctx->tree.sr, n, ctx->n_pad, ctx->d_edges, d_pm, ctx->d_lookup); break;
       }
       LAUNCHED(ctx);
       CU(cudaStreamSynchronize(ctx->stream));
@@ -1120,7 +1123,9 @@ int launch_blo_site(epa_ctx * ctx, BloArgs & a)
   if (int rc = ensure_clvT(ctx)) return rc;
   BloSiteArgs sa{};
   sa.clvT = ctx->d_clvT; sa.t_stride = clvt_node_stride(ctx->n, ctx->R);
-  if (ctx->d_gT && ctx->lookup_ready && !getenv("EPA_B200_NO_FIRST"))
+  sa.bugcompat = ctx->hm.bugcompat;
+  const bool pr = ctx->tree.sr > 1;
+  if (ctx->d_gT && ctx->lookup_ready && !pr && !getenv("EPA_B200_NO_FIRST"))
   {
     sa.gT = ctx->d_gT; sa.g_stride = sa.t_stride; sa.lookup = ctx->d_lookup; sa.n_pad = ctx->n_pad;
   }
@@ -1143,8 +1148,16 @@ int launch_blo_site(epa_ctx * ctx, BloArgs & a)
     const size_t smem = (size_t) warps * fix + (size_t) n_sm * rows;
     uint64_t grid = (uint64_t) ctx->sm_count;
     grid = std::min<uint64_t>(grid, (a.n_pairs + warps - 1) / warps);
-    CU(cudaFuncSetAttribute(blo_site_kernel<R, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
-    blo_site_kernel<R, false><<<(unsigned) grid, warps * 32, smem, ctx->stream>>>(sa);
+    if (pr)
+    {
+      CU(cudaFuncSetAttribute(blo_site_kernel<R, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+      blo_site_kernel<R, false, true><<<(unsigned) grid, warps * 32, smem, ctx->stream>>>(sa);
+    }
+    else
+    {
+      CU(cudaFuncSetAttribute(blo_site_kernel<R, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+      blo_site_kernel<R, false><<<(unsigned) grid, warps * 32, smem, ctx->stream>>>(sa);
+    }
   }
   else
   {
@@ -1156,8 +1169,16 @@ int launch_blo_site(epa_ctx * ctx, BloArgs & a)
     a.wcap = 0;
     sa.b = a;
     const size_t smem = SiteWarpSmem<R>::doubles(0) * sizeof(double) * warps;
-    CU(cudaFuncSetAttribute(blo_site_kernel<R, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
-    blo_site_kernel<R, true><<<grid, warps * 32, smem, ctx->stream>>>(sa);
+    if (pr)
+    {
+      CU(cudaFuncSetAttribute(blo_site_kernel<R, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+      blo_site_kernel<R, true, true><<<grid, warps * 32, smem, ctx->stream>>>(sa);
+    }
+    else
+    {
+      CU(cudaFuncSetAttribute(blo_site_kernel<R, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+      blo_site_kernel<R, true><<<grid, warps * 32, smem, ctx->stream>>>(sa);
+    }
   }
   LAUNCHED(ctx);
   return EPA_OK;

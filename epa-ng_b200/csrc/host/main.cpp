@@ -49,7 +49,7 @@ int main(int argc, char ** argv)
   epa_options opts;
   epa_options_default(&opts);
   uint32_t chunk = 0;
-  int precision = 10, device = 0, preserve_rooting = 1;
+  int precision = 10, device = 0, preserve_rooting = 1, rate_mode = 2, rate_bug = 1;
   std::string invocation;
   for (int i = 0; i < argc; ++i) { invocation += argv[i]; invocation += ' '; }
 
@@ -84,8 +84,10 @@ int main(int argc, char ** argv)
     else if (a == "--rate-scalers")
     {
       const std::string v = need(i);
-      if (v == "on") die("--rate-scalers on: per-rate scalers are not supported by this build (per-site scaling is used)");
+      if (v == "on") rate_mode = 1; else if (v == "off") rate_mode = 0; else if (v == "auto") rate_mode = 2;
+      else die("--rate-scalers takes on, off or auto");
     }
+    else if (a == "--correct-scaler-focus") rate_bug = 0;     // not a reference option: read the scalers of the site itself
     else if (a == "--preserve-rooting") { const std::string v = need(i); preserve_rooting = (v != "off"); }
     else if (a == "--raxml-blo" || a == "-b" || a == "--binary" ||
              a == "-B" || a == "--dump-binary" || a == "-c" || a == "--bfast" || a == "--split")
@@ -93,6 +95,7 @@ int main(int argc, char ** argv)
     else die("unknown option " + a);
   }
   if (tree.empty() || ref.empty() || query.empty()) { usage(); die("-t, -s and -q are required"); }
+  if (epa_host_set_rate_scalers(rate_mode, rate_bug)) die(epa_host_last_error());
   const int rc = epa_run_files_ex(tree.c_str(), ref.c_str(), query.c_str(), model.c_str(), outdir.c_str(), &opts, chunk,
                                   precision, device, invocation.c_str(), preserve_rooting);
   if (rc) die(epa_host_last_error());

@@ -74,6 +74,18 @@ static uint32_t tip_mask(int states, uint8_t ch)
   }
 }
 
+// per-rate scaler policy of the sessions opened next (process-wide, like a command-line option):
+// 0 = off, 1 = on, 2 = auto = on for trees with more than 2000 tips (src/tree/Tree_Numbers.hpp:11,
+// src/io/file_io.cpp:211-214). bugcompat = reproduce the reference's scaler window offset
+// (SURVEY 8a quirk 4); 0 reads the scalers of the site itself.
+static int g_rate_scalers = 2, g_rate_bugcompat = 1;
+extern "C" int epa_host_set_rate_scalers(int mode, int bugcompat)
+{
+  if (mode < 0 || mode > 2) return host_fail(EPA_ERR_ARG, "rate scaler mode must be 0 (off), 1 (on) or 2 (auto)");
+  g_rate_scalers = mode; g_rate_bugcompat = bugcompat ? 1 : 0;
+  return EPA_OK;
+}
+
 extern "C" int epa_session_open(epa_session ** out, const char * newick, uint32_t n_taxa, const char * const * names,
                                 const char * ref_rows, uint32_t sites, const char * model_desc, int device)
 {
@@ -110,6 +122,12 @@ extern "C" int epa_session_open(epa_session ** out, const char * newick, uint32_
     md.rate_cats = (uint32_t) s->model.rate_cats;
     md.sites = sites;
     md.flags = 0;
+    {
+      // auto mode only switches the kernels that have a per-rate path (DNA, <= 4 rate categories)
+      const bool can = s->model.states == 4 && s->model.rate_cats <= 4;
+      const bool want = g_rate_scalers == 1 || (g_rate_scalers == 2 && T > 2000 && can);
+      if (want) md.flags |= EPA_FLAG_RATE_SCALERS | (g_rate_bugcompat ? EPA_FLAG_BUGCOMPAT_FOCUS : 0u);
+    }
     md.eigenvals = s->model.eigenvals.data();
     md.eigenvecs = s->model.eigenvecs.data();
     md.inv_eigenvecs = s->model.inv_eigenvecs.data();

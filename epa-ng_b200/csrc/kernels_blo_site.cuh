@@ -102,6 +102,7 @@ __device__ __forceinline__ void tc_wait_st() { asm volatile("tcgen05.wait::st.sy
 
 struct BloSiteArgs {
   BloArgs b;
+  int bugcompat;                        // per-rate scalers: reproduce the reference's window offset
   const double * clvT;                  // site-blocked CLV copy
   size_t t_stride;                      // doubles per node in clvT
   double * gscratch;                    // global sumtable scratch [warp][blo_row][wpad] (GS variant)
@@ -229,7 +230,7 @@ __constant__ double c_coltab[16 * 4 * MAX_RATES / 2];      // R <= 4
 template <int R>
 __global__ void __launch_bounds__(128)
 lookup_build_site_kernel(const DevModel * __restrict__ m, const double * __restrict__ clvT, size_t t_stride,
-                         const uint32_t * __restrict__ scaler, int n, int n_pad,
+                         const uint32_t * __restrict__ scaler, int sr, int n, int n_pad,
                          const EdgeDev * __restrict__ edges, const double * __restrict__ pmats_half,
                          double * __restrict__ lookup)
 {
@@ -245,7 +246,7 @@ lookup_build_site_kernel(const DevModel * __restrict__ m, const double * __restr
   const size_t off = clvt_offset<R>(s);
   const double * dp = clvT + (size_t) e.distal * t_stride + off;
   const double * xp = clvT + (size_t) e.proximal * t_stride + off;
-  uint32_t sc = __ldg(scaler + (size_t) e.distal * n + s) + __ldg(scaler + (size_t) e.proximal * n + s);
+  uint32_t sc = 0;
   double in[C];
   bool small = true;
   #pragma unroll
@@ -265,11 +266,36 @@ lookup_build_site_kernel(const DevModel * __restrict__ m, const double * __restr
       small = small && (in[r * 4 + i] < EPA_SCALE_THRESHOLD);
     }
   }
-  if (small)
+  if (sr == 1)
   {
-    sc += 1;
+    sc = __ldg(scaler + (size_t) e.distal * n + s) + __ldg(scaler + (size_t) e.proximal * n + s);
+    if (small)
+    {
+      sc += 1;
+      #pragma unroll
+      for (int c = 0; c < C; ++c) in[c] *= EPA_SCALE_FACTOR;
+    }
+  }
+  else
+  {
+    // per-rate scalers: a rate whose count is d above the site's minimum weighs 2^(-256 d). The inner
+    // CLV is not rescaled here: its own per-rate rescaling would only move factors of 2^256 between
+    // the values and these counts.
+    uint32_t kr[R], kmin = 0xffffffffu;
     #pragma unroll
-    for (int c = 0; c < C; ++c) in[c] *= EPA_SCALE_FACTOR;
+    for (int r = 0; r < R; ++r)
+    {
+      kr[r] = __ldg(scaler + ((size_t) e.distal * n + s) * R + r) + __ldg(scaler + ((size_t) e.proximal * n + s) * R + r);
+      kmin = min(kmin, kr[r]);
+    }
+    #pragma unroll
+    for (int r = 0; r < R; ++r)
+    {
+      const double f = rate_scale_factor(min(kr[r] - kmin, EPA_RATE_MAXDIFF));
+      #pragma unroll
+      for (int i = 0; i < 4; ++i) in[r * 4 + i] *= f;
+    }
+    sc = kmin;
   }
   const double scale_term = sc ? (double) sc * EPA_LOG_SCALE_THRESHOLD : 0.0;
   double * trow = tile[warp] + lane * 17;
@@ -522,11 +548,28 @@ __device__ __forceinline__ void site_store_row(const SumRef & sr, int trip, int 
 
 // Pass A: inner CLV toward the new tip from (D, X); returns the edge log-likelihood new_tip | inner
 // over the window and leaves the pendant sumtable (inner vs tip) in `sum`.
-template <int R, bool GS>
+// Per-rate scaler weights of one window site (PR kernels): counts of the two edge CLVs per rate,
+// read where the reference reads them. shift_partition_focus advances the scale buffers by `begin`
+// ELEMENTS even though a site has R of them (src/core/pll/pll_util.cpp:405-408), so the thorough
+// phase of the reference sees entry begin + s*R + r; with bugcompat = 0 the entry of the site itself.
+template <int R>
+__device__ __forceinline__ uint32_t rate_weights(const uint32_t * __restrict__ sDn, const uint32_t * __restrict__ sXn,
+                                                 int begin, int s, int bugcompat, double (&f)[R])
+{
+  const size_t base = bugcompat ? (size_t) begin + (size_t) s * R : ((size_t) begin + s) * R;
+  uint32_t kr[R], kmin = 0xffffffffu;
+  #pragma unroll
+  for (int r = 0; r < R; ++r) { kr[r] = __ldg(sDn + base + r) + __ldg(sXn + base + r); kmin = min(kmin, kr[r]); }
+  #pragma unroll
+  for (int r = 0; r < R; ++r) f[r] = rate_scale_factor(min(kr[r] - kmin, EPA_RATE_MAXDIFF));
+  return kmin;
+}
+
+template <int R, bool GS, bool PR>
 __device__ __forceinline__ double site_pass_tip(const SiteCtaSmem & cs, const double * ws, const SumRef & sr,
                                              const double * __restrict__ DT, const double * __restrict__ XT,
                                              const uint32_t * __restrict__ sD, const uint32_t * __restrict__ sX,
-                                             const uint8_t * __restrict__ qc, int begin, int w, int lane)
+                                             const uint8_t * __restrict__ qc, int begin, int w, int lane, int bugcompat)
 {
   using L = SiteWarpSmem<R>;
   // The window log-likelihood is a sum of per-site logarithms. A lane multiplies the mantissas of
@@ -548,7 +591,10 @@ __device__ __forceinline__ double site_pass_tip(const SiteCtaSmem & cs, const do
     for (int c = 0; c < 4 * R; ++c) { dv[c] = __ldg(dp + (size_t) c * CLVT_BLOCK); xv[c] = __ldg(xp + (size_t) c * CLVT_BLOCK); }
     const int mask = qc[s] & 15;
     const int pos = tv_pos(mask);
-    const uint32_t scal = __ldg(sD + s) + __ldg(sX + s);
+    uint32_t scal;
+    double rf[R];
+    if constexpr (PR) scal = rate_weights<R>(sD, sX, begin, s, bugcompat, rf);
+    else scal = __ldg(sD + s) + __ldg(sX + s);
     double in[4 * R];
     #pragma unroll
     for (int r = 0; r < R; ++r)
@@ -562,6 +608,7 @@ __device__ __forceinline__ double site_pass_tip(const SiteCtaSmem & cs, const do
         const double ta = pd[0] * dv[r * 4] + pd[1] * dv[r * 4 + 1] + pd[2] * dv[r * 4 + 2] + pd[3] * dv[r * 4 + 3];
         const double tb = pp[0] * xv[r * 4] + pp[1] * xv[r * 4 + 1] + pp[2] * xv[r * 4 + 2] + pp[3] * xv[r * 4 + 3];
         in[r * 4 + i] = ta * tb;
+        if constexpr (PR) in[r * 4 + i] *= rf[r];
       }
     }
     double tl[4];
@@ -651,10 +698,11 @@ __device__ __forceinline__ double site_pass_first(const SiteCtaSmem & cs, const 
 }
 
 // Pass B: inner CLV toward the distal node from (T, X); leaves the distal sumtable (D vs inner)
-template <int R, bool GS>
+template <int R, bool GS, bool PR>
 __device__ __forceinline__ void site_pass_distal(const double * ws, const SumRef & sr,
                                               const double * __restrict__ DT, const double * __restrict__ XT,
-                                              const uint8_t * __restrict__ qc, int begin, int w, int lane)
+                                              const uint32_t * __restrict__ sD, const uint32_t * __restrict__ sX,
+                                              const uint8_t * __restrict__ qc, int begin, int w, int lane, int bugcompat)
 {
   using L = SiteWarpSmem<R>;
   const int trips = (w + 31) >> 5;
@@ -671,6 +719,8 @@ __device__ __forceinline__ void site_pass_distal(const double * ws, const SumRef
     for (int c = 0; c < 4 * R; ++c) { dv[c] = __ldg(dp + (size_t) c * CLVT_BLOCK); xv[c] = __ldg(xp + (size_t) c * CLVT_BLOCK); }
     const int pos = tv_pos(qc[s] & 15);
     const double * tvp = ws + L::TV + pos * L::TVS;
+    double rf[R];
+    if constexpr (PR) (void) rate_weights<R>(sD, sX, begin, s, bugcompat, rf);
     double in[4 * R];
     #pragma unroll
     for (int r = 0; r < R; ++r)
@@ -684,6 +734,7 @@ __device__ __forceinline__ void site_pass_distal(const double * ws, const SumRef
         lds_vec<4>(ws + L::P_P + r * 16 + i * 4, pp);
         const double tb = pp[0] * xv[r * 4] + pp[1] * xv[r * 4 + 1] + pp[2] * xv[r * 4 + 2] + pp[3] * xv[r * 4 + 3];
         in[r * 4 + i] = tp[i] * tb;
+        if constexpr (PR) in[r * 4 + i] *= rf[r];
       }
     }
     double base = 0.0;
@@ -728,7 +779,8 @@ __device__ __forceinline__ unsigned long long site_next_item(SiteCtaSmem & cs, u
 }
 
 // GS = sumtable in global scratch (windows that do not fit the shared-memory slice)
-template <int R, bool GS>
+// PR = per-rate scalers (the scaler pointers then address the node's [n][R] block, not the window)
+template <int R, bool GS, bool PR = false>
 __global__ void __launch_bounds__(384, 1)
 blo_site_kernel(BloSiteArgs sa)
 {
@@ -808,8 +860,8 @@ blo_site_kernel(BloSiteArgs sa)
     const int n = a.n;
     const double * DT = sa.clvT + (size_t) ed.distal * sa.t_stride;
     const double * XT = sa.clvT + (size_t) ed.proximal * sa.t_stride;
-    const uint32_t * sD = a.tree.scaler + (size_t) ed.distal * n + begin;
-    const uint32_t * sX = a.tree.scaler + (size_t) ed.proximal * n + begin;
+    const uint32_t * sD = PR ? a.tree.scaler + (size_t) ed.distal * n * R : a.tree.scaler + (size_t) ed.distal * n + begin;
+    const uint32_t * sX = PR ? a.tree.scaler + (size_t) ed.proximal * n * R : a.tree.scaler + (size_t) ed.proximal * n + begin;
     const uint8_t * qc = a.codes + (size_t) q * n + begin;
 
     // optimize_branch_triplet / opt_branch_lengths_pplacer as half rounds (see kernels_blo.cuh)
@@ -839,7 +891,7 @@ blo_site_kernel(BloSiteArgs sa)
           new_logl = -site_pass_first<R, GS>(cs, sr, sa.gT + (size_t) e * sa.g_stride,
                                              sa.lookup + (size_t) e * sa.n_pad * 16, qc, begin, w, lane);
         else
-          new_logl = -site_pass_tip<R, GS>(cs, ws, sr, DT, XT, sD, sX, qc, begin, w, lane);
+          new_logl = -site_pass_tip<R, GS, PR>(cs, ws, sr, DT, XT, sD, sX, qc, begin, w, lane, sa.bugcompat);
         if (first) { loglikelihood = new_logl; first = false; }
         else
         {
@@ -859,7 +911,7 @@ blo_site_kernel(BloSiteArgs sa)
       }
       else
       {
-        site_pass_distal<R, GS>(ws, sr, DT, XT, qc, begin, w, lane);
+        site_pass_distal<R, GS, PR>(ws, sr, DT, XT, sD, sX, qc, begin, w, lane, sa.bugcompat);
         xmin = fmin(EPA_MIN_BRLEN / 2.0, original_length / 2.0);
         xmax = original_length - xmin / 10.0;
         xguess = len[0];

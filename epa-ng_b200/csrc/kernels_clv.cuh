@@ -106,6 +106,31 @@ clv_update_kernel(DevTree tree, int n, const ClvOpDev * __restrict__ ops, const 
       all_small = all_small && (res[r][i] < EPA_SCALE_THRESHOLD);
     }
   }
+  if (tree.sr > 1)
+  {
+    // per-rate scalers (PLL_ATTRIB_RATE_SCALERS, LP/core_partials.c:690-766): every rate block is
+    // rescaled on its own and keeps its own count
+    const uint32_t * sl = tree.scaler + ((size_t) op.left * n + site) * R;
+    const uint32_t * sr = tree.scaler + ((size_t) op.right * n + site) * R;
+    uint32_t * sp = tree.scaler + ((size_t) op.parent * n + site) * R;
+    #pragma unroll
+    for (int r = 0; r < R; ++r)
+    {
+      bool small = true;
+      #pragma unroll
+      for (int i = 0; i < S; ++i) small = small && (res[r][i] < EPA_SCALE_THRESHOLD);
+      uint32_t sc = sl[r] + sr[r];
+      if (small && !op.tip_tip)
+      {
+        sc += 1;
+        #pragma unroll
+        for (int i = 0; i < S; ++i) res[r][i] *= EPA_SCALE_FACTOR;
+      }
+      store_vec<S>(out + r * S, res[r]);
+      sp[r] = sc;
+    }
+    return;
+  }
   uint32_t sc = tree.scaler[(size_t) op.left * n + site] + tree.scaler[(size_t) op.right * n + site];
   const bool scale = all_small && !op.tip_tip;
   if (scale) sc += 1;
@@ -338,6 +363,16 @@ edge_logl_kernel(const DevModel * __restrict__ m, DevTree tree, int n, EdgeDev e
     const double * A = tree.clv + e.distal * tree.clv_stride + (size_t) site * (R * S);
     const double * B = tree.clv + e.proximal * tree.clv_stride + (size_t) site * (R * S);
     double terma = 0.0;
+    uint32_t kr[R], kmin = 0xffffffffu;
+    if (tree.sr > 1)
+    {
+      #pragma unroll
+      for (int r = 0; r < R; ++r)
+      {
+        kr[r] = tree.scaler[((size_t) e.distal * n + site) * R + r] + tree.scaler[((size_t) e.proximal * n + site) * R + r];
+        kmin = min(kmin, kr[r]);
+      }
+    }
     #pragma unroll
     for (int r = 0; r < R; ++r)
     {
@@ -353,9 +388,11 @@ edge_logl_kernel(const DevModel * __restrict__ m, DevTree tree, int n, EdgeDev e
         for (int j = 0; j < S; ++j) tb += P[(r * S + i) * S + j] * bv[j];
         tr += av[i] * m->freqs[i] * tb;
       }
+      if (tree.sr > 1) tr *= rate_scale_factor(min(kr[r] - kmin, EPA_RATE_MAXDIFF));
       terma += tr * m->weights[r];
     }
-    const uint32_t sc = tree.scaler[(size_t) e.distal * n + site] + tree.scaler[(size_t) e.proximal * n + site];
+    const uint32_t sc = tree.sr > 1 ? kmin
+                                    : tree.scaler[(size_t) e.distal * n + site] + tree.scaler[(size_t) e.proximal * n + site];
     lk = log(terma) + (sc ? (double) sc * EPA_LOG_SCALE_THRESHOLD : 0.0);
   }
   red[threadIdx.x] = lk;

@@ -12,6 +12,7 @@ HOST_SYMBOLS = [
     ("epa_session_open", C.c_int, [C.POINTER(_vp), C.c_char_p, C.c_uint32, C.POINTER(C.c_char_p), _vp, C.c_uint32,
                                    C.c_char_p, C.c_int]),
     ("epa_session_place", C.c_int, [_vp, _vp, C.c_uint64, C.POINTER(capi.Options), C.c_uint32, _vp, _vp]),
+    ("epa_host_set_rate_scalers", C.c_int, [C.c_int, C.c_int]),
     ("epa_session_ctx", _vp, [_vp]),
     ("epa_session_num_edges", C.c_uint32, [_vp]),
     ("epa_session_num_tips", C.c_uint32, [_vp]),
@@ -71,8 +72,11 @@ class Session:
     """Reference tree + MSA + model resident on one GPU (mirrors the reference's Tree object)."""
 
     def __init__(self, newick: str, names, ref_rows: np.ndarray, model: str, device: int = 0, states: int = 4,
-                 rate_cats: int = 4):
+                 rate_cats: int = 4, rate_scalers: str = "auto", bugcompat_focus: bool = True):
+        """rate_scalers: "off", "on" or "auto" (the reference's --rate-scalers; auto = on above 2000 tips);
+        bugcompat_focus reproduces the reference's scaler window offset of the thorough phase."""
         L = lib()
+        _check(L.epa_host_set_rate_scalers({"off": 0, "on": 1, "auto": 2}[rate_scalers], int(bugcompat_focus)))
         ref_rows = np.ascontiguousarray(ref_rows, dtype=np.uint8)
         arr = (C.c_char_p * len(names))(*[n.encode() for n in names])
         self.handle = _vp()

@@ -57,6 +57,12 @@ void epa_session_close(epa_session * session);
 /* Whole run, files to jplace: what the reference's main() does for
  *   epa-ng -t tree -s ref_msa -q query -m model -w outdir [options]
  * Writes <outdir>/epa_result.jplace and <outdir>/epa_info.log. */
+/* Per-rate scaler policy of the sessions opened afterwards (the reference's --rate-scalers):
+ * mode 0 = off, 1 = on, 2 = auto (default: on for more than 2000 tips, src/tree/Tree_Numbers.hpp:11,
+ * src/io/file_io.cpp:211-214). bugcompat != 0 (default) reproduces the reference's scaler window
+ * offset in the thorough phase (shift_partition_focus, src/core/pll/pll_util.cpp:405-408). */
+int epa_host_set_rate_scalers(int mode, int bugcompat);
+
 int epa_run_files(const char * tree_file, const char * ref_msa_file, const char * query_file,
                   const char * model, const char * outdir, const epa_options * opts,
                   uint32_t chunk_size, int precision, int device, const char * invocation);

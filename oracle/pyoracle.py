@@ -734,7 +734,7 @@ class Placer:
         return pls[:keep]
 
 
-def run_files(tree_file, ref_msa, query_file, model_desc, opts: Options = None, per_rate=None):
+def run_files(tree_file, ref_msa, query_file, model_desc, opts: Options = None, per_rate=None, bugcompat=True):
     """Whole-run restatement of main.cpp:470-540 for unrooted trees; returns
     ({name: [Placement]}, numbered newick, Placer)."""
     opts = opts or Options()
@@ -746,6 +746,8 @@ def run_files(tree_file, ref_msa, query_file, model_desc, opts: Options = None, 
         rs, qs = apply_mask(rs, mask), apply_mask(qs, mask)
     tree = build_tree(open(tree_file).read())
     model.per_rate_scalers = (len(tree.tips) > 2000) if per_rate is None else per_rate
+    # the reference reads per-rate scalers of a window at a wrong offset: default = as it does
+    model.bugcompat_focus = bool(bugcompat) and model.per_rate_scalers
     ref = Reference(tree, model, rn, rs)
     placer = Placer(ref, opts)
     out = {}

@@ -95,11 +95,18 @@ def load_case(tree_file, ref_msa, query_file, model_desc, premasking=True, opts=
     return Case(model, tree, ref, placer, qn, qs, ref.n)
 
 
-def case_from_arrays(newick, names, ref_rows, qnames, query_rows, model_desc, opts=None) -> Case:
+def case_from_arrays(newick, names, ref_rows, qnames, query_rows, model_desc, opts=None, per_rate=False,
+                     bugcompat=False, column_mask=False) -> Case:
+    """column_mask: drop the columns that are all-gap in the reference or in the queries, as the
+    reference's pre-masking does before anything is computed (src/seq/MSA_Info.hpp:93-111)."""
     o = oracle()
     model = o.parse_model(model_desc)
+    model.per_rate_scalers, model.bugcompat_focus = bool(per_rate), bool(bugcompat)
     rs = [bytes(r).decode() for r in ref_rows]
     qs = [bytes(r).decode() for r in query_rows]
+    if column_mask:
+        mask = o.gap_mask(rs) | o.gap_mask(qs)
+        rs, qs = o.apply_mask(rs, mask), o.apply_mask(qs, mask)
     tree = o.build_tree(newick)
     ref = o.Reference(tree, model, list(names), rs)
     placer = o.Placer(ref, opts or o.Options())
@@ -114,7 +121,9 @@ def make_context(case: Case, device=0, compute=True):
     ctx = capi.Context(states=m.states, rate_cats=m.rate_cats, sites=case.n, eigenvals=m.eigenvals,
                        eigenvecs=m.eigenvecs, inv_eigenvecs=m.inv_eigenvecs, freqs=m.freqs, rates=m.rates,
                        weights=m.weights, tip_masks=case.tip_masks(), n_clv_slots=n_inner,
-                       edges=case.edges(ids, T), device=device)
+                       edges=case.edges(ids, T), device=device,
+                       flags=(capi.EPA_FLAG_RATE_SCALERS if getattr(m, "per_rate_scalers", False) else 0)
+                       | (capi.EPA_FLAG_BUGCOMPAT_FOCUS if getattr(m, "bugcompat_focus", False) else 0))
     ctx.ids = ids
     if compute:
         ctx.compute_clvs(case.ops(ids))

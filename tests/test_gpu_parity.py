@@ -395,3 +395,59 @@ def test_dense_chunk_placements_match_oracle(dense, built):
             assert abs(g["likelihood"] - p.logl) <= 1e-8 * abs(p.logl), (qi, g, p)
             assert abs(g["lwr"] - p.lwr) <= 1e-6
             assert abs(g["pendant_length"] - p.pendant) <= 1e-5 and abs(g["distal_length"] - p.distal) <= 1e-5
+
+
+# ---------------------------------------------------------------------------------------------
+# Per-rate scalers (EPA_FLAG_RATE_SCALERS; the reference's --rate-scalers on / auto above 2000 tips)
+# with and without the reference's scaler window offset (EPA_FLAG_BUGCOMPAT_FOCUS). The oracle's
+# per-rate path is pinned against the reference in tests/test_oracle_rate_scalers.py.
+# ---------------------------------------------------------------------------------------------
+@pytest.fixture(scope="module", params=[True, False], ids=["bugcompat", "corrected"])
+def rate300(built, request):
+    import json
+    import os
+    g = json.load(open(os.path.join(helpers.GOLDEN, "rate300", "reference_placements.json")))
+    ds = built.synth.dataset(**g["dataset"])
+    case = helpers.case_from_arrays(ds["newick"], ds["names"], ds["ref"], ds["qnames"], ds["queries"], ds["model"],
+                                    per_rate=True, bugcompat=request.param, column_mask=True)
+    ctx = helpers.make_context(case)
+    ctx.build_lookup()
+    yield case, ctx, (g["placements"] if request.param else None)
+    ctx.close()
+
+
+def test_per_rate_clvs_lookup_and_tree_logl(rate300):
+    case, ctx, _ = rate300
+    _check_clvs(case, ctx)
+    want = case.ref.tree_logl(0)
+    vals = [ctx.edge_loglikelihood(e) for e in range(0, case.tree.num_branches, 37)]
+    assert np.allclose(vals, want, rtol=1e-11, atol=0)
+    lk = case.placer.build_lookup()
+    for e in range(0, case.tree.num_branches, 23):
+        assert np.allclose(ctx.get_lookup(e), lk[e], rtol=1e-11, atol=1e-11), f"lookup of edge {e}"
+
+
+def test_per_rate_thorough_and_placements(rate300, built):
+    case, ctx, ref = rate300
+    opts = built.capi.default_options()
+    ctx.upload_queries(case.query_rows)
+    ctx.preplace()
+    ctx.select(opts)
+    ctx.place_pairs(opts)
+    q, e, raw = ctx.get_pairs()
+    for qi, ei, r in zip(q, e, raw):
+        p = case.placer.thorough(case.qseqs[qi], int(ei))
+        assert abs(r["likelihood"] - p.logl) <= 1e-8 * abs(p.logl), (qi, ei, r, p)
+        assert abs(r["pendant_length"] - p.pendant) <= 1e-5 and abs(r["distal_length"] - p.distal) <= 1e-5, (qi, ei, r, p)
+    out, counts = ctx.place_chunk(case.query_rows, opts)
+    for qi, name in enumerate(case.qnames):
+        got = out[qi][:counts[qi]]
+        want = case.placer.place(case.qseqs[qi])
+        assert [int(g["branch_id"]) for g in got] == [p.edge for p in want], name
+        if ref is not None:
+            # bug-compatible mode: the reference's own recorded placements
+            w = ref[name]
+            assert [int(g["branch_id"]) for g in got] == [int(x[0]) for x in w], name
+            for g, x in zip(got, w):
+                assert abs(g["likelihood"] - x[1]) <= 1e-6 * abs(x[1])
+                assert abs(g["lwr"] - x[2]) <= 1e-6 and abs(g["distal_length"] - x[3]) <= 1e-4 and abs(g["pendant_length"] - x[4]) <= 1e-4

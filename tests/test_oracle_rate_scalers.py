@@ -1,0 +1,56 @@
+"""Per-rate scalers (PLL_ATTRIB_RATE_SCALERS, the reference's --rate-scalers on / auto above 2000 tips):
+pins the oracle's per-rate path - including the reference's scaler window offset in the thorough
+phase - against placements recorded from the unmodified reference on a seeded
+300-taxon data set whose CLVs do get rescaled (tests/golden/make_golden_rate.py)."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+import helpers
+
+
+@pytest.fixture(scope="module")
+def rate300(built):
+    g = json.load(open(os.path.join(helpers.GOLDEN, "rate300", "reference_placements.json")))
+    ds = built.synth.dataset(**g["dataset"])
+    assert ds["model"] == g["model"]
+    return ds, g["placements"]
+
+
+def _case(ds, bugcompat):
+    return helpers.case_from_arrays(ds["newick"], ds["names"], ds["ref"], ds["qnames"], ds["queries"], ds["model"],
+                                    per_rate=True, bugcompat=bugcompat, column_mask=True)
+
+
+def test_scalers_are_exercised(rate300):
+    ds, _ = rate300
+    case = _case(ds, True)
+    counts = [int(side.scaler.max()) for side in case.ref.sides.values() if side.scaler is not None]
+    assert max(counts) >= 1, "no CLV of the fixture was rescaled: the test would not pin anything"
+
+
+def test_oracle_per_rate_bugcompat_matches_reference(rate300):
+    ds, want = rate300
+    case = _case(ds, True)
+    for name, seq in zip(case.qnames, case.qseqs):
+        got = case.placer.place(seq)
+        w = want[name]
+        assert [p.edge for p in got] == [int(x[0]) for x in w], name
+        for p, x in zip(got, w):
+            assert abs(p.logl - x[1]) <= 1e-9 * abs(x[1])
+            assert abs(p.lwr - x[2]) <= 1e-6 and abs(p.distal - x[3]) <= 1e-5 and abs(p.pendant - x[4]) <= 1e-5
+
+
+def test_corrected_focus_differs_from_reference(rate300):
+    """The offset is a real effect on this fixture: reading the scalers of the site itself gives
+    different log-likelihoods (documented deviation switch, not the default)."""
+    ds, want = rate300
+    case = _case(ds, False)
+    diff = 0
+    for name, seq in zip(case.qnames[:8], case.qseqs[:8]):
+        got = case.placer.place(seq)
+        if [p.edge for p in got] != [int(x[0]) for x in want[name]] or abs(got[0].logl - want[name][0][1]) > 1e-6 * abs(got[0].logl):
+            diff += 1
+    assert diff > 0
