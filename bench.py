@@ -115,6 +115,23 @@ def reference_arm(args):
     }))
 
 
+def ncu_traffic(kernel, q, chunk):
+    """DRAM bytes (read + write) of one launch of `kernel` from the committed ncu --set full summary
+    (profiles/r1_ncu_<kernel>.txt, captured on a 131 072-query chunk of this workload); None when
+    the launch of this run is not that size or the summary is missing."""
+    if min(q, chunk) != 131072:
+        return None
+    path = os.path.join(ROOT, "profiles", "r1_ncu_%s.txt" % kernel.replace("_kernel", ""))
+    if not os.path.exists(path):
+        return None
+    tot, scale = 0.0, {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    for line in open(path):
+        t = line.split()
+        if len(t) >= 3 and t[0] in ("dram__bytes_read.sum", "dram__bytes_write.sum") and t[2] in scale:
+            tot += float(t[1]) * scale[t[2]]
+    return tot or None
+
+
 def workload_config(q_per_gpu, gpus):
     return {"workload": "cfg2: 1k-taxon DNA tree (GTR+G4, 1000-site MSA), synthetic 200bp window queries, "
                         "preplacement heuristic -g 0.99999",
@@ -293,7 +310,7 @@ def ours(args):
                 "note": "bf16 dense peak in MEASURED_PEAKS.json; the 8-bit integer rate is nominally twice that"}
         n_launch = max(1, (Q + chunk - 1) // chunk)
         roofline = {"kernel": kname, "bound": "hbm", "achieved": kernels[dom]["achieved_gbs"], "peak": peak,
-                    "unit": "GB/s", "frac": kernels[dom]["frac"], "traffic": None, "peak_source": peak_src,
+                    "unit": "GB/s", "frac": kernels[dom]["frac"], "traffic": ncu_traffic(kname, Q, chunk), "peak_source": peak_src,
                     "launch_ms": kernels[dom]["ms_per_step"] / n_launch,
                     "algorithmic_bytes_per_launch": units[dom] * per_unit[dom] / n_launch}
 
