@@ -90,7 +90,7 @@ int main(int argc, char ** argv)
     else if (a == "--correct-scaler-focus") rate_bug = 0;     // not a reference option: read the scalers of the site itself
     else if (a == "--preserve-rooting") { const std::string v = need(i); preserve_rooting = (v != "off"); }
     else if (a == "--raxml-blo" || a == "-b" || a == "--binary" ||
-             a == "-B" || a == "--dump-binary" || a == "-c" || a == "--bfast" || a == "--split")
+             a == "-B" || a == "--dump-binary" || a == "-c" || a == "--bfast" || a == "--split")    // (bfast query FILES are read; the converter is not part of the path)
       die("option " + a + " is outside the accelerated hot path and not supported by this build");
     else die("unknown option " + a);
   }

@@ -2,9 +2,86 @@
 
 #include <cctype>
 #include <cstdio>
+#include <cstring>
 #include <stdexcept>
 
 namespace epa_host {
+
+// ---- bfast ------------------------------------------------------------------------------------
+// Layout (little endian, 64-bit integers), src/io/Binary_Fasta.hpp:33-96:
+//   "BFAST\0\0" (7 bytes) | n_sequences | mask: length + '0'/'1' characters (all-gap columns) |
+//   n x (sequence id, byte offset) | per sequence: label length + label, character count,
+//   ceil(count / 2) bytes of two 4-bit codes each (first character in the high nibble; code =
+//   index into "-TGKCYSBAWRDMHVN", src/util/maps.hpp:9-14; odd lengths are padded with code 0).
+static const char kBfastMagic[7] = {'B', 'F', 'A', 'S', 'T', '\0', '\0'};
+static const char kNtMap[17] = "-TGKCYSBAWRDMHVN";
+
+static std::string slurp(const std::string & path)
+{
+  FILE * fh = std::fopen(path.c_str(), "rb");
+  if (!fh) throw std::runtime_error("Cannot open file: " + path);
+  std::fseek(fh, 0, SEEK_END);
+  const long size = std::ftell(fh);
+  std::fseek(fh, 0, SEEK_SET);
+  std::string data((size_t) (size > 0 ? size : 0), '\0');
+  const bool ok = size <= 0 || std::fread(&data[0], 1, (size_t) size, fh) == (size_t) size;
+  std::fclose(fh);
+  if (!ok) throw std::runtime_error("Cannot read file: " + path);
+  return data;
+}
+
+bool is_bfast(const std::string & path)
+{
+  FILE * fh = std::fopen(path.c_str(), "rb");
+  if (!fh) return false;
+  char head[7] = {};
+  const size_t got = std::fread(head, 1, sizeof head, fh);
+  std::fclose(fh);
+  return got == sizeof head && std::memcmp(head, kBfastMagic, sizeof head) == 0;
+}
+
+Alignment read_bfast(const std::string & path)
+{
+  const std::string data = slurp(path);
+  size_t pos = 0;
+  auto need = [&](size_t n) { if (pos + n > data.size()) throw std::runtime_error(path + ": truncated bfast file"); };
+  auto u64 = [&]() { need(8); uint64_t v; std::memcpy(&v, data.data() + pos, 8); pos += 8; return v; };
+  need(sizeof kBfastMagic);
+  if (std::memcmp(data.data(), kBfastMagic, sizeof kBfastMagic) != 0) throw std::runtime_error("File is not an epa::Binary_Fasta file");
+  pos = sizeof kBfastMagic;
+  const uint64_t n_seq = u64();
+  const uint64_t mask_len = u64();
+  need(mask_len); pos += mask_len;                 // the stored all-gap mask is recomputed from the rows
+  need(n_seq * 16); pos += n_seq * 16;             // random-access table: entries are read in file order
+  Alignment a;
+  a.names.reserve(n_seq);
+  for (uint64_t i = 0; i < n_seq; ++i)
+  {
+    const uint64_t label_len = u64();
+    need(label_len);
+    a.names.emplace_back(data.substr(pos, label_len));
+    pos += label_len;
+    const uint64_t n_chars = u64();
+    if (i == 0) { a.sites = n_chars; a.rows.reserve(n_seq * n_chars); }
+    else if (n_chars != a.sites)
+      throw std::runtime_error(path + " does not contain equal size sequences! First offending sequence: " + a.names.back());
+    const size_t packed = (size_t) ((n_chars + 1) / 2);
+    need(packed);
+    for (uint64_t k = 0; k < n_chars; ++k)
+    {
+      const unsigned char byte = (unsigned char) data[pos + (k >> 1)];
+      a.rows.push_back((uint8_t) kNtMap[(k & 1) ? (byte & 15) : (byte >> 4)]);
+    }
+    pos += packed;
+  }
+  if (a.names.empty()) throw std::runtime_error(path + ": no sequences");
+  return a;
+}
+
+Alignment read_alignment(const std::string & path)
+{
+  return is_bfast(path) ? read_bfast(path) : read_fasta(path);
+}
 
 Alignment read_fasta(const std::string & path)
 {

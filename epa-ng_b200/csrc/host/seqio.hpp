@@ -18,6 +18,11 @@ struct Alignment {
 };
 
 Alignment read_fasta(const std::string & path);                       // throws std::runtime_error
+// Query files in the reference's binary 4-bit format (src/io/Binary_Fasta.hpp:33-96,252-310,
+// src/io/encoding.hpp): decoded back to upper-case rows; DNA only, like the reference's converter.
+bool is_bfast(const std::string & path);
+Alignment read_bfast(const std::string & path);
+Alignment read_alignment(const std::string & path);                  // bfast if the magic matches, FASTA otherwise
 std::vector<uint8_t> gap_mask(const Alignment & a);                  // 1 = every sequence has a gap character
 Alignment apply_mask(const Alignment & a, const std::vector<uint8_t> & drop);
 

@@ -313,7 +313,7 @@ extern "C" int epa_run_files_ex(const char * tree_file, const char * ref_msa_fil
     if (!tf) return host_fail(EPA_ERR_ARG, std::string("Cannot open file: ") + tree_file);
     std::string newick((std::istreambuf_iterator<char>(tf)), std::istreambuf_iterator<char>());
     Alignment ref = read_fasta(ref_msa_file);
-    Alignment qry = read_fasta(query_file);
+    Alignment qry = read_alignment(query_file);        // FASTA or the reference's bfast
     if (ref.sites != qry.sites)
       return host_fail(EPA_ERR_ARG, "reference and query MSA have different widths (" + std::to_string(ref.sites) + " vs " + std::to_string(qry.sites) + ")");
     if (opts->premasking)
@@ -398,6 +398,31 @@ extern "C" int epa_host_parse_tree(const char * newick, int precision, char * ou
     }
     if (n_tips) *n_tips = (uint32_t) t.num_tips();
     if (n_edges) *n_edges = (uint32_t) t.num_edges();
+    return EPA_OK;
+  }
+  catch (const std::exception & e) { return host_fail(EPA_ERR_ARG, e.what()); }
+}
+
+extern "C" int epa_host_read_alignment(const char * path, uint32_t * n_sequences, uint32_t * sites, char * rows,
+                                       size_t rows_cap, char * labels, size_t labels_cap)
+{
+  if (!path) return host_fail(EPA_ERR_ARG, "null argument");
+  try
+  {
+    const Alignment a = read_alignment(path);
+    if (n_sequences) *n_sequences = (uint32_t) a.size();
+    if (sites) *sites = (uint32_t) a.sites;
+    if (rows)
+    {
+      if (rows_cap < a.rows.size()) return host_fail(EPA_ERR_ARG, "rows buffer too small");
+      std::memcpy(rows, a.rows.data(), a.rows.size());
+    }
+    if (labels && labels_cap)
+    {
+      std::string all;
+      for (const auto & nm : a.names) { all += nm; all += '\n'; }
+      std::snprintf(labels, labels_cap, "%s", all.c_str());
+    }
     return EPA_OK;
   }
   catch (const std::exception & e) { return host_fail(EPA_ERR_ARG, e.what()); }

@@ -13,6 +13,7 @@ HOST_SYMBOLS = [
                                    C.c_char_p, C.c_int]),
     ("epa_session_place", C.c_int, [_vp, _vp, C.c_uint64, C.POINTER(capi.Options), C.c_uint32, _vp, _vp]),
     ("epa_host_set_rate_scalers", C.c_int, [C.c_int, C.c_int]),
+    ("epa_host_read_alignment", C.c_int, [C.c_char_p, _u32p, _u32p, _vp, C.c_size_t, C.c_char_p, C.c_size_t]),
     ("epa_session_ctx", _vp, [_vp]),
     ("epa_session_num_edges", C.c_uint32, [_vp]),
     ("epa_session_num_tips", C.c_uint32, [_vp]),
@@ -131,6 +132,17 @@ def run_files(tree_file, ref_msa, query_file, model, outdir, opts=None, chunk_si
     _check(lib().epa_run_files_ex(tree_file.encode(), ref_msa.encode(), query_file.encode(), model.encode(),
                                   outdir.encode(), C.byref(opts), chunk_size, precision, device, invocation.encode(),
                                   int(preserve_rooting)))
+
+
+def read_alignment(path: str):
+    """(names, uint8 rows [n][sites]) of a FASTA or bfast file, read by the host layer."""
+    n, sites = C.c_uint32(), C.c_uint32()
+    _check(lib().epa_host_read_alignment(path.encode(), C.byref(n), C.byref(sites), None, 0, None, 0))
+    rows = np.zeros((n.value, sites.value), dtype=np.uint8)
+    labels = C.create_string_buffer(64 * n.value + 1024)
+    _check(lib().epa_host_read_alignment(path.encode(), C.byref(n), C.byref(sites), rows.ctypes.data, rows.size, labels,
+                                         len(labels)))
+    return labels.value.decode().split("\n")[:n.value], rows
 
 
 def map_rooted(newick: str, edges, distal):

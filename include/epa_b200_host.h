@@ -81,6 +81,11 @@ int epa_write_jplace(const char * path, const char * numbered_newick, const char
 /* Parses the tree; writes the numbered newick (NUL-terminated, truncated to cap) and the counts. */
 int epa_host_parse_tree(const char * newick, int precision, char * out_newick, size_t cap,
                         uint32_t * n_tips, uint32_t * n_edges);
+/* Reads an aligned sequence file (FASTA, or the reference's bfast: src/io/Binary_Fasta.hpp) into
+ * upper-case rows [n][sites]; labels receives the names separated by '\n'. Pass rows = NULL to query
+ * the sizes only. */
+int epa_host_read_alignment(const char * path, uint32_t * n_sequences, uint32_t * sites, char * rows, size_t rows_cap,
+                            char * labels, size_t labels_cap);
 /* Rooted input only: translates (edge, distal length) pairs of the unrooted working tree to the
  * rooted tree, in place; writes the numbered newick of the working tree when out_newick != NULL. */
 int epa_host_map_rooted(const char * newick, uint32_t * edges, double * distal, uint32_t count,

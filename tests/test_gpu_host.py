@@ -105,3 +105,15 @@ def test_rooted_trees_match_reference(built, tmp_path, fname):
         got, doc = _read_jplace(os.path.join(out, "epa_result.jplace"))
         assert doc["tree"] == gold[rname]["tree"], rname
         _check(got, gold[rname]["placements"], f"{fname}/{rname}")
+
+
+def test_bfast_query_file_gives_the_same_jplace(built, tmp_path):
+    """A query file in the reference's binary 4-bit format (written by `epa-ng --bfast`) places like the FASTA."""
+    d = os.path.join(helpers.GOLDEN, "cfg1")
+    outs = {}
+    for kind, q in (("fasta", "query.fasta"), ("bfast", "query.fasta.bfast")):
+        out = str(tmp_path / kind)
+        built.session.run_files(os.path.join(d, "ref.tre"), os.path.join(d, "aln.fasta"), os.path.join(d, q), helpers.GTRG, out)
+        outs[kind], _ = _read_jplace(os.path.join(out, "epa_result.jplace"))
+    assert outs["fasta"] == outs["bfast"]
+    _check(outs["bfast"], helpers.golden("cfg1")["gtrg_default"]["placements"], "bfast")

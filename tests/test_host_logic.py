@@ -148,3 +148,19 @@ def test_rtree_mapper_goldens(sess):
         e, d, _ = sess.map_rooted(_read("cfg1", fname), [x[0] for x in u], [x[1] for x in u])
         assert [int(x) for x in e] == [x[0] for x in r], fname
         assert np.allclose(d, [x[1] for x in r], atol=1e-10), fname
+
+
+def test_bfast_reader_matches_fasta(built):
+    """Query files in the reference's binary 4-bit format (src/io/Binary_Fasta.hpp, src/io/encoding.hpp):
+    the fixtures were written by the reference's own converter (epa-ng --bfast)."""
+    import os
+    import numpy as np
+    g = os.path.join(os.path.dirname(__file__), "golden")
+    for fasta in (os.path.join(g, "bfast", "codes.fasta"), os.path.join(g, "cfg1", "query.fasta")):
+        n1, r1 = built.session.read_alignment(fasta)
+        n2, r2 = built.session.read_alignment(fasta + ".bfast")
+        assert n1 == n2
+        assert np.array_equal(r1, r2)
+    # every 4-bit code occurs in the first fixture
+    _, codes = built.session.read_alignment(os.path.join(g, "bfast", "codes.fasta.bfast"))
+    assert set(bytes(codes.reshape(-1)).decode()) == set("-TGKCYSBAWRDMHVN")
