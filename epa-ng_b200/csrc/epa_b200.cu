@@ -1135,7 +1135,7 @@ int launch_blo_site(epa_ctx * ctx, BloArgs & a)
   const size_t fix = (size_t) SiteWarpSmem<R>::SUM * sizeof(double);
   const size_t rows = (size_t) wmax * blo_row(R) * sizeof(double);
   const size_t budget = ctx->smem_optin - 2048;
-  const int max_warps = 12;
+  const int max_warps = SITE_MAX_WARPS;
   const int n_tm = (wmax <= SITE_TMEM_ROWS * 32 && !getenv("EPA_B200_NO_TMEM")) ? SITE_TMEM_WARPS : 0;
   int n_sm = 0;
   while (n_sm < (n_tm ? max_warps - n_tm : 9) && (size_t) (n_tm + n_sm + 1) * fix + (size_t) (n_sm + 1) * rows <= budget) ++n_sm;

@@ -40,7 +40,9 @@ __constant__ DevModel c_model;
 #define EPA_BLO_EPSILON 1e-1                          /* src/core/pll/optimize.hpp:9 */
 #define EPA_NR_MAX_ITERS 30
 #define EPA_SMOOTHINGS 32
+#ifndef EPA_WORK_BLOCK
 #define EPA_WORK_BLOCK 32u
+#endif
 
 struct BloResult { double logl, pendant, distal; };
 

@@ -79,6 +79,9 @@ struct SiteCtaSmem {
 // 8 rows per warp, two warps per 32-lane quarter. This lifts the shared-memory limit on the
 // number of pairs in flight per SM.
 constexpr int SITE_TMEM_WARPS = 8;
+#ifndef SITE_MAX_WARPS
+#define SITE_MAX_WARPS 12          /* warps per CTA: 12 x 32 threads x 168 registers fill the register file */
+#endif
 constexpr int SITE_TMEM_ROWS = 8;        // rows (trips of 32 sites) a TMEM-backed warp can hold: windows <= 256
 struct SumRef {
   double * base;
@@ -781,7 +784,7 @@ __device__ __forceinline__ unsigned long long site_next_item(SiteCtaSmem & cs, u
 // GS = sumtable in global scratch (windows that do not fit the shared-memory slice)
 // PR = per-rate scalers (the scaler pointers then address the node's [n][R] block, not the window)
 template <int R, bool GS, bool PR = false>
-__global__ void __launch_bounds__(384, 1)
+__global__ void __launch_bounds__(SITE_MAX_WARPS * 32, 1)
 blo_site_kernel(BloSiteArgs sa)
 {
   using L = SiteWarpSmem<R>;
