@@ -1079,13 +1079,19 @@ namespace {
 int ensure_clvT(epa_ctx * ctx)
 {
   if (ctx->clvT_ready) return EPA_OK;
-  const int C = ctx->R * 4;
-  const size_t t_stride = clvt_node_stride(ctx->n, ctx->R);
+  const int C = ctx->R * ctx->S;
+  const size_t t_stride = (size_t) ((ctx->n + CLVT_BLOCK - 1) / CLVT_BLOCK) * (size_t) C * CLVT_BLOCK;
   if (!ctx->d_clvT) CU(cudaMalloc(&ctx->d_clvT, (size_t) ctx->n_nodes * t_stride * sizeof(double)));
   dim3 grid((ctx->n + CLVT_BLOCK - 1) / CLVT_BLOCK, ctx->n_nodes);
   clv_site_block_kernel<<<grid, 256, (size_t) CLVT_BLOCK * (C + 1) * sizeof(double), ctx->stream>>>(
       ctx->tree.clv, ctx->tree.clv_stride, ctx->n, C, ctx->d_clvT, t_stride);
   LAUNCHED(ctx);
+  if (ctx->S != 4)
+  {
+    CU(cudaStreamSynchronize(ctx->stream));
+    ctx->clvT_ready = true;
+    return EPA_OK;
+  }
   // first-round tables: transition matrices of orig/2 per edge, then V * inner per (edge, site)
   const uint32_t B = ctx->n_edges;
   const size_t pm = (size_t) ctx->R * 16;
@@ -1252,9 +1258,15 @@ extern "C" int epa_place_pairs(epa_ctx * ctx, const epa_options * opts)
       }
     }
     else
+    {
+      const bool site = !getenv("EPA_B200_OLD_AA");
+      if (site)
+        if (int rc2 = ensure_clvT(ctx)) return rc2;
+      const size_t aa_stride = (size_t) ((ctx->n + CLVT_BLOCK - 1) / CLVT_BLOCK) * (size_t) (ctx->R * ctx->S) * CLVT_BLOCK;
       rc = launch_blo_generic(ctx->S, ctx->R, ctx->sm_count, ctx->smem_optin, ctx->max_span, ctx->d_model, a, &ctx->scratch.p,
-                              &ctx->scratch.cap, ctx->stream) == cudaSuccess ? EPA_OK
+                              &ctx->scratch.cap, ctx->stream, site ? ctx->d_clvT : nullptr, aa_stride) == cudaSuccess ? EPA_OK
            : fail(ctx, EPA_ERR_CUDA, "generic BLO launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+    }
     if (rc) return rc;
     if (ctx->S != 4) LAUNCHED(ctx);
   }

@@ -209,6 +209,186 @@ __device__ __forceinline__ void gen_pass_distal(double * sm, double * sum, int w
   __syncthreads();
 }
 
+// ---- lane = site CLV passes over the site-blocked CLV copy ------------------------------------
+// thread = site, loop over the rate categories: the transition matrices are warp-uniform 128-bit
+// shared-memory broadcasts (a (site, rate)-per-thread mapping needs one shared-memory word per FMA
+// and is bound by the shared-memory pipe at a quarter of the fp64 rate), the eigenvector tables are
+// constant-bank operands, the CLV components and the sumtable planes are coalesced, and there are no
+// cross-lane rate sums. No 2^256 rescaling inside the tiny tree (see kernels_blo_site.cuh).
+template <int S>
+__device__ __forceinline__ size_t clvt_off_c(int abs_site, int C)
+{
+  return (size_t) (abs_site >> 5) * (size_t) (C * 32) + (size_t) (abs_site & 31);
+}
+
+// Work unit = (rate, site) with the SITE index fastest: the threads of a warp share the rate (except
+// where a warp straddles two rates), R * w units keep 256 threads busy for any window length. The
+// per-rate contributions to the site likelihood and to the stationary sumtable entry go through
+// two small shared-memory arrays and are added over the rates in a fixed order afterwards.
+template <int S, int R>
+__device__ __forceinline__ double gen_pass_tip_site(double * sm, double * sum, int wpad, const double * __restrict__ DT,
+                                                    const double * __restrict__ XT, const uint32_t * __restrict__ sD,
+                                                    const uint32_t * __restrict__ sX, const uint8_t * __restrict__ qc,
+                                                    int begin, int w, double * rbuf)
+{
+  using L = GenSmem<S, R>;
+  double * termbuf = rbuf, * basebuf = rbuf + R * wpad;
+  for (int u = threadIdx.x; u < R * w; u += GEN_THREADS)
+  {
+    const int r = u / w, s = u - r * w;
+    const size_t off = clvt_off_c<S>(begin + s, R * S) + (size_t) (r * S) * 32;
+    const int code = qc[s] & (MAX_CODES - 1);
+    double dv[S], xv[S], in[S];
+    #pragma unroll
+    for (int k = 0; k < S; ++k) { dv[k] = __ldg(DT + off + (size_t) k * 32); xv[k] = __ldg(XT + off + (size_t) k * 32); }
+    const double2 * Pd = reinterpret_cast<const double2 *>(sm + L::P + r * L::PS);
+    const double2 * Pp = reinterpret_cast<const double2 *>(sm + L::P + (R + r) * L::PS);
+    #pragma unroll
+    for (int i = 0; i < S; ++i)
+    {
+      double ta = 0.0, tb = 0.0;
+      #pragma unroll
+      for (int j = 0; j < S / 2; ++j)
+      {
+        const double2 a = Pd[i * (S / 2) + j], b = Pp[i * (S / 2) + j];
+        ta += a.x * dv[2 * j]; ta += a.y * dv[2 * j + 1];
+        tb += b.x * xv[2 * j]; tb += b.y * xv[2 * j + 1];
+      }
+      in[i] = ta * tb;
+    }
+    const double * tvr = sm + L::TV + r * L::TVS + code * S;
+    const double * tl = sm + L::TIPLEFT + code * S;
+    const double wr = c_model.weights[r];
+    double tr = 0.0;
+    #pragma unroll
+    for (int i = 0; i < S; ++i) tr += (in[i] * c_model.freqs[i]) * tvr[i];
+    termbuf[r * wpad + s] = tr * wr;
+    #pragma unroll
+    for (int j = 0; j < S; ++j)
+    {
+      double right = 0.0;
+      #pragma unroll
+      for (int k = 0; k < S; ++k) right += c_model.eigenvecs[j * S + k] * in[k];
+      const double v = tl[j] * right;
+      if (j == 0) basebuf[r * wpad + s] = v * wr;
+      else sum[(size_t) (r * (S - 1) + j) * wpad + s] = v;
+    }
+  }
+  __syncthreads();
+  double acc = 0.0, unused = 0.0;
+  for (int s = threadIdx.x; s < w; s += GEN_THREADS)
+  {
+    double term = 0.0, base = 0.0;
+    #pragma unroll
+    for (int r = 0; r < R; ++r) { term += termbuf[r * wpad + s]; base += basebuf[r * wpad + s]; }
+    sum[s] = base;
+    const uint32_t scal = __ldg(sD + s) + __ldg(sX + s);
+    acc += log(term) + (scal ? (double) scal * EPA_LOG_SCALE_THRESHOLD : 0.0);
+  }
+  block_sum2(acc, unused, sm + L::RED);
+  return acc;
+}
+
+template <int S, int R>
+__device__ __forceinline__ void gen_pass_distal_site(double * sm, double * sum, int wpad, const double * __restrict__ DT,
+                                                     const double * __restrict__ XT, const uint8_t * __restrict__ qc,
+                                                     int begin, int w, double * rbuf)
+{
+  using L = GenSmem<S, R>;
+  double * basebuf = rbuf;
+  for (int u = threadIdx.x; u < R * w; u += GEN_THREADS)
+  {
+    const int r = u / w, s = u - r * w;
+    const size_t off = clvt_off_c<S>(begin + s, R * S) + (size_t) (r * S) * 32;
+    const int code = qc[s] & (MAX_CODES - 1);
+    double dv[S], xv[S], in[S];
+    #pragma unroll
+    for (int k = 0; k < S; ++k) { dv[k] = __ldg(DT + off + (size_t) k * 32); xv[k] = __ldg(XT + off + (size_t) k * 32); }
+    const double2 * Pp = reinterpret_cast<const double2 *>(sm + L::P + (R + r) * L::PS);
+    const double * tvr = sm + L::TV + r * L::TVS + code * S;
+    #pragma unroll
+    for (int i = 0; i < S; ++i)
+    {
+      double tb = 0.0;
+      #pragma unroll
+      for (int j = 0; j < S / 2; ++j)
+      {
+        const double2 b = Pp[i * (S / 2) + j];
+        tb += b.x * xv[2 * j]; tb += b.y * xv[2 * j + 1];
+      }
+      in[i] = tvr[i] * tb;
+    }
+    const double wr = c_model.weights[r];
+    #pragma unroll
+    for (int j = 0; j < S; ++j)
+    {
+      double left = 0.0, right = 0.0;
+      #pragma unroll
+      for (int k = 0; k < S; ++k) { left += dv[k] * c_model.pivinv[k * S + j]; right += c_model.eigenvecs[j * S + k] * in[k]; }
+      const double v = left * right;
+      if (j == 0) basebuf[r * wpad + s] = v * wr;
+      else sum[(size_t) (r * (S - 1) + j) * wpad + s] = v;
+    }
+  }
+  __syncthreads();
+  for (int s = threadIdx.x; s < w; s += GEN_THREADS)
+  {
+    double base = 0.0;
+    #pragma unroll
+    for (int r = 0; r < R; ++r) base += basebuf[r * wpad + s];
+    sum[s] = base;
+  }
+  __syncthreads();
+}
+
+// Derivative sums with (rate, site) work units (site fastest): every thread takes the S - 1 decaying
+// components of one rate of one site - all 256 threads stay busy for any window, the loads of a
+// unit are independent, the decay tables of the rate are warp-uniform shared-memory broadcasts -
+// and the per-rate partial sums are combined per site in a fixed order.
+template <int S, int R>
+__device__ __forceinline__ void gen_derivatives_units(double * sm, const double * sum, int wpad, int w, double t,
+                                                      double & f, double & df, double * rbuf)
+{
+  using L = GenSmem<S, R>;
+  constexpr int NK = L::NK;
+  __syncthreads();
+  for (int k = threadIdx.x; k < NK; k += GEN_THREADS)
+  {
+    const double lk = c_model.eigenvals[1 + k % (S - 1)] * c_model.rates[k / (S - 1)];
+    const double e = exp(lk * t) * c_model.weights[k / (S - 1)];
+    sm[L::DIAG + k] = e; sm[L::DIAG + NK + k] = lk * e; sm[L::DIAG + 2 * NK + k] = lk * lk * e;
+  }
+  __syncthreads();
+  double * b0 = rbuf, * b1 = rbuf + R * wpad, * b2 = rbuf + 2 * R * wpad;
+  for (int u = threadIdx.x; u < R * w; u += GEN_THREADS)
+  {
+    const int r = u / w, s = u - r * w;
+    const double * col = sum + (size_t) (r * (S - 1) + 1) * wpad + s;
+    const double * dg = sm + L::DIAG + r * (S - 1);
+    double x[S - 1];
+    #pragma unroll
+    for (int j = 0; j < S - 1; ++j) x[j] = col[(size_t) j * wpad];
+    double c0 = 0.0, c1 = 0.0, c2 = 0.0;
+    #pragma unroll
+    for (int j = 0; j < S - 1; ++j) { c0 += x[j] * dg[j]; c1 += x[j] * dg[NK + j]; c2 += x[j] * dg[2 * NK + j]; }
+    b0[r * wpad + s] = c0; b1[r * wpad + s] = c1; b2[r * wpad + s] = c2;
+  }
+  __syncthreads();
+  double a1 = 0.0, a2 = 0.0;
+  for (int s = threadIdx.x; s < w; s += GEN_THREADS)
+  {
+    double c0 = sum[s], c1 = 0.0, c2 = 0.0;
+    #pragma unroll
+    for (int r = 0; r < R; ++r) { c0 += b0[r * wpad + s]; c1 += b1[r * wpad + s]; c2 += b2[r * wpad + s]; }
+    const double inv = 1.0 / c0;
+    const double g1 = -c1 * inv;
+    a1 += g1;
+    a2 += g1 * g1 - c2 * inv;
+  }
+  block_sum2(a1, a2, sm + L::RED);
+  f = a1; df = a2;
+}
+
 template <int S, int R>
 __device__ __forceinline__ void gen_derivatives(double * sm, const double * sum, int wpad, int w, double t, double & f, double & df)
 {
@@ -243,7 +423,7 @@ __device__ __forceinline__ void gen_derivatives(double * sm, const double * sum,
 
 template <int S, int R>
 __device__ __forceinline__ double gen_newton(double * sm, const double * sum, int wpad, int w, double xmin, double xguess,
-                                             double xmax, double tol)
+                                             double xmax, double tol, double * rbuf)
 {
   double x = fmax(fmin(xguess, xmax), xmin);
   double xl = xmin, xh = xmax;
@@ -253,7 +433,8 @@ __device__ __forceinline__ double gen_newton(double * sm, const double * sum, in
   {
     if (iter++ > EPA_NR_MAX_ITERS) return 0.0;
     double f, df;
-    gen_derivatives<S, R>(sm, sum, wpad, w, x, f, df);
+    if (rbuf) gen_derivatives_units<S, R>(sm, sum, wpad, w, x, f, df, rbuf);
+    else gen_derivatives<S, R>(sm, sum, wpad, w, x, f, df);
     if (!isfinite(f) || !isfinite(df)) return 0.0;
     double dx;
     if (df > 0.0)
@@ -275,7 +456,7 @@ __device__ __forceinline__ double gen_newton(double * sm, const double * sum, in
 
 template <int S, int R>
 __global__ void __launch_bounds__(GEN_THREADS, 1)
-blo_generic_kernel(BloArgs a, int wpad)
+blo_generic_kernel(BloArgs a, int wpad, const double * __restrict__ clvT, size_t t_stride)
 {
   using L = GenSmem<S, R>;
   extern __shared__ __align__(16) double sm[];
@@ -355,7 +536,9 @@ blo_generic_kernel(BloArgs a, int wpad)
       double xmin, xmax, xguess;
       if (!distal_phase)
       {
-        const double new_logl = -gen_pass_tip<S, R>(sm, sum, wpad, D, X, sD, sX, qc, w);
+        const double new_logl = clvT
+            ? -gen_pass_tip_site<S, R>(sm, sum, wpad, clvT + (size_t) ed.distal * t_stride, clvT + (size_t) ed.proximal * t_stride, sD, sX, qc, begin, w, sm + L::TOTAL)
+            : -gen_pass_tip<S, R>(sm, sum, wpad, D, X, sD, sX, qc, w);
         if (first) { loglikelihood = new_logl; first = false; }
         else
         {
@@ -375,13 +558,16 @@ blo_generic_kernel(BloArgs a, int wpad)
       }
       else
       {
-        gen_pass_distal<S, R>(sm, sum, wpad, D, X, qc, w);
+        if (clvT)
+          gen_pass_distal_site<S, R>(sm, sum, wpad, clvT + (size_t) ed.distal * t_stride, clvT + (size_t) ed.proximal * t_stride, qc, begin, w, sm + L::TOTAL);
+        else
+          gen_pass_distal<S, R>(sm, sum, wpad, D, X, qc, w);
         xmin = fmin(EPA_MIN_BRLEN / 2.0, original_length / 2.0);
         xmax = original_length - xmin / 10.0;
         xguess = len[0];
         if (xguess < xmin || xguess > xmax) xguess = original_length / 2.0;
       }
-      const double xres = gen_newton<S, R>(sm, sum, wpad, w, xmin, xguess, xmax, xmin / 10.0);
+      const double xres = gen_newton<S, R>(sm, sum, wpad, w, xmin, xguess, xmax, xmin / 10.0, clvT ? sm + L::TOTAL : nullptr);
       if (xres > 0.0)
       {
         if (!distal_phase) { len[2] = xres; rebuild = 4u; }
@@ -403,12 +589,13 @@ blo_generic_kernel(BloArgs a, int wpad)
 // host-side launcher; scratch is (re)allocated by the caller-owned buffer
 template <int S, int R>
 inline cudaError_t launch_blo_generic_sr(int sm_count, size_t smem_optin, int max_span, BloArgs & a, void ** scratch,
-                                         size_t * scratch_cap, cudaStream_t stream)
+                                         size_t * scratch_cap, cudaStream_t stream, const double * clvT, size_t t_stride)
 {
   using L = GenSmem<S, R>;
-  const size_t smem = (size_t) L::TOTAL * sizeof(double);
-  if (smem > smem_optin) return cudaErrorInvalidConfiguration;
   const int wpad = (std::max(1, max_span) + 31) & ~31;
+  // fixed tables + (unit-mapped phases) per-rate partial sums [3][R][wpad]
+  const size_t smem = ((size_t) L::TOTAL + (clvT ? (size_t) 3 * R * wpad : 0)) * sizeof(double);
+  if (smem > smem_optin) return cudaErrorInvalidConfiguration;
   const int ctas_per_sm = (int) std::max<size_t>(1, std::min<size_t>(3, smem_optin / (smem + 1024)));
   const unsigned grid = (unsigned) std::min<uint64_t>((uint64_t) sm_count * ctas_per_sm, a.n_pairs);
   const size_t need = (size_t) grid * (1 + L::NK) * wpad * sizeof(double);
@@ -423,15 +610,16 @@ inline cudaError_t launch_blo_generic_sr(int sm_count, size_t smem_optin, int ma
   a.scratch = static_cast<double *>(*scratch);
   cudaError_t e = cudaFuncSetAttribute(blo_generic_kernel<S, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
   if (e != cudaSuccess) return e;
-  blo_generic_kernel<S, R><<<grid, GEN_THREADS, smem, stream>>>(a, wpad);
+  blo_generic_kernel<S, R><<<grid, GEN_THREADS, smem, stream>>>(a, wpad, clvT, t_stride);
   return cudaGetLastError();
 }
 
 inline cudaError_t launch_blo_generic(int S, int R, int sm_count, size_t smem_optin, int max_span, const DevModel *,
-                                      BloArgs & a, void ** scratch, size_t * scratch_cap, cudaStream_t stream)
+                                      BloArgs & a, void ** scratch, size_t * scratch_cap, cudaStream_t stream,
+                                      const double * clvT = nullptr, size_t t_stride = 0)
 {
-  if (S == 20 && R == 4) return launch_blo_generic_sr<20, 4>(sm_count, smem_optin, max_span, a, scratch, scratch_cap, stream);
-  if (S == 20 && R == 1) return launch_blo_generic_sr<20, 1>(sm_count, smem_optin, max_span, a, scratch, scratch_cap, stream);
+  if (S == 20 && R == 4) return launch_blo_generic_sr<20, 4>(sm_count, smem_optin, max_span, a, scratch, scratch_cap, stream, clvT, t_stride);
+  if (S == 20 && R == 1) return launch_blo_generic_sr<20, 1>(sm_count, smem_optin, max_span, a, scratch, scratch_cap, stream, clvT, t_stride);
   return cudaErrorNotSupported;
 }
 
