@@ -11,6 +11,11 @@
 //   CLV update / edge logl          LP/core_partials.c:202-352,612-766, LP/core_likelihood.c:351-578
 //   range focus                     src/core/pll/pll_util.cpp:388-418
 //
+// This file holds the shared definitions of the thorough kernels (constants, BloArgs, BloResult,
+// c_model) and the FIRST DNA kernel, which today only runs for 8 rate categories: DNA with 1, 2 or 4
+// categories takes the lane = site kernel of kernels_blo_site.cuh, amino acids the CTA-per-pair
+// kernel of kernels_blo_generic.cuh.
+//
 // DNA kernel (S = 4): ONE WARP PER PAIR, two lane mappings.
 //  * CLV passes (inner CLV, edge log-likelihood, sumtable build): R lanes share a site
 //    (lane % R = rate category), a warp sweeps 32/R sites per step and every lane reads exactly one
