@@ -171,6 +171,7 @@ blo_first_table_kernel(DevTree tree, int n, const EdgeDev * __restrict__ edges, 
 template <int R>
 __device__ __forceinline__ void site_pmatrix(const SiteCtaSmem & cs, double t, double * P, double * ex, int lane)
 {
+  __syncwarp();
   for (int idx = lane; idx < R * 4; idx += 32)
     ex[idx] = expm1(c_model.eigenvals[idx & 3] * c_model.rates[idx >> 2] * t);
   __syncwarp();
@@ -465,6 +466,7 @@ __device__ __forceinline__ void site_derivatives(const SumRef & sr, double * ex,
   warp_sum2(a1, a2, lane);
   f = a1;
   df = a2;
+  __syncwarp();            // the decay tables in `ex` are rewritten by the next evaluation / matrix build
 }
 
 // bounded Newton-Raphson, PM/optimize/opt_algorithms.c:133-262; returns 0.0 on failure
@@ -762,6 +764,8 @@ __device__ __forceinline__ void site_pass_distal(const double * ws, const SumRef
   if (!GS && sr.tm) tc_wait_st();
 }
 
+// (q_next, q_end are only touched under the q_lock spin lock; compute-sanitizer's racecheck does not
+// model the lock and reports them)
 __device__ __forceinline__ unsigned long long site_next_item(SiteCtaSmem & cs, unsigned long long * counter)
 {
   while (atomicCAS(&cs.q_lock, 0, 1) != 0) { }
