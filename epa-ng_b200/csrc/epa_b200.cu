@@ -1142,11 +1142,16 @@ int launch_blo_site(epa_ctx * ctx, BloArgs & a)
   const size_t rows = (size_t) wmax * blo_row(R) * sizeof(double);
   const size_t budget = ctx->smem_optin - 2048;
   const int max_warps = SITE_MAX_WARPS;
-  const int n_tm = (wmax <= SITE_TMEM_ROWS * 32 && !getenv("EPA_B200_NO_TMEM")) ? SITE_TMEM_WARPS : 0;
+  const bool tm_ok = !getenv("EPA_B200_NO_TMEM");
+  const int n_tm = !tm_ok ? 0 : (wmax <= SITE_TMEM_ROWS * 32 ? SITE_TMEM_WARPS : (wmax <= SITE_TMEM_ROWS * 64 ? SITE_TMEM_WARPS / 2 : 0));
+  sa.tmem_cols = wmax <= SITE_TMEM_ROWS * 32 ? 256 : 512;
   int n_sm = 0;
   while (n_sm < (n_tm ? max_warps - n_tm : 9) && (size_t) (n_tm + n_sm + 1) * fix + (size_t) (n_sm + 1) * rows <= budget) ++n_sm;
   int warps = n_tm + n_sm;
-  if (warps >= 2)
+  // few resident warps (long windows) lose to the global-scratch variant with 8 warps per SM (measured on
+  // 450..1000-site windows, tools/bench_window.py)
+  const int gs_below = getenv("EPA_B200_BLO_GS_BELOW") ? atoi(getenv("EPA_B200_BLO_GS_BELOW")) : 6;
+  if (warps >= gs_below)
   {
     a.wcap = wmax;
     sa.b = a;

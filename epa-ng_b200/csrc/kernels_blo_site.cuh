@@ -82,7 +82,8 @@ constexpr int SITE_TMEM_WARPS = 8;
 #ifndef SITE_MAX_WARPS
 #define SITE_MAX_WARPS 12          /* warps per CTA: 12 x 32 threads x 168 registers fill the register file */
 #endif
-constexpr int SITE_TMEM_ROWS = 8;        // rows (trips of 32 sites) a TMEM-backed warp can hold: windows <= 256
+constexpr int SITE_TMEM_ROWS = 8;        // rows (trips of 32 sites) of a TMEM-backed warp when 8 warps share the 512 columns:
+                                         // windows <= 256; windows <= 512 give 16 rows to 4 warps
 struct SumRef {
   double * base;
   int gstride;
@@ -111,6 +112,7 @@ struct BloSiteArgs {
   double * gscratch;                    // global sumtable scratch [warp][blo_row][wpad] (GS variant)
   int wpad;                             // padded window capacity of the global scratch
   int n_tmem_warps;                     // leading warps of a CTA that keep their sumtable in tensor memory
+  int tmem_cols;                        // TMEM columns per such warp: 256 (8 rows, 8 warps) or 512 (16 rows, 4 warps)
   // first-round tables (NULL = not available): every pair of an edge starts from the same three
   // lengths, so the inner CLV of the first pass, rotated into the eigenbasis, is per-edge data
   const double * gT;                    // [edge] site-blocked V * inner(orig/2, orig/2), scaled like the CLV update
@@ -832,7 +834,7 @@ blo_site_kernel(BloSiteArgs sa)
   double * ws = smem_d + (size_t) warp * FIX;
   SumRef sr;
   sr.tm = warp < n_tm ? 1 : 0;
-  sr.taddr = n_tm > 0 ? tmem_slot + ((uint32_t) ((warp & 3) * 32) << 16) + (uint32_t) (warp >> 2) * 256u : 0u;
+  sr.taddr = n_tm > 0 ? tmem_slot + ((uint32_t) ((warp & 3) * 32) << 16) + (uint32_t) (warp >> 2) * (uint32_t) sa.tmem_cols : 0u;
   sr.gstride = GS ? sa.wpad : 0;
   sr.base = GS ? sa.gscratch + ((size_t) blockIdx.x * n_warps + warp) * (size_t) sa.wpad * blo_row(R)
                : smem_d + (size_t) n_warps * FIX + (size_t) (warp - n_tm) * (size_t) a.wcap * blo_row(R);
