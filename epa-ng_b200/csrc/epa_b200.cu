@@ -1172,7 +1172,7 @@ int launch_blo_site(epa_ctx * ctx, BloArgs & a)
   }
   else
   {
-    warps = 8;
+    warps = getenv("EPA_B200_GS_WARPS") ? atoi(getenv("EPA_B200_GS_WARPS")) : 8;
     const unsigned grid = (unsigned) std::min<uint64_t>((uint64_t) ctx->sm_count, (a.n_pairs + warps - 1) / warps);
     sa.wpad = (wmax + 31) & ~31;
     CU(ctx->scratch.ensure((size_t) grid * warps * sa.wpad * blo_row(R) * sizeof(double)));

@@ -451,3 +451,23 @@ def test_per_rate_thorough_and_placements(rate300, built):
             for g, x in zip(got, w):
                 assert abs(g["likelihood"] - x[1]) <= 1e-6 * abs(x[1])
                 assert abs(g["lwr"] - x[2]) <= 1e-6 and abs(g["distal_length"] - x[3]) <= 1e-4 and abs(g["pendant_length"] - x[4]) <= 1e-4
+
+
+def test_mid_length_windows_tmem16_rows(built):
+    """Windows of 257..512 sites: the thorough kernel gives 16 tensor-memory rows to four warps and the
+    tensor-core preplacement splits K into two passes. Checked against the oracle on a sample."""
+    ds = built.synth.dataset(T=24, n_sites=640, n_queries=900, window=350, seed_tree=5, seed_q=6)
+    case = helpers.case_from_arrays(ds["newick"], ds["names"], ds["ref"], ds["qnames"], ds["queries"], ds["model"])
+    ctx = helpers.make_context(case)
+    ctx.build_lookup()
+    opts = built.capi.default_options()
+    out, counts = ctx.place_chunk(case.query_rows, opts)
+    for qi in range(0, len(case.qseqs), 60):
+        want = case.placer.place(case.qseqs[qi])
+        got = out[qi][:counts[qi]]
+        assert [int(g["branch_id"]) for g in got] == [p.edge for p in want], (qi, got, want)
+        for g, p in zip(got, want):
+            assert abs(g["likelihood"] - p.logl) <= 1e-8 * abs(p.logl), (qi, g, p)
+            assert abs(g["lwr"] - p.lwr) <= 1e-6
+            assert abs(g["pendant_length"] - p.pendant) <= 1e-5 and abs(g["distal_length"] - p.distal) <= 1e-5
+    ctx.close()
