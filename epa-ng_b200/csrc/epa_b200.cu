@@ -70,7 +70,8 @@ struct epa_ctx {
   std::vector<EdgeDev> h_edges;
   EdgeDev * d_edges = nullptr;
   double * d_lookup = nullptr;
-  double * d_pairtab = nullptr;    // DNA pair-sum tables [edge][n_pad/2][PAIR_ROW]
+  double * d_pairtab = nullptr;    // DNA pair-sum tables [edge][n_pad/2][PAIR_ROW] (fallback kernel, lazy)
+  bool pairtab_ready = false;
   uint8_t * d_btab = nullptr;      // DNA: fixed-point digit table of the tensor-core preplacement
   double * d_pn = nullptr;         // DNA: prefix sums of the fully-ambiguous lookup column [edge][n + 1]
   bool mma_ok = false;             // every table entry fits the fixed-point format
@@ -671,11 +672,7 @@ extern "C" int epa_build_lookup(epa_ctx * ctx)
   CU(cudaEventRecord(ctx->ev[1], ctx->stream));
   if (S == 4)
   {
-    // pair-sum tables of the DNA preplacement fast path (derived data, built once)
-    const size_t pair_doubles = (size_t) B * (ctx->n_pad / 2) * PAIR_ROW;
-    if (!ctx->d_pairtab) CU(cudaMalloc(&ctx->d_pairtab, pair_doubles * sizeof(double)));
-    pairtab_build_kernel<<<(unsigned) ((pair_doubles + 255) / 256), 256, 0, ctx->stream>>>(ctx->d_lookup, ctx->n_pad, B, ctx->d_pairtab);
-    LAUNCHED(ctx);
+    ctx->pairtab_ready = false;       // pair-sum tables of the fallback kernel are built on first use
     // fixed-point digit table + prefix sums of the tensor-core preplacement (kernels_preplace_mma.cuh)
     const int kc_total = mma_kc_total(n);
     const uint32_t n_eb = (B + MMA_EB - 1) / MMA_EB;
@@ -891,6 +888,14 @@ int launch_preplace(epa_ctx * ctx, uint32_t first, uint32_t count, const int2 * 
 int launch_preplace_pair(epa_ctx * ctx, uint32_t count, const int2 * range, int maxw)
 {
   constexpr int TQ = kPairTQ, NS = 2;
+  if (!ctx->pairtab_ready)
+  {
+    const size_t pair_doubles = (size_t) ctx->n_edges * (ctx->n_pad / 2) * PAIR_ROW;
+    if (!ctx->d_pairtab) CU(cudaMalloc(&ctx->d_pairtab, pair_doubles * sizeof(double)));
+    pairtab_build_kernel<<<(unsigned) ((pair_doubles + 255) / 256), 256, 0, ctx->stream>>>(ctx->d_lookup, ctx->n_pad, ctx->n_edges, ctx->d_pairtab);
+    LAUNCHED(ctx);
+    ctx->pairtab_ready = true;
+  }
   const uint32_t n_tiles = (count + TQ - 1) / TQ;
   // per 8 sites: 4 pair rows per stage + one index word per query
   const size_t per_word = (size_t) NS * 4 * PAIR_ROW * 8 + (size_t) TQ * 4;
@@ -939,7 +944,7 @@ extern "C" int epa_preplace(epa_ctx * ctx)
   CU(cudaMemsetAsync(ctx->qmax.p, 0xff, nq * sizeof(double), ctx->stream));      // NaN = no row maximum recorded
   // simple DNA queries (sorted first) take the tensor-core kernel (the pair-table kernel when the
   // digit table could not be built); the rest take the per-site kernel
-  const uint32_t nA = ctx->d_pairtab ? ctx->n_simple : 0u, nB = nq - nA;
+  const uint32_t nA = ctx->S == 4 ? ctx->n_simple : 0u, nB = nq - nA;
   const uint32_t tilesM = (nA + MMA_TQ - 1) / MMA_TQ;
   const uint32_t tilesA = (nA + kPairTQ - 1) / kPairTQ, tilesB = (nB + kPreplaceTQ - 1) / kPreplaceTQ;
   CU(ctx->range.ensure((size_t) (std::max(tilesA, tilesM) + tilesB) * sizeof(int2)));
