@@ -193,12 +193,28 @@ extern "C" int epa_session_place(epa_session * s, const char * query_rows, uint6
     DeferGuard(epa_ctx * c_, bool on_) : c(c_), on(on_) { if (on) epa_set_deferred_results(c, 1); }
     ~DeferGuard() { if (on) { epa_wait_results(c); epa_set_deferred_results(c, 0); } }
   } guard(s->ctx, defer);
-  for (uint64_t done = 0; done < n_queries; done += chunk_size)
+  // Chunk schedule: a short first chunk (its upload cannot overlap anything) and a short last one
+  // (neither can the copy of its records), full chunks in between. Results do not depend on the cut.
+  std::vector<uint32_t> sizes;
   {
-    const uint32_t nq = (uint32_t) std::min<uint64_t>(chunk_size, n_queries - done);
-    if (done + nq < n_queries)
-      epa_hint_next_chunk(s->ctx, query_rows + (done + nq) * s->sites,
-                          (uint32_t) std::min<uint64_t>(chunk_size, n_queries - done - nq));
+    uint64_t left = n_queries;
+    const uint32_t small = std::max<uint32_t>(4096u, chunk_size / 8);
+    if (left > (uint64_t) chunk_size + 2 * (uint64_t) small)
+    {
+      sizes.push_back(small); left -= small;
+      while (left > (uint64_t) chunk_size + small) { sizes.push_back(chunk_size); left -= chunk_size; }
+      if (left > small) { sizes.push_back((uint32_t) (left - small)); left = small; }
+      sizes.push_back((uint32_t) left);
+    }
+    else
+      while (left) { const uint32_t c = (uint32_t) std::min<uint64_t>(chunk_size, left); sizes.push_back(c); left -= c; }
+  }
+  uint64_t done = 0;
+  for (size_t ci = 0; ci < sizes.size(); done += sizes[ci], ++ci)
+  {
+    const uint32_t nq = sizes[ci];
+    if (ci + 1 < sizes.size())
+      epa_hint_next_chunk(s->ctx, query_rows + (done + nq) * s->sites, sizes[ci + 1]);
     const int rc = epa_place_chunk(s->ctx, query_rows + done * s->sites, nq, opts,
                                    out ? out + done * opts->filter_max : nullptr, counts ? counts + done : nullptr);
     if (rc)
