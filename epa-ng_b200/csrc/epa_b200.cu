@@ -103,6 +103,17 @@ struct epa_ctx {
   bool defer_results = false;
   const char * hint_ptr = nullptr; uint32_t hint_n = 0;         // announced next chunk
   const char * staged_ptr = nullptr; uint32_t staged_n = 0;     // chunk whose copy into raw_next is in flight
+  // developer switches (environment, read once at context creation): each one routes a stage back
+  // to its previous kernel so that two paths can be compared on the same inputs
+  struct Switches {
+    bool old_lookup = false;   // EPA_B200_OLD_LOOKUP: 4-lanes-per-site lookup build
+    bool no_mma = false;       // EPA_B200_NO_MMA: shared-memory preplacement kernels instead of tcgen05
+    bool no_first = false;     // EPA_B200_NO_FIRST: full first CLV pass instead of the per-edge tables
+    bool no_tmem = false;      // EPA_B200_NO_TMEM: sumtables in shared memory only
+    bool old_aa = false;       // EPA_B200_OLD_AA: (site, rate)-per-thread amino-acid passes
+    int gs_below = 6;          // EPA_B200_BLO_GS_BELOW: resident warps below which the global-scratch variant runs
+    int gs_warps = 8;          // EPA_B200_GS_WARPS: warps per CTA of the global-scratch variant
+  } sw;
   int * d_flags = nullptr;              // [0..1] error, [2] max tile width, [3] max span
   unsigned long long * d_counter = nullptr;
   uint64_t * d_total = nullptr;
@@ -327,6 +338,13 @@ extern "C" int epa_ctx_create(epa_ctx ** out, int device, const epa_model_desc *
   CUC(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
   for (auto & e : ctx->ev) CUC(cudaEventCreate(&e));
 
+  ctx->sw.old_lookup = getenv("EPA_B200_OLD_LOOKUP") != nullptr;
+  ctx->sw.no_mma = getenv("EPA_B200_NO_MMA") != nullptr;
+  ctx->sw.no_first = getenv("EPA_B200_NO_FIRST") != nullptr;
+  ctx->sw.no_tmem = getenv("EPA_B200_NO_TMEM") != nullptr;
+  ctx->sw.old_aa = getenv("EPA_B200_OLD_AA") != nullptr;
+  if (const char * v = getenv("EPA_B200_BLO_GS_BELOW")) ctx->sw.gs_below = atoi(v);
+  if (const char * v = getenv("EPA_B200_GS_WARPS")) ctx->sw.gs_warps = std::max(1, std::min(12, atoi(v)));
   DevModel & m = ctx->hm;
   memset(&m, 0, sizeof m);
   const int S = (int) model->states, R = (int) model->rate_cats;
@@ -630,7 +648,7 @@ extern "C" int epa_build_lookup(epa_ctx * ctx)
   if (S == 4) lookup_coltable_kernel<4><<<1, 256, 0, ctx->stream>>>(ctx->d_model, d_pm + (size_t) B * pm, d_col);
   else lookup_coltable_kernel<20><<<1, 256, 0, ctx->stream>>>(ctx->d_model, d_pm + (size_t) B * pm, d_col);
   LAUNCHED(ctx);
-  if (S == 4 && (R == 1 || R == 2 || R == 4) && (ctx->tree.sr > 1 || !getenv("EPA_B200_OLD_LOOKUP")))
+  if (S == 4 && (R == 1 || R == 2 || R == 4) && (ctx->tree.sr > 1 || !ctx->sw.old_lookup))
   {
     // lane = site kernel over the site-blocked CLV copy; its column table goes to constant memory
     // as [c][r][i] (the mutex covers copy + launch: the symbol is shared by the contexts of a process)
@@ -691,7 +709,7 @@ extern "C" int epa_build_lookup(epa_ctx * ctx)
     int bad = 1;
     CU(cudaMemcpyAsync(&bad, ctx->d_flags + 6, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
-    ctx->mma_ok = (bad == 0) && !getenv("EPA_B200_NO_MMA");
+    ctx->mma_ok = (bad == 0) && !ctx->sw.no_mma;
   }
   CU(cudaStreamSynchronize(ctx->stream));
   ctx->lookup_ready = true;
@@ -1136,7 +1154,7 @@ int launch_blo_site(epa_ctx * ctx, BloArgs & a)
   sa.clvT = ctx->d_clvT; sa.t_stride = clvt_node_stride(ctx->n, ctx->R);
   sa.bugcompat = ctx->hm.bugcompat;
   const bool pr = ctx->tree.sr > 1;
-  if (ctx->d_gT && ctx->lookup_ready && !pr && !getenv("EPA_B200_NO_FIRST"))
+  if (ctx->d_gT && ctx->lookup_ready && !pr && !ctx->sw.no_first)
   {
     sa.gT = ctx->d_gT; sa.g_stride = sa.t_stride; sa.lookup = ctx->d_lookup; sa.n_pad = ctx->n_pad;
   }
@@ -1147,7 +1165,7 @@ int launch_blo_site(epa_ctx * ctx, BloArgs & a)
   const size_t rows = (size_t) wmax * blo_row(R) * sizeof(double);
   const size_t budget = ctx->smem_optin - 2048;
   const int max_warps = SITE_MAX_WARPS;
-  const bool tm_ok = !getenv("EPA_B200_NO_TMEM");
+  const bool tm_ok = !ctx->sw.no_tmem;
   const int n_tm = !tm_ok ? 0 : (wmax <= SITE_TMEM_ROWS * 32 ? SITE_TMEM_WARPS : (wmax <= SITE_TMEM_ROWS * 64 ? SITE_TMEM_WARPS / 2 : 0));
   sa.tmem_cols = wmax <= SITE_TMEM_ROWS * 32 ? 256 : 512;
   int n_sm = 0;
@@ -1155,7 +1173,7 @@ int launch_blo_site(epa_ctx * ctx, BloArgs & a)
   int warps = n_tm + n_sm;
   // few resident warps (long windows) lose to the global-scratch variant with 8 warps per SM (measured on
   // 450..1000-site windows, tools/bench_window.py)
-  const int gs_below = getenv("EPA_B200_BLO_GS_BELOW") ? atoi(getenv("EPA_B200_BLO_GS_BELOW")) : 6;
+  const int gs_below = ctx->sw.gs_below;
   if (warps >= gs_below)
   {
     a.wcap = wmax;
@@ -1177,7 +1195,7 @@ int launch_blo_site(epa_ctx * ctx, BloArgs & a)
   }
   else
   {
-    warps = getenv("EPA_B200_GS_WARPS") ? atoi(getenv("EPA_B200_GS_WARPS")) : 8;
+    warps = ctx->sw.gs_warps;
     const unsigned grid = (unsigned) std::min<uint64_t>((uint64_t) ctx->sm_count, (a.n_pairs + warps - 1) / warps);
     sa.wpad = (wmax + 31) & ~31;
     CU(ctx->scratch.ensure((size_t) grid * warps * sa.wpad * blo_row(R) * sizeof(double)));
@@ -1269,7 +1287,7 @@ extern "C" int epa_place_pairs(epa_ctx * ctx, const epa_options * opts)
     }
     else
     {
-      const bool site = !getenv("EPA_B200_OLD_AA");
+      const bool site = !ctx->sw.old_aa;
       if (site)
         if (int rc2 = ensure_clvT(ctx)) return rc2;
       const size_t aa_stride = (size_t) ((ctx->n + CLVT_BLOCK - 1) / CLVT_BLOCK) * (size_t) (ctx->R * ctx->S) * CLVT_BLOCK;
