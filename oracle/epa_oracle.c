@@ -6,8 +6,8 @@
  * libs/libpll/src, PM = libs/pll-modules/src). Written from the published algorithms and
  * the reference's observable behaviour; no reference source is copied.
  *
- * Not supported (documented in DESIGN.md): proportion of invariant sites (+I),
- * ascertainment bias correction, site repeats, pattern weights != 1.
+ * Not supported (documented in DESIGN.md): ascertainment bias correction, site repeats,
+ * pattern weights != 1.
  */
 #include "epa_oracle.h"
 
@@ -259,6 +259,18 @@ int orc_eigen(int S, const double * subst, const double * freqs,
   return 1;
 }
 
+void orc_invariant_sites(int S, int n_tips, int n, const uint32_t * tip_masks, int * invariant)
+{
+  /* LP/models.c:651-760: start from the gap state (all bits), AND every tip's mask in */
+  const uint32_t gap = S >= 32 ? 0xffffffffu : ((1u << S) - 1u);
+  for (int s = 0; s < n; ++s)
+  {
+    uint32_t st = gap;
+    for (int t = 0; t < n_tips; ++t) st &= tip_masks[(size_t) t * n + s];
+    invariant[s] = (st == 0 || (st & (st - 1)) != 0) ? -1 : __builtin_ctz(st);
+  }
+}
+
 void orc_pmatrix(const orc_model_t * m, double t, double * pmat)
 {
   /* LP/core_pmatrix.c:185-249: P = I + Vinv diag(expm1(lambda r t)) V ; t == 0 -> I */
@@ -269,7 +281,11 @@ void orc_pmatrix(const orc_model_t * m, double t, double * pmat)
     double * P = pmat + (size_t) r * S * S;
     if (t > 0.)
     {
-      for (int j = 0; j < S; ++j) expd[j] = expm1(m->eigenvals[j] * m->rates[r] * t);
+      /* :209-220: with +I the rates are stretched by 1 / (1 - pinv) */
+      if (m->pinv > 1e-8)                     /* PLL_MISC_EPSILON, LP/pll.h:106 */
+        for (int j = 0; j < S; ++j) expd[j] = expm1(m->eigenvals[j] * m->rates[r] * t / (1.0 - m->pinv));
+      else
+        for (int j = 0; j < S; ++j) expd[j] = expm1(m->eigenvals[j] * m->rates[r] * t);
       for (int j = 0; j < S; ++j)
         for (int k = 0; k < S; ++k) temp[j * S + k] = m->inv_eigenvecs[j * S + k] * expd[k];
       for (int j = 0; j < S; ++j)
@@ -398,7 +414,7 @@ double orc_edge_logl(const orc_model_t * m, int n, const orc_side_t * parent,
   {
     unsigned int site_scalings =
         orc_site_scalings(m, P->scaler, C->tip ? NULL : C->scaler, s, rel);
-    double terma = 0;
+    double terma = 0, terminv = 0;
     for (int r = 0; r < R; ++r)
     {
       const double * clvp = P->clv + (size_t) s * span + r * S;
@@ -411,10 +427,29 @@ double orc_edge_logl(const orc_model_t * m, int n, const orc_side_t * parent,
         terma_r += clvp[j] * m->freqs[j] * termb;
       }
       if (m->per_rate_scalers && rel[r] > 0) terma_r *= minlh[rel[r] - 1];
-      terma += terma_r * m->weights[r];
+      /* core_likelihood.c:524-537: invariant-site mixture */
+      if (m->pinv > 0)
+      {
+        terma += m->weights[r] * terma_r * (1. - m->pinv);
+        if (m->invariant[s] != -1) terminv += m->weights[r] * m->freqs[m->invariant[s]] * m->pinv;
+      }
+      else
+        terma += terma_r * m->weights[r];
     }
-    double site_lk = log(terma);
-    if (site_scalings) site_lk += site_scalings * log(ORC_SCALE_THRESHOLD);
+    double site_lk;
+    if (site_scalings)
+    {
+      if (terminv > 0.)
+      {
+        /* :543-549: the scaling is undone for the variable term only */
+        unsigned int capped = site_scalings < ORC_RATE_MAXDIFF ? site_scalings : ORC_RATE_MAXDIFF;
+        site_lk = log(terma * minlh[capped - 1] + terminv);
+      }
+      else
+        site_lk = log(terma) + site_scalings * log(ORC_SCALE_THRESHOLD);
+    }
+    else
+      site_lk = log(terma + terminv);
     if (persite) persite[s] = site_lk;
     logl += site_lk;
   }
@@ -476,7 +511,7 @@ void orc_derivatives(const orc_model_t * m, int n, const double * sumtable, doub
   for (int r = 0; r < R; ++r)
     for (int j = 0; j < S; ++j)
     {
-      double lk = m->eigenvals[j] * m->rates[r];
+      double lk = m->eigenvals[j] * (m->rates[r] / (1.0 - m->pinv));      /* :757-772 ki */
       double e = exp(lk * t);
       diag[r * S + j][0] = e;
       diag[r * S + j][1] = lk * e;
@@ -495,6 +530,14 @@ void orc_derivatives(const orc_model_t * m, int n, const double * sumtable, doub
         c0 += sum[r * S + j] * diag[r * S + j][0];
         c1 += sum[r * S + j] * diag[r * S + j][1];
         c2 += sum[r * S + j] * diag[r * S + j][2];
+      }
+      if (m->pinv > 0)
+      {
+        /* :676-687: the invariant term enters unscaled, whatever the site's scaler count */
+        double inv_site_lk = m->invariant[s] == -1 ? 0 : m->freqs[m->invariant[s]] * m->pinv;
+        c0 = c0 * (1. - m->pinv) + inv_site_lk;
+        c1 = c1 * (1. - m->pinv);
+        c2 = c2 * (1. - m->pinv);
       }
       lk0 += c0 * m->weights[r];
       lk1 += c1 * m->weights[r];
@@ -625,12 +668,16 @@ static orc_side_t orc_focus(const orc_model_t * m, const orc_side_t * s, int beg
   return f;
 }
 
-void orc_place_thorough(const orc_model_t * m, int n_full, const orc_side_t * distal_full,
+void orc_place_thorough(const orc_model_t * m_full, int n_full, const orc_side_t * distal_full,
                         const orc_side_t * proximal_full, double orig_length,
                         const uint32_t * query_tip, int begin, int span,
                         orc_blo_result_t * out)
 {
   (void) n_full;
+  /* pll_util.cpp:413-414: the invariant array moves with the window */
+  orc_model_t m_focus = *m_full;
+  if (m_focus.invariant) m_focus.invariant += begin;
+  const orc_model_t * m = &m_focus;
   const int S = m->states, R = m->rate_cats, n = span;
   const size_t psz = (size_t) R * S * S;
   const orc_side_t distal = orc_focus(m, distal_full, begin);

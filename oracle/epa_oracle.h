@@ -37,6 +37,9 @@ typedef struct {
   const double * freqs;        /* [S] */
   const double * rates;        /* [R] */
   const double * weights;      /* [R] */
+  double pinv;                 /* proportion of invariant sites (+I), 0 = none (LP/models.c:495-544) */
+  const int * invariant;       /* [n] state index of an invariant site or -1 (LP/models.c:651-760);
+                                  may be NULL when pinv == 0 */
 } orc_model_t;
 
 /* one side of an edge / one child of an update: either a CLV (+ optional scaler) or tip masks */
@@ -60,6 +63,9 @@ int  orc_gamma_rates(double alpha, int ncat, int median, double * out_rates);
 /* libpll models.c:182-410: eigen system of sqrt(pi) Q sqrt(pi)^-1, mean rate 1 */
 int  orc_eigen(int S, const double * subst /*[S(S-1)/2]*/, const double * freqs,
                double * eigenvals, double * eigenvecs, double * inv_eigenvecs);
+/* libpll models.c:651-760 pll_update_invariant_sites: AND of all tip state masks per site;
+   a single remaining state -> its index, otherwise -1 */
+void orc_invariant_sites(int S, int n_tips, int n, const uint32_t * tip_masks /*[n_tips][n]*/, int * invariant);
 /* libpll core_pmatrix.c:185-249 */
 void orc_pmatrix(const orc_model_t * m, double t, double * pmat /*[R][S][S]*/);
 

@@ -50,7 +50,8 @@ class OrcModel(C.Structure):
                 ("bugcompat_focus", C.c_int),
                 ("eigenvals", C.POINTER(C.c_double)), ("eigenvecs", C.POINTER(C.c_double)),
                 ("inv_eigenvecs", C.POINTER(C.c_double)), ("freqs", C.POINTER(C.c_double)),
-                ("rates", C.POINTER(C.c_double)), ("weights", C.POINTER(C.c_double))]
+                ("rates", C.POINTER(C.c_double)), ("weights", C.POINTER(C.c_double)),
+                ("pinv", C.c_double), ("invariant", C.POINTER(C.c_int))]
 
 
 class OrcSide(C.Structure):
@@ -74,6 +75,7 @@ def lib():
         L.orc_eigen.argtypes = [C.c_int, dp, dp, dp, dp, dp]
         L.orc_eigen.restype = C.c_int
         L.orc_pmatrix.argtypes = [mp, C.c_double, dp]
+        L.orc_invariant_sites.argtypes = [C.c_int, C.c_int, C.c_int, up, ip]
         L.orc_update_partial.argtypes = [mp, C.c_int, dp, up, sp, dp, sp, dp]
         L.orc_edge_logl.argtypes = [mp, C.c_int, sp, sp, dp, dp]
         L.orc_edge_logl.restype = C.c_double
@@ -173,6 +175,8 @@ class Model:
     inv_eigenvecs: np.ndarray = None
     per_rate_scalers: bool = False
     bugcompat_focus: bool = False
+    pinv: float = 0.0                # +IU{p} (src/core/raxml/Model.cpp:355-380)
+    invariant: np.ndarray = None     # int32[n], filled by Reference from the tip masks when pinv > 0
     _c: OrcModel = field(default=None, repr=False)
 
     def finalize(self):
@@ -188,7 +192,8 @@ class Model:
     def c(self) -> OrcModel:
         m = OrcModel(self.states, self.rate_cats, int(self.per_rate_scalers), int(self.bugcompat_focus),
                      _dp(self.eigenvals), _dp(self.eigenvecs), _dp(self.inv_eigenvecs),
-                     _dp(self.freqs), _dp(self.rates), _dp(self.weights))
+                     _dp(self.freqs), _dp(self.rates), _dp(self.weights), float(self.pinv),
+                     self.invariant.ctypes.data_as(C.POINTER(C.c_int)) if self.invariant is not None else None)
         self._c = m
         return m
 
@@ -224,8 +229,9 @@ def gamma_rates(alpha: float, ncat: int, median: bool = False) -> np.ndarray:
 
 def parse_model(desc: str) -> Model:
     """Subset of the raxml-ng model grammar of src/core/raxml/Model.cpp:123-560:
-    DNA: JC, K80, F81, HKY, GTR with optional {rates}; +FU{..}/+FE/+FO/+F; +G[n][a|m][{alpha}].
-    (+I, +R, ASC and protein models are outside the oracle's scope.)"""
+    DNA: JC, K80, F81, HKY, GTR with optional {rates}; +FU{..}/+FE/+FO/+F; +G[n][a|m][{alpha}];
+    +IU{p} (and +I / +IO, which stay at the reference's unoptimised default of 0).
+    (+IC, +R and ASC are outside the oracle's scope.)"""
     pos = len(desc)
     for ch in "+{[":
         p = desc.find(ch)
@@ -259,7 +265,7 @@ def parse_model(desc: str) -> Model:
         else:
             subst = np.array([0.5] * 5 + [1.0])
         freqs = np.full(S, 1.0 / S)
-    alpha, ncat, median, gamma = 1.0, 1, False, False
+    alpha, ncat, median, gamma, pinv = 1.0, 1, False, False, 0.0
     vals, i = _read_braces(opts, 0)
     if vals is not None:
         if sym is None:
@@ -286,6 +292,19 @@ def parse_model(desc: str) -> Model:
                 freqs = np.full(S, 1.0 / S)
             else:
                 raise ValueError("oracle: empirical frequencies (+F/+FC) not supported")
+        elif ch == 'I':
+            mode = opts[i].upper() if i < len(opts) and opts[i] != '+' else 'O'
+            if i < len(opts) and opts[i] != '+':
+                i += 1
+            if mode == 'U':
+                vals, i = _read_braces(opts, i)
+                if vals is None:
+                    raise ValueError("Invalid p-inv specification")
+                pinv = vals[0]
+                if not (0.0 <= pinv < 1.0):
+                    raise ValueError("Invalid proportion of invariant sites")
+            elif mode != 'O':
+                raise ValueError("oracle: empirical p-inv (+IC) not supported")
         elif ch == 'G':
             gamma = True
             num = ""
@@ -304,7 +323,7 @@ def parse_model(desc: str) -> Model:
             raise ValueError(f"oracle: unsupported model option +{ch}")
     rates = gamma_rates(alpha, ncat, median) if gamma and ncat > 1 else np.ones(ncat)
     weights = np.full(ncat, 1.0 / ncat)
-    return Model(S, subst, freqs, alpha, ncat, rates, weights).finalize()
+    return Model(S, subst, freqs, alpha, ncat, rates, weights, pinv=pinv).finalize()
 
 
 # --------------------------------------------------------------------------------------------
@@ -578,6 +597,13 @@ class Reference:
                 raise ValueError("invalid character in reference MSA")
             self.sides[t.uid] = SideData(tip=np.ascontiguousarray(m))
         self._pm_cache = {}
+        if model.pinv > 0:
+            # pll_update_invariant_sites_proportion -> pll_update_invariant_sites, called by
+            # raxml::assign after the tips are linked (src/core/pll/epa_pll_util.cpp:59)
+            masks = np.ascontiguousarray(np.stack([self.sides[t.uid].tip for t in tree.tips]))
+            model.invariant = np.zeros(self.n, dtype=np.int32)
+            lib().orc_invariant_sites(S, len(tree.tips), self.n, _up(masks),
+                                      model.invariant.ctypes.data_as(C.POINTER(C.c_int)))
         mc = model.c()
         ssz = self.n * (R if model.per_rate_scalers else 1)
 
