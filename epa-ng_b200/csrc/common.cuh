@@ -46,6 +46,9 @@ struct DevTree {
   uint32_t n_tips;
   uint32_t n_nodes;
   uint32_t sr;                                    // scaler entries per site
+  const double * inv;                             // +I models: [n] invariant-site term of a site likelihood,
+                                                  // pinv * freq[state] * sum of rate weights where all tips share
+                                                  // one state, else 0 (LP/models.c:651-760); NULL when pinv = 0
 };
 
 // libpll caps the per-rate scaler difference of a site (PLL_SCALE_RATE_MAXDIFF, LP/pll.h:104)
@@ -56,6 +59,17 @@ __device__ __forceinline__ double rate_scale_factor(uint32_t d)
 {
   const int hi = d == 0 ? 0x3ff00000 : (d == 1 ? 0x2ff00000 : (d == 2 ? 0x1ff00000 : (d == 3 ? 0x0ff00000 : 0x00040000)));
   return __hiloint2double(hi, 0);
+}
+
+// Logarithm of a site likelihood under a +I model (LP/core_likelihood.c:524-556). `term` already
+// carries the factor (1 - pinv) through the rate weights, `inv` is the site's invariant term (0 for a
+// variable site or a model without +I), `sc` its scaler count: where the invariant term is present
+// the scaling is undone on the variable term (capped like the per-rate differences) instead of being
+// added to the logarithm.
+__device__ __forceinline__ double site_loglk(double term, uint32_t sc, double inv)
+{
+  if (inv > 0.0) return log(sc ? term * rate_scale_factor(min(sc, EPA_RATE_MAXDIFF)) + inv : term + inv);
+  return log(term) + (sc ? (double) sc * EPA_LOG_SCALE_THRESHOLD : 0.0);
 }
 
 struct ClvOpDev {

@@ -276,6 +276,7 @@ extern "C" void epa_ctx_destroy(epa_ctx * ctx)
   if (ctx->ev_collect) cudaEventDestroy(ctx->ev_collect);
   for (auto & e : ctx->ev_d2h) if (e) cudaEventDestroy(e);
   cudaFree(ctx->d_model); cudaFree(ctx->tree.clv); cudaFree(ctx->tree.scaler); cudaFree(ctx->d_edges);
+  cudaFree(const_cast<double *>(ctx->tree.inv));
   cudaFree(ctx->d_lookup); cudaFree(ctx->d_pairtab); cudaFree(ctx->d_clvT); cudaFree(ctx->d_gT); cudaFree(ctx->d_btab); cudaFree(ctx->d_pn); cudaFree(ctx->d_flags); cudaFree(ctx->d_counter); cudaFree(ctx->d_total);
   for (auto & e : ctx->ev) if (e) cudaEventDestroy(e);
   if (ctx->stream && ctx->own_stream) cudaStreamDestroy(ctx->stream);
@@ -293,7 +294,8 @@ extern "C" int epa_ctx_create(epa_ctx ** out, int device, const epa_model_desc *
     return fail(ctx, EPA_ERR_ARG, "unsupported states/rate_cats combination %u/%u", model->states, model->rate_cats);
   if ((model->flags & EPA_FLAG_RATE_SCALERS) && !(model->states == 4 && model->rate_cats <= 4))
     return fail(ctx, EPA_ERR_ARG, "per-rate scalers are only supported for DNA with at most 4 rate categories");
-  if (model->pinv != 0.0) return fail(ctx, EPA_ERR_ARG, "+I models are not supported");
+  if (!(model->pinv >= 0.0 && model->pinv < 1.0))        // LP/models.c:510-518
+    return fail(ctx, EPA_ERR_ARG, "Invalid proportion of invariant sites (%f)", model->pinv);
   if (model->sites == 0 || n_tips < 3 || n_edges == 0) return fail(ctx, EPA_ERR_ARG, "empty tree or alignment");
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
@@ -375,7 +377,15 @@ extern "C" int epa_ctx_create(epa_ctx ** out, int device, const epa_model_desc *
     }
   }
   for (int i = 0; i < S * S; ++i) m.pivinv[i] = m.freqs[i / S] * m.inv_eigenvecs[i];
-  for (int r = 0; r < R; ++r) { m.rates[r] = model->rates[r]; m.weights[r] = model->rate_weights[r]; }
+  // +I (LP/core_pmatrix.c:209-220, LP/core_derivatives.c:757-772, LP/core_likelihood.c:524-537): the
+  // rates are stretched by 1 / (1 - pinv) wherever a branch length meets them, and the variable part
+  // of every site likelihood carries (1 - pinv) - folded into the rate weights here
+  const double pinv = model->pinv;
+  for (int r = 0; r < R; ++r)
+  {
+    m.rates[r] = pinv > 0.0 ? model->rates[r] / (1.0 - pinv) : model->rates[r];
+    m.weights[r] = pinv > 0.0 ? model->rate_weights[r] * (1.0 - pinv) : model->rate_weights[r];
+  }
   build_char_tables(m);
   ctx->S = S; ctx->R = R; ctx->n = m.n; ctx->n_pad = (m.n + 3) & ~3; ctx->K = m.K;
   ctx->n_tips = n_tips; ctx->n_slots = n_clv_slots; ctx->n_nodes = n_tips + n_clv_slots; ctx->n_edges = n_edges;
@@ -391,6 +401,30 @@ extern "C" int epa_ctx_create(epa_ctx ** out, int device, const epa_model_desc *
       return bail(EPA_ERR_ARG);
     }
 
+  ctx->tree.inv = nullptr;
+  if (pinv > 0.0)
+  {
+    // pll_update_invariant_sites (LP/models.c:651-760): a site is invariant when the AND of all tip
+    // masks leaves exactly one state; its term of the site likelihood is pinv * freq[state], summed
+    // over the rate categories with their weights (LP/core_likelihood.c:529-533)
+    std::vector<double> inv((size_t) m.n, 0.0);
+    for (int s = 0; s < m.n; ++s)
+    {
+      uint32_t st = all;
+      for (uint32_t t = 0; t < n_tips; ++t) st &= tip_masks[(size_t) t * m.n + s];
+      if (st != 0 && (st & (st - 1)) == 0)
+      {
+        const double f = model->freqs[__builtin_ctz(st)];
+        double acc = 0.0;
+        for (int r = 0; r < R; ++r) acc += model->rate_weights[r] * f * pinv;
+        inv[s] = acc;
+      }
+    }
+    double * d_inv = nullptr;
+    CUC(cudaMalloc(&d_inv, inv.size() * sizeof(double)));
+    ctx->tree.inv = d_inv;
+    CUC(cudaMemcpy(d_inv, inv.data(), inv.size() * sizeof(double), cudaMemcpyHostToDevice));
+  }
   CUC(cudaMalloc(&ctx->d_model, sizeof(DevModel)));
   CUC(cudaMemcpy(ctx->d_model, &m, sizeof(DevModel), cudaMemcpyHostToDevice));
   ctx->tree.clv_stride = (size_t) m.n * R * S;
@@ -666,9 +700,9 @@ extern "C" int epa_build_lookup(epa_ctx * ctx)
       CU(cudaEventRecord(ctx->ev[0], ctx->stream));
       switch (R)
       {
-        case 1: lookup_build_site_kernel<1><<<grid, 128, 0, ctx->stream>>>(ctx->d_model, ctx->d_clvT, t_stride, ctx->tree.scaler, (int) ctx->tree.sr, n, ctx->n_pad, ctx->d_edges, d_pm, ctx->d_lookup); break;
-        case 2: lookup_build_site_kernel<2><<<grid, 128, 0, ctx->stream>>>(ctx->d_model, ctx->d_clvT, t_stride, ctx->tree.scaler, (int) ctx->tree.sr, n, ctx->n_pad, ctx->d_edges, d_pm, ctx->d_lookup); break;
-        default: lookup_build_site_kernel<4><<<grid, 128, 0, ctx->stream>>>(ctx->d_model, ctx->d_clvT, t_stride, ctx->tree.scaler, (int) ctx->tree.sr, n, ctx->n_pad, ctx->d_edges, d_pm, ctx->d_lookup); break;
+        case 1: lookup_build_site_kernel<1><<<grid, 128, 0, ctx->stream>>>(ctx->d_model, ctx->d_clvT, t_stride, ctx->tree.scaler, (int) ctx->tree.sr, ctx->tree.inv, n, ctx->n_pad, ctx->d_edges, d_pm, ctx->d_lookup); break;
+        case 2: lookup_build_site_kernel<2><<<grid, 128, 0, ctx->stream>>>(ctx->d_model, ctx->d_clvT, t_stride, ctx->tree.scaler, (int) ctx->tree.sr, ctx->tree.inv, n, ctx->n_pad, ctx->d_edges, d_pm, ctx->d_lookup); break;
+        default: lookup_build_site_kernel<4><<<grid, 128, 0, ctx->stream>>>(ctx->d_model, ctx->d_clvT, t_stride, ctx->tree.scaler, (int) ctx->tree.sr, ctx->tree.inv, n, ctx->n_pad, ctx->d_edges, d_pm, ctx->d_lookup); break;
       }
       LAUNCHED(ctx);
       CU(cudaStreamSynchronize(ctx->stream));
@@ -1145,6 +1179,25 @@ int ensure_clvT(epa_ctx * ctx)
   return EPA_OK;
 }
 
+// one instantiation of the lane = site kernel: GS = sumtable in global scratch, pr = per-rate
+// scalers, inv = +I model
+template <int R, bool GS, bool PR, bool INV>
+int launch_site_kernel(epa_ctx * ctx, const BloSiteArgs & sa, unsigned grid, int warps, size_t smem)
+{
+  CU(cudaFuncSetAttribute(blo_site_kernel<R, GS, PR, INV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+  blo_site_kernel<R, GS, PR, INV><<<grid, warps * 32, smem, ctx->stream>>>(sa);
+  return EPA_OK;
+}
+
+template <int R, bool GS>
+int launch_site_variant(epa_ctx * ctx, const BloSiteArgs & sa, unsigned grid, int warps, size_t smem, bool pr, bool inv)
+{
+  if (pr) return inv ? launch_site_kernel<R, GS, true, true>(ctx, sa, grid, warps, smem)
+                     : launch_site_kernel<R, GS, true, false>(ctx, sa, grid, warps, smem);
+  return inv ? launch_site_kernel<R, GS, false, true>(ctx, sa, grid, warps, smem)
+             : launch_site_kernel<R, GS, false, false>(ctx, sa, grid, warps, smem);
+}
+
 // R = 1, 2, 4: lane = site kernel (kernels_blo_site.cuh)
 template <int R>
 int launch_blo_site(epa_ctx * ctx, BloArgs & a)
@@ -1153,7 +1206,7 @@ int launch_blo_site(epa_ctx * ctx, BloArgs & a)
   BloSiteArgs sa{};
   sa.clvT = ctx->d_clvT; sa.t_stride = clvt_node_stride(ctx->n, ctx->R);
   sa.bugcompat = ctx->hm.bugcompat;
-  const bool pr = ctx->tree.sr > 1;
+  const bool pr = ctx->tree.sr > 1, inv = ctx->tree.inv != nullptr;
   if (ctx->d_gT && ctx->lookup_ready && !pr && !ctx->sw.no_first)
   {
     sa.gT = ctx->d_gT; sa.g_stride = sa.t_stride; sa.lookup = ctx->d_lookup; sa.n_pad = ctx->n_pad;
@@ -1182,16 +1235,7 @@ int launch_blo_site(epa_ctx * ctx, BloArgs & a)
     const size_t smem = (size_t) warps * fix + (size_t) n_sm * rows;
     uint64_t grid = (uint64_t) ctx->sm_count;
     grid = std::min<uint64_t>(grid, (a.n_pairs + warps - 1) / warps);
-    if (pr)
-    {
-      CU(cudaFuncSetAttribute(blo_site_kernel<R, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
-      blo_site_kernel<R, false, true><<<(unsigned) grid, warps * 32, smem, ctx->stream>>>(sa);
-    }
-    else
-    {
-      CU(cudaFuncSetAttribute(blo_site_kernel<R, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
-      blo_site_kernel<R, false><<<(unsigned) grid, warps * 32, smem, ctx->stream>>>(sa);
-    }
+    if (int rc = launch_site_variant<R, false>(ctx, sa, (unsigned) grid, warps, smem, pr, inv)) return rc;
   }
   else
   {
@@ -1203,16 +1247,7 @@ int launch_blo_site(epa_ctx * ctx, BloArgs & a)
     a.wcap = 0;
     sa.b = a;
     const size_t smem = SiteWarpSmem<R>::doubles(0) * sizeof(double) * warps;
-    if (pr)
-    {
-      CU(cudaFuncSetAttribute(blo_site_kernel<R, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
-      blo_site_kernel<R, true, true><<<grid, warps * 32, smem, ctx->stream>>>(sa);
-    }
-    else
-    {
-      CU(cudaFuncSetAttribute(blo_site_kernel<R, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
-      blo_site_kernel<R, true><<<grid, warps * 32, smem, ctx->stream>>>(sa);
-    }
+    if (int rc = launch_site_variant<R, true>(ctx, sa, grid, warps, smem, pr, inv)) return rc;
   }
   LAUNCHED(ctx);
   return EPA_OK;

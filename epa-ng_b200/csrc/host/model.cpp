@@ -319,8 +319,24 @@ Model Model::parse(const std::string & desc)
       vals = braces(opts, i, present);
       if (present) m.alpha = vals.at(0);
     }
+    else if (ch == 'I')
+    {
+      // src/core/raxml/Model.cpp:355-380: +I / +IO = ML mode (stays at the reference's unoptimised start
+      // value 0, Model.cpp:192), +IU{p} = user value, +IC = empirical (needs alignment statistics)
+      char mode = 'O';
+      if (i < opts.size() && opts[i] != '+') mode = (char) std::toupper((unsigned char) opts[i++]);
+      if (mode == 'U')
+      {
+        vals = braces(opts, i, present);
+        if (!present || vals.empty()) throw std::runtime_error("Invalid p-inv specification: " + desc);
+        m.pinv = vals[0];
+        if (!(m.pinv >= 0.0 && m.pinv < 1.0)) throw std::runtime_error("Invalid proportion of invariant sites: " + desc);
+      }
+      else if (mode != 'O')
+        throw std::runtime_error("model: empirical p-inv (+IC) needs alignment statistics; give +IU{p}");
+    }
     else
-      throw std::runtime_error(std::string("unsupported model option +") + ch + " (supported: +F{U,E,O}, +G)");
+      throw std::runtime_error(std::string("unsupported model option +") + ch + " (supported: +F{U,E,O}, +G, +IU{p})");
   }
   m.rates = (gamma && m.rate_cats > 1) ? discrete_gamma_rates(m.alpha, m.rate_cats, m.gamma_median)
                                        : std::vector<double>((size_t) m.rate_cats, 1.0);
@@ -340,6 +356,7 @@ std::string Model::describe() const
     for (int r = 0; r < rate_cats; ++r) os << "(" << weights[r] << "," << rates[r] << ") ";
   }
   else os << "NONE";
+  if (pinv > 0.0) os << "\n        P-inv (user): " << pinv;
   os << "\n        Base frequencies (user): ";
   for (double f : freqs) os << f << " ";
   if (states == 4)

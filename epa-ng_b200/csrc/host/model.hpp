@@ -1,8 +1,8 @@
 // model.hpp - substitution model of the host layer: the subset of the raxml-ng model grammar that
 // the reference accepts through -m (src/core/raxml/Model.cpp:123-560) and that the device path
 // supports: DNA JC/K80/F81/HKY/GTR and the protein matrices compiled into protein_models.cpp, with
-// user or equal frequencies (+FU{..}/+FE/+FO), and discrete GAMMA rate heterogeneity (+G[n][a|m]{alpha}).
-// +I, +R, ascertainment correction and per-rate scalers are rejected with a clear message.
+// user or equal frequencies (+FU{..}/+FE/+FO), discrete GAMMA rate heterogeneity (+G[n][a|m]{alpha}) and a
+// user proportion of invariant sites (+IU{p}). +R and ascertainment correction are rejected with a clear message.
 #pragma once
 #include <string>
 #include <vector>
@@ -17,6 +17,7 @@ struct Model {
   double alpha = 1.0;
   int rate_cats = 1;
   bool gamma_median = false;
+  double pinv = 0.0;                // +IU{p} (src/core/raxml/Model.cpp:355-380)
   std::vector<double> rates, weights;
   std::vector<double> eigenvals, eigenvecs, inv_eigenvecs;   // libpll layout (models.c:394-404)
 

@@ -134,7 +134,7 @@ extern "C" int epa_session_open(epa_session ** out, const char * newick, uint32_
     md.freqs = s->model.freqs.data();
     md.rates = s->model.rates.data();
     md.rate_weights = s->model.weights.data();
-    md.pinv = 0.0;
+    md.pinv = s->model.pinv;
     int rc = epa_ctx_create(&s->ctx, device, &md, (uint32_t) T, masks.data(), sch.n_slots, sch.edges.data(), (uint32_t) sch.edges.size());
     if (rc) return host_fail(rc, epa_last_error(nullptr));
     rc = epa_compute_clvs(s->ctx, sch.ops.data(), (uint32_t) sch.ops.size());

@@ -233,9 +233,10 @@ __device__ __forceinline__ void warp_derivatives(const double * sum, double * ex
 // lanes of the site, the decaying ones go to their slots of the site's row.
 template <int R>
 __device__ __forceinline__ void store_sum_row(double * sum, int s, int r, bool act, double wr,
-                                              double st0, double st1, double st2, double st3)
+                                              double st0, double st1, double st2, double st3, double inv)
 {
-  const double base = rate_sum<R>(st0 * wr);
+  // +I: the invariant term of the site joins the t-independent entry (LP/core_derivatives.c:676-687)
+  const double base = rate_sum<R>(st0 * wr) + inv;
   if (act)
   {
     double * row = sum + s * blo_row(R);
@@ -281,15 +282,17 @@ __device__ __forceinline__ double warp_newton(const double * sum, double * ex, i
 
 // Inputs of one (site, rate) unit, loaded one unit ahead of their use (software prefetch: with
 // 8-9 resident warps per SM the L2 latency of the CLV stream is not hidden by other warps).
-struct UnitIn { double dv[4], xv[4]; int mask; uint32_t scal; };
+struct UnitIn { double dv[4], xv[4]; int mask; uint32_t scal; double inv; };
 
 template <int R, bool SCALERS>
 __device__ __forceinline__ UnitIn load_unit(const double * __restrict__ D, const double * __restrict__ X,
                                             const uint32_t * __restrict__ sD, const uint32_t * __restrict__ sX,
-                                            const uint8_t * __restrict__ qc, int s, int w, int r)
+                                            const uint8_t * __restrict__ qc, int s, int w, int r,
+                                            const double * __restrict__ inv_w)
 {
   const int sc = s < w ? s : w - 1;            // tail lanes re-read the last site; results are discarded
   UnitIn u;
+  u.inv = inv_w ? __ldg(inv_w + sc) : 0.0;
   load_vec<4>(D + ((size_t) sc * R + r) * 4, u.dv);
   load_vec<4>(X + ((size_t) sc * R + r) * 4, u.xv);
   u.mask = qc[sc] & 15;
@@ -303,7 +306,8 @@ template <int R>
 __device__ __forceinline__ double warp_pass_tip(const BloCtaSmem & cs, const double * ws, double * sum,
                                              const double * __restrict__ D, const double * __restrict__ X,
                                              const uint32_t * __restrict__ sD, const uint32_t * __restrict__ sX,
-                                             const uint8_t * __restrict__ qc, int w, int lane)
+                                             const uint8_t * __restrict__ qc, int w, int lane,
+                                             const double * __restrict__ inv_w)
 {
   constexpr int SPW = 32 / R;
   const int r = lane % R, so = lane / R;
@@ -313,17 +317,17 @@ __device__ __forceinline__ double warp_pass_tip(const BloCtaSmem & cs, const dou
   const double * tv = ws + BloWarpSmem<R>::TV + r;
   const double wr = c_model.weights[r];
   double acc = 0.0;
-  double mine = 1.0;
+  double mine = 1.0, minv = 0.0;
   uint32_t mscal = 0;
   // whole trips of R unit steps: the R lanes of a site take turns at the logarithm
   const int n_units = ((w + SPW * R - 1) / (SPW * R)) * R;
-  UnitIn nxt = load_unit<R, true>(D, X, sD, sX, qc, so, w, r);
+  UnitIn nxt = load_unit<R, true>(D, X, sD, sX, qc, so, w, r, inv_w);
   #pragma unroll 1
   for (int i = 0; i < n_units; ++i)
   {
     const UnitIn cur = nxt;
     const int s = i * SPW + so;
-    nxt = load_unit<R, true>(D, X, sD, sX, qc, s + SPW, w, r);
+    nxt = load_unit<R, true>(D, X, sD, sX, qc, s + SPW, w, r, inv_w);
     const bool act = s < w;
     double in[4];
     uint32_t scal = cur.scal;
@@ -356,11 +360,11 @@ __device__ __forceinline__ double warp_pass_tip(const BloCtaSmem & cs, const dou
                            + c_model.eigenvecs[j * 4 + 2] * in[2] + c_model.eigenvecs[j * 4 + 3] * in[3];
         st[j] = cs.tipleft[cur.mask * 4 + j] * right;
       }
-      store_sum_row<R>(sum, s, r, act, wr, st[0], st[1], st[2], st[3]);
+      store_sum_row<R>(sum, s, r, act, wr, st[0], st[1], st[2], st[3], cur.inv);
     }
-    if ((i % R) == r) { mine = act ? term : 1.0; mscal = act ? scal : 0u; }
+    if ((i % R) == r) { mine = act ? term : 1.0; mscal = act ? scal : 0u; minv = act ? cur.inv : 0.0; }
     if ((i % R) == R - 1)
-      acc += log(mine) + (mscal ? (double) mscal * EPA_LOG_SCALE_THRESHOLD : 0.0);
+      acc += site_loglk(mine, mscal, minv);
   }
   __syncwarp();
   return warp_sum(acc);
@@ -370,7 +374,8 @@ __device__ __forceinline__ double warp_pass_tip(const BloCtaSmem & cs, const dou
 template <int R>
 __device__ __forceinline__ void warp_pass_distal(const BloCtaSmem & cs, const double * ws, double * sum,
                                               const double * __restrict__ D, const double * __restrict__ X,
-                                              const uint8_t * __restrict__ qc, int w, int lane)
+                                              const uint8_t * __restrict__ qc, int w, int lane,
+                                              const double * __restrict__ inv_w)
 {
   constexpr int SPW = 32 / R;
   const int r = lane % R, so = lane / R;
@@ -380,13 +385,13 @@ __device__ __forceinline__ void warp_pass_distal(const BloCtaSmem & cs, const do
   const double * tv = ws + BloWarpSmem<R>::TV + r;
   const double wr = c_model.weights[r];
   const int n_units = (w + SPW - 1) / SPW;
-  UnitIn nxt = load_unit<R, false>(D, X, nullptr, nullptr, qc, so, w, r);
+  UnitIn nxt = load_unit<R, false>(D, X, nullptr, nullptr, qc, so, w, r, inv_w);
   #pragma unroll 1
   for (int i = 0; i < n_units; ++i)
   {
     const UnitIn cur = nxt;
     const int s = i * SPW + so;
-    nxt = load_unit<R, false>(D, X, nullptr, nullptr, qc, s + SPW, w, r);
+    nxt = load_unit<R, false>(D, X, nullptr, nullptr, qc, s + SPW, w, r, inv_w);
     const bool act = s < w;
     double in[4];
     bool small = true;
@@ -412,7 +417,7 @@ __device__ __forceinline__ void warp_pass_distal(const BloCtaSmem & cs, const do
                          + c_model.eigenvecs[j * 4 + 2] * in[2] + c_model.eigenvecs[j * 4 + 3] * in[3];
       st[j] = left * right;
     }
-    store_sum_row<R>(sum, s, r, act, wr, st[0], st[1], st[2], st[3]);
+    store_sum_row<R>(sum, s, r, act, wr, st[0], st[1], st[2], st[3], cur.inv);
   }
   __syncwarp();
 }
@@ -500,6 +505,7 @@ blo_dna_kernel(BloArgs a)
     const uint32_t * sD = a.tree.scaler + (size_t) ed.distal * n + begin;
     const uint32_t * sX = a.tree.scaler + (size_t) ed.proximal * n + begin;
     const uint8_t * qc = a.codes + (size_t) q * n + begin;
+    const double * inv_w = a.tree.inv ? a.tree.inv + begin : nullptr;      // +I: pll_util.cpp:413-414
 
     // optimize_branch_triplet: lengths orig/2, orig/2, -ln 0.9. The smoothing loop of
     // opt_branch_lengths_pplacer is unrolled into half rounds (tip phase, distal phase) so that
@@ -527,7 +533,7 @@ blo_dna_kernel(BloArgs a)
       if (!distal_phase)
       {
         // score the current lengths (also builds the pendant sumtable of the coming round)
-        const double new_logl = -warp_pass_tip<R>(cs, ws, sum, D, X, sD, sX, qc, w, lane);
+        const double new_logl = -warp_pass_tip<R>(cs, ws, sum, D, X, sD, sX, qc, w, lane, inv_w);
         if (first) { loglikelihood = new_logl; first = false; }
         else
         {
@@ -547,7 +553,7 @@ blo_dna_kernel(BloArgs a)
       }
       else
       {
-        warp_pass_distal<R>(cs, ws, sum, D, X, qc, w, lane);
+        warp_pass_distal<R>(cs, ws, sum, D, X, qc, w, lane, inv_w);
         xmin = fmin(EPA_MIN_BRLEN / 2.0, original_length / 2.0);
         xmax = original_length - xmin / 10.0;
         xguess = len[0];

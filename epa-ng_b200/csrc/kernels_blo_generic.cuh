@@ -89,9 +89,11 @@ __device__ __forceinline__ void gen_tipvec(double * sm)
 // sumtable row of unit (site s, rate r): stationary component summed over the rates into plane 0,
 // decaying components into planes 1 + r(S-1) + (j-1)
 template <int S, int R>
-__device__ __forceinline__ void gen_store_row(double * sum, int wpad, int s, int r, bool act, double wr, const double (&st)[S])
+__device__ __forceinline__ void gen_store_row(double * sum, int wpad, int s, int r, bool act, double wr, const double (&st)[S],
+                                              double inv)
 {
-  const double base = rate_sum<R>(st[0] * wr);
+  // +I: the invariant term of the site joins the t-independent entry (LP/core_derivatives.c:676-687)
+  const double base = rate_sum<R>(st[0] * wr) + inv;
   if (act)
   {
     if (r == 0) sum[s] = base;
@@ -103,7 +105,8 @@ __device__ __forceinline__ void gen_store_row(double * sum, int wpad, int s, int
 template <int S, int R>
 __device__ __forceinline__ double gen_pass_tip(double * sm, double * sum, int wpad, const double * __restrict__ D,
                                                const double * __restrict__ X, const uint32_t * __restrict__ sD,
-                                               const uint32_t * __restrict__ sX, const uint8_t * __restrict__ qc, int w)
+                                               const uint32_t * __restrict__ sX, const uint8_t * __restrict__ qc, int w,
+                                               const double * __restrict__ inv_w)
 {
   using L = GenSmem<S, R>;
   const int lane = threadIdx.x & 31;
@@ -124,6 +127,7 @@ __device__ __forceinline__ double gen_pass_tip(double * sm, double * sum, int wp
     load_vec<S>(X + ((size_t) sc * R + r) * S, xv);
     const int code = qc[sc] & (MAX_CODES - 1);
     uint32_t scal = __ldg(sD + sc) + __ldg(sX + sc);
+    const double inv = inv_w ? __ldg(inv_w + sc) : 0.0;
     bool small = true;
     #pragma unroll 4
     for (int i = 0; i < S; ++i)
@@ -144,7 +148,7 @@ __device__ __forceinline__ double gen_pass_tip(double * sm, double * sum, int wp
     #pragma unroll
     for (int i = 0; i < S; ++i) term += (in[i] * c_model.freqs[i]) * tvr[code * S + i];
     term = rate_sum<R>(term * wr);
-    if (act && r == 0) acc += log(term) + (scal ? (double) scal * EPA_LOG_SCALE_THRESHOLD : 0.0);
+    if (act && r == 0) acc += site_loglk(term, scal, inv);
     double st[S];
     #pragma unroll 4
     for (int j = 0; j < S; ++j)
@@ -154,7 +158,7 @@ __device__ __forceinline__ double gen_pass_tip(double * sm, double * sum, int wp
       for (int k = 0; k < S; ++k) right += sm[L::V + j * S + k] * in[k];
       st[j] = sm[L::TIPLEFT + code * S + j] * right;
     }
-    gen_store_row<S, R>(sum, wpad, s, r, act, wr, st);
+    gen_store_row<S, R>(sum, wpad, s, r, act, wr, st, inv);
   }
   block_sum2(acc, unused, sm + L::RED);
   return acc;
@@ -162,7 +166,8 @@ __device__ __forceinline__ double gen_pass_tip(double * sm, double * sum, int wp
 
 template <int S, int R>
 __device__ __forceinline__ void gen_pass_distal(double * sm, double * sum, int wpad, const double * __restrict__ D,
-                                                const double * __restrict__ X, const uint8_t * __restrict__ qc, int w)
+                                                const double * __restrict__ X, const uint8_t * __restrict__ qc, int w,
+                                                const double * __restrict__ inv_w)
 {
   using L = GenSmem<S, R>;
   const int lane = threadIdx.x & 31;
@@ -204,7 +209,7 @@ __device__ __forceinline__ void gen_pass_distal(double * sm, double * sum, int w
       for (int k = 0; k < S; ++k) { left += dv[k] * sm[L::PIVINV + k * S + j]; right += sm[L::V + j * S + k] * in[k]; }
       st[j] = left * right;
     }
-    gen_store_row<S, R>(sum, wpad, s, r, act, wr, st);
+    gen_store_row<S, R>(sum, wpad, s, r, act, wr, st, inv_w ? __ldg(inv_w + sc) : 0.0);
   }
   __syncthreads();
 }
@@ -229,7 +234,7 @@ template <int S, int R>
 __device__ __forceinline__ double gen_pass_tip_site(double * sm, double * sum, int wpad, const double * __restrict__ DT,
                                                     const double * __restrict__ XT, const uint32_t * __restrict__ sD,
                                                     const uint32_t * __restrict__ sX, const uint8_t * __restrict__ qc,
-                                                    int begin, int w, double * rbuf)
+                                                    int begin, int w, double * rbuf, const double * __restrict__ inv_w)
 {
   using L = GenSmem<S, R>;
   double * termbuf = rbuf, * basebuf = rbuf + R * wpad;
@@ -281,9 +286,10 @@ __device__ __forceinline__ double gen_pass_tip_site(double * sm, double * sum, i
     double term = 0.0, base = 0.0;
     #pragma unroll
     for (int r = 0; r < R; ++r) { term += termbuf[r * wpad + s]; base += basebuf[r * wpad + s]; }
-    sum[s] = base;
+    const double inv = inv_w ? __ldg(inv_w + s) : 0.0;
+    sum[s] = base + inv;
     const uint32_t scal = __ldg(sD + s) + __ldg(sX + s);
-    acc += log(term) + (scal ? (double) scal * EPA_LOG_SCALE_THRESHOLD : 0.0);
+    acc += site_loglk(term, scal, inv);
   }
   block_sum2(acc, unused, sm + L::RED);
   return acc;
@@ -292,7 +298,7 @@ __device__ __forceinline__ double gen_pass_tip_site(double * sm, double * sum, i
 template <int S, int R>
 __device__ __forceinline__ void gen_pass_distal_site(double * sm, double * sum, int wpad, const double * __restrict__ DT,
                                                      const double * __restrict__ XT, const uint8_t * __restrict__ qc,
-                                                     int begin, int w, double * rbuf)
+                                                     int begin, int w, double * rbuf, const double * __restrict__ inv_w)
 {
   using L = GenSmem<S, R>;
   double * basebuf = rbuf;
@@ -336,7 +342,7 @@ __device__ __forceinline__ void gen_pass_distal_site(double * sm, double * sum, 
     double base = 0.0;
     #pragma unroll
     for (int r = 0; r < R; ++r) base += basebuf[r * wpad + s];
-    sum[s] = base;
+    sum[s] = base + (inv_w ? __ldg(inv_w + s) : 0.0);
   }
   __syncthreads();
 }
@@ -514,6 +520,7 @@ blo_generic_kernel(BloArgs a, int wpad, const double * __restrict__ clvT, size_t
     const uint32_t * sD = a.tree.scaler + (size_t) ed.distal * n + begin;
     const uint32_t * sX = a.tree.scaler + (size_t) ed.proximal * n + begin;
     const uint8_t * qc = a.codes + (size_t) q * n + begin;
+    const double * inv_w = a.tree.inv ? a.tree.inv + begin : nullptr;      // +I: pll_util.cpp:413-414
 
     const double orig = ed.length;
     double len[3] = {orig / 2.0, orig / 2.0, EPA_DEFAULT_PENDANT};
@@ -537,8 +544,8 @@ blo_generic_kernel(BloArgs a, int wpad, const double * __restrict__ clvT, size_t
       if (!distal_phase)
       {
         const double new_logl = clvT
-            ? -gen_pass_tip_site<S, R>(sm, sum, wpad, clvT + (size_t) ed.distal * t_stride, clvT + (size_t) ed.proximal * t_stride, sD, sX, qc, begin, w, sm + L::TOTAL)
-            : -gen_pass_tip<S, R>(sm, sum, wpad, D, X, sD, sX, qc, w);
+            ? -gen_pass_tip_site<S, R>(sm, sum, wpad, clvT + (size_t) ed.distal * t_stride, clvT + (size_t) ed.proximal * t_stride, sD, sX, qc, begin, w, sm + L::TOTAL, inv_w)
+            : -gen_pass_tip<S, R>(sm, sum, wpad, D, X, sD, sX, qc, w, inv_w);
         if (first) { loglikelihood = new_logl; first = false; }
         else
         {
@@ -559,9 +566,9 @@ blo_generic_kernel(BloArgs a, int wpad, const double * __restrict__ clvT, size_t
       else
       {
         if (clvT)
-          gen_pass_distal_site<S, R>(sm, sum, wpad, clvT + (size_t) ed.distal * t_stride, clvT + (size_t) ed.proximal * t_stride, qc, begin, w, sm + L::TOTAL);
+          gen_pass_distal_site<S, R>(sm, sum, wpad, clvT + (size_t) ed.distal * t_stride, clvT + (size_t) ed.proximal * t_stride, qc, begin, w, sm + L::TOTAL, inv_w);
         else
-          gen_pass_distal<S, R>(sm, sum, wpad, D, X, qc, w);
+          gen_pass_distal<S, R>(sm, sum, wpad, D, X, qc, w, inv_w);
         xmin = fmin(EPA_MIN_BRLEN / 2.0, original_length / 2.0);
         xmax = original_length - xmin / 10.0;
         xguess = len[0];

@@ -236,7 +236,7 @@ __constant__ double c_coltab[16 * 4 * MAX_RATES / 2];      // R <= 4
 template <int R>
 __global__ void __launch_bounds__(128)
 lookup_build_site_kernel(const DevModel * __restrict__ m, const double * __restrict__ clvT, size_t t_stride,
-                         const uint32_t * __restrict__ scaler, int sr, int n, int n_pad,
+                         const uint32_t * __restrict__ scaler, int sr, const double * __restrict__ inv_lk, int n, int n_pad,
                          const EdgeDev * __restrict__ edges, const double * __restrict__ pmats_half,
                          double * __restrict__ lookup)
 {
@@ -303,7 +303,7 @@ lookup_build_site_kernel(const DevModel * __restrict__ m, const double * __restr
     }
     sc = kmin;
   }
-  const double scale_term = sc ? (double) sc * EPA_LOG_SCALE_THRESHOLD : 0.0;
+  const double inv = inv_lk ? __ldg(inv_lk + s) : 0.0;
   double * trow = tile[warp] + lane * 17;
   trow[0] = 0.0;                                       // column 0 = zero column
   #pragma unroll
@@ -317,7 +317,7 @@ lookup_build_site_kernel(const DevModel * __restrict__ m, const double * __restr
                       + in[r * 4 + 2] * c_coltab[c * C + r * 4 + 2] + in[r * 4 + 3] * c_coltab[c * C + r * 4 + 3];
       term += tr * c_model.weights[r];
     }
-    trow[c] = log(term) + scale_term;
+    trow[c] = site_loglk(term, sc, inv);
   }
   __syncwarp();
   // the warp's 32 table rows are 4 KB contiguous in global memory: coalesced 256-byte stores
@@ -572,11 +572,28 @@ __device__ __forceinline__ uint32_t rate_weights(const uint32_t * __restrict__ s
   return kmin;
 }
 
-template <int R, bool GS, bool PR>
+// +I models (INV kernels): `inv_w` is the window's slice of the per-site invariant terms. The term
+// joins the t-independent sumtable entry and the site likelihood (LP/core_derivatives.c:676-687,
+// LP/core_likelihood.c:524-556). The reference adds it to sums built from a CLV its update may have
+// rescaled by 2^256, so an invariant site does take that rescaling here (per-site scalers).
+template <int R>
+__device__ __forceinline__ uint32_t site_rescale_inv(double (&in)[4 * R])
+{
+  bool small = true;
+  #pragma unroll
+  for (int c = 0; c < 4 * R; ++c) small = small && (in[c] < EPA_SCALE_THRESHOLD);
+  if (!small) return 0u;
+  #pragma unroll
+  for (int c = 0; c < 4 * R; ++c) in[c] *= EPA_SCALE_FACTOR;
+  return 1u;
+}
+
+template <int R, bool GS, bool PR, bool INV>
 __device__ __forceinline__ double site_pass_tip(const SiteCtaSmem & cs, const double * ws, const SumRef & sr,
                                              const double * __restrict__ DT, const double * __restrict__ XT,
                                              const uint32_t * __restrict__ sD, const uint32_t * __restrict__ sX,
-                                             const uint8_t * __restrict__ qc, int begin, int w, int lane, int bugcompat)
+                                             const uint8_t * __restrict__ qc, int begin, int w, int lane, int bugcompat,
+                                             const double * __restrict__ inv_w)
 {
   using L = SiteWarpSmem<R>;
   // The window log-likelihood is a sum of per-site logarithms. A lane multiplies the mantissas of
@@ -618,6 +635,13 @@ __device__ __forceinline__ double site_pass_tip(const SiteCtaSmem & cs, const do
         if constexpr (PR) in[r * 4 + i] *= rf[r];
       }
     }
+    double inv = 0.0;
+    if constexpr (INV)
+    {
+      inv = __ldg(inv_w + s);
+      if constexpr (!PR)
+        if (inv > 0.0) scal += site_rescale_inv<R>(in);
+    }
     double tl[4];
     lds_vec<4>(cs.tipleft + pos * 4, tl);
     const double * tvp = ws + L::TV + pos * L::TVS;
@@ -640,6 +664,16 @@ __device__ __forceinline__ double site_pass_tip(const SiteCtaSmem & cs, const do
         const double v = tl[j] * right;
         if (j == 0) base += v * c_model.weights[r];
         else st[r * 3 + j - 1] = v;
+      }
+    }
+    if constexpr (INV)
+    {
+      base += inv;
+      if (inv > 0.0)
+      {
+        if (scal) term *= rate_scale_factor(min(scal, EPA_RATE_MAXDIFF));
+        term += inv;
+        scal = 0;
       }
     }
     site_store_row<R, GS>(sr, tr, s, act, base, st);
@@ -669,10 +703,11 @@ __device__ __forceinline__ double site_pass_tip(const SiteCtaSmem & cs, const do
 // Pass A of the FIRST half round, from the per-edge tables: the pendant sumtable is the tip factor
 // times the stored eigen-rotated inner CLV, the window log-likelihood is the sum of the
 // preplacement table entries (the same three lengths, the same tiny tree).
-template <int R, bool GS>
+template <int R, bool GS, bool INV>
 __device__ __forceinline__ double site_pass_first(const SiteCtaSmem & cs, const SumRef & sr,
                                                   const double * __restrict__ GT, const double * __restrict__ lk,
-                                                  const uint8_t * __restrict__ qc, int begin, int w, int lane)
+                                                  const uint8_t * __restrict__ qc, int begin, int w, int lane,
+                                                  const double * __restrict__ inv_w)
 {
   double acc = 0.0;
   const int trips = (w + 31) >> 5;
@@ -698,6 +733,7 @@ __device__ __forceinline__ double site_pass_first(const SiteCtaSmem & cs, const 
       #pragma unroll
       for (int j = 1; j < 4; ++j) st[r * 3 + j - 1] = tl[j] * gv[r * 4 + j];
     }
+    if constexpr (INV) base += __ldg(inv_w + s);
     site_store_row<R, GS>(sr, tr, s, act, base, st);
   }
   if (!GS && sr.tm) tc_wait_st();
@@ -705,11 +741,12 @@ __device__ __forceinline__ double site_pass_first(const SiteCtaSmem & cs, const 
 }
 
 // Pass B: inner CLV toward the distal node from (T, X); leaves the distal sumtable (D vs inner)
-template <int R, bool GS, bool PR>
+template <int R, bool GS, bool PR, bool INV>
 __device__ __forceinline__ void site_pass_distal(const double * ws, const SumRef & sr,
                                               const double * __restrict__ DT, const double * __restrict__ XT,
                                               const uint32_t * __restrict__ sD, const uint32_t * __restrict__ sX,
-                                              const uint8_t * __restrict__ qc, int begin, int w, int lane, int bugcompat)
+                                              const uint8_t * __restrict__ qc, int begin, int w, int lane, int bugcompat,
+                                              const double * __restrict__ inv_w)
 {
   using L = SiteWarpSmem<R>;
   const int trips = (w + 31) >> 5;
@@ -744,6 +781,13 @@ __device__ __forceinline__ void site_pass_distal(const double * ws, const SumRef
         if constexpr (PR) in[r * 4 + i] *= rf[r];
       }
     }
+    double inv = 0.0;
+    if constexpr (INV)
+    {
+      inv = __ldg(inv_w + s);
+      if constexpr (!PR)
+        if (inv > 0.0) (void) site_rescale_inv<R>(in);
+    }
     double base = 0.0;
     double st[3 * R];
     #pragma unroll
@@ -761,6 +805,7 @@ __device__ __forceinline__ void site_pass_distal(const double * ws, const SumRef
         else st[r * 3 + j - 1] = v;
       }
     }
+    if constexpr (INV) base += inv;
     site_store_row<R, GS>(sr, tr, s, act, base, st);
   }
   if (!GS && sr.tm) tc_wait_st();
@@ -789,7 +834,8 @@ __device__ __forceinline__ unsigned long long site_next_item(SiteCtaSmem & cs, u
 
 // GS = sumtable in global scratch (windows that do not fit the shared-memory slice)
 // PR = per-rate scalers (the scaler pointers then address the node's [n][R] block, not the window)
-template <int R, bool GS, bool PR = false>
+// INV = +I model (a.tree.inv holds the per-site invariant terms)
+template <int R, bool GS, bool PR = false, bool INV = false>
 __global__ void __launch_bounds__(SITE_MAX_WARPS * 32, 1)
 blo_site_kernel(BloSiteArgs sa)
 {
@@ -872,6 +918,7 @@ blo_site_kernel(BloSiteArgs sa)
     const uint32_t * sD = PR ? a.tree.scaler + (size_t) ed.distal * n * R : a.tree.scaler + (size_t) ed.distal * n + begin;
     const uint32_t * sX = PR ? a.tree.scaler + (size_t) ed.proximal * n * R : a.tree.scaler + (size_t) ed.proximal * n + begin;
     const uint8_t * qc = a.codes + (size_t) q * n + begin;
+    const double * inv_w = INV ? a.tree.inv + begin : nullptr;         // pll_util.cpp:413-414
 
     // optimize_branch_triplet / opt_branch_lengths_pplacer as half rounds (see kernels_blo.cuh)
     const double orig = ed.length;
@@ -897,10 +944,10 @@ blo_site_kernel(BloSiteArgs sa)
       {
         double new_logl;
         if (first && sa.gT)
-          new_logl = -site_pass_first<R, GS>(cs, sr, sa.gT + (size_t) e * sa.g_stride,
-                                             sa.lookup + (size_t) e * sa.n_pad * 16, qc, begin, w, lane);
+          new_logl = -site_pass_first<R, GS, INV>(cs, sr, sa.gT + (size_t) e * sa.g_stride,
+                                                  sa.lookup + (size_t) e * sa.n_pad * 16, qc, begin, w, lane, inv_w);
         else
-          new_logl = -site_pass_tip<R, GS, PR>(cs, ws, sr, DT, XT, sD, sX, qc, begin, w, lane, sa.bugcompat);
+          new_logl = -site_pass_tip<R, GS, PR, INV>(cs, ws, sr, DT, XT, sD, sX, qc, begin, w, lane, sa.bugcompat, inv_w);
         if (first) { loglikelihood = new_logl; first = false; }
         else
         {
@@ -920,7 +967,7 @@ blo_site_kernel(BloSiteArgs sa)
       }
       else
       {
-        site_pass_distal<R, GS, PR>(ws, sr, DT, XT, sD, sX, qc, begin, w, lane, sa.bugcompat);
+        site_pass_distal<R, GS, PR, INV>(ws, sr, DT, XT, sD, sX, qc, begin, w, lane, sa.bugcompat, inv_w);
         xmin = fmin(EPA_MIN_BRLEN / 2.0, original_length / 2.0);
         xmax = original_length - xmin / 10.0;
         xguess = len[0];

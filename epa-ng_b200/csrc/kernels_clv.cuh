@@ -224,7 +224,7 @@ lookup_build_kernel(const DevModel * __restrict__ m, DevTree tree, int n, int n_
       #pragma unroll
       for (int i = 0; i < S; ++i) inner[r][i] *= EPA_SCALE_FACTOR;
   }
-  const double scale_term = sc ? (double) sc * EPA_LOG_SCALE_THRESHOLD : 0.0;
+  const double inv = tree.inv ? __ldg(tree.inv + site) : 0.0;
   double wr[R];
   #pragma unroll
   for (int r = 0; r < R; ++r) wr[r] = m->weights[r];
@@ -244,7 +244,7 @@ lookup_build_kernel(const DevModel * __restrict__ m, DevTree tree, int n, int n_
         for (int i = 0; i < S; ++i) tr += inner[r][i] * M[(r * K + c) * S + i];
         terma += tr * wr[r];
       }
-      v = log(terma) + scale_term;
+      v = site_loglk(terma, sc, inv);
     }
     out[c] = v;
   }
@@ -319,7 +319,7 @@ lookup_build_dna_kernel(const DevModel * __restrict__ m, DevTree tree, int n, in
       #pragma unroll
       for (int i = 0; i < S; ++i) inner[i] *= EPA_SCALE_FACTOR;
     }
-    const double scale_term = sc ? (double) sc * EPA_LOG_SCALE_THRESHOLD : 0.0;
+    const double inv = tree.inv ? __ldg(tree.inv + s) : 0.0;
 
     // per-rate contribution of every column, then sum over the four rate lanes (fixed order)
     double mine[4];
@@ -336,7 +336,7 @@ lookup_build_dna_kernel(const DevModel * __restrict__ m, DevTree tree, int n, in
     double res[4];
     #pragma unroll
     for (int k = 0; k < 4; ++k)
-      res[k] = (r == 0 && k == 0) ? 0.0 : log(mine[k]) + scale_term;   // column 0 = zero column
+      res[k] = (r == 0 && k == 0) ? 0.0 : site_loglk(mine[k], sc, inv);   // column 0 = zero column
     if (active)
       store_vec<4>(lookup + ((size_t) blockIdx.x * n_pad + site) * K + r * 4, res);
   }
@@ -393,7 +393,7 @@ edge_logl_kernel(const DevModel * __restrict__ m, DevTree tree, int n, EdgeDev e
     }
     const uint32_t sc = tree.sr > 1 ? kmin
                                     : tree.scaler[(size_t) e.distal * n + site] + tree.scaler[(size_t) e.proximal * n + site];
-    lk = log(terma) + (sc ? (double) sc * EPA_LOG_SCALE_THRESHOLD : 0.0);
+    lk = site_loglk(terma, sc, tree.inv ? __ldg(tree.inv + site) : 0.0);
   }
   red[threadIdx.x] = lk;
   __syncthreads();

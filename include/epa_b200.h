@@ -64,7 +64,8 @@ typedef struct {
   const double * freqs;           /* [states] */
   const double * rates;           /* [rate_cats] */
   const double * rate_weights;    /* [rate_cats] */
-  double pinv;                    /* proportion of invariant sites; must be 0 (not supported yet) */
+  double pinv;                    /* proportion of invariant sites in [0, 1) (+IU{p}); the invariant sites are
+                                     derived from the tip masks (libpll models.c:495-760) */
 } epa_model_desc;
 
 /* One reference-tree edge as Tiny_Tree sees it (src/tree/Tiny_Tree.cpp:48-76): the two CLVs

@@ -121,7 +121,7 @@ def make_context(case: Case, device=0, compute=True):
     ctx = capi.Context(states=m.states, rate_cats=m.rate_cats, sites=case.n, eigenvals=m.eigenvals,
                        eigenvecs=m.eigenvecs, inv_eigenvecs=m.inv_eigenvecs, freqs=m.freqs, rates=m.rates,
                        weights=m.weights, tip_masks=case.tip_masks(), n_clv_slots=n_inner,
-                       edges=case.edges(ids, T), device=device,
+                       edges=case.edges(ids, T), device=device, pinv=float(getattr(m, "pinv", 0.0)),
                        flags=(capi.EPA_FLAG_RATE_SCALERS if getattr(m, "per_rate_scalers", False) else 0)
                        | (capi.EPA_FLAG_BUGCOMPAT_FOCUS if getattr(m, "bugcompat_focus", False) else 0))
     ctx.ids = ids

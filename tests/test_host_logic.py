@@ -76,9 +76,12 @@ def test_protein_model_matches_oracle(sess, model):
 
 
 def test_model_errors(sess, built):
-    for bad in ["GTR+I", "LG{1/2}+G", "GTR{1/2/3}", "GTR+FU{0.5/0.5}", "GTR+R4", "FOO"]:
+    for bad in ["GTR+IC", "GTR+IU{1.5}", "GTR+IU", "LG{1/2}+G", "GTR{1/2/3}", "GTR+FU{0.5/0.5}", "GTR+R4", "FOO"]:
         with pytest.raises(built.capi.EpaError):
             sess.parse_model(bad)
+    # +I in ML mode stays at the reference's unoptimised 0 (src/core/raxml/Model.cpp:192,355-380); +IU{p} is a user value
+    for good in ["GTR+I+G4", "GTR+IO", "GTR+IU{0.2}+G4{0.5}", "LG+IU{0.1}+G4"]:
+        sess.parse_model(good)
 
 
 def test_schedule_reproduces_oracle_clvs(sess):
