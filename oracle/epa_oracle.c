@@ -764,6 +764,147 @@ void orc_place_thorough(const orc_model_t * m_full, int n_full, const orc_side_t
   free(inner); free(iscal); free(sumtable); free(p_dist); free(p_prox); free(p_pend);
 }
 
+/* ------------------------------------------------------------------------------------------ */
+/*  --raxml-blo: optimize_branch_triplet with sliding == false (src/core/pll/optimize.cpp:274-278) */
+/*  -> pllmod_opt_optimize_branch_lengths_local(radius 1, keep_update 1), PM/optimize/          */
+/*  pll_optimize.c:778-1097, Newton variant PM/optimize/opt_algorithms.c:281-384                */
+/* ------------------------------------------------------------------------------------------ */
+
+/* pllmod_opt_minimize_newton_old: Newton-Raphson with a bisection fallback. *failed is set where
+   the reference sets pll_errno (non-finite derivatives, iteration limit). */
+static double orc_newton_old(double x1, double xguess, double x2, double tol, int max_iters,
+                             const orc_nr_ctx_t * ctx, int * failed)
+{
+  double df, dx, f, temp, xh, xl, rts, rts_old = 0.0;
+  *failed = 0;
+  rts = xguess;
+  if (rts < x1) rts = x1;
+  if (rts > x2) rts = x2;
+  orc_derivatives(ctx->m, ctx->n, ctx->sumtable, rts, &f, &df);
+  if (!isfinite(f) || !isfinite(df)) { *failed = 1; return -INFINITY; }
+  if (df >= 0.0 && fabs(f) < tol) return rts;
+  if (f < 0.0) { xl = rts; xh = x2; }
+  else { xh = rts; xl = x1; }
+  dx = fabs(xh - xl);
+  for (int i = 1; i <= max_iters; i++)
+  {
+    rts_old = rts;
+    if ((df <= 0.0) || (((rts - xh) * df - f) * ((rts - xl) * df - f) >= 0.0))
+    {
+      dx = 0.5 * (xh - xl);
+      rts = xl + dx;
+      if (xl == rts) return rts;
+    }
+    else
+    {
+      dx = f / df;
+      temp = rts;
+      rts -= dx;
+      if (temp == rts) return rts;
+    }
+    if (fabs(dx) < tol) return rts_old;
+    if (i == max_iters) break;
+    if (rts < x1) rts = x1;
+    orc_derivatives(ctx->m, ctx->n, ctx->sumtable, rts, &f, &df);
+    if (!isfinite(f) || !isfinite(df)) { *failed = 1; return -INFINITY; }
+    if (df > 0.0 && fabs(f) < tol) return rts;
+    if (f < 0.0) xl = rts; else xh = rts;
+  }
+  *failed = 1;                               /* "Exceeded maximum number of iterations" */
+  return rts_old;
+}
+
+/* one recomp_iterative step on a single edge (pll_optimize.c:799-833): sumtable across the edge,
+   Newton, length and (if it moved by more than 1e-10) transition matrix updated. Returns 0 on failure. */
+static int orc_raxml_edge(const orc_model_t * m, int n, const orc_side_t * a, const orc_side_t * b,
+                          double * sumtable, double * len, double * pmat)
+{
+  const orc_nr_ctx_t nr = {m, n, sumtable};
+  const double xmin = ORC_MIN_BRLEN, xmax = ORC_MAX_BRLEN, xtol = ORC_MIN_BRLEN / 10.0, xorig = *len;
+  double xguess = *len;
+  if (xguess < xmin || xguess > xmax) xguess = ORC_DEFAULT_BRLEN;
+  orc_sumtable(m, n, a, b, sumtable);
+  int failed;
+  const double xres = orc_newton_old(xmin, xguess, xmax, xtol, 30, &nr, &failed);
+  if (failed) return 0;
+  *len = xres;
+  if (fabs(xres - xorig) > 1e-10) orc_pmatrix(m, xres, pmat);
+  return 1;
+}
+
+void orc_place_thorough_raxml(const orc_model_t * m_full, int n_full, const orc_side_t * distal_full,
+                              const orc_side_t * proximal_full, double orig_length,
+                              const uint32_t * query_tip, int begin, int span,
+                              orc_blo_result_t * out)
+{
+  (void) n_full;
+  orc_model_t m_focus = *m_full;
+  if (m_focus.invariant) m_focus.invariant += begin;
+  const orc_model_t * m = &m_focus;
+  const int S = m->states, R = m->rate_cats, n = span;
+  const size_t psz = (size_t) R * S * S;
+  const orc_side_t distal = orc_focus(m, distal_full, begin);
+  const orc_side_t proximal = orc_focus(m, proximal_full, begin);
+  const orc_side_t tip = {NULL, NULL, query_tip + begin};
+
+  double * inner = (double *) malloc(sizeof(double) * (size_t) n * R * S);
+  uint32_t * iscal = (uint32_t *) calloc((size_t) n * (m->per_rate_scalers ? R : 1), sizeof(uint32_t));
+  double * sumtable = (double *) malloc(sizeof(double) * (size_t) n * R * S);
+  double * p_dist = (double *) malloc(sizeof(double) * psz);
+  double * p_prox = (double *) malloc(sizeof(double) * psz);
+  double * p_pend = (double *) malloc(sizeof(double) * psz);
+  const orc_side_t in = {inner, iscal, NULL};
+
+  double len_dist = orig_length / 2.0, len_prox = orig_length / 2.0, len_pend = ORC_DEFAULT_PENDANT;
+  orc_pmatrix(m, len_dist, p_dist);
+  orc_pmatrix(m, len_prox, p_prox);
+  orc_pmatrix(m, len_pend, p_pend);
+  orc_update_partial(m, n, inner, iscal, &distal, p_dist, &proximal, p_prox);
+
+  /* pll_optimize.c:991-1091 */
+  double loglikelihood = orc_edge_logl(m, n, &tip, &in, p_pend, NULL);
+  int iters = 32, ok = 1;
+  out->rounds = 0;
+  out->restored = 0;
+  while (iters)
+  {
+    out->rounds++;
+    /* first edge, radius 1: pendant, then the edges behind the inner node's other two directions */
+    ok = orc_raxml_edge(m, n, &in, &tip, sumtable, &len_pend, p_pend);
+    if (!ok) break;
+    orc_update_partial(m, n, inner, iscal, &tip, p_pend, &proximal, p_prox);     /* toward distal */
+    ok = orc_raxml_edge(m, n, &distal, &in, sumtable, &len_dist, p_dist);
+    if (!ok) break;
+    orc_update_partial(m, n, inner, iscal, &distal, p_dist, &tip, p_pend);       /* toward proximal */
+    ok = orc_raxml_edge(m, n, &proximal, &in, sumtable, &len_prox, p_prox);
+    if (!ok) break;
+    orc_update_partial(m, n, inner, iscal, &proximal, p_prox, &distal, p_dist);  /* back toward the tip */
+    /* second edge (the new tip), radius 0: the pendant edge once more */
+    ok = orc_raxml_edge(m, n, &tip, &in, sumtable, &len_pend, p_pend);
+    if (!ok) break;
+    const double new_logl = orc_edge_logl(m, n, &tip, &in, p_pend, NULL);
+    if (new_logl - loglikelihood > new_logl * 1e-13)
+    {
+      --iters;
+      if (fabs(new_logl - loglikelihood) < ORC_BLO_EPSILON) iters = 0;
+      loglikelihood = new_logl;
+    }
+    else
+    {
+      /* PLLMOD_OPT_BLO_NEWTON_OLDFAST: a worse score is kept and ends the loop (:1084-1088) */
+      loglikelihood = new_logl;
+      out->restored = 1;
+      break;
+    }
+  }
+  /* a failed Newton call makes the optimiser return PLL_FAILURE (0): the placement carries logl 0 */
+  out->logl = ok ? loglikelihood : 0.0;
+  out->distal = (orig_length / (len_dist + len_prox)) * len_dist;
+  out->pendant = len_pend;
+
+  free(inner); free(iscal); free(sumtable); free(p_dist); free(p_prox); free(p_pend);
+}
+
 /* ========================================================================================== */
 /*  Candidate selection / output stage                                                        */
 /* ========================================================================================== */

@@ -103,6 +103,13 @@ void orc_place_thorough(const orc_model_t * m, int n, const orc_side_t * distal,
                         const uint32_t * query_tip /*[n]*/, int begin, int span,
                         orc_blo_result_t * out);
 
+/* the same with --raxml-blo (optimize.cpp:274-278 -> pllmod_opt_optimize_branch_lengths_local,
+   PM/optimize/pll_optimize.c:778-1097; Newton variant PM/optimize/opt_algorithms.c:281-384) */
+void orc_place_thorough_raxml(const orc_model_t * m, int n, const orc_side_t * distal,
+                              const orc_side_t * proximal, double orig_length,
+                              const uint32_t * query_tip /*[n]*/, int begin, int span,
+                              orc_blo_result_t * out);
+
 /* ---- candidate selection / output stage --------------------------------------------------- */
 /* set_manipulators.cpp:43-69 */
 void orc_lwr(const double * logl, int n, double * lwr);

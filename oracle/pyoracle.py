@@ -87,6 +87,7 @@ def lib():
         L.orc_preplace_score.restype = C.c_double
         L.orc_place_thorough.argtypes = [mp, C.c_int, sp, sp, C.c_double, up, C.c_int, C.c_int,
                                          C.POINTER(OrcBlo)]
+        L.orc_place_thorough_raxml.argtypes = L.orc_place_thorough.argtypes
         L.orc_lwr.argtypes = [dp, C.c_int, dp]
         L.orc_select_accumulated.argtypes = [dp, C.c_int, C.c_double, ip]
         L.orc_select_accumulated.restype = C.c_int
@@ -662,6 +663,7 @@ class Options:
     filter_max: int = 7
     premasking: bool = True
     heuristic: int = 0          # 0 dynamic (-g), 1 fixed fraction (-G), 2 baseball
+    sliding_blo: bool = True    # False = --raxml-blo (src/core/pll/optimize.cpp:274-278)
 
 
 @dataclass
@@ -716,8 +718,9 @@ class Placer:
         if span == 0:
             raise ValueError("query has no non-gap sites")
         res = OrcBlo()
-        lib().orc_place_thorough(C.byref(ref.model.c()), ref.n, C.byref(d.c), C.byref(p.c), length,
-                                 _up(np.ascontiguousarray(m)), begin, span, C.byref(res))
+        fn = lib().orc_place_thorough if self.opts.sliding_blo else lib().orc_place_thorough_raxml
+        fn(C.byref(ref.model.c()), ref.n, C.byref(d.c), C.byref(p.c), length,
+           _up(np.ascontiguousarray(m)), begin, span, C.byref(res))
         pl = Placement(edge, res.logl, 0.0, res.pendant, res.distal)
         pl.rounds, pl.restored = res.rounds, res.restored
         return pl
