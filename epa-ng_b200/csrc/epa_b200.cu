@@ -1184,6 +1184,12 @@ int ensure_clvT(epa_ctx * ctx)
 template <int R, bool GS, bool PR, bool INV>
 int launch_site_kernel(epa_ctx * ctx, const BloSiteArgs & sa, unsigned grid, int warps, size_t smem)
 {
+  if (sa.b.raxml)
+  {
+    CU(cudaFuncSetAttribute(blo_site_kernel<R, GS, PR, INV, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+    blo_site_kernel<R, GS, PR, INV, true><<<grid, warps * 32, smem, ctx->stream>>>(sa);
+    return EPA_OK;
+  }
   CU(cudaFuncSetAttribute(blo_site_kernel<R, GS, PR, INV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
   blo_site_kernel<R, GS, PR, INV><<<grid, warps * 32, smem, ctx->stream>>>(sa);
   return EPA_OK;
@@ -1268,8 +1274,16 @@ int launch_blo_dna(epa_ctx * ctx, BloArgs & a)
     // keep every SM busy but do not launch far more warps than there are pairs
     uint64_t grid = (uint64_t) ctx->sm_count * ctas_per_sm;
     grid = std::min<uint64_t>(grid, (a.n_pairs + warps - 1) / warps);
-    CU(cudaFuncSetAttribute(blo_dna_kernel<R, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
-    blo_dna_kernel<R, false><<<(unsigned) grid, warps * 32, smem, ctx->stream>>>(a);
+    if (a.raxml)
+    {
+      CU(cudaFuncSetAttribute(blo_dna_kernel<R, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+      blo_dna_kernel<R, false, true><<<(unsigned) grid, warps * 32, smem, ctx->stream>>>(a);
+    }
+    else
+    {
+      CU(cudaFuncSetAttribute(blo_dna_kernel<R, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+      blo_dna_kernel<R, false><<<(unsigned) grid, warps * 32, smem, ctx->stream>>>(a);
+    }
   }
   else
   {
@@ -1279,7 +1293,8 @@ int launch_blo_dna(epa_ctx * ctx, BloArgs & a)
     a.scratch = ctx->scratch.as<double>();
     a.wcap = 0;
     const size_t smem = BloWarpSmem<R>::doubles(0) * sizeof(double) * warps;
-    blo_dna_kernel<R, true><<<grid, warps * 32, smem, ctx->stream>>>(a);
+    if (a.raxml) blo_dna_kernel<R, true, true><<<grid, warps * 32, smem, ctx->stream>>>(a);
+    else blo_dna_kernel<R, true><<<grid, warps * 32, smem, ctx->stream>>>(a);
   }
   LAUNCHED(ctx);
   return EPA_OK;
@@ -1291,7 +1306,6 @@ extern "C" int epa_place_pairs(epa_ctx * ctx, const epa_options * opts)
   if (!ctx || !opts) return EPA_ERR_ARG;
   if (int rc = set_device(ctx)) return rc;
   if (ctx->stage < ST_SELECTED) return fail(ctx, EPA_ERR_STATE, "epa_select has not run");
-  if (!opts->sliding_blo) return fail(ctx, EPA_ERR_ARG, "--raxml-blo is not supported");
   if (int rc = check_edges_ready(ctx)) return rc;
   if (int rc = bind_constants(ctx)) return rc;
   CU(cudaEventRecord(ctx->ev[3], ctx->stream));
@@ -1308,6 +1322,7 @@ extern "C" int epa_place_pairs(epa_ctx * ctx, const epa_options * opts)
     a.perm = ctx->perm.as<uint32_t>();
     a.n_pairs = (uint32_t) ctx->n_pairs; a.nq = ctx->nq; a.n_edges = ctx->n_edges;
     a.counter = ctx->d_counter; a.out = ctx->res.as<BloResult>(); a.scratch = nullptr; a.wcap = 0;
+    a.raxml = opts->sliding_blo ? 0 : 1;
     int rc;
     if (ctx->S == 4)
     {

@@ -31,6 +31,7 @@ void usage()
       "  -G,--fix-heur FLOAT       fixed-fraction preplacement heuristic\n"
       "  --baseball-heur           baseball heuristic (strike box 3, 6 strikes, 40 pitches)\n"
       "  --no-heur                 evaluate every edge thoroughly\n"
+      "  --raxml-blo               optimise the three branch lengths the way RAxML-EPA did (default: pplacer-style)\n"
       "  --chunk-size INT          queries per device chunk [131072]\n"
       "  --no-pre-mask             do not drop all-gap columns / trim query ranges\n"
       "  --filter-acc-lwr FLOAT    accumulated-LWR output filter\n"
@@ -89,7 +90,8 @@ int main(int argc, char ** argv)
     }
     else if (a == "--correct-scaler-focus") rate_bug = 0;     // not a reference option: read the scalers of the site itself
     else if (a == "--preserve-rooting") { const std::string v = need(i); preserve_rooting = (v != "off"); }
-    else if (a == "--raxml-blo" || a == "-b" || a == "--binary" ||
+    else if (a == "--raxml-blo") opts.sliding_blo = 0;        // src/core/pll/optimize.cpp:274-278
+    else if (a == "-b" || a == "--binary" ||
              a == "-B" || a == "--dump-binary" || a == "-c" || a == "--bfast" || a == "--split")    // (bfast query FILES are read; the converter is not part of the path)
       die("option " + a + " is outside the accelerated hot path and not supported by this build");
     else die("unknown option " + a);

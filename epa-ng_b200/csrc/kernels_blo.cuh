@@ -68,7 +68,53 @@ struct BloArgs {
   BloResult * out;                // [pair id]
   double * scratch;               // global sumtable scratch (GS variant): [total warps][1 + 3R planes]
   int wcap;                       // sites the shared-memory sumtable can hold
+  int raxml;                      // 1 = --raxml-blo: the three edges optimised one after the other, unconstrained
+                                  // (pllmod_opt_optimize_branch_lengths_local, PM/optimize/pll_optimize.c:778-1097)
 };
+
+// --raxml-blo takes the older Newton-Raphson variant with a bisection fallback
+// (pllmod_opt_minimize_newton_old, PM/optimize/opt_algorithms.c:281-384). `deriv(x, f, df)` evaluates
+// the derivative sums of the current sumtable; `failed` is set where the reference sets pll_errno
+// (non-finite derivatives, iteration limit) - the optimiser then gives up on the pair.
+template <class Deriv>
+__device__ __forceinline__ double newton_old(Deriv && deriv, double x1, double xguess, double x2, double tol, bool & failed)
+{
+  double df, dx, f, xh, xl, rts, rts_old = 0.0;
+  failed = false;
+  rts = fmax(fmin(xguess, x2), x1);
+  deriv(rts, f, df);
+  if (!isfinite(f) || !isfinite(df)) { failed = true; return 0.0; }
+  if (df >= 0.0 && fabs(f) < tol) return rts;
+  if (f < 0.0) { xl = rts; xh = x2; }
+  else { xh = rts; xl = x1; }
+  #pragma unroll 1
+  for (int i = 1; i <= EPA_NR_MAX_ITERS; ++i)
+  {
+    rts_old = rts;
+    if (df <= 0.0 || ((rts - xh) * df - f) * ((rts - xl) * df - f) >= 0.0)
+    {
+      dx = 0.5 * (xh - xl);
+      rts = xl + dx;
+      if (xl == rts) return rts;
+    }
+    else
+    {
+      dx = f / df;
+      const double temp = rts;
+      rts -= dx;
+      if (temp == rts) return rts;
+    }
+    if (fabs(dx) < tol) return rts_old;
+    if (i == EPA_NR_MAX_ITERS) break;
+    if (rts < x1) rts = x1;
+    deriv(rts, f, df);
+    if (!isfinite(f) || !isfinite(df)) { failed = true; return 0.0; }
+    if (df > 0.0 && fabs(f) < tol) return rts;
+    if (f < 0.0) xl = rts; else xh = rts;
+  }
+  failed = true;
+  return rts_old;
+}
 
 // Sumtable row of one site: [stationary part, 3R decaying components], padded to an ODD number of
 // doubles so that the lane = site reads of the Newton loop (stride = one row) touch 16 distinct
@@ -375,13 +421,14 @@ template <int R>
 __device__ __forceinline__ void warp_pass_distal(const BloCtaSmem & cs, const double * ws, double * sum,
                                               const double * __restrict__ D, const double * __restrict__ X,
                                               const uint8_t * __restrict__ qc, int w, int lane,
-                                              const double * __restrict__ inv_w)
+                                              const double * __restrict__ inv_w, int pm_x = BloWarpSmem<R>::P_P)
 {
+  // pm_x: offset of X's transition matrix (--raxml-blo runs the pass with D and X swapped as well)
   constexpr int SPW = 32 / R;
   const int r = lane % R, so = lane / R;
   double pp[16];
   #pragma unroll
-  for (int k = 0; k < 16; ++k) pp[k] = ws[BloWarpSmem<R>::P_P + k * R + r];
+  for (int k = 0; k < 16; ++k) pp[k] = ws[pm_x + k * R + r];
   const double * tv = ws + BloWarpSmem<R>::TV + r;
   const double wr = c_model.weights[r];
   const int n_units = (w + SPW - 1) / SPW;
@@ -443,7 +490,8 @@ __device__ __forceinline__ unsigned long long cta_next_item(BloCtaSmem & cs, uns
 }
 
 // GS = sumtable in global scratch (windows that do not fit the shared-memory slice)
-template <int R, bool GS>
+// RAXML = --raxml-blo (see newton_old above and the lane = site kernel)
+template <int R, bool GS, bool RAXML = false>
 __global__ void __launch_bounds__(256, 1)
 blo_dna_kernel(BloArgs a)
 {
@@ -513,6 +561,64 @@ blo_dna_kernel(BloArgs a)
     // instruction cache without giving up inlining.
     const double orig = ed.length;
     double len[3] = {orig / 2.0, orig / 2.0, EPA_DEFAULT_PENDANT};      // distal, proximal, pendant
+    if constexpr (RAXML)
+    {
+      // pllmod_opt_optimize_branch_lengths_local, radius 1 (PM/optimize/pll_optimize.c:778-1097)
+      using L = BloWarpSmem<R>;
+      #pragma unroll 1
+      for (int mi = 0; mi < 3; ++mi) warp_pmatrix<R>(cs, len[mi], ws + mi * (R * 16), ex, lane);
+      warp_tipvec<R>(ws + L::P_E, ws + L::TV, lane);
+      auto pass_tip = [&]() -> double { return warp_pass_tip<R>(cs, ws, sum, D, X, sD, sX, qc, w, lane, inv_w); };
+      auto edge = [&](int mi) -> bool
+      {
+        double xguess = len[mi];
+        if (xguess < EPA_MIN_BRLEN || xguess > EPA_MAX_BRLEN) xguess = EPA_DEFAULT_BRLEN;
+        bool failed;
+        const double xres = newton_old([&](double x, double & f, double & df) { warp_derivatives<R>(sum, ex, w, x, lane, f, df); },
+                                       EPA_MIN_BRLEN, xguess, EPA_MAX_BRLEN, EPA_MIN_BRLEN / 10.0, failed);
+        if (failed) return false;
+        const bool moved = fabs(xres - len[mi]) > 1e-10;
+        len[mi] = xres;
+        if (moved)
+        {
+          warp_pmatrix<R>(cs, xres, ws + mi * (R * 16), ex, lane);
+          if (mi == 2) warp_tipvec<R>(ws + L::P_E, ws + L::TV, lane);
+        }
+        return true;
+      };
+      double loglikelihood = pass_tip();
+      int iters = EPA_SMOOTHINGS;
+      bool ok = true;
+      while (iters)
+      {
+        if (!(ok = edge(2))) break;
+        warp_pass_distal<R>(cs, ws, sum, D, X, qc, w, lane, inv_w, L::P_P);
+        if (!(ok = edge(0))) break;
+        warp_pass_distal<R>(cs, ws, sum, X, D, qc, w, lane, inv_w, L::P_D);
+        if (!(ok = edge(1))) break;
+        double new_logl = pass_tip();
+        const double pend_before = len[2];
+        if (!(ok = edge(2))) break;
+        if (fabs(len[2] - pend_before) > 1e-10) new_logl = pass_tip();
+        if (new_logl - loglikelihood > new_logl * 1e-13)
+        {
+          --iters;
+          if (fabs(new_logl - loglikelihood) < EPA_BLO_EPSILON) iters = 0;
+          loglikelihood = new_logl;
+        }
+        else { loglikelihood = new_logl; break; }
+      }
+      if (lane == 0)
+      {
+        BloResult res;
+        res.logl = ok ? loglikelihood : 0.0;
+        res.distal = (orig / (len[0] + len[1])) * len[0];
+        res.pendant = len[2];
+        a.out[pid] = res;
+      }
+      __syncwarp();
+      continue;
+    }
     const double original_length = len[0] * 2;
     double old_d = len[0], old_e = len[2], loglikelihood = 0.0;
     int smoothings = EPA_SMOOTHINGS;

@@ -167,12 +167,13 @@ __device__ __forceinline__ double gen_pass_tip(double * sm, double * sum, int wp
 template <int S, int R>
 __device__ __forceinline__ void gen_pass_distal(double * sm, double * sum, int wpad, const double * __restrict__ D,
                                                 const double * __restrict__ X, const uint8_t * __restrict__ qc, int w,
-                                                const double * __restrict__ inv_w)
+                                                const double * __restrict__ inv_w, int which_x = 1)
 {
+  // which_x: matrix of X's edge (1 = proximal; --raxml-blo also runs the pass with the nodes swapped, 0)
   using L = GenSmem<S, R>;
   const int lane = threadIdx.x & 31;
   const int r = threadIdx.x % R;
-  const double * Pp = sm + L::P + (R + r) * L::PS;
+  const double * Pp = sm + L::P + (which_x * R + r) * L::PS;
   const double * tvr = sm + L::TV + r * L::TVS;
   const double wr = c_model.weights[r];
   const int n_units = ((w * R + GEN_THREADS - 1) / GEN_THREADS) * GEN_THREADS;
@@ -298,7 +299,8 @@ __device__ __forceinline__ double gen_pass_tip_site(double * sm, double * sum, i
 template <int S, int R>
 __device__ __forceinline__ void gen_pass_distal_site(double * sm, double * sum, int wpad, const double * __restrict__ DT,
                                                      const double * __restrict__ XT, const uint8_t * __restrict__ qc,
-                                                     int begin, int w, double * rbuf, const double * __restrict__ inv_w)
+                                                     int begin, int w, double * rbuf, const double * __restrict__ inv_w,
+                                                     int which_x = 1)
 {
   using L = GenSmem<S, R>;
   double * basebuf = rbuf;
@@ -310,7 +312,7 @@ __device__ __forceinline__ void gen_pass_distal_site(double * sm, double * sum, 
     double dv[S], xv[S], in[S];
     #pragma unroll
     for (int k = 0; k < S; ++k) { dv[k] = __ldg(DT + off + (size_t) k * 32); xv[k] = __ldg(XT + off + (size_t) k * 32); }
-    const double2 * Pp = reinterpret_cast<const double2 *>(sm + L::P + (R + r) * L::PS);
+    const double2 * Pp = reinterpret_cast<const double2 *>(sm + L::P + (which_x * R + r) * L::PS);
     const double * tvr = sm + L::TV + r * L::TVS + code * S;
     #pragma unroll
     for (int i = 0; i < S; ++i)
@@ -460,7 +462,8 @@ __device__ __forceinline__ double gen_newton(double * sm, const double * sum, in
   }
 }
 
-template <int S, int R>
+// RAXML = --raxml-blo (pllmod_opt_optimize_branch_lengths_local with radius 1, PM/optimize/pll_optimize.c:778-1097)
+template <int S, int R, bool RAXML = false>
 __global__ void __launch_bounds__(GEN_THREADS, 1)
 blo_generic_kernel(BloArgs a, int wpad, const double * __restrict__ clvT, size_t t_stride)
 {
@@ -524,6 +527,87 @@ blo_generic_kernel(BloArgs a, int wpad, const double * __restrict__ clvT, size_t
 
     const double orig = ed.length;
     double len[3] = {orig / 2.0, orig / 2.0, EPA_DEFAULT_PENDANT};
+    if constexpr (RAXML)
+    {
+      // Steps of one round, one CLV pass and one Newton call each (single call sites keep the code small):
+      //   0: [tip pass] score the round, pendant   1: distal   2: proximal   3: tip pass, pendant from the tip's side
+      // Step 0 of the next round re-scores only if step 3 moved the pendant length (otherwise the
+      // log-likelihood and the sumtable of step 3 are still those of the current lengths).
+      double loglikelihood = 0.0, logl_now = 0.0;
+      int iters = EPA_SMOOTHINGS, step = 0;
+      unsigned rebuild = 7u;
+      bool first = true, need_tip = true, ok = true;
+      for (;;)
+      {
+        #pragma unroll 1
+        for (int mi = 0; mi < 3; ++mi)
+          if (rebuild & (1u << mi))
+          {
+            gen_pmatrix<S, R>(sm, len[mi], mi);
+            if (mi == 2) gen_tipvec<S, R>(sm);
+          }
+        rebuild = 0u;
+        int target;
+        if (step == 0 || step == 3)
+        {
+          if (step == 3 || need_tip)
+            logl_now = clvT
+                ? gen_pass_tip_site<S, R>(sm, sum, wpad, clvT + (size_t) ed.distal * t_stride, clvT + (size_t) ed.proximal * t_stride, sD, sX, qc, begin, w, sm + L::TOTAL, inv_w)
+                : gen_pass_tip<S, R>(sm, sum, wpad, D, X, sD, sX, qc, w, inv_w);
+          if (step == 0)
+          {
+            if (first) { loglikelihood = logl_now; first = false; }
+            else
+            {
+              const double new_logl = logl_now;
+              if (new_logl - loglikelihood > new_logl * 1e-13)
+              {
+                --iters;
+                if (fabs(new_logl - loglikelihood) < EPA_BLO_EPSILON) iters = 0;
+                loglikelihood = new_logl;
+              }
+              else { loglikelihood = new_logl; iters = 0; }      // a worse score is kept and ends the loop
+            }
+            if (!iters) break;
+          }
+          target = 2;
+        }
+        else
+        {
+          const bool prox = step == 2;          // proximal edge: the distal pass with the two nodes swapped
+          if (clvT)
+            gen_pass_distal_site<S, R>(sm, sum, wpad, clvT + (size_t) (prox ? ed.proximal : ed.distal) * t_stride,
+                                       clvT + (size_t) (prox ? ed.distal : ed.proximal) * t_stride, qc, begin, w, sm + L::TOTAL, inv_w, prox ? 0 : 1);
+          else
+            gen_pass_distal<S, R>(sm, sum, wpad, prox ? X : D, prox ? D : X, qc, w, inv_w, prox ? 0 : 1);
+          target = prox ? 1 : 0;
+        }
+        double xguess = len[target];
+        if (xguess < EPA_MIN_BRLEN || xguess > EPA_MAX_BRLEN) xguess = EPA_DEFAULT_BRLEN;
+        bool failed;
+        double * rbuf = clvT ? sm + L::TOTAL : nullptr;
+        const double xres = newton_old([&](double x, double & f, double & df)
+                                       {
+                                         if (rbuf) gen_derivatives_units<S, R>(sm, sum, wpad, w, x, f, df, rbuf);
+                                         else gen_derivatives<S, R>(sm, sum, wpad, w, x, f, df);
+                                       }, EPA_MIN_BRLEN, xguess, EPA_MAX_BRLEN, EPA_MIN_BRLEN / 10.0, failed);
+        if (failed) { ok = false; break; }
+        const bool moved = fabs(xres - len[target]) > 1e-10;
+        len[target] = xres;
+        if (moved) rebuild = 1u << target;
+        if (step == 3) need_tip = moved;
+        step = (step + 1) & 3;
+      }
+      if (threadIdx.x == 0)
+      {
+        BloResult res;
+        res.logl = ok ? loglikelihood : 0.0;
+        res.distal = (orig / (len[0] + len[1])) * len[0];
+        res.pendant = len[2];
+        a.out[pid] = res;
+      }
+      continue;
+    }
     const double original_length = len[0] * 2;
     double old_d = len[0], old_e = len[2], loglikelihood = 0.0;
     int smoothings = EPA_SMOOTHINGS;
@@ -615,6 +699,13 @@ inline cudaError_t launch_blo_generic_sr(int sm_count, size_t smem_optin, int ma
     *scratch_cap = need;
   }
   a.scratch = static_cast<double *>(*scratch);
+  if (a.raxml)
+  {
+    cudaError_t e = cudaFuncSetAttribute(blo_generic_kernel<S, R, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+    if (e != cudaSuccess) return e;
+    blo_generic_kernel<S, R, true><<<grid, GEN_THREADS, smem, stream>>>(a, wpad, clvT, t_stride);
+    return cudaGetLastError();
+  }
   cudaError_t e = cudaFuncSetAttribute(blo_generic_kernel<S, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
   if (e != cudaSuccess) return e;
   blo_generic_kernel<S, R><<<grid, GEN_THREADS, smem, stream>>>(a, wpad, clvT, t_stride);

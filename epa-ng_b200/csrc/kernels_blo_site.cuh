@@ -740,13 +740,15 @@ __device__ __forceinline__ double site_pass_first(const SiteCtaSmem & cs, const 
   return warp_sum(acc);
 }
 
-// Pass B: inner CLV toward the distal node from (T, X); leaves the distal sumtable (D vs inner)
+// Pass B: inner CLV toward the distal node from (T, X); leaves the distal sumtable (D vs inner).
+// `pm_x` is the offset of X's transition matrix in the warp's slice. (--raxml-blo also optimises the
+// proximal edge on its own: the same pass with the two nodes swapped and D's matrix.)
 template <int R, bool GS, bool PR, bool INV>
 __device__ __forceinline__ void site_pass_distal(const double * ws, const SumRef & sr,
                                               const double * __restrict__ DT, const double * __restrict__ XT,
                                               const uint32_t * __restrict__ sD, const uint32_t * __restrict__ sX,
                                               const uint8_t * __restrict__ qc, int begin, int w, int lane, int bugcompat,
-                                              const double * __restrict__ inv_w)
+                                              const double * __restrict__ inv_w, int pm_x = SiteWarpSmem<R>::P_P)
 {
   using L = SiteWarpSmem<R>;
   const int trips = (w + 31) >> 5;
@@ -775,7 +777,7 @@ __device__ __forceinline__ void site_pass_distal(const double * ws, const SumRef
       for (int i = 0; i < 4; ++i)
       {
         double pp[4];
-        lds_vec<4>(ws + L::P_P + r * 16 + i * 4, pp);
+        lds_vec<4>(ws + pm_x + r * 16 + i * 4, pp);
         const double tb = pp[0] * xv[r * 4] + pp[1] * xv[r * 4 + 1] + pp[2] * xv[r * 4 + 2] + pp[3] * xv[r * 4 + 3];
         in[r * 4 + i] = tp[i] * tb;
         if constexpr (PR) in[r * 4 + i] *= rf[r];
@@ -835,7 +837,10 @@ __device__ __forceinline__ unsigned long long site_next_item(SiteCtaSmem & cs, u
 // GS = sumtable in global scratch (windows that do not fit the shared-memory slice)
 // PR = per-rate scalers (the scaler pointers then address the node's [n][R] block, not the window)
 // INV = +I model (a.tree.inv holds the per-site invariant terms)
-template <int R, bool GS, bool PR = false, bool INV = false>
+// RAXML = --raxml-blo (optimize.cpp:274-278): pendant, distal and proximal edge optimised one after the
+// other, each unconstrained in [1e-4, 100], then the pendant edge once more from the tip's side
+// (pllmod_opt_optimize_branch_lengths_local with radius 1, PM/optimize/pll_optimize.c:778-1097)
+template <int R, bool GS, bool PR = false, bool INV = false, bool RAXML = false>
 __global__ void __launch_bounds__(SITE_MAX_WARPS * 32, 1)
 blo_site_kernel(BloSiteArgs sa)
 {
@@ -920,9 +925,77 @@ blo_site_kernel(BloSiteArgs sa)
     const uint8_t * qc = a.codes + (size_t) q * n + begin;
     const double * inv_w = INV ? a.tree.inv + begin : nullptr;         // pll_util.cpp:413-414
 
-    // optimize_branch_triplet / opt_branch_lengths_pplacer as half rounds (see kernels_blo.cuh)
     const double orig = ed.length;
     double len[3] = {orig / 2.0, orig / 2.0, EPA_DEFAULT_PENDANT};      // distal, proximal, pendant
+    if constexpr (RAXML)
+    {
+      #pragma unroll 1
+      for (int mi = 0; mi < 3; ++mi) site_pmatrix<R>(cs, len[mi], ws + mi * (R * 16), ex, lane);
+      site_tipvec<R>(ws + L::P_E, ws + L::TV, lane);
+      auto pass_tip = [&]() -> double
+      {
+        return site_pass_tip<R, GS, PR, INV>(cs, ws, sr, DT, XT, sD, sX, qc, begin, w, lane, sa.bugcompat, inv_w);
+      };
+      // one recomp_iterative step (pll_optimize.c:799-833) on the edge whose sumtable is current:
+      // Newton, new length, matrix rebuilt if the length moved by more than 1e-10
+      auto edge = [&](int mi) -> bool
+      {
+        double xguess = len[mi];
+        if (xguess < EPA_MIN_BRLEN || xguess > EPA_MAX_BRLEN) xguess = EPA_DEFAULT_BRLEN;
+        bool failed;
+        const double xres = newton_old([&](double x, double & f, double & df) { site_derivatives<R, GS>(sr, ex, w, x, lane, f, df); },
+                                       EPA_MIN_BRLEN, xguess, EPA_MAX_BRLEN, EPA_MIN_BRLEN / 10.0, failed);
+        if (failed) return false;
+        const bool moved = fabs(xres - len[mi]) > 1e-10;
+        len[mi] = xres;
+        if (moved)
+        {
+          site_pmatrix<R>(cs, xres, ws + mi * (R * 16), ex, lane);
+          if (mi == 2) site_tipvec<R>(ws + L::P_E, ws + L::TV, lane);
+        }
+        return true;
+      };
+      double loglikelihood = (sa.gT)
+          ? site_pass_first<R, GS, INV>(cs, sr, sa.gT + (size_t) e * sa.g_stride, sa.lookup + (size_t) e * sa.n_pad * 16,
+                                        qc, begin, w, lane, inv_w)
+          : pass_tip();
+      int iters = EPA_SMOOTHINGS;
+      bool ok = true;
+      while (iters)
+      {
+        if (!(ok = edge(2))) break;                                                    // pendant
+        site_pass_distal<R, GS, PR, INV>(ws, sr, DT, XT, sD, sX, qc, begin, w, lane, sa.bugcompat, inv_w, L::P_P);
+        if (!(ok = edge(0))) break;                                                    // distal
+        site_pass_distal<R, GS, PR, INV>(ws, sr, XT, DT, sX, sD, qc, begin, w, lane, sa.bugcompat, inv_w, L::P_D);
+        if (!(ok = edge(1))) break;                                                    // proximal
+        double new_logl = pass_tip();                                                  // inner CLV back toward the tip
+        const double pend_before = len[2];
+        if (!(ok = edge(2))) break;                                                    // pendant, from the tip's side
+        if (fabs(len[2] - pend_before) > 1e-10) new_logl = pass_tip();                 // score with the new matrix
+        if (new_logl - loglikelihood > new_logl * 1e-13)
+        {
+          --iters;
+          if (fabs(new_logl - loglikelihood) < EPA_BLO_EPSILON) iters = 0;
+          loglikelihood = new_logl;
+        }
+        else
+        {
+          loglikelihood = new_logl;          // the older optimiser keeps a worse score and stops (:1084-1088)
+          break;
+        }
+      }
+      if (lane == 0)
+      {
+        BloResult res;
+        res.logl = ok ? loglikelihood : 0.0;                  // a failed Newton call: PLL_FAILURE = 0 comes back
+        res.distal = (orig / (len[0] + len[1])) * len[0];     // Tiny_Tree.cpp:183-185
+        res.pendant = len[2];
+        a.out[pid] = res;
+      }
+      __syncwarp();
+      continue;
+    }
+    // optimize_branch_triplet / opt_branch_lengths_pplacer as half rounds (see kernels_blo.cuh)
     const double original_length = len[0] * 2;
     double old_d = len[0], old_e = len[2], loglikelihood = 0.0;
     int smoothings = EPA_SMOOTHINGS;

@@ -113,7 +113,7 @@ typedef struct {
   int32_t heuristic;              /* 0 dynamic (accumulated LWR, -g), 1 fixed fraction (-G), 2 baseball */
   double prescoring_threshold;    /* default 0.99999 */
   int32_t premasking;             /* 1: restrict each query to [first non-gap, last non-gap] */
-  int32_t sliding_blo;            /* 1: pplacer-style BLO (default); 0 (--raxml-blo) not supported */
+  int32_t sliding_blo;            /* 1: pplacer-style BLO (default); 0: --raxml-blo (optimize.cpp:274-278) */
   int32_t filter_acc_lwr;         /* 0: min-LWR filter (default), 1: accumulated-LWR filter */
   double support_threshold;       /* default 0.01 */
   uint32_t filter_min;            /* default 1 */

@@ -60,7 +60,7 @@ def test_cli_synth64_matches_reference(built, tmp_path):
     names = [pq["n"][0] for pq in doc["placements"]]
     assert names == sorted(names)
     # unsupported modes are refused by name, not silently ignored
-    r = subprocess.run([exe, "-t", "x", "-s", "x", "-q", "x", "--raxml-blo"], capture_output=True, text=True)
+    r = subprocess.run([exe, "-t", "x", "-s", "x", "-q", "x", "--dump-binary"], capture_output=True, text=True)
     assert r.returncode != 0 and "not supported" in r.stderr
 
 
