@@ -37,6 +37,7 @@ void usage()
       "  --filter-acc-lwr FLOAT    accumulated-LWR output filter\n"
       "  --filter-min-lwr FLOAT    minimum-LWR output filter [0.01]\n"
       "  --filter-min INT [1]      --filter-max INT [7]      --precision INT [10]\n"
+      "  -c,--bfast FILE           convert an aligned DNA FASTA file to the bfast format (into -w) and exit\n"
       "  --device INT              CUDA device [0]\n"
       "  --redo, -T/--threads N, --verbose  accepted for compatibility\n"
       "  -v,--version\n");
@@ -46,7 +47,7 @@ void usage()
 
 int main(int argc, char ** argv)
 {
-  std::string tree, ref, query, model = "GTR+G", outdir = "./";
+  std::string tree, ref, query, model = "GTR+G", outdir = "./", bfast_conv;
   epa_options opts;
   epa_options_default(&opts);
   uint32_t chunk = 0;
@@ -91,10 +92,17 @@ int main(int argc, char ** argv)
     else if (a == "--correct-scaler-focus") rate_bug = 0;     // not a reference option: read the scalers of the site itself
     else if (a == "--preserve-rooting") { const std::string v = need(i); preserve_rooting = (v != "off"); }
     else if (a == "--raxml-blo") opts.sliding_blo = 0;        // src/core/pll/optimize.cpp:274-278
-    else if (a == "-b" || a == "--binary" ||
-             a == "-B" || a == "--dump-binary" || a == "-c" || a == "--bfast" || a == "--split")    // (bfast query FILES are read; the converter is not part of the path)
+    else if (a == "-c" || a == "--bfast") bfast_conv = need(i);        // src/main.cpp:284-288
+    else if (a == "-b" || a == "--binary" || a == "-B" || a == "--dump-binary" || a == "--split")
       die("option " + a + " is outside the accelerated hot path and not supported by this build");
     else die("unknown option " + a);
+  }
+  if (!bfast_conv.empty())
+  {
+    char written[4096];
+    if (epa_host_fasta_to_bfast(bfast_conv.c_str(), outdir.c_str(), written, sizeof written)) die(epa_host_last_error());
+    std::printf("Resulting bfast file was written to: %s\n", written);
+    return 0;
   }
   if (tree.empty() || ref.empty() || query.empty()) { usage(); die("-t, -s and -q are required"); }
   if (epa_host_set_rate_scalers(rate_mode, rate_bug)) die(epa_host_last_error());

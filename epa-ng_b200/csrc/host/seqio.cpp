@@ -78,6 +78,54 @@ Alignment read_bfast(const std::string & path)
   return a;
 }
 
+// Writer of the same format (Binary_Fasta::fasta_to_bfast, src/io/Binary_Fasta.hpp:33-70,214-246):
+// header with the all-gap column mask and the random-access table, then label + packed sites per
+// sequence. DNA only: a character outside "-TGKCYSBAWRDMHVN" is refused as the reference refuses
+// amino-acid data (ensure_dna, :142-153).
+std::string write_bfast(const Alignment & a, const std::string & fasta_path, std::string out_dir)
+{
+  int code[256];
+  for (int & c : code) c = -1;
+  for (int i = 0; i < 16; ++i) code[(unsigned char) kNtMap[i]] = i;
+  for (uint8_t ch : a.rows)
+    if (code[ch] < 0)
+      throw std::runtime_error(std::string("AA DATA NOT SUPPORTED for conversion to bfast! Sorry! Offending char: ") + (char) ch);
+  const size_t slash = fasta_path.find_last_of('/');
+  if (!out_dir.empty() && out_dir.back() != '/') out_dir += '/';
+  const std::string out_path = out_dir + (slash == std::string::npos ? fasta_path : fasta_path.substr(slash + 1)) + ".bfast";
+
+  std::string out;
+  auto put_u64 = [&](uint64_t v) { char b[8]; std::memcpy(b, &v, 8); out.append(b, 8); };
+  out.append(kBfastMagic, sizeof kBfastMagic);
+  put_u64(a.size());
+  const std::vector<uint8_t> mask = gap_mask(a);
+  put_u64(mask.size());
+  for (uint8_t m : mask) out.push_back(m ? '1' : '0');
+  const size_t packed = (a.sites + 1) / 2;
+  uint64_t offset = sizeof kBfastMagic + 8 + a.size() * 16 + mask.size() + 8;      // data_section_offset, :33-36
+  for (size_t i = 0; i < a.size(); ++i)
+  {
+    put_u64(i);
+    put_u64(offset);
+    offset += 16 + a.names[i].size() + packed;
+  }
+  for (size_t i = 0; i < a.size(); ++i)
+  {
+    put_u64(a.names[i].size());
+    out += a.names[i];
+    put_u64(a.sites);
+    const uint8_t * r = a.row(i);
+    for (size_t k = 0; k < a.sites; k += 2)
+      out.push_back((char) ((code[r[k]] << 4) | (k + 1 < a.sites ? code[r[k + 1]] : 0)));
+  }
+  FILE * fh = std::fopen(out_path.c_str(), "wb");
+  if (!fh) throw std::runtime_error("Cannot open file for writing: " + out_path);
+  const bool ok = std::fwrite(out.data(), 1, out.size(), fh) == out.size();
+  std::fclose(fh);
+  if (!ok) throw std::runtime_error("Cannot write file: " + out_path);
+  return out_path;
+}
+
 Alignment read_alignment(const std::string & path)
 {
   return is_bfast(path) ? read_bfast(path) : read_fasta(path);

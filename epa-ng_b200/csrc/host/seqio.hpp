@@ -22,6 +22,8 @@ Alignment read_fasta(const std::string & path);                       // throws 
 // src/io/encoding.hpp): decoded back to upper-case rows; DNA only, like the reference's converter.
 bool is_bfast(const std::string & path);
 Alignment read_bfast(const std::string & path);
+// the converter behind -c/--bfast (Binary_Fasta::fasta_to_bfast :214-246): writes <out_dir>/<file name>.bfast, returns its path
+std::string write_bfast(const Alignment & a, const std::string & fasta_path, std::string out_dir);
 Alignment read_alignment(const std::string & path);                  // bfast if the magic matches, FASTA otherwise
 std::vector<uint8_t> gap_mask(const Alignment & a);                  // 1 = every sequence has a gap character
 Alignment apply_mask(const Alignment & a, const std::vector<uint8_t> & drop);

@@ -444,6 +444,18 @@ extern "C" int epa_host_read_alignment(const char * path, uint32_t * n_sequences
   catch (const std::exception & e) { return host_fail(EPA_ERR_ARG, e.what()); }
 }
 
+extern "C" int epa_host_fasta_to_bfast(const char * fasta_path, const char * out_dir, char * out_path, size_t cap)
+{
+  if (!fasta_path || !out_dir) return host_fail(EPA_ERR_ARG, "null argument");
+  try
+  {
+    const std::string written = write_bfast(read_fasta(fasta_path), fasta_path, out_dir);
+    if (out_path && cap) std::snprintf(out_path, cap, "%s", written.c_str());
+    return EPA_OK;
+  }
+  catch (const std::exception & e) { return host_fail(EPA_ERR_ARG, e.what()); }
+}
+
 extern "C" int epa_host_map_rooted(const char * newick, uint32_t * edges, double * distal, uint32_t count,
                                    char * out_unrooted_newick, size_t cap)
 {

@@ -14,6 +14,7 @@ HOST_SYMBOLS = [
     ("epa_session_place", C.c_int, [_vp, _vp, C.c_uint64, C.POINTER(capi.Options), C.c_uint32, _vp, _vp]),
     ("epa_host_set_rate_scalers", C.c_int, [C.c_int, C.c_int]),
     ("epa_host_read_alignment", C.c_int, [C.c_char_p, _u32p, _u32p, _vp, C.c_size_t, C.c_char_p, C.c_size_t]),
+    ("epa_host_fasta_to_bfast", C.c_int, [C.c_char_p, C.c_char_p, C.c_char_p, C.c_size_t]),
     ("epa_session_ctx", _vp, [_vp]),
     ("epa_session_num_edges", C.c_uint32, [_vp]),
     ("epa_session_num_tips", C.c_uint32, [_vp]),
@@ -143,6 +144,13 @@ def read_alignment(path: str):
     _check(lib().epa_host_read_alignment(path.encode(), C.byref(n), C.byref(sites), rows.ctypes.data, rows.size, labels,
                                          len(labels)))
     return labels.value.decode().split("\n")[:n.value], rows
+
+
+def fasta_to_bfast(fasta_path: str, out_dir: str) -> str:
+    """The reference's -c/--bfast converter; returns the path of the written file."""
+    buf = C.create_string_buffer(4096)
+    _check(lib().epa_host_fasta_to_bfast(fasta_path.encode(), out_dir.encode(), buf, len(buf)))
+    return buf.value.decode()
 
 
 def map_rooted(newick: str, edges, distal):

@@ -86,6 +86,9 @@ int epa_host_parse_tree(const char * newick, int precision, char * out_newick, s
  * the sizes only. */
 int epa_host_read_alignment(const char * path, uint32_t * n_sequences, uint32_t * sites, char * rows, size_t rows_cap,
                             char * labels, size_t labels_cap);
+/* -c/--bfast of the reference (Binary_Fasta::fasta_to_bfast, src/io/Binary_Fasta.hpp:214-246, src/main.cpp:284-288):
+ * converts an aligned DNA FASTA file to <out_dir>/<file name>.bfast; out_path (may be NULL) receives the path. */
+int epa_host_fasta_to_bfast(const char * fasta_path, const char * out_dir, char * out_path, size_t cap);
 /* Rooted input only: translates (edge, distal length) pairs of the unrooted working tree to the
  * rooted tree, in place; writes the numbered newick of the working tree when out_newick != NULL. */
 int epa_host_map_rooted(const char * newick, uint32_t * edges, double * distal, uint32_t count,

@@ -167,3 +167,22 @@ def test_bfast_reader_matches_fasta(built):
     # every 4-bit code occurs in the first fixture
     _, codes = built.session.read_alignment(os.path.join(g, "bfast", "codes.fasta.bfast"))
     assert set(bytes(codes.reshape(-1)).decode()) == set("-TGKCYSBAWRDMHVN")
+
+
+def test_bfast_converter_is_byte_identical_to_the_reference(built, tmp_path):
+    """-c/--bfast (Binary_Fasta::fasta_to_bfast, src/io/Binary_Fasta.hpp:214-246): the files written by the
+    host layer equal, byte for byte, the ones the reference's converter wrote (committed fixtures);
+    amino-acid input is refused like the reference does (ensure_dna)."""
+    g = helpers.GOLDEN
+    for fasta in (os.path.join(g, "bfast", "codes.fasta"), os.path.join(g, "cfg1", "query.fasta")):
+        out = built.session.fasta_to_bfast(fasta, str(tmp_path))
+        assert out == os.path.join(str(tmp_path), os.path.basename(fasta) + ".bfast")
+        assert open(out, "rb").read() == open(fasta + ".bfast", "rb").read()
+    with pytest.raises(built.capi.EpaError, match="AA DATA NOT SUPPORTED"):
+        built.session.fasta_to_bfast(os.path.join(g, "synthaa", "query.fasta"), str(tmp_path))
+    exe = os.path.join(helpers.ROOT, "epa-ng_b200", "epa-ng-b200")
+    d = tmp_path / "cli"
+    d.mkdir()
+    import subprocess
+    subprocess.run([exe, "-c", os.path.join(g, "bfast", "codes.fasta"), "-w", str(d)], check=True, stdout=subprocess.DEVNULL)
+    assert open(d / "codes.fasta.bfast", "rb").read() == open(os.path.join(g, "bfast", "codes.fasta.bfast"), "rb").read()
