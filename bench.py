@@ -132,6 +132,21 @@ def ncu_traffic(kernel, q, chunk):
     return tot or None
 
 
+def ncu_metric(kernel, metric):
+    """One number of the committed ncu --set full summary of `kernel` (profiles/r1_ncu_<kernel>.txt), or None."""
+    path = os.path.join(ROOT, "profiles", "r1_ncu_%s.txt" % kernel.replace("_kernel", ""))
+    if not os.path.exists(path):
+        return None
+    for line in open(path):
+        t = line.split()
+        if len(t) >= 2 and t[0] == metric:
+            try:
+                return float(t[1])
+            except ValueError:
+                return None
+    return None
+
+
 def workload_config(q_per_gpu, gpus):
     return {"workload": "cfg2: 1k-taxon DNA tree (GTR+G4, 1000-site MSA), synthetic 200bp window queries, "
                         "preplacement heuristic -g 0.99999",
@@ -313,6 +328,12 @@ def ours(args):
                     "unit": "GB/s", "frac": kernels[dom]["frac"], "traffic": ncu_traffic(kname, Q, chunk), "peak_source": peak_src,
                     "launch_ms": kernels[dom]["ms_per_step"] / n_launch,
                     "algorithmic_bytes_per_launch": units[dom] * per_unit[dom] / n_launch}
+        if dom == "thorough":
+            # the branch-length optimisation re-reads its CLV windows from L1/L2 for every pass and spends its
+            # time in fp64 arithmetic: the HBM fraction is the contract's figure, the fp64 pipe is what limits it
+            roofline["fp64_pipe_active_pct_ncu"] = ncu_metric(kname, "sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active")
+            roofline["note"] = ("fp64-issue bound (Newton-Raphson derivative sums and CLV passes, DESIGN 3.2): ncu fp64 pipe "
+                                "utilisation of the committed capture next to the HBM figure")
 
         cpu = None
         parity = None

@@ -460,6 +460,14 @@ extern "C" int epa_ctx_create(epa_ctx ** out, int device, const epa_model_desc *
     cudaDeviceSynchronize();
     CUC(cudaMemcpyToSymbol(c_model, &ctx->hm, sizeof(DevModel)));
     g_const_owner[device] = ctx;
+    // table of the lookup build's logarithm (kernels_blo_site.cuh: table_log), the same for every context
+    double2 logtab[128];
+    for (int i = 0; i < 128; ++i)
+    {
+      const double c = 1.0 / (1.0 + ((double) i + 0.5) * (1.0 / 128.0));
+      logtab[i] = make_double2(c, -std::log(c));
+    }
+    CUC(cudaMemcpyToSymbol(g_logtab, logtab, sizeof logtab));
   }
 #undef CUC
   *out = ctx;
@@ -700,9 +708,9 @@ extern "C" int epa_build_lookup(epa_ctx * ctx)
       CU(cudaEventRecord(ctx->ev[0], ctx->stream));
       switch (R)
       {
-        case 1: lookup_build_site_kernel<1><<<grid, 128, 0, ctx->stream>>>(ctx->d_model, ctx->d_clvT, t_stride, ctx->tree.scaler, (int) ctx->tree.sr, ctx->tree.inv, n, ctx->n_pad, ctx->d_edges, d_pm, ctx->d_lookup); break;
-        case 2: lookup_build_site_kernel<2><<<grid, 128, 0, ctx->stream>>>(ctx->d_model, ctx->d_clvT, t_stride, ctx->tree.scaler, (int) ctx->tree.sr, ctx->tree.inv, n, ctx->n_pad, ctx->d_edges, d_pm, ctx->d_lookup); break;
-        default: lookup_build_site_kernel<4><<<grid, 128, 0, ctx->stream>>>(ctx->d_model, ctx->d_clvT, t_stride, ctx->tree.scaler, (int) ctx->tree.sr, ctx->tree.inv, n, ctx->n_pad, ctx->d_edges, d_pm, ctx->d_lookup); break;
+        case 1: lookup_build_site_kernel<1><<<grid, 128, 4 * lookup_warp_doubles<1>() * sizeof(double), ctx->stream>>>(ctx->d_model, ctx->d_clvT, t_stride, ctx->tree.scaler, (int) ctx->tree.sr, ctx->tree.inv, n, ctx->n_pad, ctx->d_edges, d_pm, ctx->d_lookup); break;
+        case 2: lookup_build_site_kernel<2><<<grid, 128, 4 * lookup_warp_doubles<2>() * sizeof(double), ctx->stream>>>(ctx->d_model, ctx->d_clvT, t_stride, ctx->tree.scaler, (int) ctx->tree.sr, ctx->tree.inv, n, ctx->n_pad, ctx->d_edges, d_pm, ctx->d_lookup); break;
+        default: lookup_build_site_kernel<4><<<grid, 128, 4 * lookup_warp_doubles<4>() * sizeof(double), ctx->stream>>>(ctx->d_model, ctx->d_clvT, t_stride, ctx->tree.scaler, (int) ctx->tree.sr, ctx->tree.inv, n, ctx->n_pad, ctx->d_edges, d_pm, ctx->d_lookup); break;
       }
       LAUNCHED(ctx);
       CU(cudaStreamSynchronize(ctx->stream));

@@ -233,25 +233,93 @@ __device__ __forceinline__ size_t clvt_offset(int abs_site)
 // launch): the 240 table reads of a site become constant-bank operands of the FMAs
 __constant__ double c_coltab[16 * 4 * MAX_RATES / 2];      // R <= 4
 
+// Natural logarithm of a positive normal double through a 128-entry table: x = 2^e m, m in [1, 2),
+// c = tab[top 7 mantissa bits].x ~ 1 / m, r = m c - 1 exactly rounded once (|r| <= 2^-8),
+// log x = e ln 2 - log c + log1p(r) with a degree-7 Taylor polynomial (truncation 2^-59 relative).
+// Absolute error ~1e-16 (|log x| + 1): the table sums of the preplacement are insensitive to it.
+// The CUDA log() is ~90 instructions with its special-case handling, and 15 of them per site made
+// the lookup build issue bound; zero, subnormal, negative and non-finite arguments still take it.
+__device__ __forceinline__ double table_log(double x, const double2 * __restrict__ tab)
+{
+  const int hi = __double2hiint(x);
+  if ((unsigned) (hi - 0x00100000) >= 0x7fe00000u) return log(x);
+  const double2 t = tab[(hi >> 13) & 127];
+  const double m = __hiloint2double((hi & 0x000fffff) | 0x3ff00000, __double2loint(x));
+  const double r = fma(m, t.x, -1.0);
+  double p = 1.0 / 7.0;
+  p = fma(p, r, -1.0 / 6.0);
+  p = fma(p, r, 1.0 / 5.0);
+  p = fma(p, r, -1.0 / 4.0);
+  p = fma(p, r, 1.0 / 3.0);
+  p = fma(p, r, -0.5);
+  const double l1p = fma(p * r, r, r);
+  const double e = (double) ((hi >> 20) - 1023);
+  // ln 2 split so that e * hi part is exact for |e| < 2^11
+  return fma(e, 0x1.62e42fefa38p-1, t.y) + fma(e, 0x1.ef35793c7673p-45, l1p);
+}
+
+// site_loglk (common.cuh) with the table logarithm
+__device__ __forceinline__ double site_loglk_tab(double term, uint32_t sc, double inv, const double2 * __restrict__ tab)
+{
+  if (inv > 0.0) return table_log(sc ? term * rate_scale_factor(min(sc, EPA_RATE_MAXDIFF)) + inv : term + inv, tab);
+  return table_log(term, tab) + (sc ? (double) sc * EPA_LOG_SCALE_THRESHOLD : 0.0);
+}
+
+// (c_i, -log c_i), c_i = 1 / (1 + (i + 1/2) / 128): written once per device at context creation
+__device__ double2 g_logtab[128];
+
+// shared memory of one warp of the lookup build: its two CLV columns (32 sites x C components each),
+// later overwritten by its 32 x 16 result rows (stride 17)
 template <int R>
-__global__ void __launch_bounds__(128)
+__host__ __device__ constexpr int lookup_warp_doubles() { return (2 * 4 * R * 32 > 32 * 17 ? 2 * 4 * R * 32 : 32 * 17 + 32) & ~31; }
+
+template <int R>
+__global__ void __launch_bounds__(128, 6)
 lookup_build_site_kernel(const DevModel * __restrict__ m, const double * __restrict__ clvT, size_t t_stride,
                          const uint32_t * __restrict__ scaler, int sr, const double * __restrict__ inv_lk, int n, int n_pad,
                          const EdgeDev * __restrict__ edges, const double * __restrict__ pmats_half,
                          double * __restrict__ lookup)
 {
-  constexpr int K = 16, C = 4 * R;
+  constexpr int K = 16, C = 4 * R, WD = lookup_warp_doubles<R>();
+  extern __shared__ __align__(128) double lk_stage[];   // [4 warps][WD]
   __shared__ __align__(16) double P[R * 16];
-  __shared__ double tile[4][32 * 17];                // per warp: 32 sites x 16 columns, row stride 17
+  __shared__ double2 logtab[128];                    // lanes index it with their own mantissa bits
+  __shared__ uint64_t bar[4];
   const EdgeDev e = edges[blockIdx.x];
-  for (int i = threadIdx.x; i < R * 16; i += blockDim.x) P[i] = __ldg(pmats_half + (size_t) blockIdx.x * R * 16 + i);
-  __syncthreads();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int site = blockIdx.y * 128 + threadIdx.x;
+  const int site0 = blockIdx.y * 128 + warp * 32;
+  const bool have = site0 < n;                       // the site-blocked copy is padded to whole 32-site blocks
+  const int site = site0 + lane;
   const int s = site < n ? site : n - 1;
-  const size_t off = clvt_offset<R>(s);
-  const double * dp = clvT + (size_t) e.distal * t_stride + off;
-  const double * xp = clvT + (size_t) e.proximal * t_stride + off;
+  double * stage = lk_stage + warp * WD;
+  if (threadIdx.x < 4) { mbar_init(&bar[threadIdx.x], 1); mbar_fence_init(); }
+  __syncthreads();
+  // The two 32-site CLV columns of the warp (C x 256 bytes each, contiguous in the site-blocked copy)
+  // arrive as two bulk copies: no registers are tied up while they are in flight, six blocks stay
+  // resident per SM and their load and arithmetic phases overlap.
+  if (have && lane == 0)
+  {
+    constexpr uint32_t bytes = C * 32 * sizeof(double);
+    const size_t boff = (size_t) (site0 >> 5) * (size_t) (C * CLVT_BLOCK);
+    mbar_expect_tx(&bar[warp], 2 * bytes);
+    bulk_g2s(stage, clvT + (size_t) e.distal * t_stride + boff, bytes, &bar[warp]);
+    bulk_g2s(stage + C * 32, clvT + (size_t) e.proximal * t_stride + boff, bytes, &bar[warp]);
+  }
+  uint32_t kr[R];
+  if (sr == 1)
+    kr[0] = __ldg(scaler + (size_t) e.distal * n + s) + __ldg(scaler + (size_t) e.proximal * n + s);
+  else
+  {
+    #pragma unroll
+    for (int r = 0; r < R; ++r)
+      kr[r] = __ldg(scaler + ((size_t) e.distal * n + s) * R + r) + __ldg(scaler + ((size_t) e.proximal * n + s) * R + r);
+  }
+  const double inv = inv_lk ? __ldg(inv_lk + s) : 0.0;
+  for (int i = threadIdx.x; i < R * 16; i += blockDim.x) P[i] = __ldg(pmats_half + (size_t) blockIdx.x * R * 16 + i);
+  for (int i = threadIdx.x; i < 128; i += blockDim.x) logtab[i] = g_logtab[i];
+  __syncthreads();
+  if (!have) return;                                 // (no block-wide barrier below)
+  mbar_wait(&bar[warp], 0);
   uint32_t sc = 0;
   double in[C];
   bool small = true;
@@ -260,7 +328,7 @@ lookup_build_site_kernel(const DevModel * __restrict__ m, const double * __restr
   {
     double dv[4], xv[4];
     #pragma unroll
-    for (int k = 0; k < 4; ++k) { dv[k] = __ldg(dp + (size_t) (r * 4 + k) * CLVT_BLOCK); xv[k] = __ldg(xp + (size_t) (r * 4 + k) * CLVT_BLOCK); }
+    for (int k = 0; k < 4; ++k) { dv[k] = stage[(r * 4 + k) * 32 + lane]; xv[k] = stage[(C + r * 4 + k) * 32 + lane]; }
     #pragma unroll
     for (int i = 0; i < 4; ++i)
     {
@@ -272,9 +340,10 @@ lookup_build_site_kernel(const DevModel * __restrict__ m, const double * __restr
       small = small && (in[r * 4 + i] < EPA_SCALE_THRESHOLD);
     }
   }
+  __syncwarp();                                      // every lane has consumed its columns: the slice is reused for the result rows
   if (sr == 1)
   {
-    sc = __ldg(scaler + (size_t) e.distal * n + s) + __ldg(scaler + (size_t) e.proximal * n + s);
+    sc = kr[0];
     if (small)
     {
       sc += 1;
@@ -287,13 +356,9 @@ lookup_build_site_kernel(const DevModel * __restrict__ m, const double * __restr
     // per-rate scalers: a rate whose count is d above the site's minimum weighs 2^(-256 d). The inner
     // CLV is not rescaled here: its own per-rate rescaling would only move factors of 2^256 between
     // the values and these counts.
-    uint32_t kr[R], kmin = 0xffffffffu;
+    uint32_t kmin = 0xffffffffu;
     #pragma unroll
-    for (int r = 0; r < R; ++r)
-    {
-      kr[r] = __ldg(scaler + ((size_t) e.distal * n + s) * R + r) + __ldg(scaler + ((size_t) e.proximal * n + s) * R + r);
-      kmin = min(kmin, kr[r]);
-    }
+    for (int r = 0; r < R; ++r) kmin = min(kmin, kr[r]);
     #pragma unroll
     for (int r = 0; r < R; ++r)
     {
@@ -303,12 +368,13 @@ lookup_build_site_kernel(const DevModel * __restrict__ m, const double * __restr
     }
     sc = kmin;
   }
-  const double inv = inv_lk ? __ldg(inv_lk + s) : 0.0;
-  double * trow = tile[warp] + lane * 17;
-  trow[0] = 0.0;                                       // column 0 = zero column
+  // The likelihood of a state set is the sum of the likelihoods of its states: four single-state terms
+  // (columns 1, 2, 4, 8 of the column table), eleven sums, fifteen logarithms.
+  double single[4];
   #pragma unroll
-  for (int c = 1; c < K; ++c)
+  for (int j = 0; j < 4; ++j)
   {
+    const int c = 1 << j;
     double term = 0.0;
     #pragma unroll
     for (int r = 0; r < R; ++r)
@@ -317,18 +383,29 @@ lookup_build_site_kernel(const DevModel * __restrict__ m, const double * __restr
                       + in[r * 4 + 2] * c_coltab[c * C + r * 4 + 2] + in[r * 4 + 3] * c_coltab[c * C + r * 4 + 3];
       term += tr * c_model.weights[r];
     }
-    trow[c] = site_loglk(term, sc, inv);
+    single[j] = term;
+  }
+  double * trow = stage + lane * 17;
+  trow[0] = 0.0;                                       // column 0 = zero column
+  #pragma unroll
+  for (int c = 1; c < K; ++c)
+  {
+    double term = 0.0;
+    bool any = false;
+    #pragma unroll
+    for (int j = 0; j < 4; ++j)
+      if ((c >> j) & 1) { term = any ? term + single[j] : single[j]; any = true; }
+    trow[c] = site_loglk_tab(term, sc, inv, logtab);
   }
   __syncwarp();
   // the warp's 32 table rows are 4 KB contiguous in global memory: coalesced 256-byte stores
-  const int site0 = blockIdx.y * 128 + warp * 32;
   const int n_valid = min(32, n - site0) * K;
   double * out = lookup + ((size_t) blockIdx.x * n_pad + site0) * K;
   #pragma unroll
   for (int k = 0; k < K; ++k)
   {
     const int idx = k * 32 + lane;
-    if (idx < n_valid) out[idx] = tile[warp][(idx >> 4) * 17 + (idx & 15)];
+    if (idx < n_valid) out[idx] = stage[(idx >> 4) * 17 + (idx & 15)];
   }
 }
 
