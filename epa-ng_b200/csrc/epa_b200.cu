@@ -292,8 +292,9 @@ extern "C" int epa_ctx_create(epa_ctx ** out, int device, const epa_model_desc *
   *out = nullptr;
   if (!supported_sr((int) model->states, (int) model->rate_cats))
     return fail(ctx, EPA_ERR_ARG, "unsupported states/rate_cats combination %u/%u", model->states, model->rate_cats);
-  if ((model->flags & EPA_FLAG_RATE_SCALERS) && !(model->states == 4 && model->rate_cats <= 4))
-    return fail(ctx, EPA_ERR_ARG, "per-rate scalers are only supported for DNA with at most 4 rate categories");
+  if ((model->flags & EPA_FLAG_RATE_SCALERS) && model->states != 4)
+    return fail(ctx, EPA_ERR_ARG, "per-rate scalers are only supported for DNA (the reference's amino-acid path mixes per-site "
+                                  "and per-rate counts in its tip-inner updates, DESIGN section 4)");
   if (!(model->pinv >= 0.0 && model->pinv < 1.0))        // LP/models.c:510-518
     return fail(ctx, EPA_ERR_ARG, "Invalid proportion of invariant sites (%f)", model->pinv);
   if (model->sites == 0 || n_tips < 3 || n_edges == 0) return fail(ctx, EPA_ERR_ARG, "empty tree or alignment");
@@ -1267,6 +1268,22 @@ int launch_blo_site(epa_ctx * ctx, BloArgs & a)
   return EPA_OK;
 }
 
+template <int R, bool GS, bool RAXML, bool PR>
+int launch_dna_kernel(epa_ctx * ctx, const BloArgs & a, unsigned grid, int warps, size_t smem)
+{
+  CU(cudaFuncSetAttribute(blo_dna_kernel<R, GS, RAXML, PR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+  blo_dna_kernel<R, GS, RAXML, PR><<<grid, warps * 32, smem, ctx->stream>>>(a);
+  return EPA_OK;
+}
+
+template <int R, bool GS>
+int launch_dna_variant(epa_ctx * ctx, const BloArgs & a, unsigned grid, int warps, size_t smem)
+{
+  const bool pr = ctx->tree.sr > 1;
+  if (a.raxml) return pr ? launch_dna_kernel<R, GS, true, true>(ctx, a, grid, warps, smem) : launch_dna_kernel<R, GS, true, false>(ctx, a, grid, warps, smem);
+  return pr ? launch_dna_kernel<R, GS, false, true>(ctx, a, grid, warps, smem) : launch_dna_kernel<R, GS, false, false>(ctx, a, grid, warps, smem);
+}
+
 template <int R>
 int launch_blo_dna(epa_ctx * ctx, BloArgs & a)
 {
@@ -1282,16 +1299,7 @@ int launch_blo_dna(epa_ctx * ctx, BloArgs & a)
     // keep every SM busy but do not launch far more warps than there are pairs
     uint64_t grid = (uint64_t) ctx->sm_count * ctas_per_sm;
     grid = std::min<uint64_t>(grid, (a.n_pairs + warps - 1) / warps);
-    if (a.raxml)
-    {
-      CU(cudaFuncSetAttribute(blo_dna_kernel<R, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
-      blo_dna_kernel<R, false, true><<<(unsigned) grid, warps * 32, smem, ctx->stream>>>(a);
-    }
-    else
-    {
-      CU(cudaFuncSetAttribute(blo_dna_kernel<R, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
-      blo_dna_kernel<R, false><<<(unsigned) grid, warps * 32, smem, ctx->stream>>>(a);
-    }
+    if (int rc = launch_dna_variant<R, false>(ctx, a, (unsigned) grid, warps, smem)) return rc;
   }
   else
   {
@@ -1301,8 +1309,7 @@ int launch_blo_dna(epa_ctx * ctx, BloArgs & a)
     a.scratch = ctx->scratch.as<double>();
     a.wcap = 0;
     const size_t smem = BloWarpSmem<R>::doubles(0) * sizeof(double) * warps;
-    if (a.raxml) blo_dna_kernel<R, true, true><<<grid, warps * 32, smem, ctx->stream>>>(a);
-    else blo_dna_kernel<R, true><<<grid, warps * 32, smem, ctx->stream>>>(a);
+    if (int rc = launch_dna_variant<R, true>(ctx, a, grid, warps, smem)) return rc;
   }
   LAUNCHED(ctx);
   return EPA_OK;
@@ -1331,6 +1338,7 @@ extern "C" int epa_place_pairs(epa_ctx * ctx, const epa_options * opts)
     a.n_pairs = (uint32_t) ctx->n_pairs; a.nq = ctx->nq; a.n_edges = ctx->n_edges;
     a.counter = ctx->d_counter; a.out = ctx->res.as<BloResult>(); a.scratch = nullptr; a.wcap = 0;
     a.raxml = opts->sliding_blo ? 0 : 1;
+    a.bugcompat = ctx->hm.bugcompat;
     int rc;
     if (ctx->S == 4)
     {

@@ -68,6 +68,7 @@ struct BloArgs {
   BloResult * out;                // [pair id]
   double * scratch;               // global sumtable scratch (GS variant): [total warps][1 + 3R planes]
   int wcap;                       // sites the shared-memory sumtable can hold
+  int bugcompat;                  // per-rate scalers: the reference's window offset, R = 8 kernel
   int raxml;                      // 1 = --raxml-blo: the three edges optimised one after the other, unconstrained
                                   // (pllmod_opt_optimize_branch_lengths_local, PM/optimize/pll_optimize.c:778-1097)
 };
@@ -192,6 +193,14 @@ __device__ __forceinline__ double rate_sum(double v)
 {
   #pragma unroll
   for (int o = 1; o < R; o <<= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+template <int R>
+__device__ __forceinline__ uint32_t rate_min(uint32_t v)
+{
+  #pragma unroll
+  for (int o = 1; o < R; o <<= 1) v = min(v, __shfl_xor_sync(0xffffffffu, v, o));
   return v;
 }
 
@@ -330,11 +339,14 @@ __device__ __forceinline__ double warp_newton(const double * sum, double * ex, i
 // 8-9 resident warps per SM the L2 latency of the CLV stream is not hidden by other warps).
 struct UnitIn { double dv[4], xv[4]; int mask; uint32_t scal; double inv; };
 
-template <int R, bool SCALERS>
+// SCALERS: 0 = none, 1 = per-site count of the window site, 2 = per-rate scalers: the lane's own rate
+// (sD/sX then address the node's whole [n][R] block; `pr_begin` and `bugcompat` select the entry as in
+// kernels_blo_site.cuh: rate_weights)
+template <int R, int SCALERS>
 __device__ __forceinline__ UnitIn load_unit(const double * __restrict__ D, const double * __restrict__ X,
                                             const uint32_t * __restrict__ sD, const uint32_t * __restrict__ sX,
                                             const uint8_t * __restrict__ qc, int s, int w, int r,
-                                            const double * __restrict__ inv_w)
+                                            const double * __restrict__ inv_w, int pr_begin = 0, int bugcompat = 0)
 {
   const int sc = s < w ? s : w - 1;            // tail lanes re-read the last site; results are discarded
   UnitIn u;
@@ -342,18 +354,24 @@ __device__ __forceinline__ UnitIn load_unit(const double * __restrict__ D, const
   load_vec<4>(D + ((size_t) sc * R + r) * 4, u.dv);
   load_vec<4>(X + ((size_t) sc * R + r) * 4, u.xv);
   u.mask = qc[sc] & 15;
-  u.scal = SCALERS ? __ldg(sD + sc) + __ldg(sX + sc) : 0u;
+  if (SCALERS == 2)
+  {
+    const size_t base = (bugcompat ? (size_t) pr_begin + (size_t) sc * R : ((size_t) pr_begin + sc) * R) + r;
+    u.scal = __ldg(sD + base) + __ldg(sX + base);
+  }
+  else
+    u.scal = SCALERS == 1 ? __ldg(sD + sc) + __ldg(sX + sc) : 0u;
   return u;
 }
 
 // Pass A: inner CLV toward the new tip from (D, X); returns the edge log-likelihood
 // new_tip | inner over the window and leaves the pendant sumtable (inner vs tip) in `sum`.
-template <int R>
+template <int R, bool PR>
 __device__ __forceinline__ double warp_pass_tip(const BloCtaSmem & cs, const double * ws, double * sum,
                                              const double * __restrict__ D, const double * __restrict__ X,
                                              const uint32_t * __restrict__ sD, const uint32_t * __restrict__ sX,
                                              const uint8_t * __restrict__ qc, int w, int lane,
-                                             const double * __restrict__ inv_w)
+                                             const double * __restrict__ inv_w, int pr_begin, int bugcompat)
 {
   constexpr int SPW = 32 / R;
   const int r = lane % R, so = lane / R;
@@ -367,13 +385,13 @@ __device__ __forceinline__ double warp_pass_tip(const BloCtaSmem & cs, const dou
   uint32_t mscal = 0;
   // whole trips of R unit steps: the R lanes of a site take turns at the logarithm
   const int n_units = ((w + SPW * R - 1) / (SPW * R)) * R;
-  UnitIn nxt = load_unit<R, true>(D, X, sD, sX, qc, so, w, r, inv_w);
+  UnitIn nxt = load_unit<R, PR ? 2 : 1>(D, X, sD, sX, qc, so, w, r, inv_w, pr_begin, bugcompat);
   #pragma unroll 1
   for (int i = 0; i < n_units; ++i)
   {
     const UnitIn cur = nxt;
     const int s = i * SPW + so;
-    nxt = load_unit<R, true>(D, X, sD, sX, qc, s + SPW, w, r, inv_w);
+    nxt = load_unit<R, PR ? 2 : 1>(D, X, sD, sX, qc, s + SPW, w, r, inv_w, pr_begin, bugcompat);
     const bool act = s < w;
     double in[4];
     uint32_t scal = cur.scal;
@@ -386,7 +404,17 @@ __device__ __forceinline__ double warp_pass_tip(const BloCtaSmem & cs, const dou
       in[k] = ta * tb;
       small = small && (in[k] < EPA_SCALE_THRESHOLD);
     }
-    if (group_all<R>(small, lane))
+    if constexpr (PR)
+    {
+      // per-rate scalers: a rate whose count is d above the site's minimum weighs 2^(-256 d); no
+      // rescaling inside the tiny tree (it would only move factors of 2^256 between values and counts)
+      const uint32_t kmin = rate_min<R>(scal);
+      const double f = rate_scale_factor(min(scal - kmin, EPA_RATE_MAXDIFF));
+      #pragma unroll
+      for (int k = 0; k < 4; ++k) in[k] *= f;
+      scal = kmin;
+    }
+    else if (group_all<R>(small, lane))
     {
       #pragma unroll
       for (int k = 0; k < 4; ++k) in[k] *= EPA_SCALE_FACTOR;
@@ -417,11 +445,13 @@ __device__ __forceinline__ double warp_pass_tip(const BloCtaSmem & cs, const dou
 }
 
 // Pass B: inner CLV toward the distal node from (T, X); leaves the distal sumtable (D vs inner)
-template <int R>
+template <int R, bool PR>
 __device__ __forceinline__ void warp_pass_distal(const BloCtaSmem & cs, const double * ws, double * sum,
                                               const double * __restrict__ D, const double * __restrict__ X,
+                                              const uint32_t * __restrict__ sD, const uint32_t * __restrict__ sX,
                                               const uint8_t * __restrict__ qc, int w, int lane,
-                                              const double * __restrict__ inv_w, int pm_x = BloWarpSmem<R>::P_P)
+                                              const double * __restrict__ inv_w, int pr_begin, int bugcompat,
+                                              int pm_x = BloWarpSmem<R>::P_P)
 {
   // pm_x: offset of X's transition matrix (--raxml-blo runs the pass with D and X swapped as well)
   constexpr int SPW = 32 / R;
@@ -432,13 +462,13 @@ __device__ __forceinline__ void warp_pass_distal(const BloCtaSmem & cs, const do
   const double * tv = ws + BloWarpSmem<R>::TV + r;
   const double wr = c_model.weights[r];
   const int n_units = (w + SPW - 1) / SPW;
-  UnitIn nxt = load_unit<R, false>(D, X, nullptr, nullptr, qc, so, w, r, inv_w);
+  UnitIn nxt = load_unit<R, PR ? 2 : 0>(D, X, sD, sX, qc, so, w, r, inv_w, pr_begin, bugcompat);
   #pragma unroll 1
   for (int i = 0; i < n_units; ++i)
   {
     const UnitIn cur = nxt;
     const int s = i * SPW + so;
-    nxt = load_unit<R, false>(D, X, nullptr, nullptr, qc, s + SPW, w, r, inv_w);
+    nxt = load_unit<R, PR ? 2 : 0>(D, X, sD, sX, qc, s + SPW, w, r, inv_w, pr_begin, bugcompat);
     const bool act = s < w;
     double in[4];
     bool small = true;
@@ -449,7 +479,13 @@ __device__ __forceinline__ void warp_pass_distal(const BloCtaSmem & cs, const do
       in[k] = tv[(k * 16 + tv_pos(cur.mask)) * R] * tb;
       small = small && (in[k] < EPA_SCALE_THRESHOLD);
     }
-    if (group_all<R>(small, lane))
+    if constexpr (PR)
+    {
+      const double f = rate_scale_factor(min(cur.scal - rate_min<R>(cur.scal), EPA_RATE_MAXDIFF));
+      #pragma unroll
+      for (int k = 0; k < 4; ++k) in[k] *= f;
+    }
+    else if (group_all<R>(small, lane))
     {
       #pragma unroll
       for (int k = 0; k < 4; ++k) in[k] *= EPA_SCALE_FACTOR;
@@ -491,7 +527,8 @@ __device__ __forceinline__ unsigned long long cta_next_item(BloCtaSmem & cs, uns
 
 // GS = sumtable in global scratch (windows that do not fit the shared-memory slice)
 // RAXML = --raxml-blo (see newton_old above and the lane = site kernel)
-template <int R, bool GS, bool RAXML = false>
+// PR = per-rate scalers
+template <int R, bool GS, bool RAXML = false, bool PR = false>
 __global__ void __launch_bounds__(256, 1)
 blo_dna_kernel(BloArgs a)
 {
@@ -550,8 +587,8 @@ blo_dna_kernel(BloArgs a)
     const int n = a.n;
     const double * D = a.tree.clv + ed.distal * a.tree.clv_stride + (size_t) begin * R * 4;
     const double * X = a.tree.clv + ed.proximal * a.tree.clv_stride + (size_t) begin * R * 4;
-    const uint32_t * sD = a.tree.scaler + (size_t) ed.distal * n + begin;
-    const uint32_t * sX = a.tree.scaler + (size_t) ed.proximal * n + begin;
+    const uint32_t * sD = PR ? a.tree.scaler + (size_t) ed.distal * n * R : a.tree.scaler + (size_t) ed.distal * n + begin;
+    const uint32_t * sX = PR ? a.tree.scaler + (size_t) ed.proximal * n * R : a.tree.scaler + (size_t) ed.proximal * n + begin;
     const uint8_t * qc = a.codes + (size_t) q * n + begin;
     const double * inv_w = a.tree.inv ? a.tree.inv + begin : nullptr;      // +I: pll_util.cpp:413-414
 
@@ -568,7 +605,7 @@ blo_dna_kernel(BloArgs a)
       #pragma unroll 1
       for (int mi = 0; mi < 3; ++mi) warp_pmatrix<R>(cs, len[mi], ws + mi * (R * 16), ex, lane);
       warp_tipvec<R>(ws + L::P_E, ws + L::TV, lane);
-      auto pass_tip = [&]() -> double { return warp_pass_tip<R>(cs, ws, sum, D, X, sD, sX, qc, w, lane, inv_w); };
+      auto pass_tip = [&]() -> double { return warp_pass_tip<R, PR>(cs, ws, sum, D, X, sD, sX, qc, w, lane, inv_w, begin, a.bugcompat); };
       auto edge = [&](int mi) -> bool
       {
         double xguess = len[mi];
@@ -592,9 +629,9 @@ blo_dna_kernel(BloArgs a)
       while (iters)
       {
         if (!(ok = edge(2))) break;
-        warp_pass_distal<R>(cs, ws, sum, D, X, qc, w, lane, inv_w, L::P_P);
+        warp_pass_distal<R, PR>(cs, ws, sum, D, X, sD, sX, qc, w, lane, inv_w, begin, a.bugcompat, L::P_P);
         if (!(ok = edge(0))) break;
-        warp_pass_distal<R>(cs, ws, sum, X, D, qc, w, lane, inv_w, L::P_D);
+        warp_pass_distal<R, PR>(cs, ws, sum, X, D, sX, sD, qc, w, lane, inv_w, begin, a.bugcompat, L::P_D);
         if (!(ok = edge(1))) break;
         double new_logl = pass_tip();
         const double pend_before = len[2];
@@ -639,7 +676,7 @@ blo_dna_kernel(BloArgs a)
       if (!distal_phase)
       {
         // score the current lengths (also builds the pendant sumtable of the coming round)
-        const double new_logl = -warp_pass_tip<R>(cs, ws, sum, D, X, sD, sX, qc, w, lane, inv_w);
+        const double new_logl = -warp_pass_tip<R, PR>(cs, ws, sum, D, X, sD, sX, qc, w, lane, inv_w, begin, a.bugcompat);
         if (first) { loglikelihood = new_logl; first = false; }
         else
         {
@@ -659,7 +696,7 @@ blo_dna_kernel(BloArgs a)
       }
       else
       {
-        warp_pass_distal<R>(cs, ws, sum, D, X, qc, w, lane, inv_w);
+        warp_pass_distal<R, PR>(cs, ws, sum, D, X, sD, sX, qc, w, lane, inv_w, begin, a.bugcompat);
         xmin = fmin(EPA_MIN_BRLEN / 2.0, original_length / 2.0);
         xmax = original_length - xmin / 10.0;
         xguess = len[0];

@@ -215,14 +215,37 @@ lookup_build_kernel(const DevModel * __restrict__ m, DevTree tree, int n, int n_
       all_small = all_small && (inner[r][i] < EPA_SCALE_THRESHOLD);
     }
   }
-  uint32_t sc = tree.scaler[(size_t) e.distal * n + site] + tree.scaler[(size_t) e.proximal * n + site];
-  if (all_small)
+  uint32_t sc;
+  if (tree.sr > 1)
   {
-    sc += 1;
+    // per-rate scalers (as in lookup_build_site_kernel): rate weights 2^(-256 d) relative to the site's minimum count
+    uint32_t kr[R], kmin = 0xffffffffu;
     #pragma unroll
     for (int r = 0; r < R; ++r)
+    {
+      kr[r] = tree.scaler[((size_t) e.distal * n + site) * R + r] + tree.scaler[((size_t) e.proximal * n + site) * R + r];
+      kmin = min(kmin, kr[r]);
+    }
+    #pragma unroll
+    for (int r = 0; r < R; ++r)
+    {
+      const double f = rate_scale_factor(min(kr[r] - kmin, EPA_RATE_MAXDIFF));
       #pragma unroll
-      for (int i = 0; i < S; ++i) inner[r][i] *= EPA_SCALE_FACTOR;
+      for (int i = 0; i < S; ++i) inner[r][i] *= f;
+    }
+    sc = kmin;
+  }
+  else
+  {
+    sc = tree.scaler[(size_t) e.distal * n + site] + tree.scaler[(size_t) e.proximal * n + site];
+    if (all_small)
+    {
+      sc += 1;
+      #pragma unroll
+      for (int r = 0; r < R; ++r)
+        #pragma unroll
+        for (int i = 0; i < S; ++i) inner[r][i] *= EPA_SCALE_FACTOR;
+    }
   }
   const double inv = tree.inv ? __ldg(tree.inv + site) : 0.0;
   double wr[R];

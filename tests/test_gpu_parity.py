@@ -471,3 +471,48 @@ def test_mid_length_windows_tmem16_rows(built):
             assert abs(g["lwr"] - p.lwr) <= 1e-6
             assert abs(g["pendant_length"] - p.pendant) <= 1e-5 and abs(g["distal_length"] - p.distal) <= 1e-5
     ctx.close()
+
+
+@pytest.mark.parametrize("bugcompat", [True, False], ids=["bugcompat", "corrected"])
+def test_per_rate_eight_categories(built, bugcompat):
+    """GTR+G8 with per-rate scalers: the 4-lanes-per-site DNA kernel and the generic lookup build, against the
+    oracle in both scaler-window modes and (bug-compatible mode) against the reference's recorded placements."""
+    import json
+    import os
+    g = json.load(open(os.path.join(helpers.GOLDEN, "rate300", "reference_placements_rate2.json")))["dna8"]
+    ds = built.synth.dataset(**g["dataset"])
+    case = helpers.case_from_arrays(ds["newick"], ds["names"], ds["ref"], ds["qnames"], ds["queries"], g["model"],
+                                    per_rate=True, bugcompat=bugcompat, column_mask=True)
+    ctx = helpers.make_context(case)
+    ctx.build_lookup()
+    _check_clvs(case, ctx)
+    lk = case.placer.build_lookup()
+    for e in range(0, case.tree.num_branches, 23):
+        assert np.allclose(ctx.get_lookup(e), lk[e], rtol=1e-11, atol=1e-11), f"lookup of edge {e}"
+    for sliding in (1, 0):
+        o = helpers.oracle()
+        case.placer = o.Placer(case.ref, o.Options(sliding_blo=bool(sliding)))
+        case.placer.lookup = lk
+        opts = built.capi.default_options(sliding_blo=sliding)
+        ctx.upload_queries(case.query_rows)
+        ctx.preplace()
+        ctx.select(opts)
+        ctx.place_pairs(opts)
+        q, e, raw = ctx.get_pairs()
+        for qi, ei, r in zip(q, e, raw):
+            p = case.placer.thorough(case.qseqs[qi], int(ei))
+            assert abs(r["likelihood"] - p.logl) <= 1e-8 * abs(p.logl), (sliding, qi, ei, r, p)
+            assert abs(r["pendant_length"] - p.pendant) <= 1e-5 and abs(r["distal_length"] - p.distal) <= 1e-5, (sliding, qi, ei, r, p)
+    if bugcompat:
+        out, counts = ctx.place_chunk(case.query_rows, built.capi.default_options())
+        got = dict(zip(case.qnames, helpers.records_to_lists(out, counts)))
+        for name, want in g["placements"].items():
+            helpers.assert_placements_close(got[name], want, name)
+    ctx.close()
+
+
+def test_per_rate_scalers_refused_for_amino_acids(built):
+    case = helpers.synthaa_case()
+    case.model.per_rate_scalers = True
+    with pytest.raises(built.capi.EpaError, match="per-rate scalers"):
+        helpers.make_context(case, compute=False)

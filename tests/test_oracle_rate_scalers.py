@@ -54,3 +54,16 @@ def test_corrected_focus_differs_from_reference(rate300):
         if [p.edge for p in got] != [int(x[0]) for x in want[name]] or abs(got[0].logl - want[name][0][1]) > 1e-6 * abs(got[0].logl):
             diff += 1
     assert diff > 0
+
+
+def test_oracle_per_rate_eight_categories_matches_reference(built):
+    """GTR+G8 with per-rate scalers (tests/golden/make_golden_rate2.py): the 4x4 kernels of the reference keep
+    proper per-rate counts for any number of categories."""
+    g = json.load(open(os.path.join(helpers.GOLDEN, "rate300", "reference_placements_rate2.json")))["dna8"]
+    ds = built.synth.dataset(**g["dataset"])
+    case = helpers.case_from_arrays(ds["newick"], ds["names"], ds["ref"], ds["qnames"], ds["queries"], g["model"],
+                                    per_rate=True, bugcompat=True, column_mask=True)
+    assert max(int(s.scaler.max()) for s in case.ref.sides.values() if s.scaler is not None) >= 1
+    for name, seq in zip(case.qnames, case.qseqs):
+        got = [(p.edge, p.logl, p.lwr, p.distal, p.pendant) for p in case.placer.place(seq)]
+        helpers.assert_placements_close(got, g["placements"][name], name, logl_rel=1e-9, len_abs=1e-5)
