@@ -479,28 +479,40 @@ select_count_kernel(const double * __restrict__ pre, size_t pre_stride, int n_ed
   const bool fast = fast_ok && mode == 0;
   double tot = 0.0;
   int nl = 0;
-  #pragma unroll 4
-  for (int base = 0; base < n_edges; base += 32)
+  // The row is a pure stream (16 KB per query): eight 256-byte loads of the warp stay in flight while the
+  // previous eight are processed (registers as the prefetch buffer; the loads of a plain unrolled loop
+  // were issued too late and the kernel sat at a third of the HBM bandwidth waiting for them).
+  constexpr int PF = 8;
+  double buf[PF];
+  #pragma unroll
+  for (int i = 0; i < PF; ++i) { const int b = 32 * i + lane; buf[i] = b < n_edges ? __ldg(row + b) : -INFINITY; }
+  #pragma unroll 1
+  for (int base = 0; base < n_edges; base += 32 * PF)
   {
-    const int b = base + lane;
-    double v = -INFINITY;
-    if (b < n_edges)
+    double nxt[PF];
+    #pragma unroll
+    for (int i = 0; i < PF; ++i) { const int b = base + 32 * (PF + i) + lane; nxt[i] = b < n_edges ? __ldg(row + b) : -INFINITY; }
+    #pragma unroll
+    for (int i = 0; i < PF; ++i)
     {
-      v = row[b];
+      const int b = base + 32 * i + lane;
+      const double v = buf[i];             // -inf beyond the row: adds nothing, is never near
       // exp(-60) = 8.8e-27: thousands of such terms cannot reach half an ulp of a sum that holds exp(0)
       if (v - mx > -60.0) tot += exp(v - mx);
-    }
-    if (fast)
-    {
-      const bool near = v > mx - SEL_CUT;
-      const unsigned m = __ballot_sync(0xffffffffu, near);
-      if (near)
+      if (fast)
       {
-        const int pos = nl + __popc(m & ((1u << lane) - 1u));
-        if (pos < SEL_LIST) { lv[wib][pos] = v; li[wib][pos] = b; }
+        const bool near = v > mx - SEL_CUT;
+        const unsigned m = __ballot_sync(0xffffffffu, near);
+        if (near)
+        {
+          const int pos = nl + __popc(m & ((1u << lane) - 1u));
+          if (pos < SEL_LIST) { lv[wib][pos] = v; li[wib][pos] = b; }
+        }
+        nl += __popc(m);
       }
-      nl += __popc(m);
     }
+    #pragma unroll
+    for (int i = 0; i < PF; ++i) buf[i] = nxt[i];
   }
   tot = warp_sum(tot);
   __syncwarp();
