@@ -90,7 +90,7 @@ struct epa_ctx {
   uint64_t n_pairs = 0;
   size_t pre_stride = 0;
   DevBuf raw, codes, begin, span, sortkey, perm, hist, range, pre, cnt, cutv, cuti, off, pair_q, pair_e,
-         edge_hist, edge_off, work, res, out_rec, out_cnt, scratch, tmp, qmax, cand;
+         edge_hist, edge_off, work, res, out_rec, out_cnt, scratch, tmp, qmax, cand, scan_sums;
   // host -> device prefetch of the NEXT chunk on a second stream (epa_hint_next_chunk)
   cudaStream_t copy_stream = nullptr;
   cudaEvent_t ev_copy = nullptr;
@@ -811,6 +811,27 @@ static int ensure_copy_stream(epa_ctx * ctx)
   return EPA_OK;
 }
 
+// exclusive scan on the context's stream: one block for short arrays, three launches for long ones
+static int launch_exclusive_scan(epa_ctx * ctx, const uint32_t * in, uint32_t * out, uint32_t count, uint64_t * total)
+{
+  const uint32_t nb = (count + SCAN_ITEMS - 1) / SCAN_ITEMS;
+  if (count <= 2 * SCAN_ITEMS || nb > 65536)
+  {
+    exclusive_scan_kernel<<<1, 1024, 0, ctx->stream>>>(in, out, count, total);
+    LAUNCHED(ctx);
+    return EPA_OK;
+  }
+  CU(ctx->scan_sums.ensure(nb * sizeof(uint32_t)));
+  uint32_t * sums = ctx->scan_sums.as<uint32_t>();
+  scan_block_sums_kernel<<<nb, 256, 0, ctx->stream>>>(in, count, sums);
+  LAUNCHED(ctx);
+  exclusive_scan_kernel<<<1, 1024, 0, ctx->stream>>>(sums, sums, nb, total);
+  LAUNCHED(ctx);
+  scan_apply_kernel<<<nb, 256, 0, ctx->stream>>>(in, out, count, sums);
+  LAUNCHED(ctx);
+  return EPA_OK;
+}
+
 extern "C" int epa_upload_queries(epa_ctx * ctx, const char * seqs, uint32_t n_queries, int premasking)
 {
   if (!ctx) return EPA_ERR_ARG;
@@ -895,7 +916,13 @@ extern "C" int epa_encode_queries_dev(epa_ctx * ctx, const char * seqs_dev, uint
   CU(cudaMemsetAsync(ctx->d_flags, 0, 8 * sizeof(int), ctx->stream));
   const unsigned blocks = (n_queries + 7) / 8;
   CU(ctx->sortkey.ensure(n_queries * sizeof(int)));
-  encode_queries_kernel<<<blocks, 256, 0, ctx->stream>>>(ctx->d_model, src, n_queries, ctx->n, premasking ? 1 : 0,
+  // 64-bit accesses when every row of both buffers is 8-byte aligned
+  if (ctx->n % 8 == 0 && (reinterpret_cast<uintptr_t>(src) & 7) == 0 && (reinterpret_cast<uintptr_t>(ctx->codes.as<uint8_t>()) & 7) == 0)
+    encode_queries_kernel<8><<<blocks, 256, 0, ctx->stream>>>(ctx->d_model, src, n_queries, ctx->n, premasking ? 1 : 0,
+                                                         ctx->codes.as<uint8_t>(), ctx->begin.as<int>(),
+                                                         ctx->span.as<int>(), ctx->sortkey.as<int>(), ctx->d_flags);
+  else
+    encode_queries_kernel<1><<<blocks, 256, 0, ctx->stream>>>(ctx->d_model, src, n_queries, ctx->n, premasking ? 1 : 0,
                                                          ctx->codes.as<uint8_t>(), ctx->begin.as<int>(),
                                                          ctx->span.as<int>(), ctx->sortkey.as<int>(), ctx->d_flags);
   LAUNCHED(ctx);
@@ -909,8 +936,7 @@ extern "C" int epa_encode_queries_dev(epa_ctx * ctx, const char * seqs_dev, uint
     CU(cudaMemsetAsync(ctx->hist.p, 0, (size_t) (nkeys + 1) * sizeof(uint32_t), ctx->stream));
     histogram_kernel<<<(nq + 255) / 256, 256, 0, ctx->stream>>>(ctx->sortkey.as<int>(), nq, ctx->hist.as<uint32_t>());
     LAUNCHED(ctx);
-    exclusive_scan_kernel<<<1, 1024, 0, ctx->stream>>>(ctx->hist.as<uint32_t>(), ctx->hist.as<uint32_t>(), nkeys, nullptr);
-    LAUNCHED(ctx);
+    if (int rc = launch_exclusive_scan(ctx, ctx->hist.as<uint32_t>(), ctx->hist.as<uint32_t>(), nkeys, nullptr)) return rc;
     scatter_by_key_kernel<<<(nq + 255) / 256, 256, 0, ctx->stream>>>(ctx->sortkey.as<int>(), nq, ctx->hist.as<uint32_t>(), ctx->perm.as<uint32_t>());
     LAUNCHED(ctx);
   }
@@ -1105,8 +1131,7 @@ extern "C" int epa_select(epa_ctx * ctx, const epa_options * opts, uint64_t * n_
                                                            ctx->qmax.as<double>(), ctx->cnt.as<uint32_t>(),
                                                            ctx->cutv.as<double>(), ctx->cuti.as<int>(), ctx->cand.as<uint32_t>());
       LAUNCHED(ctx);
-      exclusive_scan_kernel<<<1, 1024, 0, ctx->stream>>>(ctx->cnt.as<uint32_t>(), ctx->off.as<uint32_t>(), nq, ctx->d_total);
-      LAUNCHED(ctx);
+      if (int rc = launch_exclusive_scan(ctx, ctx->cnt.as<uint32_t>(), ctx->off.as<uint32_t>(), nq, ctx->d_total)) return rc;
       uint64_t total = 0;
       CU(cudaMemcpyAsync(&total, ctx->d_total, sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
       CU(cudaStreamSynchronize(ctx->stream));
@@ -1123,8 +1148,7 @@ extern "C" int epa_select(epa_ctx * ctx, const epa_options * opts, uint64_t * n_
                                                           ctx->pair_q.as<uint32_t>(), ctx->pair_e.as<uint32_t>(),
                                                           ctx->edge_hist.as<uint32_t>());
       LAUNCHED(ctx);
-      exclusive_scan_kernel<<<1, 1024, 0, ctx->stream>>>(ctx->edge_hist.as<uint32_t>(), ctx->edge_hist.as<uint32_t>(), (uint32_t) nkeys, nullptr);
-      LAUNCHED(ctx);
+      if (int rc = launch_exclusive_scan(ctx, ctx->edge_hist.as<uint32_t>(), ctx->edge_hist.as<uint32_t>(), (uint32_t) nkeys, nullptr)) return rc;
       if (total)
       {
         work_scatter_kernel<<<(unsigned) ((total + 255) / 256), 256, 0, ctx->stream>>>(ctx->pair_q.as<uint32_t>(), ctx->pair_e.as<uint32_t>(),

@@ -57,6 +57,61 @@ exclusive_scan_kernel(const uint32_t * in, uint32_t * out, uint32_t count, uint6
   }
 }
 
+// Multi-block exclusive scan for long arrays (the single block above takes 50-170 us on 10^5 elements):
+// block sums -> single-block scan of the sums -> per-block scan with its offset. SCAN_ITEMS elements
+// per block (256 threads x 16 consecutive elements); out may alias in; total optional.
+constexpr uint32_t SCAN_ITEMS = 4096;
+
+__global__ void __launch_bounds__(256)
+scan_block_sums_kernel(const uint32_t * __restrict__ in, uint32_t count, uint32_t * __restrict__ sums)
+{
+  __shared__ uint32_t ws[8];
+  const uint32_t base = blockIdx.x * SCAN_ITEMS + threadIdx.x * 16;
+  uint32_t s = 0;
+  #pragma unroll
+  for (int k = 0; k < 16; ++k) s += base + k < count ? in[base + k] : 0u;
+  #pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0)
+  {
+    uint32_t t = 0;
+    for (int w = 0; w < 8; ++w) t += ws[w];
+    sums[blockIdx.x] = t;
+  }
+}
+
+// sums[] already holds the exclusive offsets of the blocks (low 32 bits are enough for the entries; the
+// grand total is kept in 64 bits by the sums scan)
+__global__ void __launch_bounds__(256)
+scan_apply_kernel(const uint32_t * in, uint32_t * out, uint32_t count, const uint32_t * __restrict__ offsets)
+{
+  __shared__ uint32_t ws[8];
+  const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint32_t base = blockIdx.x * SCAN_ITEMS + threadIdx.x * 16;
+  uint32_t v[16], s = 0;
+  #pragma unroll
+  for (int k = 0; k < 16; ++k) { v[k] = base + k < count ? in[base + k] : 0u; s += v[k]; }
+  uint32_t x = s;
+  #pragma unroll
+  for (int o = 1; o < 32; o <<= 1)
+  {
+    const uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
+    if (lane >= (uint32_t) o) x += y;
+  }
+  if (lane == 31) ws[warp] = x;
+  __syncthreads();
+  uint32_t run = offsets[blockIdx.x] + (x - s);
+  for (uint32_t w = 0; w < warp; ++w) run += ws[w];
+  #pragma unroll
+  for (int k = 0; k < 16; ++k)
+  {
+    if (base + k < count) out[base + k] = run;
+    run += v[k];
+  }
+}
+
 // perm[offset[key] + k] = i  (order inside one key is arbitrary)
 __global__ void scatter_by_key_kernel(const int * __restrict__ keys, uint32_t count,
                                       uint32_t * __restrict__ cursor, uint32_t * __restrict__ perm)
@@ -72,30 +127,58 @@ __global__ void scatter_by_key_kernel(const int * __restrict__ keys, uint32_t co
 // A DNA query is simple when it only holds A, C, G, T and fully ambiguous characters: those take
 // the pair-table preplacement kernel. sortkey = begin for simple queries, n + 1 + begin otherwise.
 // ---------------------------------------------------------------------------------------------
+// V = bytes per lane and step (8 when the alignment width and both buffers allow 64-bit accesses, else 1):
+// a warp then moves 256 bytes per load instead of 32.
+template <int V>
 __global__ void __launch_bounds__(256)
 encode_queries_kernel(const DevModel * __restrict__ m, const uint8_t * __restrict__ raw, uint32_t nq, int n,
                       int premask, uint8_t * __restrict__ codes, int * __restrict__ begin,
                       int * __restrict__ span, int * __restrict__ sortkey, int * __restrict__ err)
 {
   __shared__ uint8_t a2c[256];
+  __shared__ int s_simple, s_maxw;          // per-block sums: one global atomic each instead of one per query
   a2c[threadIdx.x] = m->ascii2code[threadIdx.x];
+  if (threadIdx.x == 0) { s_simple = 0; s_maxw = 0; }
   __syncthreads();
   const uint32_t q = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
-  if (q >= nq) return;
-  const uint8_t * row = raw + (size_t) q * n;
-  uint8_t * crow = codes + (size_t) q * n;
+  const bool valid = q < nq;
+  const uint8_t * row = raw + (size_t) (valid ? q : 0) * n;
+  uint8_t * crow = codes + (size_t) (valid ? q : 0) * n;
   int lo = n, hi = -1;
   bool bad = false;
   bool simple = (m->S == 4);
-  for (int s = lane; s < n; s += 32)
+  for (int s0 = lane * V; valid && s0 < n; s0 += 32 * V)
   {
-    const uint8_t ch = row[s];
-    const uint8_t c = a2c[ch];
-    bad = bad || (c == 255);
-    simple = simple && ((0x8116u >> (c & 15)) & 1u);       // masks 1, 2, 4, 8, 15
-    crow[s] = c;
-    if (ch != '-') { lo = min(lo, s); hi = max(hi, s); }
+    uint8_t chv[V], cv[V];
+    if constexpr (V == 8)
+    {
+      const uint2 w = __ldg(reinterpret_cast<const uint2 *>(row + s0));
+      #pragma unroll
+      for (int k = 0; k < 4; ++k) { chv[k] = (uint8_t) (w.x >> (8 * k)); chv[4 + k] = (uint8_t) (w.y >> (8 * k)); }
+    }
+    else
+      chv[0] = row[s0];
+    #pragma unroll
+    for (int k = 0; k < V; ++k)
+    {
+      const int s = s0 + k;
+      const uint8_t ch = chv[k];
+      const uint8_t c = a2c[ch];
+      cv[k] = c;
+      bad = bad || (c == 255);
+      simple = simple && ((0x8116u >> (c & 15)) & 1u);       // masks 1, 2, 4, 8, 15
+      if (ch != '-') { lo = min(lo, s); hi = max(hi, s); }
+    }
+    if constexpr (V == 8)
+    {
+      uint2 o;
+      o.x = (uint32_t) cv[0] | ((uint32_t) cv[1] << 8) | ((uint32_t) cv[2] << 16) | ((uint32_t) cv[3] << 24);
+      o.y = (uint32_t) cv[4] | ((uint32_t) cv[5] << 8) | ((uint32_t) cv[6] << 16) | ((uint32_t) cv[7] << 24);
+      *reinterpret_cast<uint2 *>(crow + s0) = o;
+    }
+    else
+      crow[s0] = cv[0];
   }
   #pragma unroll
   for (int o = 16; o > 0; o >>= 1)
@@ -105,17 +188,23 @@ encode_queries_kernel(const DevModel * __restrict__ m, const uint8_t * __restric
   }
   bad = __any_sync(0xffffffffu, bad);
   simple = __all_sync(0xffffffffu, simple);
-  if (lane == 0)
+  if (valid && lane == 0)
   {
     int b = 0, w = n;
     if (premask) { b = (hi < 0) ? 0 : lo; w = (hi < 0) ? 0 : hi - lo + 1; }
     begin[q] = b;
     span[q] = w;
     sortkey[q] = simple ? b : n + 1 + b;
-    if (simple) atomicAdd(&err[4], 1);
-    atomicMax(&err[3], w);
+    if (simple) atomicAdd(&s_simple, 1);
+    atomicMax(&s_maxw, w);
     if (bad) { if (atomicCAS(&err[0], 0, 1) == 0) err[1] = (int) q + 1; }
     else if (hi < 0) { if (atomicCAS(&err[0], 0, 2) == 0) err[1] = (int) q + 1; }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0)
+  {
+    if (s_simple) atomicAdd(&err[4], s_simple);
+    atomicMax(&err[3], s_maxw);
   }
 }
 
