@@ -306,7 +306,8 @@ Model Model::parse(const std::string & desc)
         for (int k = 0; k < m.states; ++k) m.freqs[k] = vals[k] / sum;
       }
       else if (mode == 'E' || mode == 'O') m.freqs.assign(m.states, 1.0 / m.states);
-      else throw std::runtime_error("model: empirical frequencies (+F/+FC) need the alignment; give +FU{...}");
+      else if (mode == 'C') m.empirical_freqs = true;      // counted once the reference MSA is linked
+      else throw std::runtime_error("Invalid frequencies specification: " + desc);
     }
     else if (ch == 'G')
     {
@@ -332,8 +333,9 @@ Model Model::parse(const std::string & desc)
         m.pinv = vals[0];
         if (!(m.pinv >= 0.0 && m.pinv < 1.0)) throw std::runtime_error("Invalid proportion of invariant sites: " + desc);
       }
+      else if (mode == 'C') m.pinv = 0.0;     // the reference never counts the empirical value ("P-inv (empirical): 0")
       else if (mode != 'O')
-        throw std::runtime_error("model: empirical p-inv (+IC) needs alignment statistics; give +IU{p}");
+        throw std::runtime_error("Invalid p-inv specification: " + desc);
     }
     else
       throw std::runtime_error(std::string("unsupported model option +") + ch + " (supported: +F{U,E,O}, +G, +IU{p})");
@@ -343,6 +345,21 @@ Model Model::parse(const std::string & desc)
   m.weights.assign((size_t) m.rate_cats, 1.0 / m.rate_cats);
   eigen_decompose(m.states, m.subst, m.freqs, m.eigenvals, m.eigenvecs, m.inv_eigenvecs);
   return m;
+}
+
+void Model::set_empirical_freqs(const uint32_t * tip_masks, size_t n_tips, size_t sites)
+{
+  std::vector<double> f((size_t) states, 0.0);
+  for (size_t i = 0; i < n_tips * sites; ++i)
+  {
+    uint32_t st = tip_masks[i];
+    const double share = 1.0 / (double) __builtin_popcount(st);
+    for (int k = 0; k < states; ++k, st >>= 1)
+      if (st & 1u) f[(size_t) k] += share;
+  }
+  for (double & v : f) v /= (double) (n_tips * sites);
+  freqs = f;
+  eigen_decompose(states, subst, freqs, eigenvals, eigenvecs, inv_eigenvecs);
 }
 
 std::string Model::describe() const
@@ -357,7 +374,7 @@ std::string Model::describe() const
   }
   else os << "NONE";
   if (pinv > 0.0) os << "\n        P-inv (user): " << pinv;
-  os << "\n        Base frequencies (user): ";
+  os << "\n        Base frequencies (" << (empirical_freqs ? "empirical" : "user") << "): ";
   for (double f : freqs) os << f << " ";
   if (states == 4)
   {

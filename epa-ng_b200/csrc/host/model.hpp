@@ -1,9 +1,11 @@
 // model.hpp - substitution model of the host layer: the subset of the raxml-ng model grammar that
 // the reference accepts through -m (src/core/raxml/Model.cpp:123-560) and that the device path
 // supports: DNA JC/K80/F81/HKY/GTR and the protein matrices compiled into protein_models.cpp, with
-// user or equal frequencies (+FU{..}/+FE/+FO), discrete GAMMA rate heterogeneity (+G[n][a|m]{alpha}) and a
+// user, equal or empirical frequencies (+FU{..}/+FE/+FO, +F/+FC), discrete GAMMA rate heterogeneity (+G[n][a|m]{alpha}) and a
 // user proportion of invariant sites (+IU{p}). +R and ascertainment correction are rejected with a clear message.
 #pragma once
+#include <cstddef>
+#include <cstdint>
 #include <string>
 #include <vector>
 
@@ -17,11 +19,16 @@ struct Model {
   double alpha = 1.0;
   int rate_cats = 1;
   bool gamma_median = false;
-  double pinv = 0.0;                // +IU{p} (src/core/raxml/Model.cpp:355-380)
+  double pinv = 0.0;                // +IU{p} (src/core/raxml/Model.cpp:355-380); +I/+IO/+IC stay 0 as in the reference
+  bool empirical_freqs = false;     // +F / +FC: frequencies are counted on the reference MSA (set_empirical_freqs)
   std::vector<double> rates, weights;
   std::vector<double> eigenvals, eigenvecs, inv_eigenvecs;   // libpll layout (models.c:394-404)
 
   static Model parse(const std::string & desc);   // throws std::runtime_error
+  // compute_and_set_empirical_frequencies (src/core/pll/optimize.cpp:457-472 -> pllmod_msa_empirical_frequencies,
+  // PM/msa/pll_msa.c:45-143): every tip character spreads one count evenly over the states of its mask; divided
+  // by sites * tips. Recomputes the eigen system.
+  void set_empirical_freqs(const uint32_t * tip_masks, size_t n_tips, size_t sites);
   std::string describe() const;                   // log text in the spirit of the reference's model print-out
 };
 

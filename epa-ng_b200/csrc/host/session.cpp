@@ -116,6 +116,7 @@ extern "C" int epa_session_open(epa_session ** out, const char * newick, uint32_
         masks[t * sites + k] = m;
       }
     }
+    if (s->model.empirical_freqs) s->model.set_empirical_freqs(masks.data(), T, sites);     // epa_pll_util.cpp:55-57
     const Tree::Schedule sch = s->tree.schedule();
     epa_model_desc md{};
     md.states = (uint32_t) s->model.states;
@@ -451,6 +452,20 @@ extern "C" int epa_host_fasta_to_bfast(const char * fasta_path, const char * out
   {
     const std::string written = write_bfast(read_fasta(fasta_path), fasta_path, out_dir);
     if (out_path && cap) std::snprintf(out_path, cap, "%s", written.c_str());
+    return EPA_OK;
+  }
+  catch (const std::exception & e) { return host_fail(EPA_ERR_ARG, e.what()); }
+}
+
+extern "C" int epa_host_empirical_frequencies(const char * model_desc, const uint32_t * tip_masks, uint32_t n_tips, uint32_t sites,
+                                              double * freqs, double * eigenvals)
+{
+  if (!model_desc || !tip_masks || !freqs) return host_fail(EPA_ERR_ARG, "null argument");
+  try
+  {
+    Model m = Model::parse(model_desc);
+    m.set_empirical_freqs(tip_masks, n_tips, sites);
+    for (int k = 0; k < m.states; ++k) { freqs[k] = m.freqs[(size_t) k]; if (eigenvals) eigenvals[k] = m.eigenvals[(size_t) k]; }
     return EPA_OK;
   }
   catch (const std::exception & e) { return host_fail(EPA_ERR_ARG, e.what()); }

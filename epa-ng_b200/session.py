@@ -15,6 +15,7 @@ HOST_SYMBOLS = [
     ("epa_host_set_rate_scalers", C.c_int, [C.c_int, C.c_int]),
     ("epa_host_read_alignment", C.c_int, [C.c_char_p, _u32p, _u32p, _vp, C.c_size_t, C.c_char_p, C.c_size_t]),
     ("epa_host_fasta_to_bfast", C.c_int, [C.c_char_p, C.c_char_p, C.c_char_p, C.c_size_t]),
+    ("epa_host_empirical_frequencies", C.c_int, [C.c_char_p, _u32p, C.c_uint32, C.c_uint32, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     ("epa_session_ctx", _vp, [_vp]),
     ("epa_session_num_edges", C.c_uint32, [_vp]),
     ("epa_session_num_tips", C.c_uint32, [_vp]),
@@ -151,6 +152,15 @@ def fasta_to_bfast(fasta_path: str, out_dir: str) -> str:
     buf = C.create_string_buffer(4096)
     _check(lib().epa_host_fasta_to_bfast(fasta_path.encode(), out_dir.encode(), buf, len(buf)))
     return buf.value.decode()
+
+
+def empirical_frequencies(model: str, tip_masks):
+    """(freqs, eigenvals) of a +F / +FC model on the given tip state masks [n_tips][sites]."""
+    m = np.ascontiguousarray(tip_masks, dtype=np.uint32)
+    f, ev = np.zeros(20), np.zeros(20)
+    _check(lib().epa_host_empirical_frequencies(model.encode(), m.ctypes.data_as(_u32p), m.shape[0], m.shape[1],
+                                                f.ctypes.data_as(C.POINTER(C.c_double)), ev.ctypes.data_as(C.POINTER(C.c_double))))
+    return f, ev
 
 
 def map_rooted(newick: str, edges, distal):

@@ -89,6 +89,11 @@ int epa_host_read_alignment(const char * path, uint32_t * n_sequences, uint32_t 
 /* -c/--bfast of the reference (Binary_Fasta::fasta_to_bfast, src/io/Binary_Fasta.hpp:214-246, src/main.cpp:284-288):
  * converts an aligned DNA FASTA file to <out_dir>/<file name>.bfast; out_path (may be NULL) receives the path. */
 int epa_host_fasta_to_bfast(const char * fasta_path, const char * out_dir, char * out_path, size_t cap);
+/* +F / +FC models: base frequencies counted on the reference MSA's tip state masks [n_tips][sites]
+ * (compute_and_set_empirical_frequencies, src/core/pll/optimize.cpp:457-472); freqs / eigenvals (optional) hold `states` doubles.
+ * epa_session_open does this itself; the entry point exists for callers that build their own epa_model_desc. */
+int epa_host_empirical_frequencies(const char * model, const uint32_t * tip_masks, uint32_t n_tips, uint32_t sites,
+                                   double * freqs, double * eigenvals);
 /* Rooted input only: translates (edge, distal length) pairs of the unrooted working tree to the
  * rooted tree, in place; writes the numbered newick of the working tree when out_newick != NULL. */
 int epa_host_map_rooted(const char * newick, uint32_t * edges, double * distal, uint32_t count,

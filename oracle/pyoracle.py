@@ -177,6 +177,7 @@ class Model:
     per_rate_scalers: bool = False
     bugcompat_focus: bool = False
     pinv: float = 0.0                # +IU{p} (src/core/raxml/Model.cpp:355-380)
+    empirical_freqs: bool = False    # +F / +FC: frequencies counted on the reference MSA (filled by Reference)
     invariant: np.ndarray = None     # int32[n], filled by Reference from the tip masks when pinv > 0
     _c: OrcModel = field(default=None, repr=False)
 
@@ -231,8 +232,9 @@ def gamma_rates(alpha: float, ncat: int, median: bool = False) -> np.ndarray:
 def parse_model(desc: str) -> Model:
     """Subset of the raxml-ng model grammar of src/core/raxml/Model.cpp:123-560:
     DNA: JC, K80, F81, HKY, GTR with optional {rates}; +FU{..}/+FE/+FO/+F; +G[n][a|m][{alpha}];
-    +IU{p} (and +I / +IO, which stay at the reference's unoptimised default of 0).
-    (+IC, +R and ASC are outside the oracle's scope.)"""
+    +F / +FC (empirical, counted on the reference MSA by Reference); +IU{p} (+I / +IO / +IC stay at 0 as
+    in the reference, which neither optimises nor counts the value).
+    (+R and ASC are outside the oracle's scope.)"""
     pos = len(desc)
     for ch in "+{[":
         p = desc.find(ch)
@@ -266,7 +268,7 @@ def parse_model(desc: str) -> Model:
         else:
             subst = np.array([0.5] * 5 + [1.0])
         freqs = np.full(S, 1.0 / S)
-    alpha, ncat, median, gamma, pinv = 1.0, 1, False, False, 0.0
+    alpha, ncat, median, gamma, pinv, empirical = 1.0, 1, False, False, 0.0, False
     vals, i = _read_braces(opts, 0)
     if vals is not None:
         if sym is None:
@@ -291,8 +293,10 @@ def parse_model(desc: str) -> Model:
                 freqs = f / f.sum()
             elif mode in ('E', 'O'):
                 freqs = np.full(S, 1.0 / S)
+            elif mode == 'C':
+                empirical = True             # counted by Reference once the tips are known
             else:
-                raise ValueError("oracle: empirical frequencies (+F/+FC) not supported")
+                raise ValueError("Invalid frequencies specification")
         elif ch == 'I':
             mode = opts[i].upper() if i < len(opts) and opts[i] != '+' else 'O'
             if i < len(opts) and opts[i] != '+':
@@ -304,8 +308,10 @@ def parse_model(desc: str) -> Model:
                 pinv = vals[0]
                 if not (0.0 <= pinv < 1.0):
                     raise ValueError("Invalid proportion of invariant sites")
+            elif mode == 'C':
+                pinv = 0.0        # the reference never computes the empirical value: it stays 0 ("P-inv (empirical): 0")
             elif mode != 'O':
-                raise ValueError("oracle: empirical p-inv (+IC) not supported")
+                raise ValueError("Invalid p-inv specification")
         elif ch == 'G':
             gamma = True
             num = ""
@@ -324,7 +330,7 @@ def parse_model(desc: str) -> Model:
             raise ValueError(f"oracle: unsupported model option +{ch}")
     rates = gamma_rates(alpha, ncat, median) if gamma and ncat > 1 else np.ones(ncat)
     weights = np.full(ncat, 1.0 / ncat)
-    return Model(S, subst, freqs, alpha, ncat, rates, weights, pinv=pinv).finalize()
+    return Model(S, subst, freqs, alpha, ncat, rates, weights, pinv=pinv, empirical_freqs=empirical).finalize()
 
 
 # --------------------------------------------------------------------------------------------
@@ -598,6 +604,18 @@ class Reference:
                 raise ValueError("invalid character in reference MSA")
             self.sides[t.uid] = SideData(tip=np.ascontiguousarray(m))
         self._pm_cache = {}
+        if model.empirical_freqs:
+            # compute_and_set_empirical_frequencies (src/core/pll/optimize.cpp:457-472) ->
+            # pllmod_msa_empirical_frequencies (PM/msa/pll_msa.c:45-143): every tip character spreads one
+            # count evenly over the states of its mask; divided by sites * tips
+            f = np.zeros(S)
+            for t in tree.tips:
+                m = self.sides[t.uid].tip
+                pop = np.array([bin(int(x)).count("1") for x in m], dtype=float)
+                for k in range(S):
+                    f[k] += (((m >> k) & 1) / pop).sum()
+            model.freqs = f / (self.n * len(tree.tips))
+            model.finalize()
         if model.pinv > 0:
             # pll_update_invariant_sites_proportion -> pll_update_invariant_sites, called by
             # raxml::assign after the tips are linked (src/core/pll/epa_pll_util.cpp:59)

@@ -117,3 +117,16 @@ def test_bfast_query_file_gives_the_same_jplace(built, tmp_path):
         outs[kind], _ = _read_jplace(os.path.join(out, "epa_result.jplace"))
     assert outs["fasta"] == outs["bfast"]
     _check(outs["bfast"], helpers.golden("cfg1")["gtrg_default"]["placements"], "bfast")
+
+
+def test_run_files_empirical_frequencies(built, tmp_path):
+    """+FC model string through the host layer: frequencies counted on the reference MSA, placements vs the
+    reference's recorded ones (tests/golden/make_golden_freqs.py)."""
+    d = os.path.join(helpers.GOLDEN, "cfg1")
+    g = json.load(open(os.path.join(d, "reference_empirical.json")))
+    for key in ("cfg1_fc_default", "cfg1_f_ic_default"):
+        out = str(tmp_path / key)
+        built.session.run_files(os.path.join(d, "ref.tre"), os.path.join(d, "aln.fasta"), os.path.join(d, "query.fasta"),
+                                g[key]["model"], out)
+        got, _ = _read_jplace(os.path.join(out, "epa_result.jplace"))
+        _check(got, g[key]["placements"], key)

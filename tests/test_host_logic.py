@@ -1,6 +1,7 @@
 """CPU: the C++ host layer (tree numbering, pruning schedule, model parsing) against the oracle and
 the reference's recorded strings. No device is touched."""
 import ctypes as C
+import json
 import os
 
 import numpy as np
@@ -76,11 +77,11 @@ def test_protein_model_matches_oracle(sess, model):
 
 
 def test_model_errors(sess, built):
-    for bad in ["GTR+IC", "GTR+IU{1.5}", "GTR+IU", "LG{1/2}+G", "GTR{1/2/3}", "GTR+FU{0.5/0.5}", "GTR+R4", "FOO"]:
+    for bad in ["GTR+IX", "GTR+IU{1.5}", "GTR+IU", "LG{1/2}+G", "GTR{1/2/3}", "GTR+FU{0.5/0.5}", "GTR+FQ", "GTR+R4", "FOO"]:
         with pytest.raises(built.capi.EpaError):
             sess.parse_model(bad)
     # +I in ML mode stays at the reference's unoptimised 0 (src/core/raxml/Model.cpp:192,355-380); +IU{p} is a user value
-    for good in ["GTR+I+G4", "GTR+IO", "GTR+IU{0.2}+G4{0.5}", "LG+IU{0.1}+G4"]:
+    for good in ["GTR+I+G4", "GTR+IO", "GTR+IC", "GTR+IU{0.2}+G4{0.5}", "LG+IU{0.1}+G4", "GTR+F+G4", "LG+FC+G4"]:
         sess.parse_model(good)
 
 
@@ -186,3 +187,20 @@ def test_bfast_converter_is_byte_identical_to_the_reference(built, tmp_path):
     import subprocess
     subprocess.run([exe, "-c", os.path.join(g, "bfast", "codes.fasta"), "-w", str(d)], check=True, stdout=subprocess.DEVNULL)
     assert open(d / "codes.fasta.bfast", "rb").read() == open(os.path.join(g, "bfast", "codes.fasta.bfast"), "rb").read()
+
+
+def test_empirical_frequencies_match_oracle(built):
+    """+F / +FC: the host layer counts the base frequencies on the reference MSA as the reference does
+    (compute_and_set_empirical_frequencies); checked against the oracle, whose +F path is pinned on the
+    reference's placements and printed frequencies (tests/test_oracle_freqs.py)."""
+    for case, model in ((helpers.cfg1_case("GTR{0.5/0.5/0.5/0.5/0.5/1.0}+FC+G4{1.0}"), "GTR{0.5/0.5/0.5/0.5/0.5/1.0}+FC+G4{1.0}"),
+                        (helpers.load_case(*[os.path.join(helpers.GOLDEN, "synthaa", f) for f in ("tree.nwk", "ref.fasta", "query.fasta")],
+                                           "LG+F+G4{0.8}"), "LG+F+G4{0.8}")):
+        S = case.model.states
+        f, ev = built.session.empirical_frequencies(model, case.tip_masks())
+        assert np.allclose(f[:S], case.model.freqs, rtol=1e-13, atol=0)
+        assert np.allclose(np.sort(ev[:S]), np.sort(case.model.eigenvals), rtol=1e-9, atol=1e-12)
+    g = json.load(open(os.path.join(helpers.GOLDEN, "cfg1", "reference_empirical.json")))
+    case = helpers.cfg1_case("GTR+FC+G4")
+    f, _ = built.session.empirical_frequencies("GTR+FC+G4", case.tip_masks())
+    assert np.allclose(f[:4], g["cfg1_printed_freqs"], atol=1e-6)
