@@ -338,11 +338,19 @@ Model Model::parse(const std::string & desc)
         throw std::runtime_error("Invalid p-inv specification: " + desc);
     }
     else
-      throw std::runtime_error(std::string("unsupported model option +") + ch + " (supported: +F{U,E,O}, +G, +IU{p})");
+      throw std::runtime_error(std::string("unsupported model option +") + ch + " (supported: +F{U,E,O,C}, +G, +I{U,O,C})");
   }
   m.rates = (gamma && m.rate_cats > 1) ? discrete_gamma_rates(m.alpha, m.rate_cats, m.gamma_median)
                                        : std::vector<double>((size_t) m.rate_cats, 1.0);
   m.weights.assign((size_t) m.rate_cats, 1.0 / m.rate_cats);
+  {
+    // pll_set_frequencies (LP/models.c:445-470): frequencies that do not sum to 1 within 1e-8 are normalised
+    // (the published protein tables carry six digits: LG sums to 1.000001, WAG to 0.9999999)
+    double sum = 0.0;
+    for (double f : m.freqs) sum += f;
+    if (std::fabs(sum - 1.0) > 1e-8)
+      for (double & f : m.freqs) f /= sum;
+  }
   eigen_decompose(m.states, m.subst, m.freqs, m.eigenvals, m.eigenvecs, m.inv_eigenvecs);
   return m;
 }

@@ -330,6 +330,10 @@ def parse_model(desc: str) -> Model:
             raise ValueError(f"oracle: unsupported model option +{ch}")
     rates = gamma_rates(alpha, ncat, median) if gamma and ncat > 1 else np.ones(ncat)
     weights = np.full(ncat, 1.0 / ncat)
+    # pll_set_frequencies (LP/models.c:445-470): frequencies that do not sum to 1 within 1e-8 are normalised
+    # (the published protein tables carry six digits: LG sums to 1.000001, WAG to 0.9999999)
+    if abs(freqs.sum() - 1.0) > 1e-8:
+        freqs = freqs / freqs.sum()
     return Model(S, subst, freqs, alpha, ncat, rates, weights, pinv=pinv, empirical_freqs=empirical).finalize()
 
 

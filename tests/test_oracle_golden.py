@@ -93,7 +93,8 @@ def test_synthaa_matches_reference():
     bad = []
     for name in want:
         try:
-            helpers.assert_placements_close(got[name], want[name], name)
+            # 1e-9: the table frequencies are normalised as pll_set_frequencies does (LG sums to 1.000001 as published)
+            helpers.assert_placements_close(got[name], want[name], name, logl_rel=1e-9)
         except AssertionError as e:
             bad.append(str(e))
     assert not bad, f"{len(bad)} of {len(want)} queries differ: {bad[:3]}"

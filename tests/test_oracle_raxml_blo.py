@@ -50,7 +50,7 @@ def test_synth64_raxml_blo_matches_reference():
 
 
 def test_synthaa_raxml_blo_matches_reference():
-    _check(helpers.synthaa_case(), gold()["synthaa_default"]["placements"], logl_rel=1e-7)
+    _check(helpers.synthaa_case(), gold()["synthaa_default"]["placements"])
 
 
 @pytest.mark.parametrize("per_rate", [False, True])
