@@ -289,6 +289,7 @@ Model Model::parse(const std::string & desc)
     for (int k = 0; k < 6; ++k) m.subst[k] = vals[sym[k]] / last;
   }
   bool gamma = false;
+  std::vector<double> free_rates, free_weights;
   while (i < opts.size())
   {
     const char ch = (char) std::toupper((unsigned char) opts[i++]);
@@ -320,6 +321,34 @@ Model Model::parse(const std::string & desc)
       vals = braces(opts, i, present);
       if (present) m.alpha = vals.at(0);
     }
+    else if (ch == 'R')
+    {
+      // free rates (src/core/raxml/Model.cpp:405-455): +R[n]{rates}{weights}; weights normalised to sum 1,
+      // rates to mean 1; without values the categories start as GAMMA(alpha = 1) with equal weights
+      gamma = true;
+      std::string num;
+      while (i < opts.size() && std::isdigit((unsigned char) opts[i])) num += opts[i++];
+      if (!num.empty()) m.rate_cats = std::stoi(num); else if (m.rate_cats == 1) m.rate_cats = 4;
+      vals = braces(opts, i, present);
+      if (present)
+      {
+        if ((int) vals.size() != m.rate_cats) throw std::runtime_error("Invalid number of free rates specified: " + desc);
+        free_rates = vals;
+        vals = braces(opts, i, present);
+        if (present)
+        {
+          if ((int) vals.size() != m.rate_cats) throw std::runtime_error("Invalid number of rate weights specified: " + desc);
+          double sum = 0.0;
+          for (double w : vals) sum += w;
+          for (double & w : vals) w /= sum;
+          free_weights = vals;
+        }
+        else free_weights.assign((size_t) m.rate_cats, 1.0 / m.rate_cats);
+        double mean = 0.0;
+        for (size_t k = 0; k < free_rates.size(); ++k) mean += free_rates[k] * free_weights[k];
+        for (double & r : free_rates) r /= mean;
+      }
+    }
     else if (ch == 'I')
     {
       // src/core/raxml/Model.cpp:355-380: +I / +IO = ML mode (stays at the reference's unoptimised start
@@ -338,11 +367,12 @@ Model Model::parse(const std::string & desc)
         throw std::runtime_error("Invalid p-inv specification: " + desc);
     }
     else
-      throw std::runtime_error(std::string("unsupported model option +") + ch + " (supported: +F{U,E,O,C}, +G, +I{U,O,C})");
+      throw std::runtime_error(std::string("unsupported model option +") + ch + " (supported: +F{U,E,O,C}, +G, +R, +I{U,O,C})");
   }
   m.rates = (gamma && m.rate_cats > 1) ? discrete_gamma_rates(m.alpha, m.rate_cats, m.gamma_median)
                                        : std::vector<double>((size_t) m.rate_cats, 1.0);
   m.weights.assign((size_t) m.rate_cats, 1.0 / m.rate_cats);
+  if (!free_rates.empty()) { m.rates = free_rates; m.weights = free_weights; }
   {
     // pll_set_frequencies (LP/models.c:445-470): frequencies that do not sum to 1 within 1e-8 are normalised
     // (the published protein tables carry six digits: LG sums to 1.000001, WAG to 0.9999999)

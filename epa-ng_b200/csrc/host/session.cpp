@@ -134,7 +134,11 @@ extern "C" int epa_session_open(epa_session ** out, const char * newick, uint32_
     md.inv_eigenvecs = s->model.inv_eigenvecs.data();
     md.freqs = s->model.freqs.data();
     md.rates = s->model.rates.data();
-    md.rate_weights = s->model.weights.data();
+    // Reference quirk: the tiny partition aliases the reference partition's category RATES but not its rate
+    // WEIGHTS (src/tree/tiny_util.cpp:110-111): every placement likelihood uses pll_partition_create's default
+    // weights 1/R, whatever +R{rates}{weights} says (the rates are still normalised with the user's weights).
+    const std::vector<double> tiny_weights((size_t) s->model.rate_cats, 1.0 / s->model.rate_cats);
+    md.rate_weights = tiny_weights.data();
     md.pinv = s->model.pinv;
     int rc = epa_ctx_create(&s->ctx, device, &md, (uint32_t) T, masks.data(), sch.n_slots, sch.edges.data(), (uint32_t) sch.edges.size());
     if (rc) return host_fail(rc, epa_last_error(nullptr));

@@ -63,7 +63,9 @@ typedef struct {
   const double * inv_eigenvecs;   /* [states*states] */
   const double * freqs;           /* [states] */
   const double * rates;           /* [rate_cats] */
-  const double * rate_weights;    /* [rate_cats] */
+  const double * rate_weights;    /* [rate_cats]; the weights of the placement likelihoods. (The reference's tiny
+                                     partition keeps the default 1/rate_cats even for +R{..}{weights} models,
+                                     src/tree/tiny_util.cpp:110-111: pass those to reproduce its placements.) */
   double pinv;                    /* proportion of invariant sites in [0, 1) (+IU{p}); the invariant sites are
                                      derived from the tip masks (libpll models.c:495-760) */
 } epa_model_desc;

@@ -234,7 +234,7 @@ def parse_model(desc: str) -> Model:
     DNA: JC, K80, F81, HKY, GTR with optional {rates}; +FU{..}/+FE/+FO/+F; +G[n][a|m][{alpha}];
     +F / +FC (empirical, counted on the reference MSA by Reference); +IU{p} (+I / +IO / +IC stay at 0 as
     in the reference, which neither optimises nor counts the value).
-    (+R and ASC are outside the oracle's scope.)"""
+    +R[n]{rates}{weights} (free rates). (ASC is outside the oracle's scope.)"""
     pos = len(desc)
     for ch in "+{[":
         p = desc.find(ch)
@@ -269,6 +269,7 @@ def parse_model(desc: str) -> Model:
             subst = np.array([0.5] * 5 + [1.0])
         freqs = np.full(S, 1.0 / S)
     alpha, ncat, median, gamma, pinv, empirical = 1.0, 1, False, False, 0.0, False
+    free_rates = free_weights = None
     vals, i = _read_braces(opts, 0)
     if vals is not None:
         if sym is None:
@@ -326,10 +327,34 @@ def parse_model(desc: str) -> Model:
             vals, i = _read_braces(opts, i)
             if vals is not None:
                 alpha = vals[0]
+        elif ch == 'R':
+            # free rates (Model.cpp:405-455): +R[n]{rates}{weights}; weights normalised to sum 1, rates to
+            # mean 1; without values the categories start as GAMMA(alpha = 1) with equal weights
+            gamma = True
+            num = ""
+            while i < len(opts) and opts[i].isdigit():
+                num += opts[i]
+                i += 1
+            ncat = int(num) if num else (4 if ncat == 1 else ncat)
+            vals, i = _read_braces(opts, i)
+            if vals is not None:
+                if len(vals) != ncat:
+                    raise ValueError("Invalid number of free rates specified")
+                free_rates = np.array(vals, dtype=float)
+                vals, i = _read_braces(opts, i)
+                if vals is not None:
+                    if len(vals) != ncat:
+                        raise ValueError("Invalid number of rate weights specified")
+                    free_weights = np.array(vals, dtype=float) / float(np.sum(vals))
+                else:
+                    free_weights = np.full(ncat, 1.0 / ncat)
+                free_rates = free_rates / float((free_rates * free_weights).sum())
         else:
             raise ValueError(f"oracle: unsupported model option +{ch}")
     rates = gamma_rates(alpha, ncat, median) if gamma and ncat > 1 else np.ones(ncat)
     weights = np.full(ncat, 1.0 / ncat)
+    if free_rates is not None:
+        rates, weights = free_rates, free_weights
     # pll_set_frequencies (LP/models.c:445-470): frequencies that do not sum to 1 within 1e-8 are normalised
     # (the published protein tables carry six digits: LG sums to 1.000001, WAG to 0.9999999)
     if abs(freqs.sum() - 1.0) > 1e-8:
@@ -706,9 +731,17 @@ class Placer:
         self.col_tab = lookup_column_table(S)
         self.mask_tab = state_mask_table(S)
         self.lookup = None
+        # Reference quirk: the tiny partition aliases the reference partition's category RATES but not its rate
+        # WEIGHTS (src/tree/tiny_util.cpp:110-111), so every tiny-tree likelihood uses pll_partition_create's
+        # default weights 1/R - visible only with user-defined free-rate weights (+R{..}{..}).
+        m = ref.model
+        self.pmodel = m
+        if not np.allclose(m.weights, 1.0 / m.rate_cats, rtol=0, atol=0):
+            import dataclasses
+            self.pmodel = dataclasses.replace(m, weights=np.full(m.rate_cats, 1.0 / m.rate_cats), _c=None)
 
     def build_lookup(self):
-        ref, mc = self.ref, self.ref.model.c()
+        ref, mc = self.ref, self.pmodel.c()
         B, n, K = len(ref.edges), ref.n, self.K
         self.lookup = np.zeros((B, n, K))
         for b, (d, p, length) in enumerate(ref.edges):
@@ -741,7 +774,7 @@ class Placer:
             raise ValueError("query has no non-gap sites")
         res = OrcBlo()
         fn = lib().orc_place_thorough if self.opts.sliding_blo else lib().orc_place_thorough_raxml
-        fn(C.byref(ref.model.c()), ref.n, C.byref(d.c), C.byref(p.c), length,
+        fn(C.byref(self.pmodel.c()), ref.n, C.byref(d.c), C.byref(p.c), length,
            _up(np.ascontiguousarray(m)), begin, span, C.byref(res))
         pl = Placement(edge, res.logl, 0.0, res.pendant, res.distal)
         pl.rounds, pl.restored = res.rounds, res.restored

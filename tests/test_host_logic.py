@@ -77,11 +77,11 @@ def test_protein_model_matches_oracle(sess, model):
 
 
 def test_model_errors(sess, built):
-    for bad in ["GTR+IX", "GTR+IU{1.5}", "GTR+IU", "LG{1/2}+G", "GTR{1/2/3}", "GTR+FU{0.5/0.5}", "GTR+FQ", "GTR+R4", "FOO"]:
+    for bad in ["GTR+IX", "GTR+IU{1.5}", "GTR+IU", "LG{1/2}+G", "GTR{1/2/3}", "GTR+FU{0.5/0.5}", "GTR+FQ", "GTR+R4{1/2}", "GTR+R4{1/2/3/4}{1/2}", "GTR+ASC_LEWIS", "FOO"]:
         with pytest.raises(built.capi.EpaError):
             sess.parse_model(bad)
     # +I in ML mode stays at the reference's unoptimised 0 (src/core/raxml/Model.cpp:192,355-380); +IU{p} is a user value
-    for good in ["GTR+I+G4", "GTR+IO", "GTR+IC", "GTR+IU{0.2}+G4{0.5}", "LG+IU{0.1}+G4", "GTR+F+G4", "LG+FC+G4"]:
+    for good in ["GTR+I+G4", "GTR+IO", "GTR+IC", "GTR+IU{0.2}+G4{0.5}", "LG+IU{0.1}+G4", "GTR+F+G4", "LG+FC+G4", "GTR+R4", "GTR+R2{0.3/2.0}", "LG+R4{0.1/0.5/1.2/3.0}{0.4/0.3/0.2/0.1}"]:
         sess.parse_model(good)
 
 
