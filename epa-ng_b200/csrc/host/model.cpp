@@ -256,19 +256,30 @@ Model Model::parse(const std::string & desc)
   std::string opts = desc.substr(pos);
   if (name == "DNA") { name = "GTR"; opts = "+G+FO"; }
 
+  // rate symmetries AC AG AT CG CT GT of the named DNA models and their aliases (PM/util/models_dna.c:40-125)
+  static const struct { const char * name; int sym[6]; } kDna[] = {
+    {"JC", {0, 0, 0, 0, 0, 0}}, {"F81", {0, 0, 0, 0, 0, 0}}, {"K80", {0, 1, 0, 0, 1, 0}}, {"HKY", {0, 1, 0, 0, 1, 0}},
+    {"TN93EF", {0, 1, 0, 0, 2, 0}}, {"TN93", {0, 1, 0, 0, 2, 0}}, {"TRNEF", {0, 1, 0, 0, 2, 0}}, {"TRN", {0, 1, 0, 0, 2, 0}},
+    {"K81", {0, 1, 2, 2, 1, 0}}, {"K81UF", {0, 1, 2, 2, 1, 0}}, {"TPM1", {0, 1, 2, 2, 1, 0}}, {"TPM1UF", {0, 1, 2, 2, 1, 0}},
+    {"TPM2", {0, 1, 0, 2, 1, 2}}, {"TPM2UF", {0, 1, 0, 2, 1, 2}}, {"TPM2EF", {0, 1, 0, 2, 1, 2}},
+    {"TPM3", {0, 1, 2, 0, 1, 2}}, {"TPM3UF", {0, 1, 2, 0, 1, 2}}, {"TPM3EF", {0, 1, 2, 0, 1, 2}},
+    {"TIM1", {0, 1, 2, 2, 3, 0}}, {"TIM1UF", {0, 1, 2, 2, 3, 0}}, {"TIM1EF", {0, 1, 2, 2, 3, 0}},
+    {"TIM2", {0, 1, 0, 2, 3, 2}}, {"TIM2UF", {0, 1, 0, 2, 3, 2}}, {"TIM2EF", {0, 1, 0, 2, 3, 2}},
+    {"TIM3", {0, 1, 2, 0, 3, 2}}, {"TIM3UF", {0, 1, 2, 0, 3, 2}}, {"TIM3EF", {0, 1, 2, 0, 3, 2}},
+    {"TVMEF", {0, 1, 2, 3, 1, 4}}, {"TVM", {0, 1, 2, 3, 1, 4}}, {"SYM", {0, 1, 2, 3, 4, 5}}, {"GTR", {0, 1, 2, 3, 4, 5}}};
   std::vector<int> sym;
-  bool dna = true;
-  if (name == "JC" || name == "F81") sym = {0, 0, 0, 0, 0, 0};
-  else if (name == "K80" || name == "HKY") sym = {0, 1, 0, 0, 1, 0};
-  else if (name == "GTR") sym = {0, 1, 2, 3, 4, 5};
-  else dna = false;
+  bool dna = false;
+  for (const auto & d : kDna)
+    if (name == d.name) { sym.assign(d.sym, d.sym + 6); dna = true; break; }
 
   if (dna)
   {
     m.states = 4;
     m.freqs.assign(4, 0.25);
-    if (name == "GTR") m.subst = {0.5, 0.5, 0.5, 0.5, 0.5, 1.0};     // ML-mode defaults, Model.cpp:484-490
-    else m.subst.assign(6, 1.0);
+    // JC / F81 carry the model's equal rates; every other DNA model without {rates} starts from the ML-mode default
+    // 0.5 0.5 0.5 0.5 0.5 1.0 over the SIX rates, whatever its symmetry (src/core/raxml/Model.cpp:484-490)
+    if (name == "JC" || name == "F81") m.subst.assign(6, 1.0);
+    else m.subst = {0.5, 0.5, 0.5, 0.5, 0.5, 1.0};
   }
   else
   {

@@ -1,6 +1,6 @@
 // model.hpp - substitution model of the host layer: the subset of the raxml-ng model grammar that
 // the reference accepts through -m (src/core/raxml/Model.cpp:123-560) and that the device path
-// supports: DNA JC/K80/F81/HKY/GTR and the 28 empirical protein matrices of the reference (protein_models.cpp), with
+// supports: the 22 named DNA models (JC ... GTR) with their aliases and the 28 empirical protein matrices of the reference (protein_models.cpp), with
 // user, equal or empirical frequencies (+FU{..}/+FE/+FO, +F/+FC), discrete GAMMA rate heterogeneity (+G[n][a|m]{alpha}), free rates (+R[n]{rates}{weights}) and a
 // user proportion of invariant sites (+IU{p}). Ascertainment correction is rejected with a clear message.
 #pragma once

@@ -229,9 +229,20 @@ def gamma_rates(alpha: float, ncat: int, median: bool = False) -> np.ndarray:
     return out
 
 
+# rate symmetries AC AG AT CG CT GT of the named DNA models and their aliases (PM/util/models_dna.c:40-125)
+_DNA_SYM = {"JC": [0] * 6, "F81": [0] * 6, "K80": [0, 1, 0, 0, 1, 0], "HKY": [0, 1, 0, 0, 1, 0],
+            "TN93EF": [0, 1, 0, 0, 2, 0], "TN93": [0, 1, 0, 0, 2, 0], "K81": [0, 1, 2, 2, 1, 0], "K81UF": [0, 1, 2, 2, 1, 0],
+            "TPM2": [0, 1, 0, 2, 1, 2], "TPM2UF": [0, 1, 0, 2, 1, 2], "TPM3": [0, 1, 2, 0, 1, 2], "TPM3UF": [0, 1, 2, 0, 1, 2],
+            "TIM1": [0, 1, 2, 2, 3, 0], "TIM1UF": [0, 1, 2, 2, 3, 0], "TIM2": [0, 1, 0, 2, 3, 2], "TIM2UF": [0, 1, 0, 2, 3, 2],
+            "TIM3": [0, 1, 2, 0, 3, 2], "TIM3UF": [0, 1, 2, 0, 3, 2], "TVMEF": [0, 1, 2, 3, 1, 4], "TVM": [0, 1, 2, 3, 1, 4],
+            "SYM": list(range(6)), "GTR": list(range(6))}
+_DNA_ALIASES = {"TRNEF": "TN93EF", "TRN": "TN93", "TPM1": "K81", "TPM1UF": "K81UF", "TPM2EF": "TPM2", "TPM3EF": "TPM3",
+                "TIM1EF": "TIM1", "TIM2EF": "TIM2", "TIM3EF": "TIM3"}
+
+
 def parse_model(desc: str) -> Model:
     """Subset of the raxml-ng model grammar of src/core/raxml/Model.cpp:123-560:
-    DNA: JC, K80, F81, HKY, GTR with optional {rates}; +FU{..}/+FE/+FO/+F; +G[n][a|m][{alpha}];
+    DNA: the 22 named models of PM/util/models_dna.c (JC ... GTR) and their aliases, with optional {rates}; +FU{..}/+FE/+FO/+F; +G[n][a|m][{alpha}];
     +F / +FC (empirical, counted on the reference MSA by Reference); +IU{p} (+I / +IO / +IC stay at 0 as
     in the reference, which neither optimises nor counts the value).
     +R[n]{rates}{weights} (free rates). (ASC is outside the oracle's scope.)"""
@@ -242,10 +253,11 @@ def parse_model(desc: str) -> Model:
             pos = min(pos, p)
     name, opts = desc[:pos].upper(), desc[pos:]
     prot = protein_tables()
-    if name not in ("GTR", "JC", "K80", "F81", "HKY", "DNA") and name not in prot:
+    name = _DNA_ALIASES.get(name, name)
+    if name not in _DNA_SYM and name != "DNA" and name not in prot:
         raise ValueError(f"oracle: unsupported model name {name}")
     if name == "DNA":
-        name, opts = "GTR", "+G+F"
+        name, opts = "GTR", "+G+FO"
     if name in prot:
         # empirical protein matrix: exchangeabilities and frequencies of the model
         # (libs/pll-modules/libs/libpll/src/maps.c:288-, :1472-; data in oracle/protein_models.json)
@@ -255,18 +267,11 @@ def parse_model(desc: str) -> Model:
         freqs = np.array(prot[name]["freqs"], dtype=float)
     else:
         S = 4
-        sym = {"JC": [0] * 6, "F81": [0] * 6, "K80": [0, 1, 0, 0, 1, 0], "HKY": [0, 1, 0, 0, 1, 0],
-               "GTR": list(range(6))}[name]
+        sym = _DNA_SYM[name]
         nuniq = max(sym) + 1
-        # defaults for ML-mode parameters: 0.5 .. 0.5 1.0 (Model.cpp:484-490); JC/F81 all-equal
-        if name in ("JC", "F81"):
-            subst = np.ones(6)
-        elif name in ("K80", "HKY"):
-            # unique rates default 0.5,... ,1.0 over the symmetry classes; last class is the normaliser
-            uniq = [1.0, 1.0]
-            subst = np.array([uniq[c] for c in sym], dtype=float)
-        else:
-            subst = np.array([0.5] * 5 + [1.0])
+        # JC / F81 carry the model's equal rates; every other DNA model without {rates} starts from the ML-mode
+        # default 0.5, 0.5, 0.5, 0.5, 0.5, 1.0 over the SIX rates, whatever its symmetry (Model.cpp:484-490)
+        subst = np.ones(6) if name in ("JC", "F81") else np.array([0.5] * 5 + [1.0])
         freqs = np.full(S, 1.0 / S)
     alpha, ncat, median, gamma, pinv, empirical = 1.0, 1, False, False, 0.0, False
     free_rates = free_weights = None
