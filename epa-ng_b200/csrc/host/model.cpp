@@ -3,6 +3,8 @@
 #include <algorithm>
 #include <cctype>
 #include <cmath>
+#include <fstream>
+#include <iterator>
 #include <cstdio>
 #include <sstream>
 #include <stdexcept>
@@ -281,6 +283,14 @@ Model Model::parse(const std::string & desc)
     if (name == "JC" || name == "F81") m.subst.assign(6, 1.0);
     else m.subst = {0.5, 0.5, 0.5, 0.5, 0.5, 1.0};
   }
+  else if (name == "PROTGTR")
+  {
+    // protein GTR: 190 user exchangeabilities in the order of the upper triangle (PM/util/models_aa.c:69); ML-mode defaults otherwise
+    m.states = 20;
+    m.subst.assign(190, 0.5);
+    m.subst.back() = 1.0;
+    m.freqs.assign(20, 1.0 / 20);
+  }
   else
   {
     m.states = 20;
@@ -293,11 +303,19 @@ Model Model::parse(const std::string & desc)
   std::vector<double> vals = braces(opts, i, present);
   if (present)
   {
-    if (!dna) throw std::runtime_error("user-defined protein exchangeabilities are not supported");
-    const int nuniq = *std::max_element(sym.begin(), sym.end()) + 1;
-    if ((int) vals.size() != nuniq) throw std::runtime_error("model: wrong number of substitution rates");
-    const double last = vals[sym.back()];
-    for (int k = 0; k < 6; ++k) m.subst[k] = vals[sym[k]] / last;
+    if (!dna && name != "PROTGTR") throw std::runtime_error("user-defined rates need PROTGTR for protein data");
+    if (!dna)
+    {
+      if (vals.size() != 190) throw std::runtime_error("model: wrong number of substitution rates");
+      for (size_t k = 0; k < 190; ++k) m.subst[k] = vals[k] / vals.back();
+    }
+    else
+    {
+      const int nuniq = *std::max_element(sym.begin(), sym.end()) + 1;
+      if ((int) vals.size() != nuniq) throw std::runtime_error("model: wrong number of substitution rates");
+      const double last = vals[sym.back()];
+      for (int k = 0; k < 6; ++k) m.subst[k] = vals[sym[k]] / last;
+    }
   }
   bool gamma = false;
   std::vector<double> free_rates, free_weights;
@@ -409,6 +427,90 @@ void Model::set_empirical_freqs(const uint32_t * tip_masks, size_t n_tips, size_
   for (double & v : f) v /= (double) (n_tips * sites);
   freqs = f;
   eigen_decompose(states, subst, freqs, eigenvals, eigenvecs, inv_eigenvecs);
+}
+
+// ---- model files (-m <file>, src/main.cpp:433-436 -> src/util/parse_model.hpp) ------------------------------
+namespace {
+
+// text after `key` (searched from pos) up to the end of its line; pos moves to that line end
+std::string field_after(const std::string & text, const std::string & key, size_t & pos)
+{
+  const size_t at = text.find(key, pos);
+  if (at == std::string::npos) throw std::invalid_argument("Couldn't parse model file! (can't find '" + key + "'!)");
+  const size_t from = at + key.size(), eol = text.find('\n', from);
+  if (eol == std::string::npos) throw std::runtime_error("couldnt find terminating newline?!");
+  pos = eol;
+  return text.substr(from, eol - from);
+}
+
+bool later_has(const std::string & text, const std::string & key, size_t pos) { return text.find(key, pos) != std::string::npos; }
+
+// "{r01/r02/.../r(S-2)(S-1)}+FU{f0/.../f(S-1)}" collected pair by pair in file order
+std::string rates_and_freqs(const std::string & text, size_t & pos, const std::string & states, const std::string & rate_prefix,
+                            const std::string & rate_infix, const std::string & rate_suffix, const std::string & freq_prefix,
+                            const std::string & freq_suffix)
+{
+  std::string out = "{";
+  for (size_t i = 0; i + 1 < states.size(); ++i)
+    for (size_t k = i + 1; k < states.size(); ++k)
+    {
+      if (k > 1) out += "/";
+      out += field_after(text, rate_prefix + states[i] + rate_infix + states[k] + rate_suffix, pos);
+    }
+  out += "}+FU{";
+  for (size_t i = 0; i < states.size(); ++i)
+  {
+    if (i) out += "/";
+    out += field_after(text, freq_prefix + states[i] + freq_suffix, pos);
+  }
+  return out + "}";
+}
+
+}  // namespace
+
+std::string model_string_from_file(const std::string & path)
+{
+  std::ifstream in(path);
+  if (!in) throw std::runtime_error("Cannot open model file: " + path);
+  const std::string text((std::istreambuf_iterator<char>(in)), std::istreambuf_iterator<char>());
+  const std::string first_line = text.substr(0, text.find('\n'));
+  const char * dna_states = "ACGT", * aa_states = "ARNDCQEGHILKMFPSTWYV";
+  size_t pos = 0;
+  if (first_line.rfind("IQ-TREE ", 0) == 0)
+  {
+    // IQ-TREE report: "Model of substitution: GTR+F+I+G4", "A-C: ..", "pi(A) = ..", "Gamma with 4 categories", ...
+    const std::string iq = field_after(text, "Model of substitution: ", pos);
+    const std::string matrix = iq.substr(0, iq.find('+'));
+    std::string desc = matrix + rates_and_freqs(text, pos, matrix == "GTR" ? dna_states : aa_states, "", "-", ": ", "pi(", ") = ");
+    std::string cats;
+    const bool gamma = later_has(text, "Gamma with ", pos);
+    if (gamma)
+    {
+      const std::string tail = field_after(text, "Gamma with ", pos);
+      const size_t end = tail.find(" categories");
+      if (end == std::string::npos) throw std::invalid_argument("Couldn't parse model file! (can't find ' categories'!)");
+      if (end == 0) throw std::runtime_error("Nothing inbetween ' categories' and 'Gamma with '?");
+      cats = tail.substr(0, end);
+    }
+    if (later_has(text, "Proportion of invariable sites: ", pos)) desc += "+IU{" + field_after(text, "Proportion of invariable sites: ", pos) + "}";
+    if (gamma) desc += "+G" + cats + "{" + field_after(text, "Gamma shape alpha: ", pos) + "}";
+    return desc;
+  }
+  if (text.find("This is RAxML version 8.") != std::string::npos)
+  {
+    // RAxML 8 info file (-f e): DataType, Substitution Matrix, alpha, invar, "rate A <-> C: ..", "freq pi(A): .."
+    const bool dna = field_after(text, "DataType: ", pos) == "DNA";
+    std::string matrix = field_after(text, "Substitution Matrix: ", pos);
+    if (!dna && matrix == "GTR") matrix = "PROTGTR";
+    std::string alpha, pinv;
+    if (later_has(text, "alpha: ", pos)) alpha = "+G4{" + field_after(text, "alpha: ", pos) + "}";
+    if (later_has(text, "invar: ", pos)) pinv = "+IU{" + field_after(text, "invar: ", pos) + "}";
+    return matrix + rates_and_freqs(text, pos, dna ? dna_states : aa_states, "rate ", " <-> ", ": ", "freq pi(", "): ") + pinv + alpha;
+  }
+  // raxml-ng .bestModel: "<model string>, <partition> = <range>"
+  const size_t comma = first_line.find(',');
+  if (comma == std::string::npos) throw std::runtime_error("Model string in provided file seems wrong.");
+  return first_line.substr(0, comma);
 }
 
 std::string Model::describe() const

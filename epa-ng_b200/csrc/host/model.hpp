@@ -32,6 +32,10 @@ struct Model {
   std::string describe() const;                   // log text in the spirit of the reference's model print-out
 };
 
+// -m <file>: model string out of a RAxML 8 info file, a raxml-ng .bestModel file or an IQ-TREE report
+// (src/main.cpp:433-436 -> src/util/parse_model.hpp); throws like the reference when a field is missing
+std::string model_string_from_file(const std::string & path);
+
 // Discrete GAMMA category rates, mean or median (Yang 1994; libpll gamma.c:220-292)
 std::vector<double> discrete_gamma_rates(double alpha, int ncat, bool median);
 

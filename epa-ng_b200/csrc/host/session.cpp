@@ -345,6 +345,18 @@ extern "C" int epa_run_files_ex(const char * tree_file, const char * ref_msa_fil
       ref = apply_mask(ref, mask);
       qry = apply_mask(qry, mask);
     }
+    // -m takes a model string or a RAxML 8 info / raxml-ng bestModel / IQ-TREE report file (src/main.cpp:433-436)
+    std::string model_desc_str = model;
+    {
+      struct stat st;
+      if (stat(model, &st) == 0 && S_ISREG(st.st_mode))
+      {
+        model_desc_str = model_string_from_file(model);
+        info("Selected: Specified model file: " + std::string(model));
+        info("  ==> model " + model_desc_str);
+      }
+    }
+    model = model_desc_str.c_str();
     const Model parsed = Model::parse(model);
     info("Using model parameters:");
     info(parsed.describe());
@@ -470,6 +482,19 @@ extern "C" int epa_host_empirical_frequencies(const char * model_desc, const uin
     Model m = Model::parse(model_desc);
     m.set_empirical_freqs(tip_masks, n_tips, sites);
     for (int k = 0; k < m.states; ++k) { freqs[k] = m.freqs[(size_t) k]; if (eigenvals) eigenvals[k] = m.eigenvals[(size_t) k]; }
+    return EPA_OK;
+  }
+  catch (const std::exception & e) { return host_fail(EPA_ERR_ARG, e.what()); }
+}
+
+extern "C" int epa_host_model_from_file(const char * path, char * out, size_t cap)
+{
+  if (!path || !out || !cap) return host_fail(EPA_ERR_ARG, "null argument");
+  try
+  {
+    const std::string desc = model_string_from_file(path);
+    if (desc.size() + 1 > cap) return host_fail(EPA_ERR_ARG, "model string buffer too small");
+    std::snprintf(out, cap, "%s", desc.c_str());
     return EPA_OK;
   }
   catch (const std::exception & e) { return host_fail(EPA_ERR_ARG, e.what()); }

@@ -16,6 +16,7 @@ HOST_SYMBOLS = [
     ("epa_host_read_alignment", C.c_int, [C.c_char_p, _u32p, _u32p, _vp, C.c_size_t, C.c_char_p, C.c_size_t]),
     ("epa_host_fasta_to_bfast", C.c_int, [C.c_char_p, C.c_char_p, C.c_char_p, C.c_size_t]),
     ("epa_host_empirical_frequencies", C.c_int, [C.c_char_p, _u32p, C.c_uint32, C.c_uint32, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
+    ("epa_host_model_from_file", C.c_int, [C.c_char_p, C.c_char_p, C.c_size_t]),
     ("epa_session_ctx", _vp, [_vp]),
     ("epa_session_num_edges", C.c_uint32, [_vp]),
     ("epa_session_num_tips", C.c_uint32, [_vp]),
@@ -161,6 +162,13 @@ def empirical_frequencies(model: str, tip_masks):
     _check(lib().epa_host_empirical_frequencies(model.encode(), m.ctypes.data_as(_u32p), m.shape[0], m.shape[1],
                                                 f.ctypes.data_as(C.POINTER(C.c_double)), ev.ctypes.data_as(C.POINTER(C.c_double))))
     return f, ev
+
+
+def model_from_file(path: str) -> str:
+    """Model string of a RAxML 8 info file, raxml-ng .bestModel file or IQ-TREE report (the reference's -m <file>)."""
+    buf = C.create_string_buffer(16384)
+    _check(lib().epa_host_model_from_file(path.encode(), buf, len(buf)))
+    return buf.value.decode()
 
 
 def map_rooted(newick: str, edges, distal):

@@ -94,6 +94,10 @@ int epa_host_fasta_to_bfast(const char * fasta_path, const char * out_dir, char 
  * epa_session_open does this itself; the entry point exists for callers that build their own epa_model_desc. */
 int epa_host_empirical_frequencies(const char * model, const uint32_t * tip_masks, uint32_t n_tips, uint32_t sites,
                                    double * freqs, double * eigenvals);
+/* -m <file> of the reference (src/main.cpp:433-436 -> src/util/parse_model.hpp): the model string of a RAxML 8 info
+ * file, a raxml-ng .bestModel file or an IQ-TREE report. epa_run_files does this itself when its model argument
+ * names an existing file. */
+int epa_host_model_from_file(const char * path, char * out, size_t cap);
 /* Rooted input only: translates (edge, distal length) pairs of the unrooted working tree to the
  * rooted tree, in place; writes the numbered newick of the working tree when out_newick != NULL. */
 int epa_host_map_rooted(const char * newick, uint32_t * edges, double * distal, uint32_t count,

@@ -254,11 +254,17 @@ def parse_model(desc: str) -> Model:
     name, opts = desc[:pos].upper(), desc[pos:]
     prot = protein_tables()
     name = _DNA_ALIASES.get(name, name)
-    if name not in _DNA_SYM and name != "DNA" and name not in prot:
+    if name not in _DNA_SYM and name not in ("DNA", "PROTGTR") and name not in prot:
         raise ValueError(f"oracle: unsupported model name {name}")
     if name == "DNA":
         name, opts = "GTR", "+G+FO"
-    if name in prot:
+    if name == "PROTGTR":
+        # protein GTR (PM/util/models_aa.c:69): 190 user exchangeabilities, ML-mode defaults otherwise
+        S = 20
+        sym, nuniq = None, 190
+        subst = np.array([0.5] * 189 + [1.0])
+        freqs = np.full(S, 1.0 / S)
+    elif name in prot:
         # empirical protein matrix: exchangeabilities and frequencies of the model
         # (libs/pll-modules/libs/libpll/src/maps.c:288-, :1472-; data in oracle/protein_models.json)
         S = 20
@@ -277,13 +283,16 @@ def parse_model(desc: str) -> Model:
     free_rates = free_weights = None
     vals, i = _read_braces(opts, 0)
     if vals is not None:
-        if sym is None:
-            raise ValueError("oracle: user-defined protein rates are not supported")
+        if sym is None and name != "PROTGTR":
+            raise ValueError("user-defined rates need PROTGTR for protein data")
         if len(vals) != nuniq:
             raise ValueError("wrong number of substitution rates")
-        last = vals[sym[-1]]
-        vals = [v / last for v in vals]
-        subst = np.array([vals[c] for c in sym], dtype=float)
+        if sym is None:
+            subst = np.array(vals, dtype=float) / vals[-1]
+        else:
+            last = vals[sym[-1]]
+            vals = [v / last for v in vals]
+            subst = np.array([vals[c] for c in sym], dtype=float)
     while i < len(opts):
         ch = opts[i].upper()
         i += 1

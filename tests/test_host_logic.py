@@ -204,3 +204,26 @@ def test_empirical_frequencies_match_oracle(built):
     case = helpers.cfg1_case("GTR+FC+G4")
     f, _ = built.session.empirical_frequencies("GTR+FC+G4", case.tip_masks())
     assert np.allclose(f[:4], g["cfg1_printed_freqs"], atol=1e-6)
+
+
+def test_model_files_give_the_reference_strings(built):
+    """-m <file>: the reference's own golden strings (test/src/parse_model.cpp:7-70) on its own data files
+    (test/data/modelfiles, copied as fixtures; the IQ-TREE report cut after its model section)."""
+    d = os.path.join(helpers.GOLDEN, "modelfiles")
+    want = {
+        "rax8_dna": "GTR{0.787874/1.821672/1.294006/0.698421/3.034135/1.000000}+FU{0.256465/0.222535/0.308594/0.212406}+G4{0.478218}",
+        "rax8_invar": "GTR{1.217620/2.720208/1.342850/1.115245/3.313319/1.000000}+FU{0.222438/0.209333/0.259930/0.308299}"
+                      "+IU{0.051355}+G4{0.532224}",
+        "raxng_dna": "GTR{5.56435/19.04/4.65971/2.04432/69.6551/1}+FC+G4m{0.193259}",
+        "iqtree_dna_invar": "GTR{0.9467/3.2100/1.8644/0.8054/5.5442/1.0000}+FU{0.2415/0.2465/0.3237/0.1884}+IU{0.1257}+G4{0.8042}",
+    }
+    for f, s in want.items():
+        assert built.session.model_from_file(os.path.join(d, f)) == s
+        built.session.parse_model(s)                      # and the strings are models the host layer accepts
+    prot = built.session.model_from_file(os.path.join(d, "rax8_prot"))
+    assert prot.startswith("PROTGTR{1.003440/0.000100/2.196009/") and prot.endswith("}+G4{0.563473}")
+    assert prot.count("/") == 189 + 19 and "+FU{0.065149/0.054231/" in prot
+    m = built.session.parse_model(prot)
+    assert m["states"] == 20 and abs(m["freqs"].sum() - 1.0) < 1e-12
+    with pytest.raises(built.capi.EpaError, match="seems wrong"):
+        built.session.model_from_file(os.path.join(helpers.GOLDEN, "cfg1", "query.fasta"))
