@@ -227,3 +227,24 @@ def test_model_files_give_the_reference_strings(built):
     assert m["states"] == 20 and abs(m["freqs"].sum() - 1.0) < 1e-12
     with pytest.raises(built.capi.EpaError, match="seems wrong"):
         built.session.model_from_file(os.path.join(helpers.GOLDEN, "cfg1", "query.fasta"))
+
+
+def test_jplace_writer_reproduces_the_reference_file(built, tmp_path):
+    """The jplace text (src/io/jplace_util.cpp:20-86: field order edge, logl, lwr, DISTAL, PENDANT; layout; metadata)
+    for the reference's own numbers: a jplace written by the unmodified reference (cfg1, --no-heur --filter-max 3
+    --filter-min-lwr 0) is parsed, its placements go through the host layer's writer, and the bytes must be equal."""
+    import json
+    src = os.path.join(helpers.GOLDEN, "cfg1", "reference_result.jplace")
+    text = open(src).read()
+    doc = json.loads(text)
+    names = [pq["n"][0] for pq in doc["placements"]]
+    fmax = max(len(pq["p"]) for pq in doc["placements"])
+    recs = np.zeros((len(names), fmax), dtype=built.capi.PLACEMENT_DTYPE)
+    counts = np.zeros(len(names), dtype=np.uint32)
+    for i, pq in enumerate(doc["placements"]):
+        counts[i] = len(pq["p"])
+        for k, (edge, logl, lwr, distal, pendant) in enumerate(pq["p"]):
+            recs[i, k] = (edge, logl, lwr, pendant, distal)
+    out = str(tmp_path / "out.jplace")
+    built.session.write_jplace(out, doc["tree"], doc["metadata"]["invocation"], names, recs, counts, precision=10)
+    assert open(out).read() == text
