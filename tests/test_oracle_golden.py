@@ -114,3 +114,20 @@ def test_synth64_other_heuristics_match_reference(rname, kw):
         except AssertionError as e:
             bad.append(str(e))
     assert not bad, f"{rname}: {len(bad)} of {len(gold)} queries differ: {bad[:3]}"
+
+
+def test_synth64_no_pre_mask_matches_reference():
+    """--no-pre-mask (no column masking, every query scored over the whole alignment with its gaps as fully
+    ambiguous sites): first 40 synth64 queries against the reference's recorded run (reference_nopremask.json,
+    written with oracle.run_reference(..., extra=("--no-pre-mask",)))."""
+    import json
+    o = helpers.oracle()
+    d = os.path.join(helpers.GOLDEN, "synth64")
+    g = json.load(open(os.path.join(d, "reference_nopremask.json")))
+    case = helpers.load_case(os.path.join(d, "tree.nwk"), os.path.join(d, "ref.fasta"), os.path.join(d, "query.fasta"),
+                             g["model"], premasking=False)
+    seqs = dict(zip(case.qnames, case.qseqs))
+    assert case.n == 300
+    for name, want in g["placements"].items():
+        got = [(p.edge, p.logl, p.lwr, p.distal, p.pendant) for p in case.placer.place(seqs[name])]
+        helpers.assert_placements_close(got, want, name, logl_rel=1e-9, len_abs=1e-5)
