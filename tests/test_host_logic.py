@@ -248,3 +248,21 @@ def test_jplace_writer_reproduces_the_reference_file(built, tmp_path):
     out = str(tmp_path / "out.jplace")
     built.session.write_jplace(out, doc["tree"], doc["metadata"]["invocation"], names, recs, counts, precision=10)
     assert open(out).read() == text
+
+
+def test_cli_takes_a_model_file_and_fails_loudly_without_a_gpu(tmp_path):
+    """The CLI resolves -m <file> (src/main.cpp:433-436) before anything touches the device; without a CUDA device the
+    run ends with an error message and a non-zero exit code - there is no CPU path to fall back to."""
+    import subprocess
+    exe = os.path.join(helpers.ROOT, "epa-ng_b200", "epa-ng-b200")
+    d = os.path.join(helpers.GOLDEN, "cfg1")
+    r = subprocess.run([exe, "-t", os.path.join(d, "ref.tre"), "-s", os.path.join(d, "aln.fasta"), "-q", os.path.join(d, "query.fasta"),
+                        "-m", os.path.join(helpers.GOLDEN, "modelfiles", "rax8_dna"), "-w", str(tmp_path), "--redo"],
+                       capture_output=True, text=True)
+    out = r.stdout + r.stderr
+    assert "==> model GTR{0.787874/1.821672/1.294006/0.698421/3.034135/1.000000}+FU{0.256465/0.222535/0.308594/0.212406}+G4{0.478218}" in out
+    if "no CUDA device" in out:
+        assert r.returncode != 0 and "no CPU path" in out
+        assert not os.path.exists(os.path.join(str(tmp_path), "epa_result.jplace")) or os.path.getsize(os.path.join(str(tmp_path), "epa_result.jplace")) == 0
+    else:
+        assert r.returncode == 0
