@@ -113,6 +113,7 @@ struct epa_ctx {
     bool old_aa = false;       // EPA_B200_OLD_AA: (site, rate)-per-thread amino-acid passes
     int gs_below = 6;          // EPA_B200_BLO_GS_BELOW: resident warps below which the global-scratch variant runs
     int gs_warps = 8;          // EPA_B200_GS_WARPS: warps per CTA of the global-scratch variant
+    int site_warps = 0;        // EPA_B200_SITE_WARPS: cap on the warps per CTA of the lane = site kernel (0 = none)
   } sw;
   int * d_flags = nullptr;              // [0..1] error, [2] max tile width, [3] max span
   unsigned long long * d_counter = nullptr;
@@ -348,6 +349,7 @@ extern "C" int epa_ctx_create(epa_ctx ** out, int device, const epa_model_desc *
   ctx->sw.old_aa = getenv("EPA_B200_OLD_AA") != nullptr;
   if (const char * v = getenv("EPA_B200_BLO_GS_BELOW")) ctx->sw.gs_below = atoi(v);
   if (const char * v = getenv("EPA_B200_GS_WARPS")) ctx->sw.gs_warps = std::max(1, std::min(12, atoi(v)));
+  if (const char * v = getenv("EPA_B200_SITE_WARPS")) ctx->sw.site_warps = atoi(v);
   DevModel & m = ctx->hm;
   memset(&m, 0, sizeof m);
   const int S = (int) model->states, R = (int) model->rate_cats;
@@ -1217,12 +1219,14 @@ int ensure_clvT(epa_ctx * ctx)
 template <int R, bool GS, bool PR, bool INV>
 int launch_site_kernel(epa_ctx * ctx, const BloSiteArgs & sa, unsigned grid, int warps, size_t smem)
 {
+#ifndef EPA_DEV_MIN
   if (sa.b.raxml)
   {
     CU(cudaFuncSetAttribute(blo_site_kernel<R, GS, PR, INV, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
     blo_site_kernel<R, GS, PR, INV, true><<<grid, warps * 32, smem, ctx->stream>>>(sa);
     return EPA_OK;
   }
+#endif
   CU(cudaFuncSetAttribute(blo_site_kernel<R, GS, PR, INV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
   blo_site_kernel<R, GS, PR, INV><<<grid, warps * 32, smem, ctx->stream>>>(sa);
   return EPA_OK;
@@ -1231,10 +1235,14 @@ int launch_site_kernel(epa_ctx * ctx, const BloSiteArgs & sa, unsigned grid, int
 template <int R, bool GS>
 int launch_site_variant(epa_ctx * ctx, const BloSiteArgs & sa, unsigned grid, int warps, size_t smem, bool pr, bool inv)
 {
+#ifdef EPA_DEV_MIN            /* developer builds: the default variant only (compiles in seconds) */
+  return launch_site_kernel<R, GS, false, false>(ctx, sa, grid, warps, smem);
+#else
   if (pr) return inv ? launch_site_kernel<R, GS, true, true>(ctx, sa, grid, warps, smem)
                      : launch_site_kernel<R, GS, true, false>(ctx, sa, grid, warps, smem);
   return inv ? launch_site_kernel<R, GS, false, true>(ctx, sa, grid, warps, smem)
              : launch_site_kernel<R, GS, false, false>(ctx, sa, grid, warps, smem);
+#endif
 }
 
 // R = 1, 2, 4: lane = site kernel (kernels_blo_site.cuh)
@@ -1254,14 +1262,16 @@ int launch_blo_site(epa_ctx * ctx, BloArgs & a)
   // up to 12 warps per CTA (register file): the first 8 keep their sumtable in tensor memory when
   // the windows fit 8 rows of 32 sites, the others in shared memory
   const size_t fix = (size_t) SiteWarpSmem<R>::SUM * sizeof(double);
-  const size_t rows = (size_t) wmax * blo_row(R) * sizeof(double);
+  const size_t rows = (size_t) ((wmax + 31) & ~31) * site_row_pad(R) * sizeof(double);
   const size_t budget = ctx->smem_optin - 2048;
   const int max_warps = SITE_MAX_WARPS;
   const bool tm_ok = !ctx->sw.no_tmem;
-  const int n_tm = !tm_ok ? 0 : (wmax <= SITE_TMEM_ROWS * 32 ? SITE_TMEM_WARPS : (wmax <= SITE_TMEM_ROWS * 64 ? SITE_TMEM_WARPS / 2 : 0));
+  int n_tm = !tm_ok ? 0 : (wmax <= SITE_TMEM_ROWS * 32 ? SITE_TMEM_WARPS : (wmax <= SITE_TMEM_ROWS * 64 ? SITE_TMEM_WARPS / 2 : 0));
+  if (ctx->sw.site_warps > 0) n_tm = std::min(n_tm, ctx->sw.site_warps);
   sa.tmem_cols = wmax <= SITE_TMEM_ROWS * 32 ? 256 : 512;
   int n_sm = 0;
   while (n_sm < (n_tm ? max_warps - n_tm : 9) && (size_t) (n_tm + n_sm + 1) * fix + (size_t) (n_sm + 1) * rows <= budget) ++n_sm;
+  if (ctx->sw.site_warps > 0) n_sm = std::max(0, std::min(n_sm, ctx->sw.site_warps - n_tm));
   int warps = n_tm + n_sm;
   // few resident warps (long windows) lose to the global-scratch variant with 8 warps per SM (measured on
   // 450..1000-site windows, tools/bench_window.py)
@@ -1368,10 +1378,12 @@ extern "C" int epa_place_pairs(epa_ctx * ctx, const epa_options * opts)
     {
       switch (ctx->R)
       {
+#ifndef EPA_DEV_MIN
         case 1: rc = launch_blo_site<1>(ctx, a); break;
         case 2: rc = launch_blo_site<2>(ctx, a); break;
-        case 4: rc = launch_blo_site<4>(ctx, a); break;
         case 8: rc = launch_blo_dna<8>(ctx, a); break;
+#endif
+        case 4: rc = launch_blo_site<4>(ctx, a); break;
         default: return fail(ctx, EPA_ERR_ARG, "unsupported rate category count %d", ctx->R);
       }
     }

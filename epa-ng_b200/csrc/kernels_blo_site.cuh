@@ -85,11 +85,34 @@ constexpr int SITE_TMEM_WARPS = 8;
 constexpr int SITE_TMEM_ROWS = 8;        // rows (trips of 32 sites) of a TMEM-backed warp when 8 warps share the 512 columns:
                                          // windows <= 256; windows <= 512 give 16 rows to 4 warps
 struct SumRef {
-  double * base;
+  double * base;        // global planes (GS)
   int gstride;
-  uint32_t taddr;
+  uint32_t taddr;       // tensor-memory address of the warp's first row
   int tm;
+  uint32_t saddr;       // shared-memory address of this LANE's row of trip 0
 };
+
+// Shared-memory sumtable rows: 1 + 3R doubles padded to an even count whose half is odd, so that the
+// lane = site accesses are 128-bit and conflict-free (a quarter-warp's eight rows start in eight
+// different 16-byte bank groups). Every storage kind keeps a row for all 32 lanes of every trip: a
+// lane beyond the window stores (1, 0, ..., 0), whose derivative terms are exact zeros, so the
+// Newton sweeps need no validity predicates.
+__host__ __device__ constexpr int site_row_pad(int R)
+{
+  int p = (1 + 3 * R + 1) & ~1;
+  if (((p / 2) & 1) == 0) p += 2;
+  return p;
+}
+__host__ __device__ constexpr uint32_t site_trip_bytes(int R) { return 32u * (uint32_t) site_row_pad(R) * 8u; }
+
+__device__ __forceinline__ void lds2(uint32_t addr, double & a, double & b)
+{
+  asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(a), "=d"(b) : "r"(addr));
+}
+__device__ __forceinline__ void sts2(uint32_t addr, double a, double b)
+{
+  asm volatile("st.shared.v2.f64 [%0], {%1, %2};" :: "r"(addr), "d"(a), "d"(b) : "memory");
+}
 
 __device__ __forceinline__ void tc_st32(uint32_t taddr, const uint32_t (&v)[32])
 {
@@ -409,16 +432,15 @@ lookup_build_site_kernel(const DevModel * __restrict__ m, const double * __restr
   }
 }
 
-// 1/x for positive normal x (a site likelihood): hardware seed + two Newton steps, no slow-path
-// branch, so that the compiler can interleave the reciprocals of several sites. Within 1 ulp.
+// 1/x for positive normal x (a site likelihood): hardware seed (relative error e <= 2^-23) times
+// 1 + e + e^2, no slow-path branch, so that the compiler can interleave the reciprocals of several
+// sites. Truncation e^3 < 2^-69: within 2 ulp.
 __device__ __forceinline__ double fast_rcp(double x)
 {
   double r;
   asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
   double e = fma(-x, r, 1.0);
   e = fma(e, e, e);
-  r = fma(r, e, r);
-  e = fma(-x, r, 1.0);
   return fma(r, e, r);
 }
 
@@ -440,7 +462,7 @@ template <int R, bool GS>
 __device__ __forceinline__ void site_derivatives(const SumRef & sr, double * ex, int w, double t,
                                                  int lane, double & f, double & df)
 {
-  constexpr int NK = 3 * R, ROW = blo_row(R);
+  constexpr int NK = 3 * R;
   if (lane < NK)
   {
     const double lk = c_model.eigenvals[1 + lane % 3] * c_model.rates[lane / 3];
@@ -460,53 +482,48 @@ __device__ __forceinline__ void site_derivatives(const SumRef & sr, double * ex,
     for (int k = 0; k < NK; ++k) { d0[k] = ex[k]; d1[k] = ex[NK + k]; d2[k] = ex[2 * NK + k]; }
   }
   // Trips of 32 sites are taken two at a time (sites s and s + 32 of a lane): six independent FMA
-  // chains and two branch-free reciprocals in flight; an odd last trip runs alone. A lane whose
-  // site lies beyond the window re-reads its first row and discards the result.
+  // chains and two branch-free reciprocals in flight; an odd last trip runs alone. Rows of lanes
+  // beyond the window hold (1, 0, ..., 0) and add exact zeros.
   double a1 = 0.0, a2 = 0.0;
   const int trips = (w + 31) >> 5;
-  const int s0 = lane < w ? lane : 0;
-  const double * sum = sr.base;
-  const int gstride = sr.gstride;
-  auto load_row = [&](int s, double (&x)[NK + 1])
+  auto load_row = [&](int tr, uint32_t ra, double (&x)[NK + 2])
   {
     if constexpr (GS)
     {
+      const double * g = sr.base + tr * 32 + lane;
       #pragma unroll
-      for (int k = 0; k <= NK; ++k) x[k] = sum[(size_t) k * gstride + s];
+      for (int k = 0; k <= NK; ++k) x[k] = g[(size_t) k * sr.gstride];
     }
     else
     {
-      const double * row = sum + s * ROW;
       #pragma unroll
-      for (int k = 0; k <= NK; ++k) x[k] = row[k];
+      for (int k = 0; k < (NK + 2) / 2; ++k) lds2(ra + 16u * k, x[2 * k], x[2 * k + 1]);
     }
   };
-  auto unpack = [](const uint32_t (&v)[32], double (&x)[NK + 1])
+  auto unpack = [](const uint32_t (&v)[32], double (&x)[NK + 2])
   {
     #pragma unroll
     for (int k = 0; k <= NK; ++k) x[k] = __hiloint2double((int) v[2 * k + 1], (int) v[2 * k]);
   };
+  constexpr uint32_t TB = site_trip_bytes(R);
+  uint32_t ra = sr.saddr;
   int tr = 0;
   #pragma unroll 1
-  for (; tr + 2 <= trips; tr += 2)
+  for (; tr + 2 <= trips; tr += 2, ra += 2 * TB)
   {
-    const int sa = lane + 32 * tr, sb = sa + 32;
-    const bool va = sa < w, vb = sb < w;
-    double xa[NK + 1], xb[NK + 1];
+    double xa[NK + 2], xb[NK + 2];
     if (!GS && sr.tm)
     {
-      // every lane reads its own rows tr and tr + 1 (rows of sites beyond the window hold the
-      // harmless values their lane stored there)
-      uint32_t ra[32], rb[32];
-      tc_ld32(sr.taddr + tr * 32, ra);
-      tc_ld32(sr.taddr + tr * 32 + 32, rb);
+      uint32_t va[32], vb[32];
+      tc_ld32(sr.taddr + tr * 32, va);
+      tc_ld32(sr.taddr + tr * 32 + 32, vb);
       tc_wait_ld();
-      unpack(ra, xa); unpack(rb, xb);
+      unpack(va, xa); unpack(vb, xb);
     }
     else
     {
-      load_row(va ? sa : s0, xa);
-      load_row(vb ? sb : s0, xb);
+      load_row(tr, ra, xa);
+      load_row(tr + 1, ra + TB, xb);
     }
     double c0a = xa[0], c1a = 0.0, c2a = 0.0, c0b = xb[0], c1b = 0.0, c2b = 0.0;
     #pragma unroll
@@ -517,30 +534,27 @@ __device__ __forceinline__ void site_derivatives(const SumRef & sr, double * ex,
     }
     const double ia = fast_rcp(c0a), ib = fast_rcp(c0b);
     const double g1a = -c1a * ia, g1b = -c1b * ib;
-    const double ha = g1a * g1a - c2a * ia, hb = g1b * g1b - c2b * ib;
-    if (va) { a1 += g1a; a2 += ha; }
-    if (vb) { a1 += g1b; a2 += hb; }
+    a1 += g1a; a2 += g1a * g1a - c2a * ia;
+    a1 += g1b; a2 += g1b * g1b - c2b * ib;
   }
   if (tr < trips)
   {
-    const int sa = lane + 32 * tr;
-    const bool va = sa < w;
-    double xa[NK + 1];
+    double xa[NK + 2];
     if (!GS && sr.tm)
     {
-      uint32_t ra[32];
-      tc_ld32(sr.taddr + tr * 32, ra);
+      uint32_t va[32];
+      tc_ld32(sr.taddr + tr * 32, va);
       tc_wait_ld();
-      unpack(ra, xa);
+      unpack(va, xa);
     }
     else
-      load_row(va ? sa : s0, xa);
+      load_row(tr, ra, xa);
     double c0a = xa[0], c1a = 0.0, c2a = 0.0;
     #pragma unroll
     for (int k = 0; k < NK; ++k) { c0a += xa[k + 1] * d0[k]; c1a += xa[k + 1] * d1[k]; c2a += xa[k + 1] * d2[k]; }
     const double ia = fast_rcp(c0a);
     const double g1a = -c1a * ia;
-    if (va) { a1 += g1a; a2 += g1a * g1a - c2a * ia; }
+    a1 += g1a; a2 += g1a * g1a - c2a * ia;
   }
   warp_sum2(a1, a2, lane);
   f = a1;
@@ -581,44 +595,47 @@ __device__ __forceinline__ double site_newton(const SumRef & sr, double * ex, in
   }
 }
 
-// stores one finished sumtable row: st[r][j], j = 0 is the stationary component. `trip` is the row
-// slot of a TMEM-backed warp (all 32 lanes store, a lane beyond the window keeps a harmless row in
-// its own slot); shared/global rows are only written for sites inside the window.
+// stores one finished sumtable row: st[r][j], j = 0 is the stationary component, into the slot of
+// (trip, this lane). All 32 lanes store: a lane beyond the window keeps (1, 0, ..., 0) in its slot.
 template <int R, bool GS>
-__device__ __forceinline__ void site_store_row(const SumRef & sr, int trip, int s, bool act, double base,
+__device__ __forceinline__ void site_store_row(const SumRef & sr, int trip, int lane, bool act, double base,
                                                const double (&st)[3 * R])
 {
+  constexpr int NK = 3 * R;
+  const double b0 = act ? base : 1.0;
   if constexpr (GS)
   {
-    if (act)
-    {
-      sr.base[s] = base;
-      #pragma unroll
-      for (int k = 0; k < 3 * R; ++k) sr.base[(size_t) (k + 1) * sr.gstride + s] = st[k];
-    }
+    double * g = sr.base + trip * 32 + lane;
+    g[0] = b0;
+    #pragma unroll
+    for (int k = 0; k < NK; ++k) g[(size_t) (k + 1) * sr.gstride] = act ? st[k] : 0.0;
   }
   else
   {
     if (sr.tm)
     {
       uint32_t v[32];
-      v[0] = (uint32_t) __double2loint(act ? base : 1.0); v[1] = (uint32_t) __double2hiint(act ? base : 1.0);
+      v[0] = (uint32_t) __double2loint(b0); v[1] = (uint32_t) __double2hiint(b0);
       #pragma unroll
-      for (int k = 0; k < 3 * R; ++k)
+      for (int k = 0; k < NK; ++k)
       {
         v[2 * k + 2] = (uint32_t) __double2loint(act ? st[k] : 0.0);
         v[2 * k + 3] = (uint32_t) __double2hiint(act ? st[k] : 0.0);
       }
       #pragma unroll
-      for (int k = 6 * R + 2; k < 32; ++k) v[k] = 0u;
+      for (int k = 2 * NK + 2; k < 32; ++k) v[k] = 0u;
       tc_st32(sr.taddr + trip * 32, v);
     }
-    else if (act)
+    else
     {
-      double * row = sr.base + s * blo_row(R);
-      row[0] = base;
+      const uint32_t ra = sr.saddr + (uint32_t) trip * site_trip_bytes(R);
+      double v[NK + 2];
+      v[0] = b0;
       #pragma unroll
-      for (int k = 0; k < 3 * R; ++k) row[k + 1] = st[k];
+      for (int k = 0; k < NK; ++k) v[k + 1] = act ? st[k] : 0.0;
+      v[NK + 1] = 0.0;
+      #pragma unroll
+      for (int k = 0; k < (NK + 2) / 2; ++k) sts2(ra + 16u * k, v[2 * k], v[2 * k + 1]);
     }
   }
 }
@@ -753,7 +770,7 @@ __device__ __forceinline__ double site_pass_tip(const SiteCtaSmem & cs, const do
         scal = 0;
       }
     }
-    site_store_row<R, GS>(sr, tr, s, act, base, st);
+    site_store_row<R, GS>(sr, tr, lane, act, base, st);
     if (act)
     {
       ssum += (int) scal;
@@ -811,7 +828,7 @@ __device__ __forceinline__ double site_pass_first(const SiteCtaSmem & cs, const 
       for (int j = 1; j < 4; ++j) st[r * 3 + j - 1] = tl[j] * gv[r * 4 + j];
     }
     if constexpr (INV) base += __ldg(inv_w + s);
-    site_store_row<R, GS>(sr, tr, s, act, base, st);
+    site_store_row<R, GS>(sr, tr, lane, act, base, st);
   }
   if (!GS && sr.tm) tc_wait_st();
   return warp_sum(acc);
@@ -885,7 +902,7 @@ __device__ __forceinline__ void site_pass_distal(const double * ws, const SumRef
       }
     }
     if constexpr (INV) base += inv;
-    site_store_row<R, GS>(sr, tr, s, act, base, st);
+    site_store_row<R, GS>(sr, tr, lane, act, base, st);
   }
   if (!GS && sr.tm) tc_wait_st();
 }
@@ -964,8 +981,11 @@ blo_site_kernel(BloSiteArgs sa)
   sr.tm = warp < n_tm ? 1 : 0;
   sr.taddr = n_tm > 0 ? tmem_slot + ((uint32_t) ((warp & 3) * 32) << 16) + (uint32_t) (warp >> 2) * (uint32_t) sa.tmem_cols : 0u;
   sr.gstride = GS ? sa.wpad : 0;
-  sr.base = GS ? sa.gscratch + ((size_t) blockIdx.x * n_warps + warp) * (size_t) sa.wpad * blo_row(R)
-               : smem_d + (size_t) n_warps * FIX + (size_t) (warp - n_tm) * (size_t) a.wcap * blo_row(R);
+  sr.base = GS ? sa.gscratch + ((size_t) blockIdx.x * n_warps + warp) * (size_t) sa.wpad * blo_row(R) : nullptr;
+  // shared-memory rows: [warp - n_tm][trips * 32][site_row_pad(R)]
+  const int wcap32 = (a.wcap + 31) & ~31;
+  sr.saddr = (GS || sr.tm) ? 0u
+           : smem_u32(smem_d + (size_t) n_warps * FIX + ((size_t) (warp - n_tm) * wcap32 + lane) * site_row_pad(R));
   double * ex = ws + L::EX;
 
   for (;;)
