@@ -23,7 +23,7 @@ struct DevModel {
   int S, R, n, K;                                 // states, rate cats, sites, lookup columns (internal)
   int ncodes;                                     // number of query character codes
   int per_rate, bugcompat;
-  int pad0;
+  int ngroups;                                    // distinct non-zero eigenvalues (DNA: 3, 2 or 1; see epa_ctx_create)
   double eigenvals[MAX_STATES];
   double eigenvecs[MAX_STATES * MAX_STATES];      // V    [j*S+k]
   double inv_eigenvecs[MAX_STATES * MAX_STATES];  // Vinv [k*S+j]

@@ -379,6 +379,30 @@ extern "C" int epa_ctx_create(epa_ctx ** out, int device, const epa_model_desc *
       }
     }
   }
+  // Equal non-zero eigenvalues (JC69, F81: all three; K80, ...: two): their sumtable components decay
+  // alike, so the thorough DNA kernel keeps one merged entry per group. Equal ones are permuted to
+  // indices 1, 2 (a permutation of the eigenpairs leaves P(t) unchanged).
+  m.ngroups = S - 1;
+  if (S == 4 && !getenv("EPA_B200_NO_EIGEN_GROUPS"))
+  {
+    auto swap_pair = [&](int a, int b)
+    {
+      std::swap(m.eigenvals[a], m.eigenvals[b]);
+      for (int k = 0; k < S; ++k)
+      {
+        std::swap(m.eigenvecs[a * S + k], m.eigenvecs[b * S + k]);
+        std::swap(m.inv_eigenvecs[k * S + a], m.inv_eigenvecs[k * S + b]);
+      }
+    };
+    double scale = 0.0;
+    for (int i = 1; i < 4; ++i) scale = std::max(scale, std::fabs(m.eigenvals[i]));
+    const double tol = 1e-13 * scale;
+    auto eq = [&](int a, int b) { return std::fabs(m.eigenvals[a] - m.eigenvals[b]) <= tol; };
+    if (eq(1, 2) && eq(1, 3) && eq(2, 3)) m.ngroups = 1;
+    else if (eq(1, 2)) m.ngroups = 2;
+    else if (eq(1, 3)) { swap_pair(2, 3); m.ngroups = 2; }
+    else if (eq(2, 3)) { swap_pair(1, 3); m.ngroups = 2; }
+  }
   for (int i = 0; i < S * S; ++i) m.pivinv[i] = m.freqs[i / S] * m.inv_eigenvecs[i];
   // +I (LP/core_pmatrix.c:209-220, LP/core_derivatives.c:757-772, LP/core_likelihood.c:524-537): the
   // rates are stretched by 1 / (1 - pinv) wherever a branch length meets them, and the variable part
@@ -1227,6 +1251,22 @@ int launch_site_kernel(epa_ctx * ctx, const BloSiteArgs & sa, unsigned grid, int
     return EPA_OK;
   }
 #endif
+  // models with equal non-zero eigenvalues (JC, F81, K80, ...): merged sumtable components
+  if constexpr (!PR && !INV)
+  {
+    if (ctx->hm.ngroups == 1)
+    {
+      CU(cudaFuncSetAttribute(blo_site_kernel<R, GS, false, false, false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+      blo_site_kernel<R, GS, false, false, false, 1><<<grid, warps * 32, smem, ctx->stream>>>(sa);
+      return EPA_OK;
+    }
+    if (ctx->hm.ngroups == 2)
+    {
+      CU(cudaFuncSetAttribute(blo_site_kernel<R, GS, false, false, false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+      blo_site_kernel<R, GS, false, false, false, 2><<<grid, warps * 32, smem, ctx->stream>>>(sa);
+      return EPA_OK;
+    }
+  }
   CU(cudaFuncSetAttribute(blo_site_kernel<R, GS, PR, INV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
   blo_site_kernel<R, GS, PR, INV><<<grid, warps * 32, smem, ctx->stream>>>(sa);
   return EPA_OK;
@@ -1262,7 +1302,9 @@ int launch_blo_site(epa_ctx * ctx, BloArgs & a)
   // up to 12 warps per CTA (register file): the first 8 keep their sumtable in tensor memory when
   // the windows fit 8 rows of 32 sites, the others in shared memory
   const size_t fix = (size_t) SiteWarpSmem<R>::SUM * sizeof(double);
-  const size_t rows = (size_t) ((wmax + 31) & ~31) * site_row_pad(R) * sizeof(double);
+  // eigenvalue groups only in the default variant (launch_site_kernel)
+  const int G = (pr || inv || a.raxml) ? 3 : ctx->hm.ngroups;
+  const size_t rows = (size_t) ((wmax + 31) & ~31) * site_row_pad(G * R) * sizeof(double);
   const size_t budget = ctx->smem_optin - 2048;
   const int max_warps = SITE_MAX_WARPS;
   const bool tm_ok = !ctx->sw.no_tmem;

@@ -68,6 +68,7 @@ struct SiteWarpSmem {
 struct SiteCtaSmem {
   double V[16], Vinv[16];
   __align__(16) double tipleft[64];     // [tv_pos(mask)][j] = sum_{k in mask} pi_k Vinv[k][j]
+  __align__(16) double tippi[64];       // [tv_pos(mask)][k] = pi_k if k in mask else 0
   unsigned long long q_next, q_end;
   int q_lock;
 };
@@ -97,13 +98,13 @@ struct SumRef {
 // different 16-byte bank groups). Every storage kind keeps a row for all 32 lanes of every trip: a
 // lane beyond the window stores (1, 0, ..., 0), whose derivative terms are exact zeros, so the
 // Newton sweeps need no validity predicates.
-__host__ __device__ constexpr int site_row_pad(int R)
+__host__ __device__ constexpr int site_row_pad(int NK)        // NK = decaying components per site
 {
-  int p = (1 + 3 * R + 1) & ~1;
+  int p = (1 + NK + 1) & ~1;
   if (((p / 2) & 1) == 0) p += 2;
   return p;
 }
-__host__ __device__ constexpr uint32_t site_trip_bytes(int R) { return 32u * (uint32_t) site_row_pad(R) * 8u; }
+__host__ __device__ constexpr uint32_t site_trip_bytes(int NK) { return 32u * (uint32_t) site_row_pad(NK) * 8u; }
 
 __device__ __forceinline__ void lds2(uint32_t addr, double & a, double & b)
 {
@@ -458,15 +459,18 @@ __device__ __forceinline__ void warp_sum2(double & a, double & b, int lane)
 }
 
 // derivative sums over the window, lane = site (LP/core_derivatives.c:643-858)
-template <int R, bool GS>
+// G = number of distinct non-zero eigenvalues (3, or 2 / 1 when the context found equal ones and
+// permuted them to the front: {1,2},{3} / {1,2,3}): components that decay alike share one entry.
+template <int R, int G, bool GS>
 __device__ __forceinline__ void site_derivatives(const SumRef & sr, double * ex, int w, double t,
                                                  int lane, double & f, double & df)
 {
-  constexpr int NK = 3 * R;
+  constexpr int NK = G * R;
   if (lane < NK)
   {
-    const double lk = c_model.eigenvals[1 + lane % 3] * c_model.rates[lane / 3];
-    const double e = exp(lk * t) * c_model.weights[lane / 3];
+    const int g = lane % G;
+    const double lk = c_model.eigenvals[G == 3 ? 1 + g : (G == 2 ? 1 + 2 * g : 1)] * c_model.rates[lane / G];
+    const double e = exp(lk * t) * c_model.weights[lane / G];
     const double e1 = lk * e;
     ex[lane] = e; ex[NK + lane] = e1; ex[2 * NK + lane] = lk * e1;
   }
@@ -505,7 +509,7 @@ __device__ __forceinline__ void site_derivatives(const SumRef & sr, double * ex,
     #pragma unroll
     for (int k = 0; k <= NK; ++k) x[k] = __hiloint2double((int) v[2 * k + 1], (int) v[2 * k]);
   };
-  constexpr uint32_t TB = site_trip_bytes(R);
+  constexpr uint32_t TB = site_trip_bytes(NK);
   uint32_t ra = sr.saddr;
   int tr = 0;
   #pragma unroll 1
@@ -563,7 +567,7 @@ __device__ __forceinline__ void site_derivatives(const SumRef & sr, double * ex,
 }
 
 // bounded Newton-Raphson, PM/optimize/opt_algorithms.c:133-262; returns 0.0 on failure
-template <int R, bool GS>
+template <int R, int G, bool GS>
 __device__ __forceinline__ double site_newton(const SumRef & sr, double * ex, int w, int lane,
                                               double xmin, double xguess, double xmax, double tol)
 {
@@ -575,7 +579,7 @@ __device__ __forceinline__ double site_newton(const SumRef & sr, double * ex, in
   {
     if (iter++ > EPA_NR_MAX_ITERS) return 0.0;
     double f, df;
-    site_derivatives<R, GS>(sr, ex, w, x, lane, f, df);
+    site_derivatives<R, G, GS>(sr, ex, w, x, lane, f, df);
     if (!isfinite(f) || !isfinite(df)) return 0.0;
     double dx;
     if (df > 0.0)
@@ -595,13 +599,22 @@ __device__ __forceinline__ double site_newton(const SumRef & sr, double * ex, in
   }
 }
 
+// the three decaying components (j = 1, 2, 3) of one rate category -> G sumtable entries
+template <int R, int G>
+__device__ __forceinline__ void site_merge(double (&st)[G * R], int r, double v1, double v2, double v3)
+{
+  if constexpr (G == 3) { st[r * 3] = v1; st[r * 3 + 1] = v2; st[r * 3 + 2] = v3; }
+  else if constexpr (G == 2) { st[r * 2] = v1 + v2; st[r * 2 + 1] = v3; }
+  else st[r] = (v1 + v2) + v3;
+}
+
 // stores one finished sumtable row: st[r][j], j = 0 is the stationary component, into the slot of
 // (trip, this lane). All 32 lanes store: a lane beyond the window keeps (1, 0, ..., 0) in its slot.
-template <int R, bool GS>
+template <int R, int G, bool GS>
 __device__ __forceinline__ void site_store_row(const SumRef & sr, int trip, int lane, bool act, double base,
-                                               const double (&st)[3 * R])
+                                               const double (&st)[G * R])
 {
-  constexpr int NK = 3 * R;
+  constexpr int NK = G * R;
   const double b0 = act ? base : 1.0;
   if constexpr (GS)
   {
@@ -628,7 +641,7 @@ __device__ __forceinline__ void site_store_row(const SumRef & sr, int trip, int 
     }
     else
     {
-      const uint32_t ra = sr.saddr + (uint32_t) trip * site_trip_bytes(R);
+      const uint32_t ra = sr.saddr + (uint32_t) trip * site_trip_bytes(NK);
       double v[NK + 2];
       v[0] = b0;
       #pragma unroll
@@ -682,7 +695,7 @@ __device__ __forceinline__ uint32_t site_rescale_inv(double (&in)[4 * R])
   return 1u;
 }
 
-template <int R, bool GS, bool PR, bool INV>
+template <int R, int G, bool GS, bool PR, bool INV>
 __device__ __forceinline__ double site_pass_tip(const SiteCtaSmem & cs, const double * ws, const SumRef & sr,
                                              const double * __restrict__ DT, const double * __restrict__ XT,
                                              const uint32_t * __restrict__ sD, const uint32_t * __restrict__ sX,
@@ -740,7 +753,9 @@ __device__ __forceinline__ double site_pass_tip(const SiteCtaSmem & cs, const do
     lds_vec<4>(cs.tipleft + pos * 4, tl);
     const double * tvp = ws + L::TV + pos * L::TVS;
     double term = 0.0, base = 0.0;
-    double st[3 * R];
+    double st[G * R];
+    double tpi[4];
+    if constexpr (G == 1) lds_vec<4>(cs.tippi + pos * 4, tpi);
     #pragma unroll
     for (int r = 0; r < R; ++r)
     {
@@ -750,14 +765,29 @@ __device__ __forceinline__ double site_pass_tip(const SiteCtaSmem & cs, const do
                       + (in[r * 4 + 2] * c_model.freqs[2]) * tp[2] + (in[r * 4 + 3] * c_model.freqs[3]) * tp[3];
       term += tr * c_model.weights[r];
       // pendant sumtable: tip side takes pi*Vinv (tipleft), inner side takes V
-      #pragma unroll
-      for (int j = 0; j < 4; ++j)
+      if constexpr (G == 1)
       {
-        const double right = c_model.eigenvecs[j * 4] * in[r * 4] + c_model.eigenvecs[j * 4 + 1] * in[r * 4 + 1]
-                           + c_model.eigenvecs[j * 4 + 2] * in[r * 4 + 2] + c_model.eigenvecs[j * 4 + 3] * in[r * 4 + 3];
-        const double v = tl[j] * right;
-        if (j == 0) base += v * c_model.weights[r];
-        else st[r * 3 + j - 1] = v;
+        // one decaying group: sum_{j>0} tl[j] (V in)[j] = sum_{k in mask} pi_k in[k] - tl[0] (V in)[0], because
+        // sum_j pi_k Vinv[k][j] V[j][i] = pi_k delta_ki
+        const double tot = tpi[0] * in[r * 4] + tpi[1] * in[r * 4 + 1] + tpi[2] * in[r * 4 + 2] + tpi[3] * in[r * 4 + 3];
+        const double right0 = c_model.eigenvecs[0] * in[r * 4] + c_model.eigenvecs[1] * in[r * 4 + 1]
+                            + c_model.eigenvecs[2] * in[r * 4 + 2] + c_model.eigenvecs[3] * in[r * 4 + 3];
+        const double b = tl[0] * right0;
+        base += b * c_model.weights[r];
+        st[r] = tot - b;
+      }
+      else
+      {
+        double v[4];
+        #pragma unroll
+        for (int j = 0; j < 4; ++j)
+        {
+          const double right = c_model.eigenvecs[j * 4] * in[r * 4] + c_model.eigenvecs[j * 4 + 1] * in[r * 4 + 1]
+                             + c_model.eigenvecs[j * 4 + 2] * in[r * 4 + 2] + c_model.eigenvecs[j * 4 + 3] * in[r * 4 + 3];
+          v[j] = tl[j] * right;
+        }
+        base += v[0] * c_model.weights[r];
+        site_merge<R, G>(st, r, v[1], v[2], v[3]);
       }
     }
     if constexpr (INV)
@@ -770,7 +800,7 @@ __device__ __forceinline__ double site_pass_tip(const SiteCtaSmem & cs, const do
         scal = 0;
       }
     }
-    site_store_row<R, GS>(sr, tr, lane, act, base, st);
+    site_store_row<R, G, GS>(sr, tr, lane, act, base, st);
     if (act)
     {
       ssum += (int) scal;
@@ -797,7 +827,7 @@ __device__ __forceinline__ double site_pass_tip(const SiteCtaSmem & cs, const do
 // Pass A of the FIRST half round, from the per-edge tables: the pendant sumtable is the tip factor
 // times the stored eigen-rotated inner CLV, the window log-likelihood is the sum of the
 // preplacement table entries (the same three lengths, the same tiny tree).
-template <int R, bool GS, bool INV>
+template <int R, int G, bool GS, bool INV>
 __device__ __forceinline__ double site_pass_first(const SiteCtaSmem & cs, const SumRef & sr,
                                                   const double * __restrict__ GT, const double * __restrict__ lk,
                                                   const uint8_t * __restrict__ qc, int begin, int w, int lane,
@@ -819,16 +849,15 @@ __device__ __forceinline__ double site_pass_first(const SiteCtaSmem & cs, const 
     double tl[4];
     lds_vec<4>(cs.tipleft + tv_pos(mask) * 4, tl);
     double base = 0.0;
-    double st[3 * R];
+    double st[G * R];
     #pragma unroll
     for (int r = 0; r < R; ++r)
     {
       base += (tl[0] * gv[r * 4]) * c_model.weights[r];
-      #pragma unroll
-      for (int j = 1; j < 4; ++j) st[r * 3 + j - 1] = tl[j] * gv[r * 4 + j];
+      site_merge<R, G>(st, r, tl[1] * gv[r * 4 + 1], tl[2] * gv[r * 4 + 2], tl[3] * gv[r * 4 + 3]);
     }
     if constexpr (INV) base += __ldg(inv_w + s);
-    site_store_row<R, GS>(sr, tr, lane, act, base, st);
+    site_store_row<R, G, GS>(sr, tr, lane, act, base, st);
   }
   if (!GS && sr.tm) tc_wait_st();
   return warp_sum(acc);
@@ -837,7 +866,7 @@ __device__ __forceinline__ double site_pass_first(const SiteCtaSmem & cs, const 
 // Pass B: inner CLV toward the distal node from (T, X); leaves the distal sumtable (D vs inner).
 // `pm_x` is the offset of X's transition matrix in the warp's slice. (--raxml-blo also optimises the
 // proximal edge on its own: the same pass with the two nodes swapped and D's matrix.)
-template <int R, bool GS, bool PR, bool INV>
+template <int R, int G, bool GS, bool PR, bool INV>
 __device__ __forceinline__ void site_pass_distal(const double * ws, const SumRef & sr,
                                               const double * __restrict__ DT, const double * __restrict__ XT,
                                               const uint32_t * __restrict__ sD, const uint32_t * __restrict__ sX,
@@ -885,24 +914,41 @@ __device__ __forceinline__ void site_pass_distal(const double * ws, const SumRef
         if (inv > 0.0) (void) site_rescale_inv<R>(in);
     }
     double base = 0.0;
-    double st[3 * R];
+    double st[G * R];
     #pragma unroll
     for (int r = 0; r < R; ++r)
     {
-      #pragma unroll
-      for (int j = 0; j < 4; ++j)
+      if constexpr (G == 1)
       {
-        const double left = dv[r * 4] * c_model.pivinv[j] + dv[r * 4 + 1] * c_model.pivinv[4 + j]
-                          + dv[r * 4 + 2] * c_model.pivinv[8 + j] + dv[r * 4 + 3] * c_model.pivinv[12 + j];
-        const double right = c_model.eigenvecs[j * 4] * in[r * 4] + c_model.eigenvecs[j * 4 + 1] * in[r * 4 + 1]
-                           + c_model.eigenvecs[j * 4 + 2] * in[r * 4 + 2] + c_model.eigenvecs[j * 4 + 3] * in[r * 4 + 3];
-        const double v = left * right;
-        if (j == 0) base += v * c_model.weights[r];
-        else st[r * 3 + j - 1] = v;
+        // sum over all four eigen-components = sum_k pi_k D[k] in[k]; minus the stationary one
+        const double tot = (dv[r * 4] * c_model.freqs[0]) * in[r * 4] + (dv[r * 4 + 1] * c_model.freqs[1]) * in[r * 4 + 1]
+                         + (dv[r * 4 + 2] * c_model.freqs[2]) * in[r * 4 + 2] + (dv[r * 4 + 3] * c_model.freqs[3]) * in[r * 4 + 3];
+        const double left0 = dv[r * 4] * c_model.pivinv[0] + dv[r * 4 + 1] * c_model.pivinv[4]
+                           + dv[r * 4 + 2] * c_model.pivinv[8] + dv[r * 4 + 3] * c_model.pivinv[12];
+        const double right0 = c_model.eigenvecs[0] * in[r * 4] + c_model.eigenvecs[1] * in[r * 4 + 1]
+                            + c_model.eigenvecs[2] * in[r * 4 + 2] + c_model.eigenvecs[3] * in[r * 4 + 3];
+        const double b = left0 * right0;
+        base += b * c_model.weights[r];
+        st[r] = tot - b;
+      }
+      else
+      {
+        double v[4];
+        #pragma unroll
+        for (int j = 0; j < 4; ++j)
+        {
+          const double left = dv[r * 4] * c_model.pivinv[j] + dv[r * 4 + 1] * c_model.pivinv[4 + j]
+                            + dv[r * 4 + 2] * c_model.pivinv[8 + j] + dv[r * 4 + 3] * c_model.pivinv[12 + j];
+          const double right = c_model.eigenvecs[j * 4] * in[r * 4] + c_model.eigenvecs[j * 4 + 1] * in[r * 4 + 1]
+                             + c_model.eigenvecs[j * 4 + 2] * in[r * 4 + 2] + c_model.eigenvecs[j * 4 + 3] * in[r * 4 + 3];
+          v[j] = left * right;
+        }
+        base += v[0] * c_model.weights[r];
+        site_merge<R, G>(st, r, v[1], v[2], v[3]);
       }
     }
     if constexpr (INV) base += inv;
-    site_store_row<R, GS>(sr, tr, lane, act, base, st);
+    site_store_row<R, G, GS>(sr, tr, lane, act, base, st);
   }
   if (!GS && sr.tm) tc_wait_st();
 }
@@ -934,7 +980,7 @@ __device__ __forceinline__ unsigned long long site_next_item(SiteCtaSmem & cs, u
 // RAXML = --raxml-blo (optimize.cpp:274-278): pendant, distal and proximal edge optimised one after the
 // other, each unconstrained in [1e-4, 100], then the pendant edge once more from the tip's side
 // (pllmod_opt_optimize_branch_lengths_local with radius 1, PM/optimize/pll_optimize.c:778-1097)
-template <int R, bool GS, bool PR = false, bool INV = false, bool RAXML = false>
+template <int R, bool GS, bool PR = false, bool INV = false, bool RAXML = false, int G = 3>
 __global__ void __launch_bounds__(SITE_MAX_WARPS * 32, 1)
 blo_site_kernel(BloSiteArgs sa)
 {
@@ -956,6 +1002,7 @@ blo_site_kernel(BloSiteArgs sa)
     for (int k = 0; k < 4; ++k)
       if ((mask >> k) & 1) acc += c_model.pivinv[k * 4 + j];
     cs.tipleft[tv_pos(mask) * 4 + j] = acc;
+    cs.tippi[tv_pos(mask) * 4 + j] = ((mask >> j) & 1) ? c_model.freqs[j] : 0.0;
   }
   if (threadIdx.x == 0) { cs.q_next = 0; cs.q_end = 0; cs.q_lock = 0; }
   __syncthreads();
@@ -982,10 +1029,10 @@ blo_site_kernel(BloSiteArgs sa)
   sr.taddr = n_tm > 0 ? tmem_slot + ((uint32_t) ((warp & 3) * 32) << 16) + (uint32_t) (warp >> 2) * (uint32_t) sa.tmem_cols : 0u;
   sr.gstride = GS ? sa.wpad : 0;
   sr.base = GS ? sa.gscratch + ((size_t) blockIdx.x * n_warps + warp) * (size_t) sa.wpad * blo_row(R) : nullptr;
-  // shared-memory rows: [warp - n_tm][trips * 32][site_row_pad(R)]
+  // shared-memory rows: [warp - n_tm][trips * 32][site_row_pad(G * R)]
   const int wcap32 = (a.wcap + 31) & ~31;
   sr.saddr = (GS || sr.tm) ? 0u
-           : smem_u32(smem_d + (size_t) n_warps * FIX + ((size_t) (warp - n_tm) * wcap32 + lane) * site_row_pad(R));
+           : smem_u32(smem_d + (size_t) n_warps * FIX + ((size_t) (warp - n_tm) * wcap32 + lane) * site_row_pad(G * R));
   double * ex = ws + L::EX;
 
   for (;;)
@@ -1031,7 +1078,7 @@ blo_site_kernel(BloSiteArgs sa)
       site_tipvec<R>(ws + L::P_E, ws + L::TV, lane);
       auto pass_tip = [&]() -> double
       {
-        return site_pass_tip<R, GS, PR, INV>(cs, ws, sr, DT, XT, sD, sX, qc, begin, w, lane, sa.bugcompat, inv_w);
+        return site_pass_tip<R, G, GS, PR, INV>(cs, ws, sr, DT, XT, sD, sX, qc, begin, w, lane, sa.bugcompat, inv_w);
       };
       // one recomp_iterative step (pll_optimize.c:799-833) on the edge whose sumtable is current:
       // Newton, new length, matrix rebuilt if the length moved by more than 1e-10
@@ -1040,7 +1087,7 @@ blo_site_kernel(BloSiteArgs sa)
         double xguess = len[mi];
         if (xguess < EPA_MIN_BRLEN || xguess > EPA_MAX_BRLEN) xguess = EPA_DEFAULT_BRLEN;
         bool failed;
-        const double xres = newton_old([&](double x, double & f, double & df) { site_derivatives<R, GS>(sr, ex, w, x, lane, f, df); },
+        const double xres = newton_old([&](double x, double & f, double & df) { site_derivatives<R, G, GS>(sr, ex, w, x, lane, f, df); },
                                        EPA_MIN_BRLEN, xguess, EPA_MAX_BRLEN, EPA_MIN_BRLEN / 10.0, failed);
         if (failed) return false;
         const bool moved = fabs(xres - len[mi]) > 1e-10;
@@ -1053,7 +1100,7 @@ blo_site_kernel(BloSiteArgs sa)
         return true;
       };
       double loglikelihood = (sa.gT)
-          ? site_pass_first<R, GS, INV>(cs, sr, sa.gT + (size_t) e * sa.g_stride, sa.lookup + (size_t) e * sa.n_pad * 16,
+          ? site_pass_first<R, G, GS, INV>(cs, sr, sa.gT + (size_t) e * sa.g_stride, sa.lookup + (size_t) e * sa.n_pad * 16,
                                         qc, begin, w, lane, inv_w)
           : pass_tip();
       int iters = EPA_SMOOTHINGS;
@@ -1061,9 +1108,9 @@ blo_site_kernel(BloSiteArgs sa)
       while (iters)
       {
         if (!(ok = edge(2))) break;                                                    // pendant
-        site_pass_distal<R, GS, PR, INV>(ws, sr, DT, XT, sD, sX, qc, begin, w, lane, sa.bugcompat, inv_w, L::P_P);
+        site_pass_distal<R, G, GS, PR, INV>(ws, sr, DT, XT, sD, sX, qc, begin, w, lane, sa.bugcompat, inv_w, L::P_P);
         if (!(ok = edge(0))) break;                                                    // distal
-        site_pass_distal<R, GS, PR, INV>(ws, sr, XT, DT, sX, sD, qc, begin, w, lane, sa.bugcompat, inv_w, L::P_D);
+        site_pass_distal<R, G, GS, PR, INV>(ws, sr, XT, DT, sX, sD, qc, begin, w, lane, sa.bugcompat, inv_w, L::P_D);
         if (!(ok = edge(1))) break;                                                    // proximal
         double new_logl = pass_tip();                                                  // inner CLV back toward the tip
         const double pend_before = len[2];
@@ -1114,10 +1161,10 @@ blo_site_kernel(BloSiteArgs sa)
       {
         double new_logl;
         if (first && sa.gT)
-          new_logl = -site_pass_first<R, GS, INV>(cs, sr, sa.gT + (size_t) e * sa.g_stride,
+          new_logl = -site_pass_first<R, G, GS, INV>(cs, sr, sa.gT + (size_t) e * sa.g_stride,
                                                   sa.lookup + (size_t) e * sa.n_pad * 16, qc, begin, w, lane, inv_w);
         else
-          new_logl = -site_pass_tip<R, GS, PR, INV>(cs, ws, sr, DT, XT, sD, sX, qc, begin, w, lane, sa.bugcompat, inv_w);
+          new_logl = -site_pass_tip<R, G, GS, PR, INV>(cs, ws, sr, DT, XT, sD, sX, qc, begin, w, lane, sa.bugcompat, inv_w);
         if (first) { loglikelihood = new_logl; first = false; }
         else
         {
@@ -1137,13 +1184,13 @@ blo_site_kernel(BloSiteArgs sa)
       }
       else
       {
-        site_pass_distal<R, GS, PR, INV>(ws, sr, DT, XT, sD, sX, qc, begin, w, lane, sa.bugcompat, inv_w);
+        site_pass_distal<R, G, GS, PR, INV>(ws, sr, DT, XT, sD, sX, qc, begin, w, lane, sa.bugcompat, inv_w);
         xmin = fmin(EPA_MIN_BRLEN / 2.0, original_length / 2.0);
         xmax = original_length - xmin / 10.0;
         xguess = len[0];
         if (xguess < xmin || xguess > xmax) xguess = original_length / 2.0;
       }
-      const double xres = site_newton<R, GS>(sr, ex, w, lane, xmin, xguess, xmax, xmin / 10.0);
+      const double xres = site_newton<R, G, GS>(sr, ex, w, lane, xmin, xguess, xmax, xmin / 10.0);
       if (xres > 0.0)
       {
         if (!distal_phase) { len[2] = xres; rebuild = 4u; }
