@@ -121,8 +121,8 @@ def ncu_traffic(kernel, q, chunk):
     the launch of this run is not that size or the summary is missing."""
     if min(q, chunk) != 131072:
         return None
-    path = os.path.join(ROOT, "profiles", "r1_ncu_%s.txt" % kernel.replace("_kernel", ""))
-    if not os.path.exists(path):
+    path = ncu_profile(kernel)
+    if not path:
         return None
     tot, scale = 0.0, {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
     for line in open(path):
@@ -132,10 +132,32 @@ def ncu_traffic(kernel, q, chunk):
     return tot or None
 
 
+def ncu_profile(kernel):
+    """Newest committed ncu --set full summary of `kernel` (profiles/r<N>_ncu_<kernel>.txt)."""
+    for rnd in ("r2", "r1"):
+        path = os.path.join(ROOT, "profiles", "%s_ncu_%s.txt" % (rnd, kernel.replace("_kernel", "")))
+        if os.path.exists(path):
+            return path
+    return None
+
+
+def ncu_fp64_per_pair():
+    """Executed fp64 warp instructions per (query, edge) pair of blo_site_kernel, from the committed capture's
+    'fp64_warp_instructions_per_pair' line (profiles/r2_ncu_blo_site.txt)."""
+    path = ncu_profile("blo_site_kernel")
+    if not path:
+        return None
+    for line in open(path):
+        t = line.split()
+        if len(t) >= 2 and t[0] == "fp64_warp_instructions_per_pair":
+            return float(t[1])
+    return None
+
+
 def ncu_metric(kernel, metric):
-    """One number of the committed ncu --set full summary of `kernel` (profiles/r1_ncu_<kernel>.txt), or None."""
-    path = os.path.join(ROOT, "profiles", "r1_ncu_%s.txt" % kernel.replace("_kernel", ""))
-    if not os.path.exists(path):
+    """One number of the committed ncu --set full summary of `kernel`, or None."""
+    path = ncu_profile(kernel)
+    if not path:
         return None
     for line in open(path):
         t = line.split()
@@ -195,6 +217,101 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------
+#  files -> jplace through the C++ host pipeline (epa_run_files_multi)
+# ------------------------------------------------------------------------------------------------
+def head_placements(jplace_path, n_first):
+    """name -> placements of the first n_first pqueries of a (large) jplace file, without parsing all of it."""
+    want = n_first
+    chunks, seen = [], 0
+    with open(jplace_path, "r") as fh:
+        while seen < want:
+            block = fh.read(1 << 22)
+            if not block:
+                break
+            chunks.append(block)
+            seen += block.count('"n": [')
+    text = "".join(chunks)
+    start = text.index("[", text.index('"placements"'))
+    pos, out = start + 1, {}
+    for _ in range(min(want, seen)):
+        a = text.find('{"p"', pos)
+        b = text.find("}", a)
+        if a < 0 or b < 0:
+            break
+        pq = json.loads(text[a:b + 1])
+        for nm in pq["n"]:
+            out[nm] = pq["p"]
+        pos = b + 1
+    return out
+
+
+def files_leg(pkg, ds, n_files, devices, chunk, recs, counts, fmax):
+    """Wall clock of files -> jplace (FASTA and bfast query files in a tmpfs directory) through
+    epa_run_files_multi on `devices`, with a 64-query run of the same files as the start-up figure."""
+    synth, session = pkg.synth, pkg.session
+    base = "/dev/shm" if os.path.isdir("/dev/shm") and os.access("/dev/shm", os.W_OK) else None
+    tmp = tempfile.mkdtemp(prefix="epa_files_", dir=base)
+    try:
+        tf, sf, _ = synth.write_dataset(dict(ds, queries=ds["queries"][:64], qnames=ds["qnames"][:64]), tmp)
+        small = os.path.join(tmp, "query.fasta")
+        qf = os.path.join(tmp, "q_full.fasta")
+        synth.write_fasta(qf, ds["qnames"][:n_files], ds["queries"][:n_files])
+        bf = session.fasta_to_bfast(qf, tmp)
+
+        def run(qfile, sub):
+            out = os.path.join(tmp, sub)
+            t0 = time.perf_counter()
+            st = session.run_files_multi(tf, sf, qfile, ds["model"], out, devices=devices, chunk_size=chunk,
+                                         invocation="bench.py files leg")
+            return time.perf_counter() - t0, st, os.path.join(out, "epa_result.jplace")
+
+        devnull = os.open(os.devnull, os.O_WRONLY)
+        saved = os.dup(1)
+        os.dup2(devnull, 1)                   # the host layer logs to stdout like the reference does
+        try:
+            run(small, "warm")
+            t_small, _, _ = run(small, "small")
+            res = {}
+            # the first full-size run page-locks the staging pool (kept for later runs in the process): reported as cold
+            for kind, qfile in (("fasta_cold", qf), ("fasta", qf), ("bfast", bf)):
+                t, st, jp = run(qfile, kind)
+                res[kind] = {"value": n_files / t, "unit": "query-seqs/s", "seconds": t,
+                             "value_startup_removed": (n_files - 64) / max(t - t_small, 1e-9),
+                             "query_file_bytes": os.path.getsize(qfile), "jplace_bytes": os.path.getsize(jp), "stats": st}
+                res[kind]["jplace"] = jp
+        finally:
+            os.dup2(saved, 1)
+            os.close(saved)
+            os.close(devnull)
+        same = subprocess.run(["cmp", "-s", res["fasta"]["jplace"], res["bfast"]["jplace"]]).returncode == 0
+        n_cmp = min(20000, n_files) if recs is not None else 0
+        got = head_placements(res["fasta"]["jplace"], n_cmp) if n_cmp else {}
+        bad = 0
+        r = recs.reshape(len(counts), fmax, 5) if n_cmp else None
+        for qi in range(n_cmp):
+            nm = ds["qnames"][qi]
+            c = int(counts[qi])
+            want = [[int(np.float64(x[0]).view(np.uint64)), x[1], x[2], x[4], x[3]] for x in r[qi, :c]]
+            g = got.get(nm)
+            if g is None or len(g) != len(want) or any(
+                    a[0] != b[0] or any(abs(a[k] - b[k]) > 5.1e-11 * max(1.0, abs(b[k])) for k in range(1, 5)) for a, b in zip(g, want)):
+                bad += 1
+        for kind in ("fasta_cold", "fasta", "bfast"):
+            del res[kind]["jplace"]
+        res.update({"queries": n_files, "devices": list(devices), "host_threads": os.cpu_count(),
+                    "startup_seconds_64_queries": t_small,
+                    "value": res["fasta"]["value"], "unit": "query-seqs/s", "fasta_and_bfast_jplace_identical": same,
+                    "vs_device_records": {"queries_compared": n_cmp, "mismatches": bad,
+                                          "note": "jplace text (10 decimals) against the records of the timed e2e step"},
+                    "what": "epa_run_files_multi: tree + reference MSA + query file -> epa_result.jplace, wall clock of the "
+                            "whole call (CUDA context, reference CLVs and lookup tables, memory-mapped query file indexed and "
+                            "decoded by host threads, placement, jplace formatting and writing), files on tmpfs"})
+        return res
+    finally:
+        shutil.rmtree(tmp, ignore_errors=True)
+
+
+# ------------------------------------------------------------------------------------------------
 #  our arm
 # ------------------------------------------------------------------------------------------------
 def ours(args):
@@ -210,8 +327,10 @@ def ours(args):
         raise SystemExit("bench.py (impl ours) needs a CUDA device: the product has no CPU path")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    cpu_group = None
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
+        cpu_group = dist.new_group(backend="gloo")       # host-side barrier around the single-process files leg
 
     Q = args.queries
     ds = synth.dataset(T=T_TAXA, n_sites=N_SITES, n_queries=Q, window=WINDOW, seed_q=2 + rank)
@@ -251,8 +370,30 @@ def ours(args):
             # records of all shards in global query order
             pkg.shard.gather_records(rec_dev, cnt_dev, Q * world, dst=0)
 
+    rec_all_host = cnt_all_host = None
+    if world > 1 and rank == 0:
+        rec_all_host = torch.zeros((Q * world, fmax * 5), dtype=torch.float64).pin_memory()
+        cnt_all_host = torch.zeros(Q * world, dtype=torch.int32).pin_memory()
+
     def step_e2e():
-        sess.place((host_q.data_ptr(), Q), opts, chunk, out=rec_host.data_ptr(), counts=cnt_host.data_ptr())
+        if world == 1:
+            sess.place((host_q.data_ptr(), Q), opts, chunk, out=rec_host.data_ptr(), counts=cnt_host.data_ptr())
+            return
+        # N > 1: queries from pinned host memory (the copy of the next chunk overlaps this one), records
+        # stay on the device, ONE gather brings every shard to rank 0 (NCCL), rank 0 copies all of them out
+        for lo in range(0, Q, chunk):
+            nq = min(chunk, Q - lo)
+            if lo + nq < Q:
+                ctx.hint_next_chunk(host_q.data_ptr() + (lo + nq) * n, min(chunk, Q - lo - nq))
+            ctx.upload_queries_ptr(host_q.data_ptr() + lo * n, nq, True)
+            ctx.preplace()
+            ctx.select(opts)
+            ctx.place_pairs(opts)
+            ctx.collect_dev(opts, rec_dev.data_ptr() + lo * fmax * 40, cnt_dev.data_ptr() + lo * 4)
+        recs, cnts = pkg.shard.gather_records(rec_dev, cnt_dev, Q * world, dst=0)
+        if rank == 0:
+            rec_all_host.copy_(recs, non_blocking=True)
+            cnt_all_host.copy_(cnts, non_blocking=True)
 
     def barrier():
         if world > 1:
@@ -285,8 +426,25 @@ def ours(args):
     ms_e2e = timed(step_e2e, args.steps)
 
     # device-resident and host paths must agree bit for bit
-    same = bool(np.array_equal(rec_host.numpy(), rec_dev.cpu().numpy())
-                and np.array_equal(cnt_host.numpy(), cnt_dev.cpu().numpy()))
+    if world == 1:
+        same = bool(np.array_equal(rec_host.numpy(), rec_dev.cpu().numpy())
+                    and np.array_equal(cnt_host.numpy(), cnt_dev.cpu().numpy()))
+    else:
+        rec_host.copy_(rec_dev)
+        cnt_host.copy_(cnt_dev)
+        same = bool(rank != 0 or (np.array_equal(rec_all_host[:Q].numpy(), rec_host.numpy())
+                                  and np.array_equal(cnt_all_host[:Q].numpy(), cnt_host.numpy())))
+
+    # files -> jplace through the C++ pipeline, all GPUs of the job driven by rank 0's process
+    files = None
+    if not args.no_files:
+        if cpu_group is not None:
+            dist.barrier(group=cpu_group)
+        if rank == 0:
+            n_files = int(min(args.files_queries or 2000000, Q))
+            files = files_leg(pkg, ds, n_files, list(range(world)), chunk, rec_host.numpy(), cnt_host.numpy(), fmax)
+        if cpu_group is not None:
+            dist.barrier(group=cpu_group)
 
     if rank == 0:
         total_q = Q * world
@@ -330,10 +488,18 @@ def ours(args):
                     "algorithmic_bytes_per_launch": units[dom] * per_unit[dom] / n_launch}
         if dom == "thorough":
             # the branch-length optimisation re-reads its CLV windows from L1/L2 for every pass and spends its
-            # time in fp64 arithmetic: the HBM fraction is the contract's figure, the fp64 pipe is what limits it
+            # time in fp64 arithmetic: the HBM fraction is the contract's figure, the fp64 pipe is what limits it.
+            # fp64 roofline: measured DFMA peak of this GPU (epa_measure_fp64_peak) against the kernel's executed fp64
+            # warp instructions per pair from the committed ncu capture (x 32 lanes x 2 flops).
+            fp64_peak = capi.measure_fp64_peak(local)
+            per_pair = ncu_fp64_per_pair()
+            roofline["fp64"] = {"peak_tflops_measured": fp64_peak, "fp64_warp_instructions_per_pair_ncu": per_pair}
+            if per_pair:
+                ach = pairs * per_pair * 64.0 / (kernels[dom]["ms_per_step"] / 1e3) / 1e12
+                roofline["fp64"].update({"achieved_tflops": ach, "frac": ach / fp64_peak})
             roofline["fp64_pipe_active_pct_ncu"] = ncu_metric(kname, "sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active")
-            roofline["note"] = ("fp64-issue bound (Newton-Raphson derivative sums and CLV passes, DESIGN 3.2): ncu fp64 pipe "
-                                "utilisation of the committed capture next to the HBM figure")
+            roofline["note"] = ("fp64-issue bound (Newton-Raphson derivative sums and CLV passes, DESIGN 3.2): fp64 figures "
+                                "next to the HBM figure")
 
         cpu = None
         parity = None
@@ -355,6 +521,8 @@ def ours(args):
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "kernels": kernels,
             "candidate_pairs_per_query": pairs / Q, "chunk": chunk, "resident_equals_e2e": same,
         }
+        if files:
+            out["e2e_files"] = files
         if cpu:
             out["cpu_baseline"] = cpu
         if parity:
@@ -402,6 +570,8 @@ def main():
     ap.add_argument("--chunk", type=int, default=131072)
     ap.add_argument("--ref-queries", type=int, default=0, help="size of the CPU reference sample")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-files", action="store_true", help="skip the files -> jplace leg")
+    ap.add_argument("--files-queries", type=int, default=0, help="queries of the files -> jplace leg [min(Q, 2M)]")
     args = ap.parse_args()
     if args.impl == "reference":
         reference_arm(args)

@@ -70,6 +70,7 @@ SYMBOLS = [
     ("epa_hint_next_chunk", C.c_int, [_vp, _vp, C.c_uint32]),
     ("epa_set_deferred_results", C.c_int, [_vp, C.c_int]),
     ("epa_wait_results", C.c_int, [_vp]),
+    ("epa_wait_older_results", C.c_int, [_vp]),
     ("epa_encode_queries_dev", C.c_int, [_vp, _vp, C.c_uint32, C.c_int]),
     ("epa_preplace", C.c_int, [_vp]),
     ("epa_select", C.c_int, [_vp, C.POINTER(Options), C.POINTER(C.c_uint64)]),
@@ -86,6 +87,9 @@ SYMBOLS = [
     ("epa_last_lookup_ms", C.c_int, [_vp, C.POINTER(C.c_float)]),
     ("epa_num_pairs", C.c_int, [_vp, C.POINTER(C.c_uint64)]),
     ("epa_synchronize", C.c_int, [_vp]),
+    ("epa_measure_fp64_peak", C.c_int, [C.c_int, C.POINTER(C.c_double)]),
+    ("epa_pinned_alloc", C.c_int, [C.POINTER(_vp), C.c_size_t]),
+    ("epa_pinned_free", None, [_vp]),
     ("epa_launch_count", C.c_uint64, [_vp]),
     ("epa_last_error", C.c_char_p, [_vp]),
     ("epa_ctx_destroy", None, [_vp]),
@@ -116,6 +120,15 @@ def default_options(**kw) -> Options:
             raise AttributeError(k)
         setattr(o, k, v)
     return o
+
+
+def measure_fp64_peak(device=0) -> float:
+    """Measured DFMA throughput of the device in TFLOP/s (the thorough kernel's roofline denominator)."""
+    v = C.c_double()
+    rc = load().epa_measure_fp64_peak(device, C.byref(v))
+    if rc != 0:
+        raise EpaError(rc, "epa_measure_fp64_peak")
+    return v.value
 
 
 def _ptr(a, typ):

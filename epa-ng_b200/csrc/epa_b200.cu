@@ -914,6 +914,16 @@ extern "C" int epa_wait_results(epa_ctx * ctx)
   return EPA_OK;
 }
 
+// Deferred results: blocks until the records of the chunk BEFORE the most recent epa_collect /
+// epa_place_chunk have landed in host memory (that copy overlapped the most recent chunk's kernels).
+extern "C" int epa_wait_older_results(epa_ctx * ctx)
+{
+  if (!ctx) return EPA_ERR_ARG;
+  if (int rc = set_device(ctx)) return rc;
+  if (ctx->copy_stream) CU(cudaEventSynchronize(ctx->ev_d2h[ctx->out_flip]));
+  return EPA_OK;
+}
+
 extern "C" int epa_hint_next_chunk(epa_ctx * ctx, const char * next_seqs, uint32_t next_n_queries)
 {
   if (!ctx) return EPA_ERR_ARG;
@@ -1585,6 +1595,76 @@ extern "C" int epa_num_pairs(epa_ctx * ctx, uint64_t * n_pairs)
   if (!ctx || !n_pairs) return EPA_ERR_ARG;
   *n_pairs = ctx->n_pairs;
   return EPA_OK;
+}
+
+// ---- fp64 roofline denominator: dependent-chain-free DFMA stream, 16 warps per SM ----------------
+namespace {
+__global__ void __launch_bounds__(512)
+fp64_peak_kernel(double * out, int iters, double x, double y)
+{
+  double a[8];
+  #pragma unroll
+  for (int i = 0; i < 8; ++i) a[i] = threadIdx.x * 1e-3 + i;
+  #pragma unroll 1
+  for (int it = 0; it < iters; ++it)
+  {
+    #pragma unroll
+    for (int rep = 0; rep < 8; ++rep)
+      #pragma unroll
+      for (int i = 0; i < 8; ++i) a[i] = fma(a[i], x, y);
+  }
+  double s = 0.0;
+  #pragma unroll
+  for (int i = 0; i < 8; ++i) s += a[i];
+  out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+}  // namespace
+
+extern "C" int epa_measure_fp64_peak(int device, double * tflops)
+{
+  if (!tflops) return EPA_ERR_ARG;
+  *tflops = 0.0;
+  if (cudaSetDevice(device) != cudaSuccess) { (void) cudaGetLastError(); return EPA_ERR_CUDA; }
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { (void) cudaGetLastError(); return EPA_ERR_CUDA; }
+  const int blocks = prop.multiProcessorCount * 2, threads = 512, iters = 20000;
+  double * out = nullptr;
+  if (cudaMalloc(&out, (size_t) blocks * threads * sizeof(double)) != cudaSuccess) { (void) cudaGetLastError(); return EPA_ERR_NOMEM; }
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0); cudaEventCreate(&e1);
+  float best = 0.0f;
+  for (int rep = 0; rep < 4; ++rep)                 // first repetition warms up
+  {
+    cudaEventRecord(e0);
+    fp64_peak_kernel<<<blocks, threads>>>(out, iters, 1.0000001, 1e-9);
+    cudaEventRecord(e1);
+    cudaEventSynchronize(e1);
+    float ms = 0.0f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    if (rep > 0 && (best == 0.0f || ms < best)) best = ms;
+  }
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  cudaFree(out);
+  if (cudaGetLastError() != cudaSuccess || best <= 0.0f) return EPA_ERR_CUDA;
+  *tflops = 2.0 * (double) blocks * threads * iters * 64.0 / (best * 1e-3) / 1e12;
+  return EPA_OK;
+}
+
+extern "C" int epa_pinned_alloc(void ** ptr, size_t bytes)
+{
+  if (!ptr) return EPA_ERR_ARG;
+  *ptr = nullptr;
+  if (cudaHostAlloc(ptr, bytes ? bytes : 1, cudaHostAllocPortable) != cudaSuccess)
+  {
+    (void) cudaGetLastError();
+    return EPA_ERR_NOMEM;
+  }
+  return EPA_OK;
+}
+
+extern "C" void epa_pinned_free(void * ptr)
+{
+  if (ptr) (void) cudaFreeHost(ptr);
 }
 
 extern "C" int epa_synchronize(epa_ctx * ctx)

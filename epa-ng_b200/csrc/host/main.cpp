@@ -39,7 +39,10 @@ void usage()
       "  --filter-min INT [1]      --filter-max INT [7]      --precision INT [10]\n"
       "  -c,--bfast FILE           convert an aligned DNA FASTA file to the bfast format (into -w) and exit\n"
       "  --device INT              CUDA device [0]\n"
-      "  --redo, -T/--threads N, --verbose  accepted for compatibility\n"
+      "  --devices LIST            several GPUs of this box, e.g. 0,1,2,3 or 0-7: query chunks are handed out\n"
+      "                            in file order, one host thread per GPU, one shared reader and jplace writer\n"
+      "  -T, --threads N           host threads for reading, decoding and formatting [all]\n"
+      "  --redo, --verbose         accepted for compatibility\n"
       "  -v,--version\n");
 }
 
@@ -51,7 +54,8 @@ int main(int argc, char ** argv)
   epa_options opts;
   epa_options_default(&opts);
   uint32_t chunk = 0;
-  int precision = 10, device = 0, preserve_rooting = 1, rate_mode = 2, rate_bug = 1;
+  int precision = 10, device = 0, preserve_rooting = 1, rate_mode = 2, rate_bug = 1, host_threads = 0;
+  std::vector<int> devices;
   std::string invocation;
   for (int i = 0; i < argc; ++i) { invocation += argv[i]; invocation += ' '; }
 
@@ -81,7 +85,26 @@ int main(int argc, char ** argv)
     else if (a == "--filter-max") opts.filter_max = (uint32_t) std::atol(need(i));
     else if (a == "--precision") precision = std::atoi(need(i));
     else if (a == "--device") device = std::atoi(need(i));
-    else if (a == "-T" || a == "--threads" || a == "--tmp") (void) need(i);
+    else if (a == "--devices")
+    {
+      // "0,1,2" and ranges "0-7"
+      const std::string list = need(i);
+      devices.clear();
+      size_t pos = 0;
+      while (pos < list.size())
+      {
+        size_t end = list.find(',', pos);
+        if (end == std::string::npos) end = list.size();
+        const std::string item = list.substr(pos, end - pos);
+        const size_t dash = item.find('-');
+        if (dash != std::string::npos && dash > 0)
+          for (int d = std::atoi(item.substr(0, dash).c_str()); d <= std::atoi(item.substr(dash + 1).c_str()); ++d) devices.push_back(d);
+        else if (!item.empty()) devices.push_back(std::atoi(item.c_str()));
+        pos = end + 1;
+      }
+    }
+    else if (a == "-T" || a == "--threads") host_threads = std::atoi(need(i));
+    else if (a == "--tmp") (void) need(i);
     else if (a == "--redo" || a == "--verbose") {}
     else if (a == "--rate-scalers")
     {
@@ -106,8 +129,10 @@ int main(int argc, char ** argv)
   }
   if (tree.empty() || ref.empty() || query.empty()) { usage(); die("-t, -s and -q are required"); }
   if (epa_host_set_rate_scalers(rate_mode, rate_bug)) die(epa_host_last_error());
-  const int rc = epa_run_files_ex(tree.c_str(), ref.c_str(), query.c_str(), model.c_str(), outdir.c_str(), &opts, chunk,
-                                  precision, device, invocation.c_str(), preserve_rooting);
+  if (devices.empty()) devices.push_back(device);
+  const int rc = epa_run_files_multi(tree.c_str(), ref.c_str(), query.c_str(), model.c_str(), outdir.c_str(), &opts, chunk,
+                                     precision, devices.data(), (uint32_t) devices.size(), invocation.c_str(), preserve_rooting,
+                                     host_threads, nullptr);
   if (rc) die(epa_host_last_error());
   return 0;
 }

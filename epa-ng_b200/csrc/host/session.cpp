@@ -15,9 +15,11 @@
 #include <unordered_map>
 #include <vector>
 
+#include "fastio.hpp"
 #include "model.hpp"
 #include "seqio.hpp"
 #include "tree.hpp"
+#include "session_internal.hpp"
 
 using namespace epa_host;
 
@@ -33,16 +35,26 @@ int host_fail(int code, const std::string & msg)
 constexpr uint32_t kDefaultChunk = 131072;
 }  // namespace
 
-struct epa_session {
-  Tree tree;
-  Model model;
-  epa_ctx * ctx = nullptr;
-  uint32_t sites = 0;
-  std::string newick_cache;
-  int newick_precision = -1;
-  bool preserve_rooting = true;    // rooted input: report placements on the rooted tree
-  ~epa_session() { if (ctx) epa_ctx_destroy(ctx); }
-};
+namespace epa_host {
+int host_fail_msg(int code, const std::string & msg) { return host_fail(code, msg); }
+
+// JSON string escaping for names, the tree and the invocation line of the jplace
+void json_escape(std::string & out, const char * s, size_t n)
+{
+  for (size_t i = 0; i < n; ++i)
+  {
+    const unsigned char c = (unsigned char) s[i];
+    if (c == '"' || c == '\\') { out += '\\'; out += (char) c; }
+    else if (c < 0x20)
+    {
+      char buf[8];
+      std::snprintf(buf, sizeof buf, "\\u%04x", c);
+      out += buf;
+    }
+    else out += (char) c;
+  }
+}
+}  // namespace epa_host
 
 extern "C" const char * epa_host_last_error(void) { return g_host_error.c_str(); }
 
@@ -183,6 +195,7 @@ extern "C" int epa_session_place(epa_session * s, const char * query_rows, uint6
                                  uint32_t chunk_size, epa_placement * out, uint32_t * counts)
 {
   if (!s || !opts || (!query_rows && n_queries)) return host_fail(EPA_ERR_ARG, "null argument");
+  if ((out == nullptr) != (counts == nullptr)) return host_fail(EPA_ERR_ARG, "out and counts must both be given or both be NULL");
   if (chunk_size == 0) chunk_size = kDefaultChunk;
   if (!opts->prescoring)
   {
@@ -203,7 +216,7 @@ extern "C" int epa_session_place(epa_session * s, const char * query_rows, uint6
   std::vector<uint32_t> sizes;
   {
     uint64_t left = n_queries;
-    const uint32_t small = std::max<uint32_t>(4096u, chunk_size / 8);
+    const uint32_t small = std::min<uint32_t>(chunk_size, std::max<uint32_t>(4096u, chunk_size / 8));    // never above the cap
     if (left > (uint64_t) chunk_size + 2 * (uint64_t) small)
     {
       sizes.push_back(small); left -= small;
@@ -258,29 +271,45 @@ extern "C" int epa_session_is_rooted(const epa_session * s) { return s && s->tre
 // ----------------------------------------------------------------------------------------------
 //  jplace
 // ----------------------------------------------------------------------------------------------
+static void append_number(std::string & out, double v, int precision)
+{
+  char buf[400];
+  out.append(buf, format_fixed(buf, v, precision));
+}
+
 static void write_pquery(FILE * fh, const char * name, const epa_placement * recs, uint32_t count, int precision, bool last)
 {
-  std::fputs("    {\"p\": [\n", fh);
+  std::string out = "    {\"p\": [\n";
   for (uint32_t k = 0; k < count; ++k)
   {
     const epa_placement & p = recs[k];
-    std::fprintf(fh, "      [%llu, %.*f, %.*f, %.*f, %.*f]%s\n", (unsigned long long) p.branch_id, precision, p.likelihood,
-                 precision, p.lwr, precision, p.distal_length, precision, p.pendant_length, k + 1 < count ? "," : "");
+    out += "      [" + std::to_string((unsigned long long) p.branch_id) + ", ";
+    append_number(out, p.likelihood, precision); out += ", ";
+    append_number(out, p.lwr, precision); out += ", ";
+    append_number(out, p.distal_length, precision); out += ", ";
+    append_number(out, p.pendant_length, precision);
+    out += k + 1 < count ? "],\n" : "]\n";
   }
-  std::fputs("      ],\n", fh);
-  std::fprintf(fh, "    \"n\": [\"%s\"]\n", name);
-  std::fprintf(fh, "    }%s\n", last ? "" : ",");
+  out += "      ],\n    \"n\": [\"";
+  json_escape(out, name, std::strlen(name));
+  out += last ? "\"]\n    }\n" : "\"]\n    },\n";
+  std::fwrite(out.data(), 1, out.size(), fh);
 }
 
 static void jplace_begin(FILE * fh, const char * newick)
 {
-  std::fprintf(fh, "{\n  \"tree\": \"%s\",\n  \"placements\": \n  [\n", newick);
+  std::string out = "{\n  \"tree\": \"";
+  json_escape(out, newick, std::strlen(newick));
+  out += "\",\n  \"placements\": \n  [\n";
+  std::fwrite(out.data(), 1, out.size(), fh);
 }
 
 static void jplace_end(FILE * fh, const char * invocation)
 {
-  std::fprintf(fh, "  ],\n  \"metadata\": {\"invocation\": \"%s\"},\n  \"version\": 3,\n", invocation ? invocation : "");
-  std::fputs("  \"fields\": [\"edge_num\", \"likelihood\", \"like_weight_ratio\", \"distal_length\", \"pendant_length\"]\n}\n", fh);
+  std::string out = "  ],\n  \"metadata\": {\"invocation\": \"";
+  if (invocation) json_escape(out, invocation, std::strlen(invocation));
+  out += "\"},\n  \"version\": 3,\n  \"fields\": [\"edge_num\", \"likelihood\", \"like_weight_ratio\", \"distal_length\", \"pendant_length\"]\n}\n";
+  std::fwrite(out.data(), 1, out.size(), fh);
 }
 
 extern "C" int epa_write_jplace(const char * path, const char * numbered_newick, const char * invocation,
@@ -290,6 +319,7 @@ extern "C" int epa_write_jplace(const char * path, const char * numbered_newick,
   if (!path || !numbered_newick || !query_names || !recs || !counts) return host_fail(EPA_ERR_ARG, "null argument");
   FILE * fh = std::fopen(path, "w");
   if (!fh) return host_fail(EPA_ERR_ARG, std::string("cannot open ") + path);
+  if (precision > 18) precision = 18;
   jplace_begin(fh, numbered_newick);
   for (uint64_t q = 0; q < n_queries; ++q)
     write_pquery(fh, query_names[q], recs + q * stride, counts[q], precision, q + 1 == n_queries);
@@ -313,105 +343,9 @@ extern "C" int epa_run_files_ex(const char * tree_file, const char * ref_msa_fil
                                 const char * model, const char * outdir, const epa_options * opts, uint32_t chunk_size,
                                 int precision, int device, const char * invocation, int preserve_rooting)
 {
-  if (!tree_file || !ref_msa_file || !query_file || !model || !outdir || !opts) return host_fail(EPA_ERR_ARG, "null argument");
-  try
-  {
-    const auto t0 = std::chrono::steady_clock::now();
-    std::string dir = outdir;
-    if (dir.empty()) dir = ".";
-    if (dir.back() != '/') dir += '/';
-    ::mkdir(dir.c_str(), 0755);
-    std::ofstream log(dir + "epa_info.log");
-    auto info = [&](const std::string & line) { log << "INFO " << line << "\n"; std::printf("INFO %s\n", line.c_str()); };
-    info("Selected: Output dir: " + dir);
-    info(std::string("Selected: Query file: ") + query_file);
-    info(std::string("Selected: Tree file: ") + tree_file);
-    info(std::string("Selected: Reference MSA: ") + ref_msa_file);
-    info(std::string("Selected: Specified model: ") + model);
-    info("Selected: device cuda:" + std::to_string(device) + " (libepa_b200, sm_100a)");
-
-    std::ifstream tf(tree_file);
-    if (!tf) return host_fail(EPA_ERR_ARG, std::string("Cannot open file: ") + tree_file);
-    std::string newick((std::istreambuf_iterator<char>(tf)), std::istreambuf_iterator<char>());
-    Alignment ref = read_fasta(ref_msa_file);
-    Alignment qry = read_alignment(query_file);        // FASTA or the reference's bfast
-    if (ref.sites != qry.sites)
-      return host_fail(EPA_ERR_ARG, "reference and query MSA have different widths (" + std::to_string(ref.sites) + " vs " + std::to_string(qry.sites) + ")");
-    if (opts->premasking)
-    {
-      std::vector<uint8_t> mask = gap_mask(ref);
-      const std::vector<uint8_t> qmask = gap_mask(qry);
-      for (size_t i = 0; i < mask.size(); ++i) mask[i] |= qmask[i];
-      ref = apply_mask(ref, mask);
-      qry = apply_mask(qry, mask);
-    }
-    // -m takes a model string or a RAxML 8 info / raxml-ng bestModel / IQ-TREE report file (src/main.cpp:433-436)
-    std::string model_desc_str = model;
-    {
-      struct stat st;
-      if (stat(model, &st) == 0 && S_ISREG(st.st_mode))
-      {
-        model_desc_str = model_string_from_file(model);
-        info("Selected: Specified model file: " + std::string(model));
-        info("  ==> model " + model_desc_str);
-      }
-    }
-    model = model_desc_str.c_str();
-    const Model parsed = Model::parse(model);
-    info("Using model parameters:");
-    info(parsed.describe());
-
-    std::vector<const char *> names(ref.size());
-    for (size_t i = 0; i < ref.size(); ++i) names[i] = ref.names[i].c_str();
-    epa_session * s = nullptr;
-    int rc = epa_session_open(&s, newick.c_str(), (uint32_t) ref.size(), names.data(),
-                              reinterpret_cast<const char *>(ref.rows.data()), (uint32_t) ref.sites, model, device);
-    if (rc) return rc;
-    std::unique_ptr<epa_session> guard(s);
-    epa_session_set_preserve_rooting(s, preserve_rooting);
-    if (epa_session_is_rooted(s))
-      info(preserve_rooting ? "Selected: Preserving the root of the input tree" : "Selected: Unrooting the input tree");
-    double tree_logl = 0.0;
-    if (epa_session_tree_logl(s, &tree_logl) == EPA_OK)
-    {
-      char buf[96];
-      std::snprintf(buf, sizeof buf, "Reference tree log-likelihood: %.6f", tree_logl);
-      info(buf);
-    }
-
-    const std::string jpath = dir + "epa_result.jplace";
-    FILE * fh = std::fopen(jpath.c_str(), "w");
-    if (!fh) return host_fail(EPA_ERR_ARG, "cannot open " + jpath);
-    info("Output file: " + jpath);
-    jplace_begin(fh, epa_session_numbered_newick(s, precision));
-    if (chunk_size == 0) chunk_size = kDefaultChunk;
-    const auto t1 = std::chrono::steady_clock::now();
-    const uint64_t Q = qry.size();
-    std::vector<epa_placement> recs((size_t) std::min<uint64_t>(Q, chunk_size) * opts->filter_max);
-    std::vector<uint32_t> counts((size_t) std::min<uint64_t>(Q, chunk_size));
-    for (uint64_t done = 0; done < Q; done += chunk_size)
-    {
-      const uint64_t nq = std::min<uint64_t>(chunk_size, Q - done);
-      rc = epa_session_place(s, reinterpret_cast<const char *>(qry.row(done)), nq, opts, chunk_size, recs.data(), counts.data());
-      if (rc) { std::fclose(fh); return rc; }
-      for (uint64_t q = 0; q < nq; ++q)
-        write_pquery(fh, qry.names[done + q].c_str(), recs.data() + q * opts->filter_max, counts[q], precision, done + q + 1 == Q);
-      info(std::to_string(done + nq) + " Sequences done!");
-    }
-    jplace_end(fh, invocation);
-    std::fclose(fh);
-    const auto t2 = std::chrono::steady_clock::now();
-    char buf[96];
-    std::snprintf(buf, sizeof buf, "Time spent placing: %.3fs", std::chrono::duration<double>(t2 - t1).count());
-    info(buf);
-    std::snprintf(buf, sizeof buf, "Elapsed Time: %.3fs", std::chrono::duration<double>(t2 - t0).count());
-    info(buf);
-    return EPA_OK;
-  }
-  catch (const std::exception & e)
-  {
-    return host_fail(EPA_ERR_ARG, e.what());
-  }
+  // one device: the same reader / device / writer pipeline as the multi-GPU run (pipeline.cpp)
+  return epa_run_files_multi(tree_file, ref_msa_file, query_file, model, outdir, opts, chunk_size, precision, &device, 1,
+                             invocation, preserve_rooting, 0, nullptr);
 }
 
 // ----------------------------------------------------------------------------------------------
@@ -454,11 +388,51 @@ extern "C" int epa_host_read_alignment(const char * path, uint32_t * n_sequences
     {
       std::string all;
       for (const auto & nm : a.names) { all += nm; all += '\n'; }
-      std::snprintf(labels, labels_cap, "%s", all.c_str());
+      if (all.size() + 1 > labels_cap) return host_fail(EPA_ERR_ARG, "labels buffer too small: " + std::to_string(all.size() + 1) + " bytes needed");
+      std::memcpy(labels, all.c_str(), all.size() + 1);
     }
     return EPA_OK;
   }
   catch (const std::exception & e) { return host_fail(EPA_ERR_ARG, e.what()); }
+}
+
+extern "C" int epa_host_read_alignment_mt(const char * path, int threads, int want_mask, uint32_t * n_sequences, uint32_t * sites,
+                                          char * rows, size_t rows_cap, char * labels, size_t labels_cap, uint8_t * gap_mask_out)
+{
+  if (!path) return host_fail(EPA_ERR_ARG, "null argument");
+  try
+  {
+    const MappedFile file(path);
+    const QueryIndex idx = index_queries(file, path, threads, want_mask != 0);
+    if (n_sequences) *n_sequences = (uint32_t) idx.records.size();
+    if (sites) *sites = (uint32_t) idx.sites;
+    if (gap_mask_out) std::memcpy(gap_mask_out, idx.gap_mask.data(), idx.sites);
+    if (rows)
+    {
+      if (rows_cap < idx.records.size() * idx.sites) return host_fail(EPA_ERR_ARG, "rows buffer too small");
+      std::vector<uint32_t> keep(idx.sites);
+      for (size_t s = 0; s < idx.sites; ++s) keep[s] = (uint32_t) s;
+      decode_rows(idx, 0, idx.records.size(), keep, reinterpret_cast<uint8_t *>(rows), threads);
+    }
+    if (labels && labels_cap)
+    {
+      std::string all;
+      for (const auto & r : idx.records) { all.append(r.name, r.name_len); all += '\n'; }
+      if (all.size() + 1 > labels_cap) return host_fail(EPA_ERR_ARG, "labels buffer too small: " + std::to_string(all.size() + 1) + " bytes needed");
+      std::memcpy(labels, all.c_str(), all.size() + 1);
+    }
+    return EPA_OK;
+  }
+  catch (const std::exception & e) { return host_fail(EPA_ERR_ARG, e.what()); }
+}
+
+extern "C" int epa_host_format_fixed(double value, int precision, char * out, size_t cap)
+{
+  if (!out || cap < 400) return host_fail(EPA_ERR_ARG, "buffer of at least 400 bytes expected");
+  if (precision > 18) precision = 18;
+  const size_t n = format_fixed(out, value, precision);
+  out[n] = 0;
+  return (int) n;
 }
 
 extern "C" int epa_host_fasta_to_bfast(const char * fasta_path, const char * out_dir, char * out_path, size_t cap)

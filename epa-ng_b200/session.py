@@ -2,6 +2,7 @@
 from __future__ import annotations
 
 import ctypes as C
+import os
 
 import numpy as np
 
@@ -30,6 +31,12 @@ HOST_SYMBOLS = [
                                 C.c_uint32, C.c_int, C.c_int, C.c_char_p]),
     ("epa_run_files_ex", C.c_int, [C.c_char_p, C.c_char_p, C.c_char_p, C.c_char_p, C.c_char_p, C.POINTER(capi.Options),
                                    C.c_uint32, C.c_int, C.c_int, C.c_char_p, C.c_int]),
+    ("epa_run_files_multi", C.c_int, [C.c_char_p, C.c_char_p, C.c_char_p, C.c_char_p, C.c_char_p, C.POINTER(capi.Options),
+                                      C.c_uint32, C.c_int, C.POINTER(C.c_int), C.c_uint32, C.c_char_p, C.c_int, C.c_int, _vp]),
+    ("epa_host_release_pinned_pool", None, []),
+    ("epa_host_read_alignment_mt", C.c_int, [C.c_char_p, C.c_int, C.c_int, _u32p, _u32p, _vp, C.c_size_t, C.c_char_p,
+                                             C.c_size_t, _vp]),
+    ("epa_host_format_fixed", C.c_int, [C.c_double, C.c_int, C.c_char_p, C.c_size_t]),
     ("epa_host_map_rooted", C.c_int, [C.c_char_p, _u32p, C.POINTER(C.c_double), C.c_uint32, C.c_char_p, C.c_size_t]),
     ("epa_write_jplace", C.c_int, [C.c_char_p, C.c_char_p, C.c_char_p, C.POINTER(C.c_char_p), C.c_uint64, _vp, _u32p,
                                    C.c_uint32, C.c_int]),
@@ -137,15 +144,64 @@ def run_files(tree_file, ref_msa, query_file, model, outdir, opts=None, chunk_si
                                   int(preserve_rooting)))
 
 
+class RunStats(C.Structure):
+    """epa_run_stats (include/epa_b200_host.h)"""
+    _fields_ = [("n_queries", C.c_uint64), ("seconds_total", C.c_double), ("seconds_index", C.c_double),
+                ("seconds_setup", C.c_double), ("seconds_place", C.c_double), ("busy_read", C.c_double),
+                ("busy_write", C.c_double), ("busy_device_max", C.c_double)]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
+def run_files_multi(tree_file, ref_msa, query_file, model, outdir, devices=(0,), opts=None, chunk_size=0, precision=10,
+                    invocation="epa_run_files_multi", preserve_rooting=True, host_threads=0):
+    """Files -> jplace as a reader / device(s) / writer pipeline over the listed GPUs; returns the run's wall-clock stats."""
+    opts = opts or capi.default_options()
+    devs = (C.c_int * len(devices))(*devices)
+    st = RunStats()
+    _check(lib().epa_run_files_multi(tree_file.encode(), ref_msa.encode(), query_file.encode(), model.encode(),
+                                     outdir.encode(), C.byref(opts), chunk_size, precision, devs, len(devices),
+                                     invocation.encode(), int(preserve_rooting), host_threads, C.byref(st)))
+    return st.as_dict()
+
+
+def _label_cap(path):
+    # the labels cannot be longer than the file itself
+    return os.path.getsize(path) + 1024
+
+
 def read_alignment(path: str):
     """(names, uint8 rows [n][sites]) of a FASTA or bfast file, read by the host layer."""
     n, sites = C.c_uint32(), C.c_uint32()
     _check(lib().epa_host_read_alignment(path.encode(), C.byref(n), C.byref(sites), None, 0, None, 0))
     rows = np.zeros((n.value, sites.value), dtype=np.uint8)
-    labels = C.create_string_buffer(64 * n.value + 1024)
+    labels = C.create_string_buffer(_label_cap(path))
     _check(lib().epa_host_read_alignment(path.encode(), C.byref(n), C.byref(sites), rows.ctypes.data, rows.size, labels,
                                          len(labels)))
     return labels.value.decode().split("\n")[:n.value], rows
+
+
+def read_alignment_mt(path: str, threads=4, want_mask=True):
+    """The pipeline's reader (memory map + parallel index/decode): (names, rows, all-gap column mask)."""
+    n, sites = C.c_uint32(), C.c_uint32()
+    _check(lib().epa_host_read_alignment_mt(path.encode(), threads, int(want_mask), C.byref(n), C.byref(sites), None, 0,
+                                            None, 0, None))
+    rows = np.zeros((n.value, sites.value), dtype=np.uint8)
+    mask = np.zeros(sites.value, dtype=np.uint8)
+    labels = C.create_string_buffer(_label_cap(path))
+    _check(lib().epa_host_read_alignment_mt(path.encode(), threads, int(want_mask), C.byref(n), C.byref(sites),
+                                            rows.ctypes.data, rows.size, labels, len(labels), mask.ctypes.data))
+    return labels.value.decode().split("\n")[:n.value], rows, mask
+
+
+def format_fixed(value: float, precision: int) -> str:
+    """printf('%.*f') as the jplace writer formats it (no printf involved)."""
+    buf = C.create_string_buffer(512)
+    n = lib().epa_host_format_fixed(C.c_double(value), precision, buf, len(buf))
+    if n < 0:
+        raise capi.EpaError(n, "format_fixed")
+    return buf.raw[:n].decode()
 
 
 def fasta_to_bfast(fasta_path: str, out_dir: str) -> str:

@@ -194,6 +194,23 @@ def discrete_gamma_mean(alpha, k):
 
 
 def write_fasta(path, names, rows):
+    rows = np.asarray(rows)
+    if len(names) > 1000 and rows.ndim == 2 and len({len(n) for n in names[:1000]}) == 1 and len(names[0]) == len(names[-1]):
+        # equal-length names: one 2-D byte array, written in one call
+        L, n, w = len(names[0]), rows.shape[0], rows.shape[1]
+        try:
+            nm = np.frombuffer("".join(names).encode(), dtype=np.uint8).reshape(n, L)
+        except ValueError:
+            nm = None
+        if nm is not None:
+            out = np.empty((n, L + w + 3), dtype=np.uint8)
+            out[:, 0] = ord(">")
+            out[:, 1:1 + L] = nm
+            out[:, 1 + L] = ord("\n")
+            out[:, 2 + L:2 + L + w] = rows
+            out[:, 2 + L + w] = ord("\n")
+            out.tofile(path)
+            return
     with open(path, "wb") as fh:
         for nm, row in zip(names, rows):
             fh.write(b">" + nm.encode() + b"\n")

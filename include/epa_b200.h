@@ -170,6 +170,9 @@ int epa_hint_next_chunk(epa_ctx * ctx, const char * next_seqs, uint32_t next_n_q
  * src/io/jplace_writer.hpp:59-65). Default: off (results are in the host buffers on return). */
 int epa_set_deferred_results(epa_ctx * ctx, int on);
 int epa_wait_results(epa_ctx * ctx);
+/* With deferred results on: waits only for the records of the chunk before the most recent one (their copy
+ * ran under the most recent chunk's kernels), so a caller can hand chunk k - 1 on while k's copy is in flight. */
+int epa_wait_older_results(epa_ctx * ctx);
 /* Same for a chunk that already lives in device memory (seqs_dev = DEVICE pointer to
  * n_queries * sites ASCII bytes): used for device-resident timing and by callers that stage
  * the query file in HBM themselves. */
@@ -219,6 +222,12 @@ int epa_last_lookup_ms(epa_ctx * ctx, float * ms);
 int epa_num_pairs(epa_ctx * ctx, uint64_t * n_pairs);
 /* Blocks until all work queued on the context's stream has finished. */
 int epa_synchronize(epa_ctx * ctx);
+/* Measured fp64 FMA throughput of the device (TFLOP/s, 2 flops per DFMA lane): an unrolled stream of
+ * independent DFMAs on every SM. The roofline denominator of the fp64-bound thorough kernel. */
+int epa_measure_fp64_peak(int device, double * tflops);
+/* Page-locked host memory for query rows and result records (full PCIe speed, asynchronous copies). */
+int epa_pinned_alloc(void ** ptr, size_t bytes);
+void epa_pinned_free(void * ptr);
 /* Number of kernel launches issued on behalf of the ctx since creation. */
 uint64_t epa_launch_count(const epa_ctx * ctx);
 

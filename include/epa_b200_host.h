@@ -72,6 +72,34 @@ int epa_run_files_ex(const char * tree_file, const char * ref_msa_file, const ch
                      uint32_t chunk_size, int precision, int device, const char * invocation,
                      int preserve_rooting);
 
+/* The same run as a pipeline over several GPUs of the box (devices[n_devices], CUDA ordinals): one host
+ * thread and one reference state per GPU, query chunks handed out in file order, one reader stage
+ * (memory-mapped file, decoded by host threads into pinned memory) and one writer stage shared by all
+ * - what the reference does with MPI ranks over query blocks (src/net/epa_mpi_util.cpp:10-30) and its
+ * async chunk reader / jplace writer (src/seq/MSA_Stream.cpp:79-85, src/io/jplace_writer.hpp:58-132).
+ * host_threads <= 0 = all hardware threads. The jplace does not depend on n_devices or host_threads.
+ * stats (may be NULL) receives wall-clock figures of the run. */
+typedef struct {
+  uint64_t n_queries;
+  double seconds_total;      /* whole call */
+  double seconds_index;      /* tree + reference MSA read, query file indexed (first pass) */
+  double seconds_setup;      /* reference state on the device(s): context, CLVs, lookup tables */
+  double seconds_place;      /* pipeline: decode -> place -> format/write, from first chunk to closed file */
+  double busy_read;          /* time the reader stage spent decoding */
+  double busy_write;         /* time the writer stage spent formatting and writing */
+  double busy_device_max;    /* longest time a device thread spent inside epa_session_place */
+} epa_run_stats;
+
+int epa_run_files_multi(const char * tree_file, const char * ref_msa_file, const char * query_file,
+                        const char * model, const char * outdir, const epa_options * opts,
+                        uint32_t chunk_size, int precision, const int * devices, uint32_t n_devices,
+                        const char * invocation, int preserve_rooting, int host_threads,
+                        epa_run_stats * stats);
+
+/* epa_run_files* keep their page-locked staging blocks (up to (3 n_devices + 2) x chunk_size x (width + 284) bytes)
+ * for the next run in the same process; this gives them back to the system. */
+void epa_host_release_pinned_pool(void);
+
 /* Formats placement records as a jplace document (src/io/jplace_util.cpp:20-86) into `path`. */
 int epa_write_jplace(const char * path, const char * numbered_newick, const char * invocation,
                      const char * const * query_names, uint64_t n_queries, const epa_placement * recs,
@@ -86,6 +114,14 @@ int epa_host_parse_tree(const char * newick, int precision, char * out_newick, s
  * the sizes only. */
 int epa_host_read_alignment(const char * path, uint32_t * n_sequences, uint32_t * sites, char * rows, size_t rows_cap,
                             char * labels, size_t labels_cap);
+/* The reader of the files -> jplace pipeline: memory-mapped file, record index and all-gap column mask
+ * built by `threads` host threads, rows decoded in parallel (same results as epa_host_read_alignment).
+ * gap_mask_out (may be NULL) receives `sites` bytes, 1 = every sequence has one of "NOX.-?" there. */
+int epa_host_read_alignment_mt(const char * path, int threads, int want_mask, uint32_t * n_sequences, uint32_t * sites,
+                               char * rows, size_t rows_cap, char * labels, size_t labels_cap, uint8_t * gap_mask_out);
+/* printf("%.*f") digit for digit without printf (the jplace writer's number formatting); returns the
+ * length, out must hold 400 bytes. */
+int epa_host_format_fixed(double value, int precision, char * out, size_t cap);
 /* -c/--bfast of the reference (Binary_Fasta::fasta_to_bfast, src/io/Binary_Fasta.hpp:214-246, src/main.cpp:284-288):
  * converts an aligned DNA FASTA file to <out_dir>/<file name>.bfast; out_path (may be NULL) receives the path. */
 int epa_host_fasta_to_bfast(const char * fasta_path, const char * out_dir, char * out_path, size_t cap);

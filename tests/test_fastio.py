@@ -1,0 +1,89 @@
+"""CPU tests of the files -> jplace pipeline's host pieces (epa-ng_b200/csrc/host/fastio.cpp):
+the printf-exact fixed-point formatter and the memory-mapped, multi-threaded query reader."""
+import math
+import os
+import random
+import struct
+
+import numpy as np
+import pytest
+
+
+def test_format_fixed_matches_printf(built):
+    fmt = built.session.format_fixed
+    rng = random.Random(7)
+    vals = [0.0, -0.0, 1.0, -1.0, 0.5, 1.5, 2.5, 0.05, 0.15, 0.25, 0.35, 1e-10, 5e-11, 4.9999999999e-11, 1e-300, 5e-324,
+            0.1053605157, -5031.3339285153, 0.99999, 1.0 - 2 ** -53, 123456789.987654321, 999999999999999.0, 1e15, 1.7e308,
+            2 ** 52 + 0.5, 0.000000000049999999999999, 0.00000000005, 8.5, 9.5, 0.125, 0.375]
+    for _ in range(4000):
+        vals.append(rng.uniform(-1e4, 1e4))
+        vals.append(rng.uniform(0, 1))
+        vals.append(math.ldexp(rng.random(), rng.randint(-80, 45)))
+        # exact halves of the last printed digit
+        vals.append(rng.randint(0, 10 ** 6) / 8.0)
+        vals.append(struct.unpack("<d", struct.pack("<Q", rng.getrandbits(62)))[0])
+    for p in (0, 1, 3, 6, 10, 15, 18):
+        for v in vals:
+            assert fmt(v, p) == "%.*f" % (p, v), (v, p)
+
+
+def _write(path, text):
+    with open(path, "w", newline="") as fh:
+        fh.write(text)
+
+
+def test_parallel_reader_equals_serial_reader(built, tmp_path):
+    rng = np.random.default_rng(3)
+    n, sites = 777, 403
+    alphabet = np.frombuffer(b"ACGTacgtNn-?.RYKMSWBDHVOX", dtype=np.uint8)
+    rows = alphabet[rng.integers(0, len(alphabet), size=(n, sites))]
+    rows[:, 17] = ord("-")                  # all-gap columns
+    rows[:, 200] = ord("n")
+    rows[:, 402] = ord("?")
+    names = ["q%05d some description \"quoted\"" % i for i in range(n)]
+    # mixed line wrapping, CRLF, trailing blanks, blank lines
+    parts = []
+    for i in range(n):
+        seq = rows[i].tobytes().decode()
+        parts.append(">" + names[i] + (" \t" if i % 5 == 0 else "") + ("\r\n" if i % 3 == 0 else "\n"))
+        if i % 4 == 0:
+            parts.append(seq + "\n")
+        else:
+            wrap = 60 + (i % 7)
+            for k in range(0, sites, wrap):
+                parts.append(seq[k:k + wrap] + ("\r\n" if i % 3 == 0 else "\n"))
+        if i % 11 == 0:
+            parts.append("\n")
+    path = str(tmp_path / "q.fasta")
+    _write(path, "".join(parts))
+    names_s, rows_s = built.session.read_alignment(path)
+    for threads in (1, 3, 8):
+        names_p, rows_p, mask = built.session.read_alignment_mt(path, threads)
+        assert names_p == names_s == names
+        assert np.array_equal(rows_p, rows_s)
+        want = np.all(np.isin(rows_s, np.frombuffer(b"NOX.-?", dtype=np.uint8)), axis=0)
+        assert np.array_equal(mask.astype(bool), want)
+        assert mask[17] and mask[200] and mask[402]
+    # the same file as bfast (DNA codes only)
+    dna = np.frombuffer(b"-TGKCYSBAWRDMHVN", dtype=np.uint8)[rng.integers(0, 16, size=(50, 33))]
+    p2 = str(tmp_path / "d.fasta")
+    _write(p2, "".join(">s%d\n%s\n" % (i, dna[i].tobytes().decode()) for i in range(50)))
+    bf = built.session.fasta_to_bfast(p2, str(tmp_path))
+    nb, rb, mb = built.session.read_alignment_mt(bf, 4)
+    assert nb == ["s%d" % i for i in range(50)] and np.array_equal(rb, dna)
+    assert np.array_equal(mb.astype(bool), np.all(np.isin(dna, np.frombuffer(b"N-", dtype=np.uint8)), axis=0))
+
+
+def test_parallel_reader_errors(built, tmp_path):
+    p = str(tmp_path / "bad.fasta")
+    _write(p, ">a\nACGT\n>b\nACG\n")
+    with pytest.raises(built.capi.EpaError, match="equal size"):
+        built.session.read_alignment_mt(p, 2)
+    _write(p, "ACGT\n>a\nACGT\n")
+    with pytest.raises(built.capi.EpaError, match="before the first"):
+        built.session.read_alignment_mt(p, 2)
+    _write(p, "\n\n")
+    with pytest.raises(built.capi.EpaError, match="no sequences"):
+        built.session.read_alignment_mt(p, 2)
+    with pytest.raises(built.capi.EpaError, match="Cannot open"):
+        built.session.read_alignment_mt(str(tmp_path / "missing.fasta"), 2)
