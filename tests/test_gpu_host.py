@@ -130,3 +130,42 @@ def test_run_files_empirical_frequencies(built, tmp_path):
                                 g[key]["model"], out)
         got, _ = _read_jplace(os.path.join(out, "epa_result.jplace"))
         _check(got, g[key]["placements"], key)
+
+
+def test_pipeline_many_chunks_and_threads_give_the_same_file(built, tmp_path):
+    """epa_run_files_multi: the jplace does not depend on the chunk size, the number of host threads or
+    the number of GPUs (one host thread per device, chunks handed out in file order)."""
+    d = os.path.join(helpers.GOLDEN, "synth64")
+    model = "GTR{1/1/1/1/1/1}+FU{0.25/0.25/0.25/0.25}+G4{0.5}"
+    files = (os.path.join(d, "tree.nwk"), os.path.join(d, "ref.fasta"), os.path.join(d, "query.fasta"))
+    texts = {}
+    runs = {"one_chunk": dict(chunk_size=0, host_threads=1), "chunks_of_7": dict(chunk_size=7, host_threads=5),
+            "chunks_of_64": dict(chunk_size=64, host_threads=0)}
+    import torch
+    if torch.cuda.device_count() >= 2:
+        runs["two_gpus"] = dict(chunk_size=16, host_threads=4, devices=(0, 1))
+    for name, kw in runs.items():
+        out = str(tmp_path / name)
+        st = built.session.run_files_multi(*files, model, out, invocation="pipeline test", **kw)
+        assert st["n_queries"] == 200 and st["seconds_total"] > 0
+        texts[name] = open(os.path.join(out, "epa_result.jplace")).read()
+    first = texts["one_chunk"]
+    for name, t in texts.items():
+        assert t == first, name
+    got, doc = _read_jplace(os.path.join(str(tmp_path / "chunks_of_7"), "epa_result.jplace"))
+    _check(got, helpers.golden("synth64")["default"]["placements"], "pipeline")
+    assert [pq["n"][0] for pq in doc["placements"]] == sorted(got)          # input order kept
+    built.session.lib().epa_host_release_pinned_pool()
+
+
+def test_pipeline_reports_query_errors(built, tmp_path):
+    d = os.path.join(helpers.GOLDEN, "cfg1")
+    bad = str(tmp_path / "bad.fasta")
+    rows = open(os.path.join(d, "query.fasta")).read().replace("A", "!", 1)
+    open(bad, "w").write(rows)
+    with pytest.raises(built.capi.EpaError):
+        built.session.run_files_multi(os.path.join(d, "ref.tre"), os.path.join(d, "aln.fasta"), bad, helpers.GTRG, str(tmp_path / "o"))
+    with pytest.raises(built.capi.EpaError, match="different widths|equal size"):
+        short = str(tmp_path / "short.fasta")
+        open(short, "w").write(">x\nACGT\n")
+        built.session.run_files_multi(os.path.join(d, "ref.tre"), os.path.join(d, "aln.fasta"), short, helpers.GTRG, str(tmp_path / "o2"))
