@@ -82,11 +82,14 @@ class _BorrowedContext(capi.Context):
 class Session:
     """Reference tree + MSA + model resident on one GPU (mirrors the reference's Tree object)."""
 
-    def __init__(self, newick: str, names, ref_rows: np.ndarray, model: str, device: int = 0, states: int = 4,
-                 rate_cats: int = 4, rate_scalers: str = "auto", bugcompat_focus: bool = True):
+    def __init__(self, newick: str, names, ref_rows: np.ndarray, model: str, device: int = 0, states: int = 0,
+                 rate_cats: int = 0, rate_scalers: str = "auto", bugcompat_focus: bool = True):
         """rate_scalers: "off", "on" or "auto" (the reference's --rate-scalers; auto = on above 2000 tips);
         bugcompat_focus reproduces the reference's scaler window offset of the thorough phase."""
         L = lib()
+        if not states or not rate_cats:
+            pm = parse_model(model)                 # shapes of the staged inspection helpers (get_clv, ...)
+            states, rate_cats = pm["states"], pm["rate_cats"]
         _check(L.epa_host_set_rate_scalers({"off": 0, "on": 1, "auto": 2}[rate_scalers], int(bugcompat_focus)))
         ref_rows = np.ascontiguousarray(ref_rows, dtype=np.uint8)
         arr = (C.c_char_p * len(names))(*[n.encode() for n in names])
