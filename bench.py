@@ -37,6 +37,24 @@ T_TAXA, N_SITES, WINDOW = 1000, 1000, 200
 METRIC = "query-seqs/sec placed (1k-taxon tree)"
 HBM_FALLBACK_GBS = 6650.0
 
+# BASELINE.json configs[1..4]. `queries` = per GPU (weak) or in total (strong); `default_queries` bounds the
+# default run of the configurations whose full size takes minutes per step.
+CONFIGS = {
+    "cfg2": dict(T=1000, sites=1000, window=200, kind="dna", heur=True, scaling="weak", queries=1000000,
+                 what="cfg2: 1k-taxon DNA tree (GTR+G4, 1000-site MSA), synthetic 200bp window queries, "
+                      "preplacement heuristic -g 0.99999"),
+    "cfg3": dict(T=1000, sites=1000, window=200, kind="dna", heur=True, scaling="strong", queries=10000000,
+                 what="cfg3: 1k-taxon DNA tree (GTR+G4, 1000-site MSA), 10M synthetic 200bp window queries in total, "
+                      "preplacement heuristic on, block-sharded over the GPUs (strong scaling)"),
+    "cfg4": dict(T=512, sites=300, window=300, kind="aa", heur=True, scaling="weak", queries=100000,
+                 what="cfg4: 512-taxon amino-acid tree (LG+G4, 300-site MSA), full-length queries, 20-state path, "
+                      "preplacement heuristic on"),
+    "cfg5": dict(T=10000, sites=1000, window=200, kind="dna", heur=False, scaling="strong", queries=1000000,
+                 default_queries=2048,
+                 what="cfg5: 10k-taxon DNA tree (19 997 edges, per-rate scalers as the reference's auto mode), 200bp window "
+                      "queries, --no-heur (every edge evaluated thoroughly)"),
+}
+
 
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
@@ -52,7 +70,7 @@ def ref_binary():
     return os.path.join(ROOT, "oracle", "_ref", "epa-ng")
 
 
-def run_reference_sample(ds, n_sample, threads, keep_jplace=False):
+def run_reference_sample(ds, n_sample, threads, keep_jplace=False, extra=(), also=None):
     """Times the unmodified reference on the first n_sample queries. The fixed start-up cost
     (file parsing, reference CLV precompute) is removed by subtracting a 64-query run."""
     synth = ge.load_package().synth
@@ -61,17 +79,18 @@ def run_reference_sample(ds, n_sample, threads, keep_jplace=False):
         tf, sf, _ = synth.write_dataset(dict(ds, queries=ds["queries"][:1], qnames=ds["qnames"][:1]), tmp)
 
         def run(nq, sub):
-            qf = os.path.join(tmp, f"q_{sub}.fasta")
+            qf = os.path.join(tmp, "q_full.fasta" if sub == "full" else f"q_{sub}.fasta")
             synth.write_fasta(qf, ds["qnames"][:nq], ds["queries"][:nq])
             out = os.path.join(tmp, sub)
             os.makedirs(out, exist_ok=True)
-            cmd = [ref_binary(), "-t", tf, "-s", sf, "-q", qf, "-m", ds["model"], "-w", out, "-T", str(threads), "--redo"]
+            cmd = [ref_binary(), "-t", tf, "-s", sf, "-q", qf, "-m", ds["model"], "-w", out, "-T", str(threads), "--redo", *extra]
             t0 = time.perf_counter()
             subprocess.run(cmd, check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
             return time.perf_counter() - t0, os.path.join(out, "epa_result.jplace")
 
-        run(min(64, n_sample), "small")                      # page the binary and the files in
-        t_small, _ = run(min(64, n_sample), "small")
+        n_small = min(64, n_sample) if n_sample >= 256 else 1
+        run(n_small, "small")                                # page the binary and the files in
+        t_small, _ = run(n_small, "small")
         t_full, jp = run(n_sample, "full")
         if t_full <= t_small:
             t_small = 0.0
@@ -80,9 +99,21 @@ def run_reference_sample(ds, n_sample, threads, keep_jplace=False):
             doc = json.load(open(jp))
             placements = {n: pq["p"] for pq in doc["placements"] for n in pq["n"]}
         dt = max(t_full - t_small, 1e-6)
-        return (n_sample - min(64, n_sample)) / dt, t_full, t_small, placements
+        if also is not None:
+            # our arm on EXACTLY the same files (the column pre-mask depends on the query set)
+            placements = (placements, also(tf, sf, os.path.join(tmp, "q_full.fasta"), tmp))
+        return (n_sample - n_small) / dt, t_full, t_small, placements
     finally:
         shutil.rmtree(tmp, ignore_errors=True)
+
+
+def ref_sample_size(name, cores):
+    """Queries of the bounded CPU sample: about 10-30 s of the reference on `cores` host threads."""
+    if name in ("cfg2", "cfg3"):
+        return int(min(200000, max(4000, 1500 * cores)))
+    if name == "cfg4":
+        return int(min(20000, max(500, 100 * cores)))
+    return max(4, cores // 2)            # cfg5: ~2 s per query and core
 
 
 def reference_arm(args):
@@ -94,22 +125,26 @@ def reference_arm(args):
         return
     synth = ge.load_package().synth
     cores = os.cpu_count() or 1
-    n_sample = args.ref_queries or int(min(200000, max(4000, 1500 * cores)))
-    ds = synth.dataset(T=T_TAXA, n_sites=N_SITES, n_queries=n_sample, window=WINDOW)
+    cfg = CONFIGS[args.config]
+    n_sample = args.ref_queries or ref_sample_size(args.config, cores)
+    ds = synth.dataset(T=cfg["T"], n_sites=cfg["sites"], n_queries=n_sample, window=cfg["window"], kind=cfg["kind"])
+    extra = () if cfg["heur"] else ("--no-heur",)
+    if args.model:
+        ds["model"] = args.model
     vals, times = [], []
     for it in range(args.warmup + args.steps):
-        qps, t_full, t_small, _ = run_reference_sample(ds, n_sample, cores)
+        qps, t_full, t_small, _ = run_reference_sample(ds, n_sample, cores, extra=extra)
         if it >= args.warmup:
             vals.append(qps)
             times.append(t_full)
     v = float(np.median(vals))
-    sample = (f"first {n_sample} of the cfg2 queries, oracle/_ref/epa-ng -T {cores}, wall clock of the whole run minus "
+    sample = (f"first {n_sample} of the {args.config} queries, oracle/_ref/epa-ng -T {cores}, wall clock of the whole run minus "
               f"a 64-query run (start-up removed); median of {len(vals)} runs")
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": v, "unit": "query-seqs/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 * float(np.median(times)),
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": workload_config(n_sample, args.gpus),
+        "higher_is_better": True, "scaling": cfg["scaling"], "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload_config(n_sample, args.gpus, args.config, args.model),
         "cpu_baseline": {"value": v, "unit": "query-seqs/s", "cores": cores, "kind": "reference", "sample": sample},
         "e2e": {"value": v, "unit": "query-seqs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
@@ -169,13 +204,17 @@ def ncu_metric(kernel, metric):
     return None
 
 
-def workload_config(q_per_gpu, gpus):
-    return {"workload": "cfg2: 1k-taxon DNA tree (GTR+G4, 1000-site MSA), synthetic 200bp window queries, "
-                        "preplacement heuristic -g 0.99999",
-            "taxa": T_TAXA, "edges": 2 * T_TAXA - 3, "sites": N_SITES, "window": WINDOW,
-            "queries_per_gpu": q_per_gpu, "queries_total": q_per_gpu * gpus,
-            "sharding": f"queries block-sharded over {gpus} GPU(s), reference state replicated",
-            "l2": "inputs larger than L2 (no flush needed)"}
+def workload_config(q_per_gpu, gpus, name="cfg2", model=""):
+    c = CONFIGS[name]
+    out = {"workload": c["what"], "name": name, "model": model or ("LG+G4{0.8}" if c["kind"] == "aa" else "GTR{1/1/1/1/1/1}+FU{0.25/0.25/0.25/0.25}+G4{0.5}"),
+           "taxa": c["T"], "edges": 2 * c["T"] - 3, "sites": c["sites"], "window": c["window"],
+           "queries_per_gpu": q_per_gpu, "queries_total": q_per_gpu * gpus,
+           "sharding": f"queries block-sharded over {gpus} GPU(s), reference state replicated",
+           "l2": "inputs larger than L2 (no flush needed)"}
+    if q_per_gpu * gpus != c["queries"] and c["scaling"] == "strong":
+        out["bounded"] = (f"{q_per_gpu * gpus} of the configuration's {c['queries']} queries (throughput per query does not "
+                          f"depend on the count; pass --queries {c['queries'] // max(1, gpus)} for the full size)")
+    return out
 
 
 # ------------------------------------------------------------------------------------------------
@@ -219,6 +258,21 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------------
 #  files -> jplace through the C++ host pipeline (epa_run_files_multi)
 # ------------------------------------------------------------------------------------------------
+class quiet_stdout:
+    """The host layer logs to stdout like the reference does; bench.py prints one JSON line."""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self.devnull = os.open(os.devnull, os.O_WRONLY)
+        self.saved = os.dup(1)
+        os.dup2(self.devnull, 1)
+
+    def __exit__(self, *exc):
+        os.dup2(self.saved, 1)
+        os.close(self.saved)
+        os.close(self.devnull)
+
+
 def head_placements(jplace_path, n_first):
     """name -> placements of the first n_first pqueries of a (large) jplace file, without parsing all of it."""
     want = n_first
@@ -265,10 +319,7 @@ def files_leg(pkg, ds, n_files, devices, chunk, recs, counts, fmax):
                                          invocation="bench.py files leg")
             return time.perf_counter() - t0, st, os.path.join(out, "epa_result.jplace")
 
-        devnull = os.open(os.devnull, os.O_WRONLY)
-        saved = os.dup(1)
-        os.dup2(devnull, 1)                   # the host layer logs to stdout like the reference does
-        try:
+        with quiet_stdout():
             run(small, "warm")
             t_small, _, _ = run(small, "small")
             res = {}
@@ -279,10 +330,6 @@ def files_leg(pkg, ds, n_files, devices, chunk, recs, counts, fmax):
                              "value_startup_removed": (n_files - 64) / max(t - t_small, 1e-9),
                              "query_file_bytes": os.path.getsize(qfile), "jplace_bytes": os.path.getsize(jp), "stats": st}
                 res[kind]["jplace"] = jp
-        finally:
-            os.dup2(saved, 1)
-            os.close(saved)
-            os.close(devnull)
         same = subprocess.run(["cmp", "-s", res["fasta"]["jplace"], res["bfast"]["jplace"]]).returncode == 0
         n_cmp = min(20000, n_files) if recs is not None else 0
         got = head_placements(res["fasta"]["jplace"], n_cmp) if n_cmp else {}
@@ -332,15 +379,32 @@ def ours(args):
         dist.init_process_group("nccl", device_id=dev)
         cpu_group = dist.new_group(backend="gloo")       # host-side barrier around the single-process files leg
 
-    Q = args.queries
-    ds = synth.dataset(T=T_TAXA, n_sites=N_SITES, n_queries=Q, window=WINDOW, seed_q=2 + rank)
+    cfg = CONFIGS[args.config]
+    if args.queries:
+        Q = args.queries
+    elif cfg["scaling"] == "strong":
+        Q = -(-cfg.get("default_queries", cfg["queries"]) // world) if "default_queries" in cfg else -(-cfg["queries"] // world)
+    else:
+        Q = cfg["queries"]
+    # unique synthetic queries per rank (at most 1M are generated; larger counts repeat them)
+    Q_gen = min(Q, 1000000)
+    ds = synth.dataset(T=cfg["T"], n_sites=cfg["sites"], n_queries=Q_gen, window=cfg["window"], kind=cfg["kind"], seed_q=2 + rank)
+    if args.model:
+        # same data, another model string (e.g. a general GTR: three distinct eigenvalues, the general kernel variant)
+        ds["model"] = args.model
+    if Q > Q_gen:
+        reps = -(-Q // Q_gen)
+        ds["queries"] = np.tile(ds["queries"], (reps, 1))[:Q]
+        ds["qnames"] = ["q%08d" % i for i in range(Q)]
     sess = session.Session(ds["newick"], ds["names"], ds["ref"], ds["model"], device=local)
     ctx = sess.ctx
     stream = torch.cuda.current_stream()
     ctx.set_stream(stream.cuda_stream)
-    opts = capi.default_options()
+    opts = capi.default_options(prescoring=1 if cfg["heur"] else 0)
     fmax = opts.filter_max
     chunk = args.chunk
+    if not cfg["heur"]:
+        chunk = int(min(chunk, max(1, (1 << 28) // sess.n_edges)))      # all-pairs mode: the session's own clamp
     B, n = sess.n_edges, sess.sites
 
     host_q = torch.from_numpy(ds["queries"]).pin_memory()
@@ -357,7 +421,8 @@ def ours(args):
         for lo in range(0, Q, chunk):
             nq = min(chunk, Q - lo)
             ctx.encode_queries_dev(dev_q.data_ptr() + lo * n, nq, True)
-            ctx.preplace()
+            if cfg["heur"]:
+                ctx.preplace()
             npairs = ctx.select(opts)
             ctx.place_pairs(opts)
             ctx.collect_dev(opts, rec_dev.data_ptr() + lo * fmax * 40, cnt_dev.data_ptr() + lo * 4)
@@ -386,7 +451,8 @@ def ours(args):
             if lo + nq < Q:
                 ctx.hint_next_chunk(host_q.data_ptr() + (lo + nq) * n, min(chunk, Q - lo - nq))
             ctx.upload_queries_ptr(host_q.data_ptr() + lo * n, nq, True)
-            ctx.preplace()
+            if cfg["heur"]:
+                ctx.preplace()
             ctx.select(opts)
             ctx.place_pairs(opts)
             ctx.collect_dev(opts, rec_dev.data_ptr() + lo * fmax * 40, cnt_dev.data_ptr() + lo * 4)
@@ -437,7 +503,7 @@ def ours(args):
 
     # files -> jplace through the C++ pipeline, all GPUs of the job driven by rank 0's process
     files = None
-    if not args.no_files:
+    if not args.no_files and args.config in ("cfg2", "cfg3"):
         if cpu_group is not None:
             dist.barrier(group=cpu_group)
         if rank == 0:
@@ -452,12 +518,14 @@ def ours(args):
         e2e = total_q * args.steps / (ms_e2e / 1e3)
         peak, peak_src = peaks()
         pairs = pairs_total[0] / args.steps           # candidate pairs per step (this rank)
-        w = WINDOW
+        w = cfg["window"]
+        S = 4 if cfg["kind"] == "dna" else 20
+        sr = 4 if (cfg["kind"] == "dna" and cfg["T"] > 2000) else 1      # per-rate scalers above 2000 tips (reference auto mode)
         per_unit = {
             "preplace": 9.0 * w,                                   # w lookup doubles + w query bytes per (query, edge)
-            "thorough": 2.0 * w * 4 * 4 * 8 + 2.0 * w * 4 + w + 40,   # two CLV windows + scalers + query + record
+            "thorough": 2.0 * w * 4 * S * 8 + 2.0 * w * 4 * sr + w + 40,   # two CLV windows + scalers + query + record
         }
-        units = {"preplace": float(Q) * B, "thorough": pairs}
+        units = {"preplace": float(Q) * B if cfg["heur"] else 0.0, "thorough": pairs}
         kernels = {}
         for k in ("preplace", "thorough"):
             ms = stage_ms[k] / args.steps
@@ -466,17 +534,20 @@ def ours(args):
                           "achieved_gbs": ach, "frac": ach / peak}
         ctx.build_lookup()                 # re-run warm: the first build pays module loading
         lk_ms = ctx.lookup_ms()
-        kernels["lookup_build"] = {"ms": lk_ms, "units": B, "bytes_per_unit": 392000.0,
-                                   "achieved_gbs": B * 392000.0 / (lk_ms / 1e3) / 1e9 if lk_ms > 0 else 0.0}
+        K = 16 if S == 4 else 24
+        lk_bytes = 2.0 * n * 4 * S * 8 + 2.0 * n * 4 * sr + n * K * 8            # two CLVs + scalers in, table out
+        kernels["lookup_build"] = {"ms": lk_ms, "units": B, "bytes_per_unit": lk_bytes,
+                                   "achieved_gbs": B * lk_bytes / (lk_ms / 1e3) / 1e9 if lk_ms > 0 else 0.0}
         kernels["lookup_build"]["frac"] = kernels["lookup_build"]["achieved_gbs"] / peak
         for k in ("upload_encode", "select", "collect"):
             kernels[k] = {"ms_per_step": stage_ms[k] / args.steps}
         dom = max(("preplace", "thorough"), key=lambda k: kernels[k]["ms_per_step"])
-        kname = {"preplace": "preplace_mma_kernel", "thorough": "blo_site_kernel"}[dom]
+        kname = {"preplace": "preplace_mma_kernel" if S == 4 else "preplace_kernel",
+                 "thorough": "blo_site_kernel" if S == 4 else "blo_generic_kernel"}[dom]
         # the preplacement kernel is an exact u8 x u8 -> s32 digit GEMM on the tensor cores: useful integer
         # operations = 2 * queries * (edges * 6 digits) * (window * 4 one-hot columns)
         pre_ms = kernels["preplace"]["ms_per_step"]
-        if pre_ms > 0:
+        if pre_ms > 0 and S == 4:
             kernels["preplace"]["tensor"] = {
                 "kind": "tcgen05.mma kind::i8 (u8 x u8 -> s32), 128 x 192 x 32",
                 "useful_tops": 2.0 * Q * B * 6 * (4 * w) / (pre_ms / 1e3) / 1e12,
@@ -486,7 +557,7 @@ def ours(args):
                     "unit": "GB/s", "frac": kernels[dom]["frac"], "traffic": ncu_traffic(kname, Q, chunk), "peak_source": peak_src,
                     "launch_ms": kernels[dom]["ms_per_step"] / n_launch,
                     "algorithmic_bytes_per_launch": units[dom] * per_unit[dom] / n_launch}
-        if dom == "thorough":
+        if dom == "thorough" and S == 4:
             # the branch-length optimisation re-reads its CLV windows from L1/L2 for every pass and spends its
             # time in fp64 arithmetic: the HBM fraction is the contract's figure, the fp64 pipe is what limits it.
             # fp64 roofline: measured DFMA peak of this GPU (epa_measure_fp64_peak) against the kernel's executed fp64
@@ -505,17 +576,33 @@ def ours(args):
         parity = None
         if world == 1 and not args.no_cpu and os.path.exists(ref_binary()):
             cores = os.cpu_count() or 1
-            n_sample = int(min(Q, args.ref_queries or min(100000, max(2000, 1000 * cores))))
-            qps, t_full, t_small, ref_pl = run_reference_sample(ds, n_sample, cores, keep_jplace=True)
+            n_sample = int(min(Q, args.ref_queries or (min(100000, max(2000, 1000 * cores)) if args.config in ("cfg2", "cfg3")
+                                                        else ref_sample_size(args.config, cores))))
+            via_files = sr > 1      # per-rate scalers: the reference's scaler window offset depends on the column pre-mask
+
+            def ours_on_files(tf, sf, qf, tmp):
+                out_dir = os.path.join(tmp, "ours")
+                with quiet_stdout():
+                    session.run_files(tf, sf, qf, ds["model"], out_dir, opts)
+                doc = json.load(open(os.path.join(out_dir, "epa_result.jplace")))
+                return {nm: pq["p"] for pq in doc["placements"] for nm in pq["n"]}
+
+            qps, t_full, t_small, ref_pl = run_reference_sample(ds, n_sample, cores, keep_jplace=True,
+                                                                extra=() if cfg["heur"] else ("--no-heur",),
+                                                                also=ours_on_files if via_files else None)
             cpu = {"value": qps, "unit": "query-seqs/s", "cores": cores, "kind": "reference",
                    "sample": f"first {n_sample} of this run's queries, oracle/_ref/epa-ng -T {cores}: {t_full:.2f}s wall "
-                             f"minus {t_small:.2f}s for a 64-query run (start-up removed)"}
-            parity = compare_with_reference(rec_host.numpy(), cnt_host.numpy(), ds["qnames"], ref_pl, fmax)
+                             f"minus {t_small:.2f}s for a short run of the same files (start-up removed)"}
+            if via_files:
+                parity = compare_placement_dicts(ref_pl[1], ref_pl[0])
+                parity["note"] = "both arms on the same files (epa_run_files): the pre-mask depends on the query set"
+            else:
+                parity = compare_with_reference(rec_host.numpy(), cnt_host.numpy(), ds["qnames"], ref_pl, fmax)
 
         out = {
             "metric": METRIC, "value": value, "unit": "query-seqs/s", "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms_res / args.steps, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload_config(Q, world),
+            "warmup": args.warmup, "ms_per_step": ms_res / args.steps, "higher_is_better": True, "scaling": cfg["scaling"],
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload_config(Q, world, args.config, args.model),
             "e2e": {"value": e2e, "unit": "query-seqs/s", "ms_per_step": ms_e2e / args.steps,
                     "h2d_bytes_per_step": int(Q) * n, "d2h_bytes_per_step": int(Q) * (fmax * 40 + 4)},
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "kernels": kernels,
@@ -531,6 +618,23 @@ def ours(args):
     if world > 1:
         dist.destroy_process_group()
     sess.close()
+
+
+def compare_placement_dicts(got, want):
+    n_edges = n_bad = 0
+    worst = 0.0
+    for name, w in want.items():
+        g = got.get(name, [])
+        if [int(p[0]) for p in g] != [int(p[0]) for p in w]:
+            n_edges += 1
+            continue
+        for a, p in zip(g, w):
+            rel = abs(a[1] - p[1]) / abs(p[1])
+            worst = max(worst, rel)
+            if rel > 1e-6 or abs(a[2] - p[2]) > 1e-6 or abs(a[3] - p[3]) > 1e-4 or abs(a[4] - p[4]) > 1e-4:
+                n_bad += 1
+                break
+    return {"queries_compared": len(want), "edge_list_mismatches": n_edges, "value_mismatches": n_bad, "worst_logl_rel": worst}
 
 
 def compare_with_reference(recs, counts, names, ref_pl, fmax):
@@ -566,10 +670,12 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--queries", type=int, default=1000000, help="queries per GPU per step")
+    ap.add_argument("--config", default="cfg2", choices=sorted(CONFIGS), help="BASELINE.json configuration [cfg2]")
+    ap.add_argument("--queries", type=int, default=0, help="queries per GPU per step [the configuration's size]")
     ap.add_argument("--chunk", type=int, default=131072)
     ap.add_argument("--ref-queries", type=int, default=0, help="size of the CPU reference sample")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--model", default="", help="place under this model string instead of the configuration's")
     ap.add_argument("--no-files", action="store_true", help="skip the files -> jplace leg")
     ap.add_argument("--files-queries", type=int, default=0, help="queries of the files -> jplace leg [min(Q, 2M)]")
     args = ap.parse_args()

@@ -1261,19 +1261,20 @@ int launch_site_kernel(epa_ctx * ctx, const BloSiteArgs & sa, unsigned grid, int
     return EPA_OK;
   }
 #endif
-  // models with equal non-zero eigenvalues (JC, F81, K80, ...): merged sumtable components
-  if constexpr (!PR && !INV)
+  // models with equal non-zero eigenvalues (JC, F81, K80, every model at the reference's default rates, ...):
+  // merged sumtable components (per-site and per-rate scalers; the +I and --raxml-blo variants keep three)
+  if constexpr (!INV)
   {
     if (ctx->hm.ngroups == 1)
     {
-      CU(cudaFuncSetAttribute(blo_site_kernel<R, GS, false, false, false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
-      blo_site_kernel<R, GS, false, false, false, 1><<<grid, warps * 32, smem, ctx->stream>>>(sa);
+      CU(cudaFuncSetAttribute(blo_site_kernel<R, GS, PR, false, false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+      blo_site_kernel<R, GS, PR, false, false, 1><<<grid, warps * 32, smem, ctx->stream>>>(sa);
       return EPA_OK;
     }
     if (ctx->hm.ngroups == 2)
     {
-      CU(cudaFuncSetAttribute(blo_site_kernel<R, GS, false, false, false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
-      blo_site_kernel<R, GS, false, false, false, 2><<<grid, warps * 32, smem, ctx->stream>>>(sa);
+      CU(cudaFuncSetAttribute(blo_site_kernel<R, GS, PR, false, false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+      blo_site_kernel<R, GS, PR, false, false, 2><<<grid, warps * 32, smem, ctx->stream>>>(sa);
       return EPA_OK;
     }
   }
@@ -1313,7 +1314,7 @@ int launch_blo_site(epa_ctx * ctx, BloArgs & a)
   // the windows fit 8 rows of 32 sites, the others in shared memory
   const size_t fix = (size_t) SiteWarpSmem<R>::SUM * sizeof(double);
   // eigenvalue groups only in the default variant (launch_site_kernel)
-  const int G = (pr || inv || a.raxml) ? 3 : ctx->hm.ngroups;
+  const int G = (inv || a.raxml) ? 3 : ctx->hm.ngroups;
   const size_t rows = (size_t) ((wmax + 31) & ~31) * site_row_pad(G * R) * sizeof(double);
   const size_t budget = ctx->smem_optin - 2048;
   const int max_warps = SITE_MAX_WARPS;
