@@ -73,6 +73,7 @@ SYMBOLS = [
     ("epa_wait_older_results", C.c_int, [_vp]),
     ("epa_encode_queries_dev", C.c_int, [_vp, _vp, C.c_uint32, C.c_int]),
     ("epa_preplace", C.c_int, [_vp]),
+    ("epa_hint_selection", C.c_int, [_vp, C.POINTER(Options)]),
     ("epa_select", C.c_int, [_vp, C.POINTER(Options), C.POINTER(C.c_uint64)]),
     ("epa_place_pairs", C.c_int, [_vp, C.POINTER(Options)]),
     ("epa_collect", C.c_int, [_vp, C.POINTER(Options), _vp, _u32p]),
@@ -240,6 +241,10 @@ class Context:
     def encode_queries_dev(self, dev_ptr, nq, premasking=True):
         self.nq = nq
         self._check(self.lib.epa_encode_queries_dev(self.handle, dev_ptr, nq, int(premasking)))
+
+    def hint_selection(self, opts):
+        """Announces the options of the next select(): the preplacement may then select in its epilogue."""
+        self._check(self.lib.epa_hint_selection(self.handle, C.byref(opts) if opts is not None else None))
 
     def preplace(self):
         self._check(self.lib.epa_preplace(self.handle))

@@ -90,7 +90,14 @@ struct epa_ctx {
   uint64_t n_pairs = 0;
   size_t pre_stride = 0;
   DevBuf raw, codes, begin, span, sortkey, perm, hist, range, pre, cnt, cutv, cuti, off, pair_q, pair_e,
-         edge_hist, edge_off, work, res, out_rec, out_cnt, scratch, tmp, qmax, cand, scan_sums;
+         edge_hist, edge_off, work, res, out_rec, out_cnt, scratch, tmp, qmax, cand, scan_sums, summary, over_list, range2;
+  // candidate selection fused into the tensor-core preplacement (dynamic heuristic): announced by
+  // epa_hint_selection before epa_preplace; the [query][edge] score matrix is then not written
+  bool sel_hint = false;
+  int sel_hint_mode = 0;
+  double sel_hint_thresh = 0.0;
+  bool fused = false;              // the last epa_preplace ran the fused kernel on perm[0, fused_n)
+  uint32_t fused_n = 0;
   // host -> device prefetch of the NEXT chunk on a second stream (epa_hint_next_chunk)
   cudaStream_t copy_stream = nullptr;
   cudaEvent_t ev_copy = nullptr;
@@ -114,6 +121,7 @@ struct epa_ctx {
     int gs_below = 6;          // EPA_B200_BLO_GS_BELOW: resident warps below which the global-scratch variant runs
     int gs_warps = 8;          // EPA_B200_GS_WARPS: warps per CTA of the global-scratch variant
     int site_warps = 0;        // EPA_B200_SITE_WARPS: cap on the warps per CTA of the lane = site kernel (0 = none)
+    bool no_fused = false;     // EPA_B200_NO_FUSED_SELECT: always materialise the prescore matrix
   } sw;
   int * d_flags = nullptr;              // [0..1] error, [2] max tile width, [3] max span
   unsigned long long * d_counter = nullptr;
@@ -350,6 +358,7 @@ extern "C" int epa_ctx_create(epa_ctx ** out, int device, const epa_model_desc *
   if (const char * v = getenv("EPA_B200_BLO_GS_BELOW")) ctx->sw.gs_below = atoi(v);
   if (const char * v = getenv("EPA_B200_GS_WARPS")) ctx->sw.gs_warps = std::max(1, std::min(12, atoi(v)));
   if (const char * v = getenv("EPA_B200_SITE_WARPS")) ctx->sw.site_warps = atoi(v);
+  ctx->sw.no_fused = getenv("EPA_B200_NO_FUSED_SELECT") != nullptr;
   DevModel & m = ctx->hm;
   memset(&m, 0, sizeof m);
   const int S = (int) model->states, R = (int) model->rate_cats;
@@ -1034,20 +1043,41 @@ int launch_preplace_pair(epa_ctx * ctx, uint32_t count, const int2 * range, int 
   return EPA_OK;
 }
 
-// DNA tensor-core kernel over perm[0, count): tiles of MMA_TQ queries, persistent CTAs
-int launch_preplace_mma(epa_ctx * ctx, uint32_t count, const int2 * range)
+// DNA tensor-core kernel over perm[0, count): tiles of MMA_TQ queries, persistent CTAs. fused = the
+// epilogue keeps the selection summaries instead of writing scores (kernels_preplace_mma.cuh).
+int launch_preplace_mma(epa_ctx * ctx, const uint32_t * perm, uint32_t count, const int2 * range, bool fused)
 {
   PreMmaArgs a{};
   a.btab = ctx->d_btab; a.pn = ctx->d_pn; a.kc_total = mma_kc_total(ctx->n); a.n = ctx->n;
   a.n_edges = ctx->n_edges; a.n_eb = (ctx->n_edges + MMA_EB - 1) / MMA_EB;
   a.codes = ctx->codes.as<uint8_t>(); a.begin = ctx->begin.as<int>(); a.span = ctx->span.as<int>();
-  a.perm = ctx->perm.as<uint32_t>(); a.nq = count; a.range = range;
+  a.perm = perm; a.nq = count; a.range = range;
   a.n_tiles = (count + MMA_TQ - 1) / MMA_TQ;
-  a.pre = ctx->pre.as<double>(); a.pre_stride = ctx->pre_stride; a.qmax = ctx->qmax.as<double>();
-  CU(cudaFuncSetAttribute(preplace_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) MMA_SMEM_BYTES));
+  a.pre = fused ? nullptr : ctx->pre.as<double>(); a.pre_stride = ctx->pre_stride; a.qmax = fused ? nullptr : ctx->qmax.as<double>();
+  a.summary = fused ? ctx->summary.as<RowSummary>() : nullptr;
   const unsigned grid = (unsigned) std::min<uint32_t>((uint32_t) ctx->sm_count, a.n_tiles);
-  preplace_mma_kernel<<<grid, MMA_THREADS, MMA_SMEM_BYTES, ctx->stream>>>(a);
+  if (fused)
+  {
+    CU(cudaFuncSetAttribute(preplace_mma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) MMA_SMEM_BYTES));
+    preplace_mma_kernel<true><<<grid, MMA_THREADS, MMA_SMEM_BYTES, ctx->stream>>>(a);
+  }
+  else
+  {
+    CU(cudaFuncSetAttribute(preplace_mma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) MMA_SMEM_BYTES));
+    preplace_mma_kernel<false><<<grid, MMA_THREADS, MMA_SMEM_BYTES, ctx->stream>>>(a);
+  }
   LAUNCHED(ctx);
+  return EPA_OK;
+}
+
+// the [query][edge] score matrix and the row maxima (not needed while every query takes the fused kernel)
+int ensure_prescores(epa_ctx * ctx)
+{
+  const uint32_t nq = ctx->nq;
+  const bool fresh = (size_t) nq * ctx->pre_stride * sizeof(double) > ctx->pre.cap || nq * sizeof(double) > ctx->qmax.cap;
+  CU(ctx->pre.ensure((size_t) nq * ctx->pre_stride * sizeof(double)));
+  CU(ctx->qmax.ensure(nq * sizeof(double)));
+  (void) fresh;
   return EPA_OK;
 }
 }  // namespace
@@ -1060,11 +1090,9 @@ extern "C" int epa_preplace(epa_ctx * ctx)
   if (ctx->stage < ST_QUERIES) return fail(ctx, EPA_ERR_STATE, "no queries uploaded");
   const uint32_t nq = ctx->nq;
   ctx->pre_stride = (ctx->n_edges + 3u) & ~3u;
+  ctx->fused = false; ctx->fused_n = 0;
   if (nq == 0) { ctx->stage = ST_PREPLACED; return EPA_OK; }
-  CU(ctx->pre.ensure((size_t) nq * ctx->pre_stride * sizeof(double)));
-  CU(ctx->qmax.ensure(nq * sizeof(double)));
   CU(cudaEventRecord(ctx->ev[1], ctx->stream));
-  CU(cudaMemsetAsync(ctx->qmax.p, 0xff, nq * sizeof(double), ctx->stream));      // NaN = no row maximum recorded
   // simple DNA queries (sorted first) take the tensor-core kernel (the pair-table kernel when the
   // digit table could not be built); the rest take the per-site kernel
   const uint32_t nA = ctx->S == 4 ? ctx->n_simple : 0u, nB = nq - nA;
@@ -1073,6 +1101,16 @@ extern "C" int epa_preplace(epa_ctx * ctx)
   CU(ctx->range.ensure((size_t) (std::max(tilesA, tilesM) + tilesB) * sizeof(int2)));
   int2 * rangeB = ctx->range.as<int2>() + std::max(tilesA, tilesM);
   const bool use_mma = ctx->mma_ok && nA > 0;
+  // fused selection: dynamic heuristic announced, single-scan selection exact (see epa_select), tensor-core path
+  const bool fuse = use_mma && ctx->sel_hint && ctx->sel_hint_mode == 0 && !ctx->sw.no_fused &&
+                    (1.0 - ctx->sel_hint_thresh) > 4.0 * (double) ctx->n_edges * std::exp(-SEL_CUT);
+  ctx->sel_hint = false;                       // a hint covers one epa_preplace
+  if (!fuse || nB)
+  {
+    if (int rc = ensure_prescores(ctx)) return rc;
+    CU(cudaMemsetAsync(ctx->qmax.p, 0xff, nq * sizeof(double), ctx->stream));      // NaN = no row maximum recorded
+  }
+  if (fuse) CU(ctx->summary.ensure((size_t) nq * 2 * sizeof(RowSummary)));
   int flags[8];
   if (use_mma)
   {
@@ -1098,7 +1136,8 @@ extern "C" int epa_preplace(epa_ctx * ctx)
     if (int rc = read_flags(ctx, flags)) return rc;
   if (nA && use_mma)
   {
-    if (int rc = launch_preplace_mma(ctx, nA, ctx->range.as<int2>())) return rc;
+    if (int rc = launch_preplace_mma(ctx, ctx->perm.as<uint32_t>(), nA, ctx->range.as<int2>(), fuse)) return rc;
+    ctx->fused = fuse; ctx->fused_n = fuse ? nA : 0;
   }
   else if (nA)
     if (int rc = launch_preplace_pair(ctx, nA, ctx->range.as<int2>(), std::max(8, flags[2]))) return rc;
@@ -1114,10 +1153,21 @@ extern "C" int epa_preplace(epa_ctx * ctx)
   return EPA_OK;
 }
 
+// Announces the options of the epa_select that will follow the next epa_preplace: with the dynamic heuristic
+// the tensor-core kernel then selects in its epilogue and never writes the score matrix.
+extern "C" int epa_hint_selection(epa_ctx * ctx, const epa_options * opts)
+{
+  if (!ctx) return EPA_ERR_ARG;
+  ctx->sel_hint = opts != nullptr && opts->prescoring != 0;
+  if (ctx->sel_hint) { ctx->sel_hint_mode = opts->heuristic; ctx->sel_hint_thresh = opts->prescoring_threshold; }
+  return EPA_OK;
+}
+
 extern "C" int epa_get_prescores(epa_ctx * ctx, double * out)
 {
   if (!ctx || !out) return EPA_ERR_ARG;
   if (ctx->stage < ST_PREPLACED) return fail(ctx, EPA_ERR_STATE, "epa_preplace has not run");
+  if (ctx->fused) return fail(ctx, EPA_ERR_STATE, "the scores were not materialised: epa_preplace ran with a selection hint");
   if (int rc = set_device(ctx)) return rc;
   if (ctx->nq == 0) return EPA_OK;
   CU(cudaStreamSynchronize(ctx->stream));
@@ -1162,11 +1212,64 @@ extern "C" int epa_select(epa_ctx * ctx, const epa_options * opts, uint64_t * n_
       if (nkeys > 0x7fffffffull) return fail(ctx, EPA_ERR_ARG, "tree x alignment too large for the work-list sort");
       CU(ctx->edge_hist.ensure((nkeys + 1) * sizeof(uint32_t)));
       const unsigned blocks = (nq + 7) / 8;
-      select_count_kernel<<<blocks, 256, 0, ctx->stream>>>(ctx->pre.as<double>(), ctx->pre_stride, (int) B, nq,
-                                                           opts->heuristic, opts->prescoring_threshold, fast_ok,
-                                                           ctx->qmax.as<double>(), ctx->cnt.as<uint32_t>(),
-                                                           ctx->cutv.as<double>(), ctx->cuti.as<int>(), ctx->cand.as<uint32_t>());
-      LAUNCHED(ctx);
+      if (ctx->fused && (opts->heuristic != ctx->sel_hint_mode || opts->prescoring_threshold != ctx->sel_hint_thresh))
+      {
+        // other options than announced: materialise the scores after all
+        ctx->sel_hint = false;
+        if (int rc = epa_preplace(ctx)) return rc;
+        CU(cudaEventRecord(ctx->ev[2], ctx->stream));
+      }
+      if (ctx->fused)
+      {
+        // 1. queries of the fused kernel: selection from the epilogue summaries
+        const uint32_t nA = ctx->fused_n;
+        CU(ctx->over_list.ensure((size_t) nA * sizeof(uint32_t)));
+        uint32_t * d_nover = reinterpret_cast<uint32_t *>(ctx->d_flags + 6);
+        CU(cudaMemsetAsync(d_nover, 0, sizeof(uint32_t), ctx->stream));
+        select_finish_kernel<<<(nA + 255) / 256, 256, 0, ctx->stream>>>(ctx->summary.as<RowSummary>(), ctx->perm.as<uint32_t>(), nA,
+                                                                        opts->prescoring_threshold, ctx->cnt.as<uint32_t>(),
+                                                                        ctx->cand.as<uint32_t>(), ctx->over_list.as<uint32_t>(), d_nover);
+        LAUNCHED(ctx);
+        uint32_t n_over = 0;
+        CU(cudaMemcpyAsync(&n_over, d_nover, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+        // 2. the ones it left over (long candidate lists, multi-pass tiles): unfused kernels on that list
+        if (n_over)
+        {
+          if (int rc = ensure_prescores(ctx)) return rc;
+          const uint32_t tiles = (n_over + MMA_TQ - 1) / MMA_TQ;
+          CU(ctx->range2.ensure((size_t) tiles * sizeof(int2)));
+          CU(cudaMemsetAsync(ctx->d_flags + 7, 0, sizeof(int), ctx->stream));
+          tile_range_kernel<<<(tiles + 7) / 8, 256, 0, ctx->stream>>>(ctx->over_list.as<uint32_t>(), ctx->begin.as<int>(), ctx->span.as<int>(),
+                                                                    n_over, MMA_TQ, tiles, 4, ctx->range2.as<int2>(), ctx->d_flags + 7);
+          LAUNCHED(ctx);
+          if (int rc = launch_preplace_mma(ctx, ctx->over_list.as<uint32_t>(), n_over, ctx->range2.as<int2>(), false)) return rc;
+          select_count_kernel<<<(n_over + 7) / 8, 256, 0, ctx->stream>>>(ctx->pre.as<double>(), ctx->pre_stride, (int) B, n_over,
+                                                                         opts->heuristic, opts->prescoring_threshold, fast_ok,
+                                                                         ctx->qmax.as<double>(), ctx->cnt.as<uint32_t>(),
+                                                                         ctx->cutv.as<double>(), ctx->cuti.as<int>(), ctx->cand.as<uint32_t>(),
+                                                                         ctx->over_list.as<uint32_t>());
+          LAUNCHED(ctx);
+        }
+        // 3. queries that never took the tensor-core kernel (other ambiguity codes): their rows exist
+        if (nq > nA)
+        {
+          select_count_kernel<<<(nq - nA + 7) / 8, 256, 0, ctx->stream>>>(ctx->pre.as<double>(), ctx->pre_stride, (int) B, nq - nA,
+                                                                          opts->heuristic, opts->prescoring_threshold, fast_ok,
+                                                                          ctx->qmax.as<double>(), ctx->cnt.as<uint32_t>(),
+                                                                          ctx->cutv.as<double>(), ctx->cuti.as<int>(), ctx->cand.as<uint32_t>(),
+                                                                          ctx->perm.as<uint32_t>() + nA);
+          LAUNCHED(ctx);
+        }
+      }
+      else
+      {
+        select_count_kernel<<<blocks, 256, 0, ctx->stream>>>(ctx->pre.as<double>(), ctx->pre_stride, (int) B, nq,
+                                                             opts->heuristic, opts->prescoring_threshold, fast_ok,
+                                                             ctx->qmax.as<double>(), ctx->cnt.as<uint32_t>(),
+                                                             ctx->cutv.as<double>(), ctx->cuti.as<int>(), ctx->cand.as<uint32_t>());
+        LAUNCHED(ctx);
+      }
       if (int rc = launch_exclusive_scan(ctx, ctx->cnt.as<uint32_t>(), ctx->off.as<uint32_t>(), nq, ctx->d_total)) return rc;
       uint64_t total = 0;
       CU(cudaMemcpyAsync(&total, ctx->d_total, sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
@@ -1543,7 +1646,10 @@ extern "C" int epa_place_chunk(epa_ctx * ctx, const char * seqs, uint32_t n_quer
     if (int rc = epa_build_lookup(ctx)) return rc;
   if (int rc = epa_upload_queries(ctx, seqs, n_queries, opts->premasking)) return rc;
   if (opts->prescoring)
+  {
+    epa_hint_selection(ctx, opts);
     if (int rc = epa_preplace(ctx)) return rc;
+  }
   if (int rc = epa_select(ctx, opts, nullptr)) return rc;
   if (int rc = epa_place_pairs(ctx, opts)) return rc;
   return epa_collect(ctx, opts, out, out_counts);

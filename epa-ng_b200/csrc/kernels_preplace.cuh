@@ -6,6 +6,7 @@
 //   LWR + candidate choice src/set_manipulators.cpp:43-69,90-113, src/core/heuristics.hpp:40-64
 #pragma once
 #include "common.cuh"
+#include "kernels_preplace_mma.cuh"     // RowSummary (fused selection)
 
 namespace epa {
 
@@ -546,7 +547,8 @@ constexpr int SEL_LIST = 64;         // near-best entries a warp keeps while it 
 __global__ void __launch_bounds__(256)
 select_count_kernel(const double * __restrict__ pre, size_t pre_stride, int n_edges, uint32_t nq, int mode,
                     double thresh, int fast_ok, const double * __restrict__ qmax, uint32_t * __restrict__ cnt,
-                    double * __restrict__ cut_v, int * __restrict__ cut_i, uint32_t * __restrict__ cand)
+                    double * __restrict__ cut_v, int * __restrict__ cut_i, uint32_t * __restrict__ cand,
+                    const uint32_t * __restrict__ qlist = nullptr)
 {
   // mode 0: dynamic  - accumulated LWR threshold (until_accumulated_reached, set_manipulators.cpp:90-113)
   // mode 1: fixed    - the best ceil(thresh * edges) (until_top_percent, set_manipulators.cpp:82-88)
@@ -554,9 +556,11 @@ select_count_kernel(const double * __restrict__ pre, size_t pre_stride, int n_ed
   //                    more (baseball_heuristic, src/core/heuristics.hpp:74-117)
   __shared__ double lv[8][SEL_LIST];
   __shared__ int li[8][SEL_LIST];
-  const uint32_t q = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  // qlist: the warps work through the listed queries (the ones the fused epilogue selection left over)
+  const uint32_t wq = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-  if (q >= nq) return;
+  if (wq >= nq) return;
+  const uint32_t q = qlist ? qlist[wq] : wq;
   const double * row = pre + (size_t) q * pre_stride;
   double mx = qmax ? qmax[q] : NAN;
   if (mx != mx)
@@ -684,6 +688,57 @@ select_count_kernel(const double * __restrict__ pre, size_t pre_stride, int n_ed
     ++c;
   }
   if (lane == 0) { cnt[q] = c; cut_v[q] = pv; cut_i[q] = pi; cand[(size_t) q * SEL_CAP] = 0xffffffffu; }
+}
+
+// Selection from the epilogue summaries of the fused tensor-core kernel (RowSummary, kernels_preplace_mma.cuh):
+// one thread per query merges its two half-row summaries and accumulates best-first exactly like the
+// fast path above. A selection that would need more than SUM_K candidates, or a tile the fused kernel
+// skipped (m = NaN), goes to over_list: those queries take the unfused kernels.
+__global__ void __launch_bounds__(256)
+select_finish_kernel(const RowSummary * __restrict__ summary, const uint32_t * __restrict__ perm, uint32_t n_fused,
+                     double thresh, uint32_t * __restrict__ cnt, uint32_t * __restrict__ cand,
+                     uint32_t * __restrict__ over_list, uint32_t * __restrict__ n_over)
+{
+  const uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
+  if (slot >= n_fused) return;
+  const uint32_t q = perm[slot];
+  const RowSummary a = summary[2 * (size_t) q], b = summary[2 * (size_t) q + 1];
+  bool over = (a.m != a.m) || (b.m != b.m);
+  uint32_t chosen[SUM_K];
+  uint32_t c = 0;
+  if (!over)
+  {
+    const double m = fmax(a.m, b.m);
+    const double tot = (a.S > 0.0 ? a.S * exp(a.m - m) : 0.0) + (b.S > 0.0 ? b.S * exp(b.m - m) : 0.0);
+    int ia = 0, ib = 0;
+    double acc = 0.0;
+    while (acc < thresh)
+    {
+      if (c == SUM_K) { over = true; break; }          // the next best is not guaranteed to be in the lists
+      const bool ha = ia < SUM_K && a.e[ia] != 0xffffffffu, hb = ib < SUM_K && b.e[ib] != 0xffffffffu;
+      if (!ha && !hb) { over = true; break; }          // (trees with fewer than 2 x SUM_K edges)
+      bool take_a = ha;
+      if (ha && hb) take_a = ranks_before(a.v[ia], (int) a.e[ia], b.v[ib], (int) b.e[ib]);
+      const double v = take_a ? a.v[ia] : b.v[ib];
+      chosen[c++] = take_a ? a.e[ia] : b.e[ib];
+      if (take_a) ++ia; else ++ib;
+      acc += exp(v - m) / tot;
+    }
+  }
+  if (over)
+  {
+    cnt[q] = 0;
+    cand[(size_t) q * SEL_CAP] = 0xffffffffu;
+    over_list[atomicAdd(n_over, 1u)] = q;
+    return;
+  }
+  // staged candidates: ascending edge order
+  #pragma unroll
+  for (int i = 1; i < SUM_K; ++i)
+    for (int j = i; j > 0; --j)
+      if ((uint32_t) j < c && chosen[j] < chosen[j - 1]) { const uint32_t t = chosen[j]; chosen[j] = chosen[j - 1]; chosen[j - 1] = t; }
+  for (uint32_t i = 0; i < c; ++i) cand[(size_t) q * SEL_CAP + i] = chosen[i];
+  cnt[q] = c;
 }
 
 // Pass 2 (fill): pair list in query-major order, edges ascending inside a query. Queries whose

@@ -189,6 +189,21 @@ struct PreMmaArgs {
   double * pre;
   size_t pre_stride;
   double * qmax;               // [query] row maximum (read by the candidate selection)
+  struct RowSummary * summary; // FUSED kernel: [query][2 halves], instead of pre / qmax
+};
+
+// Candidate selection fused into the epilogue (dynamic heuristic): an epilogue thread sees the scores of
+// its query on half of the edges, in ascending edge order, and keeps what the selection needs of them -
+// the running maximum m, S = sum exp(score - m) over everything within 60 of m (rescaled when m rises),
+// and the best SUM_K scores with their edges (value descending, lower edge first among equals). The
+// [query][edge] score matrix is never written. The global k-th best score, k <= SUM_K, is among the two
+// halves' lists, so a selection that ends within SUM_K candidates is exact; longer ones are flagged and
+// take the unfused kernels (select_finish_kernel, kernels_preplace.cuh).
+constexpr int SUM_K = 4;
+struct RowSummary {
+  double m, S;
+  double v[SUM_K];
+  uint32_t e[SUM_K];
 };
 
 // instruction descriptor (UMMA::InstrDescriptor): D = s32, A = B = unsigned 8 bit, both K-major
@@ -197,6 +212,7 @@ __host__ __device__ constexpr uint32_t mma_idesc_i8()
   return (2u << 4) | (0u << 7) | (0u << 10) | ((uint32_t) (MMA_N >> 3) << 17) | ((uint32_t) (MMA_TQ >> 4) << 24);
 }
 
+template <bool FUSED>
 __global__ void __launch_bounds__(MMA_THREADS, 1)
 preplace_mma_kernel(PreMmaArgs a)
 {
@@ -235,6 +251,21 @@ preplace_mma_kernel(PreMmaArgs a)
     const int2 rg = a.range[tile];
     const int nkc_all = (rg.y - rg.x + 3) >> 2;                          // K chunks that hold real sites
     const int n_pass = max(1, (nkc_all + MMA_KC_MAX - 1) / MMA_KC_MAX);  // windows wider than the A tile: K is split
+    if (FUSED && n_pass > 1)
+    {
+      // the fused epilogue needs final scores: such a tile is flagged (m = NaN) and redone by the unfused kernel
+      if (tid < MMA_TQ)
+      {
+        const uint32_t slot = tile * MMA_TQ + tid;
+        if (slot < a.nq)
+        {
+          const uint32_t q = a.perm[slot];
+          a.summary[2 * (size_t) q].m = NAN;
+          a.summary[2 * (size_t) q + 1].m = NAN;
+        }
+      }
+      continue;
+    }
     if (tid < MMA_TQ)
     {
       const uint32_t slot = tile * MMA_TQ + tid;
@@ -342,6 +373,10 @@ preplace_mma_kernel(PreMmaArgs a)
       double * out = a.pre + (size_t) (q == 0xffffffffu ? 0u : q) * a.pre_stride + half * 16;
       uint32_t bi = blk_it;
       double rmax = -INFINITY;     // only the last pass sees final scores
+      // fused selection state of this (query, half)
+      double fm = -INFINITY, fS = 0.0;
+      double fv0 = -INFINITY, fv1 = -INFINITY, fv2 = -INFINITY, fv3 = -INFINITY;
+      uint32_t fe0 = 0xffffffffu, fe1 = 0xffffffffu, fe2 = 0xffffffffu, fe3 = 0xffffffffu;
       // A block is drained in two steps of 8 branches (48 accumulator columns). The prefix-sum rows
       // of a step are requested one step ahead into one of two register buffers (raw values: the
       // subtraction waits until they are used, so the loads stay in flight behind the tensor work).
@@ -386,7 +421,38 @@ preplace_mma_kernel(PreMmaArgs a)
           const double base = (j & 1) == 0 ? b.hi[j / 2].x - b.lo[j / 2].x : b.hi[j / 2].y - b.lo[j / 2].y;
           res[j] = base - (double) sum * (1.0 / (double) (1ull << MMA_FRAC));
         }
-        if (q != 0xffffffffu)
+        if constexpr (FUSED)
+        {
+          // edges beyond the tree score -inf: they add nothing and never enter the list
+          double lm = -INFINITY;
+          #pragma unroll
+          for (int j = 0; j < 8; ++j)
+          {
+            if (e0 + j >= a.n_edges) res[j] = -INFINITY;
+            lm = fmax(lm, res[j]);
+          }
+          if (lm > fm)
+          {
+            fS = fm == -INFINITY ? 0.0 : fS * exp(fm - lm);
+            fm = lm;
+          }
+          #pragma unroll
+          for (int j = 0; j < 8; ++j)
+          {
+            const double x = res[j];
+            if (x - fm > -60.0) fS += exp(x - fm);
+            if (x > fv3)
+            {
+              // insert behind every entry that is >= x (edges arrive in ascending order: lower edge first among equals)
+              const uint32_t e = e0 + j;
+              if (x > fv0) { fv3 = fv2; fe3 = fe2; fv2 = fv1; fe2 = fe1; fv1 = fv0; fe1 = fe0; fv0 = x; fe0 = e; }
+              else if (x > fv1) { fv3 = fv2; fe3 = fe2; fv2 = fv1; fe2 = fe1; fv1 = x; fe1 = e; }
+              else if (x > fv2) { fv3 = fv2; fe3 = fe2; fv2 = x; fe2 = e; }
+              else { fv3 = x; fe3 = e; }
+            }
+          }
+        }
+        else if (q != 0xffffffffu)
         {
           #pragma unroll
           for (int j = 0; j < 8; j += 4)
@@ -437,12 +503,23 @@ preplace_mma_kernel(PreMmaArgs a)
           finish(bufB, v0, v1, e0 + 8, out + (size_t) eb * MMA_EB + 8);
         }
       }
-      row_max[half][r] = rmax;
+      if constexpr (FUSED)
+      {
+        if (q != 0xffffffffu)
+        {
+          RowSummary & o = a.summary[2 * (size_t) q + half];
+          o.m = fm; o.S = fS;
+          o.v[0] = fv0; o.v[1] = fv1; o.v[2] = fv2; o.v[3] = fv3;
+          o.e[0] = fe0; o.e[1] = fe1; o.e[2] = fe2; o.e[3] = fe3;
+        }
+      }
+      else
+        row_max[half][r] = rmax;
     }
     stage_it += a.n_eb * (uint32_t) n_ks;
     blk_it += a.n_eb;
     __syncthreads();           // the epilogue of the last block implies every MMA of the pass is done
-    if (last_pass && tid < MMA_TQ && row_q[tid] != 0xffffffffu) a.qmax[row_q[tid]] = fmax(row_max[0][tid], row_max[1][tid]);
+    if (!FUSED && last_pass && tid < MMA_TQ && row_q[tid] != 0xffffffffu) a.qmax[row_q[tid]] = fmax(row_max[0][tid], row_max[1][tid]);
    }
   }
 
