@@ -422,6 +422,7 @@ def ours(args):
             nq = min(chunk, Q - lo)
             ctx.encode_queries_dev(dev_q.data_ptr() + lo * n, nq, True)
             if cfg["heur"]:
+                ctx.hint_selection(opts)        # dynamic heuristic: candidates are selected in the preplacement epilogue
                 ctx.preplace()
             npairs = ctx.select(opts)
             ctx.place_pairs(opts)
@@ -452,6 +453,7 @@ def ours(args):
                 ctx.hint_next_chunk(host_q.data_ptr() + (lo + nq) * n, min(chunk, Q - lo - nq))
             ctx.upload_queries_ptr(host_q.data_ptr() + lo * n, nq, True)
             if cfg["heur"]:
+                ctx.hint_selection(opts)
                 ctx.preplace()
             ctx.select(opts)
             ctx.place_pairs(opts)

@@ -121,7 +121,9 @@ struct epa_ctx {
     int gs_below = 6;          // EPA_B200_BLO_GS_BELOW: resident warps below which the global-scratch variant runs
     int gs_warps = 8;          // EPA_B200_GS_WARPS: warps per CTA of the global-scratch variant
     int site_warps = 0;        // EPA_B200_SITE_WARPS: cap on the warps per CTA of the lane = site kernel (0 = none)
-    bool no_fused = false;     // EPA_B200_NO_FUSED_SELECT: always materialise the prescore matrix
+    bool fused_select = false; // EPA_B200_FUSED_SELECT: candidate selection in the tensor-core epilogue (measured slower: the
+                               // rare per-query events - a new list entry, a term near the running maximum - happen in
+                               // some lane of almost every epilogue step; off unless requested)
   } sw;
   int * d_flags = nullptr;              // [0..1] error, [2] max tile width, [3] max span
   unsigned long long * d_counter = nullptr;
@@ -358,7 +360,7 @@ extern "C" int epa_ctx_create(epa_ctx ** out, int device, const epa_model_desc *
   if (const char * v = getenv("EPA_B200_BLO_GS_BELOW")) ctx->sw.gs_below = atoi(v);
   if (const char * v = getenv("EPA_B200_GS_WARPS")) ctx->sw.gs_warps = std::max(1, std::min(12, atoi(v)));
   if (const char * v = getenv("EPA_B200_SITE_WARPS")) ctx->sw.site_warps = atoi(v);
-  ctx->sw.no_fused = getenv("EPA_B200_NO_FUSED_SELECT") != nullptr;
+  ctx->sw.fused_select = getenv("EPA_B200_FUSED_SELECT") != nullptr;
   DevModel & m = ctx->hm;
   memset(&m, 0, sizeof m);
   const int S = (int) model->states, R = (int) model->rate_cats;
@@ -1102,7 +1104,7 @@ extern "C" int epa_preplace(epa_ctx * ctx)
   int2 * rangeB = ctx->range.as<int2>() + std::max(tilesA, tilesM);
   const bool use_mma = ctx->mma_ok && nA > 0;
   // fused selection: dynamic heuristic announced, single-scan selection exact (see epa_select), tensor-core path
-  const bool fuse = use_mma && ctx->sel_hint && ctx->sel_hint_mode == 0 && !ctx->sw.no_fused &&
+  const bool fuse = use_mma && ctx->sel_hint && ctx->sel_hint_mode == 0 && ctx->sw.fused_select &&
                     (1.0 - ctx->sel_hint_thresh) > 4.0 * (double) ctx->n_edges * std::exp(-SEL_CUT);
   ctx->sel_hint = false;                       // a hint covers one epa_preplace
   if (!fuse || nB)
@@ -1233,6 +1235,7 @@ extern "C" int epa_select(epa_ctx * ctx, const epa_options * opts, uint64_t * n_
         uint32_t n_over = 0;
         CU(cudaMemcpyAsync(&n_over, d_nover, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
         CU(cudaStreamSynchronize(ctx->stream));
+        if (getenv("EPA_B200_DEBUG_FUSED")) fprintf(stderr, "[fused] %u of %u queries left over\n", n_over, nA);
         // 2. the ones it left over (long candidate lists, multi-pass tiles): unfused kernels on that list
         if (n_over)
         {

@@ -199,7 +199,7 @@ struct PreMmaArgs {
 // [query][edge] score matrix is never written. The global k-th best score, k <= SUM_K, is among the two
 // halves' lists, so a selection that ends within SUM_K candidates is exact; longer ones are flagged and
 // take the unfused kernels (select_finish_kernel, kernels_preplace.cuh).
-constexpr int SUM_K = 4;
+constexpr int SUM_K = 8;
 struct RowSummary {
   double m, S;
   double v[SUM_K];
@@ -375,8 +375,10 @@ preplace_mma_kernel(PreMmaArgs a)
       double rmax = -INFINITY;     // only the last pass sees final scores
       // fused selection state of this (query, half)
       double fm = -INFINITY, fS = 0.0;
-      double fv0 = -INFINITY, fv1 = -INFINITY, fv2 = -INFINITY, fv3 = -INFINITY;
-      uint32_t fe0 = 0xffffffffu, fe1 = 0xffffffffu, fe2 = 0xffffffffu, fe3 = 0xffffffffu;
+      double fv[SUM_K];
+      uint32_t fe[SUM_K];
+      #pragma unroll
+      for (int k = 0; k < SUM_K; ++k) { fv[k] = -INFINITY; fe[k] = 0xffffffffu; }
       // A block is drained in two steps of 8 branches (48 accumulator columns). The prefix-sum rows
       // of a step are requested one step ahead into one of two register buffers (raw values: the
       // subtraction waits until they are used, so the loads stay in flight behind the tensor work).
@@ -436,19 +438,36 @@ preplace_mma_kernel(PreMmaArgs a)
             fS = fm == -INFINITY ? 0.0 : fS * exp(fm - lm);
             fm = lm;
           }
-          #pragma unroll
-          for (int j = 0; j < 8; ++j)
+          // most groups lie far below the running maximum and below the list: one test skips them
+          if (lm - fm > -60.0)
           {
-            const double x = res[j];
-            if (x - fm > -60.0) fS += exp(x - fm);
-            if (x > fv3)
+            #pragma unroll
+            for (int j = 0; j < 8; ++j)
             {
-              // insert behind every entry that is >= x (edges arrive in ascending order: lower edge first among equals)
-              const uint32_t e = e0 + j;
-              if (x > fv0) { fv3 = fv2; fe3 = fe2; fv2 = fv1; fe2 = fe1; fv1 = fv0; fe1 = fe0; fv0 = x; fe0 = e; }
-              else if (x > fv1) { fv3 = fv2; fe3 = fe2; fv2 = fv1; fe2 = fe1; fv1 = x; fe1 = e; }
-              else if (x > fv2) { fv3 = fv2; fe3 = fe2; fv2 = x; fe2 = e; }
-              else { fv3 = x; fe3 = e; }
+              const double d = res[j] - fm;
+              // a term within 30 of the final maximum is within 30 of the running one: those get the double
+              // exponential; the rest weigh less than 1e-13 of the sum, where single precision is exact enough
+              if (d > -30.0) fS += exp(d);
+              else if (d > -60.0) fS += (double) __expf((float) d);
+            }
+          }
+          if (lm > fv[SUM_K - 1])
+          {
+            #pragma unroll
+            for (int j = 0; j < 8; ++j)
+            {
+              if (res[j] > fv[SUM_K - 1])
+              {
+                // bubble up behind every entry that is >= the new one (edges arrive ascending: lower edge first among equals)
+                fv[SUM_K - 1] = res[j]; fe[SUM_K - 1] = e0 + j;
+                #pragma unroll
+                for (int k = SUM_K - 1; k > 0; --k)
+                  if (fv[k] > fv[k - 1])
+                  {
+                    const double tv = fv[k]; fv[k] = fv[k - 1]; fv[k - 1] = tv;
+                    const uint32_t te = fe[k]; fe[k] = fe[k - 1]; fe[k - 1] = te;
+                  }
+              }
             }
           }
         }
@@ -509,8 +528,8 @@ preplace_mma_kernel(PreMmaArgs a)
         {
           RowSummary & o = a.summary[2 * (size_t) q + half];
           o.m = fm; o.S = fS;
-          o.v[0] = fv0; o.v[1] = fv1; o.v[2] = fv2; o.v[3] = fv3;
-          o.e[0] = fe0; o.e[1] = fe1; o.e[2] = fe2; o.e[3] = fe3;
+          #pragma unroll
+          for (int k = 0; k < SUM_K; ++k) { o.v[k] = fv[k]; o.e[k] = fe[k]; }
         }
       }
       else

@@ -179,10 +179,12 @@ int epa_wait_older_results(epa_ctx * ctx);
 int epa_encode_queries_dev(epa_ctx * ctx, const char * seqs_dev, uint32_t n_queries, int premasking);
 /* HOT LOOP A: pre[q][b] for all queries x all edges (Lookup_Store::sum_precomputed_sitelk). */
 int epa_preplace(epa_ctx * ctx);
-/* Optional, before epa_preplace: the options the following epa_select will be called with. With the dynamic
- * heuristic (-g) the tensor-core preplacement then selects the candidates in its epilogue and never writes the
- * [query][edge] score matrix (epa_get_prescores is refused for that chunk; epa_place_chunk does this itself).
- * The hint covers one epa_preplace; an epa_select with other options re-runs the preplacement unfused. */
+/* Optional, before epa_preplace: the options the following epa_select will be called with. In a context created
+ * with EPA_B200_FUSED_SELECT set in the environment, the tensor-core preplacement then selects the candidates of the
+ * dynamic heuristic (-g) in its epilogue and never writes the [query][edge] score matrix (epa_get_prescores is
+ * refused for that chunk). The hint covers one epa_preplace; an epa_select with other options re-runs the
+ * preplacement unfused. Measured slower than the two-kernel path on B200, hence opt-in;
+ * without the switch the hint is accepted and ignored. */
 int epa_hint_selection(epa_ctx * ctx, const epa_options * opts);
 /* Candidate selection -> (query, edge) work list; n_pairs receives its size. With
  * opts->prescoring == 0 the list is all queries x all edges. */

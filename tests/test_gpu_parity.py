@@ -383,6 +383,50 @@ def test_dense_chunk_tensor_core_preplace_matches_oracle(dense, built):
     ctx2.close()
 
 
+def test_fused_epilogue_selection_equals_the_two_kernel_path(dense, built):
+    """The tensor-core preplacement selecting in its epilogue (epa_hint_selection: running maximum, rescaled sum of
+    exponentials and the best eight scores of each half row, no score matrix) against the unfused path (score
+    matrix + select_count): identical pair lists, for a sharp threshold and for one that makes many queries
+    overflow the in-register lists and take the unfused kernels."""
+    case, ctx0 = dense
+    import os
+    os.environ["EPA_B200_FUSED_SELECT"] = "1"          # opt-in path (read at context creation)
+    try:
+        ctx = helpers.make_context(case)
+        ctx.build_lookup()
+    finally:
+        del os.environ["EPA_B200_FUSED_SELECT"]
+    for thresh in (0.99999, 0.9999999999):
+        opts = built.capi.default_options(prescoring_threshold=thresh)
+        ctx0.upload_queries(case.query_rows)
+        ctx0.hint_selection(opts)                       # ignored without the switch
+        ctx0.preplace()
+        ctx0.get_prescores()
+        n0 = ctx0.select(opts)
+        q0, e0, _ = ctx0.get_pairs(raw=False)
+        ctx.upload_queries(case.query_rows)
+        ctx.hint_selection(opts)
+        ctx.preplace()
+        with pytest.raises(built.capi.EpaError, match="not materialised"):
+            ctx.get_prescores()
+        n1 = ctx.select(opts)
+        q1, e1, _ = ctx.get_pairs(raw=False)
+        assert n0 == n1 and np.array_equal(q0, q1) and np.array_equal(e0, e1), thresh
+        per_query = np.bincount(q1, minlength=len(case.qseqs))
+        if thresh > 0.999999:
+            assert (per_query > 8).any(), "no query needed more than eight candidates: the left-over path did not run"
+        # a select with other options than announced falls back to the unfused kernels
+        ctx.upload_queries(case.query_rows)
+        ctx.hint_selection(opts)
+        ctx.preplace()
+        other = built.capi.default_options(heuristic=1, prescoring_threshold=0.1)
+        n2 = ctx.select(other)
+        ctx.upload_queries(case.query_rows)
+        ctx.preplace()
+        assert ctx.select(other) == n2
+    ctx.close()
+
+
 def test_dense_chunk_placements_match_oracle(dense, built):
     case, ctx = dense
     opts = built.capi.default_options()
