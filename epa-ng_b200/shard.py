@@ -38,3 +38,48 @@ def gather_records(records: torch.Tensor, counts: torch.Tensor, n_queries: int, 
     if rank != dst:
         return None, None
     return torch.cat(rec_list)[:n_queries], torch.cat(cnt_list)[:n_queries]
+
+
+def compact_records(records: torch.Tensor, counts: torch.Tensor, fields: int = 5):
+    """records: [Q, filter_max * fields] fixed-stride rows of which only the first counts[q] records of query q
+    are filled (on average 1.2 of 7). Returns the filled records as one [n, fields] tensor in query order."""
+    q = records.shape[0]
+    fmax = records.shape[1] // fields
+    keep = torch.arange(fmax, device=records.device)[None, :] < counts[:, None].to(torch.int64)
+    return records.view(q, fmax, fields)[keep]
+
+
+def gather_compact(records: torch.Tensor, counts: torch.Tensor, n_queries: int, dst: int = 0, fields: int = 5):
+    """The gather of gather_records with the records compacted first (counts-prefix form): every rank sends only
+    its filled records, padded to the largest shard's number, plus its counts. On `dst` returns
+    (list of per-rank [n_r, fields] record tensors, counts[n_queries]); (None, None) elsewhere. The fixed-stride
+    rows of query g are rebuilt from the counts' prefix sums (expand_compact)."""
+    world = dist.get_world_size() if dist.is_initialized() else 1
+    comp = compact_records(records, counts, fields)
+    if world == 1:
+        return [comp], counts[:n_queries]
+    rank = dist.get_rank()
+    n_mine = torch.tensor([comp.shape[0]], dtype=torch.int64, device=records.device)
+    n_all = [torch.zeros_like(n_mine) for _ in range(world)]
+    dist.all_gather(n_all, n_mine)
+    sizes = [int(x.item()) for x in n_all]
+    cap = max(1, max(sizes))
+    padded = torch.zeros((cap, fields), dtype=records.dtype, device=records.device)
+    padded[: comp.shape[0]] = comp
+    rec_list = [torch.empty_like(padded) for _ in range(world)] if rank == dst else None
+    cnt_list = [torch.empty_like(counts) for _ in range(world)] if rank == dst else None
+    dist.gather(padded, rec_list, dst=dst)
+    dist.gather(counts, cnt_list, dst=dst)
+    if rank != dst:
+        return None, None
+    return [r[:n] for r, n in zip(rec_list, sizes)], torch.cat(cnt_list)[:n_queries]
+
+
+def expand_compact(parts, counts: torch.Tensor, filter_max: int, fields: int = 5):
+    """Inverse of the compaction on the receiving side: fixed-stride [Q, filter_max * fields] rows in global query order."""
+    comp = torch.cat(parts) if len(parts) > 1 else parts[0]
+    q = counts.shape[0]
+    out = torch.zeros((q, filter_max, fields), dtype=comp.dtype, device=comp.device)
+    keep = torch.arange(filter_max, device=comp.device)[None, :] < counts[:, None].to(torch.int64)
+    out[keep] = comp
+    return out.view(q, filter_max * fields)

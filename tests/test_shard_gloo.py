@@ -34,10 +34,18 @@ def _worker(rank, world, port, n_queries, stride, out_path):
     rec[: hi - lo] = g[:, None] + torch.arange(stride, dtype=torch.float64)[None, :] / 100.0
     cnt[: hi - lo] = (torch.arange(lo, hi) % 7 + 1).to(torch.int32)
     all_rec, all_cnt = shard.gather_records(rec, cnt, n_queries, dst=0)
+    # the compacted form of the same gather (only the filled records travel)
+    fmax = stride // 5
+    cnt_c = torch.clamp(cnt, max=fmax)
+    parts, cnt_g = shard.gather_compact(rec, cnt_c, n_queries, dst=0)
     if rank == 0:
+        full = shard.expand_compact(parts, cnt_g, fmax)
+        want = all_rec.view(n_queries, fmax, 5) * (torch.arange(fmax)[None, :] < cnt_g[:, None]).unsqueeze(-1)
+        assert torch.equal(full.view(n_queries, fmax, 5), want.to(full.dtype))
+        assert sum(p.shape[0] for p in parts) == int(cnt_g.sum())
         np.savez(out_path, rec=all_rec.numpy(), cnt=all_cnt.numpy())
     else:
-        assert all_rec is None and all_cnt is None
+        assert all_rec is None and all_cnt is None and parts is None
     dist.barrier()
     dist.destroy_process_group()
 
