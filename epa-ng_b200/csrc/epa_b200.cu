@@ -1553,7 +1553,7 @@ extern "C" int epa_place_pairs(epa_ctx * ctx, const epa_options * opts)
         if (int rc2 = ensure_clvT(ctx)) return rc2;
       const size_t aa_stride = (size_t) ((ctx->n + CLVT_BLOCK - 1) / CLVT_BLOCK) * (size_t) (ctx->R * ctx->S) * CLVT_BLOCK;
       rc = launch_blo_generic(ctx->S, ctx->R, ctx->sm_count, ctx->smem_optin, ctx->max_span, ctx->d_model, a, &ctx->scratch.p,
-                              &ctx->scratch.cap, ctx->stream, site ? ctx->d_clvT : nullptr, aa_stride) == cudaSuccess ? EPA_OK
+                              &ctx->scratch.cap, ctx->stream, site ? ctx->d_clvT : nullptr, aa_stride, ctx->sw.no_tmem ? 0 : 1) == cudaSuccess ? EPA_OK
            : fail(ctx, EPA_ERR_CUDA, "generic BLO launch failed: %s", cudaGetErrorString(cudaGetLastError()));
     }
     if (rc) return rc;

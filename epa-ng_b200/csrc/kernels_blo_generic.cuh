@@ -13,10 +13,68 @@
 //    in a fixed order.
 #pragma once
 #include "kernels_blo.cuh"
+#include "kernels_blo_site.cuh"          // tcgen05.ld / st helpers
 
 namespace epa {
 
 constexpr int GEN_THREADS = 256;
+
+// Sumtable rows in TENSOR MEMORY (unit-mapped phases). A (rate, site) unit is always handled by the same thread -
+// unit u belongs to thread u % 256, as its (u / 256)-th unit - in the CLV passes that write its S - 1 decaying
+// entries and in the Newton sweeps that read them, so the row can live in the thread's own TMEM lane: warps w and
+// w + 4 share a 32-lane quarter and take 256 columns each, a unit takes GEN_TM_COLS of them. 6 units per thread
+// hold windows of up to 6 * 256 / R sites (384 for four rate categories); longer windows keep the L2-resident planes.
+constexpr int GEN_TM_COLS = 40;          // 19 doubles = 38 columns, padded to the x32 + x8 load shapes
+constexpr int GEN_TM_UNITS = 6;
+
+__device__ __forceinline__ void tc_st8(uint32_t taddr, const uint32_t (&v)[8])
+{
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+               :: "r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]) : "memory");
+}
+__device__ __forceinline__ void tc_ld8(uint32_t taddr, uint32_t (&v)[8])
+{
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+               : "r"(taddr) : "memory");
+}
+
+// the S - 1 decaying entries of one unit -> the thread's TMEM slot (S = 20: 19 doubles)
+template <int S>
+__device__ __forceinline__ void gen_tm_store(uint32_t taddr, const double (&st)[S])
+{
+  static_assert(S - 1 <= 20, "a unit's row must fit GEN_TM_COLS columns");
+  uint32_t a[32], b[8];
+  #pragma unroll
+  for (int j = 0; j < 16; ++j)
+  {
+    const double v = j + 1 < S ? st[j + 1] : 0.0;
+    a[2 * j] = (uint32_t) __double2loint(v); a[2 * j + 1] = (uint32_t) __double2hiint(v);
+  }
+  #pragma unroll
+  for (int j = 0; j < 4; ++j)
+  {
+    const double v = 17 + j < S ? st[17 + j] : 0.0;
+    b[2 * j] = (uint32_t) __double2loint(v); b[2 * j + 1] = (uint32_t) __double2hiint(v);
+  }
+  tc_st32(taddr, a);
+  tc_st8(taddr + 32, b);
+}
+
+template <int S>
+__device__ __forceinline__ void gen_tm_load(uint32_t taddr, double (&x)[S - 1])
+{
+  uint32_t a[32], b[8];
+  tc_ld32(taddr, a);
+  tc_ld8(taddr + 32, b);
+  tc_wait_ld();
+  #pragma unroll
+  for (int j = 0; j < 16; ++j)
+    if (j < S - 1) x[j] = __hiloint2double((int) a[2 * j + 1], (int) a[2 * j]);
+  #pragma unroll
+  for (int j = 0; j < 4; ++j)
+    if (16 + j < S - 1) x[16 + j] = __hiloint2double((int) b[2 * j + 1], (int) b[2 * j]);
+}
 
 template <int S, int R>
 struct GenSmem {
@@ -235,12 +293,19 @@ template <int S, int R>
 __device__ __forceinline__ double gen_pass_tip_site(double * sm, double * sum, int wpad, const double * __restrict__ DT,
                                                     const double * __restrict__ XT, const uint32_t * __restrict__ sD,
                                                     const uint32_t * __restrict__ sX, const uint8_t * __restrict__ qc,
-                                                    int begin, int w, double * rbuf, const double * __restrict__ inv_w)
+                                                    int begin, int w, double * rbuf, const double * __restrict__ inv_w,
+                                                    uint64_t tm)
 {
   using L = GenSmem<S, R>;
   double * termbuf = rbuf, * basebuf = rbuf + R * wpad;
-  for (int u = threadIdx.x; u < R * w; u += GEN_THREADS)
+  // tm != 0: rows go to this thread's tensor-memory slots; the loop then runs the same number of trips in every lane
+  // (tcgen05.st is warp-wide) and a lane beyond the last unit recomputes that unit and stores it in its own slot
+  const int n_units = R * w;
+  const int u_end = tm ? ((n_units + GEN_THREADS - 1) / GEN_THREADS) * GEN_THREADS : n_units;
+  for (int u0 = threadIdx.x, slot = 0; u0 < u_end; u0 += GEN_THREADS, ++slot)
   {
+    const bool act = u0 < n_units;
+    const int u = act ? u0 : n_units - 1;
     const int r = u / w, s = u - r * w;
     const size_t off = clvt_off_c<S>(begin + s, R * S) + (size_t) (r * S) * 32;
     const int code = qc[s] & (MAX_CODES - 1);
@@ -268,18 +333,25 @@ __device__ __forceinline__ double gen_pass_tip_site(double * sm, double * sum, i
     double tr = 0.0;
     #pragma unroll
     for (int i = 0; i < S; ++i) tr += (in[i] * c_model.freqs[i]) * tvr[i];
-    termbuf[r * wpad + s] = tr * wr;
+    if (act) termbuf[r * wpad + s] = tr * wr;
+    double st[S];
     #pragma unroll
     for (int j = 0; j < S; ++j)
     {
       double right = 0.0;
       #pragma unroll
       for (int k = 0; k < S; ++k) right += c_model.eigenvecs[j * S + k] * in[k];
-      const double v = tl[j] * right;
-      if (j == 0) basebuf[r * wpad + s] = v * wr;
-      else sum[(size_t) (r * (S - 1) + j) * wpad + s] = v;
+      st[j] = tl[j] * right;
+    }
+    if (act) basebuf[r * wpad + s] = st[0] * wr;
+    if (tm) gen_tm_store<S>((uint32_t) tm + (uint32_t) slot * GEN_TM_COLS, st);
+    else
+    {
+      #pragma unroll
+      for (int j = 1; j < S; ++j) sum[(size_t) (r * (S - 1) + j) * wpad + s] = st[j];
     }
   }
+  if (tm) tc_wait_st();
   __syncthreads();
   double acc = 0.0, unused = 0.0;
   for (int s = threadIdx.x; s < w; s += GEN_THREADS)
@@ -300,12 +372,16 @@ template <int S, int R>
 __device__ __forceinline__ void gen_pass_distal_site(double * sm, double * sum, int wpad, const double * __restrict__ DT,
                                                      const double * __restrict__ XT, const uint8_t * __restrict__ qc,
                                                      int begin, int w, double * rbuf, const double * __restrict__ inv_w,
-                                                     int which_x = 1)
+                                                     uint64_t tm, int which_x = 1)
 {
   using L = GenSmem<S, R>;
   double * basebuf = rbuf;
-  for (int u = threadIdx.x; u < R * w; u += GEN_THREADS)
+  const int n_units = R * w;
+  const int u_end = tm ? ((n_units + GEN_THREADS - 1) / GEN_THREADS) * GEN_THREADS : n_units;
+  for (int u0 = threadIdx.x, slot = 0; u0 < u_end; u0 += GEN_THREADS, ++slot)
   {
+    const bool act = u0 < n_units;
+    const int u = act ? u0 : n_units - 1;
     const int r = u / w, s = u - r * w;
     const size_t off = clvt_off_c<S>(begin + s, R * S) + (size_t) (r * S) * 32;
     const int code = qc[s] & (MAX_CODES - 1);
@@ -327,17 +403,24 @@ __device__ __forceinline__ void gen_pass_distal_site(double * sm, double * sum, 
       in[i] = tvr[i] * tb;
     }
     const double wr = c_model.weights[r];
+    double st[S];
     #pragma unroll
     for (int j = 0; j < S; ++j)
     {
       double left = 0.0, right = 0.0;
       #pragma unroll
       for (int k = 0; k < S; ++k) { left += dv[k] * c_model.pivinv[k * S + j]; right += c_model.eigenvecs[j * S + k] * in[k]; }
-      const double v = left * right;
-      if (j == 0) basebuf[r * wpad + s] = v * wr;
-      else sum[(size_t) (r * (S - 1) + j) * wpad + s] = v;
+      st[j] = left * right;
+    }
+    if (act) basebuf[r * wpad + s] = st[0] * wr;
+    if (tm) gen_tm_store<S>((uint32_t) tm + (uint32_t) slot * GEN_TM_COLS, st);
+    else
+    {
+      #pragma unroll
+      for (int j = 1; j < S; ++j) sum[(size_t) (r * (S - 1) + j) * wpad + s] = st[j];
     }
   }
+  if (tm) tc_wait_st();
   __syncthreads();
   for (int s = threadIdx.x; s < w; s += GEN_THREADS)
   {
@@ -355,7 +438,7 @@ __device__ __forceinline__ void gen_pass_distal_site(double * sm, double * sum, 
 // and the per-rate partial sums are combined per site in a fixed order.
 template <int S, int R>
 __device__ __forceinline__ void gen_derivatives_units(double * sm, const double * sum, int wpad, int w, double t,
-                                                      double & f, double & df, double * rbuf)
+                                                      double & f, double & df, double * rbuf, uint64_t tm)
 {
   using L = GenSmem<S, R>;
   constexpr int NK = L::NK;
@@ -368,18 +451,26 @@ __device__ __forceinline__ void gen_derivatives_units(double * sm, const double 
   }
   __syncthreads();
   double * b0 = rbuf, * b1 = rbuf + R * wpad, * b2 = rbuf + 2 * R * wpad;
-  for (int u = threadIdx.x; u < R * w; u += GEN_THREADS)
+  const int n_units = R * w;
+  const int u_end = tm ? ((n_units + GEN_THREADS - 1) / GEN_THREADS) * GEN_THREADS : n_units;
+  for (int u0 = threadIdx.x, slot = 0; u0 < u_end; u0 += GEN_THREADS, ++slot)
   {
+    const bool act = u0 < n_units;
+    const int u = act ? u0 : n_units - 1;
     const int r = u / w, s = u - r * w;
-    const double * col = sum + (size_t) (r * (S - 1) + 1) * wpad + s;
     const double * dg = sm + L::DIAG + r * (S - 1);
     double x[S - 1];
-    #pragma unroll
-    for (int j = 0; j < S - 1; ++j) x[j] = col[(size_t) j * wpad];
+    if (tm) gen_tm_load<S>((uint32_t) tm + (uint32_t) slot * GEN_TM_COLS, x);
+    else
+    {
+      const double * col = sum + (size_t) (r * (S - 1) + 1) * wpad + s;
+      #pragma unroll
+      for (int j = 0; j < S - 1; ++j) x[j] = col[(size_t) j * wpad];
+    }
     double c0 = 0.0, c1 = 0.0, c2 = 0.0;
     #pragma unroll
     for (int j = 0; j < S - 1; ++j) { c0 += x[j] * dg[j]; c1 += x[j] * dg[NK + j]; c2 += x[j] * dg[2 * NK + j]; }
-    b0[r * wpad + s] = c0; b1[r * wpad + s] = c1; b2[r * wpad + s] = c2;
+    if (act) { b0[r * wpad + s] = c0; b1[r * wpad + s] = c1; b2[r * wpad + s] = c2; }
   }
   __syncthreads();
   double a1 = 0.0, a2 = 0.0;
@@ -431,7 +522,7 @@ __device__ __forceinline__ void gen_derivatives(double * sm, const double * sum,
 
 template <int S, int R>
 __device__ __forceinline__ double gen_newton(double * sm, const double * sum, int wpad, int w, double xmin, double xguess,
-                                             double xmax, double tol, double * rbuf)
+                                             double xmax, double tol, double * rbuf, uint64_t tm)
 {
   double x = fmax(fmin(xguess, xmax), xmin);
   double xl = xmin, xh = xmax;
@@ -441,7 +532,7 @@ __device__ __forceinline__ double gen_newton(double * sm, const double * sum, in
   {
     if (iter++ > EPA_NR_MAX_ITERS) return 0.0;
     double f, df;
-    if (rbuf) gen_derivatives_units<S, R>(sm, sum, wpad, w, x, f, df, rbuf);
+    if (rbuf) gen_derivatives_units<S, R>(sm, sum, wpad, w, x, f, df, rbuf, tm);
     else gen_derivatives<S, R>(sm, sum, wpad, w, x, f, df);
     if (!isfinite(f) || !isfinite(df)) return 0.0;
     double dx;
@@ -465,7 +556,7 @@ __device__ __forceinline__ double gen_newton(double * sm, const double * sum, in
 // RAXML = --raxml-blo (pllmod_opt_optimize_branch_lengths_local with radius 1, PM/optimize/pll_optimize.c:778-1097)
 template <int S, int R, bool RAXML = false>
 __global__ void __launch_bounds__(GEN_THREADS, 1)
-blo_generic_kernel(BloArgs a, int wpad, const double * __restrict__ clvT, size_t t_stride)
+blo_generic_kernel(BloArgs a, int wpad, const double * __restrict__ clvT, size_t t_stride, int use_tmem)
 {
   using L = GenSmem<S, R>;
   extern __shared__ __align__(16) double sm[];
@@ -489,6 +580,21 @@ blo_generic_kernel(BloArgs a, int wpad, const double * __restrict__ clvT, size_t
   }
   __syncthreads();
   double * sum = a.scratch + (size_t) blockIdx.x * (size_t) (1 + L::NK) * wpad;
+  // tensor memory for the sumtable rows of the unit-mapped phases (one CTA per SM: 246 registers x 256 threads)
+  __shared__ uint32_t tmem_slot;
+  const bool have_tm = clvT != nullptr && use_tmem;
+  if (have_tm)
+  {
+    if (threadIdx.x < 32)
+    {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" :: "r"(smem_u32(&tmem_slot)) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+  }
+  const uint32_t tm_base = have_tm ? tmem_slot + ((uint32_t) (((threadIdx.x >> 5) & 3) * 32) << 16) + (uint32_t) (threadIdx.x >> 7) * 256u : 0u;
 
   for (;;)
   {
@@ -524,6 +630,8 @@ blo_generic_kernel(BloArgs a, int wpad, const double * __restrict__ clvT, size_t
     const uint32_t * sX = a.tree.scaler + (size_t) ed.proximal * n + begin;
     const uint8_t * qc = a.codes + (size_t) q * n + begin;
     const double * inv_w = a.tree.inv ? a.tree.inv + begin : nullptr;      // +I: pll_util.cpp:413-414
+    // bit 32 = rows in tensor memory, low word = this thread's slot 0
+    const uint64_t tm = (have_tm && R * w <= GEN_THREADS * GEN_TM_UNITS) ? ((1ull << 32) | tm_base) : 0ull;
 
     const double orig = ed.length;
     double len[3] = {orig / 2.0, orig / 2.0, EPA_DEFAULT_PENDANT};
@@ -552,7 +660,7 @@ blo_generic_kernel(BloArgs a, int wpad, const double * __restrict__ clvT, size_t
         {
           if (step == 3 || need_tip)
             logl_now = clvT
-                ? gen_pass_tip_site<S, R>(sm, sum, wpad, clvT + (size_t) ed.distal * t_stride, clvT + (size_t) ed.proximal * t_stride, sD, sX, qc, begin, w, sm + L::TOTAL, inv_w)
+                ? gen_pass_tip_site<S, R>(sm, sum, wpad, clvT + (size_t) ed.distal * t_stride, clvT + (size_t) ed.proximal * t_stride, sD, sX, qc, begin, w, sm + L::TOTAL, inv_w, tm)
                 : gen_pass_tip<S, R>(sm, sum, wpad, D, X, sD, sX, qc, w, inv_w);
           if (step == 0)
           {
@@ -577,7 +685,7 @@ blo_generic_kernel(BloArgs a, int wpad, const double * __restrict__ clvT, size_t
           const bool prox = step == 2;          // proximal edge: the distal pass with the two nodes swapped
           if (clvT)
             gen_pass_distal_site<S, R>(sm, sum, wpad, clvT + (size_t) (prox ? ed.proximal : ed.distal) * t_stride,
-                                       clvT + (size_t) (prox ? ed.distal : ed.proximal) * t_stride, qc, begin, w, sm + L::TOTAL, inv_w, prox ? 0 : 1);
+                                       clvT + (size_t) (prox ? ed.distal : ed.proximal) * t_stride, qc, begin, w, sm + L::TOTAL, inv_w, tm, prox ? 0 : 1);
           else
             gen_pass_distal<S, R>(sm, sum, wpad, prox ? X : D, prox ? D : X, qc, w, inv_w, prox ? 0 : 1);
           target = prox ? 1 : 0;
@@ -588,7 +696,7 @@ blo_generic_kernel(BloArgs a, int wpad, const double * __restrict__ clvT, size_t
         double * rbuf = clvT ? sm + L::TOTAL : nullptr;
         const double xres = newton_old([&](double x, double & f, double & df)
                                        {
-                                         if (rbuf) gen_derivatives_units<S, R>(sm, sum, wpad, w, x, f, df, rbuf);
+                                         if (rbuf) gen_derivatives_units<S, R>(sm, sum, wpad, w, x, f, df, rbuf, tm);
                                          else gen_derivatives<S, R>(sm, sum, wpad, w, x, f, df);
                                        }, EPA_MIN_BRLEN, xguess, EPA_MAX_BRLEN, EPA_MIN_BRLEN / 10.0, failed);
         if (failed) { ok = false; break; }
@@ -628,7 +736,7 @@ blo_generic_kernel(BloArgs a, int wpad, const double * __restrict__ clvT, size_t
       if (!distal_phase)
       {
         const double new_logl = clvT
-            ? -gen_pass_tip_site<S, R>(sm, sum, wpad, clvT + (size_t) ed.distal * t_stride, clvT + (size_t) ed.proximal * t_stride, sD, sX, qc, begin, w, sm + L::TOTAL, inv_w)
+            ? -gen_pass_tip_site<S, R>(sm, sum, wpad, clvT + (size_t) ed.distal * t_stride, clvT + (size_t) ed.proximal * t_stride, sD, sX, qc, begin, w, sm + L::TOTAL, inv_w, tm)
             : -gen_pass_tip<S, R>(sm, sum, wpad, D, X, sD, sX, qc, w, inv_w);
         if (first) { loglikelihood = new_logl; first = false; }
         else
@@ -650,7 +758,7 @@ blo_generic_kernel(BloArgs a, int wpad, const double * __restrict__ clvT, size_t
       else
       {
         if (clvT)
-          gen_pass_distal_site<S, R>(sm, sum, wpad, clvT + (size_t) ed.distal * t_stride, clvT + (size_t) ed.proximal * t_stride, qc, begin, w, sm + L::TOTAL, inv_w);
+          gen_pass_distal_site<S, R>(sm, sum, wpad, clvT + (size_t) ed.distal * t_stride, clvT + (size_t) ed.proximal * t_stride, qc, begin, w, sm + L::TOTAL, inv_w, tm);
         else
           gen_pass_distal<S, R>(sm, sum, wpad, D, X, qc, w, inv_w);
         xmin = fmin(EPA_MIN_BRLEN / 2.0, original_length / 2.0);
@@ -658,7 +766,7 @@ blo_generic_kernel(BloArgs a, int wpad, const double * __restrict__ clvT, size_t
         xguess = len[0];
         if (xguess < xmin || xguess > xmax) xguess = original_length / 2.0;
       }
-      const double xres = gen_newton<S, R>(sm, sum, wpad, w, xmin, xguess, xmax, xmin / 10.0, clvT ? sm + L::TOTAL : nullptr);
+      const double xres = gen_newton<S, R>(sm, sum, wpad, w, xmin, xguess, xmax, xmin / 10.0, clvT ? sm + L::TOTAL : nullptr, tm);
       if (xres > 0.0)
       {
         if (!distal_phase) { len[2] = xres; rebuild = 4u; }
@@ -675,12 +783,19 @@ blo_generic_kernel(BloArgs a, int wpad, const double * __restrict__ clvT, size_t
       a.out[pid] = res;
     }
   }
+  if (have_tm)
+  {
+    tc_fence_before();
+    __syncthreads();
+    if (threadIdx.x < 32)
+      asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" :: "r"(tmem_slot) : "memory");
+  }
 }
 
 // host-side launcher; scratch is (re)allocated by the caller-owned buffer
 template <int S, int R>
 inline cudaError_t launch_blo_generic_sr(int sm_count, size_t smem_optin, int max_span, BloArgs & a, void ** scratch,
-                                         size_t * scratch_cap, cudaStream_t stream, const double * clvT, size_t t_stride)
+                                         size_t * scratch_cap, cudaStream_t stream, const double * clvT, size_t t_stride, int use_tmem)
 {
   using L = GenSmem<S, R>;
   const int wpad = (std::max(1, max_span) + 31) & ~31;
@@ -703,21 +818,21 @@ inline cudaError_t launch_blo_generic_sr(int sm_count, size_t smem_optin, int ma
   {
     cudaError_t e = cudaFuncSetAttribute(blo_generic_kernel<S, R, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
     if (e != cudaSuccess) return e;
-    blo_generic_kernel<S, R, true><<<grid, GEN_THREADS, smem, stream>>>(a, wpad, clvT, t_stride);
+    blo_generic_kernel<S, R, true><<<grid, GEN_THREADS, smem, stream>>>(a, wpad, clvT, t_stride, use_tmem);
     return cudaGetLastError();
   }
   cudaError_t e = cudaFuncSetAttribute(blo_generic_kernel<S, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
   if (e != cudaSuccess) return e;
-  blo_generic_kernel<S, R><<<grid, GEN_THREADS, smem, stream>>>(a, wpad, clvT, t_stride);
+  blo_generic_kernel<S, R><<<grid, GEN_THREADS, smem, stream>>>(a, wpad, clvT, t_stride, use_tmem);
   return cudaGetLastError();
 }
 
 inline cudaError_t launch_blo_generic(int S, int R, int sm_count, size_t smem_optin, int max_span, const DevModel *,
                                       BloArgs & a, void ** scratch, size_t * scratch_cap, cudaStream_t stream,
-                                      const double * clvT = nullptr, size_t t_stride = 0)
+                                      const double * clvT = nullptr, size_t t_stride = 0, int use_tmem = 1)
 {
-  if (S == 20 && R == 4) return launch_blo_generic_sr<20, 4>(sm_count, smem_optin, max_span, a, scratch, scratch_cap, stream, clvT, t_stride);
-  if (S == 20 && R == 1) return launch_blo_generic_sr<20, 1>(sm_count, smem_optin, max_span, a, scratch, scratch_cap, stream, clvT, t_stride);
+  if (S == 20 && R == 4) return launch_blo_generic_sr<20, 4>(sm_count, smem_optin, max_span, a, scratch, scratch_cap, stream, clvT, t_stride, use_tmem);
+  if (S == 20 && R == 1) return launch_blo_generic_sr<20, 1>(sm_count, smem_optin, max_span, a, scratch, scratch_cap, stream, clvT, t_stride, use_tmem);
   return cudaErrorNotSupported;
 }
 
