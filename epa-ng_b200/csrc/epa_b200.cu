@@ -19,6 +19,7 @@
 #include "kernels_blo.cuh"
 #include "kernels_blo_site.cuh"
 #include "kernels_blo_generic.cuh"
+#include "kernels_blo_aa.cuh"
 #include "kernels_collect.cuh"
 
 using namespace epa;
@@ -118,6 +119,7 @@ struct epa_ctx {
     bool no_first = false;     // EPA_B200_NO_FIRST: full first CLV pass instead of the per-edge tables
     bool no_tmem = false;      // EPA_B200_NO_TMEM: sumtables in shared memory only
     bool old_aa = false;       // EPA_B200_OLD_AA: (site, rate)-per-thread amino-acid passes
+    bool aa_dfma = false;      // EPA_B200_AA_DFMA: the DFMA amino-acid kernel (kernels_blo_generic.cuh) instead of the DMMA one
     int gs_below = 6;          // EPA_B200_BLO_GS_BELOW: resident warps below which the global-scratch variant runs
     int gs_warps = 8;          // EPA_B200_GS_WARPS: warps per CTA of the global-scratch variant
     int site_warps = 0;        // EPA_B200_SITE_WARPS: cap on the warps per CTA of the lane = site kernel (0 = none)
@@ -357,6 +359,7 @@ extern "C" int epa_ctx_create(epa_ctx ** out, int device, const epa_model_desc *
   ctx->sw.no_first = getenv("EPA_B200_NO_FIRST") != nullptr;
   ctx->sw.no_tmem = getenv("EPA_B200_NO_TMEM") != nullptr;
   ctx->sw.old_aa = getenv("EPA_B200_OLD_AA") != nullptr;
+  ctx->sw.aa_dfma = getenv("EPA_B200_AA_DFMA") != nullptr;
   if (const char * v = getenv("EPA_B200_BLO_GS_BELOW")) ctx->sw.gs_below = atoi(v);
   if (const char * v = getenv("EPA_B200_GS_WARPS")) ctx->sw.gs_warps = std::max(1, std::min(12, atoi(v)));
   if (const char * v = getenv("EPA_B200_SITE_WARPS")) ctx->sw.site_warps = atoi(v);
@@ -1552,9 +1555,18 @@ extern "C" int epa_place_pairs(epa_ctx * ctx, const epa_options * opts)
       if (site)
         if (int rc2 = ensure_clvT(ctx)) return rc2;
       const size_t aa_stride = (size_t) ((ctx->n + CLVT_BLOCK - 1) / CLVT_BLOCK) * (size_t) (ctx->R * ctx->S) * CLVT_BLOCK;
-      rc = launch_blo_generic(ctx->S, ctx->R, ctx->sm_count, ctx->smem_optin, ctx->max_span, ctx->d_model, a, &ctx->scratch.p,
-                              &ctx->scratch.cap, ctx->stream, site ? ctx->d_clvT : nullptr, aa_stride, ctx->sw.no_tmem ? 0 : 1) == cudaSuccess ? EPA_OK
-           : fail(ctx, EPA_ERR_CUDA, "generic BLO launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+      // 20 states, windows up to 320 sites, pplacer-style BLO: fp64 tensor-core kernel with the sumtable in tensor memory
+      const bool mma = site && ctx->S == 20 && (ctx->R == 4 || ctx->R == 1) && !a.raxml && ctx->max_span <= AA_MAX_WINDOW &&
+                       !ctx->sw.aa_dfma && !ctx->sw.no_tmem;
+      if (getenv("EPA_B200_DEBUG_AA")) fprintf(stderr, "[aa] mma=%d site=%d S=%d R=%d raxml=%d max_span=%d\n", (int) mma, (int) site, ctx->S, ctx->R, a.raxml, ctx->max_span);
+      cudaError_t ce;
+      if (mma)
+        ce = ctx->R == 4 ? launch_blo_aa<4>(ctx->sm_count, a, ctx->stream, ctx->d_clvT, aa_stride)
+                         : launch_blo_aa<1>(ctx->sm_count, a, ctx->stream, ctx->d_clvT, aa_stride);
+      else
+        ce = launch_blo_generic(ctx->S, ctx->R, ctx->sm_count, ctx->smem_optin, ctx->max_span, ctx->d_model, a, &ctx->scratch.p,
+                                &ctx->scratch.cap, ctx->stream, site ? ctx->d_clvT : nullptr, aa_stride, ctx->sw.no_tmem ? 0 : 1);
+      rc = ce == cudaSuccess ? EPA_OK : fail(ctx, EPA_ERR_CUDA, "amino-acid BLO launch failed: %s", cudaGetErrorString(ce));
     }
     if (rc) return rc;
     if (ctx->S != 4) LAUNCHED(ctx);

@@ -306,6 +306,38 @@ def test_aa_thorough_matches_oracle(synthaa, built):
         assert abs(r["distal_length"] - p.distal) <= 1e-6, (qi, ei, r, p)
 
 
+def test_aa_tensor_core_kernel_and_dfma_kernel_agree(synthaa, built):
+    """The amino-acid thorough placement runs on the fp64 tensor-core kernel (DMMA.884, sumtable in tensor memory,
+    kernels_blo_aa.cuh); EPA_B200_AA_DFMA routes a context to the DFMA kernel (kernels_blo_generic.cuh). Both are
+    checked against the oracle above / here, they must not be bit-identical (different summation orders), and the
+    launch counters show that two different kernels ran."""
+    case, ctx = synthaa
+    import os
+    os.environ["EPA_B200_AA_DFMA"] = "1"
+    try:
+        ctx2 = helpers.make_context(case)
+        ctx2.build_lookup()
+    finally:
+        del os.environ["EPA_B200_AA_DFMA"]
+    opts = built.capi.default_options(prescoring=0)
+    res = []
+    for c in (ctx, ctx2):
+        c.upload_queries(case.query_rows[:6])
+        c.select(opts)
+        c.place_pairs(opts)
+        res.append(c.get_pairs())
+    (q1, e1, r1), (q2, e2, r2) = res
+    assert np.array_equal(q1, q2) and np.array_equal(e1, e2)
+    assert np.allclose(r1["likelihood"], r2["likelihood"], rtol=1e-10, atol=0)
+    assert np.allclose(r1["pendant_length"], r2["pendant_length"], rtol=0, atol=1e-7)
+    assert np.allclose(r1["distal_length"], r2["distal_length"], rtol=0, atol=1e-7)
+    assert not np.array_equal(r1["likelihood"], r2["likelihood"]), "both contexts took the same kernel"
+    for qi, ei, r in list(zip(q2, e2, r2))[::7]:
+        p = case.placer.thorough(case.qseqs[qi], int(ei))
+        assert abs(r["likelihood"] - p.logl) <= 1e-9 * abs(p.logl), (qi, ei, r, p)
+    ctx2.close()
+
+
 def test_aa_placements_match_reference(synthaa, built):
     case, ctx = synthaa
     gold = helpers.golden("synthaa")
