@@ -87,11 +87,12 @@ struct epa_ctx {
   uint32_t nq = 0;
   int max_span = 0;
   uint32_t n_simple = 0;           // queries that take the pair-table preplacement kernel (sorted first)
+  uint32_t n_ambig = 0;            // of those: queries with a few other ambiguity codes (fixed up after the tensor-core kernel)
   bool implicit_pairs = false;
   uint64_t n_pairs = 0;
   size_t pre_stride = 0;
   DevBuf raw, codes, begin, span, sortkey, perm, hist, range, pre, cnt, cutv, cuti, off, pair_q, pair_e,
-         edge_hist, edge_off, work, res, out_rec, out_cnt, scratch, tmp, qmax, cand, scan_sums, summary, over_list, range2;
+         edge_hist, edge_off, work, res, out_rec, out_cnt, scratch, tmp, qmax, cand, scan_sums, summary, over_list, range2, amb;
   // candidate selection fused into the tensor-core preplacement (dynamic heuristic): announced by
   // epa_hint_selection before epa_preplace; the [query][edge] score matrix is then not written
   bool sel_hint = false;
@@ -478,8 +479,8 @@ extern "C" int epa_ctx_create(epa_ctx ** out, int device, const epa_model_desc *
   for (uint32_t i = 0; i < n_edges; ++i) ctx->h_edges[i] = EdgeDev{edges[i].distal, edges[i].proximal, edges[i].length};
   CUC(cudaMalloc(&ctx->d_edges, n_edges * sizeof(EdgeDev)));
   CUC(cudaMemcpy(ctx->d_edges, ctx->h_edges.data(), n_edges * sizeof(EdgeDev), cudaMemcpyHostToDevice));
-  CUC(cudaMalloc(&ctx->d_flags, 8 * sizeof(int)));
-  CUC(cudaMemset(ctx->d_flags, 0, 8 * sizeof(int)));
+  CUC(cudaMalloc(&ctx->d_flags, 16 * sizeof(int)));
+  CUC(cudaMemset(ctx->d_flags, 0, 16 * sizeof(int)));
   CUC(cudaMalloc(&ctx->d_counter, sizeof(unsigned long long)));
   CUC(cudaMalloc(&ctx->d_total, 2 * sizeof(uint64_t)));
 
@@ -834,9 +835,9 @@ extern "C" int epa_get_lookup(epa_ctx * ctx, uint32_t edge, double * out)
 // ==============================================================================================
 //  chunk pipeline
 // ==============================================================================================
-static int read_flags(epa_ctx * ctx, int flags[8])
+static int read_flags(epa_ctx * ctx, int flags[16])
 {
-  CU(cudaMemcpyAsync(flags, ctx->d_flags, 8 * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaMemcpyAsync(flags, ctx->d_flags, 16 * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
   CU(cudaStreamSynchronize(ctx->stream));
   return EPA_OK;
 }
@@ -963,18 +964,22 @@ extern "C" int epa_encode_queries_dev(epa_ctx * ctx, const char * seqs_dev, uint
     CU(cudaEventRecord(ctx->ev[0], ctx->stream));
   }
   const uint8_t * src = seqs_dev ? reinterpret_cast<const uint8_t *>(seqs_dev) : ctx->raw.as<uint8_t>();
-  CU(cudaMemsetAsync(ctx->d_flags, 0, 8 * sizeof(int), ctx->stream));
+  CU(cudaMemsetAsync(ctx->d_flags, 0, 16 * sizeof(int), ctx->stream));
   const unsigned blocks = (n_queries + 7) / 8;
   CU(ctx->sortkey.ensure(n_queries * sizeof(int)));
+  CU(ctx->amb.ensure(n_queries * sizeof(uint8_t)));
+  // queries with a few other ambiguity codes (R, Y, K, M, ...) still take the tensor-core preplacement: those sites
+  // score as fully ambiguous there and preplace_ambig_fix_kernel adds the difference afterwards
+  const int amb_cap = (ctx->mma_ok && !ctx->sw.no_mma && !ctx->sw.fused_select) ? AMBIG_CAP : 0;
   // 64-bit accesses when every row of both buffers is 8-byte aligned
   if (ctx->n % 8 == 0 && (reinterpret_cast<uintptr_t>(src) & 7) == 0 && (reinterpret_cast<uintptr_t>(ctx->codes.as<uint8_t>()) & 7) == 0)
     encode_queries_kernel<8><<<blocks, 256, 0, ctx->stream>>>(ctx->d_model, src, n_queries, ctx->n, premasking ? 1 : 0,
                                                          ctx->codes.as<uint8_t>(), ctx->begin.as<int>(),
-                                                         ctx->span.as<int>(), ctx->sortkey.as<int>(), ctx->d_flags);
+                                                         ctx->span.as<int>(), ctx->sortkey.as<int>(), ctx->d_flags, amb_cap, ctx->amb.as<uint8_t>());
   else
     encode_queries_kernel<1><<<blocks, 256, 0, ctx->stream>>>(ctx->d_model, src, n_queries, ctx->n, premasking ? 1 : 0,
                                                          ctx->codes.as<uint8_t>(), ctx->begin.as<int>(),
-                                                         ctx->span.as<int>(), ctx->sortkey.as<int>(), ctx->d_flags);
+                                                         ctx->span.as<int>(), ctx->sortkey.as<int>(), ctx->d_flags, amb_cap, ctx->amb.as<uint8_t>());
   LAUNCHED(ctx);
   // counting sort of the queries by (class, window start): simple queries first. The tiles of the
   // preplacement kernels and the all-pairs work order of the thorough kernel follow this order.
@@ -991,12 +996,13 @@ extern "C" int epa_encode_queries_dev(epa_ctx * ctx, const char * seqs_dev, uint
     LAUNCHED(ctx);
   }
   CU(cudaEventRecord(ctx->ev[1], ctx->stream));
-  int flags[8];
+  int flags[16];
   if (int rc = read_flags(ctx, flags)) return rc;
   if (flags[0] == 1) return fail(ctx, EPA_ERR_QUERY, "query %d contains a character that is not valid for this data type", flags[1] - 1);
   if (flags[0] == 2) return fail(ctx, EPA_ERR_QUERY, "query %d consists entirely of gaps", flags[1] - 1);
   ctx->max_span = flags[3];
   ctx->n_simple = (uint32_t) flags[4];
+  ctx->n_ambig = (uint32_t) flags[8];
   ctx->stage = ST_QUERIES;
   return EPA_OK;
 }
@@ -1116,7 +1122,7 @@ extern "C" int epa_preplace(epa_ctx * ctx)
     CU(cudaMemsetAsync(ctx->qmax.p, 0xff, nq * sizeof(double), ctx->stream));      // NaN = no row maximum recorded
   }
   if (fuse) CU(ctx->summary.ensure((size_t) nq * 2 * sizeof(RowSummary)));
-  int flags[8];
+  int flags[16];
   if (use_mma)
   {
     tile_range_kernel<<<(tilesM + 7) / 8, 256, 0, ctx->stream>>>(ctx->perm.as<uint32_t>(), ctx->begin.as<int>(), ctx->span.as<int>(),
@@ -1143,6 +1149,14 @@ extern "C" int epa_preplace(epa_ctx * ctx)
   {
     if (int rc = launch_preplace_mma(ctx, ctx->perm.as<uint32_t>(), nA, ctx->range.as<int2>(), fuse)) return rc;
     ctx->fused = fuse; ctx->fused_n = fuse ? nA : 0;
+    if (ctx->n_ambig && !fuse)
+    {
+      preplace_ambig_fix_kernel<<<(nA + 7) / 8, 256, 0, ctx->stream>>>(ctx->d_lookup, ctx->n_pad, (int) ctx->n_edges, ctx->codes.as<uint8_t>(),
+                                                                     ctx->n, ctx->begin.as<int>(), ctx->span.as<int>(), ctx->amb.as<uint8_t>(),
+                                                                     ctx->perm.as<uint32_t>(), nA, ctx->pre.as<double>(), ctx->pre_stride,
+                                                                     ctx->qmax.as<double>());
+      LAUNCHED(ctx);
+    }
   }
   else if (nA)
     if (int rc = launch_preplace_pair(ctx, nA, ctx->range.as<int2>(), std::max(8, flags[2]))) return rc;
@@ -1625,7 +1639,7 @@ static int collect_impl(epa_ctx * ctx, const epa_options * opts, epa_placement *
     ctx->out_flip ^= 1;
     if (!ctx->defer_results) CU(cudaStreamSynchronize(ctx->copy_stream));
   }
-  int flags[8];
+  int flags[16];
   if (int rc = read_flags(ctx, flags)) return rc;
   for (int i = 0; i < 5; ++i) (void) cudaEventElapsedTime(&ctx->ms[i], ctx->ev[i], ctx->ev[i + 1]);
   (void) cudaGetLastError();

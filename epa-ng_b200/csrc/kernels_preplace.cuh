@@ -125,8 +125,9 @@ __global__ void scatter_by_key_kernel(const int * __restrict__ keys, uint32_t co
 // ASCII -> codes, valid range. One warp per query.
 // err[0] = status (0 ok, 1 invalid character, 2 all-gap query), err[1] = first offending query + 1,
 // err[3] = longest valid range of the chunk, err[4] = number of "simple" queries.
-// A DNA query is simple when it only holds A, C, G, T and fully ambiguous characters: those take
-// the pair-table preplacement kernel. sortkey = begin for simple queries, n + 1 + begin otherwise.
+// A DNA query is simple when it holds A, C, G, T, fully ambiguous characters and at most amb_cap other
+// ambiguity codes (amb[q] = their number): those take the tensor-core (or pair-table) preplacement kernel.
+// sortkey = begin for simple queries, n + 1 + begin otherwise. err[8] = simple queries with amb[q] > 0.
 // ---------------------------------------------------------------------------------------------
 // V = bytes per lane and step (8 when the alignment width and both buffers allow 64-bit accesses, else 1):
 // a warp then moves 256 bytes per load instead of 32.
@@ -134,12 +135,13 @@ template <int V>
 __global__ void __launch_bounds__(256)
 encode_queries_kernel(const DevModel * __restrict__ m, const uint8_t * __restrict__ raw, uint32_t nq, int n,
                       int premask, uint8_t * __restrict__ codes, int * __restrict__ begin,
-                      int * __restrict__ span, int * __restrict__ sortkey, int * __restrict__ err)
+                      int * __restrict__ span, int * __restrict__ sortkey, int * __restrict__ err, int amb_cap,
+                      uint8_t * __restrict__ amb)
 {
   __shared__ uint8_t a2c[256];
-  __shared__ int s_simple, s_maxw;          // per-block sums: one global atomic each instead of one per query
+  __shared__ int s_simple, s_maxw, s_ambig;  // per-block sums: one global atomic each instead of one per query
   a2c[threadIdx.x] = m->ascii2code[threadIdx.x];
-  if (threadIdx.x == 0) { s_simple = 0; s_maxw = 0; }
+  if (threadIdx.x == 0) { s_simple = 0; s_maxw = 0; s_ambig = 0; }
   __syncthreads();
   const uint32_t q = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
@@ -148,7 +150,8 @@ encode_queries_kernel(const DevModel * __restrict__ m, const uint8_t * __restric
   uint8_t * crow = codes + (size_t) (valid ? q : 0) * n;
   int lo = n, hi = -1;
   bool bad = false;
-  bool simple = (m->S == 4);
+  const bool dna = (m->S == 4);
+  int n_amb = 0;                            // characters other than A, C, G, T and the fully ambiguous ones
   for (int s0 = lane * V; valid && s0 < n; s0 += 32 * V)
   {
     uint8_t chv[V], cv[V];
@@ -168,7 +171,7 @@ encode_queries_kernel(const DevModel * __restrict__ m, const uint8_t * __restric
       const uint8_t c = a2c[ch];
       cv[k] = c;
       bad = bad || (c == 255);
-      simple = simple && ((0x8116u >> (c & 15)) & 1u);       // masks 1, 2, 4, 8, 15
+      n_amb += ((0x8116u >> (c & 15)) & 1u) ? 0 : 1;        // masks 1, 2, 4, 8, 15 are the plain ones
       if (ch != '-') { lo = min(lo, s); hi = max(hi, s); }
     }
     if constexpr (V == 8)
@@ -188,9 +191,13 @@ encode_queries_kernel(const DevModel * __restrict__ m, const uint8_t * __restric
     hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, o));
   }
   bad = __any_sync(0xffffffffu, bad);
-  simple = __all_sync(0xffffffffu, simple);
+  #pragma unroll
+  for (int o = 16; o > 0; o >>= 1) n_amb += __shfl_xor_sync(0xffffffffu, n_amb, o);
+  const bool simple = dna && n_amb <= amb_cap;
   if (valid && lane == 0)
   {
+    amb[q] = (uint8_t) (simple ? n_amb : 0);
+    if (simple && n_amb) atomicAdd(&s_ambig, 1);
     int b = 0, w = n;
     if (premask) { b = (hi < 0) ? 0 : lo; w = (hi < 0) ? 0 : hi - lo + 1; }
     begin[q] = b;
@@ -205,8 +212,49 @@ encode_queries_kernel(const DevModel * __restrict__ m, const uint8_t * __restric
   if (threadIdx.x == 0)
   {
     if (s_simple) atomicAdd(&err[4], s_simple);
+    if (s_ambig) atomicAdd(&err[8], s_ambig);
     atomicMax(&err[3], s_maxw);
   }
+}
+
+// Queries with a few ambiguity codes other than N (R, Y, K, M, S, W, B, D, H, V; src/core/Lookup_Store.hpp:33-68) after
+// the tensor-core preplacement, which scored those sites as fully ambiguous: one warp per query adds
+// lookup[e][s][code] - lookup[e][s][N] for every such site s of its window and every edge e, and withdraws the row
+// maximum the tensor-core epilogue recorded (the selection then finds it itself).
+constexpr int AMBIG_CAP = 16;
+__global__ void __launch_bounds__(256)
+preplace_ambig_fix_kernel(const double * __restrict__ lookup, int n_pad, int n_edges, const uint8_t * __restrict__ codes, int n,
+                          const int * __restrict__ begin, const int * __restrict__ span, const uint8_t * __restrict__ amb,
+                          const uint32_t * __restrict__ perm, uint32_t n_simple, double * __restrict__ pre, size_t pre_stride,
+                          double * __restrict__ qmax)
+{
+  const uint32_t slot = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (slot >= n_simple) return;
+  const uint32_t q = perm[slot];
+  if (amb[q] == 0) return;
+  const uint8_t * crow = codes + (size_t) q * n;
+  const int b = begin[q], w = span[q];
+  double * row = pre + (size_t) q * pre_stride;
+  for (int base = 0; base < w; base += 32)
+  {
+    const int s = b + base + lane;
+    const int c = base + lane < w ? (crow[s] & 15) : 15;
+    unsigned todo = __ballot_sync(0xffffffffu, !((0x8116u >> c) & 1u));
+    while (todo)
+    {
+      const int src = __ffs((int) todo) - 1;
+      todo &= todo - 1u;
+      const int site = b + base + src;
+      const int code = __shfl_sync(0xffffffffu, c, src);
+      for (int e = lane; e < n_edges; e += 32)
+      {
+        const double * lk = lookup + ((size_t) e * n_pad + site) * 16;
+        row[e] += __ldg(lk + code) - __ldg(lk + 15);
+      }
+    }
+  }
+  if (lane == 0) qmax[q] = NAN;
 }
 
 // ---------------------------------------------------------------------------------------------

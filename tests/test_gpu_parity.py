@@ -459,6 +459,62 @@ def test_fused_epilogue_selection_equals_the_two_kernel_path(dense, built):
     ctx.close()
 
 
+def test_ambiguity_codes_take_the_tensor_core_path(built):
+    """Queries with a few IUPAC ambiguity codes (R, Y, K, M, S, W, B, D, H, V) are scored by the tensor-core kernel with
+    those sites as N plus a per-site correction; queries with more than 16 of them take the shared-memory kernel. Both
+    against the oracle's scores and candidate sets, and against a context without the tensor-core path."""
+    ds = built.synth.dataset(T=24, n_sites=400, n_queries=3000, window=150, seed_tree=13, seed_q=14)
+    q = ds["queries"].copy()
+    rng = np.random.default_rng(5)
+    codes = np.frombuffer(b"RYKMSWBDHV", dtype=np.uint8)
+    for i in range(len(q)):
+        cols = np.flatnonzero(q[i] != ord("-"))
+        k = 0 if i % 3 == 0 else (1 + i % 4 if i % 50 else 30)          # none / 1..4 / 30 (beyond the cap)
+        if k:
+            pick = rng.choice(cols, size=k, replace=False)
+            q[i, pick] = codes[rng.integers(0, len(codes), size=k)]
+    case = helpers.case_from_arrays(ds["newick"], ds["names"], ds["ref"], ds["qnames"], q, ds["model"])
+    ctx = helpers.make_context(case)
+    ctx.build_lookup()
+    case.placer.build_lookup()
+    ctx.upload_queries(case.query_rows)
+    ctx.preplace()
+    got = ctx.get_prescores()
+    import os
+    os.environ["EPA_B200_NO_MMA"] = "1"
+    try:
+        ctx2 = helpers.make_context(case)
+        ctx2.build_lookup()
+    finally:
+        del os.environ["EPA_B200_NO_MMA"]
+    ctx2.upload_queries(case.query_rows)
+    ctx2.preplace()
+    ref = ctx2.get_prescores()
+    assert np.allclose(got, ref, rtol=1e-11, atol=0)
+    amb_rows = [i for i in range(len(q)) if i % 3 and i % 50]
+    assert not np.array_equal(got[amb_rows], ref[amb_rows]), "the ambiguous queries did not take the tensor-core kernel"
+    beyond = [i for i in range(len(q)) if i % 3 and i % 50 == 0]
+    assert np.array_equal(got[beyond], ref[beyond]), "queries beyond the cap must take the shared-memory kernel"
+    sample = amb_rows[::97] + beyond[:2]
+    want = {qi: case.placer.preplace(case.qseqs[qi]) for qi in sample}
+    for qi in sample:
+        assert np.allclose(got[qi], want[qi], rtol=1e-11, atol=0), f"prescores of query {qi}"
+    opts = built.capi.default_options()
+    ctx.select(opts)
+    ctx2.select(opts)
+    q1, e1, _ = ctx.get_pairs(raw=False)
+    q2, e2, _ = ctx2.get_pairs(raw=False)
+    assert np.array_equal(q1, q2) and np.array_equal(e1, e2)
+    out, counts = ctx.place_chunk(case.query_rows[amb_rows[:40]], opts)
+    for k, qi in enumerate(amb_rows[:40:8]):
+        wantp = case.placer.place(case.qseqs[qi])
+        gotp = out[8 * k][:counts[8 * k]]
+        assert [int(g["branch_id"]) for g in gotp] == [p.edge for p in wantp]
+        for g, p in zip(gotp, wantp):
+            assert abs(g["likelihood"] - p.logl) <= 1e-8 * abs(p.logl)
+    ctx.close(); ctx2.close()
+
+
 def test_dense_chunk_placements_match_oracle(dense, built):
     case, ctx = dense
     opts = built.capi.default_options()

@@ -2,7 +2,7 @@
 """Per-kernel counts of the SASS mnemonics that show which hardware paths the built library uses:
 tcgen05 MMA (UTCIMMA), tcgen05 commit/barrier (UTCBAR), tensor-memory loads/stores (LDTM/STTM), TMA bulk copies
 (UBLKCP), tensor-map TMA (UTMALDG: none - every staged tile is contiguous, bulk copies suffice), mbarrier
-(SYNCS), fp64 arithmetic (DFMA/DMUL/DADD), local-memory spills (LDL/STL).
+(SYNCS), fp64 tensor-core MMA (DMMA), fp64 arithmetic (DFMA/DMUL/DADD), local-memory spills (LDL/STL).
     python tools/sass_summary.py > profiles/r2_sass_summary.txt"""
 import collections, os, re, subprocess, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -17,7 +17,7 @@ for ln in out.splitlines():
     m = ins.match(ln)
     if m and cur: kern[cur][m.group(1)] += 1; kern[cur]["_n"] += 1
 names = subprocess.run(["c++filt"], input="\n".join(kern), capture_output=True, text=True).stdout.splitlines()
-cols = ["UTCIMMA", "UTCBAR", "LDTM", "STTM", "UBLKCP", "UTMALDG", "SYNCS", "DFMA", "DMUL", "DADD", "MUFU", "LDL", "STL"]
+cols = ["UTCIMMA", "UTCBAR", "LDTM", "STTM", "UBLKCP", "UTMALDG", "SYNCS", "DMMA", "DFMA", "DMUL", "DADD", "MUFU", "LDL", "STL"]
 print("# cuobjdump -sass epa-ng_b200/libepa_b200.so (sm_100a): static instruction counts per kernel")
 print("# kernel | instructions | " + " | ".join(cols))
 rows = []
