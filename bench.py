@@ -521,8 +521,14 @@ def ours(args):
         if cpu_group is not None:
             dist.barrier(group=cpu_group)
         if rank == 0:
-            n_files = int(min(args.files_queries or 2000000, Q))
-            files = files_leg(pkg, ds, n_files, list(range(world)), chunk, rec_host.numpy(), cnt_host.numpy(), fmax)
+            # 10^6 queries per GPU of the job, at most 4 x 10^6 (the file is written here, outside the timed part)
+            n_files = int(args.files_queries or min(4000000, Q * world))
+            fds = ds
+            if n_files > len(ds["qnames"]):
+                reps = -(-n_files // len(ds["qnames"]))
+                fds = dict(ds, queries=np.tile(ds["queries"], (reps, 1))[:n_files],
+                           qnames=["r%d%s" % (i // len(ds["qnames"]), ds["qnames"][i % len(ds["qnames"])]) for i in range(n_files)])
+            files = files_leg(pkg, fds, min(n_files, len(fds["qnames"])), list(range(world)), chunk, rec_host.numpy(), cnt_host.numpy(), fmax)
         if cpu_group is not None:
             dist.barrier(group=cpu_group)
 

@@ -253,9 +253,22 @@ void decode_rows(const QueryIndex & idx, size_t first, size_t count, const std::
       }
       else
       {
-        // one unwrapped line is the common case: a straight upper-casing copy
+        // one unwrapped line is the common case: a straight upper-casing copy (a loop the compiler vectorises) that
+        // also notices white space; wrapped or padded records take the byte-wise path
         const char * p = r.seq;
         size_t k = 0;
+        if ((size_t) (r.seq_end - r.seq) >= sites)
+        {
+          const unsigned char * src = reinterpret_cast<const unsigned char *>(r.seq);
+          unsigned char odd = 0;
+          for (size_t i = 0; i < sites; ++i)
+          {
+            const unsigned char c = src[i];
+            odd |= (unsigned char) (c <= ' ');
+            dst[i] = (uint8_t) (c - (((unsigned char) (c - 'a') < 26) ? 32 : 0));
+          }
+          if (!odd) k = sites;
+        }
         while (p < r.seq_end && k < sites)
         {
           const unsigned char c = (unsigned char) *p++;
@@ -296,7 +309,9 @@ inline size_t put_u64(char * out, uint64_t v)
 // exactly `width` digits of v (v < 10^width), zero padded
 inline void put_u64_padded(char * out, uint64_t v, int width)
 {
-  for (int i = width - 1; i >= 0; --i) { out[i] = (char) ('0' + v % 10); v /= 10; }
+  int i = width;
+  while (i >= 2) { const unsigned r = (unsigned) (v % 100); v /= 100; i -= 2; out[i] = kDigits2[2 * r]; out[i + 1] = kDigits2[2 * r + 1]; }
+  if (i == 1) out[0] = (char) ('0' + v % 10);
 }
 }  // namespace
 

@@ -195,7 +195,9 @@ extern "C" int epa_run_files_multi(const char * tree_file, const char * ref_msa_
     const size_t slot_q = (size_t) std::min<uint64_t>(q_upper, chunk_size);
     const size_t slots_upper = std::min<size_t>((q_upper + slot_q - 1) / slot_q, 3 * (size_t) n_devices + 2);
     std::vector<Slot> slots(slots_upper);
-    size_t slots_wanted = slots_upper;                 // lowered (under mu) once the real chunk count is known
+    // until the query file is indexed only the slots every run needs are made; the final number follows the chunk count
+    size_t slots_wanted = std::min<size_t>(slots_upper, (size_t) n_devices + 2);
+    bool slots_final = false;
     struct PinnedGuard {
       std::mutex m;
       std::vector<std::pair<void *, size_t>> p;
@@ -215,7 +217,11 @@ extern "C" int epa_run_files_multi(const char * tree_file, const char * ref_msa_
       {
         for (size_t i = 0; i < slots.size(); ++i)
         {
-          { std::lock_guard<std::mutex> lk(mu); if (i >= slots_wanted || rc_all != EPA_OK) break; }
+          {
+            std::unique_lock<std::mutex> lk(mu);
+            cv.wait(lk, [&]() { return i < slots_wanted || slots_final || rc_all != EPA_OK; });
+            if (i >= slots_wanted || rc_all != EPA_OK) break;
+          }
           Slot & sl = slots[i];
           sl.rows = static_cast<uint8_t *>(pinned.get(std::max<size_t>(1, slot_q * ref_sites0)));
           sl.recs = static_cast<epa_placement *>(pinned.get(std::max<size_t>(1, slot_q * fmax * sizeof(epa_placement))));
@@ -228,8 +234,9 @@ extern "C" int epa_run_files_multi(const char * tree_file, const char * ref_msa_
     });
     struct Joiner {
       std::thread & t; std::mutex & m; size_t & wanted;
-      ~Joiner() { { std::lock_guard<std::mutex> lk(m); wanted = 0; } if (t.joinable()) t.join(); }
-    } allocator_joiner{allocator, mu, slots_wanted};
+      bool & final_; std::condition_variable & c;
+      ~Joiner() { { std::lock_guard<std::mutex> lk(m); if (!final_) { wanted = 0; final_ = true; } } c.notify_all(); if (t.joinable()) t.join(); }
+    } allocator_joiner{allocator, mu, slots_wanted, slots_final, cv};
 
     // first pass over the queries: records, width, all-gap columns
     const QueryIndex qidx = index_queries(qfile, query_file, host_threads, opts->premasking != 0);
@@ -321,7 +328,12 @@ extern "C" int epa_run_files_multi(const char * tree_file, const char * ref_msa_
     // still being copied out, one prefetched; plus one being decoded and one being formatted.
     const size_t pchunk = (size_t) std::min<uint64_t>(std::max<uint64_t>(Q, 1), (uint64_t) chunk_size);
     const size_t n_chunks = (size_t) ((Q + pchunk - 1) / pchunk);
-    { std::lock_guard<std::mutex> lk(mu); slots_wanted = std::min<size_t>(slots_upper, std::max<size_t>(1, std::min<size_t>(n_chunks, 3 * (size_t) n_devices + 2))); }
+    {
+      std::lock_guard<std::mutex> lk(mu);
+      slots_wanted = std::min<size_t>(slots_upper, std::max<size_t>(1, std::min<size_t>(n_chunks, 3 * (size_t) n_devices + 2)));
+      slots_final = true;
+    }
+    cv.notify_all();
 
     const bool debug = std::getenv("EPA_B200_PIPE_DEBUG") != nullptr;
     const auto t1 = std::chrono::steady_clock::now();
