@@ -65,9 +65,9 @@ struct AaSmem {
   static constexpr int DG = LB + 3 * 5 * 32;           // [R][3: e, lambda e, lambda^2 e][AA_SP] decay factors (per evaluation)
   static constexpr int FR = DG + R * 3 * AA_SP;        // [AA_SP] stationary frequencies, padded
   static constexpr int EX = FR + AA_SP;                // [R][S] expm1 / exp scratch
-  static constexpr int V = EX + R * S;                 // [S][S] (lane-divergent indexing while a matrix is built)
-  static constexpr int VINV = V + S * S;
-  static constexpr int RED = VINV + S * S;             // [2][AA_WARPS] block-reduction scratch
+  static constexpr int VA = EX + R * S;                // [3][5][32] Vinv as A fragments (matrix build)
+  static constexpr int VN = VA + 3 * 5 * 32;           // [3][5][32] V as B fragments in natural order (matrix build)
+  static constexpr int RED = VN + 3 * 5 * 32;          // [2][AA_WARPS] block-reduction scratch
   static constexpr int TOTAL = RED + 2 * AA_WARPS;
 };
 
@@ -95,22 +95,34 @@ __device__ __forceinline__ int aa_pb_index(int r, int i, int j)
 // state index that lane q's C-layout slot (t, slot) holds = k-step kk' = 2 t + slot of the permuted order
 __device__ __forceinline__ int aa_perm(int kk, int q) { return 8 * (kk >> 1) + 2 * q + (kk & 1); }
 
-// P[r][i][j] = delta_ij + sum_k Vinv[i][k] expm1(lambda_k rate_r t) V[k][j]   (LP/core_pmatrix.c:185-249), fragment order
+// P[r][i][j] = delta_ij + sum_k Vinv[i][k] expm1(lambda_k rate_r t) V[k][j]   (LP/core_pmatrix.c:185-249), written in
+// fragment order. One 8 x 8 tile of one rate per warp task: five MMA k-steps with A = Vinv[i][k] expm1_k (the constant
+// fragment scaled by this lane's k) and B = V[k][j].
 template <int R>
 __device__ __forceinline__ void aa_pmatrix(double * sm, double t, int which)
 {
   using L = AaSmem<R>;
   constexpr int S = 20;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, q = lane & 3;
+  __syncthreads();                                     // readers of EX and of the matrix being replaced are done
   for (int idx = threadIdx.x; idx < R * S; idx += AA_THREADS)
     sm[L::EX + idx] = expm1(c_model.eigenvals[idx % S] * c_model.rates[idx / S] * t);
   __syncthreads();
   double * P = sm + L::PB + which * L::PB_MAT;
-  for (int idx = threadIdx.x; idx < R * S * S; idx += AA_THREADS)
+  #pragma unroll 1
+  for (int task = warp; task < R * 9; task += AA_WARPS)
   {
-    const int r = idx / (S * S), i = (idx / S) % S, j = idx % S;
-    double acc = (i == j) ? 1.0 : 0.0;
-    for (int k = 0; k < S; ++k) acc += (sm[L::VINV + i * S + k] * sm[L::EX + r * S + k]) * sm[L::V + k * S + j];
-    P[aa_pb_index(r, i, j)] = acc;
+    const int r = task / 9, ti = (task % 9) / 3, tj = task % 3;
+    double c[2] = {0.0, 0.0};
+    #pragma unroll
+    for (int kk = 0; kk < 5; ++kk)
+      dmma884(c, sm[L::VA + (ti * 5 + kk) * 32 + lane] * sm[L::EX + r * S + 4 * kk + q], sm[L::VN + (tj * 5 + kk) * 32 + lane]);
+    const int i = 8 * ti + g, j = 8 * tj + 2 * q;
+    if (i < S && j < S)
+    {
+      P[aa_pb_index(r, i, j)] = c[0] + (i == j ? 1.0 : 0.0);
+      P[aa_pb_index(r, i, j + 1)] = c[1] + (i == j + 1 ? 1.0 : 0.0);
+    }
   }
   __syncthreads();
 }
@@ -445,10 +457,12 @@ blo_aa_kernel(BloArgs a, const double * __restrict__ clvT, size_t t_stride)
   // constant tables: V / Vinv copies, padded frequencies, tip factors, B fragments of V and pi Vinv; zeroed matrix pads
   for (int i = threadIdx.x; i < L::TOTAL; i += AA_THREADS) sm[i] = 0.0;
   __syncthreads();
-  for (int i = threadIdx.x; i < S * S; i += AA_THREADS)
+  for (int idx = threadIdx.x; idx < 3 * 5 * 32; idx += AA_THREADS)
   {
-    sm[L::V + i] = c_model.eigenvecs[i];
-    sm[L::VINV + i] = c_model.inv_eigenvecs[i];
+    const int t = idx / (5 * 32), kk = (idx / 32) % 5, ln = idx & 31;
+    const int row = 8 * t + (ln >> 2), k = 4 * kk + (ln & 3);
+    sm[L::VA + idx] = row < S ? c_model.inv_eigenvecs[row * S + k] : 0.0;        // A[i][k] = Vinv[i][k]
+    sm[L::VN + idx] = row < S ? c_model.eigenvecs[k * S + row] : 0.0;            // B[k][j] = V[k][j], j = row
   }
   for (int i = threadIdx.x; i < S; i += AA_THREADS) sm[L::FR + i] = c_model.freqs[i];
   for (int i = threadIdx.x; i < ncodes * S; i += AA_THREADS)
