@@ -176,10 +176,11 @@ def ncu_profile(kernel):
     return None
 
 
-def ncu_fp64_per_pair():
+def ncu_fp64_per_pair(variant="blo_site"):
     """Executed fp64 warp instructions per (query, edge) pair of blo_site_kernel, from the committed capture's
-    'fp64_warp_instructions_per_pair' line (profiles/r2_ncu_blo_site.txt)."""
-    path = ncu_profile("blo_site_kernel")
+    'fp64_warp_instructions_per_pair' line: profiles/r2_ncu_blo_site.txt (one eigenvalue group, the BASELINE model),
+    ..._general_gtr.txt (three groups), ..._per_rate.txt (per-rate scalers, cfg5)."""
+    path = ncu_profile(variant + "_kernel")
     if not path:
         return None
     for line in open(path):
@@ -595,8 +596,12 @@ def ours(args):
             # fp64 roofline: measured DFMA peak of this GPU (epa_measure_fp64_peak) against the kernel's executed fp64
             # warp instructions per pair from the committed ncu capture (x 32 lanes x 2 flops).
             fp64_peak = capi.measure_fp64_peak(local)
-            per_pair = ncu_fp64_per_pair()
-            roofline["fp64"] = {"peak_tflops_measured": fp64_peak, "fp64_warp_instructions_per_pair_ncu": per_pair}
+            ev = sorted(session.parse_model(ds["model"])["eigenvals"])
+            groups = 1 + sum(abs(a - b) > 1e-13 * abs(ev[0]) for a, b in zip(ev[:-1], ev[1:-1]))     # distinct non-zero eigenvalues
+            variant = "blo_site_per_rate" if sr > 1 else {1: "blo_site", 3: "blo_site_general_gtr"}.get(groups)
+            per_pair = ncu_fp64_per_pair(variant) if variant else None
+            roofline["fp64"] = {"peak_tflops_measured": fp64_peak, "fp64_warp_instructions_per_pair_ncu": per_pair,
+                                "kernel_variant": variant}
             if per_pair:
                 ach = pairs * per_pair * 64.0 / (kernels[dom]["ms_per_step"] / 1e3) / 1e12
                 roofline["fp64"].update({"achieved_tflops": ach, "frac": ach / fp64_peak})
