@@ -84,9 +84,11 @@ collect_kernel(CollectArgs a)
     bool take;
     if (a.acc_mode)
     {
-      // until_accumulated_reached: add while summed < max and sum < thresh, then at least min
+      // until_accumulated_reached (src/set_manipulators.cpp:90-113): add while summed < max and sum < thresh; the
+      // iterator is then advanced to begin + min - 1, i.e. max(summed, min - 1) entries are kept (none for thresh = 0
+      // and min = 1)
       if (acc_open && (uint32_t) summed < a.fmax && acc < a.thresh) { acc += lwr; ++summed; take = true; }
-      else { acc_open = false; take = (uint32_t) kept < a.fmin; }
+      else { acc_open = false; take = (uint32_t) kept + 1 < a.fmin; }
     }
     else
     {

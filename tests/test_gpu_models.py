@@ -28,6 +28,13 @@ def _opts(capi, extra):
         elif a == "--filter-max":
             i += 1
             kw["filter_max"] = int(extra[i])
+        elif a == "--filter-min":
+            i += 1
+            kw["filter_min"] = int(extra[i])
+        elif a == "--filter-acc-lwr":
+            i += 1
+            kw["filter_acc_lwr"] = 1
+            kw["support_threshold"] = float(extra[i])
         else:
             raise AssertionError(f"option {a} not mapped")
         i += 1
@@ -94,3 +101,13 @@ def test_no_pre_mask(built, tmp_path):
     g = json.load(open(os.path.join(d, "reference_nopremask.json")))
     files = (os.path.join(d, "tree.nwk"), os.path.join(d, "ref.fasta"), os.path.join(d, "query.fasta"))
     _run(built, tmp_path, "nopremask", files, g["model"], g["extra"], g["placements"])
+
+
+ACC = json.load(open(os.path.join(helpers.GOLDEN, "cfg1", "reference_accmin.json")))
+
+
+@pytest.mark.parametrize("key", sorted(ACC))
+def test_accumulated_filter_with_minimum(built, tmp_path, key):
+    """--filter-acc-lwr with --filter-min: the reference keeps max(summed, min - 1) entries
+    (until_accumulated_reached, src/set_manipulators.cpp:90-113; tests/golden/make_golden_accmin.py)."""
+    _run(built, tmp_path, key, CFG1, ACC[key]["model"], ACC[key]["extra"], ACC[key]["placements"])
