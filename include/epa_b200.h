@@ -15,7 +15,10 @@
  *   - plain C types only; every pointer is a HOST pointer unless the name ends in _dev
  *   - all functions return 0 on success, a negative epa_status otherwise; epa_last_error() gives
  *     the message (the reference throws std::runtime_error, e.g. Tiny_Tree.cpp:145-156,209-212)
- *   - calls on one epa_ctx must be serialised by the caller (one host thread per GPU)
+ *   - calls on one epa_ctx must be serialised by the caller (one host thread per GPU); contexts on DIFFERENT
+ *     devices may be driven concurrently from different threads (epa_run_files_multi does), contexts on the SAME
+ *     device must not: the model tables live in one __constant__ symbol per device, bound by the context that
+ *     launches (switching contexts on one thread is fine)
  *   - the library never falls back to a CPU path: without a CUDA device every compute entry
  *     point fails with EPA_ERR_CUDA
  *
