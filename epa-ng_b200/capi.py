@@ -89,6 +89,7 @@ SYMBOLS = [
     ("epa_num_pairs", C.c_int, [_vp, C.POINTER(C.c_uint64)]),
     ("epa_synchronize", C.c_int, [_vp]),
     ("epa_measure_fp64_peak", C.c_int, [C.c_int, C.POINTER(C.c_double)]),
+    ("epa_device_pool_trim", None, []),
     ("epa_pinned_alloc", C.c_int, [C.POINTER(_vp), C.c_size_t]),
     ("epa_pinned_free", None, [_vp]),
     ("epa_launch_count", C.c_uint64, [_vp]),

@@ -115,6 +115,14 @@ __device__ __forceinline__ void store_vec(double * __restrict__ p, const double 
   for (int i = 0; i < S / 2; ++i) p2[i] = make_double2(v[2 * i], v[2 * i + 1]);
 }
 
+// ---- device memory through a per-process block cache (defined in epa_b200.cu) -----------------
+// Allocating and freeing several GB per context makes cudaMalloc / cudaFree stall for hundreds of milliseconds now and
+// then; blocks of destroyed contexts are kept per device (up to EPA_B200_DEVICE_POOL_MB, default 16384; 0 = off) and
+// handed to the next context that asks for a similar size. dev_free waits for the device like cudaFree does.
+cudaError_t dev_alloc_raw(void ** p, size_t bytes);
+void dev_free(void * p);
+template <class T> inline cudaError_t dev_alloc(T ** p, size_t bytes) { return dev_alloc_raw(reinterpret_cast<void **>(p), bytes); }
+
 // ---- mbarrier / bulk-copy (TMA 1D) helpers, sm_90+ PTX -------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void * p)
 {

@@ -27,6 +27,122 @@ using namespace epa;
 static_assert(sizeof(epa_placement) == sizeof(PlacementRec), "record layout");
 static_assert(sizeof(epa_placement) == 40, "Placement is 40 bytes");
 
+
+// ---- device block cache (common.cuh) -----------------------------------------------------------
+namespace epa {
+namespace devpool_detail {
+struct DevPool {
+  std::mutex m;
+  struct Block { void * p; size_t cap; int dev; };
+  std::vector<Block> idle;
+  std::vector<Block> live;
+  size_t idle_bytes = 0;
+  size_t limit = 0;
+  bool init = false;
+  void setup()
+  {
+    if (init) return;
+    init = true;
+    const char * v = getenv("EPA_B200_DEVICE_POOL_MB");
+    limit = (size_t) (v ? std::max(0, atoi(v)) : 16384) << 20;
+  }
+};
+DevPool g_devpool;
+}  // namespace devpool_detail
+using devpool_detail::DevPool;
+using devpool_detail::g_devpool;
+
+cudaError_t dev_alloc_raw(void ** p, size_t bytes)
+{
+  *p = nullptr;
+  if (bytes == 0) bytes = 1;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return cudaGetLastError();
+  // sizes in 2 MB steps above 2 MB (the driver's own granularity): the same buffer of the next context fits
+  const size_t cap = bytes > (2u << 20) ? (bytes + (2u << 20) - 1) & ~(size_t) ((2u << 20) - 1) : bytes;
+  {
+    std::lock_guard<std::mutex> lk(g_devpool.m);
+    g_devpool.setup();
+    size_t best = g_devpool.idle.size();
+    for (size_t i = 0; i < g_devpool.idle.size(); ++i)
+    {
+      const auto & b = g_devpool.idle[i];
+      if (b.dev == dev && b.cap >= cap && b.cap <= cap + cap / 4 + (1u << 20) &&
+          (best == g_devpool.idle.size() || b.cap < g_devpool.idle[best].cap)) best = i;
+    }
+    if (best != g_devpool.idle.size())
+    {
+      DevPool::Block b = g_devpool.idle[best];
+      g_devpool.idle.erase(g_devpool.idle.begin() + (long) best);
+      g_devpool.idle_bytes -= b.cap;
+      g_devpool.live.push_back(b);
+      *p = b.p;
+      return cudaSuccess;
+    }
+  }
+  cudaError_t e = cudaMalloc(p, cap);
+  if (e != cudaSuccess)
+  {
+    // out of memory: give the cached blocks of this device back and try once more
+    (void) cudaGetLastError();
+    std::vector<void *> drop;
+    {
+      std::lock_guard<std::mutex> lk(g_devpool.m);
+      for (size_t i = g_devpool.idle.size(); i-- > 0;)
+        if (g_devpool.idle[i].dev == dev)
+        {
+          drop.push_back(g_devpool.idle[i].p);
+          g_devpool.idle_bytes -= g_devpool.idle[i].cap;
+          g_devpool.idle.erase(g_devpool.idle.begin() + (long) i);
+        }
+    }
+    for (void * q : drop) (void) cudaFree(q);
+    e = cudaMalloc(p, cap);
+    if (e != cudaSuccess) return e;
+  }
+  std::lock_guard<std::mutex> lk(g_devpool.m);
+  g_devpool.live.push_back({*p, cap, dev});
+  return cudaSuccess;
+}
+
+void dev_free(void * p)
+{
+  if (!p) return;
+  DevPool::Block b{p, 0, -1};
+  {
+    std::lock_guard<std::mutex> lk(g_devpool.m);
+    for (size_t i = 0; i < g_devpool.live.size(); ++i)
+      if (g_devpool.live[i].p == p) { b = g_devpool.live[i]; g_devpool.live.erase(g_devpool.live.begin() + (long) i); break; }
+  }
+  if (b.dev < 0) { (void) cudaFree(p); return; }            // not ours
+  int cur = 0;
+  (void) cudaGetDevice(&cur);
+  if (cur != b.dev) (void) cudaSetDevice(b.dev);
+  (void) cudaDeviceSynchronize();                            // nothing in flight still uses the block (cudaFree semantics)
+  bool keep = false;
+  {
+    std::lock_guard<std::mutex> lk(g_devpool.m);
+    if (g_devpool.idle_bytes + b.cap <= g_devpool.limit) { g_devpool.idle.push_back(b); g_devpool.idle_bytes += b.cap; keep = true; }
+  }
+  if (!keep) (void) cudaFree(p);
+  if (cur != b.dev) (void) cudaSetDevice(cur);
+}
+}  // namespace epa
+
+extern "C" void epa_device_pool_trim(void)
+{
+  std::vector<epa::devpool_detail::DevPool::Block> drop;
+  {
+    std::lock_guard<std::mutex> lk(epa::devpool_detail::g_devpool.m);
+    drop.swap(epa::devpool_detail::g_devpool.idle);
+    epa::devpool_detail::g_devpool.idle_bytes = 0;
+  }
+  int cur = 0;
+  (void) cudaGetDevice(&cur);
+  for (auto & b : drop) { (void) cudaSetDevice(b.dev); (void) cudaFree(b.p); }
+  (void) cudaSetDevice(cur);
+}
+
 namespace {
 
 thread_local std::string g_create_error;
@@ -37,15 +153,15 @@ struct DevBuf {
   cudaError_t ensure(size_t bytes)
   {
     if (bytes <= cap) return cudaSuccess;
-    if (p) { cudaFree(p); p = nullptr; cap = 0; }
+    if (p) { dev_free(p); p = nullptr; cap = 0; }
     // grow with some slack so that slightly larger chunks do not reallocate
     const size_t want = bytes + bytes / 8 + 256;
-    cudaError_t e = cudaMalloc(&p, want);
-    if (e != cudaSuccess) { (void) cudaGetLastError(); e = cudaMalloc(&p, bytes); }
+    cudaError_t e = dev_alloc(&p, want);
+    if (e != cudaSuccess) { (void) cudaGetLastError(); e = dev_alloc(&p, bytes); }
     if (e == cudaSuccess) cap = (want > bytes && p) ? want : bytes;
     return e;
   }
-  void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+  void release() { if (p) dev_free(p); p = nullptr; cap = 0; }
   template <typename T> T * as() const { return static_cast<T *>(p); }
 };
 
@@ -289,9 +405,9 @@ extern "C" void epa_ctx_destroy(epa_ctx * ctx)
   if (ctx->ev_copy) cudaEventDestroy(ctx->ev_copy);
   if (ctx->ev_collect) cudaEventDestroy(ctx->ev_collect);
   for (auto & e : ctx->ev_d2h) if (e) cudaEventDestroy(e);
-  cudaFree(ctx->d_model); cudaFree(ctx->tree.clv); cudaFree(ctx->tree.scaler); cudaFree(ctx->d_edges);
-  cudaFree(const_cast<double *>(ctx->tree.inv));
-  cudaFree(ctx->d_lookup); cudaFree(ctx->d_pairtab); cudaFree(ctx->d_clvT); cudaFree(ctx->d_gT); cudaFree(ctx->d_btab); cudaFree(ctx->d_pn); cudaFree(ctx->d_flags); cudaFree(ctx->d_counter); cudaFree(ctx->d_total);
+  dev_free(ctx->d_model); dev_free(ctx->tree.clv); dev_free(ctx->tree.scaler); dev_free(ctx->d_edges);
+  dev_free(const_cast<double *>(ctx->tree.inv));
+  dev_free(ctx->d_lookup); dev_free(ctx->d_pairtab); dev_free(ctx->d_clvT); dev_free(ctx->d_gT); dev_free(ctx->d_btab); dev_free(ctx->d_pn); dev_free(ctx->d_flags); dev_free(ctx->d_counter); dev_free(ctx->d_total);
   for (auto & e : ctx->ev) if (e) cudaEventDestroy(e);
   if (ctx->stream && ctx->own_stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
@@ -463,31 +579,31 @@ extern "C" int epa_ctx_create(epa_ctx ** out, int device, const epa_model_desc *
       }
     }
     double * d_inv = nullptr;
-    CUC(cudaMalloc(&d_inv, inv.size() * sizeof(double)));
+    CUC(dev_alloc(&d_inv, inv.size() * sizeof(double)));
     ctx->tree.inv = d_inv;
     CUC(cudaMemcpy(d_inv, inv.data(), inv.size() * sizeof(double), cudaMemcpyHostToDevice));
   }
-  CUC(cudaMalloc(&ctx->d_model, sizeof(DevModel)));
+  CUC(dev_alloc(&ctx->d_model, sizeof(DevModel)));
   CUC(cudaMemcpy(ctx->d_model, &m, sizeof(DevModel), cudaMemcpyHostToDevice));
   ctx->tree.clv_stride = (size_t) m.n * R * S;
   ctx->tree.n_tips = n_tips; ctx->tree.n_nodes = ctx->n_nodes;
-  CUC(cudaMalloc(&ctx->tree.clv, ctx->tree.clv_stride * ctx->n_nodes * sizeof(double)));
+  CUC(dev_alloc(&ctx->tree.clv, ctx->tree.clv_stride * ctx->n_nodes * sizeof(double)));
   ctx->tree.sr = m.per_rate ? (uint32_t) R : 1u;
-  CUC(cudaMalloc(&ctx->tree.scaler, (size_t) m.n * ctx->tree.sr * ctx->n_nodes * sizeof(uint32_t)));
+  CUC(dev_alloc(&ctx->tree.scaler, (size_t) m.n * ctx->tree.sr * ctx->n_nodes * sizeof(uint32_t)));
   CUC(cudaMemset(ctx->tree.scaler, 0, (size_t) m.n * ctx->tree.sr * ctx->n_nodes * sizeof(uint32_t)));
   ctx->h_edges.resize(n_edges);
   for (uint32_t i = 0; i < n_edges; ++i) ctx->h_edges[i] = EdgeDev{edges[i].distal, edges[i].proximal, edges[i].length};
-  CUC(cudaMalloc(&ctx->d_edges, n_edges * sizeof(EdgeDev)));
+  CUC(dev_alloc(&ctx->d_edges, n_edges * sizeof(EdgeDev)));
   CUC(cudaMemcpy(ctx->d_edges, ctx->h_edges.data(), n_edges * sizeof(EdgeDev), cudaMemcpyHostToDevice));
-  CUC(cudaMalloc(&ctx->d_flags, 16 * sizeof(int)));
+  CUC(dev_alloc(&ctx->d_flags, 16 * sizeof(int)));
   CUC(cudaMemset(ctx->d_flags, 0, 16 * sizeof(int)));
-  CUC(cudaMalloc(&ctx->d_counter, sizeof(unsigned long long)));
-  CUC(cudaMalloc(&ctx->d_total, 2 * sizeof(uint64_t)));
+  CUC(dev_alloc(&ctx->d_counter, sizeof(unsigned long long)));
+  CUC(dev_alloc(&ctx->d_total, 2 * sizeof(uint64_t)));
 
   // tips -> 0/1 CLVs
   {
     uint32_t * d_masks = nullptr;
-    CUC(cudaMalloc(&d_masks, tip_sites * sizeof(uint32_t)));
+    CUC(dev_alloc(&d_masks, tip_sites * sizeof(uint32_t)));
     CUC(cudaMemcpy(d_masks, tip_masks, tip_sites * sizeof(uint32_t), cudaMemcpyHostToDevice));
     const unsigned blocks = (unsigned) ((tip_sites + 255) / 256);
     if (S == 4) tip_expand_kernel<4><<<blocks, 256, 0, ctx->stream>>>(ctx->d_model, ctx->tree, d_masks, tip_sites);
@@ -495,7 +611,7 @@ extern "C" int epa_ctx_create(epa_ctx ** out, int device, const epa_model_desc *
     ctx->launches++;
     CUC(cudaGetLastError());
     CUC(cudaStreamSynchronize(ctx->stream));
-    cudaFree(d_masks);
+    dev_free(d_masks);
   }
   {
     std::lock_guard<std::mutex> lock(g_const_mutex);
@@ -603,9 +719,9 @@ extern "C" int epa_compute_clvs(epa_ctx * ctx, const epa_clv_op * ops, uint32_t 
 
   const size_t pm = (size_t) ctx->R * ctx->S * ctx->S;
   ClvOpDev * d_ops = nullptr; double * d_len = nullptr; double * d_pm = nullptr;
-  CU(cudaMalloc(&d_ops, hops.size() * sizeof(ClvOpDev)));
-  CU(cudaMalloc(&d_len, lengths.size() * sizeof(double)));
-  CU(cudaMalloc(&d_pm, lengths.size() * pm * sizeof(double)));
+  CU(dev_alloc(&d_ops, hops.size() * sizeof(ClvOpDev)));
+  CU(dev_alloc(&d_len, lengths.size() * sizeof(double)));
+  CU(dev_alloc(&d_pm, lengths.size() * pm * sizeof(double)));
   CU(cudaMemcpyAsync(d_ops, hops.data(), hops.size() * sizeof(ClvOpDev), cudaMemcpyHostToDevice, ctx->stream));
   CU(cudaMemcpyAsync(d_len, lengths.data(), lengths.size() * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
   if (int rc = launch_pmatrices(ctx, d_len, d_pm, (uint32_t) lengths.size())) return rc;
@@ -618,7 +734,7 @@ extern "C" int epa_compute_clvs(epa_ctx * ctx, const epa_clv_op * ops, uint32_t 
     LAUNCHED(ctx);
   }
   CU(cudaStreamSynchronize(ctx->stream));
-  cudaFree(d_ops); cudaFree(d_len); cudaFree(d_pm);
+  dev_free(d_ops); dev_free(d_len); dev_free(d_pm);
   for (auto & o : hops) ctx->slot_filled[o.parent] = 1;
   ctx->clvs_ready = true;
   ctx->lookup_ready = false;
@@ -716,7 +832,7 @@ extern "C" int epa_build_lookup(epa_ctx * ctx)
   const size_t pm = (size_t) R * S * S;
   const uint32_t B = ctx->n_edges;
   const size_t lookup_doubles = (size_t) B * ctx->n_pad * K;
-  if (!ctx->d_lookup) CU(cudaMalloc(&ctx->d_lookup, lookup_doubles * sizeof(double)));
+  if (!ctx->d_lookup) CU(dev_alloc(&ctx->d_lookup, lookup_doubles * sizeof(double)));
   if (ctx->n_pad != n)      // pad rows must read as zero; every real row is written by the kernel
     CU(cudaMemsetAsync(ctx->d_lookup, 0, lookup_doubles * sizeof(double), ctx->stream));
 
@@ -779,9 +895,9 @@ extern "C" int epa_build_lookup(epa_ctx * ctx)
     const int kc_total = mma_kc_total(n);
     const uint32_t n_eb = (B + MMA_EB - 1) / MMA_EB;
     const size_t btab_bytes = (size_t) n_eb * kc_total * MMA_B_CHUNK_BYTES;
-    if (!ctx->d_btab) CU(cudaMalloc(&ctx->d_btab, btab_bytes));
+    if (!ctx->d_btab) CU(dev_alloc(&ctx->d_btab, btab_bytes));
     const uint32_t e_pad = n_eb * MMA_EB;
-    if (!ctx->d_pn) CU(cudaMalloc(&ctx->d_pn, (size_t) e_pad * (n + 1) * sizeof(double)));
+    if (!ctx->d_pn) CU(dev_alloc(&ctx->d_pn, (size_t) e_pad * (n + 1) * sizeof(double)));
     CU(cudaMemsetAsync(ctx->d_pn, 0, (size_t) e_pad * (n + 1) * sizeof(double), ctx->stream));
     CU(cudaMemsetAsync(ctx->d_btab, 0, btab_bytes, ctx->stream));
     CU(cudaMemsetAsync(ctx->d_flags + 6, 0, sizeof(int), ctx->stream));
@@ -1034,7 +1150,7 @@ int launch_preplace_pair(epa_ctx * ctx, uint32_t count, const int2 * range, int 
   if (!ctx->pairtab_ready)
   {
     const size_t pair_doubles = (size_t) ctx->n_edges * (ctx->n_pad / 2) * PAIR_ROW;
-    if (!ctx->d_pairtab) CU(cudaMalloc(&ctx->d_pairtab, pair_doubles * sizeof(double)));
+    if (!ctx->d_pairtab) CU(dev_alloc(&ctx->d_pairtab, pair_doubles * sizeof(double)));
     pairtab_build_kernel<<<(unsigned) ((pair_doubles + 255) / 256), 256, 0, ctx->stream>>>(ctx->d_lookup, ctx->n_pad, ctx->n_edges, ctx->d_pairtab);
     LAUNCHED(ctx);
     ctx->pairtab_ready = true;
@@ -1330,7 +1446,7 @@ int ensure_clvT(epa_ctx * ctx)
   if (ctx->clvT_ready) return EPA_OK;
   const int C = ctx->R * ctx->S;
   const size_t t_stride = (size_t) ((ctx->n + CLVT_BLOCK - 1) / CLVT_BLOCK) * (size_t) C * CLVT_BLOCK;
-  if (!ctx->d_clvT) CU(cudaMalloc(&ctx->d_clvT, (size_t) ctx->n_nodes * t_stride * sizeof(double)));
+  if (!ctx->d_clvT) CU(dev_alloc(&ctx->d_clvT, (size_t) ctx->n_nodes * t_stride * sizeof(double)));
   dim3 grid((ctx->n + CLVT_BLOCK - 1) / CLVT_BLOCK, ctx->n_nodes);
   clv_site_block_kernel<<<grid, 256, (size_t) CLVT_BLOCK * (C + 1) * sizeof(double), ctx->stream>>>(
       ctx->tree.clv, ctx->tree.clv_stride, ctx->n, C, ctx->d_clvT, t_stride);
@@ -1350,7 +1466,7 @@ int ensure_clvT(epa_ctx * ctx)
   double * d_len = ctx->tmp.as<double>(), * d_pm = d_len + B;
   CU(cudaMemcpyAsync(d_len, lengths.data(), B * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
   if (int rc = launch_pmatrices(ctx, d_len, d_pm, B)) return rc;
-  if (!ctx->d_gT && cudaMalloc(&ctx->d_gT, (size_t) B * t_stride * sizeof(double)) != cudaSuccess)
+  if (!ctx->d_gT && dev_alloc(&ctx->d_gT, (size_t) B * t_stride * sizeof(double)) != cudaSuccess)
   {
     (void) cudaGetLastError();
     ctx->d_gT = nullptr;                         // optional table: the kernel then runs the full first pass
@@ -1765,7 +1881,7 @@ extern "C" int epa_measure_fp64_peak(int device, double * tflops)
   if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { (void) cudaGetLastError(); return EPA_ERR_CUDA; }
   const int blocks = prop.multiProcessorCount * 2, threads = 512, iters = 20000;
   double * out = nullptr;
-  if (cudaMalloc(&out, (size_t) blocks * threads * sizeof(double)) != cudaSuccess) { (void) cudaGetLastError(); return EPA_ERR_NOMEM; }
+  if (dev_alloc(&out, (size_t) blocks * threads * sizeof(double)) != cudaSuccess) { (void) cudaGetLastError(); return EPA_ERR_NOMEM; }
   cudaEvent_t e0, e1;
   cudaEventCreate(&e0); cudaEventCreate(&e1);
   float best = 0.0f;
@@ -1780,7 +1896,7 @@ extern "C" int epa_measure_fp64_peak(int device, double * tflops)
     if (rep > 0 && (best == 0.0f || ms < best)) best = ms;
   }
   cudaEventDestroy(e0); cudaEventDestroy(e1);
-  cudaFree(out);
+  dev_free(out);
   if (cudaGetLastError() != cudaSuccess || best <= 0.0f) return EPA_ERR_CUDA;
   *tflops = 2.0 * (double) blocks * threads * iters * 64.0 / (best * 1e-3) / 1e12;
   return EPA_OK;

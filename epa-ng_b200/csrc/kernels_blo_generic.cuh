@@ -807,9 +807,9 @@ inline cudaError_t launch_blo_generic_sr(int sm_count, size_t smem_optin, int ma
   const size_t need = (size_t) grid * (1 + L::NK) * wpad * sizeof(double);
   if (need > *scratch_cap)
   {
-    if (*scratch) cudaFree(*scratch);
+    if (*scratch) dev_free(*scratch);
     *scratch = nullptr; *scratch_cap = 0;
-    cudaError_t e = cudaMalloc(scratch, need);
+    cudaError_t e = dev_alloc(scratch, need);
     if (e != cudaSuccess) return e;
     *scratch_cap = need;
   }

@@ -235,6 +235,10 @@ int epa_synchronize(epa_ctx * ctx);
 /* Measured fp64 FMA throughput of the device (TFLOP/s, 2 flops per DFMA lane): an unrolled stream of
  * independent DFMAs on every SM. The roofline denominator of the fp64-bound thorough kernel. */
 int epa_measure_fp64_peak(int device, double * tflops);
+/* The library keeps the device memory blocks of destroyed contexts (per device, up to EPA_B200_DEVICE_POOL_MB MB in the
+ * environment, default 16384, 0 = off) for the next context - allocating and freeing several GB per context otherwise
+ * stalls for hundreds of milliseconds now and then. This call returns the cached blocks to the driver. */
+void epa_device_pool_trim(void);
 /* Page-locked host memory for query rows and result records (full PCIe speed, asynchronous copies). */
 int epa_pinned_alloc(void ** ptr, size_t bytes);
 void epa_pinned_free(void * ptr);
