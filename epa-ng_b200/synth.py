@@ -12,10 +12,12 @@ DNA = "ACGT"
 AA = "ARNDCQEGHILKMFPSTWYV"
 
 
-def random_tree(T: int, seed: int = 1):
+def random_tree(T: int, seed: int = 1, ladder: float = 0.0, brlen: float = 0.05):
     """Random topology by repeatedly joining two active nodes until 3 remain (trifurcating root);
-    branch lengths Exp(mean 0.05) + 0.001 printed with 6 decimals. Returns (newick, structure)
-    where structure = (children, lengths, root_children) over node ids, tips = 0..T-1."""
+    branch lengths Exp(mean brlen) + 0.001 printed with 6 decimals. With probability `ladder` a join
+    takes the newest inner node and a random tip (deep, caterpillar-like trees: most CLV updates are
+    tip-inner). Returns (newick, structure) where structure = (children, lengths, root_children) over
+    node ids, tips = 0..T-1."""
     rng = np.random.default_rng(seed)
     active = list(range(T))
     children = {}
@@ -23,6 +25,10 @@ def random_tree(T: int, seed: int = 1):
     nxt = T
     while len(active) > 3:
         i, j = sorted(rng.choice(len(active), size=2, replace=False))
+        if ladder > 0.0 and active[-1] >= T and rng.random() < ladder:
+            tips = [k for k in range(len(active) - 1) if active[k] < T]
+            if tips:
+                i, j = int(rng.choice(tips)), len(active) - 1
         a, b = active[i], active[j]
         active.pop(j)
         active.pop(i)
@@ -30,7 +36,7 @@ def random_tree(T: int, seed: int = 1):
         active.append(nxt)
         nxt += 1
     for node in range(nxt):
-        length[node] = round(float(rng.exponential(0.05)) + 0.001, 6)
+        length[node] = round(float(rng.exponential(brlen)) + 0.001, 6)
 
     def name(t):
         return "t%04d" % t if T <= 10000 else "t%06d" % t
@@ -153,11 +159,11 @@ def make_queries(msa_states, n_queries, window, alphabet, seed=2, mut=0.05):
 
 
 def dataset(T=1000, n_sites=1000, n_queries=1000, window=200, kind="dna", seed_tree=1, seed_q=2,
-            alpha=None):
+            alpha=None, ladder=0.0, brlen=0.05):
     """Returns dict(newick, names, ref (uint8 ASCII [T][n]), queries (uint8 ASCII [Q][n]), qnames,
     model string). DNA: GTR{1/1/1/1/1/1}+FU{.25/.25/.25/.25}+G4{0.5}; AA: LG+G4{0.8}."""
     from math import isfinite  # noqa: F401
-    newick, st = random_tree(T, seed_tree)
+    newick, st = random_tree(T, seed_tree, ladder, brlen)
     if kind == "dna":
         alphabet, S = DNA, 4
         subst, freqs = np.ones(6), np.full(4, 0.25)

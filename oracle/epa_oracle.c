@@ -316,6 +316,9 @@ static inline double orc_row_dot(const double * row, const double * clv, uint32_
   return acc;
 }
 
+/* test statistic: sites rescaled by the generic tip-inner update under per-rate scalers (see below) */
+unsigned long orc_stat_ti_rescaled = 0;
+
 void orc_update_partial(const orc_model_t * m, int n,
                         double * parent_clv, uint32_t * parent_scaler,
                         const orc_side_t * left, const double * lmat,
@@ -324,6 +327,10 @@ void orc_update_partial(const orc_model_t * m, int n,
   const int S = m->states, R = m->rate_cats, span = S * R;
   const int per_rate = m->per_rate_scalers;
   const int tip_tip = left->tip && right->tip;
+  /* Generic (non-4-state) tip-inner update under per-rate scalers, core_partials.c:461-506: the whole site is
+     tested and rescaled as with per-site scalers, and the count goes to entry [site index] of the
+     [site][rate] array. */
+  const int ti_quirk = per_rate && S != 4 && !tip_tip && (left->tip || right->tip);
   const size_t scaler_size = per_rate ? (size_t) n * R : (size_t) n;
 
   /* core_partials.c:24-46 fill_parent_scaler: parent starts as the sum of the children's */
@@ -337,7 +344,7 @@ void orc_update_partial(const orc_model_t * m, int n,
   for (int s = 0; s < n; ++s)
   {
     double * out = parent_clv + (size_t) s * span;
-    int site_scale = (parent_scaler && !per_rate && !tip_tip) ? 1 : 0;
+    int site_scale = (parent_scaler && (!per_rate || ti_quirk) && !tip_tip) ? 1 : 0;
     for (int r = 0; r < R; ++r)
     {
       const double * lclv = left->clv ? left->clv + (size_t) s * span + r * S : NULL;
@@ -353,7 +360,7 @@ void orc_update_partial(const orc_model_t * m, int n,
         rate_scale &= (out[r * S + i] < ORC_SCALE_THRESHOLD);
       }
       /* tip-tip never rescales (core_partials.c:82-127) */
-      if (parent_scaler && per_rate && !tip_tip)
+      if (parent_scaler && per_rate && !tip_tip && !ti_quirk)
       {
         if (rate_scale)
         {
@@ -368,6 +375,7 @@ void orc_update_partial(const orc_model_t * m, int n,
     {
       for (int i = 0; i < span; ++i) out[i] *= ORC_SCALE_FACTOR;
       parent_scaler[s] += 1;
+      if (ti_quirk) orc_stat_ti_rescaled += 1;
     }
   }
 }

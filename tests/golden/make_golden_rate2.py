@@ -23,9 +23,9 @@ for key, spec, model in (("dna8", DNA8, DNA8_MODEL), ("aa", AA, None)):
     tf, sf, qf = pkg.synth.write_dataset(ds, tmp)
     ref, _ = orc.run_reference(tf, sf, qf, model, os.path.join(tmp, "ref"), threads=4, extra=("--rate-scalers", "on"))
     out[key] = {"dataset": spec, "model": model, "flags": "--rate-scalers on", "placements": ref}
-out["aa"]["note"] = ("recorded for documentation: the reference's generic tip-inner CLV update (libpll core_partials.c:461-506) "
-                     "rescales whole sites and bumps entry [site index] of the [site][rate] counter array under per-rate scalers, "
-                     "so these placements are not what a per-rate computation yields; no test pins them")
+out["aa"]["note"] = ("the reference's generic tip-inner CLV update (libpll core_partials.c:461-506) rescales whole sites and bumps entry "
+                     "[site index] of the [site][rate] counter array under per-rate scalers; the oracle restates that and "
+                     "tests/test_oracle_rate_scalers.py pins it on these placements")
 path = os.path.join(ROOT, "tests", "golden", "rate300", "reference_placements_rate2.json")
 json.dump(out, open(path, "w"), indent=0)
 print("wrote", path, {k: len(v["placements"]) for k, v in out.items()})

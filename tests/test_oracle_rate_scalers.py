@@ -67,3 +67,46 @@ def test_oracle_per_rate_eight_categories_matches_reference(built):
     for name, seq in zip(case.qnames, case.qseqs):
         got = [(p.edge, p.logl, p.lwr, p.distal, p.pendant) for p in case.placer.place(seq)]
         helpers.assert_placements_close(got, g["placements"][name], name, logl_rel=1e-9, len_abs=1e-5)
+
+
+def _ti_rescaled(built):
+    """oracle statistic: sites rescaled by the generic tip-inner update under per-rate scalers"""
+    import ctypes
+    return ctypes.c_ulong.in_dll(helpers.oracle().lib(), "orc_stat_ti_rescaled")
+
+
+@pytest.mark.parametrize("fixture", ["rate2", "ladder"])
+def test_oracle_amino_acids_per_rate_matches_reference(built, fixture):
+    """Amino acids under --rate-scalers on: the reference runs libpll's generic kernels, whose tip-inner CLV update
+    (LP/core_partials.c:461-506) tests and rescales whole sites and counts that in entry [site index] of the
+    [site][rate] array. 'ladder' (tests/golden/make_golden_aa_rate.py) is a caterpillar-like tree on which those
+    rescalings do happen - in the reference CLVs and inside the tiny trees; 'rate2' is a random tree where the
+    difference to a per-rate computation is that tip-inner updates do not rescale single rates."""
+    if fixture == "rate2":
+        g = json.load(open(os.path.join(helpers.GOLDEN, "rate300", "reference_placements_rate2.json")))["aa"]
+    else:
+        g = json.load(open(os.path.join(helpers.GOLDEN, "rate300", "reference_placements_aa_ladder.json")))
+    ds = built.synth.dataset(**g["dataset"])
+    cnt = _ti_rescaled(built)
+    c0 = cnt.value
+    case = helpers.case_from_arrays(ds["newick"], ds["names"], ds["ref"], ds["qnames"], ds["queries"], g["model"],
+                                    per_rate=True, bugcompat=True, column_mask=True)
+    c1 = cnt.value
+    for name, seq in zip(case.qnames, case.qseqs):
+        got = [(p.edge, p.logl, p.lwr, p.distal, p.pendant) for p in case.placer.place(seq)]
+        helpers.assert_placements_close(got, g["placements"][name], name, logl_rel=1e-9, len_abs=1e-5)
+    if fixture == "ladder":
+        assert c1 - c0 > 0, "no whole-site rescaling in the reference tree: the fixture would not pin the counter placement"
+        assert cnt.value - c1 > 0, "no whole-site rescaling inside a tiny tree"
+
+
+def test_oracle_amino_acids_per_rate_all_edges(built):
+    """--no-heur on the ladder data set: every edge goes through the thorough phase (first four queries)."""
+    g = json.load(open(os.path.join(helpers.GOLDEN, "rate300", "reference_placements_aa_ladder.json")))
+    ds = built.synth.dataset(**g["dataset"])
+    case = helpers.case_from_arrays(ds["newick"], ds["names"], ds["ref"], ds["qnames"], ds["queries"], g["model"],
+                                    per_rate=True, bugcompat=True, column_mask=True,
+                                    opts=helpers.oracle().Options(prescoring=False))
+    for name, seq in zip(case.qnames[:4], case.qseqs[:4]):
+        got = [(p.edge, p.logl, p.lwr, p.distal, p.pendant) for p in case.placer.place(seq)]
+        helpers.assert_placements_close(got, g["placements_no_heur"][name], name, logl_rel=1e-9, len_abs=1e-5)
