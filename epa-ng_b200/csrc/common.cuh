@@ -74,7 +74,7 @@ __device__ __forceinline__ double site_loglk(double term, uint32_t sc, double in
 
 struct ClvOpDev {
   uint32_t parent, left, right;
-  uint32_t tip_tip;                               // both children are tips: never rescale
+  uint32_t tip_tip;                               // 1 = both children are tips: never rescale; 2 = exactly one child is a tip
   uint32_t lmat, rmat;                            // indices into the pmatrix array of the launch
 };
 

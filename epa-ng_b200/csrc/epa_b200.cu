@@ -422,9 +422,6 @@ extern "C" int epa_ctx_create(epa_ctx ** out, int device, const epa_model_desc *
   *out = nullptr;
   if (!supported_sr((int) model->states, (int) model->rate_cats))
     return fail(ctx, EPA_ERR_ARG, "unsupported states/rate_cats combination %u/%u", model->states, model->rate_cats);
-  if ((model->flags & EPA_FLAG_RATE_SCALERS) && model->states != 4)
-    return fail(ctx, EPA_ERR_ARG, "per-rate scalers are only supported for DNA (the reference's amino-acid path mixes per-site "
-                                  "and per-rate counts in its tip-inner updates, DESIGN section 4)");
   if (!(model->pinv >= 0.0 && model->pinv < 1.0))        // LP/models.c:510-518
     return fail(ctx, EPA_ERR_ARG, "Invalid proportion of invariant sites (%f)", model->pinv);
   if (model->sites == 0 || n_tips < 3 || n_edges == 0) return fail(ctx, EPA_ERR_ARG, "empty tree or alignment");
@@ -707,7 +704,7 @@ extern "C" int epa_compute_clvs(epa_ctx * ctx, const epa_clv_op * ops, uint32_t 
       const epa_clv_op & o = ops[i];
       ClvOpDev d;
       d.parent = o.parent; d.left = o.left; d.right = o.right;
-      d.tip_tip = (o.left < T && o.right < T) ? 1u : 0u;
+      d.tip_tip = (o.left < T && o.right < T) ? 1u : ((o.left < T || o.right < T) ? 2u : 0u);
       d.lmat = (uint32_t) lengths.size(); lengths.push_back(o.left_length);
       d.rmat = (uint32_t) lengths.size(); lengths.push_back(o.right_length);
       hops.push_back(d);
@@ -726,6 +723,13 @@ extern "C" int epa_compute_clvs(epa_ctx * ctx, const epa_clv_op * ops, uint32_t 
   CU(cudaMemcpyAsync(d_len, lengths.data(), lengths.size() * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
   if (int rc = launch_pmatrices(ctx, d_len, d_pm, (uint32_t) lengths.size())) return rc;
   const size_t smem = 2 * pm * sizeof(double);
+  if (ctx->tree.sr > 1 && ctx->S != 4)
+  {
+    // tip-inner updates of the generic per-rate path add their counts atomically (kernels_clv.cuh)
+    const size_t sn = (size_t) ctx->n * ctx->tree.sr;
+    for (auto & o : hops)
+      if (o.tip_tip == 2) CU(cudaMemsetAsync(ctx->tree.scaler + (size_t) o.parent * sn, 0, sn * sizeof(uint32_t), ctx->stream));
+  }
   for (auto & rg : ranges)
   {
     if (!rg.second) continue;
@@ -884,8 +888,21 @@ extern "C" int epa_build_lookup(epa_ctx * ctx)
   {
     const size_t smem = (pm + coltab) * sizeof(double);
     dim3 grid(B, (n + 127) / 128);
-    EPA_DISPATCH_SR(ctx, (lookup_build_kernel<S_, R_><<<grid, 128, smem, ctx->stream>>>(ctx->d_model, ctx->tree, n, ctx->n_pad, K, ctx->d_edges, d_pm, d_col, ctx->d_lookup)));
+    uint8_t * d_tiflags = nullptr;
+    if (S != 4 && ctx->tree.sr > 1)
+    {
+      // amino acids under per-rate scalers: whole-site rescalings of the tip edges' inner CLVs (kernels_clv.cuh)
+      CU(dev_alloc(&d_tiflags, (size_t) B * n));
+      EPA_DISPATCH_SR(ctx, (lookup_ti_flags_kernel<S_, R_><<<grid, 128, pm * sizeof(double), ctx->stream>>>(ctx->tree, n, ctx->d_edges, d_pm, d_tiflags)));
+      LAUNCHED(ctx);
+    }
+    EPA_DISPATCH_SR(ctx, (lookup_build_kernel<S_, R_><<<grid, 128, smem, ctx->stream>>>(ctx->d_model, ctx->tree, n, ctx->n_pad, K, ctx->d_edges, d_pm, d_col, ctx->d_lookup, d_tiflags)));
     LAUNCHED(ctx);
+    if (d_tiflags)
+    {
+      CU(cudaStreamSynchronize(ctx->stream));
+      dev_free(d_tiflags);
+    }
   }
   CU(cudaEventRecord(ctx->ev[1], ctx->stream));
   if (S == 4)
@@ -1681,13 +1698,16 @@ extern "C" int epa_place_pairs(epa_ctx * ctx, const epa_options * opts)
     }
     else
     {
-      const bool site = !ctx->sw.old_aa;
+      const bool pr = ctx->tree.sr > 1;
+      if (pr && a.raxml)
+        return fail(ctx, EPA_ERR_ARG, "--raxml-blo with per-rate scalers (--rate-scalers on, or auto above 2000 tips) is only supported for DNA: use --rate-scalers off");
+      const bool site = !ctx->sw.old_aa || pr;
       if (site)
         if (int rc2 = ensure_clvT(ctx)) return rc2;
       const size_t aa_stride = (size_t) ((ctx->n + CLVT_BLOCK - 1) / CLVT_BLOCK) * (size_t) (ctx->R * ctx->S) * CLVT_BLOCK;
       // 20 states, windows up to 320 sites, pplacer-style BLO: fp64 tensor-core kernel with the sumtable in tensor memory
       const bool mma = site && ctx->S == 20 && (ctx->R == 4 || ctx->R == 1) && !a.raxml && ctx->max_span <= AA_MAX_WINDOW &&
-                       !ctx->sw.aa_dfma && !ctx->sw.no_tmem;
+                       !ctx->sw.aa_dfma && !ctx->sw.no_tmem && !pr;
       if (getenv("EPA_B200_DEBUG_AA")) fprintf(stderr, "[aa] mma=%d site=%d S=%d R=%d raxml=%d max_span=%d\n", (int) mma, (int) site, ctx->S, ctx->R, a.raxml, ctx->max_span);
       cudaError_t ce;
       if (mma)
@@ -1695,7 +1715,8 @@ extern "C" int epa_place_pairs(epa_ctx * ctx, const epa_options * opts)
                          : launch_blo_aa<1>(ctx->sm_count, a, ctx->stream, ctx->d_clvT, aa_stride);
       else
         ce = launch_blo_generic(ctx->S, ctx->R, ctx->sm_count, ctx->smem_optin, ctx->max_span, ctx->d_model, a, &ctx->scratch.p,
-                                &ctx->scratch.cap, ctx->stream, site ? ctx->d_clvT : nullptr, aa_stride, ctx->sw.no_tmem ? 0 : 1);
+                                &ctx->scratch.cap, ctx->stream, site ? ctx->d_clvT : nullptr, aa_stride, ctx->sw.no_tmem ? 0 : 1,
+                                pr ? 1 : 0, ctx->hm.bugcompat);
       rc = ce == cudaSuccess ? EPA_OK : fail(ctx, EPA_ERR_CUDA, "amino-acid BLO launch failed: %s", cudaGetErrorString(ce));
     }
     if (rc) return rc;

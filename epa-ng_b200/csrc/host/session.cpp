@@ -136,9 +136,7 @@ extern "C" int epa_session_open(epa_session ** out, const char * newick, uint32_
     md.sites = sites;
     md.flags = 0;
     {
-      // auto mode only switches the kernels that have a per-rate path (DNA)
-      const bool can = s->model.states == 4;
-      const bool want = g_rate_scalers == 1 || (g_rate_scalers == 2 && T > 2000 && can);
+      const bool want = g_rate_scalers == 1 || (g_rate_scalers == 2 && T > 2000);
       if (want) md.flags |= EPA_FLAG_RATE_SCALERS | (g_rate_bugcompat ? EPA_FLAG_BUGCOMPAT_FOCUS : 0u);
     }
     md.eigenvals = s->model.eigenvals.data();

@@ -289,12 +289,64 @@ __device__ __forceinline__ size_t clvt_off_c(int abs_site, int C)
 // where a warp straddles two rates), R * w units keep 256 threads busy for any window length. The
 // per-rate contributions to the site likelihood and to the stationary sumtable entry go through
 // two small shared-memory arrays and are added over the rates in a fixed order afterwards.
-template <int S, int R>
+// Per-rate scalers (PR kernels; amino acids run libpll's generic kernels then). A site's rate r weighs
+// 2^(-256 d_r), d_r = its counter minus the site's minimum (LP/core_likelihood.c:474-491, core_derivatives.c:404-423).
+// The counters of the two edge CLVs are read where the reference reads them (rate_weights, kernels_blo_site.cuh).
+// An inner CLV that comes from a tip-inner update (`ti`: the distal pass always, the tip pass on a tip edge) is
+// rescaled as a WHOLE site when all its R*S entries are small, and the reference counts that in entry
+// [site index] of the inner node's [site][rate] array (LP/core_partials.c:461-506): site s, rate r picks up the
+// rescaling of site s*R + r, and a rescaled site keeps its factor 2^256 uncompensated. Inner-inner updates rescale
+// single rates with their own counters, which cancels and is skipped here.
+// fbuf[r][s] = weight of unit (r, s) for the sums of this pass and its Newton sweeps; scaled[s] = site rescaled.
+struct GenPr {
+  const uint32_t * sDn, * sXn;        // [n][R] counters of the distal / proximal node
+  int begin, bugcompat, ti;
+  double * fbuf;
+  uint8_t * scaled;
+};
+
+template <int R>
+__device__ __forceinline__ uint32_t gen_pr_weights(const GenPr & pr, int wpad, int w, int s, double (&F)[R])
+{
+  const size_t base = pr.bugcompat ? (size_t) pr.begin + (size_t) s * R : ((size_t) pr.begin + s) * R;
+  uint32_t kr[R], kmin = 0xffffffffu;
+  #pragma unroll
+  for (int r = 0; r < R; ++r)
+  {
+    kr[r] = __ldg(pr.sDn + base + r) + __ldg(pr.sXn + base + r);
+    if (s * R + r < w) kr[r] += pr.scaled[s * R + r];
+    kmin = min(kmin, kr[r]);
+  }
+  const double whole = pr.scaled[s] ? EPA_SCALE_FACTOR : 1.0;
+  #pragma unroll
+  for (int r = 0; r < R; ++r)
+  {
+    F[r] = rate_scale_factor(min(kr[r] - kmin, EPA_RATE_MAXDIFF)) * whole;
+    pr.fbuf[r * wpad + s] = F[r];
+  }
+  return kmin;
+}
+
+// scaled[s] = every unit of site s flagged small (fbuf holds the flags of the unit loop), only for tip-inner updates
+template <int R>
+__device__ __forceinline__ void gen_pr_sites(const GenPr & pr, int wpad, int w)
+{
+  for (int s = threadIdx.x; s < w; s += GEN_THREADS)
+  {
+    bool all = pr.ti != 0;
+    #pragma unroll
+    for (int r = 0; r < R; ++r) all = all && (pr.fbuf[r * wpad + s] != 0.0);
+    pr.scaled[s] = all ? 1 : 0;
+  }
+  __syncthreads();
+}
+
+template <int S, int R, bool PR = false>
 __device__ __forceinline__ double gen_pass_tip_site(double * sm, double * sum, int wpad, const double * __restrict__ DT,
                                                     const double * __restrict__ XT, const uint32_t * __restrict__ sD,
                                                     const uint32_t * __restrict__ sX, const uint8_t * __restrict__ qc,
                                                     int begin, int w, double * rbuf, const double * __restrict__ inv_w,
-                                                    uint64_t tm)
+                                                    uint64_t tm, const GenPr & pr = GenPr{})
 {
   using L = GenSmem<S, R>;
   double * termbuf = rbuf, * basebuf = rbuf + R * wpad;
@@ -327,6 +379,13 @@ __device__ __forceinline__ double gen_pass_tip_site(double * sm, double * sum, i
       }
       in[i] = ta * tb;
     }
+    if constexpr (PR)
+    {
+      bool small = true;
+      #pragma unroll
+      for (int i = 0; i < S; ++i) small = small && (in[i] < EPA_SCALE_THRESHOLD);
+      if (act) pr.fbuf[r * wpad + s] = small ? 1.0 : 0.0;
+    }
     const double * tvr = sm + L::TV + r * L::TVS + code * S;
     const double * tl = sm + L::TIPLEFT + code * S;
     const double wr = c_model.weights[r];
@@ -353,26 +412,38 @@ __device__ __forceinline__ double gen_pass_tip_site(double * sm, double * sum, i
   }
   if (tm) tc_wait_st();
   __syncthreads();
+  if constexpr (PR) gen_pr_sites<R>(pr, wpad, w);
   double acc = 0.0, unused = 0.0;
   for (int s = threadIdx.x; s < w; s += GEN_THREADS)
   {
     double term = 0.0, base = 0.0;
-    #pragma unroll
-    for (int r = 0; r < R; ++r) { term += termbuf[r * wpad + s]; base += basebuf[r * wpad + s]; }
+    uint32_t scal;
+    if constexpr (PR)
+    {
+      double F[R];
+      scal = gen_pr_weights<R>(pr, wpad, w, s, F);
+      #pragma unroll
+      for (int r = 0; r < R; ++r) { term += termbuf[r * wpad + s] * F[r]; base += basebuf[r * wpad + s] * F[r]; }
+    }
+    else
+    {
+      #pragma unroll
+      for (int r = 0; r < R; ++r) { term += termbuf[r * wpad + s]; base += basebuf[r * wpad + s]; }
+      scal = __ldg(sD + s) + __ldg(sX + s);
+    }
     const double inv = inv_w ? __ldg(inv_w + s) : 0.0;
     sum[s] = base + inv;
-    const uint32_t scal = __ldg(sD + s) + __ldg(sX + s);
     acc += site_loglk(term, scal, inv);
   }
   block_sum2(acc, unused, sm + L::RED);
   return acc;
 }
 
-template <int S, int R>
+template <int S, int R, bool PR = false>
 __device__ __forceinline__ void gen_pass_distal_site(double * sm, double * sum, int wpad, const double * __restrict__ DT,
                                                      const double * __restrict__ XT, const uint8_t * __restrict__ qc,
                                                      int begin, int w, double * rbuf, const double * __restrict__ inv_w,
-                                                     uint64_t tm, int which_x = 1)
+                                                     uint64_t tm, int which_x = 1, const GenPr & pr = GenPr{})
 {
   using L = GenSmem<S, R>;
   double * basebuf = rbuf;
@@ -402,6 +473,13 @@ __device__ __forceinline__ void gen_pass_distal_site(double * sm, double * sum, 
       }
       in[i] = tvr[i] * tb;
     }
+    if constexpr (PR)
+    {
+      bool small = true;
+      #pragma unroll
+      for (int i = 0; i < S; ++i) small = small && (in[i] < EPA_SCALE_THRESHOLD);
+      if (act) pr.fbuf[r * wpad + s] = small ? 1.0 : 0.0;
+    }
     const double wr = c_model.weights[r];
     double st[S];
     #pragma unroll
@@ -422,11 +500,22 @@ __device__ __forceinline__ void gen_pass_distal_site(double * sm, double * sum, 
   }
   if (tm) tc_wait_st();
   __syncthreads();
+  if constexpr (PR) gen_pr_sites<R>(pr, wpad, w);
   for (int s = threadIdx.x; s < w; s += GEN_THREADS)
   {
     double base = 0.0;
-    #pragma unroll
-    for (int r = 0; r < R; ++r) base += basebuf[r * wpad + s];
+    if constexpr (PR)
+    {
+      double F[R];
+      (void) gen_pr_weights<R>(pr, wpad, w, s, F);
+      #pragma unroll
+      for (int r = 0; r < R; ++r) base += basebuf[r * wpad + s] * F[r];
+    }
+    else
+    {
+      #pragma unroll
+      for (int r = 0; r < R; ++r) base += basebuf[r * wpad + s];
+    }
     sum[s] = base + (inv_w ? __ldg(inv_w + s) : 0.0);
   }
   __syncthreads();
@@ -436,9 +525,10 @@ __device__ __forceinline__ void gen_pass_distal_site(double * sm, double * sum, 
 // components of one rate of one site - all 256 threads stay busy for any window, the loads of a
 // unit are independent, the decay tables of the rate are warp-uniform shared-memory broadcasts -
 // and the per-rate partial sums are combined per site in a fixed order.
-template <int S, int R>
+template <int S, int R, bool PR = false>
 __device__ __forceinline__ void gen_derivatives_units(double * sm, const double * sum, int wpad, int w, double t,
-                                                      double & f, double & df, double * rbuf, uint64_t tm)
+                                                      double & f, double & df, double * rbuf, uint64_t tm,
+                                                      const double * fbuf = nullptr)
 {
   using L = GenSmem<S, R>;
   constexpr int NK = L::NK;
@@ -470,6 +560,11 @@ __device__ __forceinline__ void gen_derivatives_units(double * sm, const double 
     double c0 = 0.0, c1 = 0.0, c2 = 0.0;
     #pragma unroll
     for (int j = 0; j < S - 1; ++j) { c0 += x[j] * dg[j]; c1 += x[j] * dg[NK + j]; c2 += x[j] * dg[2 * NK + j]; }
+    if constexpr (PR)
+    {
+      const double F = fbuf[r * wpad + s];
+      c0 *= F; c1 *= F; c2 *= F;
+    }
     if (act) { b0[r * wpad + s] = c0; b1[r * wpad + s] = c1; b2[r * wpad + s] = c2; }
   }
   __syncthreads();
@@ -520,9 +615,9 @@ __device__ __forceinline__ void gen_derivatives(double * sm, const double * sum,
   f = a1; df = a2;
 }
 
-template <int S, int R>
+template <int S, int R, bool PR = false>
 __device__ __forceinline__ double gen_newton(double * sm, const double * sum, int wpad, int w, double xmin, double xguess,
-                                             double xmax, double tol, double * rbuf, uint64_t tm)
+                                             double xmax, double tol, double * rbuf, uint64_t tm, const double * fbuf = nullptr)
 {
   double x = fmax(fmin(xguess, xmax), xmin);
   double xl = xmin, xh = xmax;
@@ -532,7 +627,7 @@ __device__ __forceinline__ double gen_newton(double * sm, const double * sum, in
   {
     if (iter++ > EPA_NR_MAX_ITERS) return 0.0;
     double f, df;
-    if (rbuf) gen_derivatives_units<S, R>(sm, sum, wpad, w, x, f, df, rbuf, tm);
+    if (rbuf) gen_derivatives_units<S, R, PR>(sm, sum, wpad, w, x, f, df, rbuf, tm, fbuf);
     else gen_derivatives<S, R>(sm, sum, wpad, w, x, f, df);
     if (!isfinite(f) || !isfinite(df)) return 0.0;
     double dx;
@@ -554,9 +649,10 @@ __device__ __forceinline__ double gen_newton(double * sm, const double * sum, in
 }
 
 // RAXML = --raxml-blo (pllmod_opt_optimize_branch_lengths_local with radius 1, PM/optimize/pll_optimize.c:778-1097)
-template <int S, int R, bool RAXML = false>
+// PR = per-rate scalers (needs the site-blocked CLV copy; not combined with RAXML)
+template <int S, int R, bool RAXML = false, bool PR = false>
 __global__ void __launch_bounds__(GEN_THREADS, 1)
-blo_generic_kernel(BloArgs a, int wpad, const double * __restrict__ clvT, size_t t_stride, int use_tmem)
+blo_generic_kernel(BloArgs a, int wpad, const double * __restrict__ clvT, size_t t_stride, int use_tmem, int bugcompat = 0)
 {
   using L = GenSmem<S, R>;
   extern __shared__ __align__(16) double sm[];
@@ -632,6 +728,15 @@ blo_generic_kernel(BloArgs a, int wpad, const double * __restrict__ clvT, size_t
     const double * inv_w = a.tree.inv ? a.tree.inv + begin : nullptr;      // +I: pll_util.cpp:413-414
     // bit 32 = rows in tensor memory, low word = this thread's slot 0
     const uint64_t tm = (have_tm && R * w <= GEN_THREADS * GEN_TM_UNITS) ? ((1ull << 32) | tm_base) : 0ull;
+    GenPr pr{};
+    if constexpr (PR)
+    {
+      pr.sDn = a.tree.scaler + (size_t) ed.distal * n * R;
+      pr.sXn = a.tree.scaler + (size_t) ed.proximal * n * R;
+      pr.begin = begin; pr.bugcompat = bugcompat;
+      pr.fbuf = sm + L::TOTAL + 3 * R * wpad;
+      pr.scaled = reinterpret_cast<uint8_t *>(sm + L::TOTAL + 4 * R * wpad);
+    }
 
     const double orig = ed.length;
     double len[3] = {orig / 2.0, orig / 2.0, EPA_DEFAULT_PENDANT};
@@ -735,8 +840,9 @@ blo_generic_kernel(BloArgs a, int wpad, const double * __restrict__ clvT, size_t
       double xmin, xmax, xguess;
       if (!distal_phase)
       {
+        if constexpr (PR) pr.ti = ed.distal < a.tree.n_tips;
         const double new_logl = clvT
-            ? -gen_pass_tip_site<S, R>(sm, sum, wpad, clvT + (size_t) ed.distal * t_stride, clvT + (size_t) ed.proximal * t_stride, sD, sX, qc, begin, w, sm + L::TOTAL, inv_w, tm)
+            ? -gen_pass_tip_site<S, R, PR>(sm, sum, wpad, clvT + (size_t) ed.distal * t_stride, clvT + (size_t) ed.proximal * t_stride, sD, sX, qc, begin, w, sm + L::TOTAL, inv_w, tm, pr)
             : -gen_pass_tip<S, R>(sm, sum, wpad, D, X, sD, sX, qc, w, inv_w);
         if (first) { loglikelihood = new_logl; first = false; }
         else
@@ -757,8 +863,9 @@ blo_generic_kernel(BloArgs a, int wpad, const double * __restrict__ clvT, size_t
       }
       else
       {
+        if constexpr (PR) pr.ti = 1;
         if (clvT)
-          gen_pass_distal_site<S, R>(sm, sum, wpad, clvT + (size_t) ed.distal * t_stride, clvT + (size_t) ed.proximal * t_stride, qc, begin, w, sm + L::TOTAL, inv_w, tm);
+          gen_pass_distal_site<S, R, PR>(sm, sum, wpad, clvT + (size_t) ed.distal * t_stride, clvT + (size_t) ed.proximal * t_stride, qc, begin, w, sm + L::TOTAL, inv_w, tm, 1, pr);
         else
           gen_pass_distal<S, R>(sm, sum, wpad, D, X, qc, w, inv_w);
         xmin = fmin(EPA_MIN_BRLEN / 2.0, original_length / 2.0);
@@ -766,7 +873,7 @@ blo_generic_kernel(BloArgs a, int wpad, const double * __restrict__ clvT, size_t
         xguess = len[0];
         if (xguess < xmin || xguess > xmax) xguess = original_length / 2.0;
       }
-      const double xres = gen_newton<S, R>(sm, sum, wpad, w, xmin, xguess, xmax, xmin / 10.0, clvT ? sm + L::TOTAL : nullptr, tm);
+      const double xres = gen_newton<S, R, PR>(sm, sum, wpad, w, xmin, xguess, xmax, xmin / 10.0, clvT ? sm + L::TOTAL : nullptr, tm, pr.fbuf);
       if (xres > 0.0)
       {
         if (!distal_phase) { len[2] = xres; rebuild = 4u; }
@@ -795,12 +902,14 @@ blo_generic_kernel(BloArgs a, int wpad, const double * __restrict__ clvT, size_t
 // host-side launcher; scratch is (re)allocated by the caller-owned buffer
 template <int S, int R>
 inline cudaError_t launch_blo_generic_sr(int sm_count, size_t smem_optin, int max_span, BloArgs & a, void ** scratch,
-                                         size_t * scratch_cap, cudaStream_t stream, const double * clvT, size_t t_stride, int use_tmem)
+                                         size_t * scratch_cap, cudaStream_t stream, const double * clvT, size_t t_stride, int use_tmem,
+                                         int per_rate = 0, int bugcompat = 0)
 {
   using L = GenSmem<S, R>;
   const int wpad = (std::max(1, max_span) + 31) & ~31;
-  // fixed tables + (unit-mapped phases) per-rate partial sums [3][R][wpad]
-  const size_t smem = ((size_t) L::TOTAL + (clvT ? (size_t) 3 * R * wpad : 0)) * sizeof(double);
+  if (per_rate && (!clvT || a.raxml || R == 1)) return cudaErrorNotSupported;
+  // fixed tables + (unit-mapped phases) per-rate partial sums [3][R][wpad] (+ per-rate scalers: weights [R][wpad], flags [wpad])
+  const size_t smem = ((size_t) L::TOTAL + (clvT ? (size_t) 3 * R * wpad : 0) + (per_rate ? (size_t) R * wpad + wpad / 8 : 0)) * sizeof(double);
   if (smem > smem_optin) return cudaErrorInvalidConfiguration;
   const int ctas_per_sm = (int) std::max<size_t>(1, std::min<size_t>(3, smem_optin / (smem + 1024)));
   const unsigned grid = (unsigned) std::min<uint64_t>((uint64_t) sm_count * ctas_per_sm, a.n_pairs);
@@ -821,6 +930,16 @@ inline cudaError_t launch_blo_generic_sr(int sm_count, size_t smem_optin, int ma
     blo_generic_kernel<S, R, true><<<grid, GEN_THREADS, smem, stream>>>(a, wpad, clvT, t_stride, use_tmem);
     return cudaGetLastError();
   }
+  if constexpr (R > 1)
+  {
+    if (per_rate)
+    {
+      cudaError_t e = cudaFuncSetAttribute(blo_generic_kernel<S, R, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+      if (e != cudaSuccess) return e;
+      blo_generic_kernel<S, R, false, true><<<grid, GEN_THREADS, smem, stream>>>(a, wpad, clvT, t_stride, use_tmem, bugcompat);
+      return cudaGetLastError();
+    }
+  }
   cudaError_t e = cudaFuncSetAttribute(blo_generic_kernel<S, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
   if (e != cudaSuccess) return e;
   blo_generic_kernel<S, R><<<grid, GEN_THREADS, smem, stream>>>(a, wpad, clvT, t_stride, use_tmem);
@@ -829,10 +948,11 @@ inline cudaError_t launch_blo_generic_sr(int sm_count, size_t smem_optin, int ma
 
 inline cudaError_t launch_blo_generic(int S, int R, int sm_count, size_t smem_optin, int max_span, const DevModel *,
                                       BloArgs & a, void ** scratch, size_t * scratch_cap, cudaStream_t stream,
-                                      const double * clvT = nullptr, size_t t_stride = 0, int use_tmem = 1)
+                                      const double * clvT = nullptr, size_t t_stride = 0, int use_tmem = 1,
+                                      int per_rate = 0, int bugcompat = 0)
 {
-  if (S == 20 && R == 4) return launch_blo_generic_sr<20, 4>(sm_count, smem_optin, max_span, a, scratch, scratch_cap, stream, clvT, t_stride, use_tmem);
-  if (S == 20 && R == 1) return launch_blo_generic_sr<20, 1>(sm_count, smem_optin, max_span, a, scratch, scratch_cap, stream, clvT, t_stride, use_tmem);
+  if (S == 20 && R == 4) return launch_blo_generic_sr<20, 4>(sm_count, smem_optin, max_span, a, scratch, scratch_cap, stream, clvT, t_stride, use_tmem, per_rate, bugcompat);
+  if (S == 20 && R == 1) return launch_blo_generic_sr<20, 1>(sm_count, smem_optin, max_span, a, scratch, scratch_cap, stream, clvT, t_stride, use_tmem, 0, 0);
   return cudaErrorNotSupported;
 }
 

@@ -113,6 +113,27 @@ clv_update_kernel(DevTree tree, int n, const ClvOpDev * __restrict__ ops, const 
     const uint32_t * sl = tree.scaler + ((size_t) op.left * n + site) * R;
     const uint32_t * sr = tree.scaler + ((size_t) op.right * n + site) * R;
     uint32_t * sp = tree.scaler + ((size_t) op.parent * n + site) * R;
+    if (S != 4 && op.tip_tip == 2)
+    {
+      // The reference runs libpll's generic kernels under per-rate scalers, and the generic tip-inner update
+      // (LP/core_partials.c:461-506) tests and rescales the WHOLE site and counts it in entry [site index] of the
+      // parent's [site][rate] array. That entry belongs to another thread's site: the parent's counters are zeroed
+      // before the launch and every contribution is an integer atomic add (order independent).
+      #pragma unroll
+      for (int r = 0; r < R; ++r)
+      {
+        if (all_small)
+        {
+          #pragma unroll
+          for (int i = 0; i < S; ++i) res[r][i] *= EPA_SCALE_FACTOR;
+        }
+        store_vec<S>(out + r * S, res[r]);
+        const uint32_t sc = sl[r] + sr[r];
+        if (sc) atomicAdd(sp + r, sc);
+      }
+      if (all_small) atomicAdd(tree.scaler + (size_t) op.parent * n * R + site, 1u);
+      return;
+    }
     #pragma unroll
     for (int r = 0; r < R; ++r)
     {
@@ -120,7 +141,7 @@ clv_update_kernel(DevTree tree, int n, const ClvOpDev * __restrict__ ops, const 
       #pragma unroll
       for (int i = 0; i < S; ++i) small = small && (res[r][i] < EPA_SCALE_THRESHOLD);
       uint32_t sc = sl[r] + sr[r];
-      if (small && !op.tip_tip)
+      if (small && op.tip_tip != 1)
       {
         sc += 1;
         #pragma unroll
@@ -132,7 +153,7 @@ clv_update_kernel(DevTree tree, int n, const ClvOpDev * __restrict__ ops, const 
     return;
   }
   uint32_t sc = tree.scaler[(size_t) op.left * n + site] + tree.scaler[(size_t) op.right * n + site];
-  const bool scale = all_small && !op.tip_tip;
+  const bool scale = all_small && op.tip_tip != 1;
   if (scale) sc += 1;
   #pragma unroll
   for (int r = 0; r < R; ++r)
@@ -175,11 +196,55 @@ __global__ void lookup_coltable_kernel(const DevModel * __restrict__ m, const do
 // Column c with colmask 0 is the zero column (preplacement reads it for out-of-range sites).
 // grid = (n_edges, ceil(n/blockDim)); dynamic smem = (R*S*S + R*K*S) doubles.
 // ---------------------------------------------------------------------------------------------
+// Generic kernels under per-rate scalers (amino acids): the inner CLV of a tiny tree whose distal node is a tip
+// comes from libpll's generic tip-inner update, which rescales a WHOLE site when all its entries are small and
+// counts that in entry [site index] of the inner node's [site][rate] array (LP/core_partials.c:461-506, see
+// clv_update_kernel). flags[e][s] = 1 where site s of tip edge e is rescaled that way; other edges are skipped.
+// grid = (n_edges, ceil(n/blockDim)); dynamic smem = R*S*S doubles.
+template <int S, int R>
+__global__ void __launch_bounds__(128)
+lookup_ti_flags_kernel(DevTree tree, int n, const EdgeDev * __restrict__ edges, const double * __restrict__ pmats_half,
+                       uint8_t * __restrict__ flags)
+{
+  extern __shared__ double smem[];
+  double * P = smem;
+  const EdgeDev e = edges[blockIdx.x];
+  if (e.distal >= tree.n_tips) return;
+  stage_doubles(P, pmats_half + (size_t) blockIdx.x * R * S * S, R * S * S);
+  __syncthreads();
+  const int site = blockIdx.y * blockDim.x + threadIdx.x;
+  if (site >= n) return;
+  const double * D = tree.clv + e.distal * tree.clv_stride + (size_t) site * (R * S);
+  const double * X = tree.clv + e.proximal * tree.clv_stride + (size_t) site * (R * S);
+  bool all_small = true;
+  #pragma unroll 1
+  for (int r = 0; r < R; ++r)
+  {
+    double dv[S], xv[S];
+    load_vec<S>(D + r * S, dv);
+    load_vec<S>(X + r * S, xv);
+    #pragma unroll 4
+    for (int i = 0; i < S; ++i)
+    {
+      double ta = 0.0, tb = 0.0;
+      #pragma unroll
+      for (int j = 0; j < S; ++j)
+      {
+        ta += P[(r * S + i) * S + j] * dv[j];
+        tb += P[(r * S + i) * S + j] * xv[j];
+      }
+      all_small = all_small && (ta * tb < EPA_SCALE_THRESHOLD);
+    }
+  }
+  flags[(size_t) blockIdx.x * n + site] = all_small ? 1 : 0;
+}
+
 template <int S, int R>
 __global__ void __launch_bounds__(128)
 lookup_build_kernel(const DevModel * __restrict__ m, DevTree tree, int n, int n_pad, int K,
                     const EdgeDev * __restrict__ edges, const double * __restrict__ pmats_half,
-                    const double * __restrict__ coltab, double * __restrict__ lookup)
+                    const double * __restrict__ coltab, double * __restrict__ lookup,
+                    const uint8_t * __restrict__ ti_flags = nullptr)
 {
   extern __shared__ double smem[];
   double * P = smem;                    // [R][S][S]
@@ -219,17 +284,21 @@ lookup_build_kernel(const DevModel * __restrict__ m, DevTree tree, int n, int n_
   if (tree.sr > 1)
   {
     // per-rate scalers (as in lookup_build_site_kernel): rate weights 2^(-256 d) relative to the site's minimum count
+    // (ti_flags: the whole-site rescalings of a tip edge's inner CLV and where the reference counts them)
+    const uint8_t * tf = (ti_flags && e.distal < tree.n_tips) ? ti_flags + (size_t) blockIdx.x * n : nullptr;
     uint32_t kr[R], kmin = 0xffffffffu;
     #pragma unroll
     for (int r = 0; r < R; ++r)
     {
       kr[r] = tree.scaler[((size_t) e.distal * n + site) * R + r] + tree.scaler[((size_t) e.proximal * n + site) * R + r];
+      if (tf && site * R + r < n) kr[r] += tf[site * R + r];
       kmin = min(kmin, kr[r]);
     }
+    const double whole = (tf && tf[site]) ? EPA_SCALE_FACTOR : 1.0;
     #pragma unroll
     for (int r = 0; r < R; ++r)
     {
-      const double f = rate_scale_factor(min(kr[r] - kmin, EPA_RATE_MAXDIFF));
+      const double f = rate_scale_factor(min(kr[r] - kmin, EPA_RATE_MAXDIFF)) * whole;
       #pragma unroll
       for (int i = 0; i < S; ++i) inner[r][i] *= f;
     }

@@ -643,8 +643,71 @@ def test_per_rate_eight_categories(built, bugcompat):
     ctx.close()
 
 
-def test_per_rate_scalers_refused_for_amino_acids(built):
-    case = helpers.synthaa_case()
-    case.model.per_rate_scalers = True
-    with pytest.raises(built.capi.EpaError, match="per-rate scalers"):
-        helpers.make_context(case, compute=False)
+@pytest.mark.parametrize("fixture,bugcompat", [("ladder", True), ("ladder", False), ("rate2", True)],
+                         ids=["ladder-bugcompat", "ladder-corrected", "random-bugcompat"])
+def test_per_rate_amino_acids(built, fixture, bugcompat):
+    """Amino acids with per-rate scalers (--rate-scalers on, auto above 2000 tips): the reference runs libpll's
+    generic kernels, whose tip-inner update rescales whole sites and counts them in entry [site index] of the
+    [site][rate] array (oracle pinned in tests/test_oracle_rate_scalers.py). On the ladder tree those rescalings
+    happen in the reference CLVs, the lookup tables and the tiny trees. Every stage against the oracle, the end
+    result (bug-compatible scaler window) against the reference's recorded placements, incl. --no-heur."""
+    import json
+    import os
+    if fixture == "ladder":
+        g = json.load(open(os.path.join(helpers.GOLDEN, "rate300", "reference_placements_aa_ladder.json")))
+    else:
+        g = json.load(open(os.path.join(helpers.GOLDEN, "rate300", "reference_placements_rate2.json")))["aa"]
+    ds = built.synth.dataset(**g["dataset"])
+    case = helpers.case_from_arrays(ds["newick"], ds["names"], ds["ref"], ds["qnames"], ds["queries"], g["model"],
+                                    per_rate=True, bugcompat=bugcompat, column_mask=True)
+    ctx = helpers.make_context(case)
+    ctx.build_lookup()
+    _check_clvs(case, ctx)
+    # (with misplaced counters the tree log-likelihood is not the same on every edge: edge by edge against the oracle)
+    for e in range(0, case.tree.num_branches, 37):
+        assert np.isclose(ctx.edge_loglikelihood(e), case.ref.tree_logl(e), rtol=1e-11, atol=0), f"tree logl at edge {e}"
+    lk = case.placer.build_lookup()
+    for e in range(0, case.tree.num_branches, 7):
+        assert np.allclose(ctx.get_lookup(e), lk[e], rtol=1e-11, atol=1e-11), f"lookup of edge {e}"
+    opts = built.capi.default_options()
+    ctx.upload_queries(case.query_rows)
+    ctx.preplace()
+    ctx.select(opts)
+    ctx.place_pairs(opts)
+    q, e, raw = ctx.get_pairs()
+    for qi, ei, r in zip(q, e, raw):
+        p = case.placer.thorough(case.qseqs[qi], int(ei))
+        assert abs(r["likelihood"] - p.logl) <= 1e-8 * abs(p.logl), (qi, ei, r, p)
+        assert abs(r["pendant_length"] - p.pendant) <= 1e-5 and abs(r["distal_length"] - p.distal) <= 1e-5, (qi, ei, r, p)
+    if bugcompat:
+        out, counts = ctx.place_chunk(case.query_rows, opts)
+        got = dict(zip(case.qnames, helpers.records_to_lists(out, counts)))
+        for name, w in g["placements"].items():
+            helpers.assert_placements_close(got[name], w, name)
+        if "placements_no_heur" in g:
+            out, counts = ctx.place_chunk(case.query_rows, built.capi.default_options(prescoring=0))
+            got = dict(zip(case.qnames, helpers.records_to_lists(out, counts)))
+            for name, w in g["placements_no_heur"].items():
+                helpers.assert_placements_close(got[name], w, name)
+    with pytest.raises(built.capi.EpaError, match="raxml-blo"):
+        ctx.place_chunk(case.query_rows, built.capi.default_options(sliding_blo=0))
+    ctx.close()
+
+
+def test_per_rate_amino_acids_files_to_jplace(built, tmp_path):
+    """The command-line program with --rate-scalers on on the amino-acid ladder data set: files -> jplace against
+    the placements the reference wrote for the same files and flags."""
+    import json
+    import os
+    import subprocess
+    g = json.load(open(os.path.join(helpers.GOLDEN, "rate300", "reference_placements_aa_ladder.json")))
+    ds = built.synth.dataset(**g["dataset"])
+    tf, sf, qf = built.synth.write_dataset(ds, str(tmp_path / "in"))
+    exe = os.path.join(helpers.ROOT, "epa-ng_b200", "epa-ng-b200")
+    out = str(tmp_path / "out")
+    subprocess.run([exe, "-t", tf, "-s", sf, "-q", qf, "-m", g["model"], "-w", out, "--redo", "--rate-scalers", "on"],
+                   check=True, stdout=subprocess.DEVNULL)
+    doc = json.load(open(os.path.join(out, "epa_result.jplace")))
+    got = {n: pq["p"] for pq in doc["placements"] for n in pq["n"]}
+    for name, want in g["placements"].items():
+        helpers.assert_placements_close(got[name], want, name)
