@@ -50,7 +50,10 @@ typedef enum {
 } epa_status;
 
 enum {
-  EPA_FLAG_RATE_SCALERS = 1u << 0,     /* PLL_ATTRIB_RATE_SCALERS (src/io/file_io.cpp:211-214) */
+  EPA_FLAG_RATE_SCALERS = 1u << 0,     /* PLL_ATTRIB_RATE_SCALERS (src/io/file_io.cpp:211-214). With 20 states the counters
+                                          are placed as libpll's generic tip-inner update places them
+                                          (LP/core_partials.c:461-506: whole-site rescaling, entry [site index]);
+                                          uploaded CLVs are expected to carry the reference's own counters */
   EPA_FLAG_BUGCOMPAT_FOCUS = 1u << 1,  /* reproduce shift_partition_focus' per-rate scaler offset
                                           (src/core/pll/pll_util.cpp:405-408) */
 };
