@@ -1699,8 +1699,6 @@ extern "C" int epa_place_pairs(epa_ctx * ctx, const epa_options * opts)
     else
     {
       const bool pr = ctx->tree.sr > 1;
-      if (pr && a.raxml)
-        return fail(ctx, EPA_ERR_ARG, "--raxml-blo with per-rate scalers (--rate-scalers on, or auto above 2000 tips) is only supported for DNA: use --rate-scalers off");
       const bool site = !ctx->sw.old_aa || pr;
       if (site)
         if (int rc2 = ensure_clvT(ctx)) return rc2;

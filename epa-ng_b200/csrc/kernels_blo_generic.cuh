@@ -649,7 +649,7 @@ __device__ __forceinline__ double gen_newton(double * sm, const double * sum, in
 }
 
 // RAXML = --raxml-blo (pllmod_opt_optimize_branch_lengths_local with radius 1, PM/optimize/pll_optimize.c:778-1097)
-// PR = per-rate scalers (needs the site-blocked CLV copy; not combined with RAXML)
+// PR = per-rate scalers (needs the site-blocked CLV copy)
 template <int S, int R, bool RAXML = false, bool PR = false>
 __global__ void __launch_bounds__(GEN_THREADS, 1)
 blo_generic_kernel(BloArgs a, int wpad, const double * __restrict__ clvT, size_t t_stride, int use_tmem, int bugcompat = 0)
@@ -764,9 +764,12 @@ blo_generic_kernel(BloArgs a, int wpad, const double * __restrict__ clvT, size_t
         if (step == 0 || step == 3)
         {
           if (step == 3 || need_tip)
+          {
+            if constexpr (PR) pr.ti = ed.distal < a.tree.n_tips;
             logl_now = clvT
-                ? gen_pass_tip_site<S, R>(sm, sum, wpad, clvT + (size_t) ed.distal * t_stride, clvT + (size_t) ed.proximal * t_stride, sD, sX, qc, begin, w, sm + L::TOTAL, inv_w, tm)
+                ? gen_pass_tip_site<S, R, PR>(sm, sum, wpad, clvT + (size_t) ed.distal * t_stride, clvT + (size_t) ed.proximal * t_stride, sD, sX, qc, begin, w, sm + L::TOTAL, inv_w, tm, pr)
                 : gen_pass_tip<S, R>(sm, sum, wpad, D, X, sD, sX, qc, w, inv_w);
+          }
           if (step == 0)
           {
             if (first) { loglikelihood = logl_now; first = false; }
@@ -788,9 +791,11 @@ blo_generic_kernel(BloArgs a, int wpad, const double * __restrict__ clvT, size_t
         else
         {
           const bool prox = step == 2;          // proximal edge: the distal pass with the two nodes swapped
+          // (proximal step on a tip edge: the inner CLV comes from a tip-tip update, which never rescales)
+          if constexpr (PR) pr.ti = !(prox && ed.distal < a.tree.n_tips);
           if (clvT)
-            gen_pass_distal_site<S, R>(sm, sum, wpad, clvT + (size_t) (prox ? ed.proximal : ed.distal) * t_stride,
-                                       clvT + (size_t) (prox ? ed.distal : ed.proximal) * t_stride, qc, begin, w, sm + L::TOTAL, inv_w, tm, prox ? 0 : 1);
+            gen_pass_distal_site<S, R, PR>(sm, sum, wpad, clvT + (size_t) (prox ? ed.proximal : ed.distal) * t_stride,
+                                           clvT + (size_t) (prox ? ed.distal : ed.proximal) * t_stride, qc, begin, w, sm + L::TOTAL, inv_w, tm, prox ? 0 : 1, pr);
           else
             gen_pass_distal<S, R>(sm, sum, wpad, prox ? X : D, prox ? D : X, qc, w, inv_w, prox ? 0 : 1);
           target = prox ? 1 : 0;
@@ -801,7 +806,7 @@ blo_generic_kernel(BloArgs a, int wpad, const double * __restrict__ clvT, size_t
         double * rbuf = clvT ? sm + L::TOTAL : nullptr;
         const double xres = newton_old([&](double x, double & f, double & df)
                                        {
-                                         if (rbuf) gen_derivatives_units<S, R>(sm, sum, wpad, w, x, f, df, rbuf, tm);
+                                         if (rbuf) gen_derivatives_units<S, R, PR>(sm, sum, wpad, w, x, f, df, rbuf, tm, pr.fbuf);
                                          else gen_derivatives<S, R>(sm, sum, wpad, w, x, f, df);
                                        }, EPA_MIN_BRLEN, xguess, EPA_MAX_BRLEN, EPA_MIN_BRLEN / 10.0, failed);
         if (failed) { ok = false; break; }
@@ -907,7 +912,7 @@ inline cudaError_t launch_blo_generic_sr(int sm_count, size_t smem_optin, int ma
 {
   using L = GenSmem<S, R>;
   const int wpad = (std::max(1, max_span) + 31) & ~31;
-  if (per_rate && (!clvT || a.raxml || R == 1)) return cudaErrorNotSupported;
+  if (per_rate && (!clvT || R == 1)) return cudaErrorNotSupported;
   // fixed tables + (unit-mapped phases) per-rate partial sums [3][R][wpad] (+ per-rate scalers: weights [R][wpad], flags [wpad])
   const size_t smem = ((size_t) L::TOTAL + (clvT ? (size_t) 3 * R * wpad : 0) + (per_rate ? (size_t) R * wpad + wpad / 8 : 0)) * sizeof(double);
   if (smem > smem_optin) return cudaErrorInvalidConfiguration;
@@ -923,6 +928,16 @@ inline cudaError_t launch_blo_generic_sr(int sm_count, size_t smem_optin, int ma
     *scratch_cap = need;
   }
   a.scratch = static_cast<double *>(*scratch);
+  if constexpr (R > 1)
+  {
+    if (a.raxml && per_rate)
+    {
+      cudaError_t e = cudaFuncSetAttribute(blo_generic_kernel<S, R, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+      if (e != cudaSuccess) return e;
+      blo_generic_kernel<S, R, true, true><<<grid, GEN_THREADS, smem, stream>>>(a, wpad, clvT, t_stride, use_tmem, bugcompat);
+      return cudaGetLastError();
+    }
+  }
   if (a.raxml)
   {
     cudaError_t e = cudaFuncSetAttribute(blo_generic_kernel<S, R, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);

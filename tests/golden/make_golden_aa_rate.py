@@ -24,6 +24,8 @@ out = {"dataset": SPEC, "model": ds["model"], "flags": "--rate-scalers on"}
 out["placements"], _ = orc.run_reference(tf, sf, qf, ds["model"], os.path.join(tmp, "ref"), threads=4, extra=("--rate-scalers", "on"))
 out["placements_no_heur"], _ = orc.run_reference(tf, sf, qf, ds["model"], os.path.join(tmp, "ref2"), threads=4,
                                                  extra=("--rate-scalers", "on", "--no-heur"))
+out["placements_raxml_blo"], _ = orc.run_reference(tf, sf, qf, ds["model"], os.path.join(tmp, "ref3"), threads=4,
+                                                   extra=("--rate-scalers", "on", "--raxml-blo"))
 path = os.path.join(ROOT, "tests", "golden", "rate300", "reference_placements_aa_ladder.json")
 json.dump(out, open(path, "w"), indent=0)
 print("wrote", path, len(out["placements"]), len(out["placements_no_heur"]))

@@ -689,8 +689,25 @@ def test_per_rate_amino_acids(built, fixture, bugcompat):
             got = dict(zip(case.qnames, helpers.records_to_lists(out, counts)))
             for name, w in g["placements_no_heur"].items():
                 helpers.assert_placements_close(got[name], w, name)
-    with pytest.raises(built.capi.EpaError, match="raxml-blo"):
-        ctx.place_chunk(case.query_rows, built.capi.default_options(sliding_blo=0))
+    # --raxml-blo: every pair against the oracle, placements against the reference's
+    o = helpers.oracle()
+    case.placer = o.Placer(case.ref, o.Options(sliding_blo=False))
+    case.placer.lookup = lk
+    opts = built.capi.default_options(sliding_blo=0)
+    ctx.upload_queries(case.query_rows)
+    ctx.preplace()
+    ctx.select(opts)
+    ctx.place_pairs(opts)
+    q, e, raw = ctx.get_pairs()
+    for qi, ei, r in zip(q, e, raw):
+        p = case.placer.thorough(case.qseqs[qi], int(ei))
+        assert abs(r["likelihood"] - p.logl) <= 1e-8 * abs(p.logl), ("raxml", qi, ei, r, p)
+        assert abs(r["pendant_length"] - p.pendant) <= 1e-5 and abs(r["distal_length"] - p.distal) <= 1e-5, ("raxml", qi, ei, r, p)
+    if bugcompat and "placements_raxml_blo" in g:
+        out, counts = ctx.place_chunk(case.query_rows, opts)
+        got = dict(zip(case.qnames, helpers.records_to_lists(out, counts)))
+        for name, w in g["placements_raxml_blo"].items():
+            helpers.assert_placements_close(got[name], w, name)
     ctx.close()
 
 

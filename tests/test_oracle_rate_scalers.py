@@ -110,3 +110,15 @@ def test_oracle_amino_acids_per_rate_all_edges(built):
     for name, seq in zip(case.qnames[:4], case.qseqs[:4]):
         got = [(p.edge, p.logl, p.lwr, p.distal, p.pendant) for p in case.placer.place(seq)]
         helpers.assert_placements_close(got, g["placements_no_heur"][name], name, logl_rel=1e-9, len_abs=1e-5)
+
+
+def test_oracle_amino_acids_per_rate_raxml_blo(built):
+    """--raxml-blo on the ladder data set (proximal step on a tip edge = tip-tip update, never rescaled)"""
+    g = json.load(open(os.path.join(helpers.GOLDEN, "rate300", "reference_placements_aa_ladder.json")))
+    ds = built.synth.dataset(**g["dataset"])
+    case = helpers.case_from_arrays(ds["newick"], ds["names"], ds["ref"], ds["qnames"], ds["queries"], g["model"],
+                                    per_rate=True, bugcompat=True, column_mask=True,
+                                    opts=helpers.oracle().Options(sliding_blo=False))
+    for name, seq in zip(case.qnames, case.qseqs):
+        got = [(p.edge, p.logl, p.lwr, p.distal, p.pendant) for p in case.placer.place(seq)]
+        helpers.assert_placements_close(got, g["placements_raxml_blo"][name], name, logl_rel=1e-9, len_abs=1e-5)
