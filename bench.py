@@ -569,8 +569,13 @@ def ours(args):
         lk_ms = ctx.lookup_ms()
         K = 16 if S == 4 else 24
         lk_bytes = 2.0 * n * 4 * S * 8 + 2.0 * n * 4 * sr + n * K * 8            # two CLVs + scalers in, table out
-        kernels["lookup_build"] = {"ms": lk_ms, "units": B, "bytes_per_unit": lk_bytes,
-                                   "achieved_gbs": B * lk_bytes / (lk_ms / 1e3) / 1e9 if lk_ms > 0 else 0.0}
+        # DNA: a tip edge reads the tip's n state masks instead of a CLV (as the reference reads tipchars)
+        lk_tip = lk_bytes - (n * 4 * S * 8 - n if cfg["kind"] == "dna" else 0)
+        T_ = cfg["T"]
+        lk_total = (B - T_) * lk_bytes + T_ * lk_tip
+        kernels["lookup_build"] = {"ms": lk_ms, "units": B, "bytes_per_unit": lk_total / B,
+                                   "bytes_inner_edge": lk_bytes, "bytes_tip_edge": lk_tip,
+                                   "achieved_gbs": lk_total / (lk_ms / 1e3) / 1e9 if lk_ms > 0 else 0.0}
         kernels["lookup_build"]["frac"] = kernels["lookup_build"]["achieved_gbs"] / peak
         for k in ("upload_encode", "select", "collect"):
             kernels[k] = {"ms_per_step": stage_ms[k] / args.steps}

@@ -193,6 +193,7 @@ struct epa_ctx {
   double * d_pn = nullptr;         // DNA: prefix sums of the fully-ambiguous lookup column [edge][n + 1]
   bool mma_ok = false;             // every table entry fits the fixed-point format
   double * d_clvT = nullptr;       // DNA: site-blocked CLV copy read by the lane = site BLO kernel
+  uint8_t * d_tipmask = nullptr;   // DNA: [tip][site] 4-bit state masks (the lookup build reads them instead of a tip's 0/1 CLV)
   double * d_gT = nullptr;         // DNA: per-edge first-round tables of the BLO kernel (site-blocked)
   bool clvT_ready = false;         // covers d_clvT and d_gT
   bool clvs_ready = false, lookup_ready = false;
@@ -236,6 +237,7 @@ struct epa_ctx {
     bool no_first = false;     // EPA_B200_NO_FIRST: full first CLV pass instead of the per-edge tables
     bool no_tmem = false;      // EPA_B200_NO_TMEM: sumtables in shared memory only
     bool old_aa = false;       // EPA_B200_OLD_AA: (site, rate)-per-thread amino-acid passes
+    bool lookup_tip_clv = false;   // EPA_B200_LOOKUP_TIP_CLV: the lookup build streams a tip's 0/1 CLV instead of its masks (A/B)
     bool aa_dfma = false;      // EPA_B200_AA_DFMA: the DFMA amino-acid kernel (kernels_blo_generic.cuh) instead of the DMMA one
     int gs_below = 6;          // EPA_B200_BLO_GS_BELOW: resident warps below which the global-scratch variant runs
     int gs_warps = 8;          // EPA_B200_GS_WARPS: warps per CTA of the global-scratch variant
@@ -407,7 +409,7 @@ extern "C" void epa_ctx_destroy(epa_ctx * ctx)
   for (auto & e : ctx->ev_d2h) if (e) cudaEventDestroy(e);
   dev_free(ctx->d_model); dev_free(ctx->tree.clv); dev_free(ctx->tree.scaler); dev_free(ctx->d_edges);
   dev_free(const_cast<double *>(ctx->tree.inv));
-  dev_free(ctx->d_lookup); dev_free(ctx->d_pairtab); dev_free(ctx->d_clvT); dev_free(ctx->d_gT); dev_free(ctx->d_btab); dev_free(ctx->d_pn); dev_free(ctx->d_flags); dev_free(ctx->d_counter); dev_free(ctx->d_total);
+  dev_free(ctx->d_lookup); dev_free(ctx->d_pairtab); dev_free(ctx->d_clvT); dev_free(ctx->d_tipmask); dev_free(ctx->d_gT); dev_free(ctx->d_btab); dev_free(ctx->d_pn); dev_free(ctx->d_flags); dev_free(ctx->d_counter); dev_free(ctx->d_total);
   for (auto & e : ctx->ev) if (e) cudaEventDestroy(e);
   if (ctx->stream && ctx->own_stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
@@ -474,6 +476,7 @@ extern "C" int epa_ctx_create(epa_ctx ** out, int device, const epa_model_desc *
   ctx->sw.no_tmem = getenv("EPA_B200_NO_TMEM") != nullptr;
   ctx->sw.old_aa = getenv("EPA_B200_OLD_AA") != nullptr;
   ctx->sw.aa_dfma = getenv("EPA_B200_AA_DFMA") != nullptr;
+  ctx->sw.lookup_tip_clv = getenv("EPA_B200_LOOKUP_TIP_CLV") != nullptr;
   if (const char * v = getenv("EPA_B200_BLO_GS_BELOW")) ctx->sw.gs_below = atoi(v);
   if (const char * v = getenv("EPA_B200_GS_WARPS")) ctx->sw.gs_warps = std::max(1, std::min(12, atoi(v)));
   if (const char * v = getenv("EPA_B200_SITE_WARPS")) ctx->sw.site_warps = atoi(v);
@@ -609,6 +612,13 @@ extern "C" int epa_ctx_create(epa_ctx ** out, int device, const epa_model_desc *
     CUC(cudaGetLastError());
     CUC(cudaStreamSynchronize(ctx->stream));
     dev_free(d_masks);
+    if (S == 4)
+    {
+      std::vector<uint8_t> m8(tip_sites);
+      for (size_t i = 0; i < tip_sites; ++i) m8[i] = (uint8_t) (tip_masks[i] & 15u);
+      CUC(dev_alloc(&ctx->d_tipmask, tip_sites));
+      CUC(cudaMemcpy(ctx->d_tipmask, m8.data(), tip_sites, cudaMemcpyHostToDevice));
+    }
   }
   {
     std::lock_guard<std::mutex> lock(g_const_mutex);
@@ -857,7 +867,7 @@ extern "C" int epa_build_lookup(epa_ctx * ctx)
     // lane = site kernel over the site-blocked CLV copy; its column table goes to constant memory
     // as [c][r][i] (the mutex covers copy + launch: the symbol is shared by the contexts of a process)
     const size_t t_stride = clvt_node_stride(n, R);
-    dim3 grid(B, (n + 127) / 128);
+    dim3 grid(B, (n + 128 * LOOKUP_ITER - 1) / (128 * LOOKUP_ITER));
     std::vector<double> hcol((size_t) R * K * 4), hperm((size_t) K * R * 4);
     CU(cudaMemcpyAsync(hcol.data(), d_col, hcol.size() * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
@@ -868,11 +878,12 @@ extern "C" int epa_build_lookup(epa_ctx * ctx)
       std::lock_guard<std::mutex> lock(g_const_mutex);
       CU(cudaMemcpyToSymbol(c_coltab, hperm.data(), hperm.size() * sizeof(double)));
       CU(cudaEventRecord(ctx->ev[0], ctx->stream));
+      const uint8_t * tipmask = ctx->sw.lookup_tip_clv ? nullptr : ctx->d_tipmask;
       switch (R)
       {
-        case 1: lookup_build_site_kernel<1><<<grid, 128, 4 * lookup_warp_doubles<1>() * sizeof(double), ctx->stream>>>(ctx->d_model, ctx->d_clvT, t_stride, ctx->tree.scaler, (int) ctx->tree.sr, ctx->tree.inv, n, ctx->n_pad, ctx->d_edges, d_pm, ctx->d_lookup); break;
-        case 2: lookup_build_site_kernel<2><<<grid, 128, 4 * lookup_warp_doubles<2>() * sizeof(double), ctx->stream>>>(ctx->d_model, ctx->d_clvT, t_stride, ctx->tree.scaler, (int) ctx->tree.sr, ctx->tree.inv, n, ctx->n_pad, ctx->d_edges, d_pm, ctx->d_lookup); break;
-        default: lookup_build_site_kernel<4><<<grid, 128, 4 * lookup_warp_doubles<4>() * sizeof(double), ctx->stream>>>(ctx->d_model, ctx->d_clvT, t_stride, ctx->tree.scaler, (int) ctx->tree.sr, ctx->tree.inv, n, ctx->n_pad, ctx->d_edges, d_pm, ctx->d_lookup); break;
+        case 1: lookup_build_site_kernel<1><<<grid, 128, 4 * lookup_warp_doubles<1>() * sizeof(double), ctx->stream>>>(ctx->d_model, ctx->d_clvT, t_stride, ctx->tree.scaler, (int) ctx->tree.sr, ctx->tree.inv, n, ctx->n_pad, ctx->d_edges, d_pm, ctx->d_lookup, tipmask, ctx->n_tips); break;
+        case 2: lookup_build_site_kernel<2><<<grid, 128, 4 * lookup_warp_doubles<2>() * sizeof(double), ctx->stream>>>(ctx->d_model, ctx->d_clvT, t_stride, ctx->tree.scaler, (int) ctx->tree.sr, ctx->tree.inv, n, ctx->n_pad, ctx->d_edges, d_pm, ctx->d_lookup, tipmask, ctx->n_tips); break;
+        default: lookup_build_site_kernel<4><<<grid, 128, 4 * lookup_warp_doubles<4>() * sizeof(double), ctx->stream>>>(ctx->d_model, ctx->d_clvT, t_stride, ctx->tree.scaler, (int) ctx->tree.sr, ctx->tree.inv, n, ctx->n_pad, ctx->d_edges, d_pm, ctx->d_lookup, tipmask, ctx->n_tips); break;
       }
       LAUNCHED(ctx);
       CU(cudaStreamSynchronize(ctx->stream));

@@ -263,10 +263,19 @@ __constant__ double c_coltab[16 * 4 * MAX_RATES / 2];      // R <= 4
 // Absolute error ~1e-16 (|log x| + 1): the table sums of the preplacement are insensitive to it.
 // The CUDA log() is ~90 instructions with its special-case handling, and 15 of them per site made
 // the lookup build issue bound; zero, subnormal, negative and non-finite arguments still take it.
+__device__ __forceinline__ bool table_log_ok(double x)      // positive normal
+{
+  return (unsigned) (__double2hiint(x) - 0x00100000) < 0x7fe00000u;
+}
+__device__ __forceinline__ double table_log_fast(double x, const double2 * __restrict__ tab);
 __device__ __forceinline__ double table_log(double x, const double2 * __restrict__ tab)
 {
+  if (!table_log_ok(x)) return log(x);
+  return table_log_fast(x, tab);
+}
+__device__ __forceinline__ double table_log_fast(double x, const double2 * __restrict__ tab)
+{
   const int hi = __double2hiint(x);
-  if ((unsigned) (hi - 0x00100000) >= 0x7fe00000u) return log(x);
   const double2 t = tab[(hi >> 13) & 127];
   const double m = __hiloint2double((hi & 0x000fffff) | 0x3ff00000, __double2loint(x));
   const double r = fma(m, t.x, -1.0);
@@ -297,12 +306,17 @@ __device__ double2 g_logtab[128];
 template <int R>
 __host__ __device__ constexpr int lookup_warp_doubles() { return (2 * 4 * R * 32 > 32 * 17 ? 2 * 4 * R * 32 : 32 * 17 + 32) & ~31; }
 
+// A block takes LOOKUP_ITER consecutive 128-site groups of its edge: the transition matrix, the logarithm table
+// and the barrier set-up are paid once per block.
+#ifndef LOOKUP_ITER
+#define LOOKUP_ITER 2
+#endif
 template <int R>
 __global__ void __launch_bounds__(128, 6)
 lookup_build_site_kernel(const DevModel * __restrict__ m, const double * __restrict__ clvT, size_t t_stride,
                          const uint32_t * __restrict__ scaler, int sr, const double * __restrict__ inv_lk, int n, int n_pad,
                          const EdgeDev * __restrict__ edges, const double * __restrict__ pmats_half,
-                         double * __restrict__ lookup)
+                         double * __restrict__ lookup, const uint8_t * __restrict__ tipmask = nullptr, uint32_t n_tips = 0)
 {
   constexpr int K = 16, C = 4 * R, WD = lookup_warp_doubles<R>();
   extern __shared__ __align__(128) double lk_stage[];   // [4 warps][WD]
@@ -311,125 +325,167 @@ lookup_build_site_kernel(const DevModel * __restrict__ m, const double * __restr
   __shared__ uint64_t bar[4];
   const EdgeDev e = edges[blockIdx.x];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int site0 = blockIdx.y * 128 + warp * 32;
-  const bool have = site0 < n;                       // the site-blocked copy is padded to whole 32-site blocks
-  const int site = site0 + lane;
-  const int s = site < n ? site : n - 1;
   double * stage = lk_stage + warp * WD;
-  if (threadIdx.x < 4) { mbar_init(&bar[threadIdx.x], 1); mbar_fence_init(); }
-  __syncthreads();
+  // every warp owns one barrier: set up by its lane 0, no block-wide synchronisation
+  if (lane == 0) { mbar_init(&bar[warp], 1); mbar_fence_init(); }
+  __syncwarp();
   // The two 32-site CLV columns of the warp (C x 256 bytes each, contiguous in the site-blocked copy)
   // arrive as two bulk copies: no registers are tied up while they are in flight, six blocks stay
   // resident per SM and their load and arithmetic phases overlap.
-  if (have && lane == 0)
+  // A tip edge (the tip is always distal) reads the tip's n state masks, as the reference reads its tipchars,
+  // instead of streaming a 0/1 CLV: 32 bytes per warp in place of 4 KB x R.
+  const bool tip_d = tipmask != nullptr && e.distal < n_tips;          // block-uniform
+  auto issue = [&](int site0)
   {
-    constexpr uint32_t bytes = C * 32 * sizeof(double);
-    const size_t boff = (size_t) (site0 >> 5) * (size_t) (C * CLVT_BLOCK);
-    mbar_expect_tx(&bar[warp], 2 * bytes);
-    bulk_g2s(stage, clvT + (size_t) e.distal * t_stride + boff, bytes, &bar[warp]);
-    bulk_g2s(stage + C * 32, clvT + (size_t) e.proximal * t_stride + boff, bytes, &bar[warp]);
-  }
-  uint32_t kr[R];
-  if (sr == 1)
-    kr[0] = __ldg(scaler + (size_t) e.distal * n + s) + __ldg(scaler + (size_t) e.proximal * n + s);
-  else
-  {
-    #pragma unroll
-    for (int r = 0; r < R; ++r)
-      kr[r] = __ldg(scaler + ((size_t) e.distal * n + s) * R + r) + __ldg(scaler + ((size_t) e.proximal * n + s) * R + r);
-  }
-  const double inv = inv_lk ? __ldg(inv_lk + s) : 0.0;
+    // (the site-blocked copy is padded to whole 32-site blocks)
+    if (site0 < n && lane == 0)
+    {
+      constexpr uint32_t bytes = C * 32 * sizeof(double);
+      const size_t boff = (size_t) (site0 >> 5) * (size_t) (C * CLVT_BLOCK);
+      mbar_expect_tx(&bar[warp], tip_d ? bytes : 2 * bytes);
+      if (!tip_d) bulk_g2s(stage, clvT + (size_t) e.distal * t_stride + boff, bytes, &bar[warp]);
+      bulk_g2s(stage + C * 32, clvT + (size_t) e.proximal * t_stride + boff, bytes, &bar[warp]);
+    }
+  };
+  const int first0 = blockIdx.y * (LOOKUP_ITER * 128) + warp * 32;
+  issue(first0);
   for (int i = threadIdx.x; i < R * 16; i += blockDim.x) P[i] = __ldg(pmats_half + (size_t) blockIdx.x * R * 16 + i);
   for (int i = threadIdx.x; i < 128; i += blockDim.x) logtab[i] = g_logtab[i];
-  __syncthreads();
-  if (!have) return;                                 // (no block-wide barrier below)
-  mbar_wait(&bar[warp], 0);
-  uint32_t sc = 0;
-  double in[C];
-  bool small = true;
-  #pragma unroll
-  for (int r = 0; r < R; ++r)
+  __syncthreads();                                   // (no block-wide barrier below)
+  #pragma unroll 1
+  for (int it = 0; it < LOOKUP_ITER; ++it)
   {
-    double dv[4], xv[4];
-    #pragma unroll
-    for (int k = 0; k < 4; ++k) { dv[k] = stage[(r * 4 + k) * 32 + lane]; xv[k] = stage[(C + r * 4 + k) * 32 + lane]; }
-    #pragma unroll
-    for (int i = 0; i < 4; ++i)
+    const int site0 = first0 + it * 128;
+    if (site0 >= n) break;
+    if (it > 0)
     {
-      double p[4];
-      lds_vec<4>(P + r * 16 + i * 4, p);
-      const double ta = p[0] * dv[0] + p[1] * dv[1] + p[2] * dv[2] + p[3] * dv[3];
-      const double tb = p[0] * xv[0] + p[1] * xv[1] + p[2] * xv[2] + p[3] * xv[3];
-      in[r * 4 + i] = ta * tb;
-      small = small && (in[r * 4 + i] < EPA_SCALE_THRESHOLD);
+      // the slice held result rows written and read through the generic proxy: order them before the bulk copies
+      fence_proxy_async_smem();
+      __syncwarp();
+      issue(site0);
     }
-  }
-  __syncwarp();                                      // every lane has consumed its columns: the slice is reused for the result rows
-  if (sr == 1)
-  {
-    sc = kr[0];
-    if (small)
+    const int site = site0 + lane;
+    const int s = site < n ? site : n - 1;
+    const uint32_t dmask = tip_d ? __ldg(tipmask + (size_t) e.distal * n + s) : 0u;
+    uint32_t kr[R];
+    if (sr == 1)
+      kr[0] = __ldg(scaler + (size_t) e.distal * n + s) + __ldg(scaler + (size_t) e.proximal * n + s);
+    else
     {
-      sc += 1;
       #pragma unroll
-      for (int c = 0; c < C; ++c) in[c] *= EPA_SCALE_FACTOR;
+      for (int r = 0; r < R; ++r)
+        kr[r] = __ldg(scaler + ((size_t) e.distal * n + s) * R + r) + __ldg(scaler + ((size_t) e.proximal * n + s) * R + r);
     }
-  }
-  else
-  {
-    // per-rate scalers: a rate whose count is d above the site's minimum weighs 2^(-256 d). The inner
-    // CLV is not rescaled here: its own per-rate rescaling would only move factors of 2^256 between
-    // the values and these counts.
-    uint32_t kmin = 0xffffffffu;
-    #pragma unroll
-    for (int r = 0; r < R; ++r) kmin = min(kmin, kr[r]);
+    const double inv = inv_lk ? __ldg(inv_lk + s) : 0.0;
+    mbar_wait(&bar[warp], (uint32_t) (it & 1));
+    uint32_t sc = 0;
+    double in[C];
+    bool small = true;
     #pragma unroll
     for (int r = 0; r < R; ++r)
     {
-      const double f = rate_scale_factor(min(kr[r] - kmin, EPA_RATE_MAXDIFF));
+      double dv[4], xv[4];
       #pragma unroll
-      for (int i = 0; i < 4; ++i) in[r * 4 + i] *= f;
+      for (int k = 0; k < 4; ++k)
+      {
+        dv[k] = tip_d ? (((dmask >> k) & 1u) ? 1.0 : 0.0) : stage[(r * 4 + k) * 32 + lane];
+        xv[k] = stage[(C + r * 4 + k) * 32 + lane];
+      }
+      #pragma unroll
+      for (int i = 0; i < 4; ++i)
+      {
+        double p[4];
+        lds_vec<4>(P + r * 16 + i * 4, p);
+        const double ta = p[0] * dv[0] + p[1] * dv[1] + p[2] * dv[2] + p[3] * dv[3];
+        const double tb = p[0] * xv[0] + p[1] * xv[1] + p[2] * xv[2] + p[3] * xv[3];
+        in[r * 4 + i] = ta * tb;
+        small = small && (in[r * 4 + i] < EPA_SCALE_THRESHOLD);
+      }
     }
-    sc = kmin;
-  }
-  // The likelihood of a state set is the sum of the likelihoods of its states: four single-state terms
-  // (columns 1, 2, 4, 8 of the column table), eleven sums, fifteen logarithms.
-  double single[4];
-  #pragma unroll
-  for (int j = 0; j < 4; ++j)
-  {
-    const int c = 1 << j;
-    double term = 0.0;
-    #pragma unroll
-    for (int r = 0; r < R; ++r)
+    __syncwarp();                                      // every lane has consumed its columns: the slice is reused for the result rows
+    if (sr == 1)
     {
-      const double tr = in[r * 4] * c_coltab[c * C + r * 4] + in[r * 4 + 1] * c_coltab[c * C + r * 4 + 1]
-                      + in[r * 4 + 2] * c_coltab[c * C + r * 4 + 2] + in[r * 4 + 3] * c_coltab[c * C + r * 4 + 3];
-      term += tr * c_model.weights[r];
+      sc = kr[0];
+      if (small)
+      {
+        sc += 1;
+        #pragma unroll
+        for (int c = 0; c < C; ++c) in[c] *= EPA_SCALE_FACTOR;
+      }
     }
-    single[j] = term;
-  }
-  double * trow = stage + lane * 17;
-  trow[0] = 0.0;                                       // column 0 = zero column
-  #pragma unroll
-  for (int c = 1; c < K; ++c)
-  {
-    double term = 0.0;
-    bool any = false;
+    else
+    {
+      // per-rate scalers: a rate whose count is d above the site's minimum weighs 2^(-256 d). The inner
+      // CLV is not rescaled here: its own per-rate rescaling would only move factors of 2^256 between
+      // the values and these counts.
+      uint32_t kmin = 0xffffffffu;
+      #pragma unroll
+      for (int r = 0; r < R; ++r) kmin = min(kmin, kr[r]);
+      #pragma unroll
+      for (int r = 0; r < R; ++r)
+      {
+        const double f = rate_scale_factor(min(kr[r] - kmin, EPA_RATE_MAXDIFF));
+        #pragma unroll
+        for (int i = 0; i < 4; ++i) in[r * 4 + i] *= f;
+      }
+      sc = kmin;
+    }
+    // The likelihood of a state set is the sum of the likelihoods of its states: four single-state terms
+    // (columns 1, 2, 4, 8 of the column table), eleven sums, fifteen logarithms.
+    double single[4];
     #pragma unroll
     for (int j = 0; j < 4; ++j)
-      if ((c >> j) & 1) { term = any ? term + single[j] : single[j]; any = true; }
-    trow[c] = site_loglk_tab(term, sc, inv, logtab);
-  }
-  __syncwarp();
-  // the warp's 32 table rows are 4 KB contiguous in global memory: coalesced 256-byte stores
-  const int n_valid = min(32, n - site0) * K;
-  double * out = lookup + ((size_t) blockIdx.x * n_pad + site0) * K;
-  #pragma unroll
-  for (int k = 0; k < K; ++k)
-  {
-    const int idx = k * 32 + lane;
-    if (idx < n_valid) out[idx] = stage[(idx >> 4) * 17 + (idx & 15)];
+    {
+      const int c = 1 << j;
+      double term = 0.0;
+      #pragma unroll
+      for (int r = 0; r < R; ++r)
+      {
+        const double tr = in[r * 4] * c_coltab[c * C + r * 4] + in[r * 4 + 1] * c_coltab[c * C + r * 4 + 1]
+                        + in[r * 4 + 2] * c_coltab[c * C + r * 4 + 2] + in[r * 4 + 3] * c_coltab[c * C + r * 4 + 3];
+        term += tr * c_model.weights[r];
+      }
+      single[j] = term;
+    }
+    double * trow = stage + lane * 17;
+    trow[0] = 0.0;                                       // column 0 = zero column
+    // site_loglk_tab for the fifteen columns, with ONE test for the table logarithm's fast path (all arguments
+    // positive and normal) instead of a branch per column
+    double x[K];
+    bool ok = true;
+    const double undo = (inv > 0.0 && sc) ? rate_scale_factor(min(sc, EPA_RATE_MAXDIFF)) : 1.0;
+    #pragma unroll
+    for (int c = 1; c < K; ++c)
+    {
+      double term = 0.0;
+      bool any = false;
+      #pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if ((c >> j) & 1) { term = any ? term + single[j] : single[j]; any = true; }
+      x[c] = inv > 0.0 ? (sc ? term * undo + inv : term + inv) : term;
+      ok = ok && table_log_ok(x[c]);
+    }
+    const double add = (!(inv > 0.0) && sc) ? (double) sc * EPA_LOG_SCALE_THRESHOLD : 0.0;
+    if (ok)
+    {
+      #pragma unroll
+      for (int c = 1; c < K; ++c) trow[c] = table_log_fast(x[c], logtab) + add;
+    }
+    else
+    {
+      #pragma unroll
+      for (int c = 1; c < K; ++c) trow[c] = table_log(x[c], logtab) + add;
+    }
+    __syncwarp();
+    // the warp's 32 table rows are 4 KB contiguous in global memory: coalesced 256-byte stores
+    const int n_valid = min(32, n - site0) * K;
+    double * out = lookup + ((size_t) blockIdx.x * n_pad + site0) * K;
+    #pragma unroll
+    for (int k = 0; k < K; ++k)
+    {
+      const int idx = k * 32 + lane;
+      if (idx < n_valid) out[idx] = stage[(idx >> 4) * 17 + (idx & 15)];
+    }
   }
 }
 
