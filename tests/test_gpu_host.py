@@ -169,3 +169,29 @@ def test_pipeline_reports_query_errors(built, tmp_path):
         short = str(tmp_path / "short.fasta")
         open(short, "w").write(">x\nACGT\n")
         built.session.run_files_multi(os.path.join(d, "ref.tre"), os.path.join(d, "aln.fasta"), short, helpers.GTRG, str(tmp_path / "o2"))
+
+
+def test_device_block_cache_reuse_and_trim(built):
+    """Contexts allocate through the per-process device block cache: a second context of the same shape takes the
+    blocks of the first, epa_device_pool_trim hands them back to the driver, and results do not depend on either."""
+    import torch
+    case = helpers.synth64_case()
+    opts = built.capi.default_options()
+
+    def run():
+        ctx = helpers.make_context(case)
+        ctx.build_lookup()
+        out, counts = ctx.place_chunk(case.query_rows, opts)
+        ctx.close()
+        return out.copy(), counts.copy()
+
+    a, ca = run()
+    free_cached, _ = torch.cuda.mem_get_info(0)
+    b, cb = run()                                   # reuses the cached blocks
+    built.capi.load().epa_device_pool_trim()
+    free_trimmed, _ = torch.cuda.mem_get_info(0)
+    c, cc = run()                                   # allocates afresh
+    assert np.array_equal(ca, cb) and np.array_equal(ca, cc)
+    assert a.tobytes() == b.tobytes() == c.tobytes()
+    assert free_trimmed >= free_cached              # the cache gave its blocks back
+    built.capi.load().epa_device_pool_trim()
