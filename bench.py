@@ -430,7 +430,24 @@ def ours(args):
     stage_ms = {"upload_encode": 0.0, "preplace": 0.0, "select": 0.0, "thorough": 0.0, "collect": 0.0}
     pairs_total = [0]
 
-    def step_resident(record=False):
+    # N > 1, device-resident step: rank 0 owns the records of all shards and every rank's collect kernel writes its block
+    # straight into that buffer over NVLink (CUDA IPC peer memory, shard.PeerRecords) - the gather happens inside the
+    # kernel; --nccl-gather (or a box without peer access) uses one NCCL gather of the fixed-stride records instead
+    peer, peer_note = None, None
+    if world > 1 and not args.nccl_gather:
+        try:
+            peer = pkg.shard.PeerRecords(capi, Q, fmax, local, dst=0, group=cpu_group)
+        except Exception as ex:                  # noqa: BLE001 - any failure falls back to the NCCL gather
+            peer_note = "peer memory unavailable (%s): NCCL gather" % str(ex)[:120]
+        ok = torch.tensor([1 if peer is not None else 0], dtype=torch.int32, device=dev)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if int(ok.item()) == 0:
+            if peer is not None:
+                peer.close()
+            peer = None
+
+    def step_resident(record=False, local_only=False):
+        use_peer = peer is not None and not local_only
         for lo in range(0, Q, chunk):
             nq = min(chunk, Q - lo)
             ctx.encode_queries_dev(dev_q.data_ptr() + lo * n, nq, True)
@@ -439,12 +456,18 @@ def ours(args):
                 ctx.preplace()
             npairs = ctx.select(opts)
             ctx.place_pairs(opts)
-            ctx.collect_dev(opts, rec_dev.data_ptr() + lo * fmax * 40, cnt_dev.data_ptr() + lo * 4)
+            if use_peer:
+                rp, cp = peer.slice_ptrs(lo)
+                ctx.collect_dev(opts, rp, cp)
+            else:
+                ctx.collect_dev(opts, rec_dev.data_ptr() + lo * fmax * 40, cnt_dev.data_ptr() + lo * 4)
             if record:
                 for k, v in ctx.timings().items():
                     stage_ms[k] += v
                 pairs_total[0] += npairs
-        if world > 1:
+        if use_peer:
+            peer.complete()                     # every rank's records are in rank 0's memory
+        elif world > 1 and not local_only:
             # the single gather of placement records (NCCL over NVLink): rank 0 ends up with the
             # records of all shards in global query order
             pkg.shard.gather_records(rec_dev, cnt_dev, Q * world, dst=0)
@@ -455,12 +478,26 @@ def ours(args):
         comp_all_host = torch.zeros((Q * world * fmax, 5), dtype=torch.float64).pin_memory()     # compacted records of all shards
         cnt_all_host = torch.zeros(Q * world, dtype=torch.int32).pin_memory()
 
+    # N > 1, end to end: the gather of a step and rank 0's copy-out of all shards (0.4 GB over one PCIe link at N = 8)
+    # run on a side stream beside the kernels of the next step; the device records alternate between two buffers
+    side = torch.cuda.Stream(device=dev) if world > 1 else None
+    rec_alt = [rec_dev, torch.zeros_like(rec_dev)] if world > 1 else [rec_dev]
+    cnt_alt = [cnt_dev, torch.zeros_like(cnt_dev)] if world > 1 else [cnt_dev]
+    gathered = [None, None]                 # event: the gather of the step that used buffer k has read it
+    e2e_no = [0]
+    e2e_last = [0]
+
     def step_e2e():
         if world == 1:
             sess.place((host_q.data_ptr(), Q), opts, chunk, out=rec_host.data_ptr(), counts=cnt_host.data_ptr())
             return
         # N > 1: queries from pinned host memory (the copy of the next chunk overlaps this one), records
         # stay on the device, ONE gather brings every shard to rank 0 (NCCL), rank 0 copies all of them out
+        k = e2e_no[0] & 1
+        e2e_no[0] += 1
+        rec_dev, cnt_dev = rec_alt[k], cnt_alt[k]
+        if gathered[k] is not None:
+            stream.wait_event(gathered[k])
         for lo in range(0, Q, chunk):
             nq = min(chunk, Q - lo)
             if lo + nq < Q:
@@ -473,14 +510,21 @@ def ours(args):
             ctx.place_pairs(opts)
             ctx.collect_dev(opts, rec_dev.data_ptr() + lo * fmax * 40, cnt_dev.data_ptr() + lo * 4)
         # compacted: only the filled records travel (1.2 of 7 per query), NCCL gather, then rank 0's copy-out
-        parts, cnts = pkg.shard.gather_compact(rec_dev, cnt_dev, Q * world, dst=0)
-        if rank == 0:
-            at = 0
-            for p_ in parts:
-                comp_all_host[at:at + p_.shape[0]].copy_(p_, non_blocking=True)
-                at += p_.shape[0]
-            e2e_records[0] = at
-            cnt_all_host.copy_(cnts, non_blocking=True)
+        side.wait_stream(stream)
+        with torch.cuda.stream(side):
+            parts, cnts = pkg.shard.gather_compact(rec_dev, cnt_dev, Q * world, dst=0)
+            gathered[k] = torch.cuda.Event()
+            gathered[k].record(side)
+            if rank == 0:
+                at = 0
+                for p_ in parts:
+                    comp_all_host[at:at + p_.shape[0]].copy_(p_, non_blocking=True)
+                    p_.record_stream(side)
+                    at += p_.shape[0]
+                e2e_records[0] = at
+                cnt_all_host.copy_(cnts, non_blocking=True)
+                cnts.record_stream(side)
+        e2e_last[0] = k
 
     def barrier():
         if world > 1:
@@ -493,6 +537,8 @@ def ours(args):
         e0.record(stream)
         for _ in range(steps):
             fn(**kw)
+        if side is not None:
+            stream.wait_stream(side)          # the last step's gather and copy-out belong to the timed region
         e1.record(stream)
         barrier()
         ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
@@ -508,6 +554,15 @@ def ours(args):
     ms_res = timed(step_resident, args.steps, record=True)
     launches = ctx.launch_count() - l0
     clocks = sampler.stop()
+    peer_same = None
+    if peer is not None:
+        # the peer-written buffer against one NCCL gather of the same records
+        step_resident(local_only=True)
+        g_rec, g_cnt = pkg.shard.gather_records(rec_dev, cnt_dev, Q * world, dst=0)
+        torch.cuda.synchronize()
+        if rank == 0:
+            peer_same = bool(torch.equal(g_rec, peer.records) and torch.equal(g_cnt, peer.counts))
+        del g_rec, g_cnt
     for _ in range(min(args.warmup, 1)):
         step_e2e()
     ms_e2e = timed(step_e2e, args.steps)
@@ -517,8 +572,8 @@ def ours(args):
         same = bool(np.array_equal(rec_host.numpy(), rec_dev.cpu().numpy())
                     and np.array_equal(cnt_host.numpy(), cnt_dev.cpu().numpy()))
     else:
-        rec_host.copy_(rec_dev)
-        cnt_host.copy_(cnt_dev)
+        rec_host.copy_(rec_alt[e2e_last[0]])
+        cnt_host.copy_(cnt_alt[e2e_last[0]])
         same = True
         if rank == 0:
             # rank 0's own shard comes first in the gathered, compacted records
@@ -649,10 +704,17 @@ def ours(args):
                     "h2d_bytes_per_step": int(Q) * n,
                     "d2h_bytes_per_step": int(Q) * (fmax * 40 + 4) if world == 1 else int(e2e_records[0]) * 40 + int(Q) * world * 4,
                     "note": None if world == 1 else "per rank: upload from pinned host memory, records stay on the device; one NCCL gather of "
-                                                    "the compacted records + counts to rank 0, which copies all shards out (d2h bytes = rank 0's)"},
+                                                    "the compacted records + counts to rank 0, which copies all shards out (d2h bytes = rank 0's); "
+                                                    "gather and copy-out of a step run on a side stream beside the next step's kernels, the last "
+                                                    "step's are waited for inside the timed region"},
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "kernels": kernels,
             "candidate_pairs_per_query": pairs / Q, "chunk": chunk, "resident_equals_e2e": same,
         }
+        if world > 1:
+            out["gather"] = ({"kind": "peer memory", "what": "rank 0 owns the records of all shards (CUDA IPC); every rank's collect kernel writes "
+                              "its block straight into it over NVLink, one 4-byte all-reduce completes the step",
+                              "equals_nccl_gather": peer_same} if peer is not None
+                             else {"kind": "nccl", "what": "one NCCL gather of the fixed-stride records + one of the counts", "note": peer_note})
         if files:
             out["e2e_files"] = files
         if cpu:
@@ -661,6 +723,13 @@ def ours(args):
             out["parity_vs_reference"] = parity
         print(json.dumps(out))
     if world > 1:
+        torch.cuda.synchronize()
+        dist.barrier()
+        if peer is not None and rank != 0:
+            peer.close()                        # the importers unmap ...
+        dist.barrier()
+        if peer is not None and rank == 0:
+            peer.close()                        # ... before the owner frees
         dist.destroy_process_group()
     sess.close()
 
@@ -718,6 +787,7 @@ def main():
     ap.add_argument("--config", default="cfg2", choices=sorted(CONFIGS), help="BASELINE.json configuration [cfg2]")
     ap.add_argument("--queries", type=int, default=0, help="queries per GPU per step [the configuration's size]")
     ap.add_argument("--chunk", type=int, default=131072)
+    ap.add_argument("--nccl-gather", action="store_true", help="N > 1: gather the records of the resident step with NCCL instead of peer-memory writes")
     ap.add_argument("--ref-queries", type=int, default=0, help="size of the CPU reference sample")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--model", default="", help="place under this model string instead of the configuration's")

@@ -90,6 +90,10 @@ SYMBOLS = [
     ("epa_synchronize", C.c_int, [_vp]),
     ("epa_measure_fp64_peak", C.c_int, [C.c_int, C.POINTER(C.c_double)]),
     ("epa_device_pool_trim", None, []),
+    ("epa_peer_alloc", C.c_int, [C.c_int, C.c_size_t, C.POINTER(_vp), C.c_char_p]),
+    ("epa_peer_open", C.c_int, [C.c_int, C.c_char_p, C.POINTER(_vp)]),
+    ("epa_peer_close", C.c_int, [C.c_int, _vp]),
+    ("epa_peer_free", C.c_int, [C.c_int, _vp]),
     ("epa_pinned_alloc", C.c_int, [C.POINTER(_vp), C.c_size_t]),
     ("epa_pinned_free", None, [_vp]),
     ("epa_launch_count", C.c_uint64, [_vp]),

@@ -1949,6 +1949,61 @@ extern "C" void epa_pinned_free(void * ptr)
   if (ptr) (void) cudaFreeHost(ptr);
 }
 
+// ---- peer memory (multi-GPU, one process per GPU) ----------------------------------------------------------
+// The gather of the placement records without a collective: the owning rank allocates the buffer of all shards and
+// exports it (CUDA IPC), the other ranks of the box map it and hand their slice to epa_collect_dev - the collect
+// kernel then writes its records straight into the owner's memory over NVLink.
+extern "C" int epa_peer_alloc(int device, size_t bytes, void ** dptr, unsigned char * handle64)
+{
+  epa_ctx * none = nullptr;
+  if (!dptr || !handle64) return fail(none, EPA_ERR_ARG, "null argument");
+  *dptr = nullptr;
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "handle size");
+  if (cudaSetDevice(device) != cudaSuccess) { (void) cudaGetLastError(); return fail(none, EPA_ERR_CUDA, "cannot select device %d", device); }
+  cudaError_t e = cudaMalloc(dptr, bytes ? bytes : 1);        // its own allocation: the handle covers exactly this buffer
+  if (e != cudaSuccess) { (void) cudaGetLastError(); return fail(none, EPA_ERR_NOMEM, "peer buffer of %zu bytes: %s", bytes, cudaGetErrorString(e)); }
+  cudaIpcMemHandle_t h;
+  e = cudaIpcGetMemHandle(&h, *dptr);
+  if (e != cudaSuccess)
+  {
+    (void) cudaGetLastError();
+    (void) cudaFree(*dptr); *dptr = nullptr;
+    return fail(none, EPA_ERR_CUDA, "cudaIpcGetMemHandle: %s", cudaGetErrorString(e));
+  }
+  std::memcpy(handle64, &h, 64);
+  return EPA_OK;
+}
+
+extern "C" int epa_peer_open(int device, const unsigned char * handle64, void ** dptr)
+{
+  epa_ctx * none = nullptr;
+  if (!dptr || !handle64) return fail(none, EPA_ERR_ARG, "null argument");
+  *dptr = nullptr;
+  if (cudaSetDevice(device) != cudaSuccess) { (void) cudaGetLastError(); return fail(none, EPA_ERR_CUDA, "cannot select device %d", device); }
+  cudaIpcMemHandle_t h;
+  std::memcpy(&h, handle64, 64);
+  const cudaError_t e = cudaIpcOpenMemHandle(dptr, h, cudaIpcMemLazyEnablePeerAccess);
+  if (e != cudaSuccess) { (void) cudaGetLastError(); *dptr = nullptr; return fail(none, EPA_ERR_CUDA, "cudaIpcOpenMemHandle: %s", cudaGetErrorString(e)); }
+  return EPA_OK;
+}
+
+extern "C" int epa_peer_close(int device, void * dptr)
+{
+  if (!dptr) return EPA_OK;
+  if (cudaSetDevice(device) != cudaSuccess) { (void) cudaGetLastError(); return EPA_ERR_CUDA; }
+  if (cudaIpcCloseMemHandle(dptr) != cudaSuccess) { (void) cudaGetLastError(); return EPA_ERR_CUDA; }
+  return EPA_OK;
+}
+
+extern "C" int epa_peer_free(int device, void * dptr)
+{
+  if (!dptr) return EPA_OK;
+  if (cudaSetDevice(device) != cudaSuccess) { (void) cudaGetLastError(); return EPA_ERR_CUDA; }
+  (void) cudaDeviceSynchronize();
+  if (cudaFree(dptr) != cudaSuccess) { (void) cudaGetLastError(); return EPA_ERR_CUDA; }
+  return EPA_OK;
+}
+
 extern "C" int epa_synchronize(epa_ctx * ctx)
 {
   if (!ctx) return EPA_ERR_ARG;

@@ -83,3 +83,68 @@ def expand_compact(parts, counts: torch.Tensor, filter_max: int, fields: int = 5
     keep = torch.arange(filter_max, device=comp.device)[None, :] < counts[:, None].to(torch.int64)
     out[keep] = comp
     return out.view(q, filter_max * fields)
+
+
+class _CudaArray:
+    """zero-copy view of raw device memory for torch.as_tensor (__cuda_array_interface__)"""
+
+    def __init__(self, ptr: int, shape, typestr: str):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": typestr, "data": (int(ptr), False),
+                                         "version": 2, "strides": None}
+
+
+class PeerRecords:
+    """The gather without a collective, for one process per GPU on one NVLink box: rank `dst` owns the fixed-stride
+    records [world * part, filter_max * 5] (float64 view of the 40-byte records) and the counts [world * part] of ALL
+    shards in its device memory (epa_peer_alloc) and sends the 64-byte CUDA IPC handle to the other ranks; they map the
+    buffer (epa_peer_open) and give `slice_ptrs()` - their block of it - to epa_collect_dev, so that the collect kernel
+    writes the records straight into the owner's memory over NVLink while it runs. `complete()` is the barrier that ends
+    the gather: a one-element all-reduce, stream-ordered behind every rank's collect kernels.
+    (`group`: a process group for the handle broadcast, e.g. a gloo group; default group otherwise.)"""
+
+    def __init__(self, capi, part: int, filter_max: int, device: int, dst: int = 0, group=None):
+        import ctypes as C
+        self.capi, self.device, self.dst = capi, int(device), dst
+        self.world, self.rank = dist.get_world_size(), dist.get_rank()
+        self.part, self.fmax = int(part), int(filter_max)
+        self.rec_bytes = self.world * self.part * self.fmax * 40
+        self.cnt_off = (self.rec_bytes + 255) & ~255
+        total = self.cnt_off + self.world * self.part * 4
+        lib = capi.load()
+        ptr = C.c_void_p()
+        handle = C.create_string_buffer(64)
+        self.owner = self.rank == dst
+        box = [None]
+        if self.owner:
+            rc = lib.epa_peer_alloc(self.device, total, C.byref(ptr), handle)
+            box = [bytes(handle.raw) if rc == 0 else "error %d: %s" % (rc, lib.epa_last_error(None).decode())]
+        dist.broadcast_object_list(box, src=dst, group=group)          # (an allocation failure reaches every rank)
+        if isinstance(box[0], str):
+            raise capi.EpaError(-2, box[0])
+        if not self.owner:
+            rc = lib.epa_peer_open(self.device, box[0], C.byref(ptr))
+            if rc != 0:
+                raise capi.EpaError(rc, lib.epa_last_error(None).decode())
+        self.ptr = int(ptr.value)
+        dev = torch.device("cuda", self.device)
+        self.flag = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.records = self.counts = None
+        if self.owner:
+            self.records = torch.as_tensor(_CudaArray(self.ptr, (self.world * self.part, self.fmax * 5), "<f8"), device=dev)
+            self.counts = torch.as_tensor(_CudaArray(self.ptr + self.cnt_off, (self.world * self.part,), "<i4"), device=dev)
+
+    def slice_ptrs(self, first_query: int = 0):
+        """device pointers (records, counts) of query `first_query` of this rank's block"""
+        q = self.rank * self.part + first_query
+        return self.ptr + q * self.fmax * 40, self.ptr + self.cnt_off + q * 4
+
+    def complete(self):
+        dist.all_reduce(self.flag)
+
+    def close(self):
+        """Unmaps (owner: frees) the buffer. The caller makes sure that no rank still writes to it (a barrier)."""
+        if self.ptr:
+            lib = self.capi.load()
+            torch.cuda.synchronize(self.device)
+            (lib.epa_peer_free if self.owner else lib.epa_peer_close)(self.device, self.ptr)
+            self.ptr = 0

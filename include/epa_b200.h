@@ -245,6 +245,16 @@ void epa_device_pool_trim(void);
 /* Page-locked host memory for query rows and result records (full PCIe speed, asynchronous copies). */
 int epa_pinned_alloc(void ** ptr, size_t bytes);
 void epa_pinned_free(void * ptr);
+/* Peer memory for the gather of the records on a multi-GPU box with one process per GPU - the counterpart of the
+ * reference's MPI gather of the samples to rank 0 (src/net/epa_mpi_util.hpp, src/io/jplace_writer.hpp:92-132) without a
+ * collective: the owning rank allocates the buffer of all shards (epa_peer_alloc: device memory + a 64-byte CUDA IPC handle
+ * to send to the other ranks by any means), they map it (epa_peer_open) and pass their slice of it to epa_collect_dev:
+ * the collect kernel writes the records straight into the owner's memory over NVLink. A barrier between the ranks, after
+ * their streams are synchronised, completes the gather. */
+int epa_peer_alloc(int device, size_t bytes, void ** dptr, unsigned char * handle64);
+int epa_peer_open(int device, const unsigned char * handle64, void ** dptr);
+int epa_peer_close(int device, void * dptr);
+int epa_peer_free(int device, void * dptr);
 /* Number of kernel launches issued on behalf of the ctx since creation. */
 uint64_t epa_launch_count(const epa_ctx * ctx);
 
