@@ -728,3 +728,19 @@ def test_per_rate_amino_acids_files_to_jplace(built, tmp_path):
     got = {n: pq["p"] for pq in doc["placements"] for n in pq["n"]}
     for name, want in g["placements"].items():
         helpers.assert_placements_close(got[name], want, name)
+
+
+def test_two_contexts_with_different_models_alternate_on_one_device(cfg1, synth64, built):
+    """The model tables of the thorough kernels live in one constant-memory symbol per device: a context rebinds it
+    before it launches when another context used the device in between."""
+    (case_a, ctx_a), (case_b, ctx_b) = cfg1, synth64
+    opts = built.capi.default_options()
+    a0, ca0 = ctx_a.place_chunk(case_a.query_rows, opts)
+    b0, cb0 = ctx_b.place_chunk(case_b.query_rows, opts)
+    for _ in range(2):
+        a1, ca1 = ctx_a.place_chunk(case_a.query_rows, opts)
+        b1, cb1 = ctx_b.place_chunk(case_b.query_rows, opts)
+        assert np.array_equal(ca0, ca1) and a0.tobytes() == a1.tobytes()
+        assert np.array_equal(cb0, cb1) and b0.tobytes() == b1.tobytes()
+    want = case_a.placer.place(case_a.qseqs[0])
+    assert [int(g["branch_id"]) for g in a1[0][:ca1[0]]] == [p.edge for p in want]

@@ -266,3 +266,40 @@ def test_cli_takes_a_model_file_and_fails_loudly_without_a_gpu(tmp_path):
         assert not os.path.exists(os.path.join(str(tmp_path), "epa_result.jplace")) or os.path.getsize(os.path.join(str(tmp_path), "epa_result.jplace")) == 0
     else:
         assert r.returncode == 0
+
+
+def test_jplace_strings_are_escaped(built, tmp_path):
+    """Query names, the tree and the invocation go into JSON strings: quotes, backslashes and control characters are
+    escaped, the file stays valid JSON and the strings come back unchanged."""
+    import json
+    names = ['plain', 'with "quotes"', 'back\\slash', 'tab\there', 'mix "\\" end']
+    recs = np.zeros((len(names), 2), dtype=built.capi.PLACEMENT_DTYPE)
+    counts = np.ones(len(names), dtype=np.uint32)
+    for i in range(len(names)):
+        recs[i, 0] = (i, -100.0 - i, 1.0, 0.1, 0.2)
+    tree = "('t \"a\"':0.1{0},B:0.2{1},C\\\\x:0.3{2});"
+    inv = 'epa-ng-b200 --model "GTR+G" -w C:\\out'
+    out = str(tmp_path / "esc.jplace")
+    built.session.write_jplace(out, tree, inv, names, recs, counts, precision=6)
+    doc = json.loads(open(out).read())
+    assert [pq["n"][0] for pq in doc["placements"]] == names
+    assert doc["tree"] == tree and doc["metadata"]["invocation"] == inv
+    assert doc["placements"][1]["p"][0][:2] == [1, -101.0]
+
+
+def test_read_alignment_fails_when_the_label_buffer_is_too_small(built, tmp_path):
+    """Long FASTA headers must not be truncated silently: a label buffer that cannot hold them is an error."""
+    import ctypes as C
+    path = str(tmp_path / "long.fasta")
+    names = ["sequence_%03d_" % i + "x" * 150 for i in range(40)]
+    with open(path, "w") as fh:
+        for nm in names:
+            fh.write(">%s\nACGTACGT\n" % nm)
+    got, rows = built.session.read_alignment(path)
+    assert got == names and rows.shape == (40, 8)
+    L = built.session.lib()
+    n, sites = C.c_uint32(), C.c_uint32()
+    out = np.zeros((40, 8), dtype=np.uint8)
+    small = C.create_string_buffer(64 * 40)
+    rc = L.epa_host_read_alignment(path.encode(), C.byref(n), C.byref(sites), out.ctypes.data, out.size, small, len(small))
+    assert rc != 0 and b"label" in L.epa_host_last_error().lower()
