@@ -427,6 +427,25 @@ def ours(args):
     rec_host = torch.zeros((Q, fmax * 5), dtype=torch.float64).pin_memory()
     cnt_host = torch.zeros(Q, dtype=torch.int32).pin_memory()
 
+    # all ranks upload their queries at the same time: what the host gives each GPU when all of them pull
+    h2d_gbs = None
+    if world > 1:
+        tmp_q = torch.empty_like(dev_q)
+        tmp_q.copy_(host_q, non_blocking=True)
+        torch.cuda.synchronize()
+        dist.barrier()
+        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        c0.record()
+        for _ in range(3):
+            tmp_q.copy_(host_q, non_blocking=True)
+        c1.record()
+        torch.cuda.synchronize()
+        g = torch.tensor([3 * host_q.numel() / (c0.elapsed_time(c1) / 1e3) / 1e9], device=dev, dtype=torch.float64)
+        gl = [torch.zeros_like(g) for _ in range(world)]
+        dist.all_gather(gl, g)
+        h2d_gbs = [round(float(x.item()), 1) for x in gl]
+        del tmp_q
+
     stage_ms = {"upload_encode": 0.0, "preplace": 0.0, "select": 0.0, "thorough": 0.0, "collect": 0.0}
     pairs_total = [0]
 
@@ -711,6 +730,7 @@ def ours(args):
             "candidate_pairs_per_query": pairs / Q, "chunk": chunk, "resident_equals_e2e": same,
         }
         if world > 1:
+            out["host"] = {"h2d_gbs_per_rank_all_ranks_uploading": h2d_gbs}
             out["gather"] = ({"kind": "peer memory", "what": "rank 0 owns the records of all shards (CUDA IPC); every rank's collect kernel writes "
                               "its block straight into it over NVLink, one 4-byte all-reduce completes the step",
                               "equals_nccl_gather": peer_same} if peer is not None

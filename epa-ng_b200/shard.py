@@ -75,6 +75,35 @@ def gather_compact(records: torch.Tensor, counts: torch.Tensor, n_queries: int, 
     return [r[:n] for r, n in zip(rec_list, sizes)], torch.cat(cnt_list)[:n_queries]
 
 
+def gather_compact_fixed(records: torch.Tensor, counts: torch.Tensor, cap: int, dst: int = 0, fields: int = 5):
+    """gather_compact without a host synchronisation (the caller can queue the next step's kernels behind it): the
+    filled records are packed to the front of a [cap, fields] buffer by their counts' prefix sums (records beyond `cap`
+    land in a spill row and are dropped: the caller checks counts.sum() <= cap afterwards), then one gather of the
+    equal-sized buffers and one of the counts. On `dst` returns (records [world, cap, fields], counts [world, part]);
+    (None, None) elsewhere."""
+    world = dist.get_world_size() if dist.is_initialized() else 1
+    q = records.shape[0]
+    fmax = records.shape[1] // fields
+    c64 = counts.to(torch.int64)
+    first = torch.cumsum(c64, 0) - c64
+    slot = torch.arange(fmax, device=records.device)[None, :]
+    dest = torch.where(slot < c64[:, None], first[:, None] + slot, cap)          # unfilled slots -> spill row
+    dest = torch.clamp(dest, max=cap).reshape(-1)
+    comp = torch.zeros((cap + 1, fields), dtype=records.dtype, device=records.device)
+    comp.index_copy_(0, dest, records.view(q * fmax, fields))
+    comp = comp[:cap]
+    if world == 1:
+        return comp[None], counts[None]
+    rank = dist.get_rank()
+    rec_list = [torch.empty_like(comp) for _ in range(world)] if rank == dst else None
+    cnt_list = [torch.empty_like(counts) for _ in range(world)] if rank == dst else None
+    dist.gather(comp.contiguous(), rec_list, dst=dst)
+    dist.gather(counts, cnt_list, dst=dst)
+    if rank != dst:
+        return None, None
+    return torch.stack(rec_list), torch.stack(cnt_list)
+
+
 def expand_compact(parts, counts: torch.Tensor, filter_max: int, fields: int = 5):
     """Inverse of the compaction on the receiving side: fixed-stride [Q, filter_max * fields] rows in global query order."""
     comp = torch.cat(parts) if len(parts) > 1 else parts[0]

@@ -73,3 +73,20 @@ def test_shard_range_matches_reference_partition():
             assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
             part = -(-q // w)
             assert all(hi - lo <= part for lo, hi in spans)
+
+
+def test_fixed_capacity_compaction_matches_masked_compaction():
+    """gather_compact_fixed (no host synchronisation) packs the same records in the same order as compact_records"""
+    shard = helpers.pkg().shard
+    g = torch.Generator().manual_seed(5)
+    q, fmax = 257, 7
+    counts = torch.randint(0, fmax + 1, (q,), generator=g, dtype=torch.int32)
+    rec = torch.rand((q, fmax * 5), generator=g, dtype=torch.float64)
+    want = shard.compact_records(rec, counts)
+    cap = int(counts.sum()) + 11
+    got, cnt = shard.gather_compact_fixed(rec, counts, cap)
+    assert got.shape == (1, cap, 5) and torch.equal(cnt[0], counts)
+    assert torch.equal(got[0][: want.shape[0]], want) and not got[0][want.shape[0]:].any()
+    # too small a capacity drops the tail instead of writing out of bounds
+    got2, _ = shard.gather_compact_fixed(rec, counts, want.shape[0] - 5)
+    assert torch.equal(got2[0], want[: want.shape[0] - 5])
