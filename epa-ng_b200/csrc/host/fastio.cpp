@@ -5,6 +5,10 @@
 #include <sys/stat.h>
 #include <unistd.h>
 
+#if defined(__SSE2__)
+#include <emmintrin.h>
+#endif
+
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
@@ -56,6 +60,18 @@ const Tables kT;
 
 const char kBfastMagic[7] = {'B', 'F', 'A', 'S', 'T', '\0', '\0'};
 const char kNtMap[17] = "-TGKCYSBAWRDMHVN";       // src/util/maps.hpp:9-14
+struct NibblePairs {
+  uint16_t t[256];                                  // the two characters of a packed byte, in memory order
+  NibblePairs()
+  {
+    for (int b = 0; b < 256; ++b)
+    {
+      const unsigned char two[2] = {(unsigned char) kNtMap[b >> 4], (unsigned char) kNtMap[b & 15]};
+      std::memcpy(&t[b], two, 2);
+    }
+  }
+};
+const NibblePairs kPairs;
 
 // runs fn(t) on `threads` threads and rethrows the first exception
 template <class F>
@@ -72,6 +88,39 @@ void parallel(int threads, F && fn)
 }
 
 std::string record_name(const QueryRecord & r) { return std::string(r.name, r.name_len); }
+
+// number of white-space bytes (the six of kT.space: 9..13 and 32) in [p, e): eight bytes per step with exact
+// per-byte flags - no carries between bytes: for b < 0x80, (b & 0x7f) + K sets bit 7 iff b >= 0x80 - K
+size_t count_space(const char * p, const char * e)
+{
+  size_t n = 0;
+#if defined(__SSE2__)
+  {
+    const __m128i c9 = _mm_set1_epi8(9), c13 = _mm_set1_epi8(13), c32 = _mm_set1_epi8(32);
+    for (; p + 16 <= e; p += 16)
+    {
+      const __m128i c = _mm_loadu_si128(reinterpret_cast<const __m128i *>(p));
+      const __m128i in = _mm_and_si128(_mm_cmpeq_epi8(_mm_max_epu8(c, c9), c), _mm_cmpeq_epi8(_mm_min_epu8(c, c13), c));
+      n += (size_t) __builtin_popcount((unsigned) _mm_movemask_epi8(_mm_or_si128(in, _mm_cmpeq_epi8(c, c32))));
+    }
+  }
+#endif
+  const uint64_t L7 = 0x7f7f7f7f7f7f7f7full, H = 0x8080808080808080ull;
+  for (; p + 8 <= e; p += 8)
+  {
+    uint64_t x;
+    std::memcpy(&x, p, 8);
+    const uint64_t lo = x & L7;
+    const uint64_t ge9 = (lo + 0x7777777777777777ull);            // bit 7: low 7 bits >= 9
+    const uint64_t ge14 = (lo + 0x7272727272727272ull);           // bit 7: low 7 bits >= 14
+    const uint64_t y = lo ^ 0x2020202020202020ull;                // zero where the low 7 bits are 0x20
+    const uint64_t eq32 = ~(y + L7);                              // bit 7 set where y == 0 (y <= 0x7f: no carry out)
+    const uint64_t ws = ((ge9 & ~ge14) | eq32) & ~x & H;          // ... and the byte itself is below 0x80
+    n += (size_t) __builtin_popcountll(ws);
+  }
+  for (; p < e; ++p) n += kT.space[(unsigned char) *p] ? 1 : 0;
+  return n;
+}
 
 void index_fasta(const MappedFile & file, const std::string & path, int threads, bool want_mask, QueryIndex & idx)
 {
@@ -164,9 +213,7 @@ void index_fasta(const MappedFile & file, const std::string & path, int threads,
         }
       }
       else
-      {
-        for (const char * p = r.seq; p < r.seq_end; ++p) k += kT.space[(unsigned char) *p] ? 0 : 1;
-      }
+        k = (size_t) (r.seq_end - r.seq) - count_space(r.seq, r.seq_end);
       if (k != sites)
         throw std::runtime_error(path + " does not contain equal size sequences! First offending sequence: " + record_name(r));
     }
@@ -179,7 +226,7 @@ void index_fasta(const MappedFile & file, const std::string & path, int threads,
         for (size_t s = 0; s < sites; ++s) idx.gap_mask[s] &= m[s];
 }
 
-void index_bfast(const MappedFile & file, const std::string & path, QueryIndex & idx)
+void index_bfast(const MappedFile & file, const std::string & path, int threads, QueryIndex & idx)
 {
   const char * d = file.data();
   const size_t n = file.size();
@@ -192,24 +239,53 @@ void index_bfast(const MappedFile & file, const std::string & path, QueryIndex &
   idx.gap_mask.resize(mask_len);
   for (uint64_t i = 0; i < mask_len; ++i) idx.gap_mask[i] = d[pos + i] == '1';     // Binary_Fasta.hpp:60-66
   pos += mask_len;
-  need(n_seq * 16); pos += n_seq * 16;             // random-access table: entries are read in file order
+  if (n_seq > (n - pos) / 16) throw std::runtime_error(path + ": truncated bfast file");
+  const char * table = d + pos;                    // random-access table: (sequence id, byte offset) per entry, :53-64
+  pos += n_seq * 16;
   idx.records.resize(n_seq);
-  for (uint64_t i = 0; i < n_seq; ++i)
+  if (n_seq == 0) throw std::runtime_error(path + ": no sequences");
+  // Entries lie back to back in table order; every thread parses a range of them from the table's offsets (the
+  // pages of the map are then touched by all threads), and every entry must end where the next one starts.
+  auto parse = [&](uint64_t i, size_t at, size_t & end)
   {
+    auto rd = [&](size_t where) { if (where + 8 > n) throw std::runtime_error(path + ": truncated bfast file"); uint64_t v; std::memcpy(&v, d + where, 8); return v; };
     QueryRecord & r = idx.records[i];
-    const uint64_t label_len = u64();
-    need(label_len);
-    r.name = d + pos; r.name_len = (uint32_t) label_len;
-    pos += label_len;
-    const uint64_t n_chars = u64();
-    if (i == 0) idx.sites = n_chars;
-    else if (n_chars != idx.sites)
-      throw std::runtime_error(path + " does not contain equal size sequences! First offending sequence: " + record_name(r));
+    const uint64_t label_len = rd(at);
+    if (label_len > n - (at + 8)) throw std::runtime_error(path + ": truncated bfast file");
+    r.name = d + at + 8; r.name_len = (uint32_t) label_len;
+    const size_t cat = at + 8 + (size_t) label_len;
+    const uint64_t n_chars = rd(cat);
     const size_t packed = (size_t) ((n_chars + 1) / 2);
-    need(packed);
-    r.seq = d + pos; r.seq_end = d + pos + packed;
-    pos += packed;
+    if (packed > n - (cat + 8)) throw std::runtime_error(path + ": truncated bfast file");
+    r.seq = d + cat + 8; r.seq_end = r.seq + packed;
+    // (the width travels in seq_end - seq; odd and even widths are told apart by the first record's count)
+    end = cat + 8 + packed;
+    return n_chars;
+  };
+  size_t end0 = 0;
+  {
+    uint64_t off0; std::memcpy(&off0, table + 8, 8);
+    if (off0 != pos) throw std::runtime_error(path + ": corrupt bfast offset table");
+    idx.sites = parse(0, (size_t) off0, end0);
   }
+  const uint64_t sites = idx.sites;
+  parallel(threads, [&](int t)
+  {
+    const uint64_t lo = std::max<uint64_t>(1, n_seq * (uint64_t) t / (uint64_t) threads), hi = n_seq * (uint64_t) (t + 1) / (uint64_t) threads;
+    for (uint64_t i = lo; i < hi; ++i)
+    {
+      uint64_t off; std::memcpy(&off, table + i * 16 + 8, 8);
+      if (off >= n) throw std::runtime_error(path + ": truncated bfast file");
+      size_t end;
+      const uint64_t n_chars = parse(i, (size_t) off, end);
+      if (n_chars != sites)
+        throw std::runtime_error(path + " does not contain equal size sequences! First offending sequence: " + record_name(idx.records[i]));
+    }
+  });
+  // back to back: every entry starts where the previous one ends
+  for (uint64_t i = 1; i < n_seq; ++i)
+    if (idx.records[i].name - 8 != idx.records[i - 1].seq_end) throw std::runtime_error(path + ": corrupt bfast offset table");
+  (void) end0;
   if (idx.records.empty()) throw std::runtime_error(path + ": no sequences");
   if (idx.gap_mask.size() != idx.sites) idx.gap_mask.assign(idx.sites, 0);
 }
@@ -222,7 +298,7 @@ QueryIndex index_queries(const MappedFile & file, const std::string & path, int 
   idx.bfast = file.size() >= sizeof kBfastMagic && std::memcmp(file.data(), kBfastMagic, sizeof kBfastMagic) == 0;
   if (idx.bfast)
   {
-    index_bfast(file, path, idx);
+    index_bfast(file, path, threads, idx);
     if (!want_mask) std::fill(idx.gap_mask.begin(), idx.gap_mask.end(), (uint8_t) 0);
   }
   else
@@ -248,7 +324,7 @@ void decode_rows(const QueryIndex & idx, size_t first, size_t count, const std::
       {
         const unsigned char * p = reinterpret_cast<const unsigned char *>(r.seq);
         size_t k = 0;
-        for (; k + 1 < sites; k += 2, ++p) { dst[k] = (uint8_t) kNtMap[*p >> 4]; dst[k + 1] = (uint8_t) kNtMap[*p & 15]; }
+        for (; k + 1 < sites; k += 2, ++p) std::memcpy(dst + k, &kPairs.t[*p], 2);      // two characters per packed byte
         if (k < sites) dst[k] = (uint8_t) kNtMap[*p >> 4];
       }
       else
@@ -261,7 +337,22 @@ void decode_rows(const QueryIndex & idx, size_t first, size_t count, const std::
         {
           const unsigned char * src = reinterpret_cast<const unsigned char *>(r.seq);
           unsigned char odd = 0;
-          for (size_t i = 0; i < sites; ++i)
+          size_t i = 0;
+#if defined(__SSE2__)
+          {
+            const __m128i sp = _mm_set1_epi8(' '), ca = _mm_set1_epi8('a'), cz = _mm_set1_epi8('z'), d32 = _mm_set1_epi8(32);
+            __m128i oddv = _mm_setzero_si128();
+            for (; i + 16 <= sites; i += 16)
+            {
+              const __m128i c = _mm_loadu_si128(reinterpret_cast<const __m128i *>(src + i));
+              oddv = _mm_or_si128(oddv, _mm_cmpeq_epi8(_mm_min_epu8(c, sp), c));                     // c <= ' '
+              const __m128i low = _mm_and_si128(_mm_cmpeq_epi8(_mm_max_epu8(c, ca), c), _mm_cmpeq_epi8(_mm_min_epu8(c, cz), c));
+              _mm_storeu_si128(reinterpret_cast<__m128i *>(dst + i), _mm_sub_epi8(c, _mm_and_si128(low, d32)));
+            }
+            odd = _mm_movemask_epi8(oddv) ? 1 : 0;
+          }
+#endif
+          for (; i < sites; ++i)
           {
             const unsigned char c = src[i];
             odd |= (unsigned char) (c <= ' ');
@@ -354,6 +445,56 @@ size_t format_fixed(char * out, double x, int precision)
     p += precision;
   }
   return (size_t) (p - out);
+}
+
+void json_escape(std::string & out, const char * s, size_t n)
+{
+  // the common case has nothing to escape: one scan, one append
+  size_t i = 0;
+  for (; i < n; ++i)
+  {
+    const unsigned char c = (unsigned char) s[i];
+    if (c == '"' || c == '\\' || c < 0x20) break;
+  }
+  out.append(s, i);
+  for (; i < n; ++i)
+  {
+    const unsigned char c = (unsigned char) s[i];
+    if (c == '"' || c == '\\') { out += '\\'; out += (char) c; }
+    else if (c < 0x20)
+    {
+      char buf[8];
+      std::snprintf(buf, sizeof buf, "\\u%04x", c);
+      out += buf;
+    }
+    else out += (char) c;
+  }
+}
+
+void append_pquery(std::string & out, const char * name, size_t name_len, const PlacementFields * p, uint32_t count,
+                   int precision, bool last)
+{
+  char buf[2048];
+  out += "    {\"p\": [\n";
+  for (uint32_t k = 0; k < count; ++k)
+  {
+    char * w = buf;
+    std::memcpy(w, "      [", 7); w += 7;
+    w += put_u64(w, p[k].branch_id);
+    *w++ = ','; *w++ = ' ';
+    w += format_fixed(w, p[k].likelihood, precision); *w++ = ','; *w++ = ' ';
+    w += format_fixed(w, p[k].lwr, precision); *w++ = ','; *w++ = ' ';
+    w += format_fixed(w, p[k].distal_length, precision); *w++ = ','; *w++ = ' ';
+    w += format_fixed(w, p[k].pendant_length, precision);
+    *w++ = ']';
+    if (k + 1 < count) *w++ = ',';
+    *w++ = '\n';
+    out.append(buf, (size_t) (w - buf));
+  }
+  out += "      ],\n    \"n\": [\"";
+  json_escape(out, name, name_len);
+  out += "\"]\n    }";
+  out += last ? "\n" : ",\n";
 }
 
 }  // namespace epa_host

@@ -58,4 +58,14 @@ void decode_rows(const QueryIndex & idx, size_t first, size_t count, const std::
 // Returns the number of characters written (no terminator); `out` must hold 48 + precision bytes.
 size_t format_fixed(char * out, double x, int precision);
 
+// JSON string contents: '"', '\\' and control characters escaped
+void json_escape(std::string & out, const char * s, size_t n);
+
+// One placement record as the caller's 40-byte struct lays it out (epa_placement, include/epa_b200.h)
+struct PlacementFields { uint64_t branch_id; double likelihood, lwr, pendant_length, distal_length; };
+
+// appends the jplace text of one pquery (src/io/jplace_util.cpp:20-64: field order edge, logl, lwr, DISTAL, PENDANT)
+void append_pquery(std::string & out, const char * name, size_t name_len, const PlacementFields * p, uint32_t count,
+                   int precision, bool last);
+
 }  // namespace epa_host

@@ -47,7 +47,6 @@ using namespace epa_host;
 
 namespace epa_host {
 int host_fail_msg(int code, const std::string & msg);      // session.cpp
-void json_escape(std::string & out, const char * s, size_t n);
 }
 
 namespace {
@@ -96,32 +95,6 @@ struct Slot {
   size_t first = 0, count = 0;
   size_t index = 0;                    // chunk number
 };
-
-// appends the jplace text of one pquery (src/io/jplace_util.cpp:20-64)
-void append_pquery(std::string & out, const QueryRecord & rec, const epa_placement * p, uint32_t count, int precision, bool last)
-{
-  char buf[2048];
-  out += "    {\"p\": [\n";
-  for (uint32_t k = 0; k < count; ++k)
-  {
-    char * w = buf;
-    std::memcpy(w, "      [", 7); w += 7;
-    w += std::snprintf(w, 24, "%llu", (unsigned long long) p[k].branch_id);
-    *w++ = ','; *w++ = ' ';
-    w += format_fixed(w, p[k].likelihood, precision); *w++ = ','; *w++ = ' ';
-    w += format_fixed(w, p[k].lwr, precision); *w++ = ','; *w++ = ' ';
-    w += format_fixed(w, p[k].distal_length, precision); *w++ = ','; *w++ = ' ';
-    w += format_fixed(w, p[k].pendant_length, precision);
-    *w++ = ']';
-    if (k + 1 < count) *w++ = ',';
-    *w++ = '\n';
-    out.append(buf, (size_t) (w - buf));
-  }
-  out += "      ],\n    \"n\": [\"";
-  json_escape(out, rec.name, rec.name_len);
-  out += "\"]\n    }";
-  out += last ? "\n" : ",\n";
-}
 
 }  // namespace
 
@@ -471,7 +444,8 @@ extern "C" int epa_run_files_multi(const char * tree_file, const char * ref_msa_
             const size_t lo = sl->count * (size_t) t / (size_t) nt, hi = sl->count * (size_t) (t + 1) / (size_t) nt;
             out.reserve((hi - lo) * 160);
             for (size_t q = lo; q < hi; ++q)
-              append_pquery(out, qidx.records[sl->first + q], sl->recs + q * fmax, sl->counts[q], precision, sl->first + q + 1 == Q);
+              append_pquery(out, qidx.records[sl->first + q].name, qidx.records[sl->first + q].name_len,
+                            reinterpret_cast<const PlacementFields *>(sl->recs + q * fmax), sl->counts[q], precision, sl->first + q + 1 == Q);
           });
         for (auto & t : th) t.join();
         for (int t = 0; t < nt; ++t) std::fwrite(parts[(size_t) t].data(), 1, parts[(size_t) t].size(), fh);

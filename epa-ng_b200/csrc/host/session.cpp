@@ -37,23 +37,6 @@ constexpr uint32_t kDefaultChunk = 131072;
 
 namespace epa_host {
 int host_fail_msg(int code, const std::string & msg) { return host_fail(code, msg); }
-
-// JSON string escaping for names, the tree and the invocation line of the jplace
-void json_escape(std::string & out, const char * s, size_t n)
-{
-  for (size_t i = 0; i < n; ++i)
-  {
-    const unsigned char c = (unsigned char) s[i];
-    if (c == '"' || c == '\\') { out += '\\'; out += (char) c; }
-    else if (c < 0x20)
-    {
-      char buf[8];
-      std::snprintf(buf, sizeof buf, "\\u%04x", c);
-      out += buf;
-    }
-    else out += (char) c;
-  }
-}
 }  // namespace epa_host
 
 extern "C" const char * epa_host_last_error(void) { return g_host_error.c_str(); }
@@ -269,28 +252,11 @@ extern "C" int epa_session_is_rooted(const epa_session * s) { return s && s->tre
 // ----------------------------------------------------------------------------------------------
 //  jplace
 // ----------------------------------------------------------------------------------------------
-static void append_number(std::string & out, double v, int precision)
-{
-  char buf[400];
-  out.append(buf, format_fixed(buf, v, precision));
-}
-
 static void write_pquery(FILE * fh, const char * name, const epa_placement * recs, uint32_t count, int precision, bool last)
 {
-  std::string out = "    {\"p\": [\n";
-  for (uint32_t k = 0; k < count; ++k)
-  {
-    const epa_placement & p = recs[k];
-    out += "      [" + std::to_string((unsigned long long) p.branch_id) + ", ";
-    append_number(out, p.likelihood, precision); out += ", ";
-    append_number(out, p.lwr, precision); out += ", ";
-    append_number(out, p.distal_length, precision); out += ", ";
-    append_number(out, p.pendant_length, precision);
-    out += k + 1 < count ? "],\n" : "]\n";
-  }
-  out += "      ],\n    \"n\": [\"";
-  json_escape(out, name, std::strlen(name));
-  out += last ? "\"]\n    }\n" : "\"]\n    },\n";
+  static_assert(sizeof(epa_host::PlacementFields) == sizeof(epa_placement), "record layout");
+  std::string out;
+  epa_host::append_pquery(out, name, std::strlen(name), reinterpret_cast<const epa_host::PlacementFields *>(recs), count, precision, last);
   std::fwrite(out.data(), 1, out.size(), fh);
 }
 

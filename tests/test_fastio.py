@@ -87,3 +87,29 @@ def test_parallel_reader_errors(built, tmp_path):
         built.session.read_alignment_mt(p, 2)
     with pytest.raises(built.capi.EpaError, match="Cannot open"):
         built.session.read_alignment_mt(str(tmp_path / "missing.fasta"), 2)
+
+
+def test_bfast_index_is_parallel_and_checks_the_offset_table(built, tmp_path):
+    """The bfast records are parsed by all threads from the file's random-access table (Binary_Fasta.hpp:53-64): the same
+    rows for any thread count, odd widths included; a table that does not match the entries, or a cut file, is an error."""
+    rng = np.random.default_rng(11)
+    for sites in (33, 64):
+        dna = np.frombuffer(b"-TGKCYSBAWRDMHVN", dtype=np.uint8)[rng.integers(0, 16, size=(301, sites))]
+        fa = str(tmp_path / ("w%d.fasta" % sites))
+        _write(fa, "".join(">name_%d_%s\n%s\n" % (i, "x" * (i % 9), dna[i].tobytes().decode()) for i in range(301)))
+        bf = built.session.fasta_to_bfast(fa, str(tmp_path))
+        for threads in (1, 2, 7):
+            names, rows, _ = built.session.read_alignment_mt(bf, threads)
+            assert names == ["name_%d_%s" % (i, "x" * (i % 9)) for i in range(301)] and np.array_equal(rows, dna)
+    raw = bytearray(open(bf, "rb").read())
+    table = 7 + 8 + 8 + 64                                  # magic, count, mask length, mask
+    bad = bytearray(raw)
+    bad[table + 16 * 5 + 8] ^= 0x04                         # offset of entry 5
+    p_bad = str(tmp_path / "bad.bfast")
+    open(p_bad, "wb").write(bad)
+    with pytest.raises(built.capi.EpaError, match="offset table|truncated|equal size"):
+        built.session.read_alignment_mt(p_bad, 3)
+    p_cut = str(tmp_path / "cut.bfast")
+    open(p_cut, "wb").write(raw[: len(raw) - 40])
+    with pytest.raises(built.capi.EpaError, match="truncated"):
+        built.session.read_alignment_mt(p_cut, 3)
