@@ -84,7 +84,17 @@ extern "C" int epa_host_set_rate_scalers(int mode, int bugcompat)
 extern "C" int epa_session_open(epa_session ** out, const char * newick, uint32_t n_taxa, const char * const * names,
                                 const char * ref_rows, uint32_t sites, const char * model_desc, int device)
 {
+  return epa_session_open_ex(out, newick, n_taxa, names, ref_rows, sites, model_desc, device, -1, -1);
+}
+
+extern "C" int epa_session_open_ex(epa_session ** out, const char * newick, uint32_t n_taxa, const char * const * names,
+                                   const char * ref_rows, uint32_t sites, const char * model_desc, int device,
+                                   int rate_scalers, int bugcompat_focus)
+{
   if (!out || !newick || !names || !ref_rows || !model_desc) return host_fail(EPA_ERR_ARG, "null argument");
+  if (rate_scalers < -1 || rate_scalers > 2) return host_fail(EPA_ERR_ARG, "rate scaler mode must be 0 (off), 1 (on), 2 (auto) or -1 (process policy)");
+  const int rate_mode = rate_scalers < 0 ? g_rate_scalers : rate_scalers;
+  const int rate_bug = bugcompat_focus < 0 ? g_rate_bugcompat : (bugcompat_focus ? 1 : 0);
   *out = nullptr;
   try
   {
@@ -119,8 +129,8 @@ extern "C" int epa_session_open(epa_session ** out, const char * newick, uint32_
     md.sites = sites;
     md.flags = 0;
     {
-      const bool want = g_rate_scalers == 1 || (g_rate_scalers == 2 && T > 2000);
-      if (want) md.flags |= EPA_FLAG_RATE_SCALERS | (g_rate_bugcompat ? EPA_FLAG_BUGCOMPAT_FOCUS : 0u);
+      const bool want = rate_mode == 1 || (rate_mode == 2 && T > 2000);
+      if (want) md.flags |= EPA_FLAG_RATE_SCALERS | (rate_bug ? EPA_FLAG_BUGCOMPAT_FOCUS : 0u);
     }
     md.eigenvals = s->model.eigenvals.data();
     md.eigenvecs = s->model.eigenvecs.data();

@@ -12,6 +12,8 @@ _vp, _u32p = C.c_void_p, C.POINTER(C.c_uint32)
 HOST_SYMBOLS = [
     ("epa_session_open", C.c_int, [C.POINTER(_vp), C.c_char_p, C.c_uint32, C.POINTER(C.c_char_p), _vp, C.c_uint32,
                                    C.c_char_p, C.c_int]),
+    ("epa_session_open_ex", C.c_int, [C.POINTER(_vp), C.c_char_p, C.c_uint32, C.POINTER(C.c_char_p), _vp, C.c_uint32,
+                                   C.c_char_p, C.c_int, C.c_int, C.c_int]),
     ("epa_session_place", C.c_int, [_vp, _vp, C.c_uint64, C.POINTER(capi.Options), C.c_uint32, _vp, _vp]),
     ("epa_host_set_rate_scalers", C.c_int, [C.c_int, C.c_int]),
     ("epa_host_read_alignment", C.c_int, [C.c_char_p, _u32p, _u32p, _vp, C.c_size_t, C.c_char_p, C.c_size_t]),
@@ -90,12 +92,12 @@ class Session:
         if not states or not rate_cats:
             pm = parse_model(model)                 # shapes of the staged inspection helpers (get_clv, ...)
             states, rate_cats = pm["states"], pm["rate_cats"]
-        _check(L.epa_host_set_rate_scalers({"off": 0, "on": 1, "auto": 2}[rate_scalers], int(bugcompat_focus)))
         ref_rows = np.ascontiguousarray(ref_rows, dtype=np.uint8)
         arr = (C.c_char_p * len(names))(*[n.encode() for n in names])
         self.handle = _vp()
-        _check(L.epa_session_open(C.byref(self.handle), newick.encode(), len(names), arr, ref_rows.ctypes.data,
-                                  ref_rows.shape[1], model.encode(), device))
+        _check(L.epa_session_open_ex(C.byref(self.handle), newick.encode(), len(names), arr, ref_rows.ctypes.data,
+                                     ref_rows.shape[1], model.encode(), device,
+                                     {"off": 0, "on": 1, "auto": 2}[rate_scalers], int(bugcompat_focus)))
         self.sites = int(L.epa_session_sites(self.handle))
         self.n_edges = int(L.epa_session_num_edges(self.handle))
         self.n_tips = int(L.epa_session_num_tips(self.handle))

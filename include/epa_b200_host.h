@@ -32,6 +32,13 @@ int epa_session_open(epa_session ** session, const char * newick, uint32_t n_tax
                      const char * const * names, const char * ref_rows, uint32_t sites,
                      const char * model, int device);
 
+/* The same with the per-rate scaler policy of THIS session (the reference's --rate-scalers): rate_scalers 0 = off,
+ * 1 = on, 2 = auto (on above 2000 tips), -1 = the process-wide policy of epa_host_set_rate_scalers; bugcompat_focus
+ * 1 / 0 / -1 likewise (the reference's scaler window offset of the thorough phase). */
+int epa_session_open_ex(epa_session ** session, const char * newick, uint32_t n_taxa,
+                        const char * const * names, const char * ref_rows, uint32_t sites,
+                        const char * model, int device, int rate_scalers, int bugcompat_focus);
+
 /* Places n_queries rows (query_rows[n_queries][sites], ASCII, HOST memory; pinned memory gives
  * full PCIe speed) in chunks of chunk_size queries (0 = default): the reference's chunk loop.
  * out[n_queries][opts->filter_max], counts[n_queries] as in epa_place_chunk. */
