@@ -38,6 +38,12 @@
 #include <thread>
 #include <vector>
 
+#include <fcntl.h>
+#include <unistd.h>
+
+#include <atomic>
+#include <cerrno>
+
 #include "fastio.hpp"
 #include "model.hpp"
 #include "seqio.hpp"
@@ -279,15 +285,33 @@ extern "C" int epa_run_files_multi(const char * tree_file, const char * ref_msa_
     const double t_setup = since(t0);
 
     const std::string jpath = dir + "epa_result.jplace";
-    FILE * fh = std::fopen(jpath.c_str(), "w");
-    if (!fh) return host_fail_msg(EPA_ERR_ARG, "cannot open " + jpath);
+    // the jplace goes out through positioned writes: the formatting threads of a chunk write their own parts side by
+    // side (a single writer copying 156 MB per 10^6 queries into the page cache was the slowest host stage)
+    struct Fd {
+      int fd = -1;
+      ~Fd() { if (fd >= 0) ::close(fd); }
+    } fh;
+    fh.fd = ::open(jpath.c_str(), O_WRONLY | O_CREAT | O_TRUNC, 0644);
+    if (fh.fd < 0) return host_fail_msg(EPA_ERR_ARG, "cannot open " + jpath);
+    uint64_t file_off = 0;
+    std::atomic<bool> write_failed{false};
+    auto write_at = [&](const char * data, size_t n, uint64_t at)
+    {
+      while (n)
+      {
+        const ssize_t k = ::pwrite(fh.fd, data, n, (off_t) at);
+        if (k <= 0) { if (k < 0 && errno == EINTR) continue; write_failed = true; return; }
+        data += k; n -= (size_t) k; at += (uint64_t) k;
+      }
+    };
     info("Output file: " + jpath);
     {
       std::string head = "{\n  \"tree\": \"";
       const char * nw = epa_session_numbered_newick(s0, precision);
       json_escape(head, nw, std::strlen(nw));
       head += "\",\n  \"placements\": \n  [\n";
-      std::fwrite(head.data(), 1, head.size(), fh);
+      write_at(head.data(), head.size(), file_off);
+      file_off += head.size();
     }
 
     const uint64_t Q = qidx.records.size();
@@ -436,19 +460,36 @@ extern "C" int epa_run_files_multi(const char * tree_file, const char * ref_msa_
         const auto ta = std::chrono::steady_clock::now();
         const int nt = (int) std::max<size_t>(1, std::min<size_t>((size_t) side_threads, sl->count / 1024 + 1));
         std::vector<std::thread> th;
+        std::vector<std::atomic<uint64_t>> sizes((size_t) nt);
+        for (auto & z : sizes) z.store(UINT64_MAX, std::memory_order_relaxed);
         for (int t = 0; t < nt; ++t)
           th.emplace_back([&, t]()
           {
             std::string & out = parts[(size_t) t];
             out.clear();
             const size_t lo = sl->count * (size_t) t / (size_t) nt, hi = sl->count * (size_t) (t + 1) / (size_t) nt;
-            out.reserve((hi - lo) * 160);
-            for (size_t q = lo; q < hi; ++q)
-              append_pquery(out, qidx.records[sl->first + q].name, qidx.records[sl->first + q].name_len,
-                            reinterpret_cast<const PlacementFields *>(sl->recs + q * fmax), sl->counts[q], precision, sl->first + q + 1 == Q);
+            try
+            {
+              out.reserve((hi - lo) * 160);
+              for (size_t q = lo; q < hi; ++q)
+                append_pquery(out, qidx.records[sl->first + q].name, qidx.records[sl->first + q].name_len,
+                              reinterpret_cast<const PlacementFields *>(sl->recs + q * fmax), sl->counts[q], precision, sl->first + q + 1 == Q);
+            }
+            catch (...) { out.clear(); write_failed = true; }       // (the other threads wait for this part's size)
+            // this part starts where the parts before it end: their sizes are published as they finish
+            sizes[(size_t) t].store(out.size(), std::memory_order_release);
+            uint64_t at = file_off;
+            for (int u = 0; u < t; ++u)
+            {
+              uint64_t z;
+              while ((z = sizes[(size_t) u].load(std::memory_order_acquire)) == UINT64_MAX) std::this_thread::yield();
+              at += z;
+            }
+            write_at(out.data(), out.size(), at);
           });
         for (auto & t : th) t.join();
-        for (int t = 0; t < nt; ++t) std::fwrite(parts[(size_t) t].data(), 1, parts[(size_t) t].size(), fh);
+        for (int t = 0; t < nt; ++t) file_off += parts[(size_t) t].size();
+        if (write_failed) set_error(EPA_ERR_ARG, "cannot write " + jpath);
         busy_write += since(ta);
         if (debug) std::fprintf(stderr, "[pipe] wrote chunk %zu: %.1f ms (at %.3f s)\n", c, since(ta) * 1e3, since(t0));
         info(std::to_string(sl->first + sl->count) + " Sequences done!");
@@ -463,17 +504,16 @@ extern "C" int epa_run_files_multi(const char * tree_file, const char * ref_msa_
     for (auto & w : workers) w.join();
     if (allocator.joinable()) allocator.join();
     if (failed())
-    {
-      std::fclose(fh);
       return host_fail_msg(rc_all, err_all);
-    }
     {
       std::string tail = "  ],\n  \"metadata\": {\"invocation\": \"";
       if (invocation) json_escape(tail, invocation, std::strlen(invocation));
       tail += "\"},\n  \"version\": 3,\n  \"fields\": [\"edge_num\", \"likelihood\", \"like_weight_ratio\", \"distal_length\", \"pendant_length\"]\n}\n";
-      std::fwrite(tail.data(), 1, tail.size(), fh);
+      write_at(tail.data(), tail.size(), file_off);
+      file_off += tail.size();
     }
-    std::fclose(fh);
+    if (write_failed || ::close(fh.fd) != 0) { fh.fd = -1; return host_fail_msg(EPA_ERR_ARG, "cannot write " + jpath); }
+    fh.fd = -1;
     const double t_place = since(t1), t_total = since(t0);
     char buf[160];
     std::snprintf(buf, sizeof buf, "Time spent placing: %.3fs", t_place);
