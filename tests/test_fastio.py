@@ -113,3 +113,31 @@ def test_bfast_index_is_parallel_and_checks_the_offset_table(built, tmp_path):
     open(p_cut, "wb").write(raw[: len(raw) - 40])
     with pytest.raises(built.capi.EpaError, match="truncated"):
         built.session.read_alignment_mt(p_cut, 3)
+
+
+def test_white_space_inside_sequence_lines(built, tmp_path):
+    """Blanks and tabs inside sequence lines, lower case and lines of every length around the 16-byte steps of the
+    vectorised paths: the parallel reader (white-space count, upper-casing copy) equals the serial one."""
+    rng = np.random.default_rng(9)
+    n, sites = 211, 131
+    alphabet = np.frombuffer(b"ACGTacgtNn-RYKM", dtype=np.uint8)
+    rows = alphabet[rng.integers(0, len(alphabet), size=(n, sites))]
+    parts = []
+    for i in range(n):
+        seq = rows[i].tobytes().decode()
+        parts.append(">s%d\n" % i)
+        if i % 3 == 0:
+            parts.append(seq + "\n")                                   # one plain line (fast path)
+        elif i % 3 == 1:
+            cut = 1 + (i % 40)
+            parts.append(seq[:cut] + " \t " + seq[cut:] + "  \n")     # blanks inside and at the end of the line
+        else:
+            w = 15 + (i % 5)                                           # 15..19 characters per line
+            parts.append("".join(seq[k:k + w] + "\n" for k in range(0, sites, w)))
+    path = str(tmp_path / "ws.fasta")
+    _write(path, "".join(parts))
+    names_s, rows_s = built.session.read_alignment(path)
+    assert np.array_equal(rows_s, np.char.upper(rows.view("S1")).view(np.uint8).reshape(n, sites))
+    for threads in (1, 4):
+        names_p, rows_p, _ = built.session.read_alignment_mt(path, threads)
+        assert names_p == names_s and np.array_equal(rows_p, rows_s)
