@@ -26,6 +26,9 @@ out["placements_no_heur"], _ = orc.run_reference(tf, sf, qf, ds["model"], os.pat
                                                  extra=("--rate-scalers", "on", "--no-heur"))
 out["placements_raxml_blo"], _ = orc.run_reference(tf, sf, qf, ds["model"], os.path.join(tmp, "ref3"), threads=4,
                                                    extra=("--rate-scalers", "on", "--raxml-blo"))
+out["model_pinv"] = "LG+G4{0.8}+IU{0.2}"
+out["placements_pinv"], _ = orc.run_reference(tf, sf, qf, out["model_pinv"], os.path.join(tmp, "ref4"), threads=4,
+                                              extra=("--rate-scalers", "on"))
 path = os.path.join(ROOT, "tests", "golden", "rate300", "reference_placements_aa_ladder.json")
 json.dump(out, open(path, "w"), indent=0)
 print("wrote", path, len(out["placements"]), len(out["placements_no_heur"]))

@@ -122,3 +122,15 @@ def test_oracle_amino_acids_per_rate_raxml_blo(built):
     for name, seq in zip(case.qnames, case.qseqs):
         got = [(p.edge, p.logl, p.lwr, p.distal, p.pendant) for p in case.placer.place(seq)]
         helpers.assert_placements_close(got, g["placements_raxml_blo"][name], name, logl_rel=1e-9, len_abs=1e-5)
+
+
+def test_oracle_amino_acids_per_rate_with_invariant_sites(built):
+    """+IU{0.2} on top: the invariant term joins sums built from CLVs that the generic tip-inner update rescaled as
+    whole sites (LP/core_derivatives.c:676-687, LP/core_likelihood.c:524-556)."""
+    g = json.load(open(os.path.join(helpers.GOLDEN, "rate300", "reference_placements_aa_ladder.json")))
+    ds = built.synth.dataset(**g["dataset"])
+    case = helpers.case_from_arrays(ds["newick"], ds["names"], ds["ref"], ds["qnames"], ds["queries"], g["model_pinv"],
+                                    per_rate=True, bugcompat=True, column_mask=True)
+    for name, seq in zip(case.qnames, case.qseqs):
+        got = [(p.edge, p.logl, p.lwr, p.distal, p.pendant) for p in case.placer.place(seq)]
+        helpers.assert_placements_close(got, g["placements_pinv"][name], name, logl_rel=1e-9, len_abs=1e-5)
